@@ -1,0 +1,823 @@
+// voxelis_oracle.hpp — CPU ORACLE (test infrastructure, NOT product code).
+//
+// A C++17 restatement of the batched SVO-DAG build path of WildPixelGames/voxelis
+// v25.4.0 (Rust).  It exists only to check the CUDA path in voxelis_b200/ and to be
+// timed as the CPU baseline by bench.py.  Only tests/, __graft_entry__.smoke() and
+// bench.py's cpu_baseline / --impl reference legs may load it.  The product path never
+// calls into this file and fails loudly when the CUDA library is missing.
+//
+// Every function cites the reference file:line it follows (paths relative to
+// /root/reference/voxelis/src unless stated).
+//
+// Parity status of the oracle itself:
+//   * The reference is Rust-only; this image has no cargo/rustc, so the reference cannot
+//     be run here and oracle/_ref does not exist ("reference unbuildable here").
+//   * The oracle is PINNED against every known-answer the reference's own test-suite
+//     holds for this path (tests/test_oracle_reference_tests.py ports
+//     spatial/voxtree.rs:1345-2185, core/block_id.rs:411,474-609,
+//     core/max_depth.rs:167-172) and cross-checked against an independent canonical
+//     builder (tests/canonical.py).
+//   * Hash VALUES are "parity unpinned": the reference hashes with rustc-hash 2.1.1
+//     FxHasher (Cargo.lock; call sites interner/hash.rs:42,57,70), which is not vendored
+//     under /root/reference and is pinned by no reference test.  Hashes never escape the
+//     interner and ids are compared up to permutation, so this does not affect results.
+//     fx_* below restates the published FxHasher algorithm for the stored `hashes` pool.
+//   * Deliberate deviation: the reference keys its pattern maps on the 64-bit hash only
+//     (interner/hash.rs:15-38; equality is only debug_assert'ed, interner/mod.rs:749-765).
+//     The oracle compares full keys, so it differs from the reference only where the
+//     reference would silently alias two different nodes on a 64-bit hash collision.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+#include <vector>
+
+namespace vxo {
+
+using u8 = uint8_t;
+using u16 = uint16_t;
+using u32 = uint32_t;
+using u64 = uint64_t;
+
+// ---------------------------------------------------------------------------------
+// BlockId — core/block_id.rs:18-30 (shifts), :94-130 (consts), :216-226 (packing),
+// :240-401 (accessors).
+// ---------------------------------------------------------------------------------
+constexpr u64 ID_INVALID = ~u64(0);      // block_id.rs:96
+constexpr u64 ID_EMPTY = 0;              // block_id.rs:112
+constexpr u16 MAX_GENERATION = 0x7FFE;   // block_id.rs:130
+constexpr int MAX_CHILDREN = 8;          // interner/consts.rs:6
+
+struct RefPanic : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+inline u64 id_pack(u32 index, u16 gen, u8 types, u8 mask, bool leaf) {
+    if (gen > MAX_GENERATION) throw RefPanic("Generation overflow");  // :217
+    return (u64(leaf) << 63) | (u64(types) << 55) | (u64(mask) << 47) |
+           ((u64(gen) & 0x7FFF) << 32) | u64(index);
+}
+inline u64 id_leaf(u32 index, u16 gen) { return id_pack(index, gen, 0, 0, true); }
+inline u64 id_branch(u32 index, u16 gen, u8 t, u8 m) { return id_pack(index, gen, t, m, false); }
+inline u32 id_index(u64 id) { return u32(id & 0xFFFFFFFFull); }
+inline u16 id_gen(u64 id) { return u16((id >> 32) & 0x7FFF); }
+inline bool id_is_leaf(u64 id) { return (id >> 63) == 1; }
+inline bool id_is_branch(u64 id) { return (id >> 63) == 0; }
+inline bool id_is_empty(u64 id) { return id == 0; }
+inline u8 id_types(u64 id) {
+    if (!id_is_branch(id)) throw RefPanic("Cannot get types from a leaf node");  // :273-276
+    return u8((id >> 55) & 0xFF);
+}
+inline u8 id_mask(u64 id) {
+    if (!id_is_branch(id)) throw RefPanic("Cannot get mask from a leaf node");  // :296-299
+    return u8((id >> 47) & 0xFF);
+}
+
+// ---------------------------------------------------------------------------------
+// Morton path — utils/common.rs:24-55.  x -> bit 3n, y -> 3n+1, z -> 3n+2, 10 bits/axis.
+// ---------------------------------------------------------------------------------
+inline u32 spread10(u32 v) {
+    v &= 0x3FF;
+    v = (v | (v << 16)) & 0x30000FF;
+    v = (v | (v << 8)) & 0x300F00F;
+    v = (v | (v << 4)) & 0x30C30C3;
+    v = (v | (v << 2)) & 0x9249249;
+    return v;
+}
+inline u32 encode_child_index_path(int x, int y, int z) {
+    return spread10(u32(x)) | (spread10(u32(y)) << 1) | (spread10(u32(z)) << 2);
+}
+
+// PATH_MASKS[max_depth][level] — spatial/voxtree.rs:41-105: the top (level+1) 3-bit
+// groups of a 3*max_depth-bit path.  The table stops at max_depth 6; the formula below
+// reproduces every tabulated row and extends it to max_depth 7 (extension).
+inline u32 path_mask(int max_depth, int level) {
+    if (level >= max_depth) return 0;
+    u32 ones = (u32(1) << (3 * (level + 1))) - 1;
+    return ones << (3 * (max_depth - level - 1));
+}
+
+// ---------------------------------------------------------------------------------
+// FxHasher (rustc-hash 2.1.1, published algorithm; parity unpinned, see header).
+// ---------------------------------------------------------------------------------
+struct Fx {
+    u64 h = 0;
+    static constexpr u64 K = 0xf1357aea2e62a9c5ull;
+    void add(u64 v) { h = (h + v) * K; }
+    u64 finish() const { return (h << 26) | (h >> 38); }
+};
+template <class T>
+inline u64 fx_leaf_hash(T v) {  // interner/hash.rs:54-64
+    Fx f;
+    f.add(0);  // NODE_TYPE_LEAF, consts.rs:7
+    f.add(u64(typename std::make_unsigned<T>::type(v)));
+    return f.finish();
+}
+inline u64 fx_branch_hash(const u64* c, u8 types, u8 mask) {  // interner/hash.rs:67-81
+    Fx f;
+    f.add(1);  // NODE_TYPE_BRANCH
+    f.add((u64(types) << 8) | mask);
+    for (int i = 0; i < 8; ++i) f.add(c[i]);
+    return f.finish();
+}
+inline u64 fx_empty_branch_hash() {  // interner/hash.rs:41-51
+    Fx f;
+    f.add(1);
+    for (int i = 0; i < 8; ++i) f.add(0);
+    return f.finish();
+}
+
+// ---------------------------------------------------------------------------------
+// calc_average — core/voxel.rs:96-141 (mode of the 8 child values; ties: a non-default
+// value beats the default, otherwise first occurrence wins).
+// ---------------------------------------------------------------------------------
+template <class T>
+inline T calc_average(const T* c) {
+    T values[8];
+    size_t counts[8];
+    int unique = 0;
+    for (int k = 0; k < 8; ++k) {
+        int i = 0;
+        while (i < unique) {
+            if (values[i] == c[k]) {
+                counts[i] += 1;
+                break;
+            }
+            ++i;
+        }
+        if (i == unique) {
+            values[unique] = c[k];
+            counts[unique] = 1;
+            ++unique;
+        }
+    }
+    if (unique == 0) return T(0);
+    int max_i = 0;
+    size_t max_cnt = counts[0];
+    for (int i = 1; i < unique; ++i) {
+        bool def_i = values[i] == T(0), def_max = values[max_i] == T(0);
+        if (counts[i] > max_cnt || (counts[i] == max_cnt && def_max && !def_i)) {
+            max_cnt = counts[i];
+            max_i = i;
+        }
+    }
+    return values[max_i];
+}
+
+// ---------------------------------------------------------------------------------
+// InternerStats — interner/stats.rs:1-28 (feature memory_stats); update sites cited
+// where they are bumped.
+// ---------------------------------------------------------------------------------
+struct Stats {
+    u64 requested_budget = 0, actual_budget = 0, node_size = 0, nodes_capacity = 0;
+    u64 total_allocations = 0, total_deallocations = 0, allocated_nodes = 0, recycled_nodes = 0;
+    u64 alive_nodes = 0, patterns = 0;
+    u64 total_cache_hits = 0, total_cache_misses = 0;
+    u64 branch_cache_hits = 0, branch_cache_misses = 0, leaf_cache_hits = 0, leaf_cache_misses = 0;
+    u64 collapsed_branches = 0, leaf_nodes = 0, branch_nodes = 0;
+    u64 max_alive_nodes = 0, max_node_id = 0, max_branch_ref_count = 0, max_leaf_ref_count = 0;
+    u64 max_generation = 0, generations_overflows = 0;
+};
+
+// Open-addressing hash -> id map standing in for the reference's
+// HashMap<u64, BlockId, IdentityHasher> (interner/hash.rs:15-38).  Linear probing with
+// back-shift deletion; equality is decided by the caller's full-key predicate.
+struct PatternMap {
+    struct Slot {
+        u64 hash;
+        u64 id;  // ID_INVALID == vacant
+    };
+    std::vector<Slot> slots;
+    size_t mask = 0, count = 0;
+    explicit PatternMap(size_t cap = 16384) {  // INITIAL_CAPACITY, interner/mod.rs:43
+        size_t n = 1;
+        while (n < cap * 2) n <<= 1;
+        slots.assign(n, Slot{0, ID_INVALID});
+        mask = n - 1;
+    }
+    static size_t mix(u64 h) {
+        h ^= h >> 32;
+        h *= 0x9E3779B97F4A7C15ull;
+        return size_t(h ^ (h >> 29));
+    }
+    template <class Eq>
+    Slot* find(u64 hash, Eq eq) {
+        size_t i = mix(hash) & mask;
+        while (slots[i].id != ID_INVALID) {
+            if (slots[i].hash == hash && eq(slots[i].id)) return &slots[i];
+            i = (i + 1) & mask;
+        }
+        return nullptr;
+    }
+    void grow() {
+        std::vector<Slot> old;
+        old.swap(slots);
+        slots.assign(old.size() * 2, Slot{0, ID_INVALID});
+        mask = slots.size() - 1;
+        for (auto& s : old)
+            if (s.id != ID_INVALID) {
+                size_t i = mix(s.hash) & mask;
+                while (slots[i].id != ID_INVALID) i = (i + 1) & mask;
+                slots[i] = s;
+            }
+    }
+    void insert(u64 hash, u64 id) {
+        if ((count + 1) * 2 > slots.size()) grow();
+        size_t i = mix(hash) & mask;
+        while (slots[i].id != ID_INVALID) i = (i + 1) & mask;
+        slots[i] = Slot{hash, id};
+        ++count;
+    }
+    void erase_id(u64 hash, u64 id) {
+        size_t i = mix(hash) & mask;
+        while (slots[i].id != ID_INVALID) {
+            if (slots[i].hash == hash && slots[i].id == id) break;
+            i = (i + 1) & mask;
+        }
+        if (slots[i].id == ID_INVALID) return;
+        // back-shift deletion
+        size_t j = i;
+        for (;;) {
+            j = (j + 1) & mask;
+            if (slots[j].id == ID_INVALID) break;
+            size_t home = mix(slots[j].hash) & mask;
+            bool between = (i <= j) ? (home > i && home <= j) : (home > i || home <= j);
+            if (!between) {
+                slots[i] = slots[j];
+                i = j;
+            }
+        }
+        slots[i].id = ID_INVALID;
+        --count;
+    }
+};
+
+// ---------------------------------------------------------------------------------
+// VoxInterner<T> — interner/mod.rs:25-40 (struct), :45-155 (with_memory_budget),
+// :158-164 (node_size), pools = voxelis-memory/src/pool_allocator_lite.rs:29-81
+// (one zeroed slab per field -> calloc here, lazily paged like alloc_zeroed).
+// ---------------------------------------------------------------------------------
+template <class T>
+struct Interner {
+    PatternMap patterns[2];  // [0]=branch, [1]=leaf — consts.rs:10-11
+    std::vector<u32> free_indices;
+    u32 next_index = 1;
+    u32* ref_counts = nullptr;
+    u16* generations = nullptr;
+    u64 (*children)[8] = nullptr;
+    T* values = nullptr;
+    u64* hashes = nullptr;
+    size_t capacity = 0;
+    u64 empty_branch_hash = 0;
+    Stats stats;
+
+    static constexpr size_t node_size() { return 4 + 2 + 64 + sizeof(T) + 8; }  // mod.rs:158-164
+
+    explicit Interner(size_t requested_budget) {  // mod.rs:45-155
+        size_t cap = requested_budget / node_size();
+        size_t actual = cap * node_size();
+        if (cap == 0 || actual == 0) throw RefPanic("Requested budget is too small");  // :63-64
+        if (cap > 0xFFFFFFFFull) throw RefPanic("Requested budget is too large");       // :65-68
+        capacity = cap;
+        ref_counts = (u32*)calloc(cap, sizeof(u32));
+        generations = (u16*)calloc(cap, sizeof(u16));
+        children = (u64(*)[8])calloc(cap, 64);
+        values = (T*)calloc(cap, sizeof(T));
+        hashes = (u64*)calloc(cap, sizeof(u64));
+        if (!ref_counts || !generations || !children || !values || !hashes)
+            throw std::bad_alloc();
+        empty_branch_hash = fx_empty_branch_hash();
+        hashes[0] = empty_branch_hash;                 // :92-96 slot 0 = permanent empty branch
+        patterns[0].insert(empty_branch_hash, ID_EMPTY);  // :97
+        next_index = 1;                                // :101
+        stats.requested_budget = requested_budget;     // :111-137
+        stats.actual_budget = actual;
+        stats.node_size = node_size();
+        stats.nodes_capacity = cap;
+        stats.total_allocations = 1;
+        stats.allocated_nodes = 1;
+        stats.alive_nodes = 1;
+        stats.patterns = 1;
+        stats.branch_nodes = 1;
+    }
+    ~Interner() {
+        free(ref_counts);
+        free(generations);
+        free(children);
+        free(values);
+        free(hashes);
+    }
+    Interner(const Interner&) = delete;
+    Interner& operator=(const Interner&) = delete;
+
+    // get_next_index_macro! — interner/macros.rs:1-41
+    u32 next_free_index() {
+        if (!free_indices.empty()) {
+            u32 i = free_indices.back();
+            free_indices.pop_back();
+            stats.alive_nodes += 1;
+            if (stats.alive_nodes > stats.max_alive_nodes) stats.max_alive_nodes = stats.alive_nodes;
+            stats.recycled_nodes -= 1;
+            stats.total_allocations += 1;
+            return i;
+        } else if (next_index < u32(capacity)) {
+            u32 i = next_index++;
+            stats.alive_nodes += 1;
+            if (stats.alive_nodes > stats.max_alive_nodes) stats.max_alive_nodes = stats.alive_nodes;
+            stats.allocated_nodes += 1;
+            stats.total_allocations += 1;
+            if (i > stats.max_node_id) stats.max_node_id = i;
+            return i;
+        }
+        throw RefPanic("Out of memory");  // macros.rs:38
+    }
+
+    bool is_valid(u64 id) const { return generations[id_index(id)] == id_gen(id); }  // mod.rs:1004-1008
+    T get_value(u64 id) const { return values[id_index(id)]; }                       // :166-176
+    u64 get_child_id(u64 id, int i) const { return children[id_index(id)][i]; }      // :205-216
+    u32 get_ref(u64 id) const { return ref_counts[id_index(id)]; }                   // :218-228
+
+    void note_ref(u64 id) {
+        u64 r = ref_counts[id_index(id)];
+        if (id_is_branch(id)) {
+            if (r > stats.max_branch_ref_count) stats.max_branch_ref_count = r;
+        } else if (r > stats.max_leaf_ref_count)
+            stats.max_leaf_ref_count = r;
+    }
+    void inc_ref(u64 id) {  // mod.rs:230-256
+        ref_counts[id_index(id)] += 1;
+        note_ref(id);
+    }
+    void inc_ref_by(u64 id, u32 n) {  // mod.rs:342-370
+        ref_counts[id_index(id)] += n;
+        note_ref(id);
+    }
+    void remove_pattern(u64 id) {
+        patterns[id_is_leaf(id) ? 1 : 0].erase_id(hashes[id_index(id)], id);
+        stats.patterns -= 1;
+    }
+    bool dec_ref(u64 id) {  // mod.rs:258-289
+        u32 i = id_index(id);
+        ref_counts[i] -= 1;
+        if (ref_counts[i] == 0) {
+            remove_pattern(id);
+            recycle(id);
+            return true;
+        }
+        return false;
+    }
+    void dec_ref_by(u64 id, u32 n) {  // mod.rs:372-417
+        u32 i = id_index(id);
+        ref_counts[i] -= n;
+        if (ref_counts[i] == 0) {
+            remove_pattern(id);
+            recycle(id);
+        }
+    }
+    void dec_child_refs(const u64* c) {  // mod.rs:536-564
+        for (int i = 0; i < 8; ++i)
+            if (!id_is_empty(c[i])) dec_ref(c[i]);
+    }
+    // dec_ref_recursive — mod.rs:419-534 (FIFO work list; the reference preallocates
+    // 32768 entries, consts.rs:15 — a growable vector here).
+    void dec_ref_recursive(u64 root) {
+        std::vector<u64> stack;
+        stack.push_back(root);
+        size_t read = 0;
+        while (read < stack.size()) {
+            u64 cur = stack[read++];
+            u32 ci = id_index(cur);
+            ref_counts[ci] -= 1;
+            if (ref_counts[ci] == 0) {
+                for (int k = 0; k < 8; ++k) {
+                    u64 ch = children[ci][k];
+                    if (!id_is_empty(ch)) {
+                        u32& rc = ref_counts[id_index(ch)];
+                        if (rc > 1)
+                            rc -= 1;
+                        else
+                            stack.push_back(ch);
+                    }
+                }
+                remove_pattern(cur);
+                recycle(cur);
+            }
+        }
+    }
+    void recycle(u64 id) {  // mod.rs:566-625
+        u32 i = id_index(id);
+        values[i] = T(0);
+        memset(children[i], 0, 64);
+        hashes[i] = 0;
+        ref_counts[i] = 0;
+        generations[i] += 1;
+        if (generations[i] >= MAX_GENERATION) {
+            generations[i] = 0;
+            stats.generations_overflows += 1;
+        }
+        if (generations[i] > stats.max_generation) stats.max_generation = generations[i];
+        free_indices.push_back(i);
+        stats.alive_nodes -= 1;
+        stats.total_deallocations += 1;
+        stats.recycled_nodes += 1;
+        if (id_is_leaf(id))
+            stats.leaf_nodes -= 1;
+        else
+            stats.branch_nodes -= 1;
+    }
+
+    u64 get_or_create_leaf(T value) {  // mod.rs:627-710
+        u64 hash = fx_leaf_hash(value);
+        auto* s = patterns[1].find(hash, [&](u64 id) { return values[id_index(id)] == value; });
+        if (s) {
+            u64 id = s->id;
+            if (!is_valid(id)) throw RefPanic("Expired node in patterns");  // :662-667
+            inc_ref(id);
+            stats.total_cache_hits += 1;
+            stats.leaf_cache_hits += 1;
+            return id;
+        }
+        u32 index = next_free_index();
+        u64 id = id_leaf(index, generations[index]);
+        patterns[1].insert(hash, id);
+        values[index] = value;
+        hashes[index] = hash;
+        inc_ref(id);
+        stats.leaf_nodes += 1;
+        stats.patterns += 1;
+        stats.total_cache_misses += 1;
+        stats.leaf_cache_misses += 1;
+        return id;
+    }
+
+    // get_or_create_branch — mod.rs:716-829.  Every non-empty child carries one bumped
+    // reference: kept on a miss, released on a hit.
+    u64 get_or_create_branch(const u64* c, u8 types, u8 mask) {
+        u64 hash = fx_branch_hash(c, types, mask);
+        auto* s = patterns[0].find(hash, [&](u64 id) {
+            return id != ID_EMPTY && id_types(id) == types && id_mask(id) == mask &&
+                   memcmp(children[id_index(id)], c, 64) == 0;
+        });
+        if (s) {
+            u64 id = s->id;
+            dec_child_refs(c);  // :767
+            inc_ref(id);        // :772
+            stats.total_cache_hits += 1;
+            stats.branch_cache_hits += 1;
+            return id;
+        }
+        u32 index = next_free_index();
+        u64 id = id_branch(index, generations[index], types, mask);
+        patterns[0].insert(hash, id);
+        T cv[8];
+        for (int i = 0; i < 8; ++i) cv[i] = values[id_index(c[i])];  // :794 (EMPTY -> slot 0 -> 0)
+        memcpy(children[index], c, 64);
+        values[index] = calc_average(cv);
+        hashes[index] = hash;
+        inc_ref(id);
+        stats.branch_nodes += 1;
+        stats.patterns += 1;
+        stats.total_cache_misses += 1;
+        stats.branch_cache_misses += 1;
+        return id;
+    }
+};
+
+// ---------------------------------------------------------------------------------
+// Batch<T> — core/batch.rs:39-45 (struct), :63-81 (new), :145-175 (just_set),
+// :178-184 (just_fill), :187-195 (just_clear).  The arrays are borrowed views so the
+// oracle consumes byte-for-byte the same buffers as the CUDA path.
+// ---------------------------------------------------------------------------------
+inline size_t batch_blocks(int max_depth) {  // batch.rs:67-72
+    int lower = max_depth > 0 ? max_depth - 1 : 0;
+    return size_t(1) << (3 * lower);
+}
+template <class T>
+struct BatchView {
+    const u8* masks;   // [B][2] = (set_mask, clear_mask)
+    const T* values;   // [B][8]
+    bool has_fill;
+    T fill;
+    bool has_patches;
+    int max_depth;
+};
+template <class T>
+inline void batch_just_set(u8* masks, T* values, int x, int y, int z, T v) {  // batch.rs:145-175
+    u32 full = encode_child_index_path(x, y, z);
+    size_t pi = full >> 3;
+    int idx = full & 7;
+    u8 bit = u8(1u << idx);
+    if (v != T(0)) {
+        masks[2 * pi] |= bit;
+        masks[2 * pi + 1] &= u8(~bit);
+    } else {
+        masks[2 * pi] &= u8(~bit);
+        masks[2 * pi + 1] |= bit;
+    }
+    values[8 * pi + idx] = v;
+}
+
+// ---------------------------------------------------------------------------------
+// set_batch_at_depth_iterative — spatial/voxtree.rs:724-1118 (called from
+// set_batch_at_root :708-722 with initial depth 0).
+// ---------------------------------------------------------------------------------
+template <class T>
+u64 set_batch_at_root(Interner<T>& in, u64 initial_node, int max_depth, const BatchView<T>& b) {
+    if (initial_node == ID_INVALID) throw RefPanic("invalid root");  // :714
+    // Phase 0 — fill (:742-754)
+    if (b.has_fill) initial_node = in.get_or_create_leaf(b.fill);
+    if (!b.has_patches) return initial_node;  // :756-758
+    if (max_depth < 2) throw RefPanic("max_depth < 2 underflows target_depth - 1");  // :913,934
+
+    const size_t data_len = batch_blocks(max_depth);
+    std::vector<u64> cur(data_len, ID_INVALID), nxt(data_len, ID_INVALID);  // :772-773
+    std::vector<size_t> paths, next_paths;
+    paths.reserve(data_len);
+    next_paths.reserve(data_len);
+
+    // Phase 1 — blocks at depth max_depth-1 (:778-897)
+    for (size_t pi = 0; pi < data_len; ++pi) {
+        u8 set_mask = b.masks[2 * pi];
+        if (set_mask == 0) continue;  // clear_mask is never read (:778-781)
+        size_t path = pi << 3;
+        u64 current = initial_node, leaf_node = ID_EMPTY;
+        for (int cd = 0; cd < max_depth - 1; ++cd) {  // :792-822
+            if (id_is_branch(current)) {
+                int idx = int((path >> ((max_depth - cd - 1) * 3)) & 7);
+                current = in.get_child_id(current, idx);
+            } else {
+                leaf_node = current;
+                current = ID_EMPTY;
+            }
+            if (id_is_empty(current)) break;
+        }
+        const T* values = b.values + 8 * pi;
+        bool all_same = set_mask == 0xFF;  // :826
+        for (int i = 1; all_same && i < 8; ++i) all_same = values[i] == values[0];
+        if (!all_same) {
+            u64 children[8];
+            u8 types, mask;
+            if (!id_is_empty(current)) {  // :829-834 (panics if `current` is a leaf)
+                memcpy(children, in.children[id_index(current)], 64);
+                types = id_types(current);
+                mask = id_mask(current);
+            } else if (id_is_leaf(leaf_node)) {  // :835-839
+                int n = __builtin_popcount(set_mask);
+                in.inc_ref_by(leaf_node, u32(8 - n));
+                for (int i = 0; i < 8; ++i) children[i] = leaf_node;
+                types = mask = 0xFF;
+            } else {  // :840-842
+                memset(children, 0, 64);
+                types = mask = 0;
+            }
+            u8 modified = 0;
+            for (u8 bits = set_mask; bits;) {  // :846-863
+                int idx = __builtin_ctz(bits);
+                bits &= u8(~(1u << idx));
+                T value = values[idx];
+                if (!id_is_empty(children[idx]) && in.get_value(children[idx]) == value) continue;
+                children[idx] = in.get_or_create_leaf(value);
+                types |= u8(1u << idx);
+                mask |= u8(1u << idx);
+                modified |= u8(1u << idx);
+            }
+            if (modified == 0) continue;  // :865-868
+            if (id_is_empty(leaf_node)) {  // :870-881
+                for (u8 bits = u8(~modified); bits;) {
+                    int idx = __builtin_ctz(bits);
+                    bits &= u8(~(1u << idx));
+                    if (!id_is_empty(children[idx])) in.inc_ref_by(children[idx], 1);
+                }
+            }
+            cur[pi] = in.get_or_create_branch(children, types, mask);  // :883-886
+            paths.push_back(path);
+        } else {  // :887-896
+            in.stats.collapsed_branches += 1;
+            T first = values[__builtin_ctz(set_mask)];
+            cur[pi] = in.get_or_create_leaf(first);
+            paths.push_back(path);
+        }
+    }
+
+    // Phase 2 — integrate upwards (:905-1106)
+    if (paths.empty()) return ID_INVALID;  // :905-911
+    int target_depth = max_depth - 1;
+    while (!paths.empty()) {
+        size_t path = paths.back();
+        paths.pop_back();
+        int pmd = target_depth > 1 ? target_depth - 2 : 0;  // :922-926
+        size_t pmask = path_mask(max_depth, pmd);
+        u64 equivalent = initial_node, leaf_id = ID_EMPTY;
+        for (int cd = 0; cd < target_depth - 1; ++cd) {  // :934-946
+            if (id_is_leaf(equivalent)) {
+                leaf_id = equivalent;
+                equivalent = ID_EMPTY;
+                break;
+            } else {
+                int idx = int((path >> ((max_depth - cd - 1) * 3)) & 7);
+                equivalent = in.get_child_id(equivalent, idx);
+            }
+            if (id_is_empty(equivalent)) break;
+        }
+        if (id_is_leaf(equivalent)) {  // :948-951
+            leaf_id = equivalent;
+            equivalent = ID_EMPTY;
+        }
+        u64 children[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        u8 types = 0, mask = 0;
+        bool has_next = true;
+        while (has_next) {  // :959-1000
+            int tidx = int((path >> ((max_depth - target_depth) * 3)) & 7);
+            bool have_next_path = !paths.empty();
+            size_t next_path = have_next_path ? paths.back() : 0;
+            if (target_depth == 1)
+                has_next = have_next_path;
+            else
+                has_next = have_next_path && ((path & pmask) == (next_path & pmask));
+            size_t cpi = path >> 3;
+            u64 id = cur[cpi];
+            children[tidx] = id;
+            cur[cpi] = ID_INVALID;
+            types |= u8(u8(id_is_leaf(id)) << tidx);
+            mask |= u8(1u << tidx);
+            if (has_next && !paths.empty()) {
+                path = paths.back();
+                paths.pop_back();
+            }
+        }
+        u8 existing_mask = id_mask(equivalent);  // :1013 (equivalent is a branch or EMPTY here)
+        u8 inv_mask = u8(~mask);
+        u8 cloned = existing_mask & inv_mask;
+        if (mask != 0xFF) {  // :1017-1048
+            if (cloned != 0) {
+                const u64* ex = in.children[id_index(equivalent)];
+                for (u8 bits = cloned; bits;) {
+                    int idx = __builtin_ctz(bits);
+                    bits &= u8(~(1u << idx));
+                    children[idx] = ex[idx];
+                    types |= u8(u8(id_is_leaf(children[idx])) << idx);
+                    mask |= u8(1u << idx);
+                }
+            } else if (!id_is_empty(leaf_id)) {
+                u32 n = u32(__builtin_popcount(inv_mask));
+                types |= inv_mask;
+                mask |= inv_mask;
+                for (u8 bits = inv_mask; bits;) {
+                    int idx = __builtin_ctz(bits);
+                    children[idx] = leaf_id;
+                    bits &= u8(~(1u << idx));
+                }
+                in.inc_ref_by(leaf_id, n);
+            }
+        }
+        bool all_same = types == 0xFF;  // :1050
+        for (int i = 1; all_same && i < 8; ++i) all_same = children[i] == children[0];
+        u64 new_id;
+        if (!all_same) {  // :1052-1061
+            for (u8 bits = cloned; bits;) {
+                int idx = __builtin_ctz(bits);
+                bits &= u8(~(1u << idx));
+                in.inc_ref(children[idx]);
+            }
+            new_id = in.get_or_create_branch(children, types, mask);
+        } else {  // :1062-1075
+            in.stats.collapsed_branches += 1;
+            u32 dec = cloned != 0 ? std::min<u32>(u32(__builtin_popcount(cloned)), 7u) : 7u;
+            in.dec_ref_by(children[0], dec);
+            new_id = children[0];
+        }
+        size_t np = path & pmask;  // :1083-1085
+        next_paths.push_back(np);
+        nxt[np >> 3] = new_id;
+        if (paths.empty()) {  // :1092-1105
+            cur.swap(nxt);
+            paths.swap(next_paths);
+            next_paths.clear();
+            target_depth -= 1;
+            if (target_depth == 0) break;
+        }
+    }
+    return cur[paths[0] >> 3];  // :1108
+}
+
+// ---------------------------------------------------------------------------------
+// VoxTree<T> — spatial/voxtree.rs:108-142 (struct/new), :264-292 (fill/clear),
+// :303-328 (apply_batch), :144-160 (get).
+// ---------------------------------------------------------------------------------
+struct Tree {
+    int max_depth;
+    u64 root_id = ID_EMPTY;
+    bool dirty = false;
+    explicit Tree(int d) : max_depth(d) {}
+};
+
+template <class T>
+bool tree_apply_batch(Interner<T>& in, Tree& t, const BatchView<T>& b) {  // :303-328
+    u64 new_root = set_batch_at_root(in, t.root_id, t.max_depth, b);
+    if (new_root != ID_INVALID) {
+        if (!id_is_empty(t.root_id)) {
+            if (new_root == t.root_id) throw RefPanic("assert_ne!(new_root_id, self.root_id)");  // :311
+            in.dec_ref_recursive(t.root_id);
+        }
+        if (!in.is_valid(new_root)) throw RefPanic("Invalid new root id");  // :316-319
+        t.root_id = new_root;
+        t.dirty = true;
+        return true;
+    }
+    return false;
+}
+template <class T>
+void tree_clear(Interner<T>& in, Tree& t) {  // :283-292
+    if (!id_is_empty(t.root_id)) {
+        in.dec_ref_recursive(t.root_id);
+        t.root_id = ID_EMPTY;
+        t.dirty = true;
+    }
+}
+template <class T>
+void tree_fill(Interner<T>& in, Tree& t, T v) {  // :264-281
+    if (v != T(0)) {
+        if (!id_is_empty(t.root_id)) in.dec_ref_recursive(t.root_id);
+        t.root_id = in.get_or_create_leaf(v);
+        t.dirty = true;
+    } else
+        tree_clear(in, t);
+}
+
+// get_at_depth — utils/common.rs:122-156.  Returns false for None.
+template <class T>
+bool tree_get(const Interner<T>& in, const Tree& t, int x, int y, int z, T* out) {
+    int md = t.max_depth;
+    int n = 1 << md;
+    if (x < 0 || x >= n || y < 0 || y >= n || z < 0 || z >= n)
+        throw RefPanic("position out of bounds");  // voxtree.rs:146-148
+    u64 node = t.root_id;
+    int depth = 0;
+    while (!id_is_empty(node)) {
+        if (depth >= md) {
+            T v = in.get_value(node);
+            if (v != T(0)) {
+                *out = v;
+                return true;
+            }
+            return false;
+        }
+        if (id_is_branch(node)) {
+            int shift = md - depth - 1;  // child_index_macro_2, common.rs:104-111
+            int idx = ((x >> shift) & 1) | (((y >> shift) & 1) << 1) | (((z >> shift) & 1) << 2);
+            node = in.get_child_id(node, idx);
+            depth += 1;
+        } else {
+            *out = in.get_value(node);
+            return true;
+        }
+    }
+    return false;
+}
+
+// to_vec — utils/common.rs:158-246.  Dense layout index = y*N*N + z*N + x (:229-238).
+template <class T>
+void tree_to_vec(const Interner<T>& in, const Tree& t, T* data) {
+    int md = t.max_depth;
+    size_t n = size_t(1) << md;
+    size_t size = n * n * n;
+    if (!id_is_branch(t.root_id)) {  // :172-174
+        T v = in.get_value(t.root_id);
+        for (size_t i = 0; i < size; ++i) data[i] = v;
+        return;
+    }
+    memset(data, 0, size * sizeof(T));
+    if (id_is_empty(t.root_id)) return;
+    struct Item {
+        u64 id;
+        int x, y, z, depth;
+    };
+    std::vector<Item> stack;
+    stack.push_back({t.root_id, 0, 0, 0, 0});
+    while (!stack.empty()) {
+        Item it = stack.back();
+        stack.pop_back();
+        if (id_is_branch(it.id) && it.depth < md) {
+            int half = 1 << (md - it.depth - 1);
+            const u64* ch = in.children[id_index(it.id)];
+            for (int i = 7; i >= 0; --i)
+                if (!id_is_empty(ch[i]))
+                    stack.push_back({ch[i], it.x + (i & 1) * half, it.y + ((i >> 1) & 1) * half,
+                                     it.z + ((i >> 2) & 1) * half, it.depth + 1});
+        } else {
+            T v = in.get_value(it.id);
+            if (v != T(0)) {
+                size_t side = size_t(1) << (md - it.depth);
+                for (size_t y = it.y; y < it.y + side; ++y)
+                    for (size_t z = it.z; z < it.z + side; ++z) {
+                        T* row = data + y * n * n + z * n + it.x;
+                        for (size_t k = 0; k < side; ++k) row[k] = v;
+                    }
+            }
+        }
+    }
+}
+
+}  // namespace vxo
