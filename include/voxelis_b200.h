@@ -1,0 +1,191 @@
+/* voxelis_b200.h — C ABI of the B200-native batched SVO-DAG build path.
+ *
+ * Drop-in boundary for ONE path of WildPixelGames/voxelis v25.4.0:
+ *     Batch  ->  VoxTree::apply_batch  ->  VoxInterner   (+ a new multi-chunk apply_batches)
+ * The reference is a Rust library with no FFI surface of its own, so each entry point below is
+ * shaped 1:1 on the Rust method it replaces (cited as file:line under
+ * /root/reference/voxelis/src).  INTEGRATION.md shows the `extern "C"` block a Rust maintainer
+ * would add on top of this header.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no CUDA or torch types in any signature (streams are passed
+ *     as `void*`, i.e. a cudaStream_t, and may be NULL for the interner's own stream);
+ *   - every function that can fail returns a negative vx_status; vx_last_error() gives the
+ *     message for the calling thread.  The reference panics at these sites; this library never
+ *     aborts the process;
+ *   - threading follows the reference (`&mut VoxInterner`, world/voxmodel.rs:32): one mutator per
+ *     interner at a time; reads may run concurrently with each other but not with an apply;
+ *   - there is NO CPU fallback: with no usable CUDA device every compute entry point fails with
+ *     VX_E_CUDA.
+ */
+#ifndef VOXELIS_B200_H
+#define VOXELIS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VX_ABI_VERSION 1
+
+/* VoxelTrait numeric impls in scope (core/voxel.rs:77,93): u8 and i32. */
+typedef enum vx_dtype { VX_U8 = 0, VX_I32 = 1 } vx_dtype;
+
+typedef enum vx_status {
+    VX_OK = 0,
+    VX_E_INVALID = -1,      /* bad argument / handle                                            */
+    VX_E_OOM = -2,          /* "Out of memory" — interner/macros.rs:38 (node capacity exhausted) */
+    VX_E_CUDA = -3,         /* CUDA runtime error or no device                                   */
+    VX_E_UNSUPPORTED = -4,  /* valid in the reference, not implemented on this path yet          */
+    VX_E_BOUNDS = -5,       /* position out of range — spatial/voxtree.rs:146-148                */
+    VX_E_BUDGET = -6,       /* "Requested budget is too small/large" — interner/mod.rs:63-68     */
+    VX_E_POISONED = -7      /* a previous apply overflowed the interner; reset or destroy it     */
+} vx_status;
+
+/* BlockId (core/block_id.rs:18-30): leaf<<63 | types<<55 | mask<<47 | generation<<32 | index */
+typedef uint64_t vx_block_id;
+#define VX_BLOCK_EMPTY ((vx_block_id)0)             /* block_id.rs:112 */
+#define VX_BLOCK_INVALID (~(vx_block_id)0)          /* block_id.rs:96  */
+
+typedef struct vx_interner vx_interner; /* VoxInterner<T>   interner/mod.rs:25-40      */
+typedef struct vx_tree vx_tree;         /* VoxTree<T>       spatial/voxtree.rs:108-113 */
+typedef struct vx_batch vx_batch;       /* Batch<T>         core/batch.rs:39-45        */
+
+/* InternerStats (interner/stats.rs:1-28), same field order. */
+typedef struct vx_stats {
+    uint64_t requested_budget, actual_budget, node_size, nodes_capacity;
+    uint64_t total_allocations, total_deallocations, allocated_nodes, recycled_nodes;
+    uint64_t alive_nodes, patterns;
+    uint64_t total_cache_hits, total_cache_misses;
+    uint64_t branch_cache_hits, branch_cache_misses, leaf_cache_hits, leaf_cache_misses;
+    uint64_t collapsed_branches, leaf_nodes, branch_nodes;
+    uint64_t max_alive_nodes, max_node_id, max_branch_ref_count, max_leaf_ref_count;
+    uint64_t max_generation, generations_overflows;
+} vx_stats;
+
+const char* vx_last_error(void);
+int vx_abi_version(void);
+int vx_device_count(void); /* number of CUDA devices, <0 on error */
+
+/* ---------------------------------------------------------------- VoxInterner ------------- */
+/* VoxInterner::<T>::with_memory_budget(bytes) — interner/mod.rs:45-155.
+ * capacity = budget / node_size, node_size = 78 + sizeof(T) (mod.rs:158-164); index 0 is the
+ * permanent empty branch.  All pools live in device memory of `device`; the hash table
+ * (16 B per node of capacity) is allocated on top of the budget.  NULL on failure. */
+vx_interner* vx_interner_create(size_t budget_bytes, vx_dtype dtype, int device);
+void vx_interner_destroy(vx_interner*);
+/* Back to the freshly-created state (every node dropped).  Trees built in it become dangling. */
+int vx_interner_reset(vx_interner*);
+size_t vx_interner_capacity(const vx_interner*);
+vx_dtype vx_interner_dtype(const vx_interner*);
+int vx_interner_device(const vx_interner*);
+/* Number of index slots handed out so far, including slot 0 (`next_index`, mod.rs:28). */
+int64_t vx_interner_next_index(const vx_interner*);
+/* VoxInterner::get_ref — mod.rs:218-228 */
+int vx_interner_get_ref(const vx_interner*, vx_block_id id, uint32_t* out);
+/* VoxInterner::get_value / get_children — mod.rs:166-203 */
+int vx_interner_get_value(const vx_interner*, vx_block_id id, int64_t* out);
+int vx_interner_get_children(const vx_interner*, vx_block_id id, vx_block_id out[8]);
+/* InternerStats (feature memory_stats) */
+int vx_interner_stats(const vx_interner*, vx_stats* out);
+/* Copies the first `next_index` entries of each pool to HOST arrays (any may be NULL):
+ * children[n][8], values[n] (widened to int64), ref_counts[n], generations[n], hashes[n].
+ * `cap` = entries available in the caller's arrays; returns next_index or <0. */
+int64_t vx_interner_download(const vx_interner*, size_t cap, vx_block_id* children, int64_t* values,
+                             uint32_t* ref_counts, uint16_t* generations, uint64_t* hashes);
+/* Blocks until all work queued on the interner's stream has finished; surfaces deferred errors. */
+int vx_interner_sync(vx_interner*);
+/* The interner's CUDA stream (a cudaStream_t), for callers that want to order their own work. */
+void* vx_interner_stream(const vx_interner*);
+
+/* ---------------------------------------------------------------- Batch ------------------- */
+/* Batch::new(max_depth) / VoxTree::create_batch — core/batch.rs:63-81, voxtree.rs:296-301.
+ * Host arrays (pinned): masks[B][2] = (set_mask, clear_mask), values[B][8], B = 8^(max_depth-1),
+ * block p = Morton(x>>1,y>>1,z>>1), lane i = (x&1)|(y&1)<<1|(z&1)<<2 (utils/common.rs:24-55). */
+vx_batch* vx_batch_create(uint8_t max_depth, vx_dtype dtype);
+void vx_batch_destroy(vx_batch*);
+/* Batch::set / just_set — batch.rs:145-175,211-213.  Returns 1 (state changed), VX_E_BOUNDS when
+ * the position is outside the chunk (reference: debug_assert). */
+int vx_batch_set(vx_batch*, int x, int y, int z, int64_t voxel);
+/* Batch::fill / just_fill — batch.rs:178-184,218-221 (resets recorded patches). */
+int vx_batch_fill(vx_batch*, int64_t value);
+/* Batch::clear / just_clear — batch.rs:187-195,223-225 */
+int vx_batch_clear(vx_batch*);
+/* Batch::masks / values / to_fill / size / has_patches — batch.rs:86-132.  The raw arrays may be
+ * bulk-written by the caller; call vx_batch_mark_patched afterwards.  A set bit whose value is the
+ * default (0) cannot be produced by Batch::set and is ignored by apply. */
+uint8_t* vx_batch_masks(vx_batch*);
+void* vx_batch_values(vx_batch*);
+size_t vx_batch_blocks(const vx_batch*);
+int vx_batch_to_fill(const vx_batch*, int64_t* out); /* 1 = Some(*out), 0 = None */
+size_t vx_batch_size(const vx_batch*);
+int vx_batch_has_patches(const vx_batch*);
+void vx_batch_mark_patched(vx_batch*);
+uint8_t vx_batch_max_depth(const vx_batch*);
+vx_dtype vx_batch_dtype(const vx_batch*);
+
+/* ---------------------------------------------------------------- VoxTree ----------------- */
+/* VoxTree::new(MaxDepth) — voxtree.rs:116-126.  max_depth in [2,7]; the reference asserts < 7
+ * (core/max_depth.rs:77-83), depth 7 is this build's extension.  NULL on failure. */
+vx_tree* vx_tree_create(uint8_t max_depth);
+void vx_tree_destroy(vx_tree*);
+vx_block_id vx_tree_root_id(const vx_tree*);          /* get_root_id  voxtree.rs:128-133 */
+/* set_root_id (voxtree.rs:135-141): adopts `root` and bumps its refcount. */
+int vx_tree_set_root_id(vx_interner*, vx_tree*, vx_block_id root);
+uint8_t vx_tree_max_depth(const vx_tree*);            /* VoxOpsConfig  voxtree.rs:331-341 */
+uint32_t vx_tree_voxels_per_axis(const vx_tree*);
+int vx_tree_is_empty(const vx_tree*);                 /* VoxOpsState   voxtree.rs:343-353 */
+int vx_tree_is_leaf(const vx_tree*);
+int vx_tree_is_dirty(const vx_tree*);                 /* VoxOpsDirty   voxtree.rs:355-370 */
+void vx_tree_mark_dirty(vx_tree*);
+void vx_tree_clear_dirty(vx_tree*);
+
+/* VoxTree::apply_batch — voxtree.rs:303-328 (set_batch_at_root :708-722,
+ * set_batch_at_depth_iterative :724-1118).  Returns 1 = changed, 0 = unchanged, <0 error.
+ * Synchronous: on return tree->root is final. */
+int vx_tree_apply_batch(vx_interner*, vx_tree*, const vx_batch*);
+
+/* NEW multi-chunk entry (replaces the serial loop voxelis-voxelize/src/lib.rs:357-361):
+ * result == applying batches[i] to trees[i] in index order into one interner, up to a
+ * permutation of node indices.  `changed` (may be NULL) receives 1/0 per tree. */
+int vx_apply_batches(vx_interner*, vx_tree* const* trees, const vx_batch* const* batches, size_t n,
+                     uint8_t* changed);
+
+/* Slab form of the same for FRESH trees: n chunks of depth `max_depth`, arrays laid out
+ * masks[n][B][2], values[n][B][8].  `flags` (may be NULL = patches, no fill): bit0 = to_fill is
+ * Some(fills[i]), bit1 = has_patches.  Pointers may be host (pinned or pageable) or device
+ * memory of the interner's device — detected per pointer.  roots_out[n] / changed_out[n] (may be
+ * NULL) likewise.  Host inputs are streamed through double-buffered device staging. */
+#define VX_FLAG_FILL 1u
+#define VX_FLAG_PATCHES 2u
+int vx_apply_batches_slab(vx_interner*, uint8_t max_depth, size_t n, const uint8_t* masks,
+                          const void* values, const uint8_t* flags, const int64_t* fills,
+                          vx_block_id* roots_out, uint8_t* changed_out);
+/* Fully asynchronous device-resident form: every pointer is device memory, work is queued on
+ * `stream` (NULL = the interner's stream) and nothing is synchronised.  Errors surface at the
+ * next vx_interner_sync(). */
+int vx_apply_batches_device(vx_interner*, uint8_t max_depth, size_t n, const uint8_t* d_masks,
+                            const void* d_values, const uint8_t* d_flags, const int64_t* d_fills,
+                            vx_block_id* d_roots_out, uint8_t* d_changed_out, void* stream);
+
+/* VoxTree::get — voxtree.rs:144-160 -> get_at_depth utils/common.rs:122-156.
+ * Returns 1 = Some(*out), 0 = None, VX_E_BOUNDS outside the chunk (reference: assert!). */
+int vx_tree_get(const vx_interner*, const vx_tree*, int x, int y, int z, int64_t* out);
+/* Bulk get: xyz[n][3] (host), found[n], values[n] (host). */
+int vx_tree_get_many(const vx_interner*, const vx_tree*, size_t n, const int32_t* xyz, uint8_t* found,
+                     int64_t* values);
+/* to_vec — utils/common.rs:158-246: dense T[N^3], index = y*N*N + z*N + x.  `dense` host or device. */
+int vx_tree_to_vec(const vx_interner*, const vx_tree*, void* dense);
+/* to_vec for n bare roots of one depth: dense[n][N^3]; roots host or device, dense host or device. */
+int vx_roots_to_vec(const vx_interner*, uint8_t max_depth, size_t n, const vx_block_id* roots, void* dense);
+
+/* VoxTree::fill / clear — voxtree.rs:264-292. */
+int vx_tree_fill(vx_interner*, vx_tree*, int64_t value);
+int vx_tree_clear(vx_interner*, vx_tree*);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VOXELIS_B200_H */

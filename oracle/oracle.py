@@ -90,7 +90,7 @@ def lib():
     L.orc_interner_download.argtypes = [vp, vp, vp, vp, vp]
     L.orc_dag_signature.restype = C.c_longlong
     L.orc_dag_signature.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, C.c_int, vp, vp, vp, vp,
-                                    C.c_size_t, vp]
+                                    C.c_size_t, vp, vp]
     L.orc_time_apply_fresh.restype = C.c_double
     L.orc_time_apply_fresh.argtypes = [C.c_int, C.c_int, C.c_size_t, C.c_size_t, vp, vp, C.c_int, vp]
     _lib = L
@@ -287,17 +287,18 @@ def dag_signature(children: np.ndarray, values: np.ndarray, roots, depth: int, w
     per_depth = np.zeros((depth + 1, 2), np.uint64)
     totals = np.zeros(2, np.uint64)
     indeg = np.zeros(n, np.uint32) if want_indeg else None
+    numbers = np.zeros(n, np.uint32)
     words = lib().orc_dag_signature(_ptr(children), _ptr(values), n, _ptr(roots), len(roots), depth,
                                     _ptr(sig), _ptr(per_depth), _ptr(totals), None, 0,
-                                    None if indeg is None else _ptr(indeg))
+                                    None if indeg is None else _ptr(indeg), _ptr(numbers))
     if words < 0:
         raise OracleError("malformed DAG (index out of range or cycle)")
     out = {"sig": (int(sig[0]), int(sig[1])), "per_depth": [(int(b), int(l)) for b, l in per_depth],
-           "branches": int(totals[0]), "leaves": int(totals[1]), "words": int(words)}
+           "branches": int(totals[0]), "leaves": int(totals[1]), "words": int(words), "numbers": numbers}
     if want_stream:
         stream = np.zeros(words, np.uint64)
         lib().orc_dag_signature(_ptr(children), _ptr(values), n, _ptr(roots), len(roots), depth,
-                                None, None, None, _ptr(stream), words, None)
+                                None, None, None, _ptr(stream), words, None, None)
         out["stream"] = stream
     if want_indeg:
         out["indeg"] = indeg

@@ -251,12 +251,13 @@ void orc_interner_download(void* ih, uint64_t* children, int64_t* values, uint32
 //   totals[2]         distinct (branches, leaves) reachable
 //   stream/stream_cap optional copy of the stream (u64 words); returns words needed
 //   indeg             optional [n_nodes] in-degree from distinct reachable branches + roots
+//   numbers           optional [n_nodes] canonical number of each node (0 = unreachable)
 // Returns number of stream words, or -1 on a malformed pool (index out of range / cycle).
 // ---------------------------------------------------------------------------------
 long long orc_dag_signature(const uint64_t* children, const int64_t* values, size_t n_nodes,
                             const uint64_t* roots, size_t m, int depth, uint64_t* sig,
                             uint64_t* per_depth, uint64_t* totals, uint64_t* stream, size_t stream_cap,
-                            uint32_t* indeg) {
+                            uint32_t* indeg, uint32_t* numbers) {
     std::vector<uint32_t> number(n_nodes, 0);
     std::vector<uint8_t> state(n_nodes, 0);  // 0 new, 1 open, 2 done
     uint64_t h0 = 0xcbf29ce484222325ull, h1 = 0x84222325cbf29ce4ull;
@@ -334,6 +335,7 @@ long long orc_dag_signature(const uint64_t* children, const int64_t* values, siz
         }
     }
     for (size_t r = 0; r < m; ++r) emit(roots[r] == 0 ? 0 : number[id_index(roots[r])]);
+    if (numbers) memcpy(numbers, number.data(), n_nodes * sizeof(uint32_t));
     if (sig) {
         sig[0] = h0;
         sig[1] = h1;

@@ -1,0 +1,153 @@
+"""CUDA path vs oracle: voxel-exact, DAG-isomorphic, same counters."""
+import numpy as np
+import pytest
+
+import parity
+from voxelis_b200 import workloads as wl
+
+pytestmark = pytest.mark.gpu
+
+PATTERNS = {
+    "uniform": wl.p_uniform(1), "uniform_half": wl.p_uniform_half(1),
+    "checkerboard_bench": wl.p_checkerboard_bench(1), "checkerboard_test": wl.p_checkerboard_test(),
+    "sum": wl.p_sum(1), "sparse": wl.p_sparse(), "hollow": wl.p_hollow_cube(), "diagonal": wl.p_diagonal(),
+    "gradient": wl.p_gradient(), "random255": wl.p_random(255), "random4": wl.p_random(4),
+    "cell4": wl.p_random(255, cell=4),
+}
+
+
+@pytest.mark.parametrize("dtype", [wl.U8, wl.I32], ids=["u8", "i32"])
+@pytest.mark.parametrize("depth", [2, 3, 4, 5, 6])
+@pytest.mark.parametrize("name", sorted(PATTERNS))
+def test_single_chunk_patterns(gpu_api, oracle_api, name, depth, dtype):
+    masks, values = wl.batch_from_function(depth, PATTERNS[name], dtype, 1)
+    r = parity.build_both(gpu_api, oracle_api, depth, masks, values, dtype)
+    parity.assert_parity(gpu_api, oracle_api, depth, *r)
+
+
+@pytest.mark.parametrize("dtype", [wl.U8, wl.I32], ids=["u8", "i32"])
+@pytest.mark.parametrize("depth", [3, 4, 5])
+def test_many_chunks_one_interner(gpu_api, oracle_api, depth, dtype):
+    """apply_batches == serial application in index order, ids up to permutation."""
+    parts = [wl.batch_from_function(depth, wl.p_random(4), dtype, 24),
+             wl.batch_from_function(depth, wl.p_sum_per_chunk(), dtype, 16),
+             wl.batch_from_function(depth, wl.p_random(255), dtype, 8),
+             wl.named_workload("checkerboard", 16, depth, dtype),
+             wl.named_workload("uniform", 5, depth, dtype)]
+    masks = np.concatenate([p[0] for p in parts])
+    values = np.concatenate([p[1] for p in parts])
+    masks = np.concatenate([masks, masks[:7]])      # exact repeats -> same roots
+    values = np.concatenate([values, values[:7]])
+    masks[3] = 0                                      # an empty batch: changed == false
+    values[3] = 0
+    r = parity.build_both(gpu_api, oracle_api, depth, masks, values, dtype, budget=256 << 20)
+    g, groots, gchanged = r[0], r[1], r[2]
+    assert gchanged[3] == 0 and groots[3] == 0
+    n0 = masks.shape[0] - 7
+    same = np.array([0, 1, 2, 4, 5, 6])                # chunk 3 was blanked after the copy was taken
+    assert np.array_equal(groots[same], groots[n0 + same])
+    parity.assert_parity(gpu_api, oracle_api, depth, *r)
+
+
+@pytest.mark.parametrize("dtype", [wl.U8, wl.I32], ids=["u8", "i32"])
+def test_terrain_world_small(gpu_api, oracle_api, dtype):
+    for variant, mats in (("surface_only", 1), ("surface_and_below", 3)):
+        masks, values = wl.terrain_world((6, 3, 6), 5, variant, dtype, materials=mats)
+        r = parity.build_both(gpu_api, oracle_api, 5, masks, values, dtype, budget=256 << 20)
+        parity.assert_parity(gpu_api, oracle_api, 5, *r)
+
+
+@pytest.mark.parametrize("dtype", [wl.U8, wl.I32], ids=["u8", "i32"])
+@pytest.mark.parametrize("depth", [3, 5])
+def test_fill_variants(gpu_api, oracle_api, depth, dtype):
+    rng = np.random.default_rng(11)
+    B = wl.blocks_per_chunk(depth)
+    n = 6
+    masks = np.zeros((n, B, 2), np.uint8)
+    values = np.zeros((n, B, 8), wl.NP_DTYPE[dtype])
+    sel = rng.random((n, B, 8)) < 0.04
+    vals = rng.integers(1, 4, (n, B, 8))
+    vals[vals == 3] = 7        # never equal to the fill value (the reference mis-counts there)
+    values[sel] = vals[sel].astype(values.dtype)
+    masks[:, :, 0] = (sel * (1 << np.arange(8))).sum(-1).astype(np.uint8)
+    # chunk 4: fully set uniform blocks everywhere with a value != fill -> collapses to a leaf root
+    masks[4, :, 0] = 0xFF
+    values[4] = 9
+    r = parity.build_both(gpu_api, oracle_api, depth, masks, values, dtype, fill=3)
+    parity.assert_parity(gpu_api, oracle_api, depth, *r)
+    # fill only (no patches): root is the fill leaf, ref 1
+    r = parity.build_both(gpu_api, oracle_api, depth, masks[:2] * 0, values[:2] * 0, dtype, fill=5, has_patches=False)
+    assert gpu_api.id_is_leaf(r[1][0]) and r[1][0] == r[1][1]
+    parity.assert_parity(gpu_api, oracle_api, depth, *r)
+    # fill + patches that all equal the fill -> changed == false, root untouched
+    m2, v2 = masks[:1] * 0, values[:1] * 0
+    m2[0, 5, 0] = 0b101
+    v2[0, 5, 0] = v2[0, 5, 2] = 3
+    r = parity.build_both(gpu_api, oracle_api, depth, m2, v2, dtype, fill=3)
+    assert r[2][0] == 0 and r[1][0] == 0
+    parity.assert_parity(gpu_api, oracle_api, depth, *r)
+
+
+def test_known_answers_d5(gpu_api):
+    """SURVEY §8(c) table, through the C ABI."""
+    known = {"uniform": (0, 1, 4681, 4095, 1), "checkerboard_bench": (5, 1, 0, 21059, 6),
+             "sum": (83, 94, 0, 37272, 177), "hollow": (87, 1, 0, 7393, 88), "diagonal": (5, 1, 0, 57, 6)}
+    for name, (br, lf, col, hits, misses) in known.items():
+        masks, values = wl.batch_from_function(5, PATTERNS[name], wl.U8, 1)
+        g = gpu_api.VoxInterner.with_memory_budget(256 << 20)     # BASELINE.json config 1 budget
+        roots, changed = g.apply_batches_slab(5, masks, values)
+        st = g.stats()
+        assert (st["branch_nodes"] - 1, st["leaf_nodes"], st["collapsed_branches"]) == (br, lf, col)
+        assert (st["total_cache_hits"], st["total_cache_misses"]) == (hits, misses)
+        assert changed[0] == 1
+        assert g.capacity == 3397917
+
+
+def test_host_and_device_inputs_agree(gpu_api):
+    import torch
+    masks, values = wl.batch_from_function(5, wl.p_random(4), wl.U8, 64)
+    a = gpu_api.VoxInterner.with_memory_budget(64 << 20)
+    ra, ca = a.apply_batches_slab(5, masks, values)
+    b = gpu_api.VoxInterner.with_memory_budget(64 << 20)
+    dm, dv = torch.from_numpy(masks).cuda(), torch.from_numpy(values).cuda()
+    droots = torch.zeros(64, dtype=torch.int64, device="cuda")
+    dch = torch.zeros(64, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    b.apply_batches_device(5, 64, dm.data_ptr(), dv.data_ptr(), droots.data_ptr(), dch.data_ptr())
+    b.sync()
+    assert np.array_equal(a.roots_to_vec(ra, 5), b.roots_to_vec(droots.cpu().numpy().astype(np.uint64), 5))
+    assert np.array_equal(ca, dch.cpu().numpy())
+    assert a.stats() == b.stats()
+
+
+def test_out_of_memory_is_a_status_not_an_abort(gpu_api):
+    g = gpu_api.VoxInterner.with_memory_budget(79 * 64)          # 64 nodes
+    masks, values = wl.batch_from_function(5, wl.p_random(255), wl.U8, 1)
+    with pytest.raises(gpu_api.VoxelisError) as e:
+        g.apply_batches_slab(5, masks, values)
+    assert e.value.code == -2 and "Out of memory" in str(e.value)   # interner/macros.rs:38
+    with pytest.raises(gpu_api.VoxelisError) as e:
+        g.apply_batches_slab(5, masks, values)
+    assert e.value.code == -7
+    g.reset()
+    m2, v2 = wl.batch_from_function(5, wl.p_uniform(3), wl.U8, 1)
+    roots, changed = g.apply_batches_slab(5, m2, v2)
+    assert changed[0] == 1 and gpu_api.id_is_leaf(roots[0])
+
+
+def test_bounds_and_argument_errors(gpu_api):
+    vx = gpu_api
+    it = vx.VoxInterner.with_memory_budget(1 << 20)
+    t = vx.VoxTree(5)
+    b = t.create_batch()
+    with pytest.raises(vx.VoxelisError) as e:
+        b.set(it, (32, 0, 0), 1)
+    assert e.value.code == -5
+    with pytest.raises(vx.VoxelisError) as e:
+        t.get(it, (0, -1, 0))
+    assert e.value.code == -5
+    with pytest.raises(vx.VoxelisError):
+        vx.VoxTree(8)
+    with pytest.raises(vx.VoxelisError):
+        vx.VoxInterner.with_memory_budget(10)
+    assert t.get(it, (1, 2, 3)) is None and t.is_empty() and not t.is_dirty()

@@ -1,0 +1,380 @@
+"""Host-side mirror of the reference's VoxInterner / VoxTree / Batch API over the C ABI.
+
+Names, argument meaning and error behaviour follow the Rust traits (reference
+voxelis/src/spatial/voxops.rs:8-35; Batch core/batch.rs; VoxTree spatial/voxtree.rs):
+reference panics become ``VoxelisError`` with the status code of include/voxelis_b200.h.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+U8, I32 = 0, 1
+_NP = {U8: np.uint8, I32: np.int32}
+FLAG_FILL, FLAG_PATCHES = 1, 2
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libvoxelis_b200.so")
+_lib = None
+
+STATUS = {0: "VX_OK", -1: "VX_E_INVALID", -2: "VX_E_OOM", -3: "VX_E_CUDA", -4: "VX_E_UNSUPPORTED",
+          -5: "VX_E_BOUNDS", -6: "VX_E_BUDGET", -7: "VX_E_POISONED"}
+
+STATS_FIELDS = [
+    "requested_budget", "actual_budget", "node_size", "nodes_capacity", "total_allocations",
+    "total_deallocations", "allocated_nodes", "recycled_nodes", "alive_nodes", "patterns",
+    "total_cache_hits", "total_cache_misses", "branch_cache_hits", "branch_cache_misses",
+    "leaf_cache_hits", "leaf_cache_misses", "collapsed_branches", "leaf_nodes", "branch_nodes",
+    "max_alive_nodes", "max_node_id", "max_branch_ref_count", "max_leaf_ref_count",
+    "max_generation", "generations_overflows",
+]
+
+# every symbol include/voxelis_b200.h declares (checked by tests/test_abi.py)
+ABI_SYMBOLS = [
+    "vx_last_error", "vx_abi_version", "vx_device_count", "vx_interner_create", "vx_interner_destroy",
+    "vx_interner_reset", "vx_interner_capacity", "vx_interner_dtype", "vx_interner_device",
+    "vx_interner_next_index", "vx_interner_get_ref", "vx_interner_get_value", "vx_interner_get_children",
+    "vx_interner_stats", "vx_interner_download", "vx_interner_sync", "vx_interner_stream",
+    "vx_batch_create", "vx_batch_destroy", "vx_batch_set", "vx_batch_fill", "vx_batch_clear",
+    "vx_batch_masks", "vx_batch_values", "vx_batch_blocks", "vx_batch_to_fill", "vx_batch_size",
+    "vx_batch_has_patches", "vx_batch_mark_patched", "vx_batch_max_depth", "vx_batch_dtype",
+    "vx_tree_create", "vx_tree_destroy", "vx_tree_root_id", "vx_tree_set_root_id", "vx_tree_max_depth",
+    "vx_tree_voxels_per_axis", "vx_tree_is_empty", "vx_tree_is_leaf", "vx_tree_is_dirty",
+    "vx_tree_mark_dirty", "vx_tree_clear_dirty", "vx_tree_apply_batch", "vx_apply_batches",
+    "vx_apply_batches_slab", "vx_apply_batches_device", "vx_tree_get", "vx_tree_get_many",
+    "vx_tree_to_vec", "vx_roots_to_vec", "vx_tree_fill", "vx_tree_clear",
+]
+
+
+class VoxelisError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"{STATUS.get(code, code)}: {msg}")
+        self.code = code
+
+
+def lib():
+    """Loads libvoxelis_b200.so; fails loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise ImportError(
+            f"{_LIB_PATH} is missing: build it with `python -m voxelis_b200.build` "
+            "(nvcc, sm_100a). voxelis_b200 has no CPU fallback.")
+    L = C.CDLL(_LIB_PATH)
+    vp, sz, i64, u64 = C.c_void_p, C.c_size_t, C.c_int64, C.c_uint64
+    L.vx_last_error.restype = C.c_char_p
+    L.vx_interner_create.restype = vp
+    L.vx_interner_create.argtypes = [sz, C.c_int, C.c_int]
+    L.vx_interner_destroy.argtypes = [vp]
+    L.vx_interner_destroy.restype = None
+    L.vx_interner_reset.argtypes = [vp]
+    L.vx_interner_capacity.restype = sz
+    L.vx_interner_capacity.argtypes = [vp]
+    L.vx_interner_dtype.argtypes = [vp]
+    L.vx_interner_device.argtypes = [vp]
+    L.vx_interner_next_index.restype = i64
+    L.vx_interner_next_index.argtypes = [vp]
+    L.vx_interner_get_ref.argtypes = [vp, u64, vp]
+    L.vx_interner_get_value.argtypes = [vp, u64, vp]
+    L.vx_interner_get_children.argtypes = [vp, u64, vp]
+    L.vx_interner_stats.argtypes = [vp, vp]
+    L.vx_interner_debug_counters.argtypes = [vp, vp]
+    L.vx_interner_download.restype = i64
+    L.vx_interner_download.argtypes = [vp, sz, vp, vp, vp, vp, vp]
+    L.vx_interner_sync.argtypes = [vp]
+    L.vx_interner_stream.restype = vp
+    L.vx_interner_stream.argtypes = [vp]
+    L.vx_batch_create.restype = vp
+    L.vx_batch_create.argtypes = [C.c_uint8, C.c_int]
+    L.vx_batch_destroy.argtypes = [vp]
+    L.vx_batch_destroy.restype = None
+    L.vx_batch_set.argtypes = [vp, C.c_int, C.c_int, C.c_int, i64]
+    L.vx_batch_fill.argtypes = [vp, i64]
+    L.vx_batch_clear.argtypes = [vp]
+    L.vx_batch_masks.restype = vp
+    L.vx_batch_masks.argtypes = [vp]
+    L.vx_batch_values.restype = vp
+    L.vx_batch_values.argtypes = [vp]
+    L.vx_batch_blocks.restype = sz
+    L.vx_batch_blocks.argtypes = [vp]
+    L.vx_batch_to_fill.argtypes = [vp, vp]
+    L.vx_batch_size.restype = sz
+    L.vx_batch_size.argtypes = [vp]
+    L.vx_batch_has_patches.argtypes = [vp]
+    L.vx_batch_mark_patched.argtypes = [vp]
+    L.vx_batch_mark_patched.restype = None
+    L.vx_batch_max_depth.restype = C.c_uint8
+    L.vx_batch_max_depth.argtypes = [vp]
+    L.vx_batch_dtype.argtypes = [vp]
+    L.vx_tree_create.restype = vp
+    L.vx_tree_create.argtypes = [C.c_uint8]
+    L.vx_tree_destroy.argtypes = [vp]
+    L.vx_tree_destroy.restype = None
+    L.vx_tree_root_id.restype = u64
+    L.vx_tree_root_id.argtypes = [vp]
+    L.vx_tree_set_root_id.argtypes = [vp, vp, u64]
+    L.vx_tree_max_depth.restype = C.c_uint8
+    L.vx_tree_max_depth.argtypes = [vp]
+    L.vx_tree_voxels_per_axis.restype = C.c_uint32
+    L.vx_tree_voxels_per_axis.argtypes = [vp]
+    for f in ("vx_tree_is_empty", "vx_tree_is_leaf", "vx_tree_is_dirty"):
+        getattr(L, f).argtypes = [vp]
+    L.vx_tree_mark_dirty.argtypes = [vp]
+    L.vx_tree_mark_dirty.restype = None
+    L.vx_tree_clear_dirty.argtypes = [vp]
+    L.vx_tree_clear_dirty.restype = None
+    L.vx_tree_apply_batch.argtypes = [vp, vp, vp]
+    L.vx_apply_batches.argtypes = [vp, vp, vp, sz, vp]
+    L.vx_apply_batches_slab.argtypes = [vp, C.c_uint8, sz, vp, vp, vp, vp, vp, vp]
+    L.vx_apply_batches_device.argtypes = [vp, C.c_uint8, sz, vp, vp, vp, vp, vp, vp, vp]
+    L.vx_tree_get.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp]
+    L.vx_tree_get_many.argtypes = [vp, vp, sz, vp, vp, vp]
+    L.vx_tree_to_vec.argtypes = [vp, vp, vp]
+    L.vx_roots_to_vec.argtypes = [vp, C.c_uint8, sz, vp, vp]
+    L.vx_tree_fill.argtypes = [vp, vp, i64]
+    L.vx_tree_clear.argtypes = [vp, vp]
+    _lib = L
+    return L
+
+
+def _err(code: int):
+    raise VoxelisError(code, lib().vx_last_error().decode())
+
+
+def _ck(code: int) -> int:
+    if code < 0:
+        _err(code)
+    return code
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def device_count() -> int:
+    return lib().vx_device_count()
+
+
+def id_index(i): return int(i) & 0xFFFFFFFF
+def id_gen(i): return (int(i) >> 32) & 0x7FFF
+def id_is_leaf(i): return (int(i) >> 63) == 1
+def id_is_branch(i): return (int(i) >> 63) == 0
+def id_types(i): return (int(i) >> 55) & 0xFF
+def id_mask(i): return (int(i) >> 47) & 0xFF
+
+
+class VoxInterner:
+    """VoxInterner<T> — reference voxelis/src/interner/mod.rs:25-40,45-155."""
+
+    def __init__(self, budget: int, dtype: int = U8, device: int = 0):
+        self.dtype = dtype
+        self.h = lib().vx_interner_create(budget, dtype, device)
+        if not self.h:
+            raise VoxelisError(-6, lib().vx_last_error().decode())
+
+    @classmethod
+    def with_memory_budget(cls, budget: int, dtype: int = U8, device: int = 0):
+        return cls(budget, dtype, device)
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().vx_interner_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self): _ck(lib().vx_interner_reset(self.h))
+    def sync(self): _ck(lib().vx_interner_sync(self.h))
+    @property
+    def capacity(self) -> int: return lib().vx_interner_capacity(self.h)
+    @property
+    def next_index(self) -> int: return _ck(lib().vx_interner_next_index(self.h))
+    @property
+    def stream(self) -> int: return lib().vx_interner_stream(self.h) or 0
+
+    def get_ref(self, block_id: int) -> int:
+        out = C.c_uint32(0)
+        _ck(lib().vx_interner_get_ref(self.h, int(block_id), C.byref(out)))
+        return out.value
+
+    def get_value(self, block_id: int) -> int:
+        out = C.c_int64(0)
+        _ck(lib().vx_interner_get_value(self.h, int(block_id), C.byref(out)))
+        return out.value
+
+    def get_children(self, block_id: int):
+        out = np.zeros(8, np.uint64)
+        _ck(lib().vx_interner_get_children(self.h, int(block_id), _ptr(out)))
+        return out
+
+    def stats(self) -> dict:
+        a = np.zeros(len(STATS_FIELDS), np.uint64)
+        _ck(lib().vx_interner_stats(self.h, _ptr(a)))
+        return {k: int(v) for k, v in zip(STATS_FIELDS, a)}
+
+    def debug_counters(self) -> dict:
+        a = np.zeros(8, np.uint64)
+        _ck(lib().vx_interner_debug_counters(self.h, _ptr(a)))
+        keys = ["leaf_calls", "branch_calls", "leaf_misses", "branch_misses", "collapsed", "probe_steps",
+                "cache_hits_local", "recycled"]
+        return {k: int(v) for k, v in zip(keys, a)}
+
+    def download(self) -> dict:
+        n = self.next_index
+        ch = np.zeros((n, 8), np.uint64)
+        va = np.zeros(n, np.int64)
+        rf = np.zeros(n, np.uint32)
+        ge = np.zeros(n, np.uint16)
+        hs = np.zeros(n, np.uint64)
+        got = _ck(lib().vx_interner_download(self.h, n, _ptr(ch), _ptr(va), _ptr(rf), _ptr(ge), _ptr(hs)))
+        assert got == n
+        return {"children": ch, "values": va, "refs": rf, "gens": ge, "hashes": hs, "n": n}
+
+    # ---- multi-chunk slab entry (new; replaces the serial loop voxelis-voxelize/src/lib.rs:357-361)
+    def apply_batches_slab(self, depth: int, masks, values, flags=None, fills=None, n=None,
+                           roots_out=None, changed_out=None):
+        """masks/values: numpy arrays [n][B][2] / [n][B][8] (host) or integer device pointers
+        (then ``n`` is required).  Returns (roots, changed) as numpy arrays unless device
+        outputs were supplied."""
+        if isinstance(masks, np.ndarray):
+            n = masks.shape[0]
+            masks = np.ascontiguousarray(masks, np.uint8)
+            values = np.ascontiguousarray(values, _NP[self.dtype])
+        assert n is not None
+        if flags is not None and isinstance(flags, np.ndarray):
+            flags = np.ascontiguousarray(flags, np.uint8)
+        if fills is not None and isinstance(fills, np.ndarray):
+            fills = np.ascontiguousarray(fills, np.int64)
+        roots = np.zeros(n, np.uint64) if roots_out is None else roots_out
+        changed = np.zeros(n, np.uint8) if changed_out is None else changed_out
+        _ck(lib().vx_apply_batches_slab(self.h, depth, n, _ptr(masks), _ptr(values), _ptr(flags), _ptr(fills),
+                                        _ptr(roots), _ptr(changed)))
+        return roots, changed
+
+    def apply_batches_device(self, depth: int, n: int, d_masks: int, d_values: int, d_roots: int,
+                             d_changed: int = 0, d_flags: int = 0, d_fills: int = 0, stream: int = 0):
+        """Asynchronous, device pointers only (see vx_apply_batches_device)."""
+        _ck(lib().vx_apply_batches_device(self.h, depth, n, C.c_void_p(d_masks), C.c_void_p(d_values),
+                                          C.c_void_p(d_flags or None), C.c_void_p(d_fills or None),
+                                          C.c_void_p(d_roots), C.c_void_p(d_changed or None),
+                                          C.c_void_p(stream or None)))
+
+    def roots_to_vec(self, roots, depth: int):
+        roots = np.ascontiguousarray(roots, np.uint64)
+        n = 1 << depth
+        out = np.zeros((len(roots), n, n, n), _NP[self.dtype])  # [r][y][z][x]
+        _ck(lib().vx_roots_to_vec(self.h, depth, len(roots), _ptr(roots), _ptr(out)))
+        return out
+
+
+class Batch:
+    """Batch<T> — reference voxelis/src/core/batch.rs:39-45."""
+
+    def __init__(self, max_depth: int, dtype: int = U8):
+        self.max_depth, self.dtype = max_depth, dtype
+        self.h = lib().vx_batch_create(max_depth, dtype)
+        if not self.h:
+            raise VoxelisError(-1, lib().vx_last_error().decode())
+        B = lib().vx_batch_blocks(self.h)
+        self.masks = np.ctypeslib.as_array(C.cast(lib().vx_batch_masks(self.h), C.POINTER(C.c_uint8)), (B, 2))
+        ct = C.c_uint8 if dtype == U8 else C.c_int32
+        self.values = np.ctypeslib.as_array(C.cast(lib().vx_batch_values(self.h), C.POINTER(ct)), (B, 8))
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.masks = self.values = None
+                lib().vx_batch_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def set(self, interner, pos, v) -> bool:          # batch.rs:211-213
+        return _ck(lib().vx_batch_set(self.h, int(pos[0]), int(pos[1]), int(pos[2]), int(v))) == 1
+
+    def fill(self, interner, v): _ck(lib().vx_batch_fill(self.h, int(v)))   # batch.rs:218-221
+    def clear(self, interner=None): _ck(lib().vx_batch_clear(self.h))       # batch.rs:223-225
+    def size(self) -> int: return lib().vx_batch_size(self.h)
+    def mark_patched(self): lib().vx_batch_mark_patched(self.h)
+
+    @property
+    def has_patches(self) -> bool: return bool(lib().vx_batch_has_patches(self.h))
+
+    @property
+    def to_fill(self):
+        out = C.c_int64(0)
+        return out.value if _ck(lib().vx_batch_to_fill(self.h, C.byref(out))) == 1 else None
+
+
+class VoxTree:
+    """VoxTree<T> — reference voxelis/src/spatial/voxtree.rs:108-142."""
+
+    def __init__(self, max_depth: int, dtype: int = U8):
+        self.max_depth, self.dtype = max_depth, dtype
+        self.h = lib().vx_tree_create(max_depth)
+        if not self.h:
+            raise VoxelisError(-1, lib().vx_last_error().decode())
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                lib().vx_tree_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def create_batch(self) -> Batch: return Batch(self.max_depth, self.dtype)   # voxtree.rs:296-301
+
+    def apply_batch(self, interner: VoxInterner, batch: Batch) -> bool:        # voxtree.rs:303-328
+        return _ck(lib().vx_tree_apply_batch(interner.h, self.h, batch.h)) == 1
+
+    def get(self, interner: VoxInterner, pos):                                  # voxtree.rs:144-160
+        out = C.c_int64(0)
+        rc = _ck(lib().vx_tree_get(interner.h, self.h, int(pos[0]), int(pos[1]), int(pos[2]), C.byref(out)))
+        return out.value if rc == 1 else None
+
+    def get_many(self, interner: VoxInterner, xyz: np.ndarray):
+        xyz = np.ascontiguousarray(xyz, np.int32)
+        n = xyz.shape[0]
+        found = np.zeros(n, np.uint8)
+        vals = np.zeros(n, np.int64)
+        _ck(lib().vx_tree_get_many(interner.h, self.h, n, _ptr(xyz), _ptr(found), _ptr(vals)))
+        return found, vals
+
+    def to_vec(self, interner: VoxInterner):                                    # utils/common.rs:158-246
+        n = 1 << self.max_depth
+        out = np.zeros((n, n, n), _NP[interner.dtype])  # [y][z][x]
+        _ck(lib().vx_tree_to_vec(interner.h, self.h, _ptr(out)))
+        return out
+
+    def fill(self, interner, v): _ck(lib().vx_tree_fill(interner.h, self.h, int(v)))
+    def clear(self, interner): _ck(lib().vx_tree_clear(interner.h, self.h))
+    def get_root_id(self) -> int: return lib().vx_tree_root_id(self.h)
+    def is_empty(self) -> bool: return bool(lib().vx_tree_is_empty(self.h))
+    def is_leaf(self) -> bool: return bool(lib().vx_tree_is_leaf(self.h))
+    def is_dirty(self) -> bool: return bool(lib().vx_tree_is_dirty(self.h))
+    def mark_dirty(self): lib().vx_tree_mark_dirty(self.h)
+    def clear_dirty(self): lib().vx_tree_clear_dirty(self.h)
+    def voxels_per_axis(self) -> int: return lib().vx_tree_voxels_per_axis(self.h)
+
+
+def apply_batches(interner: VoxInterner, trees, batches):
+    """New multi-chunk entry (vx_apply_batches): result == serial application in index order."""
+    n = len(trees)
+    assert n == len(batches)
+    th = (C.c_void_p * n)(*[t.h for t in trees])
+    bh = (C.c_void_p * n)(*[b.h for b in batches])
+    changed = np.zeros(n, np.uint8)
+    _ck(lib().vx_apply_batches(interner.h, th, bh, n, _ptr(changed)))
+    return changed.astype(bool)

@@ -1,0 +1,890 @@
+// vx_build.cuh — fresh-tree apply_batch(es) kernels (sm_100a).
+//
+// Replaces, for trees whose root is EMPTY (the north-star path):
+//   VoxTree::apply_batch                 spatial/voxtree.rs:303-328
+//   set_batch_at_depth_iterative         spatial/voxtree.rs:724-1118   (phases 0 / 1 / 2)
+//   VoxInterner::get_or_create_leaf      interner/mod.rs:627-710
+//   VoxInterner::get_or_create_branch    interner/mod.rs:716-829  (+ calc_average core/voxel.rs:96-141)
+//
+// What the reference's three phases reduce to on a fresh tree: the result is the
+// canonical bottom-up DAG of the batch's effective volume,
+//     block (depth D-1)  = EMPTY | Leaf(v) if set_mask==0xFF and 8 equal values | Branch(8 leaves/EMPTY)
+//     parent             = absent if no child entered `paths`
+//                        | that Leaf if types==0xFF and 8 identical ids (uniform collapse, :1050)
+//                        | Branch(children) interned on the 8 child ids (level-agnostic table)
+// so every level is a pure function of the level below and the work maps onto warps:
+//
+//   * a warp owns a Morton-contiguous run of <= 512 blocks (a 16^3-voxel sub-cube; Batch arrays are
+//     Morton ordered, core/batch.rs:153-157).  Lane = block at depth D-1: one 8-byte (u8) or
+//     2x16-byte (i32) coalesced load per lane, collapse / fill / skip decisions in registers.
+//   * eight consecutive lanes are siblings, so the parent key (8 child ids) already sits one child
+//     per lane: hashing is a 3-step shuffle reduction, key comparison is one ballot, and the node's
+//     64-byte children row is read / written coalesced by the 8-lane group.
+//   * duplicate detection runs warp -> shared memory -> HBM: __match_any_sync on the block value
+//     word, per-warp direct-mapped caches in shared memory (block word -> id, children[8] -> id),
+//     and only then the global open-addressing table (bucket of 8 slots = 64 B, probed by the
+//     8-lane group with one ballot).
+//   * refcount = in-degree: +1 per child slot only when a NEW unique branch is created, +1 per
+//     tree root; u8 leaf increments are histogrammed in shared memory and flushed once per CTA.
+//
+// All warp collectives below execute in warp-uniform control flow; per-group work is predicated.
+#pragma once
+#include "vx_device.cuh"
+
+namespace vx {
+
+constexpr int WARPS_PER_CTA = 8;
+constexpr int CTA_THREADS = WARPS_PER_CTA * 32;
+constexpr int UNIT_BLOCKS = 512;  // blocks per warp work unit
+constexpr int UC = 32;            // per-warp parent-cache entries (children[8] -> id)
+
+#define VX_FLAG_FILL 1u
+#define VX_FLAG_PATCHES 2u
+
+// ------------------------------------------------------------------------------------------------
+// Value-type traits: how a lane holds the 8 values of its block.
+// ------------------------------------------------------------------------------------------------
+template <class T>
+struct VT;
+
+__device__ __forceinline__ u32 nzbytes(u64 x) {  // bit i set iff byte i != 0
+    u64 y = (((x & 0x7F7F7F7F7F7F7F7Full) + 0x7F7F7F7F7F7F7F7Full) | x) & 0x8080808080808080ull;
+    return u32(((y >> 7) * 0x0102040810204080ull) >> 56);
+}
+__device__ __forceinline__ u64 expand_bits(u32 m) {  // bit i -> byte i = 0xFF
+    u64 x = (u64(m) * 0x0101010101010101ull) & 0x8040201008040201ull;
+    x = ((x + 0x7F7F7F7F7F7F7F7Full) & 0x8080808080808080ull) >> 7;
+    return x * 0xFFull;
+}
+
+template <>
+struct VT<u8> {
+    static constexpr int KW = 1;
+    static constexpr int BC = 128;  // per-warp block-cache entries
+    struct Key {
+        u64 w[1];
+    };
+    static __device__ __forceinline__ Key load(const void* values, size_t block) {
+        Key k;
+        k.w[0] = ld_stream_u64((const u8*)values + block * 8);
+        return k;
+    }
+    static __device__ __forceinline__ Key zero() { return Key{{0}}; }
+    static __device__ __forceinline__ u32 nz(const Key& k) { return nzbytes(k.w[0]); }
+    static __device__ __forceinline__ u32 first(const Key& k) { return u32(k.w[0] & 0xFF); }
+    static __device__ __forceinline__ bool uniform(const Key& k) {
+        return k.w[0] == (k.w[0] & 0xFF) * 0x0101010101010101ull;
+    }
+    static __device__ __forceinline__ u32 ne_mask(const Key& k, u32 f) {  // bits where value != f
+        return nzbytes(k.w[0] ^ (u64(f) * 0x0101010101010101ull));
+    }
+    static __device__ __forceinline__ Key select(const Key& k, u32 m, u32 f) {  // set ? value : f
+        u64 bm = expand_bits(m);
+        return Key{{(k.w[0] & bm) | ((u64(f) * 0x0101010101010101ull) & ~bm)}};
+    }
+    static __device__ __forceinline__ bool eq(const Key& a, const Key& b) { return a.w[0] == b.w[0]; }
+    static __device__ __forceinline__ u32 hash(const Key& k) { return u32(mix64(k.w[0]) >> 32); }
+    // value of child `li` of the key held by lane `src` (full-warp shuffle)
+    static __device__ __forceinline__ u32 bcast_value(const Key& k, int src, int li) {
+        u64 w = __shfl_sync(FULL, k.w[0], src);
+        return u32(w >> (8 * li)) & 0xFF;
+    }
+    static __device__ __forceinline__ Key bcast(const Key& k, int src) {
+        return Key{{__shfl_sync(FULL, k.w[0], src)}};
+    }
+};
+
+template <>
+struct VT<int32_t> {
+    static constexpr int KW = 4;
+    static constexpr int BC = 32;
+    struct Key {
+        u64 w[4];
+    };
+    static __device__ __forceinline__ Key load(const void* values, size_t block) {
+        const uint4* p = (const uint4*)((const u8*)values + block * 32);
+        uint4 a = ld_stream_v4(p), b = ld_stream_v4(p + 1);
+        Key k;
+        k.w[0] = u64(a.x) | (u64(a.y) << 32);
+        k.w[1] = u64(a.z) | (u64(a.w) << 32);
+        k.w[2] = u64(b.x) | (u64(b.y) << 32);
+        k.w[3] = u64(b.z) | (u64(b.w) << 32);
+        return k;
+    }
+    static __device__ __forceinline__ Key zero() { return Key{{0, 0, 0, 0}}; }
+    static __device__ __forceinline__ u32 get(const Key& k, int i) { return u32(k.w[i >> 1] >> (32 * (i & 1))); }
+    static __device__ __forceinline__ u32 nz(const Key& k) {
+        u32 m = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) m |= u32(get(k, i) != 0) << i;
+        return m;
+    }
+    static __device__ __forceinline__ u32 first(const Key& k) { return u32(k.w[0]); }
+    static __device__ __forceinline__ bool uniform(const Key& k) {
+        u64 f = u64(u32(k.w[0])) * 0x0000000100000001ull;
+        return k.w[0] == f && k.w[1] == f && k.w[2] == f && k.w[3] == f;
+    }
+    static __device__ __forceinline__ u32 ne_mask(const Key& k, u32 f) {
+        u32 m = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) m |= u32(get(k, i) != f) << i;
+        return m;
+    }
+    static __device__ __forceinline__ Key select(const Key& k, u32 m, u32 f) {
+        Key r;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            u32 lo = (m >> (2 * j)) & 1 ? u32(k.w[j]) : f;
+            u32 hi = (m >> (2 * j + 1)) & 1 ? u32(k.w[j] >> 32) : f;
+            r.w[j] = u64(lo) | (u64(hi) << 32);
+        }
+        return r;
+    }
+    static __device__ __forceinline__ bool eq(const Key& a, const Key& b) {
+        return a.w[0] == b.w[0] && a.w[1] == b.w[1] && a.w[2] == b.w[2] && a.w[3] == b.w[3];
+    }
+    static __device__ __forceinline__ u32 hash(const Key& k) {
+        return u32(mix64(k.w[0] + mix64(k.w[1] + mix64(k.w[2] + mix64(k.w[3])))) >> 32);
+    }
+    static __device__ __forceinline__ Key bcast(const Key& k, int src) {
+        Key r;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) r.w[j] = __shfl_sync(FULL, k.w[j], src);
+        return r;
+    }
+    static __device__ __forceinline__ u32 bcast_value(const Key& k, int src, int li) {
+        Key r = bcast(k, src);
+        u64 w = (li >> 1) == 0 ? r.w[0] : (li >> 1) == 1 ? r.w[1] : (li >> 1) == 2 ? r.w[2] : r.w[3];
+        return u32(w >> (32 * (li & 1)));
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Shared memory
+// ------------------------------------------------------------------------------------------------
+constexpr int LC = 64;  // per-warp leaf cache entries (wide T only)
+
+template <class T>
+struct WarpSmem {
+    u64 bkey[VT<T>::BC * VT<T>::KW];  // block value words -> id
+    u64 bval[VT<T>::BC];
+    u64 ukey[UC * 8];  // children[8] -> id
+    u64 uval[UC];
+    u64 l1[64];  // ids of the unit's level-1 parents (64), level-2 (8)
+    u64 l2[8];
+    u32 l1p[2];  // "entered paths" bits
+    u32 l2p;
+    u32 lkey[sizeof(T) == 1 ? 1 : LC];  // wide T only: value -> leaf id
+    u64 lid[sizeof(T) == 1 ? 1 : LC];
+};
+struct CtaSmem {
+    u64 leaf[256];     // u8: value -> leaf id (lazy copy of InternerDev::leaf_u8)
+    u32 leafref[256];  // u8: pending in-degree increments of leaves
+    u64 oct[8];        // unit results of the current 32^3 super-unit
+    u32 octp[8];
+    u64 top[64];       // super-unit results (D = 6: 8, D = 7: 64)
+    u32 topp[64];
+};
+
+struct Tally {  // per-lane statistics, reduced once at kernel exit
+    u32 leaf_calls = 0, branch_calls = 0, leaf_miss = 0, branch_miss = 0, collapsed = 0, probes = 0, local = 0;
+};
+
+template <class T>
+struct Ctx {
+    InternerDev in;
+    WarpSmem<T>* ws;
+    CtaSmem* cs;
+    int lane, li, gs;  // lane, lane within 8-group, first lane of my group
+    Tally t;
+};
+
+// ------------------------------------------------------------------------------------------------
+// Leaves — get_or_create_leaf (interner/mod.rs:627-710).  Warp-converged; `need` predicates lanes.
+// ------------------------------------------------------------------------------------------------
+template <class T>
+__device__ __forceinline__ void leaf_payload(const InternerDev& in, u32 idx, u32 v) {
+    ((T*)in.values)[idx] = T(v);
+    in.hashes[idx] = leaf_hash(v);
+}
+
+__device__ inline u64 leaf_get(Ctx<u8>& c, u32 v, bool need) {
+    need = need && v != 0;
+    u64 id = need ? c.cs->leaf[v] : 0;
+    bool miss = need && id == 0;
+    while (__any_sync(FULL, miss)) {
+        if (miss) {
+            u64 g = ld_strong(&c.in.leaf_u8[v]);
+            if (g == 0) {
+                u64 old = atomicCAS((ull*)&c.in.leaf_u8[v], 0ull, (ull)ID_PENDING);
+                if (old == 0) {  // this lane creates the leaf
+                    u32 idx = atomicAdd(c.in.next_index, 1u);
+                    if (idx >= c.in.capacity) {
+                        set_error(c.in, ERR_OOM);
+                        st_strong(&c.in.leaf_u8[v], 0);
+                        miss = false;
+                    } else {
+                        leaf_payload<u8>(c.in, idx, v);
+                        id = id_leaf(u64(idx));  // fresh index: generation 0
+                        fence_gpu();
+                        st_strong(&c.in.leaf_u8[v], id);
+                        c.cs->leaf[v] = id;
+                        c.t.leaf_miss++;
+                        miss = false;
+                    }
+                }
+            } else if (g != ID_PENDING) {
+                id = g;
+                c.cs->leaf[v] = g;
+                miss = false;
+            }
+        }
+    }
+    return id;
+}
+
+__device__ inline u64 leaf_get(Ctx<int32_t>& c, u32 v, bool need) {
+    need = need && v != 0;
+    u32 e = (v * 0x9E3779B1u) >> 26;  // LC = 64
+    u64 id = 0;
+    bool miss = need;
+    if (need && c.ws->lkey[e] == v) {
+        id = c.ws->lid[e];
+        miss = id == 0;
+    }
+    bool from_global = miss;
+    u64 mykey = u64(v) | (1ull << 32);
+    u32 s = u32(leaf_hash(v)) & c.in.leaf_mask;
+    int guard = 0;
+    while (__any_sync(FULL, miss)) {
+        if (miss) {
+            u64 k = ld_strong(&c.in.leaf_keys[s]);
+            if (k == 0) {
+                u64 old = atomicCAS((ull*)&c.in.leaf_keys[s], 0ull, (ull)mykey);
+                if (old == 0) {
+                    u32 idx = atomicAdd(c.in.next_index, 1u);
+                    if (idx >= c.in.capacity) {
+                        set_error(c.in, ERR_OOM);
+                        miss = false;
+                    } else {
+                        leaf_payload<int32_t>(c.in, idx, v);
+                        id = id_leaf(u64(idx));
+                        fence_gpu();
+                        st_strong(&c.in.leaf_ids[s], id);
+                        c.t.leaf_miss++;
+                        miss = false;
+                    }
+                } else if (old != mykey) {
+                    s = (s + 1) & c.in.leaf_mask;
+                }
+            } else if (k == mykey) {
+                u64 g = ld_strong(&c.in.leaf_ids[s]);
+                if (g != 0) {
+                    id = g;
+                    miss = false;
+                }
+            } else {
+                s = (s + 1) & c.in.leaf_mask;
+                if (++guard > (1 << 22)) {
+                    set_error(c.in, ERR_TABLE_FULL);
+                    miss = false;
+                }
+            }
+        }
+    }
+    // refresh the per-warp cache; one writer per entry (match on e) keeps key/id pairs untorn
+    u32 wmask = __ballot_sync(FULL, from_global && id != 0);
+    if (from_global && id != 0) {
+        u32 same = __match_any_sync(wmask, e);
+        if ((__ffs(same) - 1) == c.lane) {
+            c.ws->lkey[e] = v;
+            c.ws->lid[e] = id;
+        }
+    }
+    __syncwarp();
+    return id;
+}
+
+template <class T>
+__device__ __forceinline__ u32 child_value(const InternerDev& in, u64 child);
+template <>
+__device__ __forceinline__ u32 child_value<u8>(const InternerDev& in, u64 child) {
+    return ld_strong_u8((const u8*)in.values + id_index(child));
+}
+template <>
+__device__ __forceinline__ u32 child_value<int32_t>(const InternerDev& in, u64 child) {
+    return ld_strong((const u32*)in.values + id_index(child));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Branches — get_or_create_branch (interner/mod.rs:716-829) for up to four keys per warp, one per
+// 8-lane group, child i of the key in lane gs+i.  Returns the branch id to every lane of a group
+// with need == true.  `cval` = value of the lane's child when BLOCK_LEVEL (children are voxels).
+// ------------------------------------------------------------------------------------------------
+template <class T, bool BLOCK_LEVEL>
+__device__ inline u64 intern_branch(Ctx<T>& c, bool need, u64 child, u32 cval) {
+    const int li = c.li, gs = c.gs, lane = c.lane;
+    const InternerDev& in = c.in;
+    // types / mask are functions of the children (voxtree.rs:846-863, :959-1000)
+    u32 leafb = (__ballot_sync(FULL, id_is_leaf(child)) >> gs) & 0xFF;
+    u32 presb = (__ballot_sync(FULL, child != 0) >> gs) & 0xFF;
+    u64 h = child_hash(child, li);
+    h += __shfl_xor_sync(FULL, h, 1);
+    h += __shfl_xor_sync(FULL, h, 2);
+    h += __shfl_xor_sync(FULL, h, 4);
+    h = finish_hash(h);
+    const u32 fp = u32(h >> 47);
+    u32 bucket = u32(h) & in.bucket_mask;
+
+    u64 result = 0;
+    bool done = !need;
+    // ---- per-warp parent cache (upper levels; the block level has its own value-keyed cache)
+    const u32 ue = u32(h >> 32) & (UC - 1);
+    if (!BLOCK_LEVEL) {
+        u64 ck = c.ws->ukey[ue * 8 + li];
+        u32 eqb = (__ballot_sync(FULL, need && ck == child) >> gs) & 0xFF;
+        if (need && eqb == 0xFF) {
+            result = c.ws->uval[ue];
+            done = true;
+            if (li == 0) c.t.local++;
+        }
+    }
+    const bool went_global = !done;
+    u32 skip = 0;
+    int guard = 0;
+    while (__any_sync(FULL, !done)) {
+        u64 slot = 0;
+        if (!done) slot = ld_strong(&in.slots[size_t(bucket) * 8 + li]);
+        const u32 lo = u32(slot);
+        bool fpm = !done && slot != 0 && lo != IDX_TOMB && u32(slot >> 47) == fp && !((skip >> li) & 1);
+        u32 mb = (__ballot_sync(FULL, fpm) >> gs) & 0xFF;
+        u32 eb = (__ballot_sync(FULL, !done && slot == 0) >> gs) & 0xFF;
+        if (!done && li == 0) c.t.probes++;
+        // -- candidate with matching fingerprint: compare the stored children row
+        const bool has_cand = mb != 0;
+        const int k = has_cand ? (__ffs(mb) - 1) : 0;
+        u64 cslot = __shfl_sync(FULL, slot, gs + k);
+        const bool cand_pending = u32(cslot) == IDX_PENDING;
+        const bool do_cmp = !done && has_cand && !cand_pending;
+        u64 stored = 0;
+        if (do_cmp) stored = ld_strong(&in.children[size_t(u32(cslot)) * 8 + li]);
+        u32 eqb = (__ballot_sync(FULL, do_cmp && stored == child) >> gs) & 0xFF;
+        if (do_cmp) {
+            if (eqb == 0xFF) {
+                result = id_branch(cslot, leafb, presb);  // hit
+                done = true;
+            } else {
+                skip |= 1u << k;
+            }
+        }
+        // -- no candidate: claim the first empty slot of the bucket, or move on
+        const bool want_claim = !done && !has_cand && eb != 0;
+        const int ek = want_claim ? (__ffs(eb) - 1) : 0;
+        bool claimed = false;
+        if (want_claim && li == 0) {
+            u64 old = atomicCAS((ull*)&in.slots[size_t(bucket) * 8 + ek], 0ull, (ull)((u64(fp) << 47) | IDX_PENDING));
+            claimed = old == 0;
+        }
+        const u32 cb = __ballot_sync(FULL, claimed);  // bits at lanes 0, 8, 16, 24
+        if (cb != 0) {                                // warp-uniform: someone creates a node
+            u32 base = 0;
+            if (lane == 0) base = atomicAdd(in.next_index, u32(__popc(cb)));
+            base = __shfl_sync(FULL, base, 0);
+            const bool mine = (cb >> gs) & 1;
+            const u32 idx = base + __popc(cb & ((1u << gs) - 1));
+            const bool oom = idx >= in.capacity;
+            // LOD value = mode of the child values (core/voxel.rs:96-141): most frequent; ties go to
+            // a non-default value, then to the earliest first occurrence.
+            u32 v = cval;
+            if (!BLOCK_LEVEL) v = (mine && !oom && child != 0) ? child_value<T>(in, child) : 0;
+            u32 mm = __match_any_sync(FULL, (u64(v) << 2) | u64(gs >> 3));
+            u32 gm = (mm >> gs) & 0xFF;
+            u32 score = (u32(__popc(gm)) << 8) | (u32(v != 0) << 7) | (u32(8 - __ffs(gm)) << 3) | u32(li);
+            u32 best = score;
+            best = max(best, __shfl_xor_sync(FULL, best, 1));
+            best = max(best, __shfl_xor_sync(FULL, best, 2));
+            best = max(best, __shfl_xor_sync(FULL, best, 4));
+            // the winning lane is the first occurrence of the mode value
+            u32 mode = __shfl_sync(FULL, v, gs + int(best & 7));
+            if (mine) {
+                if (oom) {
+                    set_error(in, ERR_OOM);
+                } else {
+                    in.children[size_t(idx) * 8 + li] = child;
+                    if (child != 0) {
+                        if (BLOCK_LEVEL && sizeof(T) == 1)
+                            atomicAdd(&c.cs->leafref[cval], 1u);
+                        else
+                            atomicAdd(&in.refs[id_index(child)], 1u);
+                    }
+                    if (li == 0) {
+                        ((T*)in.values)[idx] = T(mode);
+                        in.hashes[idx] = h;
+                        c.t.branch_miss++;
+                    }
+                }
+            }
+            __syncwarp();
+            if (mine) {
+                if (li == 0) {
+                    fence_gpu();
+                    st_strong(&in.slots[size_t(bucket) * 8 + ek],
+                              oom ? u64(IDX_TOMB) : ((u64(fp) << 47) | u64(idx)));
+                }
+                result = oom ? 0 : id_branch(u64(idx), leafb, presb);
+                done = true;
+            }
+        }
+        if (!done && !has_cand && eb == 0) {  // bucket full and no match: next bucket
+            bucket = (bucket + 1) & in.bucket_mask;
+            skip = 0;
+            if (++guard > (1 << 22)) {
+                set_error(in, ERR_TABLE_FULL);
+                done = true;
+            }
+        }
+    }
+    if (!BLOCK_LEVEL) {
+        // refresh the parent cache; among groups mapping to the same entry only the lowest writes,
+        // so an entry is never a mix of two keys
+        bool wr = went_global && result != 0;
+        u32 wb = __ballot_sync(FULL, wr && li == 0);
+        bool write = wr;
+#pragma unroll
+        for (int g2 = 0; g2 < 3; ++g2) {
+            u32 e2 = __shfl_sync(FULL, ue, g2 * 8);
+            if (((wb >> (g2 * 8)) & 1) && g2 * 8 < gs && e2 == ue) write = false;
+        }
+        if (write) {
+            c.ws->ukey[ue * 8 + li] = child;
+            if (li == 0) c.ws->uval[ue] = result;
+        }
+        __syncwarp();
+    }
+    return result;
+}
+
+// ------------------------------------------------------------------------------------------------
+// One level of phase 2 (voxtree.rs:905-1106) for four parents per warp: lanes gs..gs+7 hold the
+// eight child ids (absent children already replaced by Leaf(fill) / EMPTY).  `present` = the child
+// entered `paths`.  Returns the parent id to all lanes of the group; *ppresent = parent entered paths.
+// ------------------------------------------------------------------------------------------------
+template <class T>
+__device__ inline u64 parent_node(Ctx<T>& c, u64 child, bool present, bool* ppresent) {
+    const int gs = c.gs;
+    u64 c0 = __shfl_sync(FULL, child, gs);
+    u32 same = (__ballot_sync(FULL, child == c0) >> gs) & 0xFF;
+    u32 pres = (__ballot_sync(FULL, present) >> gs) & 0xFF;
+    const bool any_present = pres != 0;
+    // all eight EMPTY -> nothing there; all eight the same Leaf -> uniform collapse (:1050, :1062-1075)
+    const bool collapse = same == 0xFF && (c0 == 0 || id_is_leaf(c0));
+    if (any_present && c.li == 0) {
+        if (collapse)
+            c.t.collapsed++;
+        else
+            c.t.branch_calls++;
+    }
+    u64 id = intern_branch<T, false>(c, any_present && !collapse, child, 0);
+    if (collapse || !any_present) id = c0;  // absent parent: all children are the same filler
+    *ppresent = any_present;
+    return id;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Phase 1 (voxtree.rs:770-897) for 32 blocks per warp, one per lane.
+// ------------------------------------------------------------------------------------------------
+template <class T>
+__device__ inline u64 block_node(Ctx<T>& c, bool active, typename VT<T>::Key vals, u32 set_mask, bool has_fill,
+                                 u32 fill, u64 fill_leaf, bool* present) {
+    using V = VT<T>;
+    const int lane = c.lane;
+    // a set bit whose value is the default cannot come from Batch::set (batch.rs:162-168): ignored
+    u32 m = active ? (set_mask & V::nz(vals)) : 0;
+    const bool all_same = m == 0xFF && V::uniform(vals);               // :826
+    const u32 changed_bits = has_fill ? (m & V::ne_mask(vals, fill)) : m;  // :853-856 skip unchanged
+    const bool touched = all_same || changed_bits != 0;                // :865-868
+    *present = touched;
+    const bool need_branch = touched && !all_same;
+    typename V::Key eff = V::select(vals, m, has_fill ? fill : 0);
+    if (touched) {
+        c.t.leaf_calls += all_same ? 1u : u32(__popc(changed_bits));
+        if (all_same)
+            c.t.collapsed++;  // :888-889
+        else
+            c.t.branch_calls++;
+    }
+    u64 id = touched ? 0 : fill_leaf;  // absent block: the enclosing fill leaf, or EMPTY
+    // uniform collapse -> Leaf(value)
+    u64 lid = leaf_get(c, V::first(vals), all_same);
+    if (all_same) id = lid;
+    // branch blocks: per-warp value-keyed cache, then the global table
+    const u32 e = V::hash(eff) & (V::BC - 1);
+    bool pend = need_branch;
+    if (need_branch) {
+        bool hit = true;
+#pragma unroll
+        for (int j = 0; j < V::KW; ++j) hit = hit && c.ws->bkey[e * V::KW + j] == eff.w[j];
+        if (hit) {
+            u64 v = c.ws->bval[e];
+            if (v != 0) {
+                id = v;
+                pend = false;
+                c.t.local++;
+            }
+        }
+    }
+    u32 pmask = __ballot_sync(FULL, pend);
+    while (pmask != 0) {
+        // duplicate keys inside the warp: one representative per distinct value word
+        bool leader = false;
+        if (pend) {
+            u32 mm = __match_any_sync(pmask, eff.w[0]);
+            if (V::KW > 1) {
+#pragma unroll
+                for (int j = 1; j < V::KW; ++j) mm &= __match_any_sync(pmask, eff.w[j]);
+            }
+            leader = (__ffs(mm) - 1) == lane;
+        }
+        u32 lmask = __ballot_sync(FULL, leader);
+        // group g takes the g-th leader
+        int src = __fns(lmask, 0, (c.gs >> 3) + 1);
+        const bool gvalid = src >= 0 && src < 32;
+        if (!gvalid) src = 0;
+        typename V::Key gk = V::bcast(eff, src);
+        u32 cv;
+        if (V::KW == 1)
+            cv = u32(gk.w[0] >> (8 * c.li)) & 0xFF;
+        else {
+            u64 w = (c.li >> 1) == 0 ? gk.w[0] : (c.li >> 1) == 1 ? gk.w[1 % V::KW] : (c.li >> 1) == 2 ? gk.w[2 % V::KW] : gk.w[3 % V::KW];
+            cv = u32(w >> (32 * (c.li & 1)));
+        }
+        u64 child = leaf_get(c, cv, gvalid);
+        u64 bid = intern_branch<T, true>(c, gvalid, child, gvalid ? cv : 0);
+        // cache refresh: one writer per entry
+        u32 ge = V::hash(gk) & (V::BC - 1);
+        bool wr = gvalid && bid != 0 && c.li == 0;
+        u32 wb = __ballot_sync(FULL, wr);
+        if (wr) {
+            u32 sm = __match_any_sync(wb, ge);
+            if ((__ffs(sm) - 1) == lane) {
+#pragma unroll
+                for (int j = 0; j < V::KW; ++j) c.ws->bkey[ge * V::KW + j] = gk.w[j];
+                c.ws->bval[ge] = bid;
+            }
+        }
+        // hand the ids back to every pending lane with the same key
+#pragma unroll
+        for (int g2 = 0; g2 < 4; ++g2) {
+            typename V::Key k2 = V::bcast(gk, g2 * 8);
+            u64 id2 = __shfl_sync(FULL, bid, g2 * 8);
+            bool v2 = __shfl_sync(FULL, int(gvalid), g2 * 8) != 0;
+            if (pend && v2 && V::eq(k2, eff)) {
+                id = id2;
+                pend = false;
+            }
+        }
+        __syncwarp();
+        pmask = __ballot_sync(FULL, pend);
+    }
+    return id;
+}
+
+// ------------------------------------------------------------------------------------------------
+// A warp builds the sub-tree over `nblocks` (8, 64 or 512) Morton-consecutive blocks.
+// ------------------------------------------------------------------------------------------------
+template <class T>
+__device__ inline u64 build_unit(Ctx<T>& c, const u8* masks, const void* values, size_t first_block, int nblocks,
+                                 bool has_fill, u32 fill, u64 fill_leaf, bool* upresent) {
+    using V = VT<T>;
+    const int lane = c.lane;
+    const int n_iter = (nblocks + 31) / 32;
+    // software prefetch: loads of iteration it+1 are issued before iteration it is processed
+    typename V::Key nvals = V::zero();
+    u32 nmask = 0;
+    if (lane < nblocks) {
+        nvals = V::load(values, first_block + lane);
+        nmask = ld_stream_u16(masks + (first_block + lane) * 2) & 0xFF;
+    }
+    for (int it = 0; it < n_iter; ++it) {
+        typename V::Key vals = nvals;
+        u32 smask = nmask;
+        const bool active = it * 32 + lane < nblocks;
+        const int nb = (it + 1) * 32 + lane;
+        if (nb < nblocks) {
+            nvals = V::load(values, first_block + nb);
+            nmask = ld_stream_u16(masks + (first_block + nb) * 2) & 0xFF;
+        }
+        bool present;
+        u64 id = block_node<T>(c, active, vals, smask, has_fill, fill, fill_leaf, &present);
+        bool pp;
+        u64 pid = parent_node<T>(c, id, present && active, &pp);
+        if (c.li == 0 && it * 32 + c.gs < nblocks) {
+            c.ws->l1[it * 4 + (c.gs >> 3)] = pid;
+        }
+        u32 ppb = __ballot_sync(FULL, pp && c.li == 0 && it * 32 + c.gs < nblocks);
+        if (lane == 0) {
+            // compact the four group bits (lanes 0,8,16,24) into bits 0..3
+            u32 four = (ppb & 1) | ((ppb >> 7) & 2) | ((ppb >> 14) & 4) | ((ppb >> 21) & 8);
+            int word = (it * 4) >> 5, sh = (it * 4) & 31;
+            u32 old = (sh == 0) ? 0u : c.ws->l1p[word];
+            c.ws->l1p[word] = old | (four << sh);
+        }
+    }
+    __syncwarp();
+    int n1 = nblocks / 8;
+    if (n1 <= 1) {
+        *upresent = (c.ws->l1p[0] & 1) != 0;
+        u64 r = c.ws->l1[0];
+        __syncwarp();
+        return r;
+    }
+    // level 2: n1 (8 or 64) nodes -> n1/8
+    u32 p2 = 0;
+    for (int it = 0; it * 32 < n1; ++it) {
+        const int i = it * 32 + lane;
+        const bool act = i < n1;
+        u64 ch = act ? c.ws->l1[i] : 0;
+        bool pr = act && ((c.ws->l1p[i >> 5] >> (i & 31)) & 1);
+        bool pp;
+        u64 pid = parent_node<T>(c, ch, pr, &pp);
+        const bool gact = it * 32 + c.gs < n1;
+        if (c.li == 0 && gact) c.ws->l2[it * 4 + (c.gs >> 3)] = pid;
+        u32 ppb = __ballot_sync(FULL, pp && c.li == 0 && gact);
+        u32 four = (ppb & 1) | ((ppb >> 7) & 2) | ((ppb >> 14) & 4) | ((ppb >> 21) & 8);
+        p2 |= four << (it * 4);
+    }
+    __syncwarp();
+    int n2 = n1 / 8;
+    if (n2 <= 1) {
+        *upresent = (p2 & 1) != 0;
+        u64 r = c.ws->l2[0];
+        __syncwarp();
+        return r;
+    }
+    // level 3: 8 nodes -> 1
+    {
+        const bool act = lane < 8;
+        u64 ch = act ? c.ws->l2[lane] : 0;
+        bool pr = act && ((p2 >> lane) & 1);
+        bool pp;
+        u64 pid = parent_node<T>(c, ch, pr, &pp);
+        pid = __shfl_sync(FULL, pid, 0);
+        *upresent = __shfl_sync(FULL, int(pp), 0) != 0;
+        __syncwarp();
+        return pid;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernel plumbing
+// ------------------------------------------------------------------------------------------------
+struct ApplyArgs {
+    InternerDev in;
+    const u8* masks;       // [n][B][2]
+    const void* values;    // [n][B][8]
+    const u8* flags;       // [n] or null
+    const long long* fills;  // [n] or null
+    u64* roots;            // [n]
+    u8* changed;           // [n] or null
+    u32 n;
+    u32 depth;
+    u32 blocks;  // B
+};
+
+template <class T>
+__device__ __forceinline__ void ctx_init(Ctx<T>& c, const InternerDev& in, WarpSmem<T>* ws, CtaSmem* cs) {
+    c.in = in;
+    c.lane = threadIdx.x & 31;
+    c.li = c.lane & 7;
+    c.gs = c.lane & 24;
+    c.ws = ws + (threadIdx.x >> 5);
+    c.cs = cs;
+}
+
+template <class T>
+__device__ inline void smem_init(WarpSmem<T>* ws, CtaSmem* cs) {
+    u32* w = (u32*)ws;
+    for (u32 i = threadIdx.x; i < sizeof(WarpSmem<T>) * WARPS_PER_CTA / 4; i += blockDim.x) w[i] = 0;
+    u32* q = (u32*)cs;
+    for (u32 i = threadIdx.x; i < sizeof(CtaSmem) / 4; i += blockDim.x) q[i] = 0;
+    __syncthreads();
+}
+
+template <class T>
+__device__ inline void cta_finish(Ctx<T>& c) {
+    __syncthreads();
+    if (sizeof(T) == 1) {  // flush the leaf in-degree histogram
+        for (u32 v = threadIdx.x; v < 256; v += blockDim.x) {
+            u32 n = c.cs->leafref[v];
+            if (n) atomicAdd(&c.in.refs[id_index(c.cs->leaf[v])], n);
+        }
+    }
+    Tally& t = c.t;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        t.leaf_calls += __shfl_xor_sync(FULL, t.leaf_calls, o);
+        t.branch_calls += __shfl_xor_sync(FULL, t.branch_calls, o);
+        t.leaf_miss += __shfl_xor_sync(FULL, t.leaf_miss, o);
+        t.branch_miss += __shfl_xor_sync(FULL, t.branch_miss, o);
+        t.collapsed += __shfl_xor_sync(FULL, t.collapsed, o);
+        t.probes += __shfl_xor_sync(FULL, t.probes, o);
+        t.local += __shfl_xor_sync(FULL, t.local, o);
+    }
+    if (c.lane == 0) {
+        Counters* k = c.in.ctr;
+        if (t.leaf_calls) atomicAdd(&k->leaf_calls, (ull)t.leaf_calls);
+        if (t.branch_calls) atomicAdd(&k->branch_calls, (ull)t.branch_calls);
+        if (t.leaf_miss) atomicAdd(&k->leaf_misses, (ull)t.leaf_miss);
+        if (t.branch_miss) atomicAdd(&k->branch_misses, (ull)t.branch_miss);
+        if (t.collapsed) atomicAdd(&k->collapsed, (ull)t.collapsed);
+        if (t.probes) atomicAdd(&k->probe_steps, (ull)t.probes);
+        if (t.local) atomicAdd(&k->cache_hits_local, (ull)t.local);
+    }
+}
+
+// Phase 0 (voxtree.rs:742-758) for one chunk: returns the fill leaf (0 if none) to the whole warp.
+// The reference's get_or_create_leaf(fill) hands out one reference that is either the root handle
+// (no patches) or never released — reproduced by `take_ref`.
+template <class T>
+__device__ inline u64 phase0_fill(Ctx<T>& c, bool has_fill, u32 fill, bool take_ref) {
+    u64 fl = leaf_get(c, fill, has_fill && c.lane == 0);
+    fl = __shfl_sync(FULL, fl, 0);
+    if (has_fill && take_ref && c.lane == 0 && fl != 0) {
+        atomicAdd(&c.in.refs[id_index(fl)], 1u);
+        c.t.leaf_calls++;
+    }
+    return fl;
+}
+
+template <class T>
+__device__ __forceinline__ void chunk_flags(const ApplyArgs& a, u32 chunk, bool* has_fill, u32* fill, bool* has_patches) {
+    u32 f = a.flags ? a.flags[chunk] : VX_FLAG_PATCHES;
+    *has_fill = (f & VX_FLAG_FILL) != 0;
+    *has_patches = (f & VX_FLAG_PATCHES) != 0;
+    long long fv = (*has_fill && a.fills) ? a.fills[chunk] : 0;
+    *fill = sizeof(T) == 1 ? u32(fv) & 0xFF : u32(fv);
+    if (*fill == 0) *has_fill = false;  // fill(default) == clear: nothing to intern
+}
+
+template <class T>
+__device__ __forceinline__ void write_root(Ctx<T>& c, const ApplyArgs& a, u32 chunk, u64 root, bool changed) {
+    // apply_batch (voxtree.rs:303-328): INVALID -> false, root untouched (EMPTY for a fresh tree)
+    a.roots[chunk] = changed ? root : 0;
+    if (a.changed) a.changed[chunk] = changed ? 1 : 0;
+    if (changed && root != 0) atomicAdd(&c.in.refs[id_index(root)], 1u);  // the tree's root handle
+}
+
+// D <= 4: a chunk is at most one warp unit -> one warp per chunk.
+template <class T>
+__global__ void __launch_bounds__(CTA_THREADS, 3) apply_small_kernel(ApplyArgs a) {
+    __shared__ WarpSmem<T> ws[WARPS_PER_CTA];
+    __shared__ CtaSmem cs;
+    smem_init<T>(ws, &cs);
+    Ctx<T> c;
+    ctx_init<T>(c, a.in, ws, &cs);
+    const u32 warp_global = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
+    const u32 nwarps = gridDim.x * WARPS_PER_CTA;
+    for (u32 chunk = warp_global; chunk < a.n; chunk += nwarps) {
+        bool has_fill, has_patches;
+        u32 fill;
+        chunk_flags<T>(a, chunk, &has_fill, &fill, &has_patches);
+        u64 fl = phase0_fill<T>(c, has_fill, fill, has_patches);
+        if (!has_patches) {  // :756-758
+            if (c.lane == 0) {
+                if (has_fill) c.t.leaf_calls++;
+                write_root<T>(c, a, chunk, fl, has_fill);
+            }
+            continue;
+        }
+        bool present;
+        u64 root = build_unit<T>(c, a.masks + size_t(chunk) * a.blocks * 2,
+                                 (const u8*)a.values + size_t(chunk) * a.blocks * 8 * sizeof(T), 0, int(a.blocks),
+                                 has_fill, fill, fl, &present);
+        if (c.lane == 0) write_root<T>(c, a, chunk, root, present);
+    }
+    cta_finish<T>(c);
+}
+
+// D >= 5: one CTA per chunk; each warp builds 512-block units, warp 0 joins the upper levels.
+template <class T>
+__global__ void __launch_bounds__(CTA_THREADS, 3) apply_large_kernel(ApplyArgs a) {
+    __shared__ WarpSmem<T> ws[WARPS_PER_CTA];
+    __shared__ CtaSmem cs;
+    smem_init<T>(ws, &cs);
+    Ctx<T> c;
+    ctx_init<T>(c, a.in, ws, &cs);
+    const int warp = threadIdx.x >> 5;
+    const u32 n_super = a.blocks / (UNIT_BLOCKS * WARPS_PER_CTA);  // 32^3 sub-cubes: 1, 8, 64
+    for (u32 chunk = blockIdx.x; chunk < a.n; chunk += gridDim.x) {
+        bool has_fill, has_patches;
+        u32 fill;
+        chunk_flags<T>(a, chunk, &has_fill, &fill, &has_patches);
+        u64 fl = 0;
+        if (has_fill) {  // CTA-uniform
+            if (warp == 0) {
+                fl = phase0_fill<T>(c, true, fill, has_patches);
+                if (c.lane == 0) cs.top[0] = fl;
+            }
+            __syncthreads();
+            fl = cs.top[0];
+            __syncthreads();
+        }
+        if (!has_patches) {
+            if (threadIdx.x == 0) {
+                if (has_fill) c.t.leaf_calls++;
+                write_root<T>(c, a, chunk, fl, has_fill);
+            }
+            continue;
+        }
+        const u8* cm = a.masks + size_t(chunk) * a.blocks * 2;
+        const void* cv = (const u8*)a.values + size_t(chunk) * a.blocks * 8 * sizeof(T);
+        for (u32 s = 0; s < n_super; ++s) {
+            bool present;
+            u64 uid = build_unit<T>(c, cm, cv, (size_t(s) * WARPS_PER_CTA + warp) * UNIT_BLOCKS, UNIT_BLOCKS, has_fill,
+                                    fill, fl, &present);
+            if (c.lane == 0) {
+                cs.oct[warp] = uid;
+                cs.octp[warp] = present;
+            }
+            __syncthreads();
+            if (warp == 0) {
+                const bool act = c.lane < 8;
+                u64 ch = act ? cs.oct[c.lane] : 0;
+                bool pr = act && cs.octp[c.lane] != 0;
+                bool pp;
+                u64 pid = parent_node<T>(c, ch, pr, &pp);
+                if (c.lane == 0) {
+                    cs.top[s] = pid;
+                    cs.topp[s] = pp;
+                }
+            }
+            __syncthreads();
+        }
+        if (warp == 0) {
+            u32 n = n_super;
+            while (n > 1) {  // 64 -> 8 -> 1
+                for (u32 it = 0; it * 32 < n; ++it) {
+                    const u32 i = it * 32 + c.lane;
+                    const bool act = i < n;
+                    u64 ch = act ? cs.top[i] : 0;
+                    bool pr = act && cs.topp[i] != 0;
+                    __syncwarp();
+                    bool pp;
+                    u64 pid = parent_node<T>(c, ch, pr, &pp);
+                    __syncwarp();
+                    if (c.li == 0 && it * 32 + c.gs < n) {
+                        cs.top[it * 4 + (c.gs >> 3)] = pid;
+                        cs.topp[it * 4 + (c.gs >> 3)] = pp;
+                    }
+                    __syncwarp();
+                }
+                n /= 8;
+            }
+            if (c.lane == 0) write_root<T>(c, a, chunk, cs.top[0], cs.topp[0] != 0);
+        }
+        __syncthreads();
+    }
+    cta_finish<T>(c);
+}
+
+}  // namespace vx

@@ -1,0 +1,897 @@
+// vx_capi.cu — host side of the C ABI declared in include/voxelis_b200.h.
+//
+// Owns all device memory of an interner (SoA pools + tables, see vx_device.cuh), stages host batches
+// through double-buffered device slabs, launches the sm_100a kernels of vx_build.cuh / vx_read.cuh and
+// turns device-side sticky errors into status codes.  There is no CPU implementation of any compute
+// entry point in this library.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/voxelis_b200.h"
+#include "vx_build.cuh"
+#include "vx_read.cuh"
+
+using namespace vx;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CU_TRY(expr)                                                                                   \
+    do {                                                                                               \
+        cudaError_t _e = (expr);                                                                       \
+        if (_e != cudaSuccess)                                                                         \
+            return fail(VX_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));                \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+size_t dtype_size(vx_dtype t) { return t == VX_U8 ? 1 : 4; }
+size_t blocks_for_depth(int d) { return size_t(1) << (3 * (d > 0 ? d - 1 : 0)); }
+
+struct Scalars {  // one device allocation for all interner scalars
+    u32 next_index;
+    u32 free_count;
+    u32 error;
+    u32 pad;
+    Counters ctr;
+};
+
+}  // namespace
+
+struct vx_interner {
+    int device = 0;
+    vx_dtype dtype = VX_U8;
+    size_t budget = 0, capacity = 0, nbuckets = 0, leaf_slots = 0;
+    InternerDev dev{};
+    Scalars* d_scalars = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev_copied[2]{}, ev_done[2]{};
+    int sm_count = 0;
+    bool poisoned = false;
+    // staging for host-resident batches (double buffered) and small scratch
+    void* stage[2]{};
+    size_t stage_bytes = 0;
+    void* scratch = nullptr;  // device
+    size_t scratch_bytes = 0;
+    void* hscratch = nullptr;  // pinned host
+    size_t hscratch_bytes = 0;
+    std::mutex mu;
+};
+
+struct vx_tree {
+    uint8_t depth;
+    vx_block_id root;
+    bool dirty;
+};
+
+struct vx_batch {
+    uint8_t depth;
+    vx_dtype dtype;
+    size_t blocks;
+    uint8_t* masks;  // pinned
+    void* values;    // pinned
+    bool has_fill;
+    int64_t fill;
+    bool has_patches;
+};
+
+namespace {
+
+int ensure_scratch(vx_interner* it, size_t dev_bytes, size_t host_bytes) {
+    if (dev_bytes > it->scratch_bytes) {
+        if (it->scratch) cudaFree(it->scratch);
+        it->scratch = nullptr;
+        it->scratch_bytes = 0;
+        size_t want = std::max<size_t>(dev_bytes, 1 << 20);
+        CU_TRY(cudaMalloc(&it->scratch, want));
+        it->scratch_bytes = want;
+    }
+    if (host_bytes > it->hscratch_bytes) {
+        if (it->hscratch) cudaFreeHost(it->hscratch);
+        it->hscratch = nullptr;
+        it->hscratch_bytes = 0;
+        size_t want = std::max<size_t>(host_bytes, 1 << 16);
+        CU_TRY(cudaMallocHost(&it->hscratch, want));
+        it->hscratch_bytes = want;
+    }
+    return VX_OK;
+}
+
+bool is_device_ptr(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+int check_device_error(vx_interner* it) {
+    u32 err = 0;
+    CU_TRY(cudaMemcpyAsync(&err, &it->d_scalars->error, sizeof(u32), cudaMemcpyDeviceToHost, it->stream));
+    CU_TRY(cudaStreamSynchronize(it->stream));
+    if (err == ERR_NONE) return VX_OK;
+    it->poisoned = true;
+    if (err == ERR_OOM) return fail(VX_E_OOM, "Out of memory");  // interner/macros.rs:38
+    if (err == ERR_TABLE_FULL) return fail(VX_E_OOM, "interner hash table full");
+    return fail(VX_E_CUDA, "device-side internal error");
+}
+
+template <class T>
+int launch_apply_t(vx_interner* it, int depth, size_t n, const u8* d_masks, const void* d_values, const u8* d_flags,
+                   const int64_t* d_fills, u64* d_roots, u8* d_changed, cudaStream_t s) {
+    if (n == 0) return VX_OK;
+    ApplyArgs a{};
+    a.in = it->dev;
+    a.masks = d_masks;
+    a.values = d_values;
+    a.flags = d_flags;
+    a.fills = (const long long*)d_fills;
+    a.roots = d_roots;
+    a.changed = d_changed;
+    a.n = u32(n);
+    a.depth = u32(depth);
+    a.blocks = u32(blocks_for_depth(depth));
+    int occ = 0;
+    if (depth >= 5) {
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, apply_large_kernel<T>, CTA_THREADS, 0));
+        size_t grid = std::min<size_t>(n, size_t(std::max(occ, 1)) * it->sm_count);
+        apply_large_kernel<T><<<unsigned(grid), CTA_THREADS, 0, s>>>(a);
+    } else {
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, apply_small_kernel<T>, CTA_THREADS, 0));
+        size_t ctas = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+        size_t grid = std::min<size_t>(ctas, size_t(std::max(occ, 1)) * it->sm_count);
+        apply_small_kernel<T><<<unsigned(grid), CTA_THREADS, 0, s>>>(a);
+    }
+    CU_TRY(cudaGetLastError());
+    return VX_OK;
+}
+
+int launch_apply(vx_interner* it, int depth, size_t n, const u8* d_masks, const void* d_values, const u8* d_flags,
+                 const int64_t* d_fills, u64* d_roots, u8* d_changed, cudaStream_t s) {
+    if (n > 0xFFFFFFFFull) return fail(VX_E_INVALID, "too many chunks in one call");
+    if (it->dtype == VX_U8)
+        return launch_apply_t<u8>(it, depth, n, d_masks, d_values, d_flags, d_fills, d_roots, d_changed, s);
+    return launch_apply_t<int32_t>(it, depth, n, d_masks, d_values, d_flags, d_fills, d_roots, d_changed, s);
+}
+
+int valid_depth(int d) { return d >= 2 && d <= 7; }
+
+int init_state(vx_interner* it) {
+    cudaStream_t s = it->stream;
+    CU_TRY(cudaMemsetAsync(it->dev.slots, 0, it->nbuckets * 64, s));
+    CU_TRY(cudaMemsetAsync(it->dev.refs, 0, it->capacity * 4, s));
+    CU_TRY(cudaMemsetAsync(it->dev.gens, 0, it->capacity * 2, s));
+    CU_TRY(cudaMemsetAsync(it->dev.children, 0, 64, s));               // slot 0: the empty branch
+    CU_TRY(cudaMemsetAsync(it->dev.values, 0, dtype_size(it->dtype), s));
+    CU_TRY(cudaMemsetAsync(it->dev.hashes, 0, 8, s));
+    if (it->dtype == VX_U8)
+        CU_TRY(cudaMemsetAsync(it->dev.leaf_u8, 0, 256 * 8, s));
+    else {
+        CU_TRY(cudaMemsetAsync(it->dev.leaf_keys, 0, it->leaf_slots * 8, s));
+        CU_TRY(cudaMemsetAsync(it->dev.leaf_ids, 0, it->leaf_slots * 8, s));
+    }
+    Scalars init{};
+    init.next_index = 1;  // interner/mod.rs:101
+    CU_TRY(cudaMemcpyAsync(it->d_scalars, &init, sizeof(init), cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    it->poisoned = false;
+    return VX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* vx_last_error(void) { return g_err.c_str(); }
+int vx_abi_version(void) { return VX_ABI_VERSION; }
+int vx_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(VX_E_CUDA, "no CUDA device");
+    }
+    return n;
+}
+
+// ------------------------------------------------------------------------------- interner
+vx_interner* vx_interner_create(size_t budget, vx_dtype dtype, int device) {
+    if (dtype != VX_U8 && dtype != VX_I32) {
+        fail(VX_E_INVALID, "unsupported voxel type");
+        return nullptr;
+    }
+    size_t node_size = 78 + dtype_size(dtype);  // interner/mod.rs:158-164
+    size_t cap = budget / node_size;
+    if (cap == 0) {
+        fail(VX_E_BUDGET, "Requested budget is too small");  // mod.rs:63-64
+        return nullptr;
+    }
+    if (cap >= 0xFFFFFFF0ull) {
+        fail(VX_E_BUDGET, "Requested budget is too large");  // mod.rs:65-68
+        return nullptr;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        fail(VX_E_CUDA, "no usable CUDA device (this library has no CPU fallback)");
+        return nullptr;
+    }
+    DeviceGuard g(device);
+    vx_interner* it = new vx_interner();
+    it->device = device;
+    it->dtype = dtype;
+    it->budget = budget;
+    it->capacity = cap;
+    size_t nb = 1024;
+    while (nb * 4 < cap) nb <<= 1;  // >= 2 slots per node of capacity (load factor <= 0.5)
+    it->nbuckets = nb;
+    size_t ls = 1024;
+    if (dtype != VX_U8)
+        while (ls < cap * 2) ls <<= 1;
+    it->leaf_slots = ls;
+    auto bail = [&](const char* what) -> vx_interner* {
+        fail(VX_E_CUDA, std::string("vx_interner_create: ") + what + ": " + cudaGetErrorString(cudaGetLastError()));
+        vx_interner_destroy(it);
+        return nullptr;
+    };
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail("cudaGetDeviceProperties");
+    it->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&it->stream, cudaStreamNonBlocking) != cudaSuccess) return bail("stream");
+    if (cudaStreamCreateWithFlags(&it->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return bail("stream");
+    for (int i = 0; i < 2; ++i) {
+        if (cudaEventCreateWithFlags(&it->ev_copied[i], cudaEventDisableTiming) != cudaSuccess) return bail("event");
+        if (cudaEventCreateWithFlags(&it->ev_done[i], cudaEventDisableTiming) != cudaSuccess) return bail("event");
+    }
+    InternerDev& d = it->dev;
+    if (cudaMalloc(&d.children, cap * 64) != cudaSuccess) return bail("children pool");
+    if (cudaMalloc(&d.values, cap * dtype_size(dtype)) != cudaSuccess) return bail("values pool");
+    if (cudaMalloc(&d.refs, cap * 4) != cudaSuccess) return bail("ref_counts pool");
+    if (cudaMalloc(&d.gens, cap * 2) != cudaSuccess) return bail("generations pool");
+    if (cudaMalloc(&d.hashes, cap * 8) != cudaSuccess) return bail("hashes pool");
+    if (cudaMalloc(&d.free_list, cap * 4) != cudaSuccess) return bail("free list");
+    if (cudaMalloc(&d.slots, nb * 64) != cudaSuccess) return bail("branch table");
+    if (dtype == VX_U8) {
+        if (cudaMalloc(&d.leaf_u8, 256 * 8) != cudaSuccess) return bail("leaf table");
+    } else {
+        if (cudaMalloc(&d.leaf_keys, ls * 8) != cudaSuccess) return bail("leaf table");
+        if (cudaMalloc(&d.leaf_ids, ls * 8) != cudaSuccess) return bail("leaf table");
+    }
+    if (cudaMalloc(&it->d_scalars, sizeof(Scalars)) != cudaSuccess) return bail("scalars");
+    d.bucket_mask = u32(nb - 1);
+    d.leaf_mask = u32(ls - 1);
+    d.capacity = u32(cap);
+    d.next_index = &it->d_scalars->next_index;
+    d.free_count = &it->d_scalars->free_count;
+    d.error = &it->d_scalars->error;
+    d.ctr = &it->d_scalars->ctr;
+    if (init_state(it) != VX_OK) {
+        vx_interner_destroy(it);
+        return nullptr;
+    }
+    return it;
+}
+
+void vx_interner_destroy(vx_interner* it) {
+    if (!it) return;
+    DeviceGuard g(it->device);
+    if (it->stream) cudaStreamSynchronize(it->stream);
+    InternerDev& d = it->dev;
+    cudaFree(d.children);
+    cudaFree(d.values);
+    cudaFree(d.refs);
+    cudaFree(d.gens);
+    cudaFree(d.hashes);
+    cudaFree(d.free_list);
+    cudaFree(d.slots);
+    cudaFree(d.leaf_u8);
+    cudaFree(d.leaf_keys);
+    cudaFree(d.leaf_ids);
+    cudaFree(it->d_scalars);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(it->stage[i]);
+        if (it->ev_copied[i]) cudaEventDestroy(it->ev_copied[i]);
+        if (it->ev_done[i]) cudaEventDestroy(it->ev_done[i]);
+    }
+    cudaFree(it->scratch);
+    if (it->hscratch) cudaFreeHost(it->hscratch);
+    if (it->stream) cudaStreamDestroy(it->stream);
+    if (it->copy_stream) cudaStreamDestroy(it->copy_stream);
+    cudaGetLastError();
+    delete it;
+}
+
+int vx_interner_reset(vx_interner* it) {
+    if (!it) return fail(VX_E_INVALID, "null interner");
+    DeviceGuard g(it->device);
+    return init_state(it);
+}
+size_t vx_interner_capacity(const vx_interner* it) { return it ? it->capacity : 0; }
+vx_dtype vx_interner_dtype(const vx_interner* it) { return it ? it->dtype : VX_U8; }
+int vx_interner_device(const vx_interner* it) { return it ? it->device : -1; }
+void* vx_interner_stream(const vx_interner* it) { return it ? (void*)it->stream : nullptr; }
+
+int vx_interner_sync(vx_interner* it) {
+    if (!it) return fail(VX_E_INVALID, "null interner");
+    DeviceGuard g(it->device);
+    CU_TRY(cudaStreamSynchronize(it->stream));
+    return check_device_error(it);
+}
+
+static int read_scalars(const vx_interner* cit, Scalars* out) {
+    vx_interner* it = const_cast<vx_interner*>(cit);
+    DeviceGuard g(it->device);
+    CU_TRY(cudaMemcpyAsync(out, it->d_scalars, sizeof(Scalars), cudaMemcpyDeviceToHost, it->stream));
+    CU_TRY(cudaStreamSynchronize(it->stream));
+    return VX_OK;
+}
+
+int64_t vx_interner_next_index(const vx_interner* it) {
+    if (!it) return fail(VX_E_INVALID, "null interner");
+    Scalars s;
+    int rc = read_scalars(it, &s);
+    if (rc != VX_OK) return rc;
+    return std::min<int64_t>(s.next_index, int64_t(it->capacity));
+}
+
+static int read_node_field(const vx_interner* cit, vx_block_id id, const void* base, size_t elt, void* out, size_t n) {
+    vx_interner* it = const_cast<vx_interner*>(cit);
+    if (!it) return fail(VX_E_INVALID, "null interner");
+    if (id == VX_BLOCK_INVALID || id_index(id) >= it->capacity) return fail(VX_E_INVALID, "invalid block id");
+    DeviceGuard g(it->device);
+    CU_TRY(cudaMemcpyAsync(out, (const u8*)base + size_t(id_index(id)) * elt, n, cudaMemcpyDeviceToHost, it->stream));
+    CU_TRY(cudaStreamSynchronize(it->stream));
+    return VX_OK;
+}
+int vx_interner_get_ref(const vx_interner* it, vx_block_id id, uint32_t* out) {
+    if (!out) return fail(VX_E_INVALID, "null out");
+    return it ? read_node_field(it, id, it->dev.refs, 4, out, 4) : fail(VX_E_INVALID, "null interner");
+}
+int vx_interner_get_value(const vx_interner* it, vx_block_id id, int64_t* out) {
+    if (!it || !out) return fail(VX_E_INVALID, "null argument");
+    if (it->dtype == VX_U8) {
+        u8 v = 0;
+        int rc = read_node_field(it, id, it->dev.values, 1, &v, 1);
+        *out = v;
+        return rc;
+    }
+    int32_t v = 0;
+    int rc = read_node_field(it, id, it->dev.values, 4, &v, 4);
+    *out = v;
+    return rc;
+}
+int vx_interner_get_children(const vx_interner* it, vx_block_id id, vx_block_id out[8]) {
+    if (!it || !out) return fail(VX_E_INVALID, "null argument");
+    if (id_is_leaf(id)) return fail(VX_E_INVALID, "Cannot get children for value node");
+    return read_node_field(it, id, it->dev.children, 64, out, 64);
+}
+
+int vx_interner_stats(const vx_interner* it, vx_stats* out) {
+    if (!it || !out) return fail(VX_E_INVALID, "null argument");
+    Scalars s;
+    int rc = read_scalars(it, &s);
+    if (rc != VX_OK) return rc;
+    memset(out, 0, sizeof(*out));
+    size_t node_size = 78 + dtype_size(it->dtype);
+    u64 next = std::min<u64>(s.next_index, it->capacity);
+    u64 freec = s.free_count;
+    out->requested_budget = it->budget;
+    out->actual_budget = it->capacity * node_size;
+    out->node_size = node_size;
+    out->nodes_capacity = it->capacity;
+    out->allocated_nodes = next;  // includes slot 0, like the reference (mod.rs:117)
+    out->recycled_nodes = freec;
+    out->alive_nodes = next - freec;
+    out->patterns = next - freec;
+    out->total_deallocations = s.ctr.recycled;
+    out->total_allocations = 1 + s.ctr.leaf_misses + s.ctr.branch_misses;
+    out->leaf_cache_misses = s.ctr.leaf_misses;
+    out->branch_cache_misses = s.ctr.branch_misses;
+    out->leaf_cache_hits = s.ctr.leaf_calls - s.ctr.leaf_misses;
+    out->branch_cache_hits = s.ctr.branch_calls - s.ctr.branch_misses;
+    out->total_cache_hits = out->leaf_cache_hits + out->branch_cache_hits;
+    out->total_cache_misses = out->leaf_cache_misses + out->branch_cache_misses;
+    out->collapsed_branches = s.ctr.collapsed;
+    out->max_alive_nodes = out->alive_nodes;
+    out->max_node_id = next ? next - 1 : 0;
+    // leaf_nodes / branch_nodes: live counts need the release counters split by kind; for
+    // build-only histories they are the miss counters (+ the permanent empty branch, mod.rs:131)
+    out->leaf_nodes = s.ctr.leaf_misses;
+    out->branch_nodes = 1 + s.ctr.branch_misses;
+    // max_*_ref_count / max_generation are running maxima over transient states in the reference;
+    // the in-degree refcount model has no such transients: reported as 0.
+    return VX_OK;
+}
+
+// diagnostic counters not part of InternerStats: probe_steps, cache_hits_local
+int vx_interner_debug_counters(const vx_interner* it, uint64_t out[8]) {
+    if (!it || !out) return fail(VX_E_INVALID, "null argument");
+    Scalars s;
+    int rc = read_scalars(it, &s);
+    if (rc != VX_OK) return rc;
+    out[0] = s.ctr.leaf_calls;
+    out[1] = s.ctr.branch_calls;
+    out[2] = s.ctr.leaf_misses;
+    out[3] = s.ctr.branch_misses;
+    out[4] = s.ctr.collapsed;
+    out[5] = s.ctr.probe_steps;
+    out[6] = s.ctr.cache_hits_local;
+    out[7] = s.ctr.recycled;
+    return VX_OK;
+}
+
+int64_t vx_interner_download(const vx_interner* cit, size_t cap, vx_block_id* children, int64_t* values,
+                             uint32_t* refs, uint16_t* gens, uint64_t* hashes) {
+    vx_interner* it = const_cast<vx_interner*>(cit);
+    if (!it) return fail(VX_E_INVALID, "null interner");
+    int64_t n = vx_interner_next_index(it);
+    if (n < 0) return n;
+    if (size_t(n) > cap) return fail(VX_E_INVALID, "download: caller arrays too small");
+    DeviceGuard g(it->device);
+    cudaStream_t s = it->stream;
+    if (children) CU_TRY(cudaMemcpyAsync(children, it->dev.children, size_t(n) * 64, cudaMemcpyDeviceToHost, s));
+    if (refs) CU_TRY(cudaMemcpyAsync(refs, it->dev.refs, size_t(n) * 4, cudaMemcpyDeviceToHost, s));
+    if (gens) CU_TRY(cudaMemcpyAsync(gens, it->dev.gens, size_t(n) * 2, cudaMemcpyDeviceToHost, s));
+    if (hashes) CU_TRY(cudaMemcpyAsync(hashes, it->dev.hashes, size_t(n) * 8, cudaMemcpyDeviceToHost, s));
+    std::vector<u8> tmp;
+    if (values) {
+        tmp.resize(size_t(n) * dtype_size(it->dtype));
+        CU_TRY(cudaMemcpyAsync(tmp.data(), it->dev.values, tmp.size(), cudaMemcpyDeviceToHost, s));
+    }
+    CU_TRY(cudaStreamSynchronize(s));
+    if (values) {
+        if (it->dtype == VX_U8)
+            for (int64_t i = 0; i < n; ++i) values[i] = tmp[i];
+        else
+            for (int64_t i = 0; i < n; ++i) values[i] = ((const int32_t*)tmp.data())[i];
+    }
+    return n;
+}
+
+// ------------------------------------------------------------------------------- batch
+vx_batch* vx_batch_create(uint8_t max_depth, vx_dtype dtype) {
+    if (!valid_depth(max_depth) || (dtype != VX_U8 && dtype != VX_I32)) {
+        fail(VX_E_INVALID, "vx_batch_create: max_depth must be in [2,7] and dtype u8/i32");
+        return nullptr;
+    }
+    vx_batch* b = new vx_batch();
+    b->depth = max_depth;
+    b->dtype = dtype;
+    b->blocks = blocks_for_depth(max_depth);
+    b->has_fill = false;
+    b->fill = 0;
+    b->has_patches = false;
+    // pinned so apply can DMA straight from the batch; falls back to pageable if no device
+    size_t mb = b->blocks * 2, vb = b->blocks * 8 * dtype_size(dtype);
+    if (cudaMallocHost((void**)&b->masks, mb + vb) != cudaSuccess) {
+        cudaGetLastError();
+        fail(VX_E_CUDA, "vx_batch_create: cudaMallocHost failed (no CUDA device?)");
+        delete b;
+        return nullptr;
+    }
+    b->values = b->masks + mb;
+    memset(b->masks, 0, mb + vb);
+    return b;
+}
+void vx_batch_destroy(vx_batch* b) {
+    if (!b) return;
+    cudaFreeHost(b->masks);
+    cudaGetLastError();
+    delete b;
+}
+
+static inline u32 spread10(u32 v) {  // utils/common.rs:24-55
+    v &= 0x3FF;
+    v = (v | (v << 16)) & 0x30000FF;
+    v = (v | (v << 8)) & 0x300F00F;
+    v = (v | (v << 4)) & 0x30C30C3;
+    v = (v | (v << 2)) & 0x9249249;
+    return v;
+}
+
+int vx_batch_set(vx_batch* b, int x, int y, int z, int64_t voxel) {
+    if (!b) return fail(VX_E_INVALID, "null batch");
+    int n = 1 << b->depth;
+    if (x < 0 || y < 0 || z < 0 || x >= n || y >= n || z >= n) return fail(VX_E_BOUNDS, "position out of bounds");
+    u32 full = spread10(u32(x)) | (spread10(u32(y)) << 1) | (spread10(u32(z)) << 2);
+    size_t p = full >> 3;
+    u32 i = full & 7;
+    u8 bit = u8(1u << i);
+    bool nonzero;
+    if (b->dtype == VX_U8) {
+        u8 v = u8(voxel);
+        nonzero = v != 0;
+        ((u8*)b->values)[p * 8 + i] = v;
+    } else {
+        int32_t v = int32_t(voxel);
+        nonzero = v != 0;
+        ((int32_t*)b->values)[p * 8 + i] = v;
+    }
+    if (nonzero) {  // batch.rs:162-168
+        b->masks[2 * p] |= bit;
+        b->masks[2 * p + 1] &= u8(~bit);
+    } else {
+        b->masks[2 * p] &= u8(~bit);
+        b->masks[2 * p + 1] |= bit;
+    }
+    b->has_patches = true;
+    return 1;
+}
+int vx_batch_clear(vx_batch* b) {
+    if (!b) return fail(VX_E_INVALID, "null batch");
+    memset(b->masks, 0, b->blocks * 2 + b->blocks * 8 * dtype_size(b->dtype));
+    b->has_fill = false;
+    b->fill = 0;
+    b->has_patches = false;
+    return VX_OK;
+}
+int vx_batch_fill(vx_batch* b, int64_t value) {
+    int rc = vx_batch_clear(b);
+    if (rc != VX_OK) return rc;
+    b->has_fill = true;
+    b->fill = b->dtype == VX_U8 ? int64_t(u8(value)) : int64_t(int32_t(value));
+    return VX_OK;
+}
+uint8_t* vx_batch_masks(vx_batch* b) { return b ? b->masks : nullptr; }
+void* vx_batch_values(vx_batch* b) { return b ? b->values : nullptr; }
+size_t vx_batch_blocks(const vx_batch* b) { return b ? b->blocks : 0; }
+int vx_batch_to_fill(const vx_batch* b, int64_t* out) {
+    if (!b) return fail(VX_E_INVALID, "null batch");
+    if (b->has_fill && out) *out = b->fill;
+    return b->has_fill ? 1 : 0;
+}
+size_t vx_batch_size(const vx_batch* b) {  // batch.rs:110-121
+    if (!b) return 0;
+    size_t n = 0;
+    for (size_t p = 0; p < b->blocks; ++p) n += (b->masks[2 * p] | b->masks[2 * p + 1]) != 0;
+    return n;
+}
+int vx_batch_has_patches(const vx_batch* b) { return b && b->has_patches; }
+void vx_batch_mark_patched(vx_batch* b) {
+    if (b) b->has_patches = true;
+}
+uint8_t vx_batch_max_depth(const vx_batch* b) { return b ? b->depth : 0; }
+vx_dtype vx_batch_dtype(const vx_batch* b) { return b ? b->dtype : VX_U8; }
+
+// ------------------------------------------------------------------------------- tree
+vx_tree* vx_tree_create(uint8_t max_depth) {
+    if (!valid_depth(max_depth)) {
+        fail(VX_E_INVALID, "Max depth exceeds allowed limit (supported: 2..7)");  // max_depth.rs:77-83
+        return nullptr;
+    }
+    return new vx_tree{max_depth, VX_BLOCK_EMPTY, false};
+}
+void vx_tree_destroy(vx_tree* t) { delete t; }
+vx_block_id vx_tree_root_id(const vx_tree* t) { return t ? t->root : VX_BLOCK_INVALID; }
+uint8_t vx_tree_max_depth(const vx_tree* t) { return t ? t->depth : 0; }
+uint32_t vx_tree_voxels_per_axis(const vx_tree* t) { return t ? 1u << t->depth : 0; }
+int vx_tree_is_empty(const vx_tree* t) { return t && t->root == 0; }
+int vx_tree_is_leaf(const vx_tree* t) { return t && id_is_leaf(t->root); }
+int vx_tree_is_dirty(const vx_tree* t) { return t && t->dirty; }
+void vx_tree_mark_dirty(vx_tree* t) {
+    if (t) t->dirty = true;
+}
+void vx_tree_clear_dirty(vx_tree* t) {
+    if (t) t->dirty = false;
+}
+
+// ------------------------------------------------------------------------------- apply
+int vx_apply_batches_device(vx_interner* it, uint8_t depth, size_t n, const uint8_t* d_masks, const void* d_values,
+                            const uint8_t* d_flags, const int64_t* d_fills, vx_block_id* d_roots, uint8_t* d_changed,
+                            void* stream) {
+    if (!it || !d_masks || !d_values || !d_roots) return fail(VX_E_INVALID, "null argument");
+    if (!valid_depth(depth)) return fail(VX_E_INVALID, "max_depth must be in [2,7]");
+    if (it->poisoned) return fail(VX_E_POISONED, "interner overflowed earlier; reset it");
+    DeviceGuard g(it->device);
+    cudaStream_t s = stream ? (cudaStream_t)stream : it->stream;
+    return launch_apply(it, depth, n, d_masks, d_values, d_flags, d_fills, d_roots, d_changed, s);
+}
+
+int vx_apply_batches_slab(vx_interner* it, uint8_t depth, size_t n, const uint8_t* masks, const void* values,
+                          const uint8_t* flags, const int64_t* fills, vx_block_id* roots_out, uint8_t* changed_out) {
+    if (!it || !masks || !values || !roots_out) return fail(VX_E_INVALID, "null argument");
+    if (!valid_depth(depth)) return fail(VX_E_INVALID, "max_depth must be in [2,7]");
+    if (it->poisoned) return fail(VX_E_POISONED, "interner overflowed earlier; reset it");
+    if (n == 0) return VX_OK;
+    std::lock_guard<std::mutex> lk(it->mu);
+    DeviceGuard g(it->device);
+    const size_t B = blocks_for_depth(depth), mbytes = B * 2, vbytes = B * 8 * dtype_size(it->dtype);
+    const bool dev_in = is_device_ptr(masks);
+    if (dev_in != is_device_ptr(values)) return fail(VX_E_INVALID, "masks and values must live in the same memory space");
+    const bool dev_roots = is_device_ptr(roots_out), dev_changed = changed_out && is_device_ptr(changed_out);
+    cudaStream_t s = it->stream;
+    // per-chunk options and outputs live in device scratch: [roots n*8][fills n*8][changed n][flags n]
+    size_t need = n * 8 + n * 8 + n + n + 64;
+    int rc = ensure_scratch(it, need, 0);
+    if (rc != VX_OK) return rc;
+    u64* d_roots = dev_roots ? roots_out : (u64*)it->scratch;
+    int64_t* d_fills = (int64_t*)((u8*)it->scratch + n * 8);
+    u8* d_changed = dev_changed ? changed_out : (u8*)it->scratch + n * 16;
+    u8* d_flags = (u8*)it->scratch + n * 17;
+    const u8* k_flags = nullptr;
+    const int64_t* k_fills = nullptr;
+    if (flags) {
+        if (is_device_ptr(flags))
+            k_flags = flags;
+        else {
+            CU_TRY(cudaMemcpyAsync(d_flags, flags, n, cudaMemcpyHostToDevice, s));
+            k_flags = d_flags;
+        }
+    }
+    if (fills) {
+        if (is_device_ptr(fills))
+            k_fills = fills;
+        else {
+            CU_TRY(cudaMemcpyAsync(d_fills, fills, n * 8, cudaMemcpyHostToDevice, s));
+            k_fills = d_fills;
+        }
+    }
+    if (dev_in) {
+        rc = launch_apply(it, depth, n, masks, values, k_flags, k_fills, d_roots, d_changed, s);
+        if (rc != VX_OK) return rc;
+    } else {
+        // host batches: H2D on the copy stream into one of two staging slabs while the previous slab
+        // is being built on the compute stream
+        size_t per = mbytes + vbytes;
+        size_t slab = std::max<size_t>(1, std::min<size_t>(n, (size_t(96) << 20) / per));
+        if (slab * per > it->stage_bytes) {
+            for (int i = 0; i < 2; ++i) {
+                cudaFree(it->stage[i]);
+                it->stage[i] = nullptr;
+            }
+            it->stage_bytes = 0;
+            for (int i = 0; i < 2; ++i) CU_TRY(cudaMalloc(&it->stage[i], slab * per));
+            it->stage_bytes = slab * per;
+        }
+        CU_TRY(cudaEventRecord(it->ev_done[0], s));  // orders the flags/fills copies, frees both slabs
+        CU_TRY(cudaEventRecord(it->ev_done[1], s));
+        size_t k = 0;
+        for (size_t lo = 0; lo < n; lo += slab, ++k) {
+            size_t cnt = std::min(slab, n - lo);
+            int b = int(k & 1);
+            u8* sm = (u8*)it->stage[b];
+            u8* sv = sm + slab * mbytes;
+            CU_TRY(cudaStreamWaitEvent(it->copy_stream, it->ev_done[b], 0));
+            CU_TRY(cudaMemcpyAsync(sm, masks + lo * mbytes, cnt * mbytes, cudaMemcpyHostToDevice, it->copy_stream));
+            CU_TRY(cudaMemcpyAsync(sv, (const u8*)values + lo * vbytes, cnt * vbytes, cudaMemcpyHostToDevice,
+                                   it->copy_stream));
+            CU_TRY(cudaEventRecord(it->ev_copied[b], it->copy_stream));
+            CU_TRY(cudaStreamWaitEvent(s, it->ev_copied[b], 0));
+            rc = launch_apply(it, depth, cnt, sm, sv, k_flags ? k_flags + lo : nullptr, k_fills ? k_fills + lo : nullptr,
+                              d_roots + lo, d_changed + lo, s);
+            if (rc != VX_OK) return rc;
+            CU_TRY(cudaEventRecord(it->ev_done[b], s));
+        }
+    }
+    if (!dev_roots) CU_TRY(cudaMemcpyAsync(roots_out, d_roots, n * 8, cudaMemcpyDeviceToHost, s));
+    if (changed_out && !dev_changed) CU_TRY(cudaMemcpyAsync(changed_out, d_changed, n, cudaMemcpyDeviceToHost, s));
+    return check_device_error(it);
+}
+
+int vx_tree_apply_batch(vx_interner* it, vx_tree* t, const vx_batch* b) {
+    if (!it || !t || !b) return fail(VX_E_INVALID, "null argument");
+    if (b->depth != t->depth) return fail(VX_E_INVALID, "batch and tree depths differ");
+    if (b->dtype != it->dtype) return fail(VX_E_INVALID, "batch and interner voxel types differ");
+    if (t->root != VX_BLOCK_EMPTY)
+        return fail(VX_E_UNSUPPORTED, "apply_batch on a non-empty tree is not implemented yet (SURVEY 8f-1)");
+    uint8_t flag = (b->has_fill ? VX_FLAG_FILL : 0) | (b->has_patches ? VX_FLAG_PATCHES : 0);
+    int64_t fill = b->fill;
+    vx_block_id root = 0;
+    uint8_t changed = 0;
+    int rc = vx_apply_batches_slab(it, b->depth, 1, b->masks, b->values, &flag, &fill, &root, &changed);
+    if (rc != VX_OK) return rc;
+    if (changed) {  // voxtree.rs:309-324
+        t->root = root;
+        t->dirty = true;
+        return 1;
+    }
+    return 0;
+}
+
+int vx_apply_batches(vx_interner* it, vx_tree* const* trees, const vx_batch* const* batches, size_t n,
+                     uint8_t* changed) {
+    if (!it || (n && (!trees || !batches))) return fail(VX_E_INVALID, "null argument");
+    if (n == 0) return VX_OK;
+    bool uniform = true;
+    for (size_t i = 0; i < n; ++i) {
+        if (!trees[i] || !batches[i]) return fail(VX_E_INVALID, "null tree or batch");
+        if (batches[i]->depth != trees[i]->depth) return fail(VX_E_INVALID, "batch and tree depths differ");
+        if (batches[i]->dtype != it->dtype) return fail(VX_E_INVALID, "batch and interner voxel types differ");
+        uniform = uniform && trees[i]->root == VX_BLOCK_EMPTY && batches[i]->depth == batches[0]->depth;
+    }
+    if (uniform) {  // a tree may appear only once in the fused path
+        std::vector<const vx_tree*> seen(trees, trees + n);
+        std::sort(seen.begin(), seen.end());
+        uniform = std::adjacent_find(seen.begin(), seen.end()) == seen.end();
+    }
+    if (!uniform) {  // mixed depths / non-empty trees: the reference's serial loop
+        for (size_t i = 0; i < n; ++i) {
+            int rc = vx_tree_apply_batch(it, trees[i], batches[i]);
+            if (rc < 0) return rc;
+            if (changed) changed[i] = uint8_t(rc);
+        }
+        return VX_OK;
+    }
+    if (it->poisoned) return fail(VX_E_POISONED, "interner overflowed earlier; reset it");
+    std::unique_lock<std::mutex> lk(it->mu);
+    DeviceGuard g(it->device);
+    const int depth = batches[0]->depth;
+    const size_t B = blocks_for_depth(depth), mbytes = B * 2, vbytes = B * 8 * dtype_size(it->dtype);
+    const size_t per = mbytes + vbytes;
+    // one contiguous device slab for all batches + options + results
+    size_t dev_need = n * per + n * 8 + n * 8 + n + n + 256;
+    size_t host_need = n * 8 + n * 8 + n + n;
+    int rc = ensure_scratch(it, dev_need, host_need);
+    if (rc != VX_OK) return rc;
+    u8* dm = (u8*)it->scratch;
+    u8* dv = dm + n * mbytes;
+    u64* d_roots = (u64*)(dv + n * vbytes);
+    int64_t* d_fills = (int64_t*)(d_roots + n);
+    u8* d_changed = (u8*)(d_fills + n);
+    u8* d_flags = d_changed + n;
+    u64* h_roots = (u64*)it->hscratch;
+    int64_t* h_fills = (int64_t*)(h_roots + n);
+    u8* h_changed = (u8*)(h_fills + n);
+    u8* h_flags = h_changed + n;
+    cudaStream_t s = it->stream;
+    for (size_t i = 0; i < n; ++i) {
+        const vx_batch* b = batches[i];
+        h_flags[i] = (b->has_fill ? VX_FLAG_FILL : 0) | (b->has_patches ? VX_FLAG_PATCHES : 0);
+        h_fills[i] = b->fill;
+        if (b->has_patches) {
+            CU_TRY(cudaMemcpyAsync(dm + i * mbytes, b->masks, mbytes, cudaMemcpyHostToDevice, s));
+            CU_TRY(cudaMemcpyAsync(dv + i * vbytes, b->values, vbytes, cudaMemcpyHostToDevice, s));
+        }
+    }
+    CU_TRY(cudaMemcpyAsync(d_flags, h_flags, n, cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaMemcpyAsync(d_fills, h_fills, n * 8, cudaMemcpyHostToDevice, s));
+    rc = launch_apply(it, depth, n, dm, dv, d_flags, d_fills, d_roots, d_changed, s);
+    if (rc != VX_OK) return rc;
+    CU_TRY(cudaMemcpyAsync(h_roots, d_roots, n * 8, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(h_changed, d_changed, n, cudaMemcpyDeviceToHost, s));
+    rc = check_device_error(it);
+    if (rc != VX_OK) return rc;
+    for (size_t i = 0; i < n; ++i) {
+        if (h_changed[i]) {
+            trees[i]->root = h_roots[i];
+            trees[i]->dirty = true;
+        }
+        if (changed) changed[i] = h_changed[i];
+    }
+    return VX_OK;
+}
+
+// ------------------------------------------------------------------------------- read back
+int vx_tree_get_many(const vx_interner* cit, const vx_tree* t, size_t n, const int32_t* xyz, uint8_t* found,
+                     int64_t* values) {
+    vx_interner* it = const_cast<vx_interner*>(cit);
+    if (!it || !t || !xyz || !found || !values) return fail(VX_E_INVALID, "null argument");
+    if (n == 0) return VX_OK;
+    const int N = 1 << t->depth;
+    for (size_t i = 0; i < 3 * n; ++i)
+        if (xyz[i] < 0 || xyz[i] >= N) return fail(VX_E_BOUNDS, "position out of bounds");  // voxtree.rs:146-148
+    std::lock_guard<std::mutex> lk(it->mu);
+    DeviceGuard g(it->device);
+    int rc = ensure_scratch(it, n * 12 + n + n * 8 + 64, 0);
+    if (rc != VX_OK) return rc;
+    long long* d_out = (long long*)it->scratch;
+    int* d_xyz = (int*)(d_out + n);
+    u8* d_found = (u8*)(d_xyz + 3 * n);
+    cudaStream_t s = it->stream;
+    CU_TRY(cudaMemcpyAsync(d_xyz, xyz, n * 12, cudaMemcpyHostToDevice, s));
+    unsigned grid = unsigned((n + 255) / 256);
+    if (it->dtype == VX_U8)
+        get_many_kernel<u8><<<grid, 256, 0, s>>>(it->dev.children, (const u8*)it->dev.values, t->root, t->depth, n,
+                                                  d_xyz, d_found, d_out);
+    else
+        get_many_kernel<int32_t><<<grid, 256, 0, s>>>(it->dev.children, (const int32_t*)it->dev.values, t->root,
+                                                       t->depth, n, d_xyz, d_found, d_out);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(found, d_found, n, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(values, d_out, n * 8, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    return VX_OK;
+}
+
+int vx_tree_get(const vx_interner* it, const vx_tree* t, int x, int y, int z, int64_t* out) {
+    if (!out) return fail(VX_E_INVALID, "null out");
+    int32_t xyz[3] = {x, y, z};
+    uint8_t found = 0;
+    int64_t v = 0;
+    int rc = vx_tree_get_many(it, t, 1, xyz, &found, &v);
+    if (rc != VX_OK) return rc;
+    *out = v;
+    return found ? 1 : 0;
+}
+
+int vx_roots_to_vec(const vx_interner* cit, uint8_t depth, size_t n, const vx_block_id* roots, void* dense) {
+    vx_interner* it = const_cast<vx_interner*>(cit);
+    if (!it || !roots || !dense) return fail(VX_E_INVALID, "null argument");
+    if (!valid_depth(depth)) return fail(VX_E_INVALID, "max_depth must be in [2,7]");
+    if (n == 0) return VX_OK;
+    std::lock_guard<std::mutex> lk(it->mu);
+    DeviceGuard g(it->device);
+    const size_t vol = size_t(1) << (3 * depth), esz = dtype_size(it->dtype);
+    const bool dev_roots = is_device_ptr(roots), dev_dense = is_device_ptr(dense);
+    int rc = ensure_scratch(it, (dev_roots ? 0 : n * 8) + (dev_dense ? 0 : n * vol * esz) + 256, 0);
+    if (rc != VX_OK) return rc;
+    cudaStream_t s = it->stream;
+    u8* p = (u8*)it->scratch;
+    const u64* d_roots = roots;
+    if (!dev_roots) {
+        CU_TRY(cudaMemcpyAsync(p, roots, n * 8, cudaMemcpyHostToDevice, s));
+        d_roots = (const u64*)p;
+        p += (n * 8 + 255) / 256 * 256;
+    }
+    void* d_dense = dev_dense ? dense : (void*)p;
+    size_t total = n * vol;
+    unsigned grid = unsigned(std::min<size_t>((total + 255) / 256, size_t(it->sm_count) * 16));
+    if (it->dtype == VX_U8)
+        to_vec_kernel<u8><<<grid, 256, 0, s>>>(it->dev.children, (const u8*)it->dev.values, d_roots, n, depth,
+                                                (u8*)d_dense);
+    else
+        to_vec_kernel<int32_t><<<grid, 256, 0, s>>>(it->dev.children, (const int32_t*)it->dev.values, d_roots, n,
+                                                     depth, (int32_t*)d_dense);
+    CU_TRY(cudaGetLastError());
+    if (!dev_dense) CU_TRY(cudaMemcpyAsync(dense, d_dense, total * esz, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    return VX_OK;
+}
+
+int vx_tree_to_vec(const vx_interner* it, const vx_tree* t, void* dense) {
+    if (!t) return fail(VX_E_INVALID, "null tree");
+    return vx_roots_to_vec(it, t->depth, 1, &t->root, dense);
+}
+
+// ------------------------------------------------------------------------------- fill / clear / set_root
+int vx_tree_set_root_id(vx_interner*, vx_tree*, vx_block_id) {
+    return fail(VX_E_UNSUPPORTED, "set_root_id is not implemented yet");
+}
+int vx_tree_fill(vx_interner* it, vx_tree* t, int64_t value) {
+    if (!it || !t) return fail(VX_E_INVALID, "null argument");
+    if (t->root != VX_BLOCK_EMPTY) return fail(VX_E_UNSUPPORTED, "fill on a built tree needs release (SURVEY 8f-1)");
+    int64_t v = it->dtype == VX_U8 ? int64_t(u8(value)) : int64_t(int32_t(value));
+    if (v == 0) return VX_OK;  // fill(default) == clear (voxtree.rs:269-279)
+    // a fill-only batch on a fresh tree is exactly get_or_create_leaf(value) + root handle
+    uint8_t flag = VX_FLAG_FILL;
+    vx_block_id root = 0;
+    uint8_t changed = 0;
+    // masks/values are not read for a fill-only chunk; pass any valid device pointer
+    int rc = ensure_scratch(it, 256, 0);
+    if (rc != VX_OK) return rc;
+    rc = vx_apply_batches_slab(it, t->depth, 1, (const uint8_t*)it->scratch, it->scratch, &flag, &v, &root, &changed);
+    if (rc != VX_OK) return rc;
+    t->root = root;
+    t->dirty = true;
+    return VX_OK;
+}
+int vx_tree_clear(vx_interner* it, vx_tree* t) {
+    if (!it || !t) return fail(VX_E_INVALID, "null argument");
+    if (t->root == VX_BLOCK_EMPTY) return VX_OK;  // voxtree.rs:283-292
+    return fail(VX_E_UNSUPPORTED, "clear on a built tree needs release (SURVEY 8f-1)");
+}
+
+}  // extern "C"
