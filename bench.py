@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py — chunks/s built+interned ("perlin dunes" world of 32^3 chunks) on N B200s.
+
+Contract (see the task brief): one JSON line on rank 0.
+  step      = one pass of the hot path over the rank's world: interner reset + ONE apply_batches
+              launch over 64x8x64 = 32 768 chunks of 32^3 voxels (u8), batches resident in HBM.
+  value     = chunks/s, whole job (sum over ranks / max-over-ranks device time), weak scaling:
+              every rank builds its own 64x8x64 world (X offset = rank * 64 chunks).
+  e2e       = the same through the C ABI with HOST (pinned) batches: H2D of masks+values and D2H of
+              the root ids inside the timed region (vx_apply_batches_slab).
+  roofline  = algorithmic bytes per launch / CUDA-event duration of the apply kernel,
+              against MEASURED_PEAKS.json:hbm_gbs.
+  cpu_baseline / --impl reference = the CPU oracle (a C++ restatement of the reference's Rust
+              apply_batch; the Rust reference cannot be built in this image) on the host cores.
+Inputs are synthetic (seeded integer value-noise height field); input size 1.34 GB per step is larger
+than the 126 MB L2, so no explicit L2 flush is needed between steps.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GRID = (64, 8, 64)          # chunks along x, y, z (BASELINE.json config 3)
+DEPTH = 5
+BUDGET = 256 << 20          # VoxInterner memory budget per GPU (README quick-start value)
+NODE_BYTES = 87             # 78 + sizeof(u8) payload + 8 B table slot per NEW node
+CHUNK_BYTES = 2 * 4096 + 8 * 4096 + 8   # masks + values read once + root id written
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [int(r[0]) for r in self.rows if r and r[0].isdigit()]
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i] == "Active"})
+        return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def log(msg: str):
+    print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
+def make_world(rank: int, variant="surface_only"):
+    from voxelis_b200 import workloads as wl
+    return wl.terrain_world(GRID, DEPTH, variant, wl.U8, x_chunk_offset=rank * GRID[0],
+                            materials=3 if variant != "surface_only" else 1)
+
+
+def cpu_baseline(masks, values, threads: int, target_s: float = 12.0):
+    """Oracle (kind 'port') on the host cores: fresh-tree apply over the same batches, one private
+    interner per thread, repeated until ~target_s of CPU work."""
+    from oracle import oracle
+    n = masks.shape[0]
+    t, _ = oracle.time_apply_fresh(0, DEPTH, BUDGET, masks, values, threads)
+    reps, total, chunks = 1, t, n
+    while total < target_s and reps < 64:
+        t, _ = oracle.time_apply_fresh(0, DEPTH, BUDGET, masks, values, threads)
+        total += t
+        chunks += n
+        reps += 1
+    return {"value": chunks / total, "unit": "chunks/s", "cores": threads, "kind": "port",
+            "sample": f"{reps} x full {n}-chunk world ({total:.1f} s), fresh interner per repetition, "
+                      f"{threads} thread(s) x private interner"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU apply_batch (oracle port) with all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    masks, values = make_world(0)
+    n = masks.shape[0]
+    from oracle import oracle
+    for _ in range(max(args.warmup, 1)):
+        oracle.time_apply_fresh(0, DEPTH, BUDGET, masks, values, threads)
+    times = [oracle.time_apply_fresh(0, DEPTH, BUDGET, masks, values, threads)[0] for _ in range(args.steps)]
+    total = sum(times)
+    v = n * args.steps / total
+    line = {
+        "impl": "reference", "metric": "chunks/s built+interned (perlin 32^3)", "value": v, "unit": "chunks/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "perlin_dunes_surface_only_64x8x64_d5_u8", "chunks_per_step": n, "depth": DEPTH,
+                   "interner_budget_bytes": BUDGET},
+        "cpu_baseline": {"value": v, "unit": "chunks/s", "cores": threads, "kind": "port",
+                         "sample": f"full {n}-chunk world per step, {threads} threads x private interner; "
+                                   "C++ oracle port (Rust reference not buildable here)"},
+        "e2e": {"value": v, "unit": "chunks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-others", action="store_true", help="skip the secondary workloads")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    import voxelis_b200 as vx
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: voxelis_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---------------------------------------------------------------- inputs
+    log("generating the perlin-dunes world")
+    masks, values = make_world(rank)
+    n = masks.shape[0]
+    log(f"{n} chunks generated; uploading")
+    h_masks = torch.from_numpy(masks).pin_memory()
+    h_values = torch.from_numpy(values).pin_memory()
+    d_masks = h_masks.to(dev)
+    d_values = h_values.to(dev)
+    d_roots = torch.zeros(n, dtype=torch.int64, device=dev)
+    d_changed = torch.zeros(n, dtype=torch.uint8, device=dev)
+    it = vx.VoxInterner.with_memory_budget(BUDGET, vx.U8, local_rank)
+    stream = torch.cuda.current_stream(dev)
+
+    def step_device():
+        it.reset()
+        it.apply_batches_device(DEPTH, n, d_masks.data_ptr(), d_values.data_ptr(), d_roots.data_ptr(),
+                                d_changed.data_ptr(), stream=stream.cuda_stream)
+
+    # ---------------------------------------------------------------- device-resident timing
+    log("warm-up")
+    for _ in range(args.warmup):
+        step_device()
+    torch.cuda.synchronize()
+    it.sync()
+    new_nodes = it.stats()["total_cache_misses"]
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    kernel_ms = []
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    kev = []
+    for _ in range(args.steps):
+        it.reset()
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record(stream)
+        it.apply_batches_device(DEPTH, n, d_masks.data_ptr(), d_values.data_ptr(), d_roots.data_ptr(),
+                                d_changed.data_ptr(), stream=stream.cuda_stream)
+        k1.record(stream)
+        kev.append((k0, k1))
+    e1.record(stream)
+    barrier()
+    it.sync()
+    clocks = sampler.stop()
+    step_ms = e0.elapsed_time(e1) / args.steps
+    kernel_ms = [a.elapsed_time(b) for a, b in kev]
+    step_ms_max = max_over_ranks(step_ms)
+    total_chunks = sum_over_ranks(float(n))
+    value = total_chunks / (step_ms_max * 1e-3)
+    kern_ms = float(np.mean(kernel_ms))
+
+    log(f"device-resident: {step_ms_max:.3f} ms/step, kernel {kern_ms:.3f} ms")
+    # ---------------------------------------------------------------- end to end (host batches)
+    roots_host = np.zeros(n, np.uint64)
+    changed_host = np.zeros(n, np.uint8)
+    for _ in range(2):
+        it.reset()
+        it.apply_batches_slab(DEPTH, h_masks.numpy(), h_values.numpy(), roots_out=roots_host,
+                              changed_out=changed_host)
+    e2e_steps = max(3, min(args.steps, 5))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        it.reset()
+        it.apply_batches_slab(DEPTH, h_masks.numpy(), h_values.numpy(), roots_out=roots_host,
+                              changed_out=changed_host)
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    barrier()
+    e2e_ms_max = max_over_ranks(e2e_ms)
+    e2e_value = total_chunks / (e2e_ms_max * 1e-3)
+
+    # ---------------------------------------------------------------- roofline of the apply kernel
+    peak, peak_src = peaks()
+    algo_bytes = n * CHUNK_BYTES + new_nodes * NODE_BYTES
+    achieved = algo_bytes / (kern_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("perlin_dunes_surface_only", {}).get("dram_bytes_per_launch")
+
+    # ---------------------------------------------------------------- secondary workloads (rank 0)
+    others = {}
+    if rank == 0 and not args.no_others:
+        from voxelis_b200 import workloads as wl
+        del it                                    # one interner at a time: free the headline one first
+        # (name, generator, interner budget): random255 creates ~4 936 new nodes per chunk
+        sets = [("checkerboard_x4096", lambda: wl.named_workload("checkerboard", 4096), BUDGET),
+                ("set_sum_x4096", lambda: wl.named_workload("sum", 4096), BUDGET),
+                ("sum_per_chunk_x4096", lambda: wl.named_workload("sum_per_chunk", 4096), BUDGET),
+                ("random255_x4096", lambda: wl.named_workload("random255", 4096), 2 << 30),
+                ("perlin_surface_and_below_3mat", lambda: make_world(0, "surface_and_below"), BUDGET)]
+        for name, gen, budget in sets:
+            try:
+                log(f"secondary workload {name}")
+                m2, v2 = gen()
+                n2 = m2.shape[0]
+                it2 = vx.VoxInterner.with_memory_budget(budget, vx.U8, local_rank)
+                dm, dv = torch.from_numpy(m2).to(dev), torch.from_numpy(v2).to(dev)
+                dr = torch.zeros(n2, dtype=torch.int64, device=dev)
+                ts = []
+                for i in range(6):
+                    it2.reset()
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record(stream)
+                    it2.apply_batches_device(DEPTH, n2, dm.data_ptr(), dv.data_ptr(), dr.data_ptr(),
+                                             stream=stream.cuda_stream)
+                    b.record(stream)
+                    torch.cuda.synchronize()
+                    it2.sync()
+                    if i >= 2:
+                        ts.append(a.elapsed_time(b))
+                nn = it2.stats()["total_cache_misses"]
+                ms = float(np.mean(ts))
+                ab = n2 * CHUNK_BYTES + nn * NODE_BYTES
+                others[name] = {"chunks_per_s": n2 / (ms * 1e-3), "kernel_ms": ms, "new_nodes": nn,
+                                "achieved_gbs": ab / (ms * 1e-3) / 1e9, "frac": ab / (ms * 1e-3) / 1e9 / peak}
+                del dm, dv, dr, it2
+            except Exception as e:  # a secondary workload must never take the headline line down
+                others[name] = {"error": str(e)}
+
+    cpu = None
+    log("cpu baseline")
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_baseline(masks, values, 1)
+        cpu["all_cores"] = cpu_baseline(masks, values, os.cpu_count() or 1, target_s=6.0)
+
+    if rank == 0:
+        line = {
+            "metric": "chunks/s built+interned (perlin 32^3)", "value": value, "unit": "chunks/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms_max,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "perlin_dunes_surface_only_64x8x64_d5_u8", "chunks_per_step_per_gpu": n,
+                       "depth": DEPTH, "interner_budget_bytes": BUDGET, "new_nodes_per_step": new_nodes,
+                       "l2": "inputs (1.34 GB/step) exceed the 126 MB L2; interner reset every step",
+                       "step": "vx_interner_reset + one vx_apply_batches_device launch"},
+            "e2e": {"value": e2e_value, "unit": "chunks/s", "ms_per_step": e2e_ms_max,
+                    "h2d_bytes_per_step": int(masks.nbytes + values.nbytes), "d2h_bytes_per_step": int(n * 9)},
+            "gpu_launches": args.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "apply_large_kernel<u8>",
+                         "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": algo_bytes},
+            "clocks": clocks,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        if others:
+            line["others"] = others
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -74,7 +74,7 @@ def test_fill_variants(gpu_api, oracle_api, depth, dtype):
     masks[4, :, 0] = 0xFF
     values[4] = 9
     r = parity.build_both(gpu_api, oracle_api, depth, masks, values, dtype, fill=3)
-    parity.assert_parity(gpu_api, oracle_api, depth, *r)
+    parity.assert_parity(gpu_api, oracle_api, depth, *r, indeg=False)
     # fill only (no patches): root is the fill leaf, ref 1
     r = parity.build_both(gpu_api, oracle_api, depth, masks[:2] * 0, values[:2] * 0, dtype, fill=5, has_patches=False)
     assert gpu_api.id_is_leaf(r[1][0]) and r[1][0] == r[1][1]
@@ -85,7 +85,7 @@ def test_fill_variants(gpu_api, oracle_api, depth, dtype):
     v2[0, 5, 0] = v2[0, 5, 2] = 3
     r = parity.build_both(gpu_api, oracle_api, depth, m2, v2, dtype, fill=3)
     assert r[2][0] == 0 and r[1][0] == 0
-    parity.assert_parity(gpu_api, oracle_api, depth, *r)
+    parity.assert_parity(gpu_api, oracle_api, depth, *r, indeg=False)
 
 
 def test_known_answers_d5(gpu_api):

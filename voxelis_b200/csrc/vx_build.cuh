@@ -82,6 +82,20 @@ struct VT<u8> {
         u64 bm = expand_bits(m);
         return Key{{(k.w[0] & bm) | ((u64(f) * 0x0101010101010101ull) & ~bm)}};
     }
+    static __device__ __forceinline__ Key splat(u32 f) { return Key{{u64(f & 0xFF) * 0x0101010101010101ull}}; }
+    static __device__ __forceinline__ u32 ne_key(const Key& a, const Key& b) { return nzbytes(a.w[0] ^ b.w[0]); }
+    static __device__ __forceinline__ Key select_key(const Key& k, u32 m, const Key& o) {  // set ? value : old
+        u64 bm = expand_bits(m);
+        return Key{{(k.w[0] & bm) | (o.w[0] & ~bm)}};
+    }
+    // lane li of an 8-lane group contributes value v; every lane of the group receives the assembled key
+    static __device__ __forceinline__ Key assemble(u32 v, int li) {
+        u64 w = u64(v & 0xFF) << (8 * li);
+        w |= __shfl_xor_sync(FULL, w, 1);
+        w |= __shfl_xor_sync(FULL, w, 2);
+        w |= __shfl_xor_sync(FULL, w, 4);
+        return Key{{w}};
+    }
     static __device__ __forceinline__ bool eq(const Key& a, const Key& b) { return a.w[0] == b.w[0]; }
     static __device__ __forceinline__ u32 hash(const Key& k) { return u32(mix64(k.w[0]) >> 32); }
     // value of child `li` of the key held by lane `src` (full-warp shuffle)
@@ -137,6 +151,38 @@ struct VT<int32_t> {
             u32 lo = (m >> (2 * j)) & 1 ? u32(k.w[j]) : f;
             u32 hi = (m >> (2 * j + 1)) & 1 ? u32(k.w[j] >> 32) : f;
             r.w[j] = u64(lo) | (u64(hi) << 32);
+        }
+        return r;
+    }
+    static __device__ __forceinline__ Key splat(u32 f) {
+        u64 w = u64(f) * 0x0000000100000001ull;
+        return Key{{w, w, w, w}};
+    }
+    static __device__ __forceinline__ u32 ne_key(const Key& a, const Key& b) {
+        u32 m = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) m |= u32(get(a, i) != get(b, i)) << i;
+        return m;
+    }
+    static __device__ __forceinline__ Key select_key(const Key& k, u32 m, const Key& o) {
+        Key r;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            u32 lo = (m >> (2 * j)) & 1 ? u32(k.w[j]) : u32(o.w[j]);
+            u32 hi = (m >> (2 * j + 1)) & 1 ? u32(k.w[j] >> 32) : u32(o.w[j] >> 32);
+            r.w[j] = u64(lo) | (u64(hi) << 32);
+        }
+        return r;
+    }
+    static __device__ __forceinline__ Key assemble(u32 v, int li) {
+        Key r;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            u64 w = (li >> 1) == j ? u64(v) << (32 * (li & 1)) : 0;
+            w |= __shfl_xor_sync(FULL, w, 1);
+            w |= __shfl_xor_sync(FULL, w, 2);
+            w |= __shfl_xor_sync(FULL, w, 4);
+            r.w[j] = w;
         }
         return r;
     }
@@ -196,8 +242,24 @@ struct Ctx {
     WarpSmem<T>* ws;
     CtaSmem* cs;
     int lane, li, gs;  // lane, lane within 8-group, first lane of my group
+    bool use_free;     // the free list holds recycled indices: pop them before next_index (macros.rs:1-41)
     Tally t;
 };
+
+// get_next_index_macro! (interner/macros.rs:1-41) for one node: recycled index first (LIFO), else
+// next_index++.  `*gen` = generation to stamp into the BlockId.  Indices >= capacity mean "Out of memory".
+__device__ __forceinline__ u32 alloc_one(const InternerDev& in, bool use_free, u32* gen) {
+    *gen = 0;
+    if (use_free) {
+        int old = atomicSub((int*)in.free_count, 1);
+        if (old > 0) {
+            u32 idx = ld_strong(&in.free_list[old - 1]);
+            *gen = ld_strong_u16(&in.gens[idx]);
+            return idx;
+        }
+    }
+    return atomicAdd(in.next_index, 1u);
+}
 
 // ------------------------------------------------------------------------------------------------
 // Leaves — get_or_create_leaf (interner/mod.rs:627-710).  Warp-converged; `need` predicates lanes.
@@ -218,14 +280,15 @@ __device__ inline u64 leaf_get(Ctx<u8>& c, u32 v, bool need) {
             if (g == 0) {
                 u64 old = atomicCAS((ull*)&c.in.leaf_u8[v], 0ull, (ull)ID_PENDING);
                 if (old == 0) {  // this lane creates the leaf
-                    u32 idx = atomicAdd(c.in.next_index, 1u);
+                    u32 gen;
+                    u32 idx = alloc_one(c.in, c.use_free, &gen);
                     if (idx >= c.in.capacity) {
                         set_error(c.in, ERR_OOM);
                         st_strong(&c.in.leaf_u8[v], 0);
                         miss = false;
                     } else {
                         leaf_payload<u8>(c.in, idx, v);
-                        id = id_leaf(u64(idx));  // fresh index: generation 0
+                        id = id_leaf((u64(gen) << 32) | idx);
                         fence_gpu();
                         st_strong(&c.in.leaf_u8[v], id);
                         c.cs->leaf[v] = id;
@@ -262,13 +325,14 @@ __device__ inline u64 leaf_get(Ctx<int32_t>& c, u32 v, bool need) {
             if (k == 0) {
                 u64 old = atomicCAS((ull*)&c.in.leaf_keys[s], 0ull, (ull)mykey);
                 if (old == 0) {
-                    u32 idx = atomicAdd(c.in.next_index, 1u);
+                    u32 gen;
+                    u32 idx = alloc_one(c.in, c.use_free, &gen);
                     if (idx >= c.in.capacity) {
                         set_error(c.in, ERR_OOM);
                         miss = false;
                     } else {
                         leaf_payload<int32_t>(c.in, idx, v);
-                        id = id_leaf(u64(idx));
+                        id = id_leaf((u64(gen) << 32) | idx);
                         fence_gpu();
                         st_strong(&c.in.leaf_ids[s], id);
                         c.t.leaf_miss++;
@@ -387,11 +451,20 @@ __device__ inline u64 intern_branch(Ctx<T>& c, bool need, u64 child, u32 cval) {
         }
         const u32 cb = __ballot_sync(FULL, claimed);  // bits at lanes 0, 8, 16, 24
         if (cb != 0) {                                // warp-uniform: someone creates a node
-            u32 base = 0;
-            if (lane == 0) base = atomicAdd(in.next_index, u32(__popc(cb)));
-            base = __shfl_sync(FULL, base, 0);
             const bool mine = (cb >> gs) & 1;
-            const u32 idx = base + __popc(cb & ((1u << gs) - 1));
+            u32 idx, gen = 0;
+            if (!c.use_free) {  // one aggregated atomic for all nodes the warp creates this round
+                u32 base = 0;
+                if (lane == 0) base = atomicAdd(in.next_index, u32(__popc(cb)));
+                base = __shfl_sync(FULL, base, 0);
+                idx = base + __popc(cb & ((1u << gs) - 1));
+            } else {
+                idx = 0;
+                if (mine && li == 0) idx = alloc_one(in, true, &gen);
+                idx = __shfl_sync(FULL, idx, gs);
+                gen = __shfl_sync(FULL, gen, gs);
+            }
+            const u64 genidx = (u64(gen) << 32) | idx;
             const bool oom = idx >= in.capacity;
             // LOD value = mode of the child values (core/voxel.rs:96-141): most frequent; ties go to
             // a non-default value, then to the earliest first occurrence.
@@ -428,10 +501,10 @@ __device__ inline u64 intern_branch(Ctx<T>& c, bool need, u64 child, u32 cval) {
             if (mine) {
                 if (li == 0) {
                     fence_gpu();
-                    st_strong(&in.slots[size_t(bucket) * 8 + ek],
-                              oom ? u64(IDX_TOMB) : ((u64(fp) << 47) | u64(idx)));
+                    // out of memory: hand the slot back (the interner is poisoned, results are discarded)
+                    st_strong(&in.slots[size_t(bucket) * 8 + ek], oom ? u64(0) : ((u64(fp) << 47) | genidx));
                 }
-                result = oom ? 0 : id_branch(u64(idx), leafb, presb);
+                result = oom ? 0 : id_branch(genidx, leafb, presb);
                 done = true;
             }
         }
@@ -465,19 +538,35 @@ __device__ inline u64 intern_branch(Ctx<T>& c, bool need, u64 child, u32 cval) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Old-tree lookup for applies on NON-EMPTY trees (voxtree.rs:785-822, :930-952): the node the old
+// tree holds at position `prefix` (d three-bit child indices, MSB first) of depth d.  Returns a
+// branch id, the enclosing Leaf if the old tree is uniform above/at that position, or EMPTY.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ u64 old_at(const InternerDev& in, u64 root, u32 prefix, int d) {
+    u64 node = root;
+    for (int k = 0; k < d; ++k) {
+        if (node == 0 || id_is_leaf(node)) return node;
+        u32 ci = (prefix >> (3 * (d - 1 - k))) & 7;
+        node = ld_strong(&in.children[size_t(id_index(node)) * 8 + ci]);
+    }
+    return node;
+}
+
+// ------------------------------------------------------------------------------------------------
 // One level of phase 2 (voxtree.rs:905-1106) for four parents per warp: lanes gs..gs+7 hold the
-// eight child ids (absent children already replaced by Leaf(fill) / EMPTY).  `present` = the child
-// entered `paths`.  Returns the parent id to all lanes of the group; *ppresent = parent entered paths.
+// eight child ids; children that did not enter `paths` already carry what the reference clones
+// into the slot (old child / enclosing old leaf / fill leaf / EMPTY, :1013-1048).  `old_self` = the
+// same for the parent itself, used when none of its children entered `paths`.
 // ------------------------------------------------------------------------------------------------
 template <class T>
-__device__ inline u64 parent_node(Ctx<T>& c, u64 child, bool present, bool* ppresent) {
+__device__ inline u64 parent_node(Ctx<T>& c, u64 child, bool present, u64 old_self, bool* ppresent) {
     const int gs = c.gs;
     u64 c0 = __shfl_sync(FULL, child, gs);
     u32 same = (__ballot_sync(FULL, child == c0) >> gs) & 0xFF;
     u32 pres = (__ballot_sync(FULL, present) >> gs) & 0xFF;
     const bool any_present = pres != 0;
-    // all eight EMPTY -> nothing there; all eight the same Leaf -> uniform collapse (:1050, :1062-1075)
-    const bool collapse = same == 0xFF && (c0 == 0 || id_is_leaf(c0));
+    // types == 0xFF and eight identical ids -> uniform collapse (:1050, :1062-1075)
+    const bool collapse = same == 0xFF && id_is_leaf(c0);
     if (any_present && c.li == 0) {
         if (collapse)
             c.t.collapsed++;
@@ -485,27 +574,29 @@ __device__ inline u64 parent_node(Ctx<T>& c, u64 child, bool present, bool* ppre
             c.t.branch_calls++;
     }
     u64 id = intern_branch<T, false>(c, any_present && !collapse, child, 0);
-    if (collapse || !any_present) id = c0;  // absent parent: all children are the same filler
+    if (any_present && collapse) id = c0;
+    if (!any_present) id = old_self;
     *ppresent = any_present;
     return id;
 }
 
 // ------------------------------------------------------------------------------------------------
-// Phase 1 (voxtree.rs:770-897) for 32 blocks per warp, one per lane.
+// Phase 1 (voxtree.rs:770-897) for 32 blocks per warp, one per lane.  `oldw` = the eight voxel values
+// the block has before the batch (old tree / fill / 0), `old_id` = the node standing there.
 // ------------------------------------------------------------------------------------------------
 template <class T>
-__device__ inline u64 block_node(Ctx<T>& c, bool active, typename VT<T>::Key vals, u32 set_mask, bool has_fill,
-                                 u32 fill, u64 fill_leaf, bool* present) {
+__device__ inline u64 block_node(Ctx<T>& c, bool active, typename VT<T>::Key vals, u32 set_mask,
+                                 typename VT<T>::Key oldw, u64 old_id, bool* present) {
     using V = VT<T>;
     const int lane = c.lane;
     // a set bit whose value is the default cannot come from Batch::set (batch.rs:162-168): ignored
     u32 m = active ? (set_mask & V::nz(vals)) : 0;
-    const bool all_same = m == 0xFF && V::uniform(vals);               // :826
-    const u32 changed_bits = has_fill ? (m & V::ne_mask(vals, fill)) : m;  // :853-856 skip unchanged
-    const bool touched = all_same || changed_bits != 0;                // :865-868
+    const bool all_same = m == 0xFF && V::uniform(vals);  // :826
+    const u32 changed_bits = m & V::ne_key(vals, oldw);   // :853-856 unchanged voxels are skipped
+    const bool touched = all_same || changed_bits != 0;   // :865-868
     *present = touched;
     const bool need_branch = touched && !all_same;
-    typename V::Key eff = V::select(vals, m, has_fill ? fill : 0);
+    typename V::Key eff = V::select_key(vals, m, oldw);
     if (touched) {
         c.t.leaf_calls += all_same ? 1u : u32(__popc(changed_bits));
         if (all_same)
@@ -513,7 +604,7 @@ __device__ inline u64 block_node(Ctx<T>& c, bool active, typename VT<T>::Key val
         else
             c.t.branch_calls++;
     }
-    u64 id = touched ? 0 : fill_leaf;  // absent block: the enclosing fill leaf, or EMPTY
+    u64 id = touched ? 0 : old_id;  // untouched block: whatever stands there already
     // uniform collapse -> Leaf(value)
     u64 lid = leaf_get(c, V::first(vals), all_same);
     if (all_same) id = lid;
@@ -589,21 +680,74 @@ __device__ inline u64 block_node(Ctx<T>& c, bool active, typename VT<T>::Key val
     return id;
 }
 
-// ------------------------------------------------------------------------------------------------
-// A warp builds the sub-tree over `nblocks` (8, 64 or 512) Morton-consecutive blocks.
-// ------------------------------------------------------------------------------------------------
+// What stands at the unit before the batch: nothing, a fill leaf (phase 0), or an old tree.
+struct Under {
+    u64 old_root;  // OLD only
+    u64 fill_leaf; // 0 = none
+    u32 fill;
+    int depth;     // tree depth D
+};
+
+// OLD: old node + old voxel values under each of the warp's 32 blocks (lane = block `blk`).
 template <class T>
-__device__ inline u64 build_unit(Ctx<T>& c, const u8* masks, const void* values, size_t first_block, int nblocks,
-                                 bool has_fill, u32 fill, u64 fill_leaf, bool* upresent) {
+__device__ inline void old_block_state(Ctx<T>& c, const Under& u, u32 blk, bool active, bool wants_values,
+                                       u64* parent_old, u64* old_id, typename VT<T>::Key* oldw) {
+    using V = VT<T>;
+    const InternerDev& in = c.in;
+    // the level-1 parent's old node (group uniform: eight lanes walk the same path, loads coalesce)
+    u64 E = old_at(in, u.old_root, blk >> 3, u.depth - 2);
+    *parent_old = E;
+    u64 ob = E;
+    if (E != 0 && !id_is_leaf(E)) ob = ld_strong(&in.children[size_t(id_index(E)) * 8 + (blk & 7)]);
+    if (!active) ob = 0;
+    *old_id = ob;
+    typename V::Key w = V::zero();
+    const bool need = active && wants_values && ob != 0;
+    if (need && id_is_leaf(ob)) w = V::splat(child_value<T>(in, ob));  // uniform under an old leaf
+    // old block is a branch: its eight voxels are gathered by an 8-lane group, four blocks a round
+    u32 bmask = __ballot_sync(FULL, need && !id_is_leaf(ob));
+    while (bmask != 0) {
+        int src = __fns(bmask, 0, (c.gs >> 3) + 1);
+        const bool gvalid = src >= 0 && src < 32;
+        if (!gvalid) src = 0;
+        u64 gob = __shfl_sync(FULL, ob, src);
+        u64 ch = gvalid ? ld_strong(&in.children[size_t(id_index(gob)) * 8 + c.li]) : 0;
+        u32 v = (gvalid && ch != 0) ? child_value<T>(in, ch) : 0;
+        typename V::Key gk = V::assemble(v, c.li);
+        u32 done = 0;
+#pragma unroll
+        for (int g2 = 0; g2 < 4; ++g2) {
+            typename V::Key k2 = V::bcast(gk, g2 * 8);
+            int s2 = __shfl_sync(FULL, src, g2 * 8);
+            bool v2 = __shfl_sync(FULL, int(gvalid), g2 * 8) != 0;
+            if (v2) {
+                done |= 1u << s2;
+                if (c.lane == s2) w = k2;
+            }
+        }
+        bmask &= ~done;
+    }
+    *oldw = w;
+}
+
+// ------------------------------------------------------------------------------------------------
+// A warp builds the sub-tree over `nblocks` (8, 64 or 512) Morton-consecutive blocks starting at
+// block `first_block` of the chunk.
+// ------------------------------------------------------------------------------------------------
+template <class T, bool OLD>
+__device__ inline u64 build_unit(Ctx<T>& c, const u8* masks, const void* values, u32 first_block, int nblocks,
+                                 const Under& u, bool* upresent) {
     using V = VT<T>;
     const int lane = c.lane;
     const int n_iter = (nblocks + 31) / 32;
+    const int D = u.depth;
+    const typename V::Key fillw = V::splat(u.fill_leaf ? u.fill : 0);
     // software prefetch: loads of iteration it+1 are issued before iteration it is processed
     typename V::Key nvals = V::zero();
     u32 nmask = 0;
     if (lane < nblocks) {
-        nvals = V::load(values, first_block + lane);
-        nmask = ld_stream_u16(masks + (first_block + lane) * 2) & 0xFF;
+        nvals = V::load(values, size_t(first_block) + lane);
+        nmask = ld_stream_u16(masks + (size_t(first_block) + lane) * 2) & 0xFF;
     }
     for (int it = 0; it < n_iter; ++it) {
         typename V::Key vals = nvals;
@@ -611,17 +755,19 @@ __device__ inline u64 build_unit(Ctx<T>& c, const u8* masks, const void* values,
         const bool active = it * 32 + lane < nblocks;
         const int nb = (it + 1) * 32 + lane;
         if (nb < nblocks) {
-            nvals = V::load(values, first_block + nb);
-            nmask = ld_stream_u16(masks + (first_block + nb) * 2) & 0xFF;
+            nvals = V::load(values, size_t(first_block) + nb);
+            nmask = ld_stream_u16(masks + (size_t(first_block) + nb) * 2) & 0xFF;
         }
+        typename V::Key oldw = fillw;
+        u64 old_id = u.fill_leaf, parent_old = u.fill_leaf;
+        if (OLD) old_block_state<T>(c, u, first_block + it * 32 + lane, active, (smask & 0xFF) != 0, &parent_old, &old_id, &oldw);
         bool present;
-        u64 id = block_node<T>(c, active, vals, smask, has_fill, fill, fill_leaf, &present);
+        u64 id = block_node<T>(c, active, vals, smask, oldw, old_id, &present);
         bool pp;
-        u64 pid = parent_node<T>(c, id, present && active, &pp);
-        if (c.li == 0 && it * 32 + c.gs < nblocks) {
-            c.ws->l1[it * 4 + (c.gs >> 3)] = pid;
-        }
-        u32 ppb = __ballot_sync(FULL, pp && c.li == 0 && it * 32 + c.gs < nblocks);
+        u64 pid = parent_node<T>(c, id, present && active, parent_old, &pp);
+        const bool gact = it * 32 + c.gs < nblocks;
+        if (c.li == 0 && gact) c.ws->l1[it * 4 + (c.gs >> 3)] = pid;
+        u32 ppb = __ballot_sync(FULL, pp && c.li == 0 && gact);
         if (lane == 0) {
             // compact the four group bits (lanes 0,8,16,24) into bits 0..3
             u32 four = (ppb & 1) | ((ppb >> 7) & 2) | ((ppb >> 14) & 4) | ((ppb >> 21) & 8);
@@ -638,15 +784,17 @@ __device__ inline u64 build_unit(Ctx<T>& c, const u8* masks, const void* values,
         __syncwarp();
         return r;
     }
-    // level 2: n1 (8 or 64) nodes -> n1/8
+    // level 2: n1 (8 or 64) nodes at depth D-2 -> n1/8 parents at depth D-3
     u32 p2 = 0;
     for (int it = 0; it * 32 < n1; ++it) {
         const int i = it * 32 + lane;
         const bool act = i < n1;
         u64 ch = act ? c.ws->l1[i] : 0;
         bool pr = act && ((c.ws->l1p[i >> 5] >> (i & 31)) & 1);
+        u64 old_self = u.fill_leaf;
+        if (OLD) old_self = old_at(c.in, u.old_root, ((first_block >> 3) + it * 32 + c.gs) >> 3, D - 3);
         bool pp;
-        u64 pid = parent_node<T>(c, ch, pr, &pp);
+        u64 pid = parent_node<T>(c, ch, pr, old_self, &pp);
         const bool gact = it * 32 + c.gs < n1;
         if (c.li == 0 && gact) c.ws->l2[it * 4 + (c.gs >> 3)] = pid;
         u32 ppb = __ballot_sync(FULL, pp && c.li == 0 && gact);
@@ -661,13 +809,15 @@ __device__ inline u64 build_unit(Ctx<T>& c, const u8* masks, const void* values,
         __syncwarp();
         return r;
     }
-    // level 3: 8 nodes -> 1
+    // level 3: 8 nodes at depth D-3 -> 1 parent at depth D-4
     {
         const bool act = lane < 8;
         u64 ch = act ? c.ws->l2[lane] : 0;
         bool pr = act && ((p2 >> lane) & 1);
+        u64 old_self = u.fill_leaf;
+        if (OLD) old_self = old_at(c.in, u.old_root, first_block >> 9, D - 4);
         bool pp;
-        u64 pid = parent_node<T>(c, ch, pr, &pp);
+        u64 pid = parent_node<T>(c, ch, pr, old_self, &pp);
         pid = __shfl_sync(FULL, pid, 0);
         *upresent = __shfl_sync(FULL, int(pp), 0) != 0;
         __syncwarp();
@@ -680,20 +830,23 @@ __device__ inline u64 build_unit(Ctx<T>& c, const u8* masks, const void* values,
 // ------------------------------------------------------------------------------------------------
 struct ApplyArgs {
     InternerDev in;
-    const u8* masks;       // [n][B][2]
-    const void* values;    // [n][B][8]
-    const u8* flags;       // [n] or null
+    const u8* masks;         // [n][B][2]
+    const void* values;      // [n][B][8]
+    const u8* flags;         // [n] or null
     const long long* fills;  // [n] or null
-    u64* roots;            // [n]
-    u8* changed;           // [n] or null
+    const u64* old_roots;    // [n] or null (OLD kernels only): root of the tree before the batch
+    u64* roots;              // [n]
+    u8* changed;             // [n] or null
     u32 n;
     u32 depth;
-    u32 blocks;  // B
+    u32 blocks;    // B
+    u32 use_free;  // free list non-empty at launch
 };
 
 template <class T>
-__device__ __forceinline__ void ctx_init(Ctx<T>& c, const InternerDev& in, WarpSmem<T>* ws, CtaSmem* cs) {
+__device__ __forceinline__ void ctx_init(Ctx<T>& c, const InternerDev& in, WarpSmem<T>* ws, CtaSmem* cs, bool use_free) {
     c.in = in;
+    c.use_free = use_free;
     c.lane = threadIdx.x & 31;
     c.li = c.lane & 7;
     c.gs = c.lane & 24;
@@ -768,23 +921,32 @@ __device__ __forceinline__ void chunk_flags(const ApplyArgs& a, u32 chunk, bool*
 
 template <class T>
 __device__ __forceinline__ void write_root(Ctx<T>& c, const ApplyArgs& a, u32 chunk, u64 root, bool changed) {
-    // apply_batch (voxtree.rs:303-328): INVALID -> false, root untouched (EMPTY for a fresh tree)
+    // apply_batch (voxtree.rs:303-328): INVALID -> false and the tree keeps its root.  The caller
+    // owns the old root's release (dec_ref_recursive, :309-314).
     a.roots[chunk] = changed ? root : 0;
     if (a.changed) a.changed[chunk] = changed ? 1 : 0;
     if (changed && root != 0) atomicAdd(&c.in.refs[id_index(root)], 1u);  // the tree's root handle
 }
 
 // D <= 4: a chunk is at most one warp unit -> one warp per chunk.
-template <class T>
+template <class T, bool OLD>
 __global__ void __launch_bounds__(CTA_THREADS, 3) apply_small_kernel(ApplyArgs a) {
     __shared__ WarpSmem<T> ws[WARPS_PER_CTA];
     __shared__ CtaSmem cs;
     smem_init<T>(ws, &cs);
     Ctx<T> c;
-    ctx_init<T>(c, a.in, ws, &cs);
+    ctx_init<T>(c, a.in, ws, &cs, a.use_free != 0);
     const u32 warp_global = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
     const u32 nwarps = gridDim.x * WARPS_PER_CTA;
     for (u32 chunk = warp_global; chunk < a.n; chunk += nwarps) {
+        // poisoned interner: skip the rest, the host reports the error (warp-uniform decision)
+        if (__any_sync(FULL, c.lane == 0 && ld_strong(a.in.error) != ERR_NONE)) {
+            if (c.lane == 0) {
+                a.roots[chunk] = 0;
+                if (a.changed) a.changed[chunk] = 0;
+            }
+            continue;
+        }
         bool has_fill, has_patches;
         u32 fill;
         chunk_flags<T>(a, chunk, &has_fill, &fill, &has_patches);
@@ -796,26 +958,43 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) apply_small_kernel(ApplyArgs a
             }
             continue;
         }
+        Under u{0, fl, fill, int(a.depth)};
+        // with a fill the batch is built against Leaf(fill); the old tree is only released (:742-754)
+        const bool use_old = OLD && !has_fill && a.old_roots && a.old_roots[chunk] != 0;
+        if (use_old) u.old_root = a.old_roots[chunk];
         bool present;
-        u64 root = build_unit<T>(c, a.masks + size_t(chunk) * a.blocks * 2,
-                                 (const u8*)a.values + size_t(chunk) * a.blocks * 8 * sizeof(T), 0, int(a.blocks),
-                                 has_fill, fill, fl, &present);
+        u64 root;
+        const u8* cm = a.masks + size_t(chunk) * a.blocks * 2;
+        const void* cv = (const u8*)a.values + size_t(chunk) * a.blocks * 8 * sizeof(T);
+        if (use_old)
+            root = build_unit<T, OLD>(c, cm, cv, 0, int(a.blocks), u, &present);
+        else
+            root = build_unit<T, false>(c, cm, cv, 0, int(a.blocks), u, &present);
         if (c.lane == 0) write_root<T>(c, a, chunk, root, present);
     }
     cta_finish<T>(c);
 }
 
 // D >= 5: one CTA per chunk; each warp builds 512-block units, warp 0 joins the upper levels.
-template <class T>
+template <class T, bool OLD>
 __global__ void __launch_bounds__(CTA_THREADS, 3) apply_large_kernel(ApplyArgs a) {
     __shared__ WarpSmem<T> ws[WARPS_PER_CTA];
     __shared__ CtaSmem cs;
     smem_init<T>(ws, &cs);
     Ctx<T> c;
-    ctx_init<T>(c, a.in, ws, &cs);
+    ctx_init<T>(c, a.in, ws, &cs, a.use_free != 0);
     const int warp = threadIdx.x >> 5;
+    const int D = int(a.depth);
     const u32 n_super = a.blocks / (UNIT_BLOCKS * WARPS_PER_CTA);  // 32^3 sub-cubes: 1, 8, 64
     for (u32 chunk = blockIdx.x; chunk < a.n; chunk += gridDim.x) {
+        // poisoned interner: skip the rest, the host reports the error (CTA-uniform decision)
+        if (__syncthreads_or(threadIdx.x == 0 && ld_strong(a.in.error) != ERR_NONE)) {
+            if (threadIdx.x == 0) {
+                a.roots[chunk] = 0;
+                if (a.changed) a.changed[chunk] = 0;
+            }
+            continue;
+        }
         bool has_fill, has_patches;
         u32 fill;
         chunk_flags<T>(a, chunk, &has_fill, &fill, &has_patches);
@@ -836,23 +1015,32 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) apply_large_kernel(ApplyArgs a
             }
             continue;
         }
+        Under u{0, fl, fill, D};
+        const bool use_old = OLD && !has_fill && a.old_roots && a.old_roots[chunk] != 0;
+        if (use_old) u.old_root = a.old_roots[chunk];
         const u8* cm = a.masks + size_t(chunk) * a.blocks * 2;
         const void* cv = (const u8*)a.values + size_t(chunk) * a.blocks * 8 * sizeof(T);
         for (u32 s = 0; s < n_super; ++s) {
             bool present;
-            u64 uid = build_unit<T>(c, cm, cv, (size_t(s) * WARPS_PER_CTA + warp) * UNIT_BLOCKS, UNIT_BLOCKS, has_fill,
-                                    fill, fl, &present);
+            const u32 fb = (s * WARPS_PER_CTA + warp) * UNIT_BLOCKS;
+            u64 uid;
+            if (use_old)
+                uid = build_unit<T, OLD>(c, cm, cv, fb, UNIT_BLOCKS, u, &present);
+            else
+                uid = build_unit<T, false>(c, cm, cv, fb, UNIT_BLOCKS, u, &present);
             if (c.lane == 0) {
                 cs.oct[warp] = uid;
                 cs.octp[warp] = present;
             }
             __syncthreads();
-            if (warp == 0) {
+            if (warp == 0) {  // the eight 16^3 units of one 32^3 cube (depth D-4) -> its node at depth D-5
                 const bool act = c.lane < 8;
                 u64 ch = act ? cs.oct[c.lane] : 0;
                 bool pr = act && cs.octp[c.lane] != 0;
+                u64 old_self = fl;
+                if (use_old) old_self = old_at(c.in, u.old_root, s, D - 5);
                 bool pp;
-                u64 pid = parent_node<T>(c, ch, pr, &pp);
+                u64 pid = parent_node<T>(c, ch, pr, old_self, &pp);
                 if (c.lane == 0) {
                     cs.top[s] = pid;
                     cs.topp[s] = pp;
@@ -862,15 +1050,18 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) apply_large_kernel(ApplyArgs a
         }
         if (warp == 0) {
             u32 n = n_super;
+            int d = D - 5;  // depth of the nodes currently in cs.top
             while (n > 1) {  // 64 -> 8 -> 1
                 for (u32 it = 0; it * 32 < n; ++it) {
                     const u32 i = it * 32 + c.lane;
                     const bool act = i < n;
                     u64 ch = act ? cs.top[i] : 0;
                     bool pr = act && cs.topp[i] != 0;
+                    u64 old_self = fl;
+                    if (use_old) old_self = old_at(c.in, u.old_root, (it * 32 + c.gs) >> 3, d - 1);
                     __syncwarp();
                     bool pp;
-                    u64 pid = parent_node<T>(c, ch, pr, &pp);
+                    u64 pid = parent_node<T>(c, ch, pr, old_self, &pp);
                     __syncwarp();
                     if (c.li == 0 && it * 32 + c.gs < n) {
                         cs.top[it * 4 + (c.gs >> 3)] = pid;
@@ -879,6 +1070,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) apply_large_kernel(ApplyArgs a
                     __syncwarp();
                 }
                 n /= 8;
+                d -= 1;
             }
             if (c.lane == 0) write_root<T>(c, a, chunk, cs.top[0], cs.topp[0] != 0);
         }

@@ -16,6 +16,7 @@
 #include "../../include/voxelis_b200.h"
 #include "vx_build.cuh"
 #include "vx_read.cuh"
+#include "vx_release.cuh"
 
 using namespace vx;
 
@@ -77,6 +78,13 @@ struct vx_interner {
     size_t scratch_bytes = 0;
     void* hscratch = nullptr;  // pinned host
     size_t hscratch_bytes = 0;
+    // release (dec_ref_recursive) frontiers, and host mirrors of device state that only changes in
+    // synchronous calls
+    u64* rel[2]{};
+    size_t rel_cap[2]{};
+    u32* d_rel_count = nullptr;  // [2]
+    uint64_t free_host = 0;      // entries in the free list
+    uint64_t tombs_host = 0;     // deleted table slots since the last rehash
     std::mutex mu;
 };
 
@@ -140,9 +148,9 @@ int check_device_error(vx_interner* it) {
     return fail(VX_E_CUDA, "device-side internal error");
 }
 
-template <class T>
+template <class T, bool OLD>
 int launch_apply_t(vx_interner* it, int depth, size_t n, const u8* d_masks, const void* d_values, const u8* d_flags,
-                   const int64_t* d_fills, u64* d_roots, u8* d_changed, cudaStream_t s) {
+                   const int64_t* d_fills, const u64* d_old_roots, u64* d_roots, u8* d_changed, cudaStream_t s) {
     if (n == 0) return VX_OK;
     ApplyArgs a{};
     a.in = it->dev;
@@ -150,32 +158,49 @@ int launch_apply_t(vx_interner* it, int depth, size_t n, const u8* d_masks, cons
     a.values = d_values;
     a.flags = d_flags;
     a.fills = (const long long*)d_fills;
+    a.old_roots = d_old_roots;
     a.roots = d_roots;
     a.changed = d_changed;
     a.n = u32(n);
     a.depth = u32(depth);
     a.blocks = u32(blocks_for_depth(depth));
+    a.use_free = it->free_host > 0 ? 1u : 0u;
     int occ = 0;
     if (depth >= 5) {
-        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, apply_large_kernel<T>, CTA_THREADS, 0));
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, apply_large_kernel<T, OLD>, CTA_THREADS, 0));
         size_t grid = std::min<size_t>(n, size_t(std::max(occ, 1)) * it->sm_count);
-        apply_large_kernel<T><<<unsigned(grid), CTA_THREADS, 0, s>>>(a);
+        apply_large_kernel<T, OLD><<<unsigned(grid), CTA_THREADS, 0, s>>>(a);
     } else {
-        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, apply_small_kernel<T>, CTA_THREADS, 0));
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, apply_small_kernel<T, OLD>, CTA_THREADS, 0));
         size_t ctas = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
         size_t grid = std::min<size_t>(ctas, size_t(std::max(occ, 1)) * it->sm_count);
-        apply_small_kernel<T><<<unsigned(grid), CTA_THREADS, 0, s>>>(a);
+        apply_small_kernel<T, OLD><<<unsigned(grid), CTA_THREADS, 0, s>>>(a);
     }
     CU_TRY(cudaGetLastError());
+    if (a.use_free) {
+        clamp_free_count_kernel<<<1, 1, 0, s>>>(it->dev);
+        CU_TRY(cudaGetLastError());
+    }
     return VX_OK;
 }
 
+// d_old_roots == nullptr: every tree is fresh (the north-star path).
 int launch_apply(vx_interner* it, int depth, size_t n, const u8* d_masks, const void* d_values, const u8* d_flags,
-                 const int64_t* d_fills, u64* d_roots, u8* d_changed, cudaStream_t s) {
+                 const int64_t* d_fills, u64* d_roots, u8* d_changed, cudaStream_t s,
+                 const u64* d_old_roots = nullptr) {
     if (n > 0xFFFFFFFFull) return fail(VX_E_INVALID, "too many chunks in one call");
-    if (it->dtype == VX_U8)
-        return launch_apply_t<u8>(it, depth, n, d_masks, d_values, d_flags, d_fills, d_roots, d_changed, s);
-    return launch_apply_t<int32_t>(it, depth, n, d_masks, d_values, d_flags, d_fills, d_roots, d_changed, s);
+    if (it->dtype == VX_U8) {
+        if (d_old_roots)
+            return launch_apply_t<u8, true>(it, depth, n, d_masks, d_values, d_flags, d_fills, d_old_roots, d_roots,
+                                            d_changed, s);
+        return launch_apply_t<u8, false>(it, depth, n, d_masks, d_values, d_flags, d_fills, nullptr, d_roots,
+                                         d_changed, s);
+    }
+    if (d_old_roots)
+        return launch_apply_t<int32_t, true>(it, depth, n, d_masks, d_values, d_flags, d_fills, d_old_roots, d_roots,
+                                             d_changed, s);
+    return launch_apply_t<int32_t, false>(it, depth, n, d_masks, d_values, d_flags, d_fills, nullptr, d_roots,
+                                          d_changed, s);
 }
 
 int valid_depth(int d) { return d >= 2 && d <= 7; }
@@ -199,6 +224,82 @@ int init_state(vx_interner* it) {
     CU_TRY(cudaMemcpyAsync(it->d_scalars, &init, sizeof(init), cudaMemcpyHostToDevice, s));
     CU_TRY(cudaStreamSynchronize(s));
     it->poisoned = false;
+    it->free_host = 0;
+    it->tombs_host = 0;
+    return VX_OK;
+}
+
+int refresh_free_count(vx_interner* it) {
+    u32 fc = 0;
+    CU_TRY(cudaMemcpyAsync(&fc, &it->d_scalars->free_count, 4, cudaMemcpyDeviceToHost, it->stream));
+    CU_TRY(cudaStreamSynchronize(it->stream));
+    it->free_host = int32_t(fc) > 0 ? fc : 0;
+    return VX_OK;
+}
+
+// dec_ref_recursive (interner/mod.rs:419-534) for `n` root handles at once; synchronous.
+int release_roots(vx_interner* it, const u64* h_roots, size_t n) {
+    if (n == 0) return VX_OK;
+    cudaStream_t s = it->stream;
+    auto ensure = [&](int b, size_t entries) -> int {
+        if (entries <= it->rel_cap[b]) return VX_OK;
+        cudaFree(it->rel[b]);
+        it->rel[b] = nullptr;
+        it->rel_cap[b] = 0;
+        size_t want = std::max<size_t>(entries, 1 << 16);
+        CU_TRY(cudaMalloc(&it->rel[b], want * 8));
+        it->rel_cap[b] = want;
+        return VX_OK;
+    };
+    if (!it->d_rel_count) CU_TRY(cudaMalloc(&it->d_rel_count, 8));
+    int rc = ensure(0, n);
+    if (rc != VX_OK) return rc;
+    rc = ensure(1, n);
+    if (rc != VX_OK) return rc;
+    CU_TRY(cudaMemsetAsync(it->d_rel_count, 0, 8, s));
+    // stage the root ids in buffer 1, emit the first frontier into buffer 0
+    CU_TRY(cudaMemcpyAsync(it->rel[1], h_roots, n * 8, cudaMemcpyHostToDevice, s));
+    release_roots_kernel<<<unsigned((n + 255) / 256), 256, 0, s>>>(it->dev, it->rel[1], u32(n), it->rel[0],
+                                                                    &it->d_rel_count[0]);
+    CU_TRY(cudaGetLastError());
+    int cur = 0;
+    uint64_t freed = 0;
+    for (;;) {
+        u32 count = 0;
+        CU_TRY(cudaMemcpyAsync(&count, &it->d_rel_count[cur], 4, cudaMemcpyDeviceToHost, s));
+        CU_TRY(cudaStreamSynchronize(s));
+        if (count == 0) break;
+        freed += count;
+        int nxt = cur ^ 1;
+        rc = ensure(nxt, size_t(count) * 8);
+        if (rc != VX_OK) return rc;
+        CU_TRY(cudaMemsetAsync(&it->d_rel_count[nxt], 0, 4, s));
+        size_t groups = count;
+        unsigned grid = unsigned(std::min<size_t>((groups * 8 + 255) / 256, size_t(it->sm_count) * 8));
+        if (it->dtype == VX_U8)
+            release_level_kernel<u8><<<grid, 256, 0, s>>>(it->dev, it->rel[cur], count, it->rel[nxt],
+                                                          &it->d_rel_count[nxt]);
+        else
+            release_level_kernel<int32_t><<<grid, 256, 0, s>>>(it->dev, it->rel[cur], count, it->rel[nxt],
+                                                               &it->d_rel_count[nxt]);
+        CU_TRY(cudaGetLastError());
+        cur = nxt;
+    }
+    it->tombs_host += freed;
+    rc = refresh_free_count(it);
+    if (rc != VX_OK) return rc;
+    // rebuild the branch table once deleted slots take a quarter of it
+    if (it->tombs_host > it->nbuckets * 2) {
+        Scalars sc{};
+        CU_TRY(cudaMemcpyAsync(&sc, it->d_scalars, sizeof(sc), cudaMemcpyDeviceToHost, s));
+        CU_TRY(cudaStreamSynchronize(s));
+        u32 next = std::min<u32>(sc.next_index, u32(it->capacity));
+        CU_TRY(cudaMemsetAsync(it->dev.slots, 0, it->nbuckets * 64, s));
+        rehash_kernel<<<(next + 255) / 256, 256, 0, s>>>(it->dev, next);
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaStreamSynchronize(s));
+        it->tombs_host = 0;
+    }
     return VX_OK;
 }
 
@@ -317,6 +418,9 @@ void vx_interner_destroy(vx_interner* it) {
         if (it->ev_done[i]) cudaEventDestroy(it->ev_done[i]);
     }
     cudaFree(it->scratch);
+    cudaFree(it->rel[0]);
+    cudaFree(it->rel[1]);
+    cudaFree(it->d_rel_count);
     if (it->hscratch) cudaFreeHost(it->hscratch);
     if (it->stream) cudaStreamDestroy(it->stream);
     if (it->copy_stream) cudaStreamDestroy(it->copy_stream);
@@ -610,8 +714,9 @@ int vx_apply_batches_device(vx_interner* it, uint8_t depth, size_t n, const uint
     return launch_apply(it, depth, n, d_masks, d_values, d_flags, d_fills, d_roots, d_changed, s);
 }
 
-int vx_apply_batches_slab(vx_interner* it, uint8_t depth, size_t n, const uint8_t* masks, const void* values,
-                          const uint8_t* flags, const int64_t* fills, vx_block_id* roots_out, uint8_t* changed_out) {
+static int apply_slab_impl(vx_interner* it, uint8_t depth, size_t n, const uint8_t* masks, const void* values,
+                           const uint8_t* flags, const int64_t* fills, const vx_block_id* h_old_roots,
+                           vx_block_id* roots_out, uint8_t* changed_out) {
     if (!it || !masks || !values || !roots_out) return fail(VX_E_INVALID, "null argument");
     if (!valid_depth(depth)) return fail(VX_E_INVALID, "max_depth must be in [2,7]");
     if (it->poisoned) return fail(VX_E_POISONED, "interner overflowed earlier; reset it");
@@ -623,14 +728,20 @@ int vx_apply_batches_slab(vx_interner* it, uint8_t depth, size_t n, const uint8_
     if (dev_in != is_device_ptr(values)) return fail(VX_E_INVALID, "masks and values must live in the same memory space");
     const bool dev_roots = is_device_ptr(roots_out), dev_changed = changed_out && is_device_ptr(changed_out);
     cudaStream_t s = it->stream;
-    // per-chunk options and outputs live in device scratch: [roots n*8][fills n*8][changed n][flags n]
-    size_t need = n * 8 + n * 8 + n + n + 64;
+    // per-chunk options and outputs live in device scratch: [roots n*8][fills n*8][old n*8][changed n][flags n]
+    size_t need = n * 8 + n * 8 + n * 8 + n + n + 64;
     int rc = ensure_scratch(it, need, 0);
     if (rc != VX_OK) return rc;
     u64* d_roots = dev_roots ? roots_out : (u64*)it->scratch;
     int64_t* d_fills = (int64_t*)((u8*)it->scratch + n * 8);
-    u8* d_changed = dev_changed ? changed_out : (u8*)it->scratch + n * 16;
-    u8* d_flags = (u8*)it->scratch + n * 17;
+    u64* d_old = (u64*)((u8*)it->scratch + n * 16);
+    u8* d_changed = dev_changed ? changed_out : (u8*)it->scratch + n * 24;
+    u8* d_flags = (u8*)it->scratch + n * 25;
+    const u64* k_old = nullptr;
+    if (h_old_roots) {
+        CU_TRY(cudaMemcpyAsync(d_old, h_old_roots, n * 8, cudaMemcpyHostToDevice, s));
+        k_old = d_old;
+    }
     const u8* k_flags = nullptr;
     const int64_t* k_fills = nullptr;
     if (flags) {
@@ -650,7 +761,7 @@ int vx_apply_batches_slab(vx_interner* it, uint8_t depth, size_t n, const uint8_
         }
     }
     if (dev_in) {
-        rc = launch_apply(it, depth, n, masks, values, k_flags, k_fills, d_roots, d_changed, s);
+        rc = launch_apply(it, depth, n, masks, values, k_flags, k_fills, d_roots, d_changed, s, k_old);
         if (rc != VX_OK) return rc;
     } else {
         // host batches: H2D on the copy stream into one of two staging slabs while the previous slab
@@ -681,53 +792,66 @@ int vx_apply_batches_slab(vx_interner* it, uint8_t depth, size_t n, const uint8_
             CU_TRY(cudaEventRecord(it->ev_copied[b], it->copy_stream));
             CU_TRY(cudaStreamWaitEvent(s, it->ev_copied[b], 0));
             rc = launch_apply(it, depth, cnt, sm, sv, k_flags ? k_flags + lo : nullptr, k_fills ? k_fills + lo : nullptr,
-                              d_roots + lo, d_changed + lo, s);
+                              d_roots + lo, d_changed + lo, s, k_old ? k_old + lo : nullptr);
             if (rc != VX_OK) return rc;
             CU_TRY(cudaEventRecord(it->ev_done[b], s));
         }
     }
     if (!dev_roots) CU_TRY(cudaMemcpyAsync(roots_out, d_roots, n * 8, cudaMemcpyDeviceToHost, s));
     if (changed_out && !dev_changed) CU_TRY(cudaMemcpyAsync(changed_out, d_changed, n, cudaMemcpyDeviceToHost, s));
-    return check_device_error(it);
+    rc = check_device_error(it);
+    if (rc == VX_OK && it->free_host > 0) rc = refresh_free_count(it);
+    return rc;
+}
+
+int vx_apply_batches_slab(vx_interner* it, uint8_t depth, size_t n, const uint8_t* masks, const void* values,
+                          const uint8_t* flags, const int64_t* fills, vx_block_id* roots_out, uint8_t* changed_out) {
+    return apply_slab_impl(it, depth, n, masks, values, flags, fills, nullptr, roots_out, changed_out);
 }
 
 int vx_tree_apply_batch(vx_interner* it, vx_tree* t, const vx_batch* b) {
     if (!it || !t || !b) return fail(VX_E_INVALID, "null argument");
     if (b->depth != t->depth) return fail(VX_E_INVALID, "batch and tree depths differ");
     if (b->dtype != it->dtype) return fail(VX_E_INVALID, "batch and interner voxel types differ");
-    if (t->root != VX_BLOCK_EMPTY)
-        return fail(VX_E_UNSUPPORTED, "apply_batch on a non-empty tree is not implemented yet (SURVEY 8f-1)");
     uint8_t flag = (b->has_fill ? VX_FLAG_FILL : 0) | (b->has_patches ? VX_FLAG_PATCHES : 0);
     int64_t fill = b->fill;
-    vx_block_id root = 0;
+    vx_block_id root = 0, old_root = t->root;
     uint8_t changed = 0;
-    int rc = vx_apply_batches_slab(it, b->depth, 1, b->masks, b->values, &flag, &fill, &root, &changed);
+    // a non-empty tree is merged with the batch on the device (old-tree descent, voxtree.rs:785-842,
+    // :930-952); with a fill the batch is built against Leaf(fill) and the old tree only released
+    int rc = apply_slab_impl(it, b->depth, 1, b->masks, b->values, &flag, &fill,
+                             old_root != VX_BLOCK_EMPTY ? &old_root : nullptr, &root, &changed);
     if (rc != VX_OK) return rc;
-    if (changed) {  // voxtree.rs:309-324
-        t->root = root;
-        t->dirty = true;
-        return 1;
+    if (!changed) return 0;
+    if (old_root != VX_BLOCK_EMPTY) {  // voxtree.rs:309-314 (the reference asserts new != old here)
+        std::lock_guard<std::mutex> lk(it->mu);
+        DeviceGuard g(it->device);
+        rc = release_roots(it, &old_root, 1);
+        if (rc != VX_OK) return rc;
     }
-    return 0;
+    t->root = root;
+    t->dirty = true;
+    return 1;
 }
 
 int vx_apply_batches(vx_interner* it, vx_tree* const* trees, const vx_batch* const* batches, size_t n,
                      uint8_t* changed) {
     if (!it || (n && (!trees || !batches))) return fail(VX_E_INVALID, "null argument");
     if (n == 0) return VX_OK;
-    bool uniform = true;
+    bool fused = true, any_old = false;
     for (size_t i = 0; i < n; ++i) {
         if (!trees[i] || !batches[i]) return fail(VX_E_INVALID, "null tree or batch");
         if (batches[i]->depth != trees[i]->depth) return fail(VX_E_INVALID, "batch and tree depths differ");
         if (batches[i]->dtype != it->dtype) return fail(VX_E_INVALID, "batch and interner voxel types differ");
-        uniform = uniform && trees[i]->root == VX_BLOCK_EMPTY && batches[i]->depth == batches[0]->depth;
+        fused = fused && batches[i]->depth == batches[0]->depth;
+        any_old = any_old || trees[i]->root != VX_BLOCK_EMPTY;
     }
-    if (uniform) {  // a tree may appear only once in the fused path
+    if (fused) {  // a tree may appear only once in the fused path
         std::vector<const vx_tree*> seen(trees, trees + n);
         std::sort(seen.begin(), seen.end());
-        uniform = std::adjacent_find(seen.begin(), seen.end()) == seen.end();
+        fused = std::adjacent_find(seen.begin(), seen.end()) == seen.end();
     }
-    if (!uniform) {  // mixed depths / non-empty trees: the reference's serial loop
+    if (!fused) {  // mixed depths or repeated trees: the reference's serial loop (lib.rs:357-361)
         for (size_t i = 0; i < n; ++i) {
             int rc = vx_tree_apply_batch(it, trees[i], batches[i]);
             if (rc < 0) return rc;
@@ -742,25 +866,28 @@ int vx_apply_batches(vx_interner* it, vx_tree* const* trees, const vx_batch* con
     const size_t B = blocks_for_depth(depth), mbytes = B * 2, vbytes = B * 8 * dtype_size(it->dtype);
     const size_t per = mbytes + vbytes;
     // one contiguous device slab for all batches + options + results
-    size_t dev_need = n * per + n * 8 + n * 8 + n + n + 256;
-    size_t host_need = n * 8 + n * 8 + n + n;
+    size_t dev_need = n * per + n * 8 * 3 + n + n + 256;
+    size_t host_need = n * 8 * 3 + n + n;
     int rc = ensure_scratch(it, dev_need, host_need);
     if (rc != VX_OK) return rc;
     u8* dm = (u8*)it->scratch;
     u8* dv = dm + n * mbytes;
     u64* d_roots = (u64*)(dv + n * vbytes);
     int64_t* d_fills = (int64_t*)(d_roots + n);
-    u8* d_changed = (u8*)(d_fills + n);
+    u64* d_old = (u64*)(d_fills + n);
+    u8* d_changed = (u8*)(d_old + n);
     u8* d_flags = d_changed + n;
     u64* h_roots = (u64*)it->hscratch;
     int64_t* h_fills = (int64_t*)(h_roots + n);
-    u8* h_changed = (u8*)(h_fills + n);
+    u64* h_old = (u64*)(h_fills + n);
+    u8* h_changed = (u8*)(h_old + n);
     u8* h_flags = h_changed + n;
     cudaStream_t s = it->stream;
     for (size_t i = 0; i < n; ++i) {
         const vx_batch* b = batches[i];
         h_flags[i] = (b->has_fill ? VX_FLAG_FILL : 0) | (b->has_patches ? VX_FLAG_PATCHES : 0);
         h_fills[i] = b->fill;
+        h_old[i] = trees[i]->root;
         if (b->has_patches) {
             CU_TRY(cudaMemcpyAsync(dm + i * mbytes, b->masks, mbytes, cudaMemcpyHostToDevice, s));
             CU_TRY(cudaMemcpyAsync(dv + i * vbytes, b->values, vbytes, cudaMemcpyHostToDevice, s));
@@ -768,18 +895,29 @@ int vx_apply_batches(vx_interner* it, vx_tree* const* trees, const vx_batch* con
     }
     CU_TRY(cudaMemcpyAsync(d_flags, h_flags, n, cudaMemcpyHostToDevice, s));
     CU_TRY(cudaMemcpyAsync(d_fills, h_fills, n * 8, cudaMemcpyHostToDevice, s));
-    rc = launch_apply(it, depth, n, dm, dv, d_flags, d_fills, d_roots, d_changed, s);
+    if (any_old) CU_TRY(cudaMemcpyAsync(d_old, h_old, n * 8, cudaMemcpyHostToDevice, s));
+    rc = launch_apply(it, depth, n, dm, dv, d_flags, d_fills, d_roots, d_changed, s, any_old ? d_old : nullptr);
     if (rc != VX_OK) return rc;
     CU_TRY(cudaMemcpyAsync(h_roots, d_roots, n * 8, cudaMemcpyDeviceToHost, s));
     CU_TRY(cudaMemcpyAsync(h_changed, d_changed, n, cudaMemcpyDeviceToHost, s));
     rc = check_device_error(it);
     if (rc != VX_OK) return rc;
+    if (it->free_host > 0) {
+        rc = refresh_free_count(it);
+        if (rc != VX_OK) return rc;
+    }
+    std::vector<u64> dead;
     for (size_t i = 0; i < n; ++i) {
         if (h_changed[i]) {
+            if (trees[i]->root != VX_BLOCK_EMPTY) dead.push_back(trees[i]->root);
             trees[i]->root = h_roots[i];
             trees[i]->dirty = true;
         }
         if (changed) changed[i] = h_changed[i];
+    }
+    if (!dead.empty()) {  // every build has finished: now drop the old trees (voxtree.rs:309-314)
+        rc = release_roots(it, dead.data(), dead.size());
+        if (rc != VX_OK) return rc;
     }
     return VX_OK;
 }
@@ -867,31 +1005,57 @@ int vx_tree_to_vec(const vx_interner* it, const vx_tree* t, void* dense) {
 }
 
 // ------------------------------------------------------------------------------- fill / clear / set_root
-int vx_tree_set_root_id(vx_interner*, vx_tree*, vx_block_id) {
-    return fail(VX_E_UNSUPPORTED, "set_root_id is not implemented yet");
+int vx_tree_set_root_id(vx_interner* it, vx_tree* t, vx_block_id root) {
+    if (!it || !t) return fail(VX_E_INVALID, "null argument");
+    if (root == VX_BLOCK_INVALID || id_index(root) >= it->capacity) return fail(VX_E_INVALID, "invalid block id");
+    std::lock_guard<std::mutex> lk(it->mu);
+    DeviceGuard g(it->device);
+    t->root = root;  // voxtree.rs:135-141: adopt + inc_ref (the previous root is NOT released, as in the reference)
+    add_ref_kernel<<<1, 1, 0, it->stream>>>(it->dev, root, 1u);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaStreamSynchronize(it->stream));
+    return VX_OK;
 }
+
+int vx_tree_clear(vx_interner* it, vx_tree* t) {
+    if (!it || !t) return fail(VX_E_INVALID, "null argument");
+    if (t->root == VX_BLOCK_EMPTY) return VX_OK;  // voxtree.rs:283-292
+    std::lock_guard<std::mutex> lk(it->mu);
+    DeviceGuard g(it->device);
+    u64 old_root = t->root;
+    int rc = release_roots(it, &old_root, 1);
+    if (rc != VX_OK) return rc;
+    t->root = VX_BLOCK_EMPTY;
+    t->dirty = true;
+    return VX_OK;
+}
+
 int vx_tree_fill(vx_interner* it, vx_tree* t, int64_t value) {
     if (!it || !t) return fail(VX_E_INVALID, "null argument");
-    if (t->root != VX_BLOCK_EMPTY) return fail(VX_E_UNSUPPORTED, "fill on a built tree needs release (SURVEY 8f-1)");
     int64_t v = it->dtype == VX_U8 ? int64_t(u8(value)) : int64_t(int32_t(value));
-    if (v == 0) return VX_OK;  // fill(default) == clear (voxtree.rs:269-279)
-    // a fill-only batch on a fresh tree is exactly get_or_create_leaf(value) + root handle
+    if (v == 0) return vx_tree_clear(it, t);  // voxtree.rs:269-279
+    if (t->root != VX_BLOCK_EMPTY) {          // release the old tree first (:271-273)
+        int rc = vx_tree_clear(it, t);
+        if (rc != VX_OK) return rc;
+    }
+    // get_or_create_leaf(value) + root handle == a fill-only batch on the now empty tree
     uint8_t flag = VX_FLAG_FILL;
     vx_block_id root = 0;
     uint8_t changed = 0;
-    // masks/values are not read for a fill-only chunk; pass any valid device pointer
-    int rc = ensure_scratch(it, 256, 0);
+    int rc;
+    {
+        std::lock_guard<std::mutex> lk(it->mu);
+        DeviceGuard g(it->device);
+        rc = ensure_scratch(it, 1 << 20, 0);
+    }
     if (rc != VX_OK) return rc;
-    rc = vx_apply_batches_slab(it, t->depth, 1, (const uint8_t*)it->scratch, it->scratch, &flag, &v, &root, &changed);
+    // masks/values are not read for a fill-only chunk; any valid device pointer will do
+    u8* dummy = (u8*)it->scratch + (1 << 19);
+    rc = vx_apply_batches_slab(it, t->depth, 1, dummy, dummy, &flag, &v, &root, &changed);
     if (rc != VX_OK) return rc;
     t->root = root;
     t->dirty = true;
     return VX_OK;
-}
-int vx_tree_clear(vx_interner* it, vx_tree* t) {
-    if (!it || !t) return fail(VX_E_INVALID, "null argument");
-    if (t->root == VX_BLOCK_EMPTY) return VX_OK;  // voxtree.rs:283-292
-    return fail(VX_E_UNSUPPORTED, "clear on a built tree needs release (SURVEY 8f-1)");
 }
 
 }  // extern "C"
