@@ -55,7 +55,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -135,11 +135,14 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-others", action="store_true", help="skip the secondary workloads")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (profiling runs)")
+    ap.add_argument("--workload", default="perlin", help="profiling only: time another workload in the main loop "
+                    "(checkerboard | sum | sum_per_chunk | random255 | below); the headline is 'perlin'")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -182,7 +185,15 @@ def main():
 
     # ---------------------------------------------------------------- inputs
     log("generating the perlin-dunes world")
-    masks, values = make_world(rank)
+    budget = BUDGET
+    if args.workload == "perlin":
+        masks, values = make_world(rank)
+    elif args.workload == "below":
+        masks, values = make_world(rank, "surface_and_below")
+    else:
+        from voxelis_b200 import workloads as wl
+        masks, values = wl.named_workload(args.workload, 4096)
+        budget = 2 << 30
     n = masks.shape[0]
     log(f"{n} chunks generated; uploading")
     h_masks = torch.from_numpy(masks).pin_memory()
@@ -191,11 +202,12 @@ def main():
     d_values = h_values.to(dev)
     d_roots = torch.zeros(n, dtype=torch.int64, device=dev)
     d_changed = torch.zeros(n, dtype=torch.uint8, device=dev)
-    it = vx.VoxInterner.with_memory_budget(BUDGET, vx.U8, local_rank)
-    stream = torch.cuda.current_stream(dev)
+    it = vx.VoxInterner.with_memory_budget(budget, vx.U8, local_rank)
+    stream = torch.cuda.Stream(dev)          # a real (non-default) stream: events on it bracket our launches
+    torch.cuda.synchronize()
 
     def step_device():
-        it.reset()
+        it.reset_async(stream.cuda_stream)
         it.apply_batches_device(DEPTH, n, d_masks.data_ptr(), d_values.data_ptr(), d_roots.data_ptr(),
                                 d_changed.data_ptr(), stream=stream.cuda_stream)
 
@@ -206,6 +218,7 @@ def main():
     torch.cuda.synchronize()
     it.sync()
     new_nodes = it.stats()["total_cache_misses"]
+    dbg = it.debug_counters()
     sampler = ClockSampler(local_rank)
     sampler.start()
     kernel_ms = []
@@ -214,7 +227,7 @@ def main():
     e0.record(stream)
     kev = []
     for _ in range(args.steps):
-        it.reset()
+        it.reset_async(stream.cuda_stream)
         k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         k0.record(stream)
         it.apply_batches_device(DEPTH, n, d_masks.data_ptr(), d_values.data_ptr(), d_roots.data_ptr(),
@@ -234,24 +247,27 @@ def main():
 
     log(f"device-resident: {step_ms_max:.3f} ms/step, kernel {kern_ms:.3f} ms")
     # ---------------------------------------------------------------- end to end (host batches)
-    roots_host = np.zeros(n, np.uint64)
-    changed_host = np.zeros(n, np.uint8)
-    for _ in range(2):
-        it.reset()
-        it.apply_batches_slab(DEPTH, h_masks.numpy(), h_values.numpy(), roots_out=roots_host,
-                              changed_out=changed_host)
-    e2e_steps = max(3, min(args.steps, 5))
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        it.reset()
-        it.apply_batches_slab(DEPTH, h_masks.numpy(), h_values.numpy(), roots_out=roots_host,
-                              changed_out=changed_host)
-    torch.cuda.synchronize()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
-    barrier()
-    e2e_ms_max = max_over_ranks(e2e_ms)
-    e2e_value = total_chunks / (e2e_ms_max * 1e-3)
+    e2e_value, e2e_ms_max = None, None
+    if not args.no_e2e:
+        roots_host = np.zeros(n, np.uint64)
+        changed_host = np.zeros(n, np.uint8)
+        for _ in range(2):
+            it.reset()
+            it.apply_batches_slab(DEPTH, h_masks.numpy(), h_values.numpy(), roots_out=roots_host,
+                                  changed_out=changed_host)
+        e2e_steps = max(3, min(args.steps, 5))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            it.reset()
+            it.apply_batches_slab(DEPTH, h_masks.numpy(), h_values.numpy(), roots_out=roots_host,
+                                  changed_out=changed_host)
+        torch.cuda.synchronize()
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+        barrier()
+        e2e_ms_max = max_over_ranks(e2e_ms)
+        e2e_value = total_chunks / (e2e_ms_max * 1e-3)
+        log(f"end-to-end (host batches): {e2e_ms_max:.3f} ms/step")
 
     # ---------------------------------------------------------------- roofline of the apply kernel
     peak, peak_src = peaks()
@@ -283,7 +299,7 @@ def main():
                 dr = torch.zeros(n2, dtype=torch.int64, device=dev)
                 ts = []
                 for i in range(6):
-                    it2.reset()
+                    it2.reset_async(stream.cuda_stream)
                     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     a.record(stream)
                     it2.apply_batches_device(DEPTH, n2, dm.data_ptr(), dv.data_ptr(), dr.data_ptr(),
@@ -294,10 +310,13 @@ def main():
                     if i >= 2:
                         ts.append(a.elapsed_time(b))
                 nn = it2.stats()["total_cache_misses"]
+                d2 = it2.debug_counters()
                 ms = float(np.mean(ts))
                 ab = n2 * CHUNK_BYTES + nn * NODE_BYTES
                 others[name] = {"chunks_per_s": n2 / (ms * 1e-3), "kernel_ms": ms, "new_nodes": nn,
-                                "achieved_gbs": ab / (ms * 1e-3) / 1e9, "frac": ab / (ms * 1e-3) / 1e9 / peak}
+                                "achieved_gbs": ab / (ms * 1e-3) / 1e9, "frac": ab / (ms * 1e-3) / 1e9 / peak,
+                                "branch_calls": d2["branch_calls"], "probe_steps": d2["probe_steps"],
+                                "cache_hits_local": d2["cache_hits_local"]}
                 del dm, dv, dr, it2
             except Exception as e:  # a secondary workload must never take the headline line down
                 others[name] = {"error": str(e)}
@@ -313,15 +332,17 @@ def main():
             "metric": "chunks/s built+interned (perlin 32^3)", "value": value, "unit": "chunks/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms_max,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "perlin_dunes_surface_only_64x8x64_d5_u8", "chunks_per_step_per_gpu": n,
+            "config": {"workload": "perlin_dunes_surface_only_64x8x64_d5_u8" if args.workload == "perlin" else args.workload,
+                       "chunks_per_step_per_gpu": n,
                        "depth": DEPTH, "interner_budget_bytes": BUDGET, "new_nodes_per_step": new_nodes,
                        "l2": "inputs (1.34 GB/step) exceed the 126 MB L2; interner reset every step",
-                       "step": "vx_interner_reset + one vx_apply_batches_device launch"},
+                       "step": "vx_interner_reset + one vx_apply_batches_device launch",
+                       "per_step_counters": dbg},
             "e2e": {"value": e2e_value, "unit": "chunks/s", "ms_per_step": e2e_ms_max,
                     "h2d_bytes_per_step": int(masks.nbytes + values.nbytes), "d2h_bytes_per_step": int(n * 9)},
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "apply_large_kernel<u8>",
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "apply_kernel<u8,false>",
                          "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": algo_bytes},
             "clocks": clocks,
         }

@@ -78,6 +78,8 @@ vx_interner* vx_interner_create(size_t budget_bytes, vx_dtype dtype, int device)
 void vx_interner_destroy(vx_interner*);
 /* Back to the freshly-created state (every node dropped).  Trees built in it become dangling. */
 int vx_interner_reset(vx_interner*);
+/* Same, queued on `stream` (a cudaStream_t; NULL = the interner's stream) without synchronising. */
+int vx_interner_reset_async(vx_interner*, void* stream);
 size_t vx_interner_capacity(const vx_interner*);
 vx_dtype vx_interner_dtype(const vx_interner*);
 int vx_interner_device(const vx_interner*);

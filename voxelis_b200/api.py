@@ -34,7 +34,7 @@ STATS_FIELDS = [
 # every symbol include/voxelis_b200.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
     "vx_last_error", "vx_abi_version", "vx_device_count", "vx_interner_create", "vx_interner_destroy",
-    "vx_interner_reset", "vx_interner_capacity", "vx_interner_dtype", "vx_interner_device",
+    "vx_interner_reset", "vx_interner_reset_async", "vx_interner_capacity", "vx_interner_dtype", "vx_interner_device",
     "vx_interner_next_index", "vx_interner_get_ref", "vx_interner_get_value", "vx_interner_get_children",
     "vx_interner_stats", "vx_interner_download", "vx_interner_sync", "vx_interner_stream",
     "vx_batch_create", "vx_batch_destroy", "vx_batch_set", "vx_batch_fill", "vx_batch_clear",
@@ -71,6 +71,7 @@ def lib():
     L.vx_interner_destroy.argtypes = [vp]
     L.vx_interner_destroy.restype = None
     L.vx_interner_reset.argtypes = [vp]
+    L.vx_interner_reset_async.argtypes = [vp, vp]
     L.vx_interner_capacity.restype = sz
     L.vx_interner_capacity.argtypes = [vp]
     L.vx_interner_dtype.argtypes = [vp]
@@ -195,6 +196,7 @@ class VoxInterner:
             pass
 
     def reset(self): _ck(lib().vx_interner_reset(self.h))
+    def reset_async(self, stream: int = 0): _ck(lib().vx_interner_reset_async(self.h, C.c_void_p(stream or None)))
     def sync(self): _ck(lib().vx_interner_sync(self.h))
     @property
     def capacity(self) -> int: return lib().vx_interner_capacity(self.h)

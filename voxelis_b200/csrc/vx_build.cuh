@@ -226,10 +226,6 @@ struct WarpSmem {
 struct CtaSmem {
     u64 leaf[256];     // u8: value -> leaf id (lazy copy of InternerDev::leaf_u8)
     u32 leafref[256];  // u8: pending in-degree increments of leaves
-    u64 oct[8];        // unit results of the current 32^3 super-unit
-    u32 octp[8];
-    u64 top[64];       // super-unit results (D = 6: 8, D = 7: 64)
-    u32 topp[64];
 };
 
 struct Tally {  // per-lane statistics, reduced once at kernel exit
@@ -389,6 +385,7 @@ template <class T, bool BLOCK_LEVEL>
 __device__ inline u64 intern_branch(Ctx<T>& c, bool need, u64 child, u32 cval) {
     const int li = c.li, gs = c.gs, lane = c.lane;
     const InternerDev& in = c.in;
+    if (!__any_sync(FULL, need)) return 0;
     // types / mask are functions of the children (voxtree.rs:846-863, :959-1000)
     u32 leafb = (__ballot_sync(FULL, id_is_leaf(child)) >> gs) & 0xFF;
     u32 presb = (__ballot_sync(FULL, child != 0) >> gs) & 0xFF;
@@ -734,46 +731,89 @@ __device__ inline void old_block_state(Ctx<T>& c, const Under& u, u32 blk, bool 
 // A warp builds the sub-tree over `nblocks` (8, 64 or 512) Morton-consecutive blocks starting at
 // block `first_block` of the chunk.
 // ------------------------------------------------------------------------------------------------
+// All set_masks of a unit in one shot: lane L gets the masks of blocks [16L, 16L+16) — two 16-byte
+// coalesced loads per lane, 1 KiB per warp for a full 512-block unit.  clear_mask bytes are dropped
+// here: apply never reads them (voxtree.rs:778-781).
+__device__ __forceinline__ void load_unit_masks(const u8* masks, size_t first_block, int nblocks, int lane, u64* mlo,
+                                                u64* mhi) {
+    *mlo = 0;
+    *mhi = 0;
+    const uint4* mp = (const uint4*)(masks + (first_block + 16 * lane) * 2);
+    if (16 * lane + 8 <= nblocks) {
+        uint4 q = ld_stream_v4(mp);
+        *mlo = u64(__byte_perm(q.x, q.y, 0x6420)) | (u64(__byte_perm(q.z, q.w, 0x6420)) << 32);
+    }
+    if (16 * lane + 16 <= nblocks) {
+        uint4 q = ld_stream_v4(mp + 1);
+        *mhi = u64(__byte_perm(q.x, q.y, 0x6420)) | (u64(__byte_perm(q.z, q.w, 0x6420)) << 32);
+    }
+}
+
 template <class T, bool OLD>
-__device__ inline u64 build_unit(Ctx<T>& c, const u8* masks, const void* values, u32 first_block, int nblocks,
+__device__ inline u64 build_unit(Ctx<T>& c, u64 mlo, u64 mhi, const void* values, u32 first_block, int nblocks,
                                  const Under& u, bool* upresent) {
     using V = VT<T>;
     const int lane = c.lane;
     const int n_iter = (nblocks + 31) / 32;
     const int D = u.depth;
     const typename V::Key fillw = V::splat(u.fill_leaf ? u.fill : 0);
-    // software prefetch: loads of iteration it+1 are issued before iteration it is processed
+    // (2) Which 32-block iterations contain any set bit (iteration it <- lanes 2it, 2it+1).  Blocks with
+    //     set_mask == 0 are skipped by phase 1 (voxtree.rs:779-781): their VALUES are never loaded, and
+    //     iterations without a set bit cost nothing.
+    u32 nzl = __ballot_sync(FULL, (mlo | mhi) != 0);
+    u32 iters = (nzl | (nzl >> 1)) & 0x55555555u;  // bit 2*it
+    if (OLD) iters = (n_iter >= 16 ? 0xFFFFFFFFu : ((1u << (2 * n_iter)) - 1)) & 0x55555555u;  // every group needs its old node
+    if (!OLD && iters == 0) {  // nothing set in this unit: it stays what it was (fill leaf / EMPTY)
+        *upresent = false;
+        return u.fill_leaf;
+    }
+    if (!OLD) {
+        c.ws->l1[lane] = u.fill_leaf;
+        c.ws->l1[lane + 32] = u.fill_leaf;
+    }
+    if (lane < 2) c.ws->l1p[lane] = 0;
+    __syncwarp();
+    auto mask_of = [&](int it) -> u32 {
+        const int src = 2 * it + (lane >> 4);
+        u64 lo = __shfl_sync(FULL, mlo, src), hi = __shfl_sync(FULL, mhi, src);
+        u64 w = (lane & 8) ? hi : lo;
+        return u32(w >> (8 * (lane & 7))) & 0xFF;
+    };
+    // (3) software pipeline over the non-empty iterations: the value loads of the next one are issued
+    //     before the current one is processed; only lanes whose block has a set bit load (8 B / 32 B).
+    int it = iters ? ((__ffs(iters) - 1) >> 1) : -1;
     typename V::Key nvals = V::zero();
     u32 nmask = 0;
-    if (lane < nblocks) {
-        nvals = V::load(values, size_t(first_block) + lane);
-        nmask = ld_stream_u16(masks + (size_t(first_block) + lane) * 2) & 0xFF;
+    if (it >= 0) {
+        nmask = mask_of(it);
+        if (nmask) nvals = V::load(values, size_t(first_block) + it * 32 + lane);
     }
-    for (int it = 0; it < n_iter; ++it) {
+    while (it >= 0) {
+        iters &= iters - 1;
+        const int cur = it;
         typename V::Key vals = nvals;
         u32 smask = nmask;
-        const bool active = it * 32 + lane < nblocks;
-        const int nb = (it + 1) * 32 + lane;
-        if (nb < nblocks) {
-            nvals = V::load(values, size_t(first_block) + nb);
-            nmask = ld_stream_u16(masks + (size_t(first_block) + nb) * 2) & 0xFF;
+        it = iters ? ((__ffs(iters) - 1) >> 1) : -1;
+        if (it >= 0) {
+            nmask = mask_of(it);
+            nvals = V::zero();
+            if (nmask) nvals = V::load(values, size_t(first_block) + it * 32 + lane);
         }
+        const bool active = cur * 32 + lane < nblocks;
         typename V::Key oldw = fillw;
         u64 old_id = u.fill_leaf, parent_old = u.fill_leaf;
-        if (OLD) old_block_state<T>(c, u, first_block + it * 32 + lane, active, (smask & 0xFF) != 0, &parent_old, &old_id, &oldw);
+        if (OLD) old_block_state<T>(c, u, first_block + cur * 32 + lane, active, smask != 0, &parent_old, &old_id, &oldw);
         bool present;
         u64 id = block_node<T>(c, active, vals, smask, oldw, old_id, &present);
         bool pp;
         u64 pid = parent_node<T>(c, id, present && active, parent_old, &pp);
-        const bool gact = it * 32 + c.gs < nblocks;
-        if (c.li == 0 && gact) c.ws->l1[it * 4 + (c.gs >> 3)] = pid;
+        const bool gact = cur * 32 + c.gs < nblocks;
+        if (c.li == 0 && gact) c.ws->l1[cur * 4 + (c.gs >> 3)] = pid;
         u32 ppb = __ballot_sync(FULL, pp && c.li == 0 && gact);
         if (lane == 0) {
             // compact the four group bits (lanes 0,8,16,24) into bits 0..3
             u32 four = (ppb & 1) | ((ppb >> 7) & 2) | ((ppb >> 14) & 4) | ((ppb >> 21) & 8);
-            int word = (it * 4) >> 5, sh = (it * 4) & 31;
-            u32 old = (sh == 0) ? 0u : c.ws->l1p[word];
-            c.ws->l1p[word] = old | (four << sh);
+            c.ws->l1p[(cur * 4) >> 5] |= four << ((cur * 4) & 31);
         }
     }
     __syncwarp();
@@ -837,6 +877,14 @@ struct ApplyArgs {
     const u64* old_roots;    // [n] or null (OLD kernels only): root of the tree before the batch
     u64* roots;              // [n]
     u8* changed;             // [n] or null
+    // join scratch (D >= 5): units of 512 blocks are built by independent warps; the last warp to
+    // finish a 32^3 cube joins its eight unit nodes, the last cube of a chunk joins the top levels
+    u64* unit_ids;      // [n][units_per_chunk]
+    u8* unit_present;   // [n][units_per_chunk]
+    u32* cube_done;     // [n][cubes_per_chunk]  zeroed before launch
+    u64* cube_ids;      // [n][cubes_per_chunk]
+    u8* cube_present;   // [n][cubes_per_chunk]
+    u32* chunk_done;    // [n]                   zeroed before launch
     u32 n;
     u32 depth;
     u32 blocks;    // B
@@ -928,68 +976,42 @@ __device__ __forceinline__ void write_root(Ctx<T>& c, const ApplyArgs& a, u32 ch
     if (changed && root != 0) atomicAdd(&c.in.refs[id_index(root)], 1u);  // the tree's root handle
 }
 
-// D <= 4: a chunk is at most one warp unit -> one warp per chunk.
+// ------------------------------------------------------------------------------------------------
+// apply kernel.  Work item = one unit (<= 512 Morton-consecutive blocks = a 16^3-voxel sub-cube, or
+// the whole chunk when D <= 4), one warp per unit, persistent warps striding over all units of all
+// chunks.  Warps never wait for each other: a unit's node is published to global scratch, and the
+// LAST warp to arrive at a 32^3 cube (atomic counter) joins its eight unit nodes; likewise the last
+// cube of a chunk joins the top levels (D = 6: 8 cubes, D = 7: 64) and writes the root.
+// ------------------------------------------------------------------------------------------------
 template <class T, bool OLD>
-__global__ void __launch_bounds__(CTA_THREADS, 3) apply_small_kernel(ApplyArgs a) {
+__global__ void __launch_bounds__(CTA_THREADS, 3) apply_kernel(ApplyArgs a) {
     __shared__ WarpSmem<T> ws[WARPS_PER_CTA];
     __shared__ CtaSmem cs;
     smem_init<T>(ws, &cs);
     Ctx<T> c;
     ctx_init<T>(c, a.in, ws, &cs, a.use_free != 0);
-    const u32 warp_global = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
-    const u32 nwarps = gridDim.x * WARPS_PER_CTA;
-    for (u32 chunk = warp_global; chunk < a.n; chunk += nwarps) {
-        // poisoned interner: skip the rest, the host reports the error (warp-uniform decision)
-        if (__any_sync(FULL, c.lane == 0 && ld_strong(a.in.error) != ERR_NONE)) {
-            if (c.lane == 0) {
-                a.roots[chunk] = 0;
-                if (a.changed) a.changed[chunk] = 0;
-            }
-            continue;
-        }
-        bool has_fill, has_patches;
-        u32 fill;
-        chunk_flags<T>(a, chunk, &has_fill, &fill, &has_patches);
-        u64 fl = phase0_fill<T>(c, has_fill, fill, has_patches);
-        if (!has_patches) {  // :756-758
-            if (c.lane == 0) {
-                if (has_fill) c.t.leaf_calls++;
-                write_root<T>(c, a, chunk, fl, has_fill);
-            }
-            continue;
-        }
-        Under u{0, fl, fill, int(a.depth)};
-        // with a fill the batch is built against Leaf(fill); the old tree is only released (:742-754)
-        const bool use_old = OLD && !has_fill && a.old_roots && a.old_roots[chunk] != 0;
-        if (use_old) u.old_root = a.old_roots[chunk];
-        bool present;
-        u64 root;
-        const u8* cm = a.masks + size_t(chunk) * a.blocks * 2;
-        const void* cv = (const u8*)a.values + size_t(chunk) * a.blocks * 8 * sizeof(T);
-        if (use_old)
-            root = build_unit<T, OLD>(c, cm, cv, 0, int(a.blocks), u, &present);
-        else
-            root = build_unit<T, false>(c, cm, cv, 0, int(a.blocks), u, &present);
-        if (c.lane == 0) write_root<T>(c, a, chunk, root, present);
-    }
-    cta_finish<T>(c);
-}
-
-// D >= 5: one CTA per chunk; each warp builds 512-block units, warp 0 joins the upper levels.
-template <class T, bool OLD>
-__global__ void __launch_bounds__(CTA_THREADS, 3) apply_large_kernel(ApplyArgs a) {
-    __shared__ WarpSmem<T> ws[WARPS_PER_CTA];
-    __shared__ CtaSmem cs;
-    smem_init<T>(ws, &cs);
-    Ctx<T> c;
-    ctx_init<T>(c, a.in, ws, &cs, a.use_free != 0);
-    const int warp = threadIdx.x >> 5;
+    const int lane = c.lane;
     const int D = int(a.depth);
-    const u32 n_super = a.blocks / (UNIT_BLOCKS * WARPS_PER_CTA);  // 32^3 sub-cubes: 1, 8, 64
-    for (u32 chunk = blockIdx.x; chunk < a.n; chunk += gridDim.x) {
-        // poisoned interner: skip the rest, the host reports the error (CTA-uniform decision)
-        if (__syncthreads_or(threadIdx.x == 0 && ld_strong(a.in.error) != ERR_NONE)) {
-            if (threadIdx.x == 0) {
+    const u32 upc = a.blocks > UNIT_BLOCKS ? a.blocks / UNIT_BLOCKS : 1;  // units per chunk: 1, 8, 64, 512
+    const int nblocks = a.blocks > UNIT_BLOCKS ? UNIT_BLOCKS : int(a.blocks);
+    const u32 cpc = upc / 8;                                             // 32^3 cubes per chunk: 0, 1, 8, 64
+    const unsigned long long total = (unsigned long long)a.n * upc;
+    const unsigned long long nwarps = (unsigned long long)gridDim.x * WARPS_PER_CTA;
+    unsigned long long w = (unsigned long long)blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
+    // masks of the first unit; inside the loop the next unit's masks are requested before the current
+    // unit is processed, so an empty unit never exposes its DRAM latency
+    u64 nlo = 0, nhi = 0;
+    if (w < total) load_unit_masks(a.masks + size_t(w / upc) * a.blocks * 2, size_t(w % upc) * UNIT_BLOCKS, nblocks, lane, &nlo, &nhi);
+    for (; w < total; w += nwarps) {
+        const u32 chunk = u32(w / upc), unit = u32(w % upc);
+        const u64 mlo = nlo, mhi = nhi;
+        {
+            const unsigned long long w2 = w + nwarps;
+            if (w2 < total) load_unit_masks(a.masks + size_t(w2 / upc) * a.blocks * 2, size_t(w2 % upc) * UNIT_BLOCKS, nblocks, lane, &nlo, &nhi);
+        }
+        // poisoned interner: skip the rest, the host reports the error (warp-uniform decision)
+        if (__any_sync(FULL, lane == 0 && ld_strong(a.in.error) != ERR_NONE)) {
+            if (lane == 0 && unit == 0) {
                 a.roots[chunk] = 0;
                 if (a.changed) a.changed[chunk] = 0;
             }
@@ -998,83 +1020,114 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) apply_large_kernel(ApplyArgs a
         bool has_fill, has_patches;
         u32 fill;
         chunk_flags<T>(a, chunk, &has_fill, &fill, &has_patches);
-        u64 fl = 0;
-        if (has_fill) {  // CTA-uniform
-            if (warp == 0) {
-                fl = phase0_fill<T>(c, true, fill, has_patches);
-                if (c.lane == 0) cs.top[0] = fl;
-            }
-            __syncthreads();
-            fl = cs.top[0];
-            __syncthreads();
-        }
-        if (!has_patches) {
-            if (threadIdx.x == 0) {
+        // phase 0 once per chunk (unit 0 takes the reference); every unit needs the fill leaf's id
+        u64 fl = phase0_fill<T>(c, has_fill, fill, has_patches && unit == 0);
+        if (!has_patches) {  // :756-758 — the tree becomes Leaf(fill), or nothing happens
+            if (lane == 0 && unit == 0) {
                 if (has_fill) c.t.leaf_calls++;
                 write_root<T>(c, a, chunk, fl, has_fill);
             }
             continue;
         }
         Under u{0, fl, fill, D};
+        // with a fill the batch is built against Leaf(fill); the old tree is only released (:742-754)
         const bool use_old = OLD && !has_fill && a.old_roots && a.old_roots[chunk] != 0;
         if (use_old) u.old_root = a.old_roots[chunk];
-        const u8* cm = a.masks + size_t(chunk) * a.blocks * 2;
         const void* cv = (const u8*)a.values + size_t(chunk) * a.blocks * 8 * sizeof(T);
-        for (u32 s = 0; s < n_super; ++s) {
-            bool present;
-            const u32 fb = (s * WARPS_PER_CTA + warp) * UNIT_BLOCKS;
-            u64 uid;
-            if (use_old)
-                uid = build_unit<T, OLD>(c, cm, cv, fb, UNIT_BLOCKS, u, &present);
-            else
-                uid = build_unit<T, false>(c, cm, cv, fb, UNIT_BLOCKS, u, &present);
-            if (c.lane == 0) {
-                cs.oct[warp] = uid;
-                cs.octp[warp] = present;
-            }
-            __syncthreads();
-            if (warp == 0) {  // the eight 16^3 units of one 32^3 cube (depth D-4) -> its node at depth D-5
-                const bool act = c.lane < 8;
-                u64 ch = act ? cs.oct[c.lane] : 0;
-                bool pr = act && cs.octp[c.lane] != 0;
-                u64 old_self = fl;
-                if (use_old) old_self = old_at(c.in, u.old_root, s, D - 5);
-                bool pp;
-                u64 pid = parent_node<T>(c, ch, pr, old_self, &pp);
-                if (c.lane == 0) {
-                    cs.top[s] = pid;
-                    cs.topp[s] = pp;
-                }
-            }
-            __syncthreads();
+        bool present;
+        u64 uid;
+        if (use_old)
+            uid = build_unit<T, OLD>(c, mlo, mhi, cv, unit * UNIT_BLOCKS, nblocks, u, &present);
+        else
+            uid = build_unit<T, false>(c, mlo, mhi, cv, unit * UNIT_BLOCKS, nblocks, u, &present);
+        if (upc == 1) {  // D <= 4: the unit is the tree
+            if (lane == 0) write_root<T>(c, a, chunk, uid, present);
+            continue;
         }
-        if (warp == 0) {
-            u32 n = n_super;
-            int d = D - 5;  // depth of the nodes currently in cs.top
-            while (n > 1) {  // 64 -> 8 -> 1
+        // ---- publish the unit; the last arriver of the cube joins it
+        const u32 cube = unit >> 3;
+        u32 arrived = 0;
+        if (lane == 0) {
+            st_strong(&a.unit_ids[w], uid);
+            a.unit_present[w] = present;
+            fence_gpu();
+            arrived = atomicAdd(&a.cube_done[size_t(chunk) * cpc + cube], 1u);
+        }
+        arrived = __shfl_sync(FULL, arrived, 0);
+        if (arrived != 7) continue;
+        fence_gpu();
+        u64 cid;
+        bool cpres;
+        {  // eight 16^3 units (depth D-4) -> the 32^3 cube's node (depth D-5)
+            const size_t base = (size_t(chunk) * cpc + cube) * 8;
+            const bool act = lane < 8;
+            u64 ch = act ? ld_strong(&a.unit_ids[base + lane]) : 0;
+            bool pr = act && ((volatile u8*)a.unit_present)[base + lane] != 0;
+            u64 old_self = fl;
+            if (use_old) old_self = old_at(c.in, u.old_root, cube, D - 5);
+            cid = parent_node<T>(c, ch, pr, old_self, &cpres);
+            cid = __shfl_sync(FULL, cid, 0);
+            cpres = __shfl_sync(FULL, int(cpres), 0) != 0;
+        }
+        if (cpc == 1) {
+            if (lane == 0) write_root<T>(c, a, chunk, cid, cpres);
+            continue;
+        }
+        // ---- D >= 6: publish the cube; the last cube of the chunk joins the top levels
+        if (lane == 0) {
+            st_strong(&a.cube_ids[size_t(chunk) * cpc + cube], cid);
+            a.cube_present[size_t(chunk) * cpc + cube] = cpres;
+            fence_gpu();
+            arrived = atomicAdd(&a.chunk_done[chunk], 1u);
+        }
+        arrived = __shfl_sync(FULL, arrived, 0);
+        if (arrived != cpc - 1) continue;
+        fence_gpu();
+        {
+            // stage the cube nodes (depth D-5) in the warp's scratch and reduce 64 -> 8 -> 1
+            u32 n = cpc;
+            for (u32 i = lane; i < n; i += 32) c.ws->l1[i] = ld_strong(&a.cube_ids[size_t(chunk) * cpc + i]);
+            u32 pb0 = __ballot_sync(FULL, lane < n && ((volatile u8*)a.cube_present)[size_t(chunk) * cpc + lane] != 0);
+            u32 pb1 = __ballot_sync(FULL, lane + 32 < n && ((volatile u8*)a.cube_present)[size_t(chunk) * cpc + lane + 32] != 0);
+            if (lane == 0) {
+                c.ws->l1p[0] = pb0;
+                c.ws->l1p[1] = pb1;
+            }
+            __syncwarp();
+            int d = D - 5;  // depth of the nodes currently staged
+            while (n > 1) {
+                u32 newp = 0;
+                u64 outv[2] = {0, 0};
                 for (u32 it = 0; it * 32 < n; ++it) {
-                    const u32 i = it * 32 + c.lane;
+                    const u32 i = it * 32 + lane;
                     const bool act = i < n;
-                    u64 ch = act ? cs.top[i] : 0;
-                    bool pr = act && cs.topp[i] != 0;
+                    u64 ch = act ? c.ws->l1[i] : 0;
+                    bool pr = act && ((c.ws->l1p[i >> 5] >> (i & 31)) & 1);
                     u64 old_self = fl;
                     if (use_old) old_self = old_at(c.in, u.old_root, (it * 32 + c.gs) >> 3, d - 1);
-                    __syncwarp();
                     bool pp;
                     u64 pid = parent_node<T>(c, ch, pr, old_self, &pp);
-                    __syncwarp();
-                    if (c.li == 0 && it * 32 + c.gs < n) {
-                        cs.top[it * 4 + (c.gs >> 3)] = pid;
-                        cs.topp[it * 4 + (c.gs >> 3)] = pp;
-                    }
-                    __syncwarp();
+                    const bool gact = it * 32 + c.gs < n;
+                    outv[it & 1] = pid;
+                    u32 ppb = __ballot_sync(FULL, pp && c.li == 0 && gact);
+                    u32 four = (ppb & 1) | ((ppb >> 7) & 2) | ((ppb >> 14) & 4) | ((ppb >> 21) & 8);
+                    newp |= four << (it * 4);
                 }
+                __syncwarp();
+                // write the parents back compacted (reads of this round are complete)
+                for (u32 it = 0; it * 32 < n; ++it)
+                    if (c.li == 0 && it * 32 + c.gs < n) c.ws->l1[it * 4 + (c.gs >> 3)] = outv[it & 1];
+                if (lane == 0) {
+                    c.ws->l1p[0] = newp;
+                    c.ws->l1p[1] = 0;
+                }
+                __syncwarp();
                 n /= 8;
                 d -= 1;
             }
-            if (c.lane == 0) write_root<T>(c, a, chunk, cs.top[0], cs.topp[0] != 0);
+            if (lane == 0) write_root<T>(c, a, chunk, c.ws->l1[0], (c.ws->l1p[0] & 1) != 0);
+            __syncwarp();
         }
-        __syncthreads();
     }
     cta_finish<T>(c);
 }

@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -83,6 +84,8 @@ struct vx_interner {
     u64* rel[2]{};
     size_t rel_cap[2]{};
     u32* d_rel_count = nullptr;  // [2]
+    void* join = nullptr;        // apply_kernel's join scratch (unit/cube ids + arrival counters)
+    size_t join_bytes = 0;
     uint64_t free_host = 0;      // entries in the free list
     uint64_t tombs_host = 0;     // deleted table slots since the last rehash
     std::mutex mu;
@@ -137,6 +140,19 @@ bool is_device_ptr(const void* p) {
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
+// Device-visible alias of a pinned + mapped host pointer (cudaMallocHost / cudaHostRegister), else null.
+const void* host_device_alias(const void* p) {
+    if (!p) return nullptr;
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    if (a.type != cudaMemoryTypeHost || !a.devicePointer) return nullptr;
+    if ((reinterpret_cast<uintptr_t>(a.devicePointer) & 15) != 0) return nullptr;  // the kernel loads 16 B vectors
+    return a.devicePointer;
+}
+
 int check_device_error(vx_interner* it) {
     u32 err = 0;
     CU_TRY(cudaMemcpyAsync(&err, &it->d_scalars->error, sizeof(u32), cudaMemcpyDeviceToHost, it->stream));
@@ -165,17 +181,37 @@ int launch_apply_t(vx_interner* it, int depth, size_t n, const u8* d_masks, cons
     a.depth = u32(depth);
     a.blocks = u32(blocks_for_depth(depth));
     a.use_free = it->free_host > 0 ? 1u : 0u;
-    int occ = 0;
-    if (depth >= 5) {
-        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, apply_large_kernel<T, OLD>, CTA_THREADS, 0));
-        size_t grid = std::min<size_t>(n, size_t(std::max(occ, 1)) * it->sm_count);
-        apply_large_kernel<T, OLD><<<unsigned(grid), CTA_THREADS, 0, s>>>(a);
-    } else {
-        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, apply_small_kernel<T, OLD>, CTA_THREADS, 0));
-        size_t ctas = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-        size_t grid = std::min<size_t>(ctas, size_t(std::max(occ, 1)) * it->sm_count);
-        apply_small_kernel<T, OLD><<<unsigned(grid), CTA_THREADS, 0, s>>>(a);
+    // join scratch for D >= 5 (see apply_kernel): ids/present flags per unit and per cube + arrival counters
+    const size_t upc = a.blocks > UNIT_BLOCKS ? a.blocks / UNIT_BLOCKS : 1, cpc = upc / 8;
+    if (upc > 1) {
+        const size_t counters = (n * cpc + n) * 4;
+        const size_t need = counters + n * upc * 8 + n * cpc * 8 + n * upc + n * cpc + 64;
+        if (need > it->join_bytes) {
+            CU_TRY(cudaStreamSynchronize(s));
+            cudaFree(it->join);
+            it->join = nullptr;
+            it->join_bytes = 0;
+            CU_TRY(cudaMalloc(&it->join, need));
+            it->join_bytes = need;
+        }
+        u8* p = (u8*)it->join;
+        a.cube_done = (u32*)p;
+        a.chunk_done = a.cube_done + n * cpc;
+        p += (counters + 15) / 16 * 16;
+        a.unit_ids = (u64*)p;
+        p += n * upc * 8;
+        a.cube_ids = (u64*)p;
+        p += n * cpc * 8;
+        a.unit_present = p;
+        p += n * upc;
+        a.cube_present = p;
+        CU_TRY(cudaMemsetAsync(it->join, 0, counters, s));
     }
+    int occ = 0;
+    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, apply_kernel<T, OLD>, CTA_THREADS, 0));
+    const size_t ctas = (n * upc + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    const size_t grid = std::min<size_t>(ctas, size_t(std::max(occ, 1)) * it->sm_count);
+    apply_kernel<T, OLD><<<unsigned(grid), CTA_THREADS, 0, s>>>(a);
     CU_TRY(cudaGetLastError());
     if (a.use_free) {
         clamp_free_count_kernel<<<1, 1, 0, s>>>(it->dev);
@@ -205,8 +241,11 @@ int launch_apply(vx_interner* it, int depth, size_t n, const u8* d_masks, const 
 
 int valid_depth(int d) { return d >= 2 && d <= 7; }
 
-int init_state(vx_interner* it) {
-    cudaStream_t s = it->stream;
+__global__ void init_scalars_kernel(u32* words, u32 n) {
+    for (u32 i = threadIdx.x; i < n; i += blockDim.x) words[i] = i == 0 ? 1u : 0u;  // next_index = 1 (mod.rs:101)
+}
+
+int init_state(vx_interner* it, cudaStream_t s, bool sync) {
     CU_TRY(cudaMemsetAsync(it->dev.slots, 0, it->nbuckets * 64, s));
     CU_TRY(cudaMemsetAsync(it->dev.refs, 0, it->capacity * 4, s));
     CU_TRY(cudaMemsetAsync(it->dev.gens, 0, it->capacity * 2, s));
@@ -219,10 +258,10 @@ int init_state(vx_interner* it) {
         CU_TRY(cudaMemsetAsync(it->dev.leaf_keys, 0, it->leaf_slots * 8, s));
         CU_TRY(cudaMemsetAsync(it->dev.leaf_ids, 0, it->leaf_slots * 8, s));
     }
-    Scalars init{};
-    init.next_index = 1;  // interner/mod.rs:101
-    CU_TRY(cudaMemcpyAsync(it->d_scalars, &init, sizeof(init), cudaMemcpyHostToDevice, s));
-    CU_TRY(cudaStreamSynchronize(s));
+    // (a kernel, not a memcpy from a stack variable: the async form must not read host memory later)
+    init_scalars_kernel<<<1, 32, 0, s>>>((u32*)it->d_scalars, u32(sizeof(Scalars) / 4));
+    CU_TRY(cudaGetLastError());
+    if (sync) CU_TRY(cudaStreamSynchronize(s));
     it->poisoned = false;
     it->free_host = 0;
     it->tombs_host = 0;
@@ -389,7 +428,7 @@ vx_interner* vx_interner_create(size_t budget, vx_dtype dtype, int device) {
     d.free_count = &it->d_scalars->free_count;
     d.error = &it->d_scalars->error;
     d.ctr = &it->d_scalars->ctr;
-    if (init_state(it) != VX_OK) {
+    if (init_state(it, it->stream, true) != VX_OK) {
         vx_interner_destroy(it);
         return nullptr;
     }
@@ -418,6 +457,7 @@ void vx_interner_destroy(vx_interner* it) {
         if (it->ev_done[i]) cudaEventDestroy(it->ev_done[i]);
     }
     cudaFree(it->scratch);
+    cudaFree(it->join);
     cudaFree(it->rel[0]);
     cudaFree(it->rel[1]);
     cudaFree(it->d_rel_count);
@@ -431,7 +471,12 @@ void vx_interner_destroy(vx_interner* it) {
 int vx_interner_reset(vx_interner* it) {
     if (!it) return fail(VX_E_INVALID, "null interner");
     DeviceGuard g(it->device);
-    return init_state(it);
+    return init_state(it, it->stream, true);
+}
+int vx_interner_reset_async(vx_interner* it, void* stream) {
+    if (!it) return fail(VX_E_INVALID, "null interner");
+    DeviceGuard g(it->device);
+    return init_state(it, stream ? (cudaStream_t)stream : it->stream, false);
 }
 size_t vx_interner_capacity(const vx_interner* it) { return it ? it->capacity : 0; }
 vx_dtype vx_interner_dtype(const vx_interner* it) { return it ? it->dtype : VX_U8; }
@@ -709,6 +754,8 @@ int vx_apply_batches_device(vx_interner* it, uint8_t depth, size_t n, const uint
     if (!it || !d_masks || !d_values || !d_roots) return fail(VX_E_INVALID, "null argument");
     if (!valid_depth(depth)) return fail(VX_E_INVALID, "max_depth must be in [2,7]");
     if (it->poisoned) return fail(VX_E_POISONED, "interner overflowed earlier; reset it");
+    if ((reinterpret_cast<uintptr_t>(d_masks) | reinterpret_cast<uintptr_t>(d_values)) & 15)
+        return fail(VX_E_INVALID, "device masks/values must be 16-byte aligned");
     DeviceGuard g(it->device);
     cudaStream_t s = stream ? (cudaStream_t)stream : it->stream;
     return launch_apply(it, depth, n, d_masks, d_values, d_flags, d_fills, d_roots, d_changed, s);
@@ -726,6 +773,8 @@ static int apply_slab_impl(vx_interner* it, uint8_t depth, size_t n, const uint8
     const size_t B = blocks_for_depth(depth), mbytes = B * 2, vbytes = B * 8 * dtype_size(it->dtype);
     const bool dev_in = is_device_ptr(masks);
     if (dev_in != is_device_ptr(values)) return fail(VX_E_INVALID, "masks and values must live in the same memory space");
+    if (dev_in && ((reinterpret_cast<uintptr_t>(masks) | reinterpret_cast<uintptr_t>(values)) & 15))
+        return fail(VX_E_INVALID, "device masks/values must be 16-byte aligned");
     const bool dev_roots = is_device_ptr(roots_out), dev_changed = changed_out && is_device_ptr(changed_out);
     cudaStream_t s = it->stream;
     // per-chunk options and outputs live in device scratch: [roots n*8][fills n*8][old n*8][changed n][flags n]
@@ -760,8 +809,19 @@ static int apply_slab_impl(vx_interner* it, uint8_t depth, size_t n, const uint8
             k_fills = d_fills;
         }
     }
+    // Pinned (page-locked, mapped) host batches are read by the kernel itself over PCIe ("zero copy"):
+    // the kernel loads every mask once but VALUES only for blocks that have a set bit, so a sparse
+    // batch moves a fraction of its bytes across the bus and nothing is staged through HBM.
+    // VX_HOST_MODE=staged forces the double-buffered copy path (the only one for pageable memory).
+    const void* zm = dev_in ? nullptr : host_device_alias(masks);
+    const void* zv = dev_in ? nullptr : host_device_alias(values);
+    const char* mode = getenv("VX_HOST_MODE");
+    const bool zero_copy = zm && zv && !(mode && strcmp(mode, "staged") == 0);
     if (dev_in) {
         rc = launch_apply(it, depth, n, masks, values, k_flags, k_fills, d_roots, d_changed, s, k_old);
+        if (rc != VX_OK) return rc;
+    } else if (zero_copy) {
+        rc = launch_apply(it, depth, n, (const u8*)zm, zv, k_flags, k_fills, d_roots, d_changed, s, k_old);
         if (rc != VX_OK) return rc;
     } else {
         // host batches: H2D on the copy stream into one of two staging slabs while the previous slab
