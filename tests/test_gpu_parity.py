@@ -151,3 +151,33 @@ def test_bounds_and_argument_errors(gpu_api):
     with pytest.raises(vx.VoxelisError):
         vx.VoxInterner.with_memory_budget(10)
     assert t.get(it, (1, 2, 3)) is None and t.is_empty() and not t.is_dirty()
+
+
+@pytest.mark.parametrize("run", ["1", "8"])
+@pytest.mark.parametrize("depth", [5, 6])
+def test_both_join_paths(gpu_api, oracle_api, depth, run, monkeypatch):
+    """apply_kernel hands out runs of 8 units (a warp owns a 32^3 cube, local join) when there are many
+    cubes, single units (atomic last-arriver join) otherwise; VX_FORCE_RUN pins either path."""
+    monkeypatch.setenv("VX_FORCE_RUN", run)
+    n = 24 if depth == 5 else 4
+    parts = [wl.batch_from_function(depth, wl.p_random(4), wl.U8, n),
+             wl.batch_from_function(depth, wl.p_random(255, cell=4), wl.U8, 3),
+             wl.named_workload("hollow", 2, depth, wl.U8)]
+    masks = np.concatenate([p[0] for p in parts])
+    values = np.concatenate([p[1] for p in parts])
+    masks[1] = 0
+    r = parity.build_both(gpu_api, oracle_api, depth, masks, values, wl.U8, budget=512 << 20)
+    parity.assert_parity(gpu_api, oracle_api, depth, *r)
+
+
+def test_depth7_extension(gpu_api, oracle_api):
+    """D = 7 (128^3) is beyond the reference (MaxDepth::new asserts < 7, core/max_depth.rs:77-83);
+    parity is against the oracle generalised with the PATH_MASKS formula."""
+    parts = [wl.batch_from_function(7, wl.p_random(255, cell=4), wl.U8, 1),
+             wl.batch_from_function(7, wl.p_sparse(3, 8), wl.U8, 1)]
+    masks = np.concatenate([p[0] for p in parts])
+    values = np.concatenate([p[1] for p in parts])
+    r = parity.build_both(gpu_api, oracle_api, 7, masks, values, wl.U8, budget=512 << 20)
+    parity.assert_parity(gpu_api, oracle_api, 7, *r, dense_check=False)
+    g, groots, c, croots = r[0], r[1], r[3], r[4]
+    assert np.array_equal(g.roots_to_vec(groots[:1], 7)[0], c.root_to_vec(croots[0], 7))

@@ -216,16 +216,17 @@ struct WarpSmem {
     u64 bval[VT<T>::BC];
     u64 ukey[UC * 8];  // children[8] -> id
     u64 uval[UC];
-    u64 l1[64];  // ids of the unit's level-1 parents (64), level-2 (8)
-    u64 l2[8];
-    u32 l1p[2];  // "entered paths" bits
-    u32 l2p;
+    u64 l1[64];       // nodes being joined (level-1 parents of a unit; unit / cube nodes during joins)
+    u8 p1[64];        // "entered paths" flag per node
+    u64 run_ids[8];   // run == 8: the unit nodes of the cube this warp owns
+    u8 run_pres[8];
     u32 lkey[sizeof(T) == 1 ? 1 : LC];  // wide T only: value -> leaf id
     u64 lid[sizeof(T) == 1 ? 1 : LC];
 };
 struct CtaSmem {
     u64 leaf[256];     // u8: value -> leaf id (lazy copy of InternerDev::leaf_u8)
     u32 leafref[256];  // u8: pending in-degree increments of leaves
+    u32 warps_done;    // exit arrival counter (the last warp flushes leafref)
 };
 
 struct Tally {  // per-lane statistics, reduced once at kernel exit
@@ -728,8 +729,9 @@ __device__ inline void old_block_state(Ctx<T>& c, const Under& u, u32 blk, bool 
 }
 
 // ------------------------------------------------------------------------------------------------
-// A warp builds the sub-tree over `nblocks` (8, 64 or 512) Morton-consecutive blocks starting at
-// block `first_block` of the chunk.
+// Block stage of a unit: `nblocks` (8, 64 or 512) Morton-consecutive blocks starting at block
+// `first_block` of the chunk -> the unit's level-1 parents in ws->l1[0 .. nblocks/8) / ws->p1.
+// Returns false when nothing in the unit has a set bit (fresh trees only).
 // ------------------------------------------------------------------------------------------------
 // All set_masks of a unit in one shot: lane L gets the masks of blocks [16L, 16L+16) — two 16-byte
 // coalesced loads per lane, 1 KiB per warp for a full 512-block unit.  clear_mask bytes are dropped
@@ -750,28 +752,24 @@ __device__ __forceinline__ void load_unit_masks(const u8* masks, size_t first_bl
 }
 
 template <class T, bool OLD>
-__device__ inline u64 build_unit(Ctx<T>& c, u64 mlo, u64 mhi, const void* values, u32 first_block, int nblocks,
-                                 const Under& u, bool* upresent) {
+__device__ __forceinline__ bool build_blocks(Ctx<T>& c, u64 mlo, u64 mhi, const void* values, u32 first_block,
+                                             int nblocks, const Under& u) {
     using V = VT<T>;
     const int lane = c.lane;
     const int n_iter = (nblocks + 31) / 32;
-    const int D = u.depth;
     const typename V::Key fillw = V::splat(u.fill_leaf ? u.fill : 0);
-    // (2) Which 32-block iterations contain any set bit (iteration it <- lanes 2it, 2it+1).  Blocks with
-    //     set_mask == 0 are skipped by phase 1 (voxtree.rs:779-781): their VALUES are never loaded, and
-    //     iterations without a set bit cost nothing.
+    // Which 32-block iterations contain any set bit (iteration it <- lanes 2it, 2it+1).  Blocks with
+    // set_mask == 0 are skipped by phase 1 (voxtree.rs:779-781): their VALUES are never loaded, and
+    // iterations without a set bit cost nothing.
     u32 nzl = __ballot_sync(FULL, (mlo | mhi) != 0);
     u32 iters = (nzl | (nzl >> 1)) & 0x55555555u;  // bit 2*it
     if (OLD) iters = (n_iter >= 16 ? 0xFFFFFFFFu : ((1u << (2 * n_iter)) - 1)) & 0x55555555u;  // every group needs its old node
-    if (!OLD && iters == 0) {  // nothing set in this unit: it stays what it was (fill leaf / EMPTY)
-        *upresent = false;
-        return u.fill_leaf;
-    }
+    if (!OLD && iters == 0) return false;  // nothing set in this unit: it stays what it was (fill leaf / EMPTY)
     if (!OLD) {
         c.ws->l1[lane] = u.fill_leaf;
         c.ws->l1[lane + 32] = u.fill_leaf;
     }
-    if (lane < 2) c.ws->l1p[lane] = 0;
+    ((u16*)c.ws->p1)[lane] = 0;
     __syncwarp();
     auto mask_of = [&](int it) -> u32 {
         const int src = 2 * it + (lane >> 4);
@@ -779,8 +777,8 @@ __device__ inline u64 build_unit(Ctx<T>& c, u64 mlo, u64 mhi, const void* values
         u64 w = (lane & 8) ? hi : lo;
         return u32(w >> (8 * (lane & 7))) & 0xFF;
     };
-    // (3) software pipeline over the non-empty iterations: the value loads of the next one are issued
-    //     before the current one is processed; only lanes whose block has a set bit load (8 B / 32 B).
+    // software pipeline over the non-empty iterations: the value loads of the next one are issued
+    // before the current one is processed; only lanes whose block has a set bit load (8 B / 32 B).
     int it = iters ? ((__ffs(iters) - 1) >> 1) : -1;
     typename V::Key nvals = V::zero();
     u32 nmask = 0;
@@ -807,62 +805,46 @@ __device__ inline u64 build_unit(Ctx<T>& c, u64 mlo, u64 mhi, const void* values
         u64 id = block_node<T>(c, active, vals, smask, oldw, old_id, &present);
         bool pp;
         u64 pid = parent_node<T>(c, id, present && active, parent_old, &pp);
-        const bool gact = cur * 32 + c.gs < nblocks;
-        if (c.li == 0 && gact) c.ws->l1[cur * 4 + (c.gs >> 3)] = pid;
-        u32 ppb = __ballot_sync(FULL, pp && c.li == 0 && gact);
-        if (lane == 0) {
-            // compact the four group bits (lanes 0,8,16,24) into bits 0..3
-            u32 four = (ppb & 1) | ((ppb >> 7) & 2) | ((ppb >> 14) & 4) | ((ppb >> 21) & 8);
-            c.ws->l1p[(cur * 4) >> 5] |= four << ((cur * 4) & 31);
+        if (c.li == 0 && cur * 32 + c.gs < nblocks) {
+            c.ws->l1[cur * 4 + (c.gs >> 3)] = pid;
+            c.ws->p1[cur * 4 + (c.gs >> 3)] = pp;
         }
     }
     __syncwarp();
-    int n1 = nblocks / 8;
-    if (n1 <= 1) {
-        *upresent = (c.ws->l1p[0] & 1) != 0;
-        u64 r = c.ws->l1[0];
+    return true;
+}
+
+// Joins ws->l1[0..n) (nodes of depth d; node i sits at position pos0+i of that depth) level by level
+// down to one node, compacting in place.  The ONLY other call site of parent_node (keeps the kernel
+// inside the instruction cache).
+template <class T>
+__device__ __forceinline__ u64 reduce_levels(Ctx<T>& c, u32 n, int d, u32 pos0, const Under& u, bool use_old,
+                                             bool* present) {
+    while (n > 1) {
+        for (u32 it = 0; it * 32 < n; ++it) {
+            const u32 i = it * 32 + c.lane;
+            const bool act = i < n;
+            u64 ch = act ? c.ws->l1[i] : 0;
+            bool pr = act && c.ws->p1[i] != 0;
+            u64 old_self = u.fill_leaf;
+            if (use_old) old_self = old_at(c.in, u.old_root, (pos0 + it * 32 + c.gs) >> 3, d - 1);
+            bool pp;
+            u64 pid = parent_node<T>(c, ch, pr, old_self, &pp);
+            __syncwarp();  // all reads of this slice are done before its head is overwritten
+            if (c.li == 0 && it * 32 + c.gs < n) {
+                c.ws->l1[it * 4 + (c.gs >> 3)] = pid;
+                c.ws->p1[it * 4 + (c.gs >> 3)] = pp;
+            }
+        }
         __syncwarp();
-        return r;
+        n >>= 3;
+        d -= 1;
+        pos0 >>= 3;
     }
-    // level 2: n1 (8 or 64) nodes at depth D-2 -> n1/8 parents at depth D-3
-    u32 p2 = 0;
-    for (int it = 0; it * 32 < n1; ++it) {
-        const int i = it * 32 + lane;
-        const bool act = i < n1;
-        u64 ch = act ? c.ws->l1[i] : 0;
-        bool pr = act && ((c.ws->l1p[i >> 5] >> (i & 31)) & 1);
-        u64 old_self = u.fill_leaf;
-        if (OLD) old_self = old_at(c.in, u.old_root, ((first_block >> 3) + it * 32 + c.gs) >> 3, D - 3);
-        bool pp;
-        u64 pid = parent_node<T>(c, ch, pr, old_self, &pp);
-        const bool gact = it * 32 + c.gs < n1;
-        if (c.li == 0 && gact) c.ws->l2[it * 4 + (c.gs >> 3)] = pid;
-        u32 ppb = __ballot_sync(FULL, pp && c.li == 0 && gact);
-        u32 four = (ppb & 1) | ((ppb >> 7) & 2) | ((ppb >> 14) & 4) | ((ppb >> 21) & 8);
-        p2 |= four << (it * 4);
-    }
+    *present = c.ws->p1[0] != 0;
+    u64 r = c.ws->l1[0];
     __syncwarp();
-    int n2 = n1 / 8;
-    if (n2 <= 1) {
-        *upresent = (p2 & 1) != 0;
-        u64 r = c.ws->l2[0];
-        __syncwarp();
-        return r;
-    }
-    // level 3: 8 nodes at depth D-3 -> 1 parent at depth D-4
-    {
-        const bool act = lane < 8;
-        u64 ch = act ? c.ws->l2[lane] : 0;
-        bool pr = act && ((p2 >> lane) & 1);
-        u64 old_self = u.fill_leaf;
-        if (OLD) old_self = old_at(c.in, u.old_root, first_block >> 9, D - 4);
-        bool pp;
-        u64 pid = parent_node<T>(c, ch, pr, old_self, &pp);
-        pid = __shfl_sync(FULL, pid, 0);
-        *upresent = __shfl_sync(FULL, int(pp), 0) != 0;
-        __syncwarp();
-        return pid;
-    }
+    return r;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -885,6 +867,8 @@ struct ApplyArgs {
     u64* cube_ids;      // [n][cubes_per_chunk]
     u8* cube_present;   // [n][cubes_per_chunk]
     u32* chunk_done;    // [n]                   zeroed before launch
+    u32* work_next;     // dynamic work counter (runs), zeroed before launch
+    u32 run;            // units per work item: 8 = a whole 32^3 cube per warp (local join), 1 = one unit
     u32 n;
     u32 depth;
     u32 blocks;    // B
@@ -911,15 +895,10 @@ __device__ inline void smem_init(WarpSmem<T>* ws, CtaSmem* cs) {
     __syncthreads();
 }
 
+// Kernel exit.  No CTA barrier: warps leave as they run out of work; the last one to arrive flushes
+// the CTA's leaf in-degree histogram.
 template <class T>
 __device__ inline void cta_finish(Ctx<T>& c) {
-    __syncthreads();
-    if (sizeof(T) == 1) {  // flush the leaf in-degree histogram
-        for (u32 v = threadIdx.x; v < 256; v += blockDim.x) {
-            u32 n = c.cs->leafref[v];
-            if (n) atomicAdd(&c.in.refs[id_index(c.cs->leaf[v])], n);
-        }
-    }
     Tally& t = c.t;
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
@@ -940,6 +919,22 @@ __device__ inline void cta_finish(Ctx<T>& c) {
         if (t.collapsed) atomicAdd(&k->collapsed, (ull)t.collapsed);
         if (t.probes) atomicAdd(&k->probe_steps, (ull)t.probes);
         if (t.local) atomicAdd(&k->cache_hits_local, (ull)t.local);
+    }
+    if (sizeof(T) == 1) {
+        u32 arrived = 0;
+        __syncwarp();
+        if (c.lane == 0) {
+            __threadfence_block();
+            arrived = atomicAdd(&c.cs->warps_done, 1u);
+        }
+        arrived = __shfl_sync(FULL, arrived, 0);
+        if (arrived == WARPS_PER_CTA - 1) {
+            __threadfence_block();
+            for (u32 v = c.lane; v < 256; v += 32) {
+                u32 n = ((volatile u32*)c.cs->leafref)[v];
+                if (n) atomicAdd(&c.in.refs[id_index(((volatile u64*)c.cs->leaf)[v])], n);
+            }
+        }
     }
 }
 
@@ -977,11 +972,14 @@ __device__ __forceinline__ void write_root(Ctx<T>& c, const ApplyArgs& a, u32 ch
 }
 
 // ------------------------------------------------------------------------------------------------
-// apply kernel.  Work item = one unit (<= 512 Morton-consecutive blocks = a 16^3-voxel sub-cube, or
-// the whole chunk when D <= 4), one warp per unit, persistent warps striding over all units of all
-// chunks.  Warps never wait for each other: a unit's node is published to global scratch, and the
-// LAST warp to arrive at a 32^3 cube (atomic counter) joins its eight unit nodes; likewise the last
-// cube of a chunk joins the top levels (D = 6: 8 cubes, D = 7: 64) and writes the root.
+// apply kernel.  Unit = <= 512 Morton-consecutive blocks (a 16^3-voxel sub-cube, or the whole chunk
+// when D <= 4), built by ONE warp.  Work items are runs of `a.run` consecutive units handed out by an
+// atomic counter (dynamic load balance: units range from empty to 512 new nodes):
+//   run == 8  a warp owns a whole 32^3 cube and joins its eight unit nodes locally;
+//   run == 1  (few chunks) units of a cube go to different warps; each publishes its node to global
+//             scratch and the LAST to arrive (atomic counter) joins the cube.
+// The last cube of a chunk joins the top levels the same way (D = 6: 8 cubes, D = 7: 64).
+// No __syncthreads anywhere in the loop: warps never wait for each other.
 // ------------------------------------------------------------------------------------------------
 template <class T, bool OLD>
 __global__ void __launch_bounds__(CTA_THREADS, 3) apply_kernel(ApplyArgs a) {
@@ -995,139 +993,144 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) apply_kernel(ApplyArgs a) {
     const u32 upc = a.blocks > UNIT_BLOCKS ? a.blocks / UNIT_BLOCKS : 1;  // units per chunk: 1, 8, 64, 512
     const int nblocks = a.blocks > UNIT_BLOCKS ? UNIT_BLOCKS : int(a.blocks);
     const u32 cpc = upc / 8;                                             // 32^3 cubes per chunk: 0, 1, 8, 64
-    const unsigned long long total = (unsigned long long)a.n * upc;
-    const unsigned long long nwarps = (unsigned long long)gridDim.x * WARPS_PER_CTA;
-    unsigned long long w = (unsigned long long)blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
-    // masks of the first unit; inside the loop the next unit's masks are requested before the current
-    // unit is processed, so an empty unit never exposes its DRAM latency
+    const u32 R = a.run;
+    const unsigned long long total_units = (unsigned long long)a.n * upc;
+    const unsigned long long total_runs = (total_units + R - 1) / R;
+
+    auto grab = [&]() -> unsigned long long {  // next run index (dynamic)
+        u32 r = 0;
+        if (lane == 0) r = atomicAdd(a.work_next, 1u);
+        return __shfl_sync(FULL, r, 0);
+    };
+    auto masks_of = [&](unsigned long long w, u64* lo, u64* hi) {
+        load_unit_masks(a.masks + size_t(w / upc) * a.blocks * 2, size_t(w % upc) * UNIT_BLOCKS, nblocks, lane, lo, hi);
+    };
+
+    unsigned long long run = grab();
+    unsigned long long next_run = run < total_runs ? grab() : total_runs;
     u64 nlo = 0, nhi = 0;
-    if (w < total) load_unit_masks(a.masks + size_t(w / upc) * a.blocks * 2, size_t(w % upc) * UNIT_BLOCKS, nblocks, lane, &nlo, &nhi);
-    for (; w < total; w += nwarps) {
-        const u32 chunk = u32(w / upc), unit = u32(w % upc);
-        const u64 mlo = nlo, mhi = nhi;
-        {
-            const unsigned long long w2 = w + nwarps;
-            if (w2 < total) load_unit_masks(a.masks + size_t(w2 / upc) * a.blocks * 2, size_t(w2 % upc) * UNIT_BLOCKS, nblocks, lane, &nlo, &nhi);
-        }
-        // poisoned interner: skip the rest, the host reports the error (warp-uniform decision)
-        if (__any_sync(FULL, lane == 0 && ld_strong(a.in.error) != ERR_NONE)) {
-            if (lane == 0 && unit == 0) {
-                a.roots[chunk] = 0;
-                if (a.changed) a.changed[chunk] = 0;
+    if (run < total_runs) masks_of(run * R, &nlo, &nhi);
+    while (run < total_runs) {
+        for (u32 k = 0; k < R; ++k) {
+            const unsigned long long w = run * R + k;
+            if (w >= total_units) break;
+            const u32 chunk = u32(w / upc), unit = u32(w % upc);
+            const u64 mlo = nlo, mhi = nhi;
+            {  // request the masks of the unit after this one before doing any work
+                unsigned long long w2 = (k + 1 < R) ? w + 1 : next_run * R;
+                if (k + 1 < R ? (w2 < total_units) : (next_run < total_runs)) masks_of(w2, &nlo, &nhi);
             }
-            continue;
-        }
-        bool has_fill, has_patches;
-        u32 fill;
-        chunk_flags<T>(a, chunk, &has_fill, &fill, &has_patches);
-        // phase 0 once per chunk (unit 0 takes the reference); every unit needs the fill leaf's id
-        u64 fl = phase0_fill<T>(c, has_fill, fill, has_patches && unit == 0);
-        if (!has_patches) {  // :756-758 — the tree becomes Leaf(fill), or nothing happens
-            if (lane == 0 && unit == 0) {
-                if (has_fill) c.t.leaf_calls++;
-                write_root<T>(c, a, chunk, fl, has_fill);
-            }
-            continue;
-        }
-        Under u{0, fl, fill, D};
-        // with a fill the batch is built against Leaf(fill); the old tree is only released (:742-754)
-        const bool use_old = OLD && !has_fill && a.old_roots && a.old_roots[chunk] != 0;
-        if (use_old) u.old_root = a.old_roots[chunk];
-        const void* cv = (const u8*)a.values + size_t(chunk) * a.blocks * 8 * sizeof(T);
-        bool present;
-        u64 uid;
-        if (use_old)
-            uid = build_unit<T, OLD>(c, mlo, mhi, cv, unit * UNIT_BLOCKS, nblocks, u, &present);
-        else
-            uid = build_unit<T, false>(c, mlo, mhi, cv, unit * UNIT_BLOCKS, nblocks, u, &present);
-        if (upc == 1) {  // D <= 4: the unit is the tree
-            if (lane == 0) write_root<T>(c, a, chunk, uid, present);
-            continue;
-        }
-        // ---- publish the unit; the last arriver of the cube joins it
-        const u32 cube = unit >> 3;
-        u32 arrived = 0;
-        if (lane == 0) {
-            st_strong(&a.unit_ids[w], uid);
-            a.unit_present[w] = present;
-            fence_gpu();
-            arrived = atomicAdd(&a.cube_done[size_t(chunk) * cpc + cube], 1u);
-        }
-        arrived = __shfl_sync(FULL, arrived, 0);
-        if (arrived != 7) continue;
-        fence_gpu();
-        u64 cid;
-        bool cpres;
-        {  // eight 16^3 units (depth D-4) -> the 32^3 cube's node (depth D-5)
-            const size_t base = (size_t(chunk) * cpc + cube) * 8;
-            const bool act = lane < 8;
-            u64 ch = act ? ld_strong(&a.unit_ids[base + lane]) : 0;
-            bool pr = act && ((volatile u8*)a.unit_present)[base + lane] != 0;
-            u64 old_self = fl;
-            if (use_old) old_self = old_at(c.in, u.old_root, cube, D - 5);
-            cid = parent_node<T>(c, ch, pr, old_self, &cpres);
-            cid = __shfl_sync(FULL, cid, 0);
-            cpres = __shfl_sync(FULL, int(cpres), 0) != 0;
-        }
-        if (cpc == 1) {
-            if (lane == 0) write_root<T>(c, a, chunk, cid, cpres);
-            continue;
-        }
-        // ---- D >= 6: publish the cube; the last cube of the chunk joins the top levels
-        if (lane == 0) {
-            st_strong(&a.cube_ids[size_t(chunk) * cpc + cube], cid);
-            a.cube_present[size_t(chunk) * cpc + cube] = cpres;
-            fence_gpu();
-            arrived = atomicAdd(&a.chunk_done[chunk], 1u);
-        }
-        arrived = __shfl_sync(FULL, arrived, 0);
-        if (arrived != cpc - 1) continue;
-        fence_gpu();
-        {
-            // stage the cube nodes (depth D-5) in the warp's scratch and reduce 64 -> 8 -> 1
-            u32 n = cpc;
-            for (u32 i = lane; i < n; i += 32) c.ws->l1[i] = ld_strong(&a.cube_ids[size_t(chunk) * cpc + i]);
-            u32 pb0 = __ballot_sync(FULL, lane < n && ((volatile u8*)a.cube_present)[size_t(chunk) * cpc + lane] != 0);
-            u32 pb1 = __ballot_sync(FULL, lane + 32 < n && ((volatile u8*)a.cube_present)[size_t(chunk) * cpc + lane + 32] != 0);
-            if (lane == 0) {
-                c.ws->l1p[0] = pb0;
-                c.ws->l1p[1] = pb1;
-            }
-            __syncwarp();
-            int d = D - 5;  // depth of the nodes currently staged
-            while (n > 1) {
-                u32 newp = 0;
-                u64 outv[2] = {0, 0};
-                for (u32 it = 0; it * 32 < n; ++it) {
-                    const u32 i = it * 32 + lane;
-                    const bool act = i < n;
-                    u64 ch = act ? c.ws->l1[i] : 0;
-                    bool pr = act && ((c.ws->l1p[i >> 5] >> (i & 31)) & 1);
-                    u64 old_self = fl;
-                    if (use_old) old_self = old_at(c.in, u.old_root, (it * 32 + c.gs) >> 3, d - 1);
-                    bool pp;
-                    u64 pid = parent_node<T>(c, ch, pr, old_self, &pp);
-                    const bool gact = it * 32 + c.gs < n;
-                    outv[it & 1] = pid;
-                    u32 ppb = __ballot_sync(FULL, pp && c.li == 0 && gact);
-                    u32 four = (ppb & 1) | ((ppb >> 7) & 2) | ((ppb >> 14) & 4) | ((ppb >> 21) & 8);
-                    newp |= four << (it * 4);
+            // poisoned interner: skip the rest, the host reports the error (warp-uniform decision)
+            if (__any_sync(FULL, lane == 0 && ld_strong(a.in.error) != ERR_NONE)) {
+                if (lane == 0 && unit == 0) {
+                    a.roots[chunk] = 0;
+                    if (a.changed) a.changed[chunk] = 0;
                 }
-                __syncwarp();
-                // write the parents back compacted (reads of this round are complete)
-                for (u32 it = 0; it * 32 < n; ++it)
-                    if (c.li == 0 && it * 32 + c.gs < n) c.ws->l1[it * 4 + (c.gs >> 3)] = outv[it & 1];
-                if (lane == 0) {
-                    c.ws->l1p[0] = newp;
-                    c.ws->l1p[1] = 0;
-                }
-                __syncwarp();
-                n /= 8;
-                d -= 1;
+                continue;
             }
-            if (lane == 0) write_root<T>(c, a, chunk, c.ws->l1[0], (c.ws->l1p[0] & 1) != 0);
-            __syncwarp();
+            bool has_fill, has_patches;
+            u32 fill;
+            chunk_flags<T>(a, chunk, &has_fill, &fill, &has_patches);
+            // phase 0 once per chunk (unit 0 takes the reference); every unit needs the fill leaf's id
+            u64 fl = phase0_fill<T>(c, has_fill, fill, has_patches && unit == 0);
+            if (!has_patches) {  // :756-758 — the tree becomes Leaf(fill), or nothing happens
+                if (lane == 0 && unit == 0) {
+                    if (has_fill) c.t.leaf_calls++;
+                    write_root<T>(c, a, chunk, fl, has_fill);
+                }
+                continue;
+            }
+            Under u{0, fl, fill, D};
+            // with a fill the batch is built against Leaf(fill); the old tree is only released (:742-754)
+            const bool use_old = OLD && !has_fill && a.old_roots && a.old_roots[chunk] != 0;
+            if (use_old) u.old_root = a.old_roots[chunk];
+            const void* cv = (const u8*)a.values + size_t(chunk) * a.blocks * 8 * sizeof(T);
+
+            // ---- stage 0: the unit.  stage 1: its 32^3 cube.  stage 2: the chunk's top levels.
+            bool some;
+            if (use_old)
+                some = build_blocks<T, OLD>(c, mlo, mhi, cv, unit * UNIT_BLOCKS, nblocks, u);
+            else
+                some = build_blocks<T, false>(c, mlo, mhi, cv, unit * UNIT_BLOCKS, nblocks, u);
+            u32 rn = u32(nblocks) / 8, rpos = (unit * UNIT_BLOCKS) >> 3;
+            int rd = D - 2;
+            for (int stage = 0;; ++stage) {
+                u64 node = u.fill_leaf;
+                bool present = false;
+                if (some) node = reduce_levels<T>(c, rn, rd, rpos, u, use_old, &present);
+                if (stage == 0) {
+                    if (upc == 1) {  // D <= 4: the unit is the tree
+                        if (lane == 0) write_root<T>(c, a, chunk, node, present);
+                        break;
+                    }
+                    const u32 cube = unit >> 3;
+                    if (R == 8) {  // this warp owns the whole cube: keep the unit nodes in shared memory
+                        if (lane == 0) {
+                            c.ws->run_ids[unit & 7] = node;
+                            c.ws->run_pres[unit & 7] = present;
+                        }
+                        __syncwarp();
+                        if ((unit & 7) != 7) break;
+                        if (lane < 8) {
+                            c.ws->l1[lane] = c.ws->run_ids[lane];
+                            c.ws->p1[lane] = c.ws->run_pres[lane];
+                        }
+                    } else {  // publish the unit; the last arriver of the cube joins it
+                        u32 arrived = 0;
+                        if (lane == 0) {
+                            st_strong(&a.unit_ids[w], node);
+                            ((volatile u8*)a.unit_present)[w] = present;
+                            fence_gpu();
+                            arrived = atomicAdd(&a.cube_done[size_t(chunk) * cpc + cube], 1u);
+                        }
+                        arrived = __shfl_sync(FULL, arrived, 0);
+                        if (arrived != 7) break;
+                        fence_gpu();
+                        const size_t base = (size_t(chunk) * cpc + cube) * 8;
+                        if (lane < 8) {
+                            c.ws->l1[lane] = ld_strong(&a.unit_ids[base + lane]);
+                            c.ws->p1[lane] = ((volatile u8*)a.unit_present)[base + lane];
+                        }
+                    }
+                    __syncwarp();
+                    some = true;  // eight 16^3 units (depth D-4) -> the cube's node (depth D-5)
+                    rn = 8;
+                    rd = D - 4;
+                    rpos = cube * 8;
+                } else if (stage == 1) {
+                    if (cpc == 1) {
+                        if (lane == 0) write_root<T>(c, a, chunk, node, present);
+                        break;
+                    }
+                    // D >= 6: publish the cube; the last cube of the chunk joins the top levels
+                    const u32 cube = unit >> 3;
+                    u32 arrived = 0;
+                    if (lane == 0) {
+                        st_strong(&a.cube_ids[size_t(chunk) * cpc + cube], node);
+                        ((volatile u8*)a.cube_present)[size_t(chunk) * cpc + cube] = present;
+                        fence_gpu();
+                        arrived = atomicAdd(&a.chunk_done[chunk], 1u);
+                    }
+                    arrived = __shfl_sync(FULL, arrived, 0);
+                    if (arrived != cpc - 1) break;
+                    fence_gpu();
+                    for (u32 i = lane; i < cpc; i += 32) {
+                        c.ws->l1[i] = ld_strong(&a.cube_ids[size_t(chunk) * cpc + i]);
+                        c.ws->p1[i] = ((volatile u8*)a.cube_present)[size_t(chunk) * cpc + i];
+                    }
+                    __syncwarp();
+                    some = true;  // cube nodes (depth D-5) -> root
+                    rn = cpc;
+                    rd = D - 5;
+                    rpos = 0;
+                } else {
+                    if (lane == 0) write_root<T>(c, a, chunk, node, present);
+                    break;
+                }
+            }
         }
+        run = next_run;
+        next_run = run < total_runs ? grab() : total_runs;
     }
     cta_finish<T>(c);
 }

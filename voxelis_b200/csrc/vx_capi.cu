@@ -181,10 +181,23 @@ int launch_apply_t(vx_interner* it, int depth, size_t n, const u8* d_masks, cons
     a.depth = u32(depth);
     a.blocks = u32(blocks_for_depth(depth));
     a.use_free = it->free_host > 0 ? 1u : 0u;
-    // join scratch for D >= 5 (see apply_kernel): ids/present flags per unit and per cube + arrival counters
+    // join scratch (see apply_kernel): arrival counters + dynamic work counter, ids/present flags per
+    // unit and per cube
     const size_t upc = a.blocks > UNIT_BLOCKS ? a.blocks / UNIT_BLOCKS : 1, cpc = upc / 8;
-    if (upc > 1) {
-        const size_t counters = (n * cpc + n) * 4;
+    int occ = 0;
+    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, apply_kernel<T, OLD>, CTA_THREADS, 0));
+    const size_t max_ctas = size_t(std::max(occ, 1)) * it->sm_count, max_warps = max_ctas * WARPS_PER_CTA;
+    // a warp takes a whole 32^3 cube when there are plenty of cubes; otherwise single units, so that a
+    // one-chunk apply still spreads over 8 (D=5) .. 512 (D=7) warps
+    a.run = (upc >= 8 && n * cpc >= 4 * max_warps) ? 8u : 1u;
+    if (const char* fr = getenv("VX_FORCE_RUN")) {  // tests: exercise both join paths at any size
+        if (upc >= 8 && fr[0] == '8') a.run = 8;
+        if (fr[0] == '1') a.run = 1;
+    }
+    const size_t total_runs = (n * upc + a.run - 1) / a.run;
+    if (total_runs >= 0xFFFFFFF0ull) return fail(VX_E_INVALID, "too many chunks in one call");
+    {
+        const size_t counters = (n * cpc + n + 4) * 4;
         const size_t need = counters + n * upc * 8 + n * cpc * 8 + n * upc + n * cpc + 64;
         if (need > it->join_bytes) {
             CU_TRY(cudaStreamSynchronize(s));
@@ -197,6 +210,7 @@ int launch_apply_t(vx_interner* it, int depth, size_t n, const u8* d_masks, cons
         u8* p = (u8*)it->join;
         a.cube_done = (u32*)p;
         a.chunk_done = a.cube_done + n * cpc;
+        a.work_next = a.chunk_done + n;
         p += (counters + 15) / 16 * 16;
         a.unit_ids = (u64*)p;
         p += n * upc * 8;
@@ -207,10 +221,8 @@ int launch_apply_t(vx_interner* it, int depth, size_t n, const u8* d_masks, cons
         a.cube_present = p;
         CU_TRY(cudaMemsetAsync(it->join, 0, counters, s));
     }
-    int occ = 0;
-    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, apply_kernel<T, OLD>, CTA_THREADS, 0));
-    const size_t ctas = (n * upc + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-    const size_t grid = std::min<size_t>(ctas, size_t(std::max(occ, 1)) * it->sm_count);
+    const size_t ctas = (total_runs + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    const size_t grid = std::min<size_t>(ctas, max_ctas);
     apply_kernel<T, OLD><<<unsigned(grid), CTA_THREADS, 0, s>>>(a);
     CU_TRY(cudaGetLastError());
     if (a.use_free) {
