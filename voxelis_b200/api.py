@@ -59,11 +59,12 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(_LIB_PATH):
+    path = os.environ.get("VX_LIB", _LIB_PATH)      # VX_LIB: try an experimental build of the same ABI
+    if not os.path.exists(path):
         raise ImportError(
-            f"{_LIB_PATH} is missing: build it with `python -m voxelis_b200.build` "
+            f"{path} is missing: build it with `python -m voxelis_b200.build` "
             "(nvcc, sm_100a). voxelis_b200 has no CPU fallback.")
-    L = C.CDLL(_LIB_PATH)
+    L = C.CDLL(path)
     vp, sz, i64, u64 = C.c_void_p, C.c_size_t, C.c_int64, C.c_uint64
     L.vx_last_error.restype = C.c_char_p
     L.vx_interner_create.restype = vp

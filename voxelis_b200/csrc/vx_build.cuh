@@ -72,6 +72,7 @@ struct VT<u8> {
     static __device__ __forceinline__ Key zero() { return Key{{0}}; }
     static __device__ __forceinline__ u32 nz(const Key& k) { return nzbytes(k.w[0]); }
     static __device__ __forceinline__ u32 first(const Key& k) { return u32(k.w[0] & 0xFF); }
+    static __device__ __forceinline__ u32 get(const Key& k, int i) { return u32(k.w[0] >> (8 * i)) & 0xFF; }
     static __device__ __forceinline__ bool uniform(const Key& k) {
         return k.w[0] == (k.w[0] & 0xFF) * 0x0101010101010101ull;
     }
@@ -97,7 +98,9 @@ struct VT<u8> {
         return Key{{w}};
     }
     static __device__ __forceinline__ bool eq(const Key& a, const Key& b) { return a.w[0] == b.w[0]; }
-    static __device__ __forceinline__ u32 hash(const Key& k) { return u32(mix64(k.w[0]) >> 32); }
+    static __device__ __forceinline__ u32 hash(const Key& k) {  // index of the per-warp block cache
+        return ((u32(k.w[0]) * 0x9E3779B1u) ^ (u32(k.w[0] >> 32) * 0x85EBCA77u)) >> 20;
+    }
     // value of child `li` of the key held by lane `src` (full-warp shuffle)
     static __device__ __forceinline__ u32 bcast_value(const Key& k, int src, int li) {
         u64 w = __shfl_sync(FULL, k.w[0], src);
@@ -378,12 +381,19 @@ __device__ __forceinline__ u32 child_value<int32_t>(const InternerDev& in, u64 c
 }
 
 // ------------------------------------------------------------------------------------------------
-// Branches — get_or_create_branch (interner/mod.rs:716-829) for up to four keys per warp, one per
-// 8-lane group, child i of the key in lane gs+i.  Returns the branch id to every lane of a group
-// with need == true.  `cval` = value of the lane's child when BLOCK_LEVEL (children are voxels).
+// Branches — get_or_create_branch (interner/mod.rs:716-829), upper levels: up to four keys per warp,
+// one per 8-lane group, child i of the key in lane gs+i.  Returns the branch id to every lane of a
+// group with need == true.
 // ------------------------------------------------------------------------------------------------
-template <class T, bool BLOCK_LEVEL>
-__device__ inline u64 intern_branch(Ctx<T>& c, bool need, u64 child, u32 cval) {
+// `block_level`: the children are voxels (Leaf(cval) / EMPTY) — used for iterations where at most four
+// distinct block keys miss the per-warp cache; busier iterations go through intern_block below.
+template <class T>
+#ifdef VX_INTERN_NOINLINE
+__device__ __noinline__
+#else
+__device__ inline
+#endif
+u64 intern_branch(Ctx<T>& c, bool need, u64 child, bool block_level, u32 cval) {
     const int li = c.li, gs = c.gs, lane = c.lane;
     const InternerDev& in = c.in;
     if (!__any_sync(FULL, need)) return 0;
@@ -400,9 +410,9 @@ __device__ inline u64 intern_branch(Ctx<T>& c, bool need, u64 child, u32 cval) {
 
     u64 result = 0;
     bool done = !need;
-    // ---- per-warp parent cache (upper levels; the block level has its own value-keyed cache)
+    // ---- per-warp parent cache (the block level has its own value-keyed cache)
     const u32 ue = u32(h >> 32) & (UC - 1);
-    if (!BLOCK_LEVEL) {
+    if (!block_level) {
         u64 ck = c.ws->ukey[ue * 8 + li];
         u32 eqb = (__ballot_sync(FULL, need && ck == child) >> gs) & 0xFF;
         if (need && eqb == 0xFF) {
@@ -467,7 +477,7 @@ __device__ inline u64 intern_branch(Ctx<T>& c, bool need, u64 child, u32 cval) {
             // LOD value = mode of the child values (core/voxel.rs:96-141): most frequent; ties go to
             // a non-default value, then to the earliest first occurrence.
             u32 v = cval;
-            if (!BLOCK_LEVEL) v = (mine && !oom && child != 0) ? child_value<T>(in, child) : 0;
+            if (!block_level) v = (mine && !oom && child != 0) ? child_value<T>(in, child) : 0;
             u32 mm = __match_any_sync(FULL, (u64(v) << 2) | u64(gs >> 3));
             u32 gm = (mm >> gs) & 0xFF;
             u32 score = (u32(__popc(gm)) << 8) | (u32(v != 0) << 7) | (u32(8 - __ffs(gm)) << 3) | u32(li);
@@ -475,15 +485,14 @@ __device__ inline u64 intern_branch(Ctx<T>& c, bool need, u64 child, u32 cval) {
             best = max(best, __shfl_xor_sync(FULL, best, 1));
             best = max(best, __shfl_xor_sync(FULL, best, 2));
             best = max(best, __shfl_xor_sync(FULL, best, 4));
-            // the winning lane is the first occurrence of the mode value
-            u32 mode = __shfl_sync(FULL, v, gs + int(best & 7));
+            u32 mode = __shfl_sync(FULL, v, gs + int(best & 7));  // the winner is a first occurrence
             if (mine) {
                 if (oom) {
                     set_error(in, ERR_OOM);
                 } else {
                     in.children[size_t(idx) * 8 + li] = child;
                     if (child != 0) {
-                        if (BLOCK_LEVEL && sizeof(T) == 1)
+                        if (block_level && sizeof(T) == 1)
                             atomicAdd(&c.cs->leafref[cval], 1u);
                         else
                             atomicAdd(&in.refs[id_index(child)], 1u);
@@ -515,7 +524,7 @@ __device__ inline u64 intern_branch(Ctx<T>& c, bool need, u64 child, u32 cval) {
             }
         }
     }
-    if (!BLOCK_LEVEL) {
+    if (!block_level) {
         // refresh the parent cache; among groups mapping to the same entry only the lowest writes,
         // so an entry is never a mix of two keys
         bool wr = went_global && result != 0;
@@ -531,6 +540,196 @@ __device__ inline u64 intern_branch(Ctx<T>& c, bool need, u64 child, u32 cval) {
             if (li == 0) c.ws->uval[ue] = result;
         }
         __syncwarp();
+    }
+    return result;
+}
+
+// mode of eight values with the reference's tie-breaks (core/voxel.rs:96-141), one thread.  Only runs
+// when a new block-level branch is created; kept out of line to protect the instruction cache.
+__device__ __noinline__ u32 mode8(u32 v0, u32 v1, u32 v2, u32 v3, u32 v4, u32 v5, u32 v6, u32 v7) {
+    const u32 v[8] = {v0, v1, v2, v3, v4, v5, v6, v7};
+    u32 best = v[0], best_score = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        u32 cnt = 0;
+        bool first = true;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            cnt += v[j] == v[i];
+            if (j < i && v[j] == v[i]) first = false;
+        }
+        u32 score = (cnt << 1) | u32(v[i] != 0);  // count, then non-default; earlier first occurrence wins ties
+        if (first && score > best_score) {
+            best_score = score;
+            best = v[i];
+        }
+    }
+    return best;
+}
+
+// Ids of the eight voxel children (Leaf(value) / EMPTY) of a block key.  u8: re-derived on demand from
+// the CTA's value -> leaf table in shared memory (no registers held); wider T: held in registers.
+template <class T>
+struct ChildIds;
+template <>
+struct ChildIds<u8> {
+    const u64* leaf;
+    u64 w;
+    __device__ __forceinline__ void init(Ctx<u8>& c, const VT<u8>::Key& eff, bool need) {
+        leaf = c.cs->leaf;
+        w = eff.w[0];
+        bool missing = false;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            u32 v = u32(w >> (8 * i)) & 0xFF;
+            missing = missing || (need && v != 0 && leaf[v] == 0);
+        }
+        if (__any_sync(FULL, missing)) {  // rare: some leaf does not exist yet (get_or_create_leaf)
+#pragma unroll 1
+            for (int i = 0; i < 8; ++i) leaf_get(c, u32(w >> (8 * i)) & 0xFF, need);
+        }
+    }
+    __device__ __forceinline__ u64 get(int i) const {
+        u32 v = u32(w >> (8 * i)) & 0xFF;
+        return v ? leaf[v] : 0;
+    }
+};
+template <>
+struct ChildIds<int32_t> {
+    u64 id[8];
+    __device__ __forceinline__ void init(Ctx<int32_t>& c, const VT<int32_t>::Key& eff, bool need) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) id[i] = leaf_get(c, VT<int32_t>::get(eff, i), need);
+    }
+    __device__ __forceinline__ u64 get(int i) const { return id[i]; }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Branches at the BLOCK level (children are voxels): thread-per-key.  Every lane with need == true
+// owns one key (its block's eight effective values) and probes for it on its own: the 64-byte bucket
+// and the stored children row are read as 4 x 16-byte loads, so up to 32 lookups of a warp are in
+// flight at once (the 8-lane scheme above has 4).  Inserts of one warp step share a single
+// aggregated index allocation and a single fence.
+// ------------------------------------------------------------------------------------------------
+template <class T>
+__device__ inline u64 intern_block(Ctx<T>& c, bool need, const typename VT<T>::Key& eff) {
+    using V = VT<T>;
+    const InternerDev& in = c.in;
+    if (!__any_sync(FULL, need)) return 0;
+    ChildIds<T> ch;
+    ch.init(c, eff, need);
+    u64 h = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) h += child_hash(ch.get(i), i);
+    h = finish_hash(h);
+    const u32 nzm = V::nz(eff);  // types == mask == voxels present (voxtree.rs:846-863)
+    const u32 fp = u32(h >> 47);
+    u32 bucket = u32(h) & in.bucket_mask;
+    u64 result = 0;
+    bool done = !need;
+    u32 skip = 0;
+    int guard = 0;
+    while (__any_sync(FULL, !done)) {
+        bool claimed = false;
+        int ek = 0;
+        if (!done) {
+            const u64* bp = &in.slots[size_t(bucket) * 8];
+            c.t.probes++;
+            // the whole 64-byte bucket first (four independent 16-byte loads in flight), then the scan
+            u64 sl[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ld_strong_v2(bp + 2 * j, &sl[2 * j], &sl[2 * j + 1]);
+            u32 mb = 0, eb = 0, pb = 0;
+            u64 cand = 0;
+#pragma unroll
+            for (int k = 7; k >= 0; --k) {
+                const u64 sv = sl[k];
+                const u32 lo = u32(sv);
+                if (sv == 0)
+                    eb |= 1u << k;
+                else if (lo != IDX_TOMB && u32(sv >> 47) == fp && !((skip >> k) & 1)) {
+                    if (lo == IDX_PENDING)
+                        pb |= 1u << k;
+                    else {
+                        mb |= 1u << k;
+                        cand = sv;  // ends up as the lowest matching slot
+                    }
+                }
+            }
+            if (mb) {  // compare the stored children row with the key (row loaded in one go as well)
+                const u64* rp = &in.children[size_t(u32(cand)) * 8];
+                u64 r[8];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) ld_strong_v2(rp + 2 * j, &r[2 * j], &r[2 * j + 1]);
+                bool eq = true;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) eq = eq && r[i] == ch.get(i);
+                if (eq) {
+                    result = id_branch(cand, nzm, nzm);
+                    done = true;
+                } else {
+                    skip |= 1u << (__ffs(mb) - 1);
+                }
+            } else if (pb) {
+                // a slot with my fingerprint is being published (possibly my key): look again
+            } else if (eb) {
+                ek = __ffs(eb) - 1;
+                u64 old = atomicCAS((ull*)&in.slots[size_t(bucket) * 8 + ek], 0ull, (ull)((u64(fp) << 47) | IDX_PENDING));
+                claimed = old == 0;
+            } else {
+                bucket = (bucket + 1) & in.bucket_mask;
+                skip = 0;
+                if (++guard > (1 << 22)) {
+                    set_error(in, ERR_TABLE_FULL);
+                    done = true;
+                }
+            }
+        }
+        // ---- nodes created in this step: one index allocation, one fence, then publish (inside the
+        //      loop, so a lane waiting on a PENDING slot of its own warp always sees it resolve)
+        const u32 cb = __ballot_sync(FULL, claimed);
+        if (cb != 0) {
+            u32 idx = 0, gen = 0;
+            if (!c.use_free) {
+                u32 base = 0;
+                if (c.lane == 0) base = atomicAdd(in.next_index, u32(__popc(cb)));
+                base = __shfl_sync(FULL, base, 0);
+                idx = base + __popc(cb & ((1u << c.lane) - 1));
+            } else if (claimed) {
+                idx = alloc_one(in, true, &gen);
+            }
+            const u64 genidx = (u64(gen) << 32) | idx;
+            const bool oom = idx >= in.capacity;
+            if (claimed) {
+                if (oom) {
+                    set_error(in, ERR_OOM);
+                } else {
+                    u64* rp = &in.children[size_t(idx) * 8];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        *reinterpret_cast<ulonglong2*>(rp + 2 * j) = make_ulonglong2(ch.get(2 * j), ch.get(2 * j + 1));
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const u32 v = V::get(eff, i);
+                        if (v != 0) {
+                            if (sizeof(T) == 1)
+                                atomicAdd(&c.cs->leafref[v], 1u);
+                            else
+                                atomicAdd(&in.refs[id_index(ch.get(i))], 1u);
+                        }
+                    }
+                    ((T*)in.values)[idx] = T(mode8(V::get(eff, 0), V::get(eff, 1), V::get(eff, 2), V::get(eff, 3),
+                                                   V::get(eff, 4), V::get(eff, 5), V::get(eff, 6), V::get(eff, 7)));
+                    in.hashes[idx] = h;
+                    c.t.branch_miss++;
+                }
+                fence_gpu();
+                // out of memory: hand the slot back (the interner is poisoned, results are discarded)
+                st_strong(&in.slots[size_t(bucket) * 8 + ek], oom ? u64(0) : ((u64(fp) << 47) | genidx));
+                result = oom ? 0 : id_branch(genidx, nzm, nzm);
+                done = true;
+            }
+        }
     }
     return result;
 }
@@ -571,7 +770,7 @@ __device__ inline u64 parent_node(Ctx<T>& c, u64 child, bool present, u64 old_se
         else
             c.t.branch_calls++;
     }
-    u64 id = intern_branch<T, false>(c, any_present && !collapse, child, 0);
+    u64 id = intern_branch<T>(c, any_present && !collapse, child, false, 0);
     if (any_present && collapse) id = c0;
     if (!any_present) id = old_self;
     *ppresent = any_present;
@@ -622,58 +821,57 @@ __device__ inline u64 block_node(Ctx<T>& c, bool active, typename VT<T>::Key val
             }
         }
     }
-    u32 pmask = __ballot_sync(FULL, pend);
-    while (pmask != 0) {
-        // duplicate keys inside the warp: one representative per distinct value word
-        bool leader = false;
+    const u32 pmask = __ballot_sync(FULL, pend);
+    if (pmask != 0) {
+        // duplicate keys inside the warp: one representative (leader) per distinct value word
+        u32 mm = 0;
         if (pend) {
-            u32 mm = __match_any_sync(pmask, eff.w[0]);
+            mm = __match_any_sync(pmask, eff.w[0]);
             if (V::KW > 1) {
 #pragma unroll
                 for (int j = 1; j < V::KW; ++j) mm &= __match_any_sync(pmask, eff.w[j]);
             }
-            leader = (__ffs(mm) - 1) == lane;
         }
-        u32 lmask = __ballot_sync(FULL, leader);
-        // group g takes the g-th leader
-        int src = __fns(lmask, 0, (c.gs >> 3) + 1);
-        const bool gvalid = src >= 0 && src < 32;
-        if (!gvalid) src = 0;
-        typename V::Key gk = V::bcast(eff, src);
-        u32 cv;
-        if (V::KW == 1)
-            cv = u32(gk.w[0] >> (8 * c.li)) & 0xFF;
-        else {
-            u64 w = (c.li >> 1) == 0 ? gk.w[0] : (c.li >> 1) == 1 ? gk.w[1 % V::KW] : (c.li >> 1) == 2 ? gk.w[2 % V::KW] : gk.w[3 % V::KW];
-            cv = u32(w >> (32 * (c.li & 1)));
+        const int leader_lane = pend ? (__ffs(mm) - 1) : 0;
+        const bool leader = pend && leader_lane == lane;
+        const u32 lmask = __ballot_sync(FULL, leader);
+        u64 bid;
+        if (__popc(lmask) > 4) {
+            bid = intern_block<T>(c, leader, eff);  // many distinct misses: every leader probes on its own
+        } else {
+            // a few misses: one 8-lane group per key (group g takes the g-th leader)
+            int src = __fns(lmask, 0, (c.gs >> 3) + 1);
+            const bool gvalid = src >= 0 && src < 32;
+            if (!gvalid) src = 0;
+            typename V::Key gk = V::bcast(eff, src);
+            const u32 cv = gvalid ? V::get(gk, c.li) : 0;
+            u64 child = leaf_get(c, cv, gvalid);
+            u64 gid = intern_branch<T>(c, gvalid, child, true, cv);
+            // hand the id to the leader lane it belongs to
+            bid = 0;
+#pragma unroll
+            for (int g2 = 0; g2 < 4; ++g2) {
+                int s2 = __shfl_sync(FULL, src, g2 * 8);
+                u64 id2 = __shfl_sync(FULL, gid, g2 * 8);
+                bool v2 = __shfl_sync(FULL, int(gvalid), g2 * 8) != 0;
+                if (v2 && lane == s2) bid = id2;
+            }
         }
-        u64 child = leaf_get(c, cv, gvalid);
-        u64 bid = intern_branch<T, true>(c, gvalid, child, gvalid ? cv : 0);
-        // cache refresh: one writer per entry
-        u32 ge = V::hash(gk) & (V::BC - 1);
-        bool wr = gvalid && bid != 0 && c.li == 0;
-        u32 wb = __ballot_sync(FULL, wr);
+        // cache refresh: one writer per entry, so key and id of an entry always belong together
+        const bool wr = leader && bid != 0;
+        const u32 wb = __ballot_sync(FULL, wr);
         if (wr) {
-            u32 sm = __match_any_sync(wb, ge);
+            u32 sm = __match_any_sync(wb, e);
             if ((__ffs(sm) - 1) == lane) {
 #pragma unroll
-                for (int j = 0; j < V::KW; ++j) c.ws->bkey[ge * V::KW + j] = gk.w[j];
-                c.ws->bval[ge] = bid;
+                for (int j = 0; j < V::KW; ++j) c.ws->bkey[e * V::KW + j] = eff.w[j];
+                c.ws->bval[e] = bid;
             }
         }
-        // hand the ids back to every pending lane with the same key
-#pragma unroll
-        for (int g2 = 0; g2 < 4; ++g2) {
-            typename V::Key k2 = V::bcast(gk, g2 * 8);
-            u64 id2 = __shfl_sync(FULL, bid, g2 * 8);
-            bool v2 = __shfl_sync(FULL, int(gvalid), g2 * 8) != 0;
-            if (pend && v2 && V::eq(k2, eff)) {
-                id = id2;
-                pend = false;
-            }
-        }
+        // every pending lane takes its leader's id
+        u64 lid2 = __shfl_sync(FULL, bid, leader_lane);
+        if (pend) id = lid2;
         __syncwarp();
-        pmask = __ballot_sync(FULL, pend);
     }
     return id;
 }
@@ -981,8 +1179,11 @@ __device__ __forceinline__ void write_root(Ctx<T>& c, const ApplyArgs& a, u32 ch
 // The last cube of a chunk joins the top levels the same way (D = 6: 8 cubes, D = 7: 64).
 // No __syncthreads anywhere in the loop: warps never wait for each other.
 // ------------------------------------------------------------------------------------------------
+#ifndef VX_MIN_CTAS
+#define VX_MIN_CTAS 3
+#endif
 template <class T, bool OLD>
-__global__ void __launch_bounds__(CTA_THREADS, 3) apply_kernel(ApplyArgs a) {
+__global__ void __launch_bounds__(CTA_THREADS, VX_MIN_CTAS) apply_kernel(ApplyArgs a) {
     __shared__ WarpSmem<T> ws[WARPS_PER_CTA];
     __shared__ CtaSmem cs;
     smem_init<T>(ws, &cs);

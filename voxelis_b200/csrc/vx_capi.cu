@@ -821,25 +821,27 @@ static int apply_slab_impl(vx_interner* it, uint8_t depth, size_t n, const uint8
             k_fills = d_fills;
         }
     }
-    // Pinned (page-locked, mapped) host batches are read by the kernel itself over PCIe ("zero copy"):
-    // the kernel loads every mask once but VALUES only for blocks that have a set bit, so a sparse
-    // batch moves a fraction of its bytes across the bus and nothing is staged through HBM.
-    // VX_HOST_MODE=staged forces the double-buffered copy path (the only one for pageable memory).
+    // Host batches.  Masks are always streamed H2D by the copy engine into one of two staging slabs while
+    // the previous slab is being built.  VALUES of pinned (page-locked, mapped) batches are NOT copied:
+    // the kernel reads them in place over PCIe ("zero copy") and only for blocks that have a set bit, so
+    // a sparse batch moves a fraction of its bytes across the bus and its values never touch HBM.
+    //   VX_HOST_MODE=staged    copy masks and values (the only mode for pageable memory)
+    //   VX_HOST_MODE=zerocopy  the kernel reads masks and values in place
     const void* zm = dev_in ? nullptr : host_device_alias(masks);
     const void* zv = dev_in ? nullptr : host_device_alias(values);
     const char* mode = getenv("VX_HOST_MODE");
-    const bool zero_copy = zm && zv && !(mode && strcmp(mode, "staged") == 0);
+    const bool pinned = zm && zv;
+    const bool all_zero_copy = pinned && mode && strcmp(mode, "zerocopy") == 0;
+    const bool copy_values = !pinned || (mode && strcmp(mode, "staged") == 0);
     if (dev_in) {
         rc = launch_apply(it, depth, n, masks, values, k_flags, k_fills, d_roots, d_changed, s, k_old);
         if (rc != VX_OK) return rc;
-    } else if (zero_copy) {
+    } else if (all_zero_copy) {
         rc = launch_apply(it, depth, n, (const u8*)zm, zv, k_flags, k_fills, d_roots, d_changed, s, k_old);
         if (rc != VX_OK) return rc;
     } else {
-        // host batches: H2D on the copy stream into one of two staging slabs while the previous slab
-        // is being built on the compute stream
-        size_t per = mbytes + vbytes;
-        size_t slab = std::max<size_t>(1, std::min<size_t>(n, (size_t(96) << 20) / per));
+        size_t per = mbytes + (copy_values ? vbytes : 0);
+        size_t slab = std::max<size_t>(1, std::min<size_t>(n, (size_t(copy_values ? 96 : 32) << 20) / per));
         if (slab * per > it->stage_bytes) {
             for (int i = 0; i < 2; ++i) {
                 cudaFree(it->stage[i]);
@@ -856,11 +858,15 @@ static int apply_slab_impl(vx_interner* it, uint8_t depth, size_t n, const uint8
             size_t cnt = std::min(slab, n - lo);
             int b = int(k & 1);
             u8* sm = (u8*)it->stage[b];
-            u8* sv = sm + slab * mbytes;
+            const void* sv = (const u8*)zv + lo * vbytes;
             CU_TRY(cudaStreamWaitEvent(it->copy_stream, it->ev_done[b], 0));
             CU_TRY(cudaMemcpyAsync(sm, masks + lo * mbytes, cnt * mbytes, cudaMemcpyHostToDevice, it->copy_stream));
-            CU_TRY(cudaMemcpyAsync(sv, (const u8*)values + lo * vbytes, cnt * vbytes, cudaMemcpyHostToDevice,
-                                   it->copy_stream));
+            if (copy_values) {
+                u8* dv = sm + slab * mbytes;
+                CU_TRY(cudaMemcpyAsync(dv, (const u8*)values + lo * vbytes, cnt * vbytes, cudaMemcpyHostToDevice,
+                                       it->copy_stream));
+                sv = dv;
+            }
             CU_TRY(cudaEventRecord(it->ev_copied[b], it->copy_stream));
             CU_TRY(cudaStreamWaitEvent(s, it->ev_copied[b], 0));
             rc = launch_apply(it, depth, cnt, sm, sv, k_flags ? k_flags + lo : nullptr, k_fills ? k_fills + lo : nullptr,

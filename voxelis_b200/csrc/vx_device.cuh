@@ -104,6 +104,10 @@ __device__ __forceinline__ u32 ld_strong_u16(const u16* p) {
                  : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+// 16-byte strong load (two u64): L2-coherent like the scalar forms
+__device__ __forceinline__ void ld_strong_v2(const u64* p, u64* a, u64* b) {
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(*a), "=l"(*b) : "l"(p) : "memory");
+}
 __device__ __forceinline__ void st_strong(u64* p, u64 v) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -143,13 +147,28 @@ __host__ __device__ inline u64 mix64(u64 x) {
     x ^= x >> 33;
     return x;
 }
-// contribution of child `i` to the branch hash; the 8 contributions are summed.
-__host__ __device__ inline u64 child_hash(u64 child, int i) {
-    return mix64(child + 0x9E3779B97F4A7C15ull * u64(i + 1));
+// Branch hash = finish( sum_i child_i * HC_i ): a multilinear hash with one odd 64-bit multiplier per
+// child position — one multiply per child instead of a full avalanche, the sum is order-sensitive
+// through the multipliers, and the final mix spreads the entropy into the bucket (low) and the
+// fingerprint (high) bits.  Both probing schemes (8-lane group, thread-per-key) use this formula.
+#define VX_HC0 0x9E3779B97F4A7C15ull
+#define VX_HC1 0xBF58476D1CE4E5B9ull
+#define VX_HC2 0x94D049BB133111EBull
+#define VX_HC3 0xD6E8FEB86659FD93ull
+#define VX_HC4 0xC2B2AE3D27D4EB4Full
+#define VX_HC5 0x165667B19E3779F9ull
+#define VX_HC6 0x27D4EB2F165667C5ull
+#define VX_HC7 0xFF51AFD7ED558CCDull
+__host__ __device__ inline u64 child_mult(int i) {
+    return i == 0 ? VX_HC0 : i == 1 ? VX_HC1 : i == 2 ? VX_HC2 : i == 3 ? VX_HC3 : i == 4 ? VX_HC4
+         : i == 5 ? VX_HC5 : i == 6 ? VX_HC6 : VX_HC7;
 }
+__host__ __device__ inline u64 child_hash(u64 child, int i) { return child * child_mult(i); }
 __host__ __device__ inline u64 finish_hash(u64 h) {
-    h ^= h >> 29;
+    h ^= h >> 32;
     h *= 0xbf58476d1ce4e5b9ull;
+    h ^= h >> 29;
+    h *= 0x94d049bb133111ebull;
     h ^= h >> 32;
     return h;
 }
