@@ -1180,7 +1180,7 @@ __device__ __forceinline__ void write_root(Ctx<T>& c, const ApplyArgs& a, u32 ch
 // No __syncthreads anywhere in the loop: warps never wait for each other.
 // ------------------------------------------------------------------------------------------------
 #ifndef VX_MIN_CTAS
-#define VX_MIN_CTAS 3
+#define VX_MIN_CTAS 4
 #endif
 template <class T, bool OLD>
 __global__ void __launch_bounds__(CTA_THREADS, VX_MIN_CTAS) apply_kernel(ApplyArgs a) {
@@ -1192,6 +1192,7 @@ __global__ void __launch_bounds__(CTA_THREADS, VX_MIN_CTAS) apply_kernel(ApplyAr
     const int lane = c.lane;
     const int D = int(a.depth);
     const u32 upc = a.blocks > UNIT_BLOCKS ? a.blocks / UNIT_BLOCKS : 1;  // units per chunk: 1, 8, 64, 512
+    const int upc_log = 31 - __clz(upc);
     const int nblocks = a.blocks > UNIT_BLOCKS ? UNIT_BLOCKS : int(a.blocks);
     const u32 cpc = upc / 8;                                             // 32^3 cubes per chunk: 0, 1, 8, 64
     const u32 R = a.run;
@@ -1204,7 +1205,8 @@ __global__ void __launch_bounds__(CTA_THREADS, VX_MIN_CTAS) apply_kernel(ApplyAr
         return __shfl_sync(FULL, r, 0);
     };
     auto masks_of = [&](unsigned long long w, u64* lo, u64* hi) {
-        load_unit_masks(a.masks + size_t(w / upc) * a.blocks * 2, size_t(w % upc) * UNIT_BLOCKS, nblocks, lane, lo, hi);
+        load_unit_masks(a.masks + size_t(w >> upc_log) * a.blocks * 2, size_t(w & (upc - 1)) * UNIT_BLOCKS, nblocks, lane, lo,
+                        hi);
     };
 
     unsigned long long run = grab();
@@ -1212,17 +1214,18 @@ __global__ void __launch_bounds__(CTA_THREADS, VX_MIN_CTAS) apply_kernel(ApplyAr
     u64 nlo = 0, nhi = 0;
     if (run < total_runs) masks_of(run * R, &nlo, &nhi);
     while (run < total_runs) {
+        const bool poisoned = __any_sync(FULL, lane == 0 && ld_strong(a.in.error) != ERR_NONE);
         for (u32 k = 0; k < R; ++k) {
             const unsigned long long w = run * R + k;
             if (w >= total_units) break;
-            const u32 chunk = u32(w / upc), unit = u32(w % upc);
+            const u32 chunk = u32(w >> upc_log), unit = u32(w) & (upc - 1);
             const u64 mlo = nlo, mhi = nhi;
             {  // request the masks of the unit after this one before doing any work
                 unsigned long long w2 = (k + 1 < R) ? w + 1 : next_run * R;
                 if (k + 1 < R ? (w2 < total_units) : (next_run < total_runs)) masks_of(w2, &nlo, &nhi);
             }
-            // poisoned interner: skip the rest, the host reports the error (warp-uniform decision)
-            if (__any_sync(FULL, lane == 0 && ld_strong(a.in.error) != ERR_NONE)) {
+            // poisoned interner: skip the rest, the host reports the error (warp-uniform, checked per run)
+            if (poisoned) {
                 if (lane == 0 && unit == 0) {
                     a.roots[chunk] = 0;
                     if (a.changed) a.changed[chunk] = 0;
