@@ -36,7 +36,13 @@ namespace vx {
 constexpr int WARPS_PER_CTA = 8;
 constexpr int CTA_THREADS = WARPS_PER_CTA * 32;
 constexpr int UNIT_BLOCKS = 512;  // blocks per warp work unit
-constexpr int UC = 32;            // per-warp parent-cache entries (children[8] -> id)
+#ifndef VX_UC
+#define VX_UC 32
+#endif
+#ifndef VX_BC_U8
+#define VX_BC_U8 256
+#endif
+constexpr int UC = VX_UC;         // per-warp parent-cache entries (children[8] -> id)
 
 #define VX_FLAG_FILL 1u
 #define VX_FLAG_PATCHES 2u
@@ -60,7 +66,7 @@ __device__ __forceinline__ u64 expand_bits(u32 m) {  // bit i -> byte i = 0xFF
 template <>
 struct VT<u8> {
     static constexpr int KW = 1;
-    static constexpr int BC = 128;  // per-warp block-cache entries
+    static constexpr int BC = VX_BC_U8;  // per-warp block-cache entries
     struct Key {
         u64 w[1];
     };
@@ -1180,15 +1186,20 @@ __device__ __forceinline__ void write_root(Ctx<T>& c, const ApplyArgs& a, u32 ch
 // No __syncthreads anywhere in the loop: warps never wait for each other.
 // ------------------------------------------------------------------------------------------------
 #ifndef VX_MIN_CTAS
-#define VX_MIN_CTAS 4
+#define VX_MIN_CTAS 3
 #endif
+template <class T>
+constexpr size_t apply_smem_bytes() {
+    return sizeof(WarpSmem<T>) * WARPS_PER_CTA + sizeof(CtaSmem);
+}
 template <class T, bool OLD>
 __global__ void __launch_bounds__(CTA_THREADS, VX_MIN_CTAS) apply_kernel(ApplyArgs a) {
-    __shared__ WarpSmem<T> ws[WARPS_PER_CTA];
-    __shared__ CtaSmem cs;
-    smem_init<T>(ws, &cs);
+    extern __shared__ __align__(16) unsigned char smem_raw[];  // may exceed 48 KiB: dynamic (apply_smem_bytes)
+    WarpSmem<T>* ws = reinterpret_cast<WarpSmem<T>*>(smem_raw);
+    CtaSmem* csp = reinterpret_cast<CtaSmem*>(smem_raw + sizeof(WarpSmem<T>) * WARPS_PER_CTA);
+    smem_init<T>(ws, csp);
     Ctx<T> c;
-    ctx_init<T>(c, a.in, ws, &cs, a.use_free != 0);
+    ctx_init<T>(c, a.in, ws, csp, a.use_free != 0);
     const int lane = c.lane;
     const int D = int(a.depth);
     const u32 upc = a.blocks > UNIT_BLOCKS ? a.blocks / UNIT_BLOCKS : 1;  // units per chunk: 1, 8, 64, 512

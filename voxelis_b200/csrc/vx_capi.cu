@@ -185,7 +185,9 @@ int launch_apply_t(vx_interner* it, int depth, size_t n, const u8* d_masks, cons
     // unit and per cube
     const size_t upc = a.blocks > UNIT_BLOCKS ? a.blocks / UNIT_BLOCKS : 1, cpc = upc / 8;
     int occ = 0;
-    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, apply_kernel<T, OLD>, CTA_THREADS, 0));
+    const size_t smem = apply_smem_bytes<T>();
+    CU_TRY(cudaFuncSetAttribute(apply_kernel<T, OLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, apply_kernel<T, OLD>, CTA_THREADS, smem));
     const size_t max_ctas = size_t(std::max(occ, 1)) * it->sm_count, max_warps = max_ctas * WARPS_PER_CTA;
     // a warp takes a whole 32^3 cube when there are plenty of cubes; otherwise single units, so that a
     // one-chunk apply still spreads over 8 (D=5) .. 512 (D=7) warps
@@ -223,7 +225,7 @@ int launch_apply_t(vx_interner* it, int depth, size_t n, const u8* d_masks, cons
     }
     const size_t ctas = (total_runs + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     const size_t grid = std::min<size_t>(ctas, max_ctas);
-    apply_kernel<T, OLD><<<unsigned(grid), CTA_THREADS, 0, s>>>(a);
+    apply_kernel<T, OLD><<<unsigned(grid), CTA_THREADS, smem, s>>>(a);
     CU_TRY(cudaGetLastError());
     if (a.use_free) {
         clamp_free_count_kernel<<<1, 1, 0, s>>>(it->dev);
