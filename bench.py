@@ -271,11 +271,16 @@ def main():
 
     # ---------------------------------------------------------------- roofline of the apply kernel
     peak, peak_src = peaks()
+    # SURVEY §8(d) / BASELINE.md §3: masks + values read once + root written + 87 B per NEW node
     algo_bytes = n * CHUNK_BYTES + new_nodes * NODE_BYTES
     achieved = algo_bytes / (kern_ms * 1e-3) / 1e9
+    # compulsory bytes for THIS input: values of blocks whose set_mask is 0 are never needed (phase 1
+    # skips them, voxtree.rs:779-781) and the kernel does not load them
+    touched_blocks = int(np.count_nonzero(masks[:, :, 0]))
+    compulsory = n * (2 * 4096 + 8) + touched_blocks * 8 + new_nodes * NODE_BYTES
     traffic = None
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp) and args.workload == "perlin":
         traffic = json.load(open(tp)).get("perlin_dunes_surface_only", {}).get("dram_bytes_per_launch")
 
     # ---------------------------------------------------------------- secondary workloads (rank 0)
@@ -339,11 +344,22 @@ def main():
                        "step": "vx_interner_reset + one vx_apply_batches_device launch",
                        "per_step_counters": dbg},
             "e2e": {"value": e2e_value, "unit": "chunks/s", "ms_per_step": e2e_ms_max,
-                    "h2d_bytes_per_step": int(masks.nbytes + values.nbytes), "d2h_bytes_per_step": int(n * 9)},
+                    # masks are DMA-copied; values stay in pinned host memory and the kernel reads, over PCIe,
+                    # only those of blocks with a set bit (lower bound: 8 B each, fetched as 32 B sectors)
+                    "h2d_bytes_per_step": int(masks.nbytes + touched_blocks * 8),
+                    "host_input_bytes_per_step": int(masks.nbytes + values.nbytes),
+                    "d2h_bytes_per_step": int(n * 9),
+                    "path": "vx_apply_batches_slab on pinned host batches (masks H2D by copy engine in slabs, "
+                            "values zero-copy), roots + changed flags D2H"},
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "apply_kernel<u8,false>",
-                         "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": algo_bytes},
+                         "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": algo_bytes,
+                         "compulsory_bytes_per_launch": compulsory,
+                         "achieved_compulsory": compulsory / (kern_ms * 1e-3) / 1e9,
+                         "note": "achieved uses the dense SURVEY 8(d) formula; the input is sparse "
+                                 f"({touched_blocks} of {n * 4096} blocks have a set bit) and the kernel skips the "
+                                 "values of untouched blocks, so DRAM traffic is below the formula"},
             "clocks": clocks,
         }
         if cpu is not None:
