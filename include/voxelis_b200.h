@@ -187,6 +187,26 @@ int vx_roots_to_vec(const vx_interner*, uint8_t max_depth, size_t n, const vx_bl
 int vx_tree_fill(vx_interner*, vx_tree*, int64_t value);
 int vx_tree_clear(vx_interner*, vx_tree*);
 
+/* ---------------------------------------------------------------- global dedup (new) ------ */
+/* Optional merge of per-GPU interners into hash-partitioned global shards (the Voxelis Bible's
+ * "shard the pattern map by hash % N", §3.9/§13).  Height-synchronous rounds: pack the local
+ * nodes of one height by owner = hash(children as global ids) mod G, exchange (NCCL all-to-all, done
+ * by the caller), intern on the owner, send the global ids back.  global id = the owner shard's BlockId
+ * with the owner's rank in generation bits [44..46].  All pointers are DEVICE memory; calls synchronise.
+ *   vx_dedup_heights            d_heights[next_index]: 0 leaf, h>=1 branch, 255 unused; returns max height
+ *   vx_dedup_pack               counts_out[G] (host); with d_records != NULL also writes the 72-byte records
+ *                               (8 global child ids + value) grouped by owner and d_src[j] = local node index
+ *   vx_dedup_scatter            d_gmap[d_src[j]] = d_ids[j]
+ *   vx_dedup_map_roots          d_out[j] = d_gmap[index(d_roots[j])]
+ *   vx_interner_intern_records  owner side: get_or_create for n records; *created_out = new nodes */
+int vx_dedup_heights(vx_interner*, uint8_t* d_heights);
+int vx_dedup_pack(vx_interner*, int height, const uint8_t* d_heights, const uint64_t* d_gmap, int G,
+                  uint64_t* counts_out, uint64_t* d_records, uint32_t* d_src);
+int vx_dedup_scatter(vx_interner*, size_t n, const uint32_t* d_src, const uint64_t* d_ids, uint64_t* d_gmap);
+int vx_dedup_map_roots(vx_interner*, size_t n, const uint64_t* d_roots, const uint64_t* d_gmap, uint64_t* d_out);
+int vx_interner_intern_records(vx_interner* shard, size_t n, const uint64_t* d_records, int rank, int leaf_round,
+                               uint64_t* d_ids_out, uint64_t* created_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -45,6 +45,7 @@ ABI_SYMBOLS = [
     "vx_tree_mark_dirty", "vx_tree_clear_dirty", "vx_tree_apply_batch", "vx_apply_batches",
     "vx_apply_batches_slab", "vx_apply_batches_device", "vx_tree_get", "vx_tree_get_many",
     "vx_tree_to_vec", "vx_roots_to_vec", "vx_tree_fill", "vx_tree_clear",
+    "vx_dedup_heights", "vx_dedup_pack", "vx_dedup_scatter", "vx_dedup_map_roots", "vx_interner_intern_records",
 ]
 
 
@@ -138,6 +139,11 @@ def lib():
     L.vx_roots_to_vec.argtypes = [vp, C.c_uint8, sz, vp, vp]
     L.vx_tree_fill.argtypes = [vp, vp, i64]
     L.vx_tree_clear.argtypes = [vp, vp]
+    L.vx_dedup_heights.argtypes = [vp, vp]
+    L.vx_dedup_pack.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp, vp, vp]
+    L.vx_dedup_scatter.argtypes = [vp, sz, vp, vp, vp]
+    L.vx_dedup_map_roots.argtypes = [vp, sz, vp, vp, vp]
+    L.vx_interner_intern_records.argtypes = [vp, sz, vp, C.c_int, C.c_int, vp, vp]
     _lib = L
     return L
 

@@ -18,6 +18,7 @@
 #include "vx_build.cuh"
 #include "vx_read.cuh"
 #include "vx_release.cuh"
+#include "vx_dedup.cuh"
 
 using namespace vx;
 
@@ -1135,6 +1136,133 @@ int vx_tree_fill(vx_interner* it, vx_tree* t, int64_t value) {
     if (rc != VX_OK) return rc;
     t->root = root;
     t->dirty = true;
+    return VX_OK;
+}
+
+// ------------------------------------------------------------------------------- global dedup
+// Synchronous helpers for the hash-partitioned merge of per-GPU interners; the all-to-all itself is done
+// by the caller (NCCL through torch.distributed, see voxelis_b200/dedup.py).  All pointers are device memory.
+int vx_dedup_heights(vx_interner* it, uint8_t* d_heights) {
+    if (!it || !d_heights) return fail(VX_E_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(it->mu);
+    DeviceGuard g(it->device);
+    Scalars sc{};
+    cudaStream_t s = it->stream;
+    CU_TRY(cudaMemcpyAsync(&sc, it->d_scalars, sizeof(sc), cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    const u32 n = std::min<u32>(sc.next_index, u32(it->capacity));
+    int rc = ensure_scratch(it, 64, 0);
+    if (rc != VX_OK) return rc;
+    u32* d_changed = (u32*)it->scratch;
+    const unsigned grid = (n + 255) / 256;
+    if (it->dtype == VX_U8)
+        heights_init_kernel<u8><<<grid, 256, 0, s>>>(it->dev, n, d_heights);
+    else
+        heights_init_kernel<int32_t><<<grid, 256, 0, s>>>(it->dev, n, d_heights);
+    CU_TRY(cudaGetLastError());
+    int sweeps = 0;
+    for (; sweeps < 64; ++sweeps) {
+        u32 changed = 0;
+        CU_TRY(cudaMemsetAsync(d_changed, 0, 4, s));
+        heights_sweep_kernel<<<grid, 256, 0, s>>>(it->dev, n, d_heights, d_changed);
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaMemcpyAsync(&changed, d_changed, 4, cudaMemcpyDeviceToHost, s));
+        CU_TRY(cudaStreamSynchronize(s));
+        if (!changed) break;
+    }
+    return sweeps;  // == height of the tallest node
+}
+
+int vx_dedup_pack(vx_interner* it, int height, const uint8_t* d_heights, const uint64_t* d_gmap, int G,
+                  uint64_t* counts_out, uint64_t* d_records, uint32_t* d_src) {
+    if (!it || !d_heights || !d_gmap || !counts_out || G < 1 || G > 8) return fail(VX_E_INVALID, "bad argument");
+    std::lock_guard<std::mutex> lk(it->mu);
+    DeviceGuard g(it->device);
+    Scalars sc{};
+    cudaStream_t s = it->stream;
+    CU_TRY(cudaMemcpyAsync(&sc, it->d_scalars, sizeof(sc), cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    const u32 n = std::min<u32>(sc.next_index, u32(it->capacity));
+    int rc = ensure_scratch(it, 256, 0);
+    if (rc != VX_OK) return rc;
+    u32* d_counts = (u32*)it->scratch;   // [8] counts, [8] bases, [8] cursors
+    u32* d_bases = d_counts + 8;
+    u32* d_cursors = d_counts + 16;
+    const unsigned grid = (n + 255) / 256;
+    CU_TRY(cudaMemsetAsync(d_counts, 0, 96, s));
+    if (it->dtype == VX_U8)
+        dedup_count_kernel<u8><<<grid, 256, 0, s>>>(it->dev, n, d_heights, u32(height), d_gmap, u32(G), d_counts);
+    else
+        dedup_count_kernel<int32_t><<<grid, 256, 0, s>>>(it->dev, n, d_heights, u32(height), d_gmap, u32(G), d_counts);
+    CU_TRY(cudaGetLastError());
+    u32 h_counts[8] = {0};
+    CU_TRY(cudaMemcpyAsync(h_counts, d_counts, 32, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    u32 h_bases[8] = {0};
+    for (int o = 0; o < G; ++o) {
+        counts_out[o] = h_counts[o];
+        if (o) h_bases[o] = h_bases[o - 1] + h_counts[o - 1];
+    }
+    if (!d_records) return VX_OK;  // counting call
+    if (!d_src) return fail(VX_E_INVALID, "null src");
+    CU_TRY(cudaMemcpyAsync(d_bases, h_bases, 32, cudaMemcpyHostToDevice, s));
+    if (it->dtype == VX_U8)
+        dedup_fill_kernel<u8><<<grid, 256, 0, s>>>(it->dev, n, d_heights, u32(height), d_gmap, u32(G), d_bases, d_cursors,
+                                                    d_records, d_src);
+    else
+        dedup_fill_kernel<int32_t><<<grid, 256, 0, s>>>(it->dev, n, d_heights, u32(height), d_gmap, u32(G), d_bases,
+                                                         d_cursors, d_records, d_src);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaStreamSynchronize(s));
+    return VX_OK;
+}
+
+int vx_dedup_scatter(vx_interner* it, size_t n, const uint32_t* d_src, const uint64_t* d_ids, uint64_t* d_gmap) {
+    if (!it || (n && (!d_src || !d_ids || !d_gmap))) return fail(VX_E_INVALID, "null argument");
+    if (n == 0) return VX_OK;
+    DeviceGuard g(it->device);
+    dedup_scatter_kernel<<<unsigned((n + 255) / 256), 256, 0, it->stream>>>(u32(n), d_src, d_ids, d_gmap);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaStreamSynchronize(it->stream));
+    return VX_OK;
+}
+
+int vx_dedup_map_roots(vx_interner* it, size_t n, const uint64_t* d_roots, const uint64_t* d_gmap, uint64_t* d_out) {
+    if (!it || (n && (!d_roots || !d_gmap || !d_out))) return fail(VX_E_INVALID, "null argument");
+    if (n == 0) return VX_OK;
+    DeviceGuard g(it->device);
+    dedup_map_roots_kernel<<<unsigned((n + 255) / 256), 256, 0, it->stream>>>(u32(n), d_roots, d_gmap, d_out);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaStreamSynchronize(it->stream));
+    return VX_OK;
+}
+
+int vx_interner_intern_records(vx_interner* shard, size_t n, const uint64_t* d_records, int rank, int leaf_round,
+                               uint64_t* d_ids_out, uint64_t* created_out) {
+    if (!shard || (n && (!d_records || !d_ids_out))) return fail(VX_E_INVALID, "null argument");
+    if (shard->poisoned) return fail(VX_E_POISONED, "interner overflowed earlier; reset it");
+    if (created_out) *created_out = 0;
+    if (n == 0) return VX_OK;
+    std::lock_guard<std::mutex> lk(shard->mu);
+    DeviceGuard g(shard->device);
+    int rc = ensure_scratch(shard, 64, 0);
+    if (rc != VX_OK) return rc;
+    u32* d_created = (u32*)shard->scratch;
+    cudaStream_t s = shard->stream;
+    CU_TRY(cudaMemsetAsync(d_created, 0, 4, s));
+    const unsigned grid = unsigned((n + 255) / 256);
+    if (shard->dtype == VX_U8)
+        intern_records_kernel<u8><<<grid, 256, 0, s>>>(shard->dev, u32(n), d_records, u32(rank), leaf_round != 0, d_ids_out,
+                                                        d_created);
+    else
+        intern_records_kernel<int32_t><<<grid, 256, 0, s>>>(shard->dev, u32(n), d_records, u32(rank), leaf_round != 0,
+                                                             d_ids_out, d_created);
+    CU_TRY(cudaGetLastError());
+    u32 created = 0;
+    CU_TRY(cudaMemcpyAsync(&created, d_created, 4, cudaMemcpyDeviceToHost, s));
+    rc = check_device_error(shard);
+    if (rc != VX_OK) return rc;
+    if (created_out) *created_out = created;
     return VX_OK;
 }
 
