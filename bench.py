@@ -141,6 +141,8 @@ def main():
     ap.add_argument("--no-others", action="store_true", help="skip the secondary workloads")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (profiling runs)")
+    ap.add_argument("--dedup", action="store_true", help="also run the global-dedup variant (BASELINE config 5) "
+                    "after the timed build and report it under 'global_dedup'")
     ap.add_argument("--workload", default="perlin", help="profiling only: time another workload in the main loop "
                     "(checkerboard | sum | sum_per_chunk | random255 | below); the headline is 'perlin'")
     args = ap.parse_args()
@@ -162,6 +164,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: stdout is ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -294,11 +298,15 @@ def main():
                 ("sum_per_chunk_x4096", lambda: wl.named_workload("sum_per_chunk", 4096), BUDGET),
                 ("random255_x4096", lambda: wl.named_workload("random255", 4096), 2 << 30),
                 ("perlin_surface_and_below_3mat", lambda: make_world(0, "surface_and_below"), BUDGET)]
+        sets.append(("d7_128cube_random255_x24", lambda: wl.named_workload("random255", 24, depth=7), 3 << 30))
+        sets.append(("d6_64cube_cell4_random255_x256", lambda: wl.named_workload("cell4_random255", 256, depth=6), 1 << 30))
         for name, gen, budget in sets:
             try:
                 log(f"secondary workload {name}")
                 m2, v2 = gen()
                 n2 = m2.shape[0]
+                depth2 = int(round(np.log2(m2.shape[1] * 8) / 3))
+                chunk_bytes2 = 2 * m2.shape[1] + 8 * m2.shape[1] + 8
                 it2 = vx.VoxInterner.with_memory_budget(budget, vx.U8, local_rank)
                 dm, dv = torch.from_numpy(m2).to(dev), torch.from_numpy(v2).to(dev)
                 dr = torch.zeros(n2, dtype=torch.int64, device=dev)
@@ -307,7 +315,7 @@ def main():
                     it2.reset_async(stream.cuda_stream)
                     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     a.record(stream)
-                    it2.apply_batches_device(DEPTH, n2, dm.data_ptr(), dv.data_ptr(), dr.data_ptr(),
+                    it2.apply_batches_device(depth2, n2, dm.data_ptr(), dv.data_ptr(), dr.data_ptr(),
                                              stream=stream.cuda_stream)
                     b.record(stream)
                     torch.cuda.synchronize()
@@ -317,14 +325,38 @@ def main():
                 nn = it2.stats()["total_cache_misses"]
                 d2 = it2.debug_counters()
                 ms = float(np.mean(ts))
-                ab = n2 * CHUNK_BYTES + nn * NODE_BYTES
-                others[name] = {"chunks_per_s": n2 / (ms * 1e-3), "kernel_ms": ms, "new_nodes": nn,
+                ab = n2 * chunk_bytes2 + nn * NODE_BYTES
+                others[name] = {"depth": depth2, "chunks": n2, "chunks_per_s": n2 / (ms * 1e-3), "kernel_ms": ms,
+                                "new_nodes": nn,
                                 "achieved_gbs": ab / (ms * 1e-3) / 1e9, "frac": ab / (ms * 1e-3) / 1e9 / peak,
                                 "branch_calls": d2["branch_calls"], "probe_steps": d2["probe_steps"],
                                 "cache_hits_local": d2["cache_hits_local"]}
                 del dm, dv, dr, it2
             except Exception as e:  # a secondary workload must never take the headline line down
                 others[name] = {"error": str(e)}
+
+    # ---------------------------------------------------------------- global dedup variant (config 5)
+    dedup_info = None
+    if args.dedup:
+        from voxelis_b200 import dedup as vd
+        log("global dedup variant")
+        itd = vx.VoxInterner.with_memory_budget(BUDGET, vx.U8, local_rank)
+        rts, _ = itd.apply_batches_slab(DEPTH, d_masks.data_ptr(), d_values.data_ptr(), n=n)
+        local_unique = itd.next_index - 1
+        barrier()
+        t0 = time.perf_counter()
+        if world > 1:
+            shard, groots, summ = vd.global_dedup_dist(itd, rts, BUDGET, vx.U8, local_rank)
+        else:
+            shards, groots_l, summ = vd.global_dedup_local([itd], [rts], BUDGET, vx.U8, local_rank)
+        torch.cuda.synchronize()
+        barrier()
+        dd_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        dedup_info = {"ms": dd_ms, "rounds": summ["rounds"], "global_unique_branches": summ["branches"],
+                      "global_unique_leaves": summ["leaves"], "bytes_sent_all_ranks": summ["bytes_sent"],
+                      "sum_of_per_gpu_unique_nodes": int(sum_over_ranks(float(local_unique))),
+                      "exchange": "torch.distributed.all_to_all_single over NCCL" if world > 1 else "single rank (no exchange)"}
+        del itd
 
     cpu = None
     log("cpu baseline")
@@ -366,6 +398,8 @@ def main():
             line["cpu_baseline"] = cpu
         if others:
             line["others"] = others
+        if dedup_info:
+            line["global_dedup"] = dedup_info
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
