@@ -357,6 +357,15 @@ def main():
                       "sum_of_per_gpu_unique_nodes": int(sum_over_ranks(float(local_unique))),
                       "exchange": "torch.distributed.all_to_all_single over NCCL" if world > 1 else "single rank (no exchange)"}
         del itd
+        if rank == 0:   # the reference's model: ONE interner for every chunk of every rank (oracle, CPU)
+            from oracle import oracle
+            ref = oracle.VoxInterner(4 * BUDGET)
+            for r in range(world):
+                mr, vr = (masks, values) if r == 0 else make_world(r)
+                ref.apply_batches_fresh(DEPTH, mr, vr)
+            st = ref.stats()
+            dedup_info["oracle_single_interner"] = {"branches": st["branch_nodes"] - 1, "leaves": st["leaf_nodes"]}
+            dedup_info["matches_oracle"] = (st["branch_nodes"] - 1 == summ["branches"] and st["leaf_nodes"] == summ["leaves"])
 
     cpu = None
     log("cpu baseline")
