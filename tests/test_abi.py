@@ -47,3 +47,19 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.lower() or f == "workloads.py", f
+
+
+def test_cpp_mirror_compiles_and_links():
+    """include/voxelis_b200.hpp (C++ mirror of the Rust API) + the README quick start compile with g++
+    and link against the C-ABI library; the binary is run on the GPU box by test_gpu_cpp_mirror.py."""
+    import subprocess
+    from voxelis_b200 import build
+    build.build()
+    out = os.path.join(ROOT, "tests", "cpp", "readme_quickstart")
+    cmd = ["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "cpp", "readme_quickstart.cpp"), "-o", out,
+           "-L", os.path.join(ROOT, "voxelis_b200"), "-lvoxelis_b200",
+           "-Wl,-rpath," + os.path.join(ROOT, "voxelis_b200")]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    assert os.path.exists(out)

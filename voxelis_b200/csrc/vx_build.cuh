@@ -406,7 +406,7 @@ u64 intern_branch(Ctx<T>& c, bool need, u64 child, bool block_level, u32 cval) {
     // types / mask are functions of the children (voxtree.rs:846-863, :959-1000)
     u32 leafb = (__ballot_sync(FULL, id_is_leaf(child)) >> gs) & 0xFF;
     u32 presb = (__ballot_sync(FULL, child != 0) >> gs) & 0xFF;
-    u64 h = child_hash(child, li);
+    u64 h = child_hash_lane(child, li);
     h += __shfl_xor_sync(FULL, h, 1);
     h += __shfl_xor_sync(FULL, h, 2);
     h += __shfl_xor_sync(FULL, h, 4);
@@ -1346,6 +1346,13 @@ __global__ void __launch_bounds__(CTA_THREADS, VX_MIN_CTAS) apply_kernel(ApplyAr
         }
         run = next_run;
         next_run = run < total_runs ? grab() : total_runs;
+        if (next_run < total_runs) {
+            // pull the masks of the run after the next into L2 (R units x 2*nblocks bytes, 128-byte lines):
+            // empty units are so cheap that one unit of register prefetch does not cover DRAM latency
+            const u8* mp = a.masks + (size_t((next_run * R) >> upc_log) * a.blocks + size_t((next_run * R) & (upc - 1)) * UNIT_BLOCKS) * 2;
+            const u32 bytes = R * u32(nblocks) * 2;
+            for (u32 off = u32(lane) * 128; off < bytes; off += 32 * 128) prefetch_l2(mp + off);
+        }
     }
     cta_finish<T>(c);
 }

@@ -159,6 +159,10 @@ __host__ __device__ inline u64 mix64(u64 x) {
 #define VX_HC5 0x165667B19E3779F9ull
 #define VX_HC6 0x27D4EB2F165667C5ull
 #define VX_HC7 0xFF51AFD7ED558CCDull
+// per-lane form: one constant-bank load instead of a select chain
+__device__ __constant__ u64 VX_HC_TABLE[8] = {VX_HC0, VX_HC1, VX_HC2, VX_HC3, VX_HC4, VX_HC5, VX_HC6, VX_HC7};
+__device__ __forceinline__ u64 child_hash_lane(u64 child, int li) { return child * VX_HC_TABLE[li]; }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __host__ __device__ inline u64 child_mult(int i) {
     return i == 0 ? VX_HC0 : i == 1 ? VX_HC1 : i == 2 ? VX_HC2 : i == 3 ? VX_HC3 : i == 4 ? VX_HC4
          : i == 5 ? VX_HC5 : i == 6 ? VX_HC6 : VX_HC7;

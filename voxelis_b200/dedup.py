@@ -41,6 +41,13 @@ def _p(t):
     return C.c_void_p(t.data_ptr() if t is not None and t.numel() else 0)
 
 
+def _sync(device):
+    """The library's kernels run on the interner's own stream and synchronise on return; torch (and
+    NCCL) work is queued on torch's streams.  Before handing a torch tensor to the library, wait for
+    whatever torch still has in flight for it (an all-to-all, a cat, a slice copy)."""
+    torch.cuda.current_stream(device).synchronize()
+
+
 class _Rank:
     """State of one (logical) rank during the merge."""
 
@@ -53,6 +60,7 @@ class _Rank:
         self.created = [0, 0]  # [branches, leaves] created in this rank's shard
 
     def pack(self, height: int, G: int):
+        _sync(self.device)
         counts = np.zeros(G, np.uint64)
         _ck(lib().vx_dedup_pack(self.local.h, height, _p(self.heights), _p(self.gmap), G,
                                 counts.ctypes.data_as(C.c_void_p), None, None))
@@ -68,6 +76,7 @@ class _Rank:
         n = records.numel() // REC_WORDS
         ids = torch.empty(max(n, 1), dtype=torch.int64, device=self.device)
         created = C.c_uint64(0)
+        _sync(self.device)
         if n:
             _ck(lib().vx_interner_intern_records(self.shard.h, n, _p(records), self.rank, int(leaf_round), _p(ids),
                                                  C.byref(created)))
@@ -75,11 +84,13 @@ class _Rank:
         return ids[:n]
 
     def scatter(self, src: torch.Tensor, ids: torch.Tensor):
+        _sync(self.device)
         if src.numel():
             _ck(lib().vx_dedup_scatter(self.local.h, src.numel(), _p(src), _p(ids), _p(self.gmap)))
 
     def map_roots(self, roots: torch.Tensor) -> torch.Tensor:
         out = torch.zeros_like(roots)
+        _sync(self.device)
         if roots.numel():
             _ck(lib().vx_dedup_map_roots(self.local.h, roots.numel(), _p(roots), _p(self.gmap), _p(out)))
         return out
