@@ -1223,17 +1223,35 @@ __global__ void __launch_bounds__(CTA_THREADS, VX_MIN_CTAS) apply_kernel(ApplyAr
     unsigned long long run = grab();
     unsigned long long next_run = run < total_runs ? grab() : total_runs;
     u64 nlo = 0, nhi = 0;
-    if (run < total_runs) masks_of(run * R, &nlo, &nhi);
+    if (R != 8 && run < total_runs) masks_of(run * R, &nlo, &nhi);
     while (run < total_runs) {
         const bool poisoned = __any_sync(FULL, lane == 0 && ld_strong(a.in.error) != ERR_NONE);
+        // run == 8: one pass over the cube's 8 KiB of masks (already pulled into L2) tells which of its
+        // eight units have a set bit at all; units without one cost nothing more than this test
+        u32 ne_units = 0xFF;
+        if (R == 8 && !poisoned) {
+            const unsigned long long w0 = run * 8;
+            const uint4* mp = (const uint4*)(a.masks + (size_t(w0 >> upc_log) * a.blocks + size_t(u32(w0) & (upc - 1)) * UNIT_BLOCKS) * 2) + lane * 2;
+            ne_units = 0;
+#pragma unroll 2
+            for (int k2 = 0; k2 < 8; ++k2) {
+                const uint4 q0 = ld_stream_v4(mp + k2 * 64), q1 = ld_stream_v4(mp + k2 * 64 + 1);
+                const bool any = ((q0.x | q0.y | q0.z | q0.w | q1.x | q1.y | q1.z | q1.w) & 0x00FF00FFu) != 0;  // set_mask bytes only
+                ne_units |= u32(__any_sync(FULL, any)) << k2;
+            }
+        }
         for (u32 k = 0; k < R; ++k) {
             const unsigned long long w = run * R + k;
             if (w >= total_units) break;
             const u32 chunk = u32(w >> upc_log), unit = u32(w) & (upc - 1);
-            const u64 mlo = nlo, mhi = nhi;
-            {  // request the masks of the unit after this one before doing any work
-                unsigned long long w2 = (k + 1 < R) ? w + 1 : next_run * R;
-                if (k + 1 < R ? (w2 < total_units) : (next_run < total_runs)) masks_of(w2, &nlo, &nhi);
+            u64 mlo = 0, mhi = 0;
+            if (R == 8) {
+                if ((ne_units >> k) & 1) masks_of(w, &mlo, &mhi);  // L1/L2 hit: the pre-scan just read them
+            } else {
+                mlo = nlo;
+                mhi = nhi;
+                // request the masks of the unit after this one before doing any work
+                if (next_run < total_runs) masks_of(next_run * R, &nlo, &nhi);
             }
             // poisoned interner: skip the rest, the host reports the error (warp-uniform, checked per run)
             if (poisoned) {
@@ -1261,11 +1279,16 @@ __global__ void __launch_bounds__(CTA_THREADS, VX_MIN_CTAS) apply_kernel(ApplyAr
             if (use_old) u.old_root = a.old_roots[chunk];
             const void* cv = (const u8*)a.values + size_t(chunk) * a.blocks * 8 * sizeof(T);
 
+            if (R == 8 && ne_units == 0 && !use_old && cpc == 1) {
+                // nothing set anywhere in this 32^3 chunk: no block enters `paths` (voxtree.rs:905-911)
+                if (lane == 0) write_root<T>(c, a, chunk, fl, false);
+                break;
+            }
             // ---- stage 0: the unit.  stage 1: its 32^3 cube.  stage 2: the chunk's top levels.
-            bool some;
+            bool some = false;
             if (use_old)
                 some = build_blocks<T, OLD>(c, mlo, mhi, cv, unit * UNIT_BLOCKS, nblocks, u);
-            else
+            else if (R != 8 || ((ne_units >> k) & 1))
                 some = build_blocks<T, false>(c, mlo, mhi, cv, unit * UNIT_BLOCKS, nblocks, u);
             u32 rn = u32(nblocks) / 8, rpos = (unit * UNIT_BLOCKS) >> 3;
             int rd = D - 2;
