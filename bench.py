@@ -298,6 +298,7 @@ def main():
                 ("sum_per_chunk_x4096", lambda: wl.named_workload("sum_per_chunk", 4096), BUDGET),
                 ("random255_x4096", lambda: wl.named_workload("random255", 4096), 2 << 30),
                 ("perlin_surface_and_below_3mat", lambda: make_world(0, "surface_and_below"), BUDGET)]
+        sets.append(("set_sum_i32_x4096", lambda: wl.named_workload("sum", 4096, dtype=wl.I32), BUDGET))
         sets.append(("d7_128cube_random255_x24", lambda: wl.named_workload("random255", 24, depth=7), 3 << 30))
         sets.append(("d6_64cube_cell4_random255_x256", lambda: wl.named_workload("cell4_random255", 256, depth=6), 1 << 30))
         for name, gen, budget in sets:
@@ -306,8 +307,10 @@ def main():
                 m2, v2 = gen()
                 n2 = m2.shape[0]
                 depth2 = int(round(np.log2(m2.shape[1] * 8) / 3))
-                chunk_bytes2 = 2 * m2.shape[1] + 8 * m2.shape[1] + 8
-                it2 = vx.VoxInterner.with_memory_budget(budget, vx.U8, local_rank)
+                chunk_bytes2 = 2 * m2.shape[1] + 8 * m2.shape[1] * (4 if v2.dtype == np.int32 else 1) + 8
+                dt2 = vx.I32 if v2.dtype == np.int32 else vx.U8
+                esz = 4 if dt2 == vx.I32 else 1
+                it2 = vx.VoxInterner.with_memory_budget(budget, dt2, local_rank)
                 dm, dv = torch.from_numpy(m2).to(dev), torch.from_numpy(v2).to(dev)
                 dr = torch.zeros(n2, dtype=torch.int64, device=dev)
                 ts = []
@@ -325,7 +328,7 @@ def main():
                 nn = it2.stats()["total_cache_misses"]
                 d2 = it2.debug_counters()
                 ms = float(np.mean(ts))
-                ab = n2 * chunk_bytes2 + nn * NODE_BYTES
+                ab = n2 * chunk_bytes2 + nn * (NODE_BYTES + esz - 1)
                 others[name] = {"depth": depth2, "chunks": n2, "chunks_per_s": n2 / (ms * 1e-3), "kernel_ms": ms,
                                 "new_nodes": nn,
                                 "achieved_gbs": ab / (ms * 1e-3) / 1e9, "frac": ab / (ms * 1e-3) / 1e9 / peak,

@@ -181,3 +181,40 @@ def test_depth7_extension(gpu_api, oracle_api):
     parity.assert_parity(gpu_api, oracle_api, 7, *r, dense_check=False)
     g, groots, c, croots = r[0], r[1], r[3], r[4]
     assert np.array_equal(g.roots_to_vec(groots[:1], 7)[0], c.root_to_vec(croots[0], 7))
+
+
+def test_full_size_configs_properties(gpu_api, oracle_api):
+    """BASELINE.json configs at their full sizes, checked through size-independent properties:
+    config 2 — 4096 identical checkerboard / set_sum chunks in one interner: every root identical, node
+    counts equal the single-chunk known answers (all-hit after the first chunk);
+    config 3 — the 64x8x64 perlin-dunes world: changed flags == "batch has a set bit", unique node counts
+    and hit/miss counters equal the oracle's, random chunks unfold voxel-exactly."""
+    vx, o = gpu_api, oracle_api
+    for name, (br, lf) in {"checkerboard": (5, 1), "sum": (83, 94)}.items():
+        masks, values = wl.named_workload(name, 4096)
+        g = vx.VoxInterner.with_memory_budget(256 << 20)
+        roots, changed = g.apply_batches_slab(5, masks, values)
+        assert changed.all() and (roots == roots[0]).all()
+        st = g.stats()
+        assert (st["branch_nodes"] - 1, st["leaf_nodes"]) == (br, lf)
+        assert g.get_ref(int(roots[0])) == 4096                      # 4096 tree handles on one root
+    masks, values = wl.terrain_world((64, 8, 64), 5, "surface_only")
+    g = vx.VoxInterner.with_memory_budget(256 << 20)
+    roots, changed = g.apply_batches_slab(5, masks, values)
+    assert np.array_equal(changed.astype(bool), masks[:, :, 0].any(1))
+    assert ((roots == 0) == (changed == 0)).all()
+    c = o.VoxInterner(256 << 20)
+    croots, cchanged = c.apply_batches_fresh(5, masks, values)
+    gst, cst = g.stats(), c.stats()
+    for k in ("branch_nodes", "leaf_nodes", "collapsed_branches", "total_cache_hits", "total_cache_misses"):
+        assert gst[k] == cst[k], k
+    rng = np.random.default_rng(0)
+    pick = rng.choice(np.flatnonzero(changed), 24, replace=False)
+    dense = g.roots_to_vec(roots[pick], 5)
+    for j, i in enumerate(pick):
+        assert np.array_equal(dense[j], wl.dense_expected(masks[i], values[i]))
+    # identical batches anywhere in the world got identical roots (dedup across chunks)
+    key = {}
+    for i in np.flatnonzero(changed)[:2000]:
+        k = (masks[i].tobytes(), values[i].tobytes())
+        assert key.setdefault(k, roots[i]) == roots[i]
