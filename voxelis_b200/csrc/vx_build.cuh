@@ -278,7 +278,7 @@ __device__ __forceinline__ void leaf_payload(const InternerDev& in, u32 idx, u32
 
 __device__ inline u64 leaf_get(Ctx<u8>& c, u32 v, bool need) {
     need = need && v != 0;
-    u64 id = need ? c.cs->leaf[v] : 0;
+    u64 id = need ? lds_relaxed(&c.cs->leaf[v]) : 0;
     bool miss = need && id == 0;
     while (__any_sync(FULL, miss)) {
         if (miss) {
@@ -297,14 +297,14 @@ __device__ inline u64 leaf_get(Ctx<u8>& c, u32 v, bool need) {
                         id = id_leaf((u64(gen) << 32) | idx);
                         fence_gpu();
                         st_strong(&c.in.leaf_u8[v], id);
-                        c.cs->leaf[v] = id;
+                        sts_relaxed(&c.cs->leaf[v], id);
                         c.t.leaf_miss++;
                         miss = false;
                     }
                 }
             } else if (g != ID_PENDING) {
                 id = g;
-                c.cs->leaf[v] = g;
+                sts_relaxed(&c.cs->leaf[v], g);
                 miss = false;
             }
         }
@@ -364,6 +364,7 @@ __device__ inline u64 leaf_get(Ctx<int32_t>& c, u32 v, bool need) {
     }
     // refresh the per-warp cache; one writer per entry (match on e) keeps key/id pairs untorn
     u32 wmask = __ballot_sync(FULL, from_global && id != 0);
+    __syncwarp();
     if (from_global && id != 0) {
         u32 same = __match_any_sync(wmask, e);
         if ((__ffs(same) - 1) == c.lane) {
@@ -541,6 +542,7 @@ u64 intern_branch(Ctx<T>& c, bool need, u64 child, bool block_level, u32 cval) {
             u32 e2 = __shfl_sync(FULL, ue, g2 * 8);
             if (((wb >> (g2 * 8)) & 1) && g2 * 8 < gs && e2 == ue) write = false;
         }
+        __syncwarp();  // the entry's earlier reads by other lanes are done (WAR)
         if (write) {
             c.ws->ukey[ue * 8 + li] = child;
             if (li == 0) c.ws->uval[ue] = result;
@@ -588,7 +590,7 @@ struct ChildIds<u8> {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             u32 v = u32(w >> (8 * i)) & 0xFF;
-            missing = missing || (need && v != 0 && leaf[v] == 0);
+            missing = missing || (need && v != 0 && lds_relaxed(&leaf[v]) == 0);
         }
         if (__any_sync(FULL, missing)) {  // rare: some leaf does not exist yet (get_or_create_leaf)
 #pragma unroll 1
@@ -597,7 +599,7 @@ struct ChildIds<u8> {
     }
     __device__ __forceinline__ u64 get(int i) const {
         u32 v = u32(w >> (8 * i)) & 0xFF;
-        return v ? leaf[v] : 0;
+        return v ? lds_relaxed(&leaf[v]) : 0;
     }
 };
 template <>
@@ -866,6 +868,7 @@ __device__ inline u64 block_node(Ctx<T>& c, bool active, typename VT<T>::Key val
         // cache refresh: one writer per entry, so key and id of an entry always belong together
         const bool wr = leader && bid != 0;
         const u32 wb = __ballot_sync(FULL, wr);
+        __syncwarp();  // the entry's earlier reads by other lanes are done (WAR)
         if (wr) {
             u32 sm = __match_any_sync(wb, e);
             if ((__ffs(sm) - 1) == lane) {
@@ -1136,7 +1139,7 @@ __device__ inline void cta_finish(Ctx<T>& c) {
             __threadfence_block();
             for (u32 v = c.lane; v < 256; v += 32) {
                 u32 n = ((volatile u32*)c.cs->leafref)[v];
-                if (n) atomicAdd(&c.in.refs[id_index(((volatile u64*)c.cs->leaf)[v])], n);
+                if (n) atomicAdd(&c.in.refs[id_index(lds_relaxed(&c.cs->leaf[v]))], n);
             }
         }
     }

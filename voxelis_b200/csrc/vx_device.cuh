@@ -115,6 +115,18 @@ __device__ __forceinline__ void st_strong(u32* p, u32 v) {
     asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void fence_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+// CTA-shared memo words (CtaSmem::leaf) are read and written by every warp of the CTA with no barrier
+// in between: all writers store the same value and a reader takes either 0 (-> global table) or that
+// value.  Relaxed .cta accesses make those morally-strong operations under the PTX memory model, so the
+// (benign, idempotent) race is not a data race and the 8-byte word cannot be observed torn.
+__device__ __forceinline__ u64 lds_relaxed(const u64* p) {
+    u64 v;
+    asm volatile("ld.relaxed.cta.shared.u64 %0, [%1];" : "=l"(v) : "r"(u32(__cvta_generic_to_shared(p))) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_relaxed(u64* p, u64 v) {
+    asm volatile("st.relaxed.cta.shared.u64 [%0], %1;" ::"r"(u32(__cvta_generic_to_shared(p))), "l"(v) : "memory");
+}
 
 // Streaming (read-once) batch loads: keep them out of L1 so the
 // interner's table and pools keep the cache.
