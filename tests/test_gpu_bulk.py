@@ -1,0 +1,141 @@
+"""The two builders for fresh trees — the fused apply_kernel and the level-synchronous bulk pipeline
+(voxelis_b200/csrc/vx_bulk.cuh) — against the oracle and against each other.  VX_BUILDER pins one."""
+import numpy as np
+import pytest
+
+import parity
+from voxelis_b200 import workloads as wl
+
+pytestmark = pytest.mark.gpu
+
+
+def _mixed(depth, dtype, n_small):
+    parts = [wl.batch_from_function(depth, wl.p_random(4), dtype, n_small),
+             wl.batch_from_function(depth, wl.p_random(255, cell=2), dtype, 3),
+             wl.batch_from_function(depth, wl.p_sparse(), dtype, 4),
+             wl.named_workload("checkerboard", 5, depth, dtype),
+             wl.named_workload("hollow", 2, depth, dtype),
+             wl.named_workload("uniform", 3, depth, dtype)]
+    masks = np.concatenate([p[0] for p in parts])
+    values = np.concatenate([p[1] for p in parts])
+    masks[1] = 0                       # nothing set: the tree stays EMPTY, changed == false
+    masks[2, ::3, 0] = 0               # ragged: whole blocks without set bits
+    masks[4, 100:, 0] = 0              # only the first 100 blocks carry patches
+    return masks, values
+
+
+@pytest.mark.parametrize("builder", ["bulk", "fused"])
+@pytest.mark.parametrize("dtype", [wl.U8, wl.I32], ids=["u8", "i32"])
+@pytest.mark.parametrize("depth", [4, 5, 6])
+def test_builders_match_oracle(gpu_api, oracle_api, depth, dtype, builder, monkeypatch):
+    monkeypatch.setenv("VX_BUILDER", builder)
+    masks, values = _mixed(depth, dtype, 24 if depth < 6 else 3)
+    r = parity.build_both(gpu_api, oracle_api, depth, masks, values, dtype, budget=512 << 20)
+    assert r[2][1] == 0 and r[1][1] == 0
+    parity.assert_parity(gpu_api, oracle_api, depth, *r)
+
+
+def test_bulk_depth7(gpu_api, oracle_api, monkeypatch):
+    monkeypatch.setenv("VX_BUILDER", "bulk")
+    parts = [wl.batch_from_function(7, wl.p_random(255, cell=4), wl.U8, 1),
+             wl.batch_from_function(7, wl.p_sparse(3, 8), wl.U8, 2)]
+    masks = np.concatenate([p[0] for p in parts])
+    values = np.concatenate([p[1] for p in parts])
+    r = parity.build_both(gpu_api, oracle_api, 7, masks, values, wl.U8, budget=512 << 20)
+    parity.assert_parity(gpu_api, oracle_api, 7, *r, dense_check=False)
+
+
+def test_bulk_terrain_and_repeat_calls(gpu_api, oracle_api, monkeypatch):
+    """Two calls into one interner (the second finds the first one's nodes), slices forced by a tiny scratch
+    limit, and the terrain world: same DAG as the oracle's serial application."""
+    vx, o = gpu_api, oracle_api
+    monkeypatch.setenv("VX_BUILDER", "bulk")
+    monkeypatch.setenv("VX_BULK_MAX_BYTES", str(3 << 20))   # ~50 chunks of 32^3 per slice
+    m1, v1 = wl.terrain_world((6, 3, 6), 5, "surface_and_below", wl.U8, materials=3)
+    m2, v2 = wl.terrain_world((5, 3, 5), 5, "surface_only", wl.U8, x_chunk_offset=3)
+    g = vx.VoxInterner.with_memory_budget(256 << 20)
+    r1, c1 = g.apply_batches_slab(5, m1, v1)
+    r2, c2 = g.apply_batches_slab(5, m2, v2)
+    c = o.VoxInterner(256 << 20)
+    cr, cc = c.apply_batches_fresh(5, np.concatenate([m1, m2]), np.concatenate([v1, v2]))
+    parity.assert_parity(vx, o, 5, g, np.concatenate([r1, r2]), np.concatenate([c1, c2]), c, cr, cc)
+
+
+def test_bulk_after_release_uses_free_list(gpu_api, oracle_api, monkeypatch):
+    """Nodes released by VoxTree::clear go to the free list (interner/macros.rs:1-41); a bulk build after
+    that recycles them with bumped generations, exactly like the fused kernel does."""
+    vx, o = gpu_api, oracle_api
+    m, v = wl.batch_from_function(5, wl.p_random(255, cell=2), wl.U8, 6)
+    results = {}
+    for builder in ("fused", "bulk"):
+        monkeypatch.setenv("VX_BUILDER", builder)
+        g = vx.VoxInterner.with_memory_budget(256 << 20)
+        t = vx.VoxTree(5)
+        b = t.create_batch()
+        b.masks[:] = m[0]
+        b.values[:] = v[0]
+        b.mark_patched()
+        t.apply_batch(g, b)
+        before = g.stats()["alive_nodes"]
+        t.clear(g)                                   # everything but the empty branch is released
+        assert g.stats()["alive_nodes"] == 1 and before > 500
+        roots, changed = g.apply_batches_slab(5, m, v)
+        st = g.stats()
+        dense = g.roots_to_vec(roots, 5)
+        for i in range(len(roots)):
+            assert np.array_equal(dense[i], wl.dense_expected(m[i], v[i]))
+        gens = np.array([(int(r) >> 32) & 0x7FFF for r in roots])
+        results[builder] = (st["alive_nodes"], st["recycled_nodes"], int(g.next_index), sorted(gens.tolist()))
+        d = g.download()
+        sig = o.dag_signature(d["children"], d["values"], roots, 5, want_stream=True, want_indeg=True)
+        live = sig["numbers"] != 0
+        assert np.array_equal(d["refs"][live], sig["indeg"][live])
+        results[builder + "_sig"] = sig["sig"]
+    assert results["fused"][:3] == results["bulk"][:3]
+    assert results["fused_sig"] == results["bulk_sig"]
+
+
+def test_bulk_host_paths_and_device_path_agree(gpu_api, monkeypatch):
+    import torch
+    vx = gpu_api
+    monkeypatch.setenv("VX_BUILDER", "bulk")
+    masks, values = wl.terrain_world((8, 2, 8), 5, "surface_only", wl.U8)
+    ref = None
+    for mode in ("pageable", "pinned", "pinned_staged", "device"):
+        g = vx.VoxInterner.with_memory_budget(128 << 20)
+        if mode == "pageable":
+            roots, changed = g.apply_batches_slab(5, masks, values)
+        elif mode.startswith("pinned"):
+            if mode == "pinned_staged":
+                monkeypatch.setenv("VX_HOST_MODE", "staged")
+            hm, hv = torch.from_numpy(masks).pin_memory(), torch.from_numpy(values).pin_memory()
+            roots, changed = g.apply_batches_slab(5, hm.numpy(), hv.numpy())
+            monkeypatch.delenv("VX_HOST_MODE", raising=False)
+        else:
+            dm, dv = torch.from_numpy(masks).cuda(), torch.from_numpy(values).cuda()
+            dr = torch.zeros(len(masks), dtype=torch.int64, device="cuda")
+            dc = torch.zeros(len(masks), dtype=torch.uint8, device="cuda")
+            torch.cuda.synchronize()
+            g.apply_batches_device(5, len(masks), dm.data_ptr(), dv.data_ptr(), dr.data_ptr(), dc.data_ptr())
+            g.sync()
+            roots, changed = dr.cpu().numpy().view(np.uint64), dc.cpu().numpy()
+        st = g.stats()
+        dense = g.roots_to_vec(roots[:16], 5)
+        got = (st["alive_nodes"], st["leaf_nodes"], st["collapsed_branches"], changed.tobytes(), dense.tobytes())
+        ref = ref or got
+        assert got == ref, mode
+
+
+def test_bulk_out_of_memory_is_a_status(gpu_api, monkeypatch):
+    vx = gpu_api
+    monkeypatch.setenv("VX_BUILDER", "bulk")
+    masks, values = wl.batch_from_function(5, wl.p_random(255), wl.U8, 16)
+    g = vx.VoxInterner.with_memory_budget(1 << 20)            # ~13k nodes; the batch needs ~75k
+    with pytest.raises(vx.VoxelisError) as e:
+        g.apply_batches_slab(5, masks, values)
+    assert "Out of memory" in str(e.value)
+    with pytest.raises(vx.VoxelisError):
+        g.apply_batches_slab(5, masks[:1], values[:1])        # poisoned until reset
+    g.reset()
+    roots, changed = g.apply_batches_slab(5, *wl.named_workload("checkerboard", 4, 5, wl.U8))
+    assert changed.all()

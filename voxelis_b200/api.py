@@ -85,6 +85,8 @@ def lib():
     L.vx_interner_get_children.argtypes = [vp, u64, vp]
     L.vx_interner_stats.argtypes = [vp, vp]
     L.vx_interner_debug_counters.argtypes = [vp, vp]
+    L.vx_interner_profile_stages.argtypes = [vp, C.c_int]
+    L.vx_interner_stage_ms.argtypes = [vp, vp, vp]
     L.vx_interner_download.restype = i64
     L.vx_interner_download.argtypes = [vp, sz, vp, vp, vp, vp, vp]
     L.vx_interner_sync.argtypes = [vp]
@@ -238,6 +240,17 @@ class VoxInterner:
         keys = ["leaf_calls", "branch_calls", "leaf_misses", "branch_misses", "collapsed", "probe_steps",
                 "cache_hits_local", "recycled"]
         return {k: int(v) for k, v in zip(keys, a)}
+
+    def profile_stages(self, on: bool = True) -> None:
+        """Diagnostics: record CUDA events between the launches of every following apply call."""
+        _ck(lib().vx_interner_profile_stages(self.h, 1 if on else 0))
+
+    def stage_ms(self) -> list:
+        """[(kernel name, device ms)] of the last apply call (empty unless profile_stages is on)."""
+        ms = (C.c_float * 9)()
+        names = (C.c_char_p * 9)()
+        k = _ck(lib().vx_interner_stage_ms(self.h, ms, names))
+        return [(names[i].decode(), float(ms[i])) for i in range(k)]
 
     def download(self) -> dict:
         n = self.next_index

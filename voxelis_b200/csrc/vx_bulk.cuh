@@ -1,0 +1,508 @@
+// vx_bulk.cuh — level-synchronous bulk builder for MANY fresh trees (sm_100a).
+//
+// Same result as apply_kernel (vx_build.cuh) for the north-star shape — n fresh trees, no fill flags,
+// depth >= 4 — i.e. set_batch_at_depth_iterative (spatial/voxtree.rs:724-1118) on EMPTY roots, which
+// reduces to the canonical bottom-up DAG of each batch.  The fused kernel gives every warp
+// one 16^3 sub-cube and walks its levels one after the other, so a warp has a handful of dependent
+// table lookups in flight; with 10^5..10^8 non-empty blocks in a call that chain latency is the
+// bound.  Here every LEVEL of every chunk is one launch with one THREAD per node, so hundreds of
+// thousands of independent lookups are in flight and the levels cost a few round trips each:
+//
+//   plan     warp per 512-block unit reads its 1 KiB of masks once and emits, order-preserving,
+//            the candidate blocks (set_mask != 0) and the candidate nodes of the three levels above
+//            them as (first child slot, child mask) — siblings are adjacent, so a node's children are
+//            a contiguous run of the level below.  Lists are allocated per unit with atomic counters.
+//   blocks   thread per candidate block: block_node() of vx_build.cuh (phase 1, :770-897)
+//   levels   thread per candidate node: uniform collapse / get_or_create_branch (phase 2, :905-1106)
+//   upper    dense levels from the unit nodes (depth D-4) up to the root, thread per node; the last
+//            one writes the roots (apply_batch, voxtree.rs:303-328)
+//
+// HBM layout of the scratch (allocated once per interner for the largest call seen, vx_capi.cu):
+//   level l in {0,1,2}:  first[l][cnt_l] u32, cm[l][cnt_l] u8, ids[l][cnt_l] u64   (level 0: first = block index,
+//                        cm = set_mask)
+//   units:               first[U] u32, cm[U] u8 (dense, U = n * B / 512);  dense id arrays ping-pong above
+#pragma once
+#include "vx_build.cuh"
+
+namespace vx {
+
+struct BulkArgs {
+    InternerDev in;
+    const u8* masks;     // [n][B][2]
+    const void* values;  // [n][B][8]
+    u64* roots;          // [n]
+    u8* changed;         // [n] or null
+    u32* cnt;            // [0..2] candidates per sparse level, [3] dense units, [4] dense-unit work counter;
+                         // zeroed before the plan kernel
+    u32* first[3];
+    u8* cm[3];
+    u64* ids[3];
+    u32* unit_first;  // [U]
+    u8* unit_cm;      // [U]
+    u64* dense[2];    // ping-pong dense id arrays for the levels above the units
+    u32* dense_units; // [<= U] units with >= dense_min candidate blocks: built by one warp each
+    unsigned long long units;  // U
+    u32 n;
+    u32 depth;
+    u32 blocks;       // B
+    u32 dense_min;
+    u32 use_free;
+};
+constexpr u32 UNIT_PREBUILT = 0xFFFFFFFFu;  // unit_first marker: the unit's node is already in dense[0]
+
+__device__ __forceinline__ u32 ld_stream_u32(const void* p) {
+    u32 v;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ u32 ld_stream_u8(const void* p) {
+    u32 v;
+    asm volatile("ld.global.nc.L1::no_allocate.u8 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// plan: one warp per unit of 512 Morton-consecutive blocks (lane = 16 blocks = 32 B of masks).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bulk_plan_kernel(BulkArgs a) {
+    const u32 lane = threadIdx.x & 31;
+    const unsigned long long warp = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const unsigned long long nwarps = (size_t(gridDim.x) * blockDim.x) >> 5;
+    uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;
+    if (warp < a.units) {
+        const uint4* mp = (const uint4*)(a.masks + warp * (UNIT_BLOCKS * 2)) + lane * 2;
+        n0 = ld_stream_v4(mp);
+        n1 = ld_stream_v4(mp + 1);
+    }
+    for (unsigned long long w = warp; w < a.units; w += nwarps) {
+        const uint4 q0 = n0, q1 = n1;
+        if (w + nwarps < a.units) {  // the next unit's masks are in flight while this one is planned
+            const uint4* mp = (const uint4*)(a.masks + (w + nwarps) * (UNIT_BLOCKS * 2)) + lane * 2;
+            n0 = ld_stream_v4(mp);
+            n1 = ld_stream_v4(mp + 1);
+        }
+        // set_mask bytes (even positions; clear_mask is never read by the reference)
+        const u64 sa = u64(__byte_perm(q0.x, q0.y, 0x6420)) | (u64(__byte_perm(q0.z, q0.w, 0x6420)) << 32);
+        const u64 sb = u64(__byte_perm(q1.x, q1.y, 0x6420)) | (u64(__byte_perm(q1.z, q1.w, 0x6420)) << 32);
+        const u32 bits = nzbytes(sa) | (nzbytes(sb) << 8);  // candidate blocks of this lane
+        if (!__any_sync(FULL, bits != 0)) {
+            if (lane == 0) a.unit_cm[w] = 0;
+            continue;
+        }
+        const u32 pa = (bits & 0xFF) != 0, pb = (bits >> 8) != 0;  // this lane's two level-1 parents
+        // exclusive prefix sums over the lanes: candidates at level 0 (r0) and level 1 (r1), packed
+        const u32 mine = u32(__popc(bits)) | ((pa + pb) << 16);
+        u32 incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            u32 t = __shfl_up_sync(FULL, incl, o);
+            if (lane >= u32(o)) incl += t;
+        }
+        const u32 tot = __shfl_sync(FULL, incl, 31);
+        const u32 r0 = (incl - mine) & 0xFFFF, r1 = (incl - mine) >> 16;
+        const u32 c0 = tot & 0xFFFF, c1 = tot >> 16;
+        if (c0 >= a.dense_min) {
+            // a busy unit: thread-per-block lists would cost more than they save; one warp builds it the
+            // way apply_kernel does (lane = block, siblings in neighbouring lanes)
+            if (lane == 0) {
+                a.dense_units[atomicAdd(&a.cnt[3], 1u)] = u32(w);
+                a.unit_first[w] = UNIT_PREBUILT;
+                a.unit_cm[w] = 0xFF;
+            }
+            continue;
+        }
+        // level 2: node q = lanes 4q..4q+3 (eight level-1 parents)
+        u32 cm2 = (pa | (pb << 1)) << (2 * (lane & 3));
+        cm2 |= __shfl_xor_sync(FULL, cm2, 1);
+        cm2 |= __shfl_xor_sync(FULL, cm2, 2);
+        const u32 b2 = __ballot_sync(FULL, (lane & 3) == 0 && cm2 != 0);  // bits at lanes 0,4,..,28
+        const u32 c2 = __popc(b2);
+        u32 base = 0;
+        if (lane < 3) base = atomicAdd(&a.cnt[lane], lane == 0 ? c0 : lane == 1 ? c1 : c2);
+        const u32 base0 = __shfl_sync(FULL, base, 0), base1 = __shfl_sync(FULL, base, 1), base2 = __shfl_sync(FULL, base, 2);
+        // level 0 entries: global block index + set_mask
+        {
+            u32 bb = bits, k = base0 + r0;
+            const u32 blk0 = u32(w * UNIT_BLOCKS) + lane * 16;
+            while (bb) {
+                const int j = __ffs(bb) - 1;
+                bb &= bb - 1;
+                a.first[0][k] = blk0 + j;
+                a.cm[0][k] = u8((j < 8 ? sa >> (8 * j) : sb >> (8 * (j - 8))) & 0xFF);
+                ++k;
+            }
+        }
+        // level 1 entries: first child slot in level 0 + which of the eight blocks are candidates
+        if (pa) {
+            a.first[1][base1 + r1] = base0 + r0;
+            a.cm[1][base1 + r1] = u8(bits & 0xFF);
+        }
+        if (pb) {
+            a.first[1][base1 + r1 + pa] = base0 + r0 + __popc(bits & 0xFF);
+            a.cm[1][base1 + r1 + pa] = u8(bits >> 8);
+        }
+        // level 2 entries
+        if ((lane & 3) == 0 && cm2 != 0) {
+            const u32 k2 = base2 + __popc(b2 & ((1u << lane) - 1));
+            a.first[2][k2] = base1 + r1;
+            a.cm[2][k2] = u8(cm2);
+        }
+        // the unit node (dense): children = the unit's level-2 candidates
+        if (lane == 0) {
+            u32 cm3 = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) cm3 |= ((b2 >> (4 * q)) & 1u) << q;
+            a.unit_first[w] = base2;
+            a.unit_cm[w] = u8(cm3);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// get_or_create_branch (interner/mod.rs:716-829), thread-per-key with the eight child ids in
+// registers — the probing protocol of intern_block with the children given directly.
+// ------------------------------------------------------------------------------------------------
+template <class T>
+__device__ inline u64 intern_node(Ctx<T>& c, bool need, const u64 (&ch)[8], u32 types, u32 mask) {
+    const InternerDev& in = c.in;
+    if (!__any_sync(FULL, need)) return 0;
+    u64 h = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) h += child_hash(ch[i], i);
+    h = finish_hash(h);
+    const u32 fp = u32(h >> 47);
+    u32 bucket = u32(h) & in.bucket_mask;
+    u64 result = 0;
+    bool done = !need;
+    // ---- per-warp parent cache (hot keys must not all go to the same L2 line)
+    const u32 ue = u32(h >> 32) & (UC - 1);
+    if (need) {
+        bool hit = true;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) hit = hit && c.ws->ukey[ue * 8 + i] == ch[i];
+        if (hit) {
+            result = c.ws->uval[ue];
+            done = result != 0;
+            if (done) c.t.local++;
+        }
+    }
+    const bool went_global = !done;
+    u32 skip = 0;
+    int guard = 0;
+    while (__any_sync(FULL, !done)) {
+        bool claimed = false;
+        int ek = 0;
+        if (!done) {
+            const u64* bp = &in.slots[size_t(bucket) * 8];
+            c.t.probes++;
+            u64 sl[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ld_strong_v2(bp + 2 * j, &sl[2 * j], &sl[2 * j + 1]);
+            u32 mb = 0, eb = 0, pb = 0;
+            u64 cand = 0;
+#pragma unroll
+            for (int k = 7; k >= 0; --k) {
+                const u64 sv = sl[k];
+                const u32 lo = u32(sv);
+                if (sv == 0)
+                    eb |= 1u << k;
+                else if (lo != IDX_TOMB && u32(sv >> 47) == fp && !((skip >> k) & 1)) {
+                    if (lo == IDX_PENDING)
+                        pb |= 1u << k;
+                    else {
+                        mb |= 1u << k;
+                        cand = sv;  // ends up as the lowest matching slot
+                    }
+                }
+            }
+            if (mb) {
+                const u64* rp = &in.children[size_t(u32(cand)) * 8];
+                u64 r[8];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) ld_strong_v2(rp + 2 * j, &r[2 * j], &r[2 * j + 1]);
+                bool eq = true;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) eq = eq && r[i] == ch[i];
+                if (eq) {
+                    result = id_branch(cand, types, mask);
+                    done = true;
+                } else {
+                    skip |= 1u << (__ffs(mb) - 1);
+                }
+            } else if (pb) {
+                // a slot with my fingerprint is being published (possibly my key): look again
+            } else if (eb) {
+                ek = __ffs(eb) - 1;
+                u64 old = atomicCAS((ull*)&in.slots[size_t(bucket) * 8 + ek], 0ull, (ull)((u64(fp) << 47) | IDX_PENDING));
+                claimed = old == 0;
+            } else {
+                bucket = (bucket + 1) & in.bucket_mask;
+                skip = 0;
+                if (++guard > (1 << 22)) {
+                    set_error(in, ERR_TABLE_FULL);
+                    done = true;
+                }
+            }
+        }
+        // ---- nodes created in this step: one index allocation per warp, payload, fence, publish
+        const u32 cb = __ballot_sync(FULL, claimed);
+        if (cb != 0) {
+            u32 idx = 0, gen = 0;
+            if (!c.use_free) {
+                u32 base = 0;
+                if (c.lane == 0) base = atomicAdd(in.next_index, u32(__popc(cb)));
+                base = __shfl_sync(FULL, base, 0);
+                idx = base + __popc(cb & ((1u << c.lane) - 1));
+            } else if (claimed) {
+                idx = alloc_one(in, true, &gen);
+            }
+            const u64 genidx = (u64(gen) << 32) | idx;
+            const bool oom = idx >= in.capacity;
+            if (claimed) {
+                if (oom) {
+                    set_error(in, ERR_OOM);
+                } else {
+                    u64* rp = &in.children[size_t(idx) * 8];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        *reinterpret_cast<ulonglong2*>(rp + 2 * j) = make_ulonglong2(ch[2 * j], ch[2 * j + 1]);
+                    // LOD value = mode of the child values (core/voxel.rs:96-141); in-degree of every child
+                    u32 v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = ch[i] != 0 ? child_value<T>(in, ch[i]) : 0;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        if (ch[i] != 0) {
+                            if (sizeof(T) == 1 && id_is_leaf(ch[i])) {
+                                sts_relaxed(&c.cs->leaf[v[i]], ch[i]);  // cta_finish flushes through this table
+                                atomicAdd(&c.cs->leafref[v[i]], 1u);
+                            } else {
+                                atomicAdd(&in.refs[id_index(ch[i])], 1u);
+                            }
+                        }
+                    }
+                    ((T*)in.values)[idx] = T(mode8(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]));
+                    in.hashes[idx] = h;
+                    c.t.branch_miss++;
+                }
+                fence_gpu();
+                // out of memory: hand the slot back (the interner is poisoned, results are discarded)
+                st_strong(&in.slots[size_t(bucket) * 8 + ek], oom ? u64(0) : ((u64(fp) << 47) | genidx));
+                result = oom ? 0 : id_branch(genidx, types, mask);
+                done = true;
+            }
+        }
+    }
+    // refresh the parent cache: one writer per entry, so an entry is never a mix of two keys
+    const bool wr = went_global && result != 0;
+    const u32 wb = __ballot_sync(FULL, wr);
+    __syncwarp();
+    if (wr) {
+        const u32 sm = __match_any_sync(wb, ue);
+        if ((__ffs(sm) - 1) == c.lane) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) c.ws->ukey[ue * 8 + i] = ch[i];
+            c.ws->uval[ue] = result;
+        }
+    }
+    __syncwarp();
+    return result;
+}
+
+// One parent of phase 2 (voxtree.rs:905-1106) on a fresh tree, one thread: absent if no child entered
+// `paths`, the shared Leaf if eight identical leaves (:1050, :1062-1075), else the interned branch.
+template <class T>
+__device__ inline u64 parent_tpk(Ctx<T>& c, bool active, const u64 (&ch)[8]) {
+    u32 pres = 0, leafb = 0;
+    bool same = true;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        pres |= u32(ch[i] != 0) << i;
+        leafb |= u32(id_is_leaf(ch[i])) << i;
+        same = same && ch[i] == ch[0];
+    }
+    const bool any = active && pres != 0;
+    const bool collapse = any && same && id_is_leaf(ch[0]);
+    if (any) {
+        if (collapse)
+            c.t.collapsed++;
+        else
+            c.t.branch_calls++;
+    }
+    u64 id = intern_node<T>(c, any && !collapse, ch, leafb, pres);
+    if (collapse) id = ch[0];
+    return any ? id : 0;
+}
+
+template <class T>
+__device__ __forceinline__ void bulk_prologue(Ctx<T>& c, const BulkArgs& a, unsigned char* smem_raw) {
+    WarpSmem<T>* ws = reinterpret_cast<WarpSmem<T>*>(smem_raw);
+    CtaSmem* csp = reinterpret_cast<CtaSmem*>(smem_raw + sizeof(WarpSmem<T>) * WARPS_PER_CTA);
+    smem_init<T>(ws, csp);
+    ctx_init<T>(c, a.in, ws, csp, a.use_free != 0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// blocks: thread per candidate block.
+// ------------------------------------------------------------------------------------------------
+template <class T>
+__global__ void __launch_bounds__(CTA_THREADS, VX_MIN_CTAS) bulk_blocks_kernel(BulkArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    using V = VT<T>;
+    Ctx<T> c;
+    bulk_prologue<T>(c, a, smem_raw);
+    const u32 cnt = a.cnt[0];
+    const u32 stride = gridDim.x * CTA_THREADS;
+    // software pipeline: (block index, set_mask) two iterations ahead, the block's values one ahead
+    const u32 base0 = blockIdx.x * CTA_THREADS + (threadIdx.x & ~31u);
+    u32 blk1 = 0, set1 = 0, blk2 = 0, set2 = 0;
+    typename V::Key vals1 = V::zero();
+    if (base0 + c.lane < cnt) {
+        blk1 = ld_stream_u32(a.first[0] + base0 + c.lane);
+        set1 = ld_stream_u8(a.cm[0] + base0 + c.lane);
+        vals1 = V::load(a.values, blk1);
+    }
+    if (u64(base0) + stride + c.lane < cnt) {
+        blk2 = ld_stream_u32(a.first[0] + base0 + stride + c.lane);
+        set2 = ld_stream_u8(a.cm[0] + base0 + stride + c.lane);
+    }
+    for (u32 base = base0; base < cnt; base += stride) {
+        if (__any_sync(FULL, c.lane == 0 && ld_strong(a.in.error) != ERR_NONE)) break;  // poisoned: host reports it
+        const u32 k = base + c.lane;
+        const bool active = k < cnt;
+        const u32 set = set1;
+        const typename V::Key vals = vals1;
+        blk1 = blk2;
+        set1 = set2;
+        vals1 = V::zero();
+        if (u64(k) + stride < cnt) vals1 = V::load(a.values, blk1);
+        if (u64(k) + 2ull * stride < cnt) {
+            blk2 = ld_stream_u32(a.first[0] + k + 2 * stride);
+            set2 = ld_stream_u8(a.cm[0] + k + 2 * stride);
+        }
+        bool present;
+        u64 id = block_node<T>(c, active, vals, set, V::zero(), 0, &present);
+        if (active) a.ids[0][k] = present ? id : 0;
+    }
+    cta_finish<T>(c);
+}
+
+// ------------------------------------------------------------------------------------------------
+// busy units: one warp per unit, the fused kernel's phase 1 + in-unit phase 2 (vx_build.cuh); the unit's
+// node goes straight into the dense array the upper levels read.
+// ------------------------------------------------------------------------------------------------
+template <class T>
+__global__ void __launch_bounds__(CTA_THREADS, VX_MIN_CTAS) bulk_dense_units_kernel(BulkArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Ctx<T> c;
+    bulk_prologue<T>(c, a, smem_raw);
+    const u32 cnt = a.cnt[3];
+    const u32 upc = a.blocks / UNIT_BLOCKS;
+    const int upc_log = 31 - __clz(upc);
+    const int D = int(a.depth);
+    for (;;) {
+        u32 i = 0;
+        if (c.lane == 0) i = atomicAdd(&a.cnt[4], 1u);
+        i = __shfl_sync(FULL, i, 0);
+        if (i >= cnt) break;
+        if (__any_sync(FULL, c.lane == 0 && ld_strong(a.in.error) != ERR_NONE)) break;
+        const u32 w = a.dense_units[i];
+        const u32 chunk = w >> upc_log, unit = w & (upc - 1);
+        u64 mlo, mhi;
+        load_unit_masks(a.masks + size_t(chunk) * a.blocks * 2, size_t(unit) * UNIT_BLOCKS, UNIT_BLOCKS, c.lane, &mlo, &mhi);
+        const Under u{0, 0, 0, D};
+        const void* cv = (const u8*)a.values + size_t(chunk) * a.blocks * 8 * sizeof(T);
+        const bool some = build_blocks<T, false>(c, mlo, mhi, cv, unit * UNIT_BLOCKS, UNIT_BLOCKS, u);
+        u64 node = 0;
+        bool present = false;
+        if (some) node = reduce_levels<T>(c, UNIT_BLOCKS / 8, D - 2, (unit * UNIT_BLOCKS) >> 3, u, false, &present);
+        if (c.lane == 0) a.dense[0][w] = present ? node : 0;
+    }
+    cta_finish<T>(c);
+}
+
+// ------------------------------------------------------------------------------------------------
+// levels 1 and 2 (sparse): thread per candidate node; children = a run of the level below.
+// ------------------------------------------------------------------------------------------------
+template <class T>
+__global__ void __launch_bounds__(CTA_THREADS, VX_MIN_CTAS) bulk_level_kernel(BulkArgs a, int level) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Ctx<T> c;
+    bulk_prologue<T>(c, a, smem_raw);
+    const u32 cnt = a.cnt[level];
+    const u32* first = a.first[level];
+    const u8* cmv = a.cm[level];
+    const u64* below = a.ids[level - 1];
+    u64* out = a.ids[level];
+    const u32 stride = gridDim.x * CTA_THREADS;
+    for (u32 base = (blockIdx.x * CTA_THREADS + (threadIdx.x & ~31u)); base < cnt; base += stride) {
+        if (__any_sync(FULL, c.lane == 0 && ld_strong(a.in.error) != ERR_NONE)) break;
+        const u32 k = base + c.lane;
+        const bool active = k < cnt;
+        const u32 f = active ? ld_stream_u32(first + k) : 0;
+        const u32 cm = active ? ld_stream_u8(cmv + k) : 0;
+        u64 ch[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            ch[i] = ((cm >> i) & 1) ? ld_stream_u64(below + f + __popc(cm & ((1u << i) - 1))) : 0;
+        u64 id = parent_tpk<T>(c, active, ch);
+        if (active) out[k] = id;
+    }
+    cta_finish<T>(c);
+}
+
+// ------------------------------------------------------------------------------------------------
+// upper levels (dense): thread per node.  from_units: the nodes are the 512-block units and their
+// children come from level 2 through (unit_first, unit_cm); otherwise the children are the eight
+// consecutive nodes of the dense array below.  is_root: the nodes are the trees' roots.
+// ------------------------------------------------------------------------------------------------
+template <class T>
+__global__ void __launch_bounds__(CTA_THREADS, VX_MIN_CTAS)
+bulk_upper_kernel(BulkArgs a, unsigned long long nodes, const u64* below, u64* out, int from_units, int is_root) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Ctx<T> c;
+    bulk_prologue<T>(c, a, smem_raw);
+    const unsigned long long stride = size_t(gridDim.x) * CTA_THREADS;
+    const bool poisoned0 = ld_strong(a.in.error) != ERR_NONE;
+    for (unsigned long long base = (size_t(blockIdx.x) * CTA_THREADS + (threadIdx.x & ~31u)); base < nodes; base += stride) {
+        const unsigned long long k = base + c.lane;
+        const bool active = k < nodes && !poisoned0;
+        u64 ch[8];
+        bool prebuilt = false;
+        u64 pre_id = 0;
+        if (from_units) {
+            u32 cm = active ? ld_stream_u8(a.unit_cm + k) : 0;
+            const u32 f = cm ? ld_stream_u32(a.unit_first + k) : 0;
+            if (cm && f == UNIT_PREBUILT) {  // built by bulk_dense_units_kernel
+                prebuilt = true;
+                pre_id = a.dense[0][k];
+                cm = 0;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                ch[i] = ((cm >> i) & 1) ? ld_stream_u64(a.ids[2] + f + __popc(cm & ((1u << i) - 1))) : 0;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                ulonglong2 q = active ? *reinterpret_cast<const ulonglong2*>(below + k * 8 + 2 * j) : make_ulonglong2(0, 0);
+                ch[2 * j] = q.x;
+                ch[2 * j + 1] = q.y;
+            }
+        }
+        u64 id = parent_tpk<T>(c, active && !prebuilt, ch);
+        if (prebuilt) id = pre_id;
+        if (k < nodes) {
+            if (is_root) {
+                // apply_batch (voxtree.rs:303-328): nothing entered `paths` -> INVALID -> false, root stays EMPTY
+                a.roots[k] = id;
+                if (a.changed) a.changed[k] = id != 0;
+                if (id != 0) atomicAdd(&c.in.refs[id_index(id)], 1u);  // the tree's root handle
+            } else {
+                out[k] = id;
+            }
+        }
+    }
+    cta_finish<T>(c);
+}
+
+}  // namespace vx

@@ -16,6 +16,7 @@
 
 #include "../../include/voxelis_b200.h"
 #include "vx_build.cuh"
+#include "vx_bulk.cuh"
 #include "vx_read.cuh"
 #include "vx_release.cuh"
 #include "vx_dedup.cuh"
@@ -87,6 +88,13 @@ struct vx_interner {
     u32* d_rel_count = nullptr;  // [2]
     void* join = nullptr;        // apply_kernel's join scratch (unit/cube ids + arrival counters)
     size_t join_bytes = 0;
+    void* bulk = nullptr;        // bulk builder's level lists (vx_bulk.cuh), sized for the largest call seen
+    size_t bulk_bytes = 0;
+    // diagnostic: CUDA events between the launches of the last apply (vx_interner_profile_stages)
+    bool prof = false;
+    cudaEvent_t pev[10]{};
+    const char* pname[9]{};
+    int pstages = 0;
     uint64_t free_host = 0;      // entries in the free list
     uint64_t tombs_host = 0;     // deleted table slots since the last rehash
     std::mutex mu;
@@ -165,6 +173,18 @@ int check_device_error(vx_interner* it) {
     return fail(VX_E_CUDA, "device-side internal error");
 }
 
+// stage markers of the last apply (only when profiling is on)
+void prof_begin(vx_interner* it, cudaStream_t s) {
+    if (!it->prof) return;
+    it->pstages = 0;
+    cudaEventRecord(it->pev[0], s);
+}
+void prof_mark(vx_interner* it, cudaStream_t s, const char* name) {
+    if (!it->prof || it->pstages >= 9) return;
+    it->pname[it->pstages] = name;
+    cudaEventRecord(it->pev[++it->pstages], s);
+}
+
 template <class T, bool OLD>
 int launch_apply_t(vx_interner* it, int depth, size_t n, const u8* d_masks, const void* d_values, const u8* d_flags,
                    const int64_t* d_fills, const u64* d_old_roots, u64* d_roots, u8* d_changed, cudaStream_t s) {
@@ -226,8 +246,10 @@ int launch_apply_t(vx_interner* it, int depth, size_t n, const u8* d_masks, cons
     }
     const size_t ctas = (total_runs + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     const size_t grid = std::min<size_t>(ctas, max_ctas);
+    prof_begin(it, s);
     apply_kernel<T, OLD><<<unsigned(grid), CTA_THREADS, smem, s>>>(a);
     CU_TRY(cudaGetLastError());
+    prof_mark(it, s, "apply_kernel");
     if (a.use_free) {
         clamp_free_count_kernel<<<1, 1, 0, s>>>(it->dev);
         CU_TRY(cudaGetLastError());
@@ -235,11 +257,156 @@ int launch_apply_t(vx_interner* it, int depth, size_t n, const u8* d_masks, cons
     return VX_OK;
 }
 
+// ---- bulk builder (vx_bulk.cuh): n fresh trees, no flags, depth >= 4 ------------------------------
+size_t bulk_scratch_bytes(size_t n, size_t blocks) {
+    const size_t nb = n * blocks;
+    size_t need = 256;
+    for (int l = 0; l < 3; ++l) need += ((nb >> (3 * l)) * 13 + 3 * 256);
+    const size_t units = nb / UNIT_BLOCKS;
+    need += units * 5 + 2 * 256 + units * 8 + units + 2 * 256 + units * 4 + 256;
+    return need;
+}
+size_t bulk_max_bytes() {
+    if (const char* e = getenv("VX_BULK_MAX_BYTES")) return size_t(strtoull(e, nullptr, 10));
+    return size_t(8) << 30;
+}
+
+template <class T>
+int launch_bulk_t(vx_interner* it, int depth, size_t n, const u8* d_masks, const void* d_values, u64* d_roots,
+                  u8* d_changed, cudaStream_t s) {
+    const size_t blocks = blocks_for_depth(depth), nb = n * blocks, units = nb / UNIT_BLOCKS;
+    const size_t need = bulk_scratch_bytes(n, blocks);
+    if (need > it->bulk_bytes) {
+        CU_TRY(cudaStreamSynchronize(s));
+        CU_TRY(cudaStreamSynchronize(it->stream));
+        cudaFree(it->bulk);
+        it->bulk = nullptr;
+        it->bulk_bytes = 0;
+        CU_TRY(cudaMalloc(&it->bulk, need));
+        it->bulk_bytes = need;
+    }
+    BulkArgs a{};
+    a.in = it->dev;
+    a.masks = d_masks;
+    a.values = d_values;
+    a.roots = d_roots;
+    a.changed = d_changed;
+    a.units = units;
+    a.n = u32(n);
+    a.depth = u32(depth);
+    a.blocks = u32(blocks);
+    a.dense_min = 128;  // candidate blocks (of 512) from which a unit is built by one warp instead
+    if (const char* e = getenv("VX_BULK_DENSE_MIN")) a.dense_min = u32(atoi(e));
+    a.use_free = it->free_host > 0 ? 1u : 0u;
+    u8* p = (u8*)it->bulk;
+    auto take = [&](size_t bytes) {
+        u8* r = p;
+        p += (bytes + 255) / 256 * 256;
+        return r;
+    };
+    a.cnt = (u32*)take(32);
+    for (int l = 0; l < 3; ++l) {
+        const size_t m = nb >> (3 * l);
+        a.ids[l] = (u64*)take(m * 8);
+        a.first[l] = (u32*)take(m * 4);
+        a.cm[l] = take(m);
+    }
+    a.unit_first = (u32*)take(units * 4);
+    a.unit_cm = take(units);
+    a.dense[0] = (u64*)take(units * 8);
+    a.dense[1] = (u64*)take(units);
+    a.dense_units = (u32*)take(units * 4);
+    prof_begin(it, s);
+    CU_TRY(cudaMemsetAsync(a.cnt, 0, 32, s));
+
+    const size_t smem = apply_smem_bytes<T>();
+    int occ = 0;
+    CU_TRY(cudaFuncSetAttribute(bulk_blocks_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    CU_TRY(cudaFuncSetAttribute(bulk_level_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    CU_TRY(cudaFuncSetAttribute(bulk_upper_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    CU_TRY(cudaFuncSetAttribute(bulk_dense_units_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bulk_level_kernel<T>, CTA_THREADS, smem));
+    const size_t max_ctas = size_t(std::max(occ, 1)) * it->sm_count;
+    auto grid_for = [&](size_t threads) {
+        return unsigned(std::max<size_t>(1, std::min<size_t>((threads + CTA_THREADS - 1) / CTA_THREADS, max_ctas)));
+    };
+    {   // plan: a warp per unit, enough warps to keep the memory system full
+        const size_t ctas = std::min<size_t>((units + 7) / 8, size_t(it->sm_count) * 8);
+        bulk_plan_kernel<<<unsigned(std::max<size_t>(ctas, 1)), 256, 0, s>>>(a);
+        CU_TRY(cudaGetLastError());
+        prof_mark(it, s, "bulk_plan_kernel");
+    }
+    // the sparse levels are sized by device-side counters: launch for the worst case the call allows,
+    // capped at one resident wave (the kernels are grid-stride loops)
+    bulk_blocks_kernel<T><<<grid_for(nb), CTA_THREADS, smem, s>>>(a);
+    CU_TRY(cudaGetLastError());
+    prof_mark(it, s, "bulk_blocks_kernel");
+    bulk_level_kernel<T><<<grid_for(nb >> 3), CTA_THREADS, smem, s>>>(a, 1);
+    CU_TRY(cudaGetLastError());
+    prof_mark(it, s, "bulk_level_kernel[1]");
+    bulk_level_kernel<T><<<grid_for(nb >> 6), CTA_THREADS, smem, s>>>(a, 2);
+    CU_TRY(cudaGetLastError());
+    prof_mark(it, s, "bulk_level_kernel[2]");
+    bulk_dense_units_kernel<T><<<grid_for(units * 32), CTA_THREADS, smem, s>>>(a);
+    CU_TRY(cudaGetLastError());
+    prof_mark(it, s, "bulk_dense_units_kernel");
+    // dense levels: units (depth D-4) up to the roots
+    size_t nodes = units;
+    int pp = 0;
+    const u64* below = nullptr;
+    bool from_units = true;
+    for (;;) {
+        const bool is_root = nodes == n;
+        bulk_upper_kernel<T><<<grid_for(nodes), CTA_THREADS, smem, s>>>(a, nodes, below, a.dense[pp], from_units ? 1 : 0,
+                                                                         is_root ? 1 : 0);
+        CU_TRY(cudaGetLastError());
+        prof_mark(it, s, from_units ? "bulk_upper_kernel[units]" : is_root ? "bulk_upper_kernel[root]" : "bulk_upper_kernel");
+        if (is_root) break;
+        below = a.dense[pp];
+        pp ^= 1;
+        from_units = false;
+        nodes >>= 3;
+    }
+    if (a.use_free) {
+        clamp_free_count_kernel<<<1, 1, 0, s>>>(it->dev);
+        CU_TRY(cudaGetLastError());
+    }
+    return VX_OK;
+}
+
+// Which builder takes a call on fresh trees: "bulk" = level-synchronous (vx_bulk.cuh), "fused" =
+// apply_kernel.  VX_BUILDER=bulk|fused forces one where it is applicable (tests, A/B runs).
+bool use_bulk_builder(int depth, size_t n, const u8* d_flags, const u64* d_old_roots) {
+    if (d_flags || d_old_roots || depth < 4) return false;
+    const size_t nb = n * blocks_for_depth(depth);
+    if (nb >= 0xFFFFFFF0ull) return false;
+    if (const char* e = getenv("VX_BUILDER")) {
+        if (!strcmp(e, "bulk")) return true;
+        if (!strcmp(e, "fused")) return false;
+    }
+    return nb >= (size_t(1) << 18);  // 64 chunks of 32^3: below that one fused launch is cheaper than six
+}
+
 // d_old_roots == nullptr: every tree is fresh (the north-star path).
 int launch_apply(vx_interner* it, int depth, size_t n, const u8* d_masks, const void* d_values, const u8* d_flags,
                  const int64_t* d_fills, u64* d_roots, u8* d_changed, cudaStream_t s,
                  const u64* d_old_roots = nullptr) {
     if (n > 0xFFFFFFFFull) return fail(VX_E_INVALID, "too many chunks in one call");
+    if (n > 0 && use_bulk_builder(depth, n, d_flags, d_old_roots)) {
+        // bound the level lists: very large calls go through in slices (any order gives the same DAG)
+        const size_t blocks = blocks_for_depth(depth);
+        size_t per = n;
+        while (per > 1 && bulk_scratch_bytes(per, blocks) > bulk_max_bytes()) per = (per + 1) / 2;
+        for (size_t o = 0; o < n; o += per) {
+            const size_t m = std::min(per, n - o);
+            const u8* mk = d_masks + o * blocks * 2;
+            const void* vl = (const u8*)d_values + o * blocks * 8 * dtype_size(it->dtype);
+            int rc = it->dtype == VX_U8 ? launch_bulk_t<u8>(it, depth, m, mk, vl, d_roots + o, d_changed ? d_changed + o : nullptr, s)
+                                        : launch_bulk_t<int32_t>(it, depth, m, mk, vl, d_roots + o, d_changed ? d_changed + o : nullptr, s);
+            if (rc != VX_OK) return rc;
+        }
+        return VX_OK;
+    }
     if (it->dtype == VX_U8) {
         if (d_old_roots)
             return launch_apply_t<u8, true>(it, depth, n, d_masks, d_values, d_flags, d_fills, d_old_roots, d_roots,
@@ -466,6 +633,9 @@ void vx_interner_destroy(vx_interner* it) {
     cudaFree(d.leaf_keys);
     cudaFree(d.leaf_ids);
     cudaFree(it->d_scalars);
+    cudaFree(it->bulk);
+    for (auto& e : it->pev)
+        if (e) cudaEventDestroy(e);
     for (int i = 0; i < 2; ++i) {
         cudaFree(it->stage[i]);
         if (it->ev_copied[i]) cudaEventDestroy(it->ev_copied[i]);
@@ -591,6 +761,29 @@ int vx_interner_stats(const vx_interner* it, vx_stats* out) {
 }
 
 // diagnostic counters not part of InternerStats: probe_steps, cache_hits_local
+// Diagnostics (not part of the reference-facing ABI): per-launch device times of the LAST apply call.
+int vx_interner_profile_stages(vx_interner* it, int on) {
+    if (!it) return fail(VX_E_INVALID, "null interner");
+    DeviceGuard g(it->device);
+    if (on && !it->pev[0])
+        for (auto& e : it->pev) CU_TRY(cudaEventCreate(&e));
+    it->prof = on != 0;
+    it->pstages = 0;
+    return VX_OK;
+}
+// ms[i] / names[i] for i < return value (<= 9); synchronises the interner's last launches.
+int vx_interner_stage_ms(vx_interner* it, float ms[9], const char* names[9]) {
+    if (!it || !ms) return fail(VX_E_INVALID, "null argument");
+    if (!it->prof) return 0;
+    DeviceGuard g(it->device);
+    for (int i = 0; i < it->pstages; ++i) {
+        CU_TRY(cudaEventSynchronize(it->pev[i + 1]));
+        CU_TRY(cudaEventElapsedTime(&ms[i], it->pev[i], it->pev[i + 1]));
+        if (names) names[i] = it->pname[i];
+    }
+    return it->pstages;
+}
+
 int vx_interner_debug_counters(const vx_interner* it, uint64_t out[8]) {
     if (!it || !out) return fail(VX_E_INVALID, "null argument");
     Scalars s;
@@ -812,8 +1005,13 @@ static int apply_slab_impl(vx_interner* it, uint8_t depth, size_t n, const uint8
         if (is_device_ptr(flags))
             k_flags = flags;
         else {
-            CU_TRY(cudaMemcpyAsync(d_flags, flags, n, cudaMemcpyHostToDevice, s));
-            k_flags = d_flags;
+            // host flags that only say "has patches" are the default: no per-chunk options needed
+            bool plain = true;
+            for (size_t i = 0; i < n && plain; ++i) plain = flags[i] == VX_FLAG_PATCHES;
+            if (!plain) {
+                CU_TRY(cudaMemcpyAsync(d_flags, flags, n, cudaMemcpyHostToDevice, s));
+                k_flags = d_flags;
+            }
         }
     }
     if (fills) {
