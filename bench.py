@@ -249,7 +249,21 @@ def main():
     value = total_chunks / (step_ms_max * 1e-3)
     kern_ms = float(np.mean(kernel_ms))
 
-    log(f"device-resident: {step_ms_max:.3f} ms/step, kernel {kern_ms:.3f} ms")
+    log(f"device-resident: {step_ms_max:.3f} ms/step, apply {kern_ms:.3f} ms")
+    # per-launch device times of the apply pipeline (CUDA events between its launches, outside the timed
+    # region above: the extra event records would perturb it)
+    it.profile_stages(True)
+    acc = {}
+    prof_steps = 30
+    for _ in range(prof_steps):
+        step_device()
+        for name, ms in it.stage_ms():
+            acc[name] = acc.get(name, 0.0) + ms
+    it.profile_stages(False)
+    stages = {k: v / prof_steps for k, v in acc.items()}
+    launches_per_step = len(stages) + 1               # + the reset's init kernel
+    dom = max(stages, key=stages.get) if stages else "apply_kernel"
+    log("stages: " + ", ".join(f"{k} {v * 1e3:.1f} us" for k, v in stages.items()))
     # ---------------------------------------------------------------- end to end (host batches)
     e2e_value, e2e_ms_max = None, None
     if not args.no_e2e:
@@ -385,7 +399,7 @@ def main():
                        "chunks_per_step_per_gpu": n,
                        "depth": DEPTH, "interner_budget_bytes": BUDGET, "new_nodes_per_step": new_nodes,
                        "l2": "inputs (1.34 GB/step) exceed the 126 MB L2; interner reset every step",
-                       "step": "vx_interner_reset + one vx_apply_batches_device launch",
+                       "step": "vx_interner_reset_async + one vx_apply_batches_device call",
                        "per_step_counters": dbg},
             "e2e": {"value": e2e_value, "unit": "chunks/s", "ms_per_step": e2e_ms_max,
                     # masks are DMA-copied; values stay in pinned host memory and the kernel reads, over PCIe,
@@ -395,9 +409,14 @@ def main():
                     "d2h_bytes_per_step": int(n * 9),
                     "path": "vx_apply_batches_slab on pinned host batches (masks H2D by copy engine in slabs, "
                             "values zero-copy), roots + changed flags D2H"},
-            "gpu_launches": args.steps,
+            "gpu_launches": args.steps * launches_per_step,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "apply_kernel<u8,false>",
+                         "traffic": traffic, "peak_source": peak_src,
+                         # the path is a pipeline of dependent launches (vx_bulk.cuh): the roofline is taken over
+                         # the whole apply call, the per-launch times are listed beside it
+                         "kernel": "apply call = " + " + ".join(stages) if stages else "apply_kernel<u8,false>",
+                         "stages_ms": stages, "dominant_stage": dom,
+                         "dominant_share": (stages[dom] / sum(stages.values())) if stages else 1.0,
                          "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": algo_bytes,
                          "compulsory_bytes_per_launch": compulsory,
                          "achieved_compulsory": compulsory / (kern_ms * 1e-3) / 1e9,

@@ -4,12 +4,24 @@ Joins the SASS rows of `ncu --page source --csv` (in address order) with nvdisas
 import csv, re, subprocess, sys, tempfile, os, collections, glob
 rep, lib, kname = sys.argv[1:4]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + os.environ.get("NCU_ARGS", "").split(), capture_output=True, text=True).stdout  # NCU_ARGS e.g. "-k regex:level -s 0 -c 1" selects one launch
 rows = list(csv.reader(out.splitlines()))
 hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[hdr_i]
 col = {h: i for i, h in enumerate(hdr)}
 sass = rows[hdr_i + 1:]
+# several launches in the selection: rows restart at a lower address; NCU_CHUNK picks one (default 0)
+chunks, curc, prev = [], [], -1
+for r in sass:
+    try:
+        ad = int(r[0], 16) if not r[0].isdigit() else int(r[0])
+    except (ValueError, IndexError):
+        continue
+    if ad < prev:
+        chunks.append(curc); curc = []
+    curc.append(r); prev = ad
+chunks.append(curc)
+sass = chunks[int(os.environ.get("NCU_CHUNK", "0"))]
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, capture_output=True)
 cubin = glob.glob(tmp + "/*.cubin")[0]

@@ -9,7 +9,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB = os.path.join(_HERE, "libvoxelis_b200.so")
 SOURCES = ["vx_capi.cu"]
-HEADERS = ["vx_device.cuh", "vx_build.cuh", "vx_read.cuh", "vx_release.cuh", os.path.join("..", "..", "include", "voxelis_b200.h")]
+HEADERS = ["vx_device.cuh", "vx_build.cuh", "vx_bulk.cuh", "vx_read.cuh", "vx_release.cuh", "vx_dedup.cuh",
+           os.path.join("..", "..", "include", "voxelis_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 
@@ -32,7 +33,8 @@ def is_stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB
-    cmd = [_nvcc(), *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-o", LIB,
+    extra = os.environ.get("VX_NVCC_EXTRA", "").split()     # e.g. -DVX_MIN_CTAS=4 for A/B builds
+    cmd = [_nvcc(), *NVCC_FLAGS, *extra, *(["-Xptxas", "-v"] if verbose else []), "-o", LIB,
            *[os.path.join(CSRC, s) for s in SOURCES]]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:

@@ -334,12 +334,16 @@ __device__ inline u64 parent_tpk(Ctx<T>& c, bool active, const u64 (&ch)[8]) {
     return any ? id : 0;
 }
 
+// The level kernels are launched with programmatic stream serialization: their CTAs may start (and run
+// this prologue, which touches only shared memory and the argument block) while the previous launch is
+// draining; griddepcontrol.wait then blocks until that launch has completed and its writes are visible.
 template <class T>
 __device__ __forceinline__ void bulk_prologue(Ctx<T>& c, const BulkArgs& a, unsigned char* smem_raw) {
     WarpSmem<T>* ws = reinterpret_cast<WarpSmem<T>*>(smem_raw);
     CtaSmem* csp = reinterpret_cast<CtaSmem*>(smem_raw + sizeof(WarpSmem<T>) * WARPS_PER_CTA);
     smem_init<T>(ws, csp);
     ctx_init<T>(c, a.in, ws, csp, a.use_free != 0);
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -271,6 +271,24 @@ size_t bulk_max_bytes() {
     return size_t(8) << 30;
 }
 
+// Launch that may overlap its prologue with the tail of the previous kernel in the stream (the kernel
+// itself waits with griddepcontrol.wait before it reads anything that kernel wrote).
+template <class... P, class... A>
+cudaError_t launch_chained(void (*kernel)(P...), unsigned grid, unsigned block, size_t smem, cudaStream_t s, bool chained,
+                           A... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = chained ? 1 : 0;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, P(args)...);
+}
+
 template <class T>
 int launch_bulk_t(vx_interner* it, int depth, size_t n, const u8* d_masks, const void* d_values, u64* d_roots,
                   u8* d_changed, cudaStream_t s) {
@@ -331,24 +349,23 @@ int launch_bulk_t(vx_interner* it, int depth, size_t n, const u8* d_masks, const
         return unsigned(std::max<size_t>(1, std::min<size_t>((threads + CTA_THREADS - 1) / CTA_THREADS, max_ctas)));
     };
     {   // plan: a warp per unit, enough warps to keep the memory system full
-        const size_t ctas = std::min<size_t>((units + 7) / 8, size_t(it->sm_count) * 8);
+        // ~4 units per warp: short CTAs that the hardware scheduler balances (units differ a lot in cost)
+        static const size_t upw = getenv("VX_PLAN_UPW") ? size_t(atoi(getenv("VX_PLAN_UPW"))) : 4;
+        const size_t ctas = std::max<size_t>((units + 8 * upw - 1) / (8 * upw), std::min<size_t>((units + 7) / 8, size_t(it->sm_count) * 8));
         bulk_plan_kernel<<<unsigned(std::max<size_t>(ctas, 1)), 256, 0, s>>>(a);
         CU_TRY(cudaGetLastError());
         prof_mark(it, s, "bulk_plan_kernel");
     }
     // the sparse levels are sized by device-side counters: launch for the worst case the call allows,
     // capped at one resident wave (the kernels are grid-stride loops)
-    bulk_blocks_kernel<T><<<grid_for(nb), CTA_THREADS, smem, s>>>(a);
-    CU_TRY(cudaGetLastError());
+    static const bool chained = getenv("VX_BULK_NO_PDL") == nullptr;
+    CU_TRY(launch_chained(bulk_blocks_kernel<T>, grid_for(nb), CTA_THREADS, smem, s, chained, a));
     prof_mark(it, s, "bulk_blocks_kernel");
-    bulk_level_kernel<T><<<grid_for(nb >> 3), CTA_THREADS, smem, s>>>(a, 1);
-    CU_TRY(cudaGetLastError());
+    CU_TRY(launch_chained(bulk_level_kernel<T>, grid_for(nb >> 3), CTA_THREADS, smem, s, chained, a, 1));
     prof_mark(it, s, "bulk_level_kernel[1]");
-    bulk_level_kernel<T><<<grid_for(nb >> 6), CTA_THREADS, smem, s>>>(a, 2);
-    CU_TRY(cudaGetLastError());
+    CU_TRY(launch_chained(bulk_level_kernel<T>, grid_for(nb >> 6), CTA_THREADS, smem, s, chained, a, 2));
     prof_mark(it, s, "bulk_level_kernel[2]");
-    bulk_dense_units_kernel<T><<<grid_for(units * 32), CTA_THREADS, smem, s>>>(a);
-    CU_TRY(cudaGetLastError());
+    CU_TRY(launch_chained(bulk_dense_units_kernel<T>, grid_for(units * 32), CTA_THREADS, smem, s, chained, a));
     prof_mark(it, s, "bulk_dense_units_kernel");
     // dense levels: units (depth D-4) up to the roots
     size_t nodes = units;
@@ -357,9 +374,8 @@ int launch_bulk_t(vx_interner* it, int depth, size_t n, const u8* d_masks, const
     bool from_units = true;
     for (;;) {
         const bool is_root = nodes == n;
-        bulk_upper_kernel<T><<<grid_for(nodes), CTA_THREADS, smem, s>>>(a, nodes, below, a.dense[pp], from_units ? 1 : 0,
-                                                                         is_root ? 1 : 0);
-        CU_TRY(cudaGetLastError());
+        CU_TRY(launch_chained(bulk_upper_kernel<T>, grid_for(nodes), CTA_THREADS, smem, s, chained, a,
+                              (unsigned long long)nodes, below, a.dense[pp], from_units ? 1 : 0, is_root ? 1 : 0));
         prof_mark(it, s, from_units ? "bulk_upper_kernel[units]" : is_root ? "bulk_upper_kernel[root]" : "bulk_upper_kernel");
         if (is_root) break;
         below = a.dense[pp];
