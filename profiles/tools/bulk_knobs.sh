@@ -1,9 +1,11 @@
-for cfg in "" "VX_BULK_NO_PDL=1" "VX_PLAN_UPW=28" "VX_PLAN_UPW=1" "VX_PLAN_UPW=2" "VX_BULK_DENSE_MIN=64" "VX_BULK_DENSE_MIN=256"; do
-  echo "== $cfg"; env $cfg timeout 200 python profiles/tools/bulk_ab.py perlin 2>&1 | python -c "
+run() { echo "== $*"; env "$@" timeout 200 python profiles/tools/bulk_ab.py perlin 2>&1 | python -c "
 import sys, json
 for l in sys.stdin:
     if l.startswith('perlin'):
-        d = json.loads(l.split(' ',1)[1]); print(d['bulk']['ms'], d['bulk']['stages'])
+        d = json.loads(l.split(' ',1)[1]); print(round(d['bulk']['ms'],4), d['bulk']['nodes'], [(a.replace('bulk_','').replace('_kernel',''), b) for a,b in d['bulk']['stages']])
     elif 'Error' in l: print(l)
-"
-done
+"; }
+run A=1
+run VX_LIB=/root/repo/voxelis_b200/libvoxelis_b200_c4.so
+run VX_PLAN_UPW=4
+run A=2

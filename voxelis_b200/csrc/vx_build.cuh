@@ -232,10 +232,14 @@ struct WarpSmem {
     u32 lkey[sizeof(T) == 1 ? 1 : LC];  // wide T only: value -> leaf id
     u64 lid[sizeof(T) == 1 ? 1 : LC];
 };
+constexpr int RH = 512;  // entries of the CTA's in-degree combining table
 struct CtaSmem {
     u64 leaf[256];     // u8: value -> leaf id (lazy copy of InternerDev::leaf_u8)
     u32 leafref[256];  // u8: pending in-degree increments of leaves
-    u32 warps_done;    // exit arrival counter (the last warp flushes leafref)
+    u32 rkey[RH];      // pending in-degree increments of other children: node index + 1 (0 = free) ...
+    u32 rcnt[RH];      // ... and how many; hot children (flat ground, solid rock) would otherwise take
+                       // thousands of same-address RED.ADDs that serialise in one L2 slice
+    u32 warps_done;    // exit arrival counter (the last warp flushes leafref / rkey,rcnt)
 };
 
 struct Tally {  // per-lane statistics, reduced once at kernel exit
@@ -249,8 +253,31 @@ struct Ctx {
     CtaSmem* cs;
     int lane, li, gs;  // lane, lane within 8-group, first lane of my group
     bool use_free;     // the free list holds recycled indices: pop them before next_index (macros.rs:1-41)
+    bool tpk_only;     // block level: always thread-per-key (bulk builder); the fused kernel uses the hybrid
     Tally t;
 };
+
+// inc_ref of a child of a NEW node (interner/mod.rs:301-330 via inc_all_child_refs): combined per CTA in
+// shared memory, flushed once at kernel exit; falls back to the global counter when the two probed
+// entries belong to other nodes.  Nothing reads refs while an apply kernel runs.
+template <class T>
+__device__ __forceinline__ void ref_add(Ctx<T>& c, u32 idx) {
+    u32 h = (idx * 0x9E3779B1u) >> 23;  // RH = 512
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        u32 k = ((volatile u32*)c.cs->rkey)[h];
+        if (k == 0) {
+            k = atomicCAS(&c.cs->rkey[h], 0u, idx + 1);
+            if (k == 0) k = idx + 1;
+        }
+        if (k == idx + 1) {
+            atomicAdd(&c.cs->rcnt[h], 1u);
+            return;
+        }
+        h = (h + 1) & (RH - 1);
+    }
+    atomicAdd(&c.in.refs[idx], 1u);
+}
 
 // get_next_index_macro! (interner/macros.rs:1-41) for one node: recycled index first (LIFO), else
 // next_index++.  `*gen` = generation to stamp into the BlockId.  Indices >= capacity mean "Out of memory".
@@ -295,7 +322,7 @@ __device__ inline u64 leaf_get(Ctx<u8>& c, u32 v, bool need) {
                     } else {
                         leaf_payload<u8>(c.in, idx, v);
                         id = id_leaf((u64(gen) << 32) | idx);
-                        fence_gpu();
+                        fence_release_gpu();
                         st_strong(&c.in.leaf_u8[v], id);
                         sts_relaxed(&c.cs->leaf[v], id);
                         c.t.leaf_miss++;
@@ -339,7 +366,7 @@ __device__ inline u64 leaf_get(Ctx<int32_t>& c, u32 v, bool need) {
                     } else {
                         leaf_payload<int32_t>(c.in, idx, v);
                         id = id_leaf((u64(gen) << 32) | idx);
-                        fence_gpu();
+                        fence_release_gpu();
                         st_strong(&c.in.leaf_ids[s], id);
                         c.t.leaf_miss++;
                         miss = false;
@@ -514,7 +541,7 @@ u64 intern_branch(Ctx<T>& c, bool need, u64 child, bool block_level, u32 cval) {
             __syncwarp();
             if (mine) {
                 if (li == 0) {
-                    fence_gpu();
+                    fence_release_gpu();
                     // out of memory: hand the slot back (the interner is poisoned, results are discarded)
                     st_strong(&in.slots[size_t(bucket) * 8 + ek], oom ? u64(0) : ((u64(fp) << 47) | genidx));
                 }
@@ -731,7 +758,7 @@ __device__ inline u64 intern_block(Ctx<T>& c, bool need, const typename VT<T>::K
                     in.hashes[idx] = h;
                     c.t.branch_miss++;
                 }
-                fence_gpu();
+                fence_release_gpu();
                 // out of memory: hand the slot back (the interner is poisoned, results are discarded)
                 st_strong(&in.slots[size_t(bucket) * 8 + ek], oom ? u64(0) : ((u64(fp) << 47) | genidx));
                 result = oom ? 0 : id_branch(genidx, nzm, nzm);
@@ -844,7 +871,7 @@ __device__ inline u64 block_node(Ctx<T>& c, bool active, typename VT<T>::Key val
         const bool leader = pend && leader_lane == lane;
         const u32 lmask = __ballot_sync(FULL, leader);
         u64 bid;
-        if (__popc(lmask) > 4) {
+        if (c.tpk_only || __popc(lmask) > 4) {
             bid = intern_block<T>(c, leader, eff);  // many distinct misses: every leader probes on its own
         } else {
             // a few misses: one 8-lane group per key (group g takes the g-th leader)
@@ -1086,6 +1113,7 @@ template <class T>
 __device__ __forceinline__ void ctx_init(Ctx<T>& c, const InternerDev& in, WarpSmem<T>* ws, CtaSmem* cs, bool use_free) {
     c.in = in;
     c.use_free = use_free;
+    c.tpk_only = false;
     c.lane = threadIdx.x & 31;
     c.li = c.lane & 7;
     c.gs = c.lane & 24;
@@ -1127,7 +1155,7 @@ __device__ inline void cta_finish(Ctx<T>& c) {
         if (t.probes) atomicAdd(&k->probe_steps, (ull)t.probes);
         if (t.local) atomicAdd(&k->cache_hits_local, (ull)t.local);
     }
-    if (sizeof(T) == 1) {
+    {
         u32 arrived = 0;
         __syncwarp();
         if (c.lane == 0) {
@@ -1137,9 +1165,15 @@ __device__ inline void cta_finish(Ctx<T>& c) {
         arrived = __shfl_sync(FULL, arrived, 0);
         if (arrived == WARPS_PER_CTA - 1) {
             __threadfence_block();
-            for (u32 v = c.lane; v < 256; v += 32) {
-                u32 n = ((volatile u32*)c.cs->leafref)[v];
-                if (n) atomicAdd(&c.in.refs[id_index(lds_relaxed(&c.cs->leaf[v]))], n);
+            if (sizeof(T) == 1) {
+                for (u32 v = c.lane; v < 256; v += 32) {
+                    u32 n = ((volatile u32*)c.cs->leafref)[v];
+                    if (n) atomicAdd(&c.in.refs[id_index(lds_relaxed(&c.cs->leaf[v]))], n);
+                }
+            }
+            for (u32 i = c.lane; i < RH; i += 32) {
+                u32 k = ((volatile u32*)c.cs->rkey)[i], n = ((volatile u32*)c.cs->rcnt)[i];
+                if (k != 0 && n != 0) atomicAdd(&c.in.refs[k - 1], n);
             }
         }
     }

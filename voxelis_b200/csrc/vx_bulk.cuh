@@ -46,8 +46,12 @@ struct BulkArgs {
     u32 depth;
     u32 blocks;       // B
     u32 dense_min;
+    u32 tpk_only;
     u32 use_free;
 };
+#ifndef VX_BULK_MIN_CTAS
+#define VX_BULK_MIN_CTAS 3
+#endif
 constexpr u32 UNIT_PREBUILT = 0xFFFFFFFFu;  // unit_first marker: the unit's node is already in dense[0]
 
 __device__ __forceinline__ u32 ld_stream_u32(const void* p) {
@@ -61,6 +65,13 @@ __device__ __forceinline__ u32 ld_stream_u8(const void* p) {
     return v;
 }
 
+// 32-byte streaming load (sm_100: LDG.256): one fully coalesced 1 KiB request per warp
+__device__ __forceinline__ void ld_stream_v8(const void* p, uint4* a, uint4* b) {
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a->x), "=r"(a->y), "=r"(a->z), "=r"(a->w), "=r"(b->x), "=r"(b->y), "=r"(b->z), "=r"(b->w)
+                 : "l"(p));
+}
+
 // ------------------------------------------------------------------------------------------------
 // plan: one warp per unit of 512 Morton-consecutive blocks (lane = 16 blocks = 32 B of masks).
 // ------------------------------------------------------------------------------------------------
@@ -68,18 +79,26 @@ __global__ void __launch_bounds__(256) bulk_plan_kernel(BulkArgs a) {
     const u32 lane = threadIdx.x & 31;
     const unsigned long long warp = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const unsigned long long nwarps = (size_t(gridDim.x) * blockDim.x) >> 5;
-    uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;
-    if (warp < a.units) {
-        const uint4* mp = (const uint4*)(a.masks + warp * (UNIT_BLOCKS * 2)) + lane * 2;
-        n0 = ld_stream_v4(mp);
-        n1 = ld_stream_v4(mp + 1);
+    // register queue: the masks of the next PLAN_AHEAD units of this warp are in flight while one is planned
+    constexpr int PLAN_AHEAD = 1;
+    uint4 qa[PLAN_AHEAD], qb[PLAN_AHEAD];
+#pragma unroll
+    for (int d = 0; d < PLAN_AHEAD; ++d) {
+        qa[d] = qb[d] = make_uint4(0, 0, 0, 0);
+        if (warp + d * nwarps < a.units) {
+            ld_stream_v8(a.masks + (warp + d * nwarps) * (UNIT_BLOCKS * 2) + lane * 32, &qa[d], &qb[d]);
+        }
     }
     for (unsigned long long w = warp; w < a.units; w += nwarps) {
-        const uint4 q0 = n0, q1 = n1;
-        if (w + nwarps < a.units) {  // the next unit's masks are in flight while this one is planned
-            const uint4* mp = (const uint4*)(a.masks + (w + nwarps) * (UNIT_BLOCKS * 2)) + lane * 2;
-            n0 = ld_stream_v4(mp);
-            n1 = ld_stream_v4(mp + 1);
+        const uint4 q0 = qa[0], q1 = qb[0];
+#pragma unroll
+        for (int d = 0; d + 1 < PLAN_AHEAD; ++d) {
+            qa[d] = qa[d + 1];
+            qb[d] = qb[d + 1];
+        }
+        if (w + PLAN_AHEAD * nwarps < a.units) {
+            ld_stream_v8(a.masks + (w + PLAN_AHEAD * nwarps) * (UNIT_BLOCKS * 2) + lane * 32, &qa[PLAN_AHEAD - 1],
+                         &qb[PLAN_AHEAD - 1]);
         }
         // set_mask bytes (even positions; clear_mask is never read by the reference)
         const u64 sa = u64(__byte_perm(q0.x, q0.y, 0x6420)) | (u64(__byte_perm(q0.z, q0.w, 0x6420)) << 32);
@@ -158,6 +177,33 @@ __global__ void __launch_bounds__(256) bulk_plan_kernel(BulkArgs a) {
     }
 }
 
+// Values of the eight children of a key (leaf value / branch LOD value; 0 for EMPTY), loaded with plain
+// cached loads: the children were created by earlier launches.  u8 packs them into one register pair.
+template <class T>
+struct ChildValues;
+template <>
+struct ChildValues<u8> {
+    u64 w;
+    __device__ __forceinline__ void load(const InternerDev& in, const u64 (&ch)[8], bool need) {
+        u32 b[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) b[i] = (need && ch[i] != 0) ? u32(((const u8*)in.values)[id_index(ch[i])]) : 0;
+        w = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w |= u64(b[i]) << (8 * i);
+    }
+    __device__ __forceinline__ u32 get(int i) const { return u32(w >> (8 * i)) & 0xFF; }
+};
+template <>
+struct ChildValues<int32_t> {
+    u32 v[8];
+    __device__ __forceinline__ void load(const InternerDev& in, const u64 (&ch)[8], bool need) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = (need && ch[i] != 0) ? ((const u32*)in.values)[id_index(ch[i])] : 0;
+    }
+    __device__ __forceinline__ u32 get(int i) const { return v[i]; }
+};
+
 // ------------------------------------------------------------------------------------------------
 // get_or_create_branch (interner/mod.rs:716-829), thread-per-key with the eight child ids in
 // registers — the probing protocol of intern_block with the children given directly.
@@ -187,6 +233,11 @@ __device__ inline u64 intern_node(Ctx<T>& c, bool need, const u64 (&ch)[8], u32 
         }
     }
     const bool went_global = !done;
+    // The child values (needed for the LOD value if the node turns out to be new) are requested together
+    // with the first bucket, not after the claim: in a warp step some lane almost always creates a node,
+    // so the step would pay that round trip anyway.  Children were published by earlier launches.
+    ChildValues<T> cv;
+    cv.load(in, ch, went_global);
     u32 skip = 0;
     int guard = 0;
     while (__any_sync(FULL, !done)) {
@@ -269,7 +320,7 @@ __device__ inline u64 intern_node(Ctx<T>& c, bool need, const u64 (&ch)[8], u32 
                     // LOD value = mode of the child values (core/voxel.rs:96-141); in-degree of every child
                     u32 v[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = ch[i] != 0 ? child_value<T>(in, ch[i]) : 0;
+                    for (int i = 0; i < 8; ++i) v[i] = cv.get(i);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         if (ch[i] != 0) {
@@ -277,7 +328,7 @@ __device__ inline u64 intern_node(Ctx<T>& c, bool need, const u64 (&ch)[8], u32 
                                 sts_relaxed(&c.cs->leaf[v[i]], ch[i]);  // cta_finish flushes through this table
                                 atomicAdd(&c.cs->leafref[v[i]], 1u);
                             } else {
-                                atomicAdd(&in.refs[id_index(ch[i])], 1u);
+                                ref_add(c, id_index(ch[i]));
                             }
                         }
                     }
@@ -285,7 +336,7 @@ __device__ inline u64 intern_node(Ctx<T>& c, bool need, const u64 (&ch)[8], u32 
                     in.hashes[idx] = h;
                     c.t.branch_miss++;
                 }
-                fence_gpu();
+                fence_release_gpu();
                 // out of memory: hand the slot back (the interner is poisoned, results are discarded)
                 st_strong(&in.slots[size_t(bucket) * 8 + ek], oom ? u64(0) : ((u64(fp) << 47) | genidx));
                 result = oom ? 0 : id_branch(genidx, types, mask);
@@ -350,11 +401,12 @@ __device__ __forceinline__ void bulk_prologue(Ctx<T>& c, const BulkArgs& a, unsi
 // blocks: thread per candidate block.
 // ------------------------------------------------------------------------------------------------
 template <class T>
-__global__ void __launch_bounds__(CTA_THREADS, VX_MIN_CTAS) bulk_blocks_kernel(BulkArgs a) {
+__global__ void __launch_bounds__(CTA_THREADS, VX_BULK_MIN_CTAS) bulk_blocks_kernel(BulkArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using V = VT<T>;
     Ctx<T> c;
     bulk_prologue<T>(c, a, smem_raw);
+    c.tpk_only = a.tpk_only != 0;
     const u32 cnt = a.cnt[0];
     const u32 stride = gridDim.x * CTA_THREADS;
     // software pipeline: (block index, set_mask) two iterations ahead, the block's values one ahead
@@ -371,7 +423,9 @@ __global__ void __launch_bounds__(CTA_THREADS, VX_MIN_CTAS) bulk_blocks_kernel(B
         set2 = ld_stream_u8(a.cm[0] + base0 + stride + c.lane);
     }
     for (u32 base = base0; base < cnt; base += stride) {
-        if (__any_sync(FULL, c.lane == 0 && ld_strong(a.in.error) != ERR_NONE)) break;  // poisoned: host reports it
+        // poisoned interner: stop (the host reports it).  The word is requested here and tested at the end
+        // of the iteration, so its round trip hides behind the work
+        const u32 errw = c.lane == 0 ? ld_strong(a.in.error) : u32(ERR_NONE);
         const u32 k = base + c.lane;
         const bool active = k < cnt;
         const u32 set = set1;
@@ -387,6 +441,7 @@ __global__ void __launch_bounds__(CTA_THREADS, VX_MIN_CTAS) bulk_blocks_kernel(B
         bool present;
         u64 id = block_node<T>(c, active, vals, set, V::zero(), 0, &present);
         if (active) a.ids[0][k] = present ? id : 0;
+        if (__any_sync(FULL, errw != ERR_NONE)) break;
     }
     cta_finish<T>(c);
 }
@@ -429,7 +484,7 @@ __global__ void __launch_bounds__(CTA_THREADS, VX_MIN_CTAS) bulk_dense_units_ker
 // levels 1 and 2 (sparse): thread per candidate node; children = a run of the level below.
 // ------------------------------------------------------------------------------------------------
 template <class T>
-__global__ void __launch_bounds__(CTA_THREADS, VX_MIN_CTAS) bulk_level_kernel(BulkArgs a, int level) {
+__global__ void __launch_bounds__(CTA_THREADS, VX_BULK_MIN_CTAS) bulk_level_kernel(BulkArgs a, int level) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Ctx<T> c;
     bulk_prologue<T>(c, a, smem_raw);
@@ -440,7 +495,7 @@ __global__ void __launch_bounds__(CTA_THREADS, VX_MIN_CTAS) bulk_level_kernel(Bu
     u64* out = a.ids[level];
     const u32 stride = gridDim.x * CTA_THREADS;
     for (u32 base = (blockIdx.x * CTA_THREADS + (threadIdx.x & ~31u)); base < cnt; base += stride) {
-        if (__any_sync(FULL, c.lane == 0 && ld_strong(a.in.error) != ERR_NONE)) break;
+        const u32 errw = c.lane == 0 ? ld_strong(a.in.error) : u32(ERR_NONE);
         const u32 k = base + c.lane;
         const bool active = k < cnt;
         const u32 f = active ? ld_stream_u32(first + k) : 0;
@@ -451,6 +506,7 @@ __global__ void __launch_bounds__(CTA_THREADS, VX_MIN_CTAS) bulk_level_kernel(Bu
             ch[i] = ((cm >> i) & 1) ? ld_stream_u64(below + f + __popc(cm & ((1u << i) - 1))) : 0;
         u64 id = parent_tpk<T>(c, active, ch);
         if (active) out[k] = id;
+        if (__any_sync(FULL, errw != ERR_NONE)) break;
     }
     cta_finish<T>(c);
 }
@@ -461,7 +517,7 @@ __global__ void __launch_bounds__(CTA_THREADS, VX_MIN_CTAS) bulk_level_kernel(Bu
 // consecutive nodes of the dense array below.  is_root: the nodes are the trees' roots.
 // ------------------------------------------------------------------------------------------------
 template <class T>
-__global__ void __launch_bounds__(CTA_THREADS, VX_MIN_CTAS)
+__global__ void __launch_bounds__(CTA_THREADS, VX_BULK_MIN_CTAS)
 bulk_upper_kernel(BulkArgs a, unsigned long long nodes, const u64* below, u64* out, int from_units, int is_root) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Ctx<T> c;

@@ -315,6 +315,7 @@ int launch_bulk_t(vx_interner* it, int depth, size_t n, const u8* d_masks, const
     a.blocks = u32(blocks);
     a.dense_min = 128;  // candidate blocks (of 512) from which a unit is built by one warp instead
     if (const char* e = getenv("VX_BULK_DENSE_MIN")) a.dense_min = u32(atoi(e));
+    a.tpk_only = getenv("VX_BULK_TPK") ? u32(atoi(getenv("VX_BULK_TPK"))) : 0u;
     a.use_free = it->free_host > 0 ? 1u : 0u;
     u8* p = (u8*)it->bulk;
     auto take = [&](size_t bytes) {
@@ -349,8 +350,8 @@ int launch_bulk_t(vx_interner* it, int depth, size_t n, const u8* d_masks, const
         return unsigned(std::max<size_t>(1, std::min<size_t>((threads + CTA_THREADS - 1) / CTA_THREADS, max_ctas)));
     };
     {   // plan: a warp per unit, enough warps to keep the memory system full
-        // ~4 units per warp: short CTAs that the hardware scheduler balances (units differ a lot in cost)
-        static const size_t upw = getenv("VX_PLAN_UPW") ? size_t(atoi(getenv("VX_PLAN_UPW"))) : 4;
+        // ~8 units per warp: short CTAs that the hardware scheduler balances (units differ a lot in cost)
+        static const size_t upw = getenv("VX_PLAN_UPW") ? size_t(atoi(getenv("VX_PLAN_UPW"))) : 8;
         const size_t ctas = std::max<size_t>((units + 8 * upw - 1) / (8 * upw), std::min<size_t>((units + 7) / 8, size_t(it->sm_count) * 8));
         bulk_plan_kernel<<<unsigned(std::max<size_t>(ctas, 1)), 256, 0, s>>>(a);
         CU_TRY(cudaGetLastError());
@@ -392,8 +393,9 @@ int launch_bulk_t(vx_interner* it, int depth, size_t n, const u8* d_masks, const
 
 // Which builder takes a call on fresh trees: "bulk" = level-synchronous (vx_bulk.cuh), "fused" =
 // apply_kernel.  VX_BUILDER=bulk|fused forces one where it is applicable (tests, A/B runs).
-bool use_bulk_builder(int depth, size_t n, const u8* d_flags, const u64* d_old_roots) {
+bool use_bulk_builder(int depth, size_t n, const u8* d_masks, const u8* d_flags, const u64* d_old_roots) {
     if (d_flags || d_old_roots || depth < 4) return false;
+    if (reinterpret_cast<uintptr_t>(d_masks) & 31) return false;  // the plan kernel reads 32-byte vectors
     const size_t nb = n * blocks_for_depth(depth);
     if (nb >= 0xFFFFFFF0ull) return false;
     if (const char* e = getenv("VX_BUILDER")) {
@@ -408,7 +410,7 @@ int launch_apply(vx_interner* it, int depth, size_t n, const u8* d_masks, const 
                  const int64_t* d_fills, u64* d_roots, u8* d_changed, cudaStream_t s,
                  const u64* d_old_roots = nullptr) {
     if (n > 0xFFFFFFFFull) return fail(VX_E_INVALID, "too many chunks in one call");
-    if (n > 0 && use_bulk_builder(depth, n, d_flags, d_old_roots)) {
+    if (n > 0 && use_bulk_builder(depth, n, d_masks, d_flags, d_old_roots)) {
         // bound the level lists: very large calls go through in slices (any order gives the same DAG)
         const size_t blocks = blocks_for_depth(depth);
         size_t per = n;

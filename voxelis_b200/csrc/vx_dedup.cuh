@@ -144,7 +144,7 @@ __global__ void intern_records_kernel(InternerDev in, u32 n, const u64* records,
                                 ((u8*)in.values)[idx] = u8(v);
                                 in.hashes[idx] = leaf_hash(v);
                                 result = id_leaf(u64(idx));
-                                fence_gpu();
+                                fence_release_gpu();
                                 st_strong(keyp, result);
                                 atomicAdd(created, 1u);
                             }
@@ -166,7 +166,7 @@ __global__ void intern_records_kernel(InternerDev in, u32 n, const u64* records,
                                 ((u32*)in.values)[idx] = v;
                                 in.hashes[idx] = leaf_hash(v);
                                 result = id_leaf(u64(idx));
-                                fence_gpu();
+                                fence_release_gpu();
                                 st_strong(&in.leaf_ids[s], result);
                                 atomicAdd(created, 1u);
                             }
@@ -277,7 +277,7 @@ __global__ void intern_records_kernel(InternerDev in, u32 n, const u64* records,
                     in.hashes[idx] = h;
                     atomicAdd(created, 1u);
                 }
-                fence_gpu();
+                fence_release_gpu();
                 st_strong(&in.slots[size_t(bucket) * 8 + ek], oom ? u64(0) : ((u64(fp) << 47) | u64(idx)));
                 result = oom ? 0 : id_branch(u64(idx), types, mask);
                 done = true;

@@ -115,6 +115,9 @@ __device__ __forceinline__ void st_strong(u32* p, u32 v) {
     asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void fence_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+// Publisher side only: orders the payload stores before the slot store.  Unlike fence.acq_rel it does
+// not invalidate the SM's L1 (no CCTL.IVALL): the publisher acquires nothing.
+__device__ __forceinline__ void fence_release_gpu() { asm volatile("fence.release.gpu;" ::: "memory"); }
 // CTA-shared memo words (CtaSmem::leaf) are read and written by every warp of the CTA with no barrier
 // in between: all writers store the same value and a reader takes either 0 (-> global table) or that
 // value.  Relaxed .cta accesses make those morally-strong operations under the PTX memory model, so the
