@@ -396,6 +396,17 @@ __device__ __forceinline__ void bulk_prologue(Ctx<T>& c, const BulkArgs& a, unsi
     ctx_init<T>(c, a.in, ws, csp, a.use_free != 0);
     asm volatile("griddepcontrol.wait;" ::: "memory");
 }
+// CTAs of a list kernel that have no element to process leave right after the prologue (the grids are
+// sized for the worst case the call allows; the real counts only exist on the device).
+__device__ __forceinline__ bool bulk_cta_idle(const u32* cnt, u32 per_cta) {
+    return size_t(blockIdx.x) * per_cta >= *cnt;
+}
+// Every warp takes one CONTIGUOUS span of a list (a multiple of 32 elements): neighbours in the list are
+// neighbours in space, so the per-warp caches see the local repetition of the world.
+__device__ __forceinline__ u32 bulk_span(u32 cnt) {
+    const u32 nwarps = gridDim.x * WARPS_PER_CTA;
+    return (((cnt + nwarps - 1) / nwarps) + 31u) & ~31u;
+}
 
 // ------------------------------------------------------------------------------------------------
 // blocks: thread per candidate block.
@@ -408,33 +419,37 @@ __global__ void __launch_bounds__(CTA_THREADS, VX_BULK_MIN_CTAS) bulk_blocks_ker
     bulk_prologue<T>(c, a, smem_raw);
     c.tpk_only = a.tpk_only != 0;
     const u32 cnt = a.cnt[0];
-    const u32 stride = gridDim.x * CTA_THREADS;
+    const u32 span = bulk_span(cnt);
+    if (bulk_cta_idle(&a.cnt[0], WARPS_PER_CTA * span)) return;
+    const u64 first = u64(blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5)) * span;
+    const u32 base0 = u32(min(first, u64(cnt)));
+    const u32 end = u32(min(first + span, u64(cnt)));
+    constexpr u32 stride = 32;
     // software pipeline: (block index, set_mask) two iterations ahead, the block's values one ahead
-    const u32 base0 = blockIdx.x * CTA_THREADS + (threadIdx.x & ~31u);
     u32 blk1 = 0, set1 = 0, blk2 = 0, set2 = 0;
     typename V::Key vals1 = V::zero();
-    if (base0 + c.lane < cnt) {
+    if (base0 + c.lane < end) {
         blk1 = ld_stream_u32(a.first[0] + base0 + c.lane);
         set1 = ld_stream_u8(a.cm[0] + base0 + c.lane);
         vals1 = V::load(a.values, blk1);
     }
-    if (u64(base0) + stride + c.lane < cnt) {
+    if (u64(base0) + stride + c.lane < end) {
         blk2 = ld_stream_u32(a.first[0] + base0 + stride + c.lane);
         set2 = ld_stream_u8(a.cm[0] + base0 + stride + c.lane);
     }
-    for (u32 base = base0; base < cnt; base += stride) {
+    for (u32 base = base0; base < end; base += stride) {
         // poisoned interner: stop (the host reports it).  The word is requested here and tested at the end
         // of the iteration, so its round trip hides behind the work
         const u32 errw = c.lane == 0 ? ld_strong(a.in.error) : u32(ERR_NONE);
         const u32 k = base + c.lane;
-        const bool active = k < cnt;
+        const bool active = k < end;
         const u32 set = set1;
         const typename V::Key vals = vals1;
         blk1 = blk2;
         set1 = set2;
         vals1 = V::zero();
-        if (u64(k) + stride < cnt) vals1 = V::load(a.values, blk1);
-        if (u64(k) + 2ull * stride < cnt) {
+        if (u64(k) + stride < end) vals1 = V::load(a.values, blk1);
+        if (u64(k) + 2ull * stride < end) {
             blk2 = ld_stream_u32(a.first[0] + k + 2 * stride);
             set2 = ld_stream_u8(a.cm[0] + k + 2 * stride);
         }
@@ -455,6 +470,7 @@ __global__ void __launch_bounds__(CTA_THREADS, VX_MIN_CTAS) bulk_dense_units_ker
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Ctx<T> c;
     bulk_prologue<T>(c, a, smem_raw);
+    if (bulk_cta_idle(&a.cnt[3], WARPS_PER_CTA)) return;
     const u32 cnt = a.cnt[3];
     const u32 upc = a.blocks / UNIT_BLOCKS;
     const int upc_log = 31 - __clz(upc);
@@ -489,15 +505,19 @@ __global__ void __launch_bounds__(CTA_THREADS, VX_BULK_MIN_CTAS) bulk_level_kern
     Ctx<T> c;
     bulk_prologue<T>(c, a, smem_raw);
     const u32 cnt = a.cnt[level];
+    const u32 span = bulk_span(cnt);
+    if (bulk_cta_idle(&a.cnt[level], WARPS_PER_CTA * span)) return;
     const u32* first = a.first[level];
     const u8* cmv = a.cm[level];
     const u64* below = a.ids[level - 1];
     u64* out = a.ids[level];
-    const u32 stride = gridDim.x * CTA_THREADS;
-    for (u32 base = (blockIdx.x * CTA_THREADS + (threadIdx.x & ~31u)); base < cnt; base += stride) {
+    const u64 wfirst = u64(blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5)) * span;
+    const u32 base0 = u32(min(wfirst, u64(cnt)));
+    const u32 end = u32(min(wfirst + span, u64(cnt)));
+    for (u32 base = base0; base < end; base += 32) {
         const u32 errw = c.lane == 0 ? ld_strong(a.in.error) : u32(ERR_NONE);
         const u32 k = base + c.lane;
-        const bool active = k < cnt;
+        const bool active = k < end;
         const u32 f = active ? ld_stream_u32(first + k) : 0;
         const u32 cm = active ? ld_stream_u8(cmv + k) : 0;
         u64 ch[8];
@@ -517,8 +537,20 @@ __global__ void __launch_bounds__(CTA_THREADS, VX_BULK_MIN_CTAS) bulk_level_kern
 // consecutive nodes of the dense array below.  is_root: the nodes are the trees' roots.
 // ------------------------------------------------------------------------------------------------
 template <class T>
+__device__ __forceinline__ void bulk_write_root(Ctx<T>& c, const BulkArgs& a, unsigned long long chunk, u64 id) {
+    // apply_batch (voxtree.rs:303-328): nothing entered `paths` -> INVALID -> false, root stays EMPTY
+    a.roots[chunk] = id;
+    if (a.changed) a.changed[chunk] = id != 0;
+    if (id != 0) atomicAdd(&c.in.refs[id_index(id)], 1u);  // the tree's root handle
+}
+
+// levels: 1 = the nodes are one level; 2 = lane 0 of every 8-lane group goes on to build the parent of the
+// group's eight nodes in the same launch (their ids never leave the registers).  top_is_root: the topmost
+// level handled here is the trees' roots; otherwise it is written to `out` (dense).
+template <class T>
 __global__ void __launch_bounds__(CTA_THREADS, VX_BULK_MIN_CTAS)
-bulk_upper_kernel(BulkArgs a, unsigned long long nodes, const u64* below, u64* out, int from_units, int is_root) {
+bulk_upper_kernel(BulkArgs a, unsigned long long nodes, const u64* below, u64* out, int from_units, int levels,
+                  int top_is_root) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Ctx<T> c;
     bulk_prologue<T>(c, a, smem_raw);
@@ -551,15 +583,25 @@ bulk_upper_kernel(BulkArgs a, unsigned long long nodes, const u64* below, u64* o
         }
         u64 id = parent_tpk<T>(c, active && !prebuilt, ch);
         if (prebuilt) id = pre_id;
-        if (k < nodes) {
-            if (is_root) {
-                // apply_batch (voxtree.rs:303-328): nothing entered `paths` -> INVALID -> false, root stays EMPTY
-                a.roots[k] = id;
-                if (a.changed) a.changed[k] = id != 0;
-                if (id != 0) atomicAdd(&c.in.refs[id_index(id)], 1u);  // the tree's root handle
-            } else {
-                out[k] = id;
+        if (levels == 1) {
+            if (k < nodes) {
+                if (top_is_root)
+                    bulk_write_root<T>(c, a, k, id);
+                else
+                    out[k] = id;
             }
+            continue;
+        }
+        // the level above: eight consecutive lanes are siblings (nodes and the warp base are multiples of 8)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ch[i] = __shfl_sync(FULL, id, c.gs + i);
+        const bool act2 = active && c.li == 0;
+        const u64 id2 = parent_tpk<T>(c, act2, ch);
+        if (k < nodes && c.li == 0) {
+            if (top_is_root)
+                bulk_write_root<T>(c, a, k >> 3, id2);
+            else
+                out[k >> 3] = id2;
         }
     }
     cta_finish<T>(c);

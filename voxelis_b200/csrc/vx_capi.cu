@@ -368,21 +368,24 @@ int launch_bulk_t(vx_interner* it, int depth, size_t n, const u8* d_masks, const
     prof_mark(it, s, "bulk_level_kernel[2]");
     CU_TRY(launch_chained(bulk_dense_units_kernel<T>, grid_for(units * 32), CTA_THREADS, smem, s, chained, a));
     prof_mark(it, s, "bulk_dense_units_kernel");
-    // dense levels: units (depth D-4) up to the roots
+    // dense levels: units (depth D-4) up to the roots, two levels per launch where there are two
     size_t nodes = units;
-    int pp = 0;
+    int pp = 1;  // dense[0] holds the prebuilt unit nodes
     const u64* below = nullptr;
     bool from_units = true;
     for (;;) {
-        const bool is_root = nodes == n;
+        const int levels = nodes == n ? 1 : 2;
+        const size_t top = levels == 1 ? nodes : nodes / 8;
+        const bool top_is_root = top == n;
         CU_TRY(launch_chained(bulk_upper_kernel<T>, grid_for(nodes), CTA_THREADS, smem, s, chained, a,
-                              (unsigned long long)nodes, below, a.dense[pp], from_units ? 1 : 0, is_root ? 1 : 0));
-        prof_mark(it, s, from_units ? "bulk_upper_kernel[units]" : is_root ? "bulk_upper_kernel[root]" : "bulk_upper_kernel");
-        if (is_root) break;
+                              (unsigned long long)nodes, below, a.dense[pp], from_units ? 1 : 0, levels, top_is_root ? 1 : 0));
+        prof_mark(it, s, from_units ? (top_is_root ? "bulk_upper_kernel[units..root]" : "bulk_upper_kernel[units..]")
+                                    : (top_is_root ? "bulk_upper_kernel[..root]" : "bulk_upper_kernel"));
+        if (top_is_root) break;
         below = a.dense[pp];
         pp ^= 1;
         from_units = false;
-        nodes >>= 3;
+        nodes = top / 8;
     }
     if (a.use_free) {
         clamp_free_count_kernel<<<1, 1, 0, s>>>(it->dev);
