@@ -32,8 +32,8 @@ struct BulkArgs {
     const void* values;  // [n][B][8]
     u64* roots;          // [n]
     u8* changed;         // [n] or null
-    u32* cnt;            // [0..2] candidates per sparse level, [3] dense units, [4] dense-unit work counter;
-                         // zeroed before the plan kernel
+    u32* cnt;            // [0..2] candidates per sparse level, [3] dense units, [4] dense-unit work counter,
+                         // [5] non-empty groups of eight units; zeroed before the plan kernel
     u32* first[3];
     u8* cm[3];
     u64* ids[3];
@@ -41,6 +41,8 @@ struct BulkArgs {
     u8* unit_cm;      // [U]
     u64* dense[2];    // ping-pong dense id arrays for the levels above the units
     u32* dense_units; // [<= U] units with >= dense_min candidate blocks: built by one warp each
+    u32* cube_flag;   // [U/8] zeroed before the plan kernel: 1 = some unit of this group of eight is not empty
+    u32* cube_list;   // [<= U/8] those groups, in the order they were first seen (count in cnt[5])
     unsigned long long units;  // U
     u32 n;
     u32 depth;
@@ -100,14 +102,15 @@ __global__ void __launch_bounds__(256) bulk_plan_kernel(BulkArgs a) {
             ld_stream_v8(a.masks + (w + PLAN_AHEAD * nwarps) * (UNIT_BLOCKS * 2) + lane * 32, &qa[PLAN_AHEAD - 1],
                          &qb[PLAN_AHEAD - 1]);
         }
+        // most units of a sparse world are empty: one OR over the set_mask bytes settles those
+        if (!__any_sync(FULL, ((q0.x | q0.y | q0.z | q0.w | q1.x | q1.y | q1.z | q1.w) & 0x00FF00FFu) != 0)) {
+            if (lane == 0) a.unit_cm[w] = 0;
+            continue;
+        }
         // set_mask bytes (even positions; clear_mask is never read by the reference)
         const u64 sa = u64(__byte_perm(q0.x, q0.y, 0x6420)) | (u64(__byte_perm(q0.z, q0.w, 0x6420)) << 32);
         const u64 sb = u64(__byte_perm(q1.x, q1.y, 0x6420)) | (u64(__byte_perm(q1.z, q1.w, 0x6420)) << 32);
         const u32 bits = nzbytes(sa) | (nzbytes(sb) << 8);  // candidate blocks of this lane
-        if (!__any_sync(FULL, bits != 0)) {
-            if (lane == 0) a.unit_cm[w] = 0;
-            continue;
-        }
         const u32 pa = (bits & 0xFF) != 0, pb = (bits >> 8) != 0;  // this lane's two level-1 parents
         // exclusive prefix sums over the lanes: candidates at level 0 (r0) and level 1 (r1), packed
         const u32 mine = u32(__popc(bits)) | ((pa + pb) << 16);
@@ -120,6 +123,10 @@ __global__ void __launch_bounds__(256) bulk_plan_kernel(BulkArgs a) {
         const u32 tot = __shfl_sync(FULL, incl, 31);
         const u32 r0 = (incl - mine) & 0xFFFF, r1 = (incl - mine) >> 16;
         const u32 c0 = tot & 0xFFFF, c1 = tot >> 16;
+        if (lane == 0 && a.blocks > UNIT_BLOCKS) {  // the group of eight units this one belongs to has work above it
+            const u32 cube = u32(w >> 3);
+            if (atomicExch(&a.cube_flag[cube], 1u) == 0) a.cube_list[atomicAdd(&a.cnt[5], 1u)] = cube;
+        }
         if (c0 >= a.dense_min) {
             // a busy unit: thread-per-block lists would cost more than they save; one warp builds it the
             // way apply_kernel does (lane = block, siblings in neighbouring lanes)
@@ -487,6 +494,31 @@ __global__ void __launch_bounds__(CTA_THREADS, VX_MIN_CTAS) bulk_dense_units_ker
         load_unit_masks(a.masks + size_t(chunk) * a.blocks * 2, size_t(unit) * UNIT_BLOCKS, UNIT_BLOCKS, c.lane, &mlo, &mhi);
         const Under u{0, 0, 0, D};
         const void* cv = (const u8*)a.values + size_t(chunk) * a.blocks * 8 * sizeof(T);
+        // Solid unit (underground rock, filled volumes): every voxel set to the same non-default value.
+        // Phase 1 makes 512 identical leaves, phase 2 collapses 64 + 8 + 1 parents (:826, :1050) — the
+        // outcome is that one leaf, so the unit costs one streaming pass over its values.
+        if (__all_sync(FULL, (mlo & mhi) == ~0ull)) {
+            const uint4* vp = reinterpret_cast<const uint4*>((const u8*)cv + (size_t(unit) * UNIT_BLOCKS + 16 * c.lane) * 8 * sizeof(T));
+            constexpr int NV = 8 * int(sizeof(T));  // 16-byte vectors holding this lane's 16 blocks
+            uint4 q = ld_stream_v4(vp);
+            const u32 v0 = __shfl_sync(FULL, sizeof(T) == 1 ? (q.x & 0xFFu) : q.x, 0);
+            const u32 splat = sizeof(T) == 1 ? v0 * 0x01010101u : v0;
+            bool uni = v0 != 0;
+#pragma unroll 4
+            for (int j = 0; j < NV; ++j) {
+                if (j) q = ld_stream_v4(vp + j);
+                uni = uni && q.x == splat && q.y == splat && q.z == splat && q.w == splat;
+            }
+            if (__all_sync(FULL, uni)) {
+                u64 leaf = leaf_get(c, v0, c.lane == 0);
+                if (c.lane == 0) {
+                    c.t.leaf_calls += UNIT_BLOCKS;                                    // one per all_same block
+                    c.t.collapsed += UNIT_BLOCKS + UNIT_BLOCKS / 8 + UNIT_BLOCKS / 64 + 1;  // blocks + 3 levels
+                    a.dense[0][w] = leaf;
+                }
+                continue;
+            }
+        }
         const bool some = build_blocks<T, false>(c, mlo, mhi, cv, unit * UNIT_BLOCKS, UNIT_BLOCKS, u);
         u64 node = 0;
         bool present = false;
@@ -556,15 +588,20 @@ bulk_upper_kernel(BulkArgs a, unsigned long long nodes, const u64* below, u64* o
     bulk_prologue<T>(c, a, smem_raw);
     const unsigned long long stride = size_t(gridDim.x) * CTA_THREADS;
     const bool poisoned0 = ld_strong(a.in.error) != ERR_NONE;
+    // from_units with two levels: only the groups of eight units that hold something are visited (list
+    // written by the plan kernel); everything they do not touch was zeroed by the host
+    const bool listed = from_units && levels == 2;
+    if (listed) nodes = size_t(a.cnt[5]) * 8;
     for (unsigned long long base = (size_t(blockIdx.x) * CTA_THREADS + (threadIdx.x & ~31u)); base < nodes; base += stride) {
-        const unsigned long long k = base + c.lane;
+        unsigned long long k = base + c.lane;
         const bool active = k < nodes && !poisoned0;
+        if (listed) k = k < nodes ? size_t(a.cube_list[k >> 3]) * 8 + (k & 7) : ~0ull;
         u64 ch[8];
         bool prebuilt = false;
         u64 pre_id = 0;
         if (from_units) {
-            u32 cm = active ? ld_stream_u8(a.unit_cm + k) : 0;
-            const u32 f = cm ? ld_stream_u32(a.unit_first + k) : 0;
+            u32 cm = active ? u32(a.unit_cm[k]) : 0;
+            const u32 f = cm ? a.unit_first[k] : 0;
             if (cm && f == UNIT_PREBUILT) {  // built by bulk_dense_units_kernel
                 prebuilt = true;
                 pre_id = a.dense[0][k];
@@ -584,7 +621,7 @@ bulk_upper_kernel(BulkArgs a, unsigned long long nodes, const u64* below, u64* o
         u64 id = parent_tpk<T>(c, active && !prebuilt, ch);
         if (prebuilt) id = pre_id;
         if (levels == 1) {
-            if (k < nodes) {
+            if (active || (k < nodes && !listed)) {
                 if (top_is_root)
                     bulk_write_root<T>(c, a, k, id);
                 else
@@ -597,7 +634,7 @@ bulk_upper_kernel(BulkArgs a, unsigned long long nodes, const u64* below, u64* o
         for (int i = 0; i < 8; ++i) ch[i] = __shfl_sync(FULL, id, c.gs + i);
         const bool act2 = active && c.li == 0;
         const u64 id2 = parent_tpk<T>(c, act2, ch);
-        if (k < nodes && c.li == 0) {
+        if ((listed ? active : k < nodes) && c.li == 0) {
             if (top_is_root)
                 bulk_write_root<T>(c, a, k >> 3, id2);
             else

@@ -263,7 +263,7 @@ size_t bulk_scratch_bytes(size_t n, size_t blocks) {
     size_t need = 256;
     for (int l = 0; l < 3; ++l) need += ((nb >> (3 * l)) * 13 + 3 * 256);
     const size_t units = nb / UNIT_BLOCKS;
-    need += units * 5 + 2 * 256 + units * 8 + units + 2 * 256 + units * 4 + 256;
+    need += units * 5 + 2 * 256 + units * 8 + units + 2 * 256 + units * 4 + 256 + units + 2 * 256;
     return need;
 }
 size_t bulk_max_bytes() {
@@ -335,8 +335,21 @@ int launch_bulk_t(vx_interner* it, int depth, size_t n, const u8* d_masks, const
     a.dense[0] = (u64*)take(units * 8);
     a.dense[1] = (u64*)take(units);
     a.dense_units = (u32*)take(units * 4);
+    a.cube_flag = (u32*)take(units / 8 * 4 + 4);
+    a.cube_list = (u32*)take(units / 8 * 4 + 4);
     prof_begin(it, s);
     CU_TRY(cudaMemsetAsync(a.cnt, 0, 32, s));
+    if (units > n) {
+        // the first upper launch only visits groups of eight units that hold something: what it does not
+        // write must already say "empty"
+        CU_TRY(cudaMemsetAsync(a.cube_flag, 0, units / 8 * 4, s));
+        if (units / 8 == n) {
+            CU_TRY(cudaMemsetAsync(d_roots, 0, n * 8, s));
+            if (d_changed) CU_TRY(cudaMemsetAsync(d_changed, 0, n, s));
+        } else {
+            CU_TRY(cudaMemsetAsync(a.dense[1], 0, units, s));
+        }
+    }
 
     const size_t smem = apply_smem_bytes<T>();
     int occ = 0;
