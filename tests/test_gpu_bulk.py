@@ -139,3 +139,28 @@ def test_bulk_out_of_memory_is_a_status(gpu_api, monkeypatch):
     g.reset()
     roots, changed = g.apply_batches_slab(5, *wl.named_workload("checkerboard", 4, 5, wl.U8))
     assert changed.all()
+
+
+def test_bulk_repeated_calls_varied_sizes(gpu_api, monkeypatch):
+    """The bulk scratch (level lists, epoch-tagged flags) is reused across calls of any size and depth:
+    every call must come out as if it were the only one."""
+    vx = gpu_api
+    monkeypatch.setenv("VX_BUILDER", "bulk")
+    g = vx.VoxInterner.with_memory_budget(512 << 20)
+    rng = np.random.default_rng(5)
+    world = wl.terrain_world((8, 3, 8), 5, "surface_and_below", wl.U8, materials=2)
+    for step, (depth, n) in enumerate([(5, 64), (5, 192), (6, 3), (5, 7), (4, 40), (5, 192), (7, 1), (5, 64)]):
+        if depth == 5:
+            pick = rng.choice(world[0].shape[0], n, replace=False)
+            masks, values = world[0][pick].copy(), world[1][pick].copy()
+            masks[rng.integers(0, n)] = 0
+        else:
+            masks, values = wl.batch_from_function(depth, wl.p_random(255, cell=4 if depth > 5 else 2), wl.U8, n)
+            masks[n // 2, ::2, 0] = 0
+        roots, changed = g.apply_batches_slab(depth, masks, values)
+        assert np.array_equal(changed.astype(bool), masks[:, :, 0].any(1)), step
+        assert ((roots == 0) == (changed == 0)).all(), step
+        check = rng.choice(n, min(n, 6), replace=False)
+        dense = g.roots_to_vec(roots[check], depth)
+        for j, i in enumerate(check):
+            assert np.array_equal(dense[j], wl.dense_expected(masks[i], values[i])), (step, i)

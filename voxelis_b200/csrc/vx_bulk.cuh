@@ -41,7 +41,8 @@ struct BulkArgs {
     u8* unit_cm;      // [U]
     u64* dense[2];    // ping-pong dense id arrays for the levels above the units
     u32* dense_units; // [<= U] units with >= dense_min candidate blocks: built by one warp each
-    u32* cube_flag;   // [U/8] zeroed before the plan kernel: 1 = some unit of this group of eight is not empty
+    u32* cube_flag;   // [U/8] == epoch: some unit of this group of eight is not empty (no per-call clearing)
+    u32 epoch;        // call counter of the interner's bulk scratch, never 0
     u32* cube_list;   // [<= U/8] those groups, in the order they were first seen (count in cnt[5])
     unsigned long long units;  // U
     u32 n;
@@ -102,6 +103,16 @@ __global__ void __launch_bounds__(256) bulk_plan_kernel(BulkArgs a) {
             ld_stream_v8(a.masks + (w + PLAN_AHEAD * nwarps) * (UNIT_BLOCKS * 2) + lane * 32, &qa[PLAN_AHEAD - 1],
                          &qb[PLAN_AHEAD - 1]);
         }
+        // the first upper launch only visits groups of eight units that hold something; the first unit of
+        // every group says "empty" for it beforehand (roots / changed for D = 5, the dense level above else)
+        if (lane == 0 && (w & 7) == 0 && a.blocks > UNIT_BLOCKS) {
+            if (a.blocks == 8 * UNIT_BLOCKS) {
+                a.roots[w >> 3] = 0;
+                if (a.changed) a.changed[w >> 3] = 0;
+            } else {
+                a.dense[1][w >> 3] = 0;
+            }
+        }
         // most units of a sparse world are empty: one OR over the set_mask bytes settles those
         if (!__any_sync(FULL, ((q0.x | q0.y | q0.z | q0.w | q1.x | q1.y | q1.z | q1.w) & 0x00FF00FFu) != 0)) {
             if (lane == 0) a.unit_cm[w] = 0;
@@ -125,7 +136,7 @@ __global__ void __launch_bounds__(256) bulk_plan_kernel(BulkArgs a) {
         const u32 c0 = tot & 0xFFFF, c1 = tot >> 16;
         if (lane == 0 && a.blocks > UNIT_BLOCKS) {  // the group of eight units this one belongs to has work above it
             const u32 cube = u32(w >> 3);
-            if (atomicExch(&a.cube_flag[cube], 1u) == 0) a.cube_list[atomicAdd(&a.cnt[5], 1u)] = cube;
+            if (atomicExch(&a.cube_flag[cube], a.epoch) != a.epoch) a.cube_list[atomicAdd(&a.cnt[5], 1u)] = cube;
         }
         if (c0 >= a.dense_min) {
             // a busy unit: thread-per-block lists would cost more than they save; one warp builds it the

@@ -90,6 +90,9 @@ struct vx_interner {
     size_t join_bytes = 0;
     void* bulk = nullptr;        // bulk builder's level lists (vx_bulk.cuh), sized for the largest call seen
     size_t bulk_bytes = 0;
+    uint32_t* bulk_flags = nullptr;  // epoch-tagged "group of units is not empty" flags (own allocation:
+    size_t bulk_flags_n = 0;         // they must only ever hold tags, whatever the call sizes were)
+    uint32_t bulk_epoch = 0;         // tag of the current call
     // diagnostic: CUDA events between the launches of the last apply (vx_interner_profile_stages)
     bool prof = false;
     cudaEvent_t pev[10]{};
@@ -303,6 +306,21 @@ int launch_bulk_t(vx_interner* it, int depth, size_t n, const u8* d_masks, const
         CU_TRY(cudaMalloc(&it->bulk, need));
         it->bulk_bytes = need;
     }
+    if (units / 8 + 1 > it->bulk_flags_n) {
+        CU_TRY(cudaStreamSynchronize(s));
+        CU_TRY(cudaStreamSynchronize(it->stream));
+        cudaFree(it->bulk_flags);
+        it->bulk_flags = nullptr;
+        it->bulk_flags_n = 0;
+        CU_TRY(cudaMalloc(&it->bulk_flags, (units / 8 + 1) * 4));
+        it->bulk_flags_n = units / 8 + 1;
+        CU_TRY(cudaMemsetAsync(it->bulk_flags, 0, it->bulk_flags_n * 4, s));
+        it->bulk_epoch = 0;
+    }
+    if (++it->bulk_epoch == 0) {  // wrapped: the tags of 2^32 calls ago could alias
+        CU_TRY(cudaMemsetAsync(it->bulk_flags, 0, it->bulk_flags_n * 4, s));
+        it->bulk_epoch = 1;
+    }
     BulkArgs a{};
     a.in = it->dev;
     a.masks = d_masks;
@@ -313,6 +331,7 @@ int launch_bulk_t(vx_interner* it, int depth, size_t n, const u8* d_masks, const
     a.n = u32(n);
     a.depth = u32(depth);
     a.blocks = u32(blocks);
+    a.epoch = it->bulk_epoch;
     a.dense_min = 128;  // candidate blocks (of 512) from which a unit is built by one warp instead
     if (const char* e = getenv("VX_BULK_DENSE_MIN")) a.dense_min = u32(atoi(e));
     a.tpk_only = getenv("VX_BULK_TPK") ? u32(atoi(getenv("VX_BULK_TPK"))) : 0u;
@@ -335,22 +354,10 @@ int launch_bulk_t(vx_interner* it, int depth, size_t n, const u8* d_masks, const
     a.dense[0] = (u64*)take(units * 8);
     a.dense[1] = (u64*)take(units);
     a.dense_units = (u32*)take(units * 4);
-    a.cube_flag = (u32*)take(units / 8 * 4 + 4);
+    a.cube_flag = it->bulk_flags;
     a.cube_list = (u32*)take(units / 8 * 4 + 4);
     prof_begin(it, s);
     CU_TRY(cudaMemsetAsync(a.cnt, 0, 32, s));
-    if (units > n) {
-        // the first upper launch only visits groups of eight units that hold something: what it does not
-        // write must already say "empty"
-        CU_TRY(cudaMemsetAsync(a.cube_flag, 0, units / 8 * 4, s));
-        if (units / 8 == n) {
-            CU_TRY(cudaMemsetAsync(d_roots, 0, n * 8, s));
-            if (d_changed) CU_TRY(cudaMemsetAsync(d_changed, 0, n, s));
-        } else {
-            CU_TRY(cudaMemsetAsync(a.dense[1], 0, units, s));
-        }
-    }
-
     const size_t smem = apply_smem_bytes<T>();
     int occ = 0;
     CU_TRY(cudaFuncSetAttribute(bulk_blocks_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
@@ -668,6 +675,7 @@ void vx_interner_destroy(vx_interner* it) {
     cudaFree(d.leaf_ids);
     cudaFree(it->d_scalars);
     cudaFree(it->bulk);
+    cudaFree(it->bulk_flags);
     for (auto& e : it->pev)
         if (e) cudaEventDestroy(e);
     for (int i = 0; i < 2; ++i) {
