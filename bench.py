@@ -51,11 +51,13 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
 
     def start(self):
+        """Launch the sampler (before the warm-up, so it is already delivering when the timed region starts)."""
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -63,17 +65,27 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.monotonic(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def begin(self):
+        self.t0 = time.monotonic()
+
+    def end(self):
+        self.t1 = time.monotonic()
+
+    def in_window(self):
+        return sum(1 for t, r in self.rows if self.t0 <= t <= (self.t1 or time.monotonic()) and r and r[0].isdigit())
+
+    def stop(self, window="timed region"):
         if self.proc:
             self.proc.terminate()
-        sm = [int(r[0]) for r in self.rows if r and r[0].isdigit()]
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        rows = [r for t, r in self.rows if self.t0 is None or (self.t0 <= t <= (self.t1 or t))]
+        sm = [int(r[0]) for r in rows if r and r[0].isdigit()]
+        mx = [int(r[1]) for r in rows if len(r) > 1 and r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i] == "Active"})
+        reasons = sorted({names[i] for r in rows if len(r) >= 6 for i in range(4) if r[2 + i] == "Active"})
         return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "window": window}
 
 
 def log(msg: str):
@@ -135,7 +147,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-others", action="store_true", help="skip the secondary workloads")
@@ -216,6 +228,8 @@ def main():
                                 d_changed.data_ptr(), stream=stream.cuda_stream)
 
     # ---------------------------------------------------------------- device-resident timing
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     log("warm-up")
     for _ in range(args.warmup):
         step_device()
@@ -223,10 +237,9 @@ def main():
     it.sync()
     new_nodes = it.stats()["total_cache_misses"]
     dbg = it.debug_counters()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     kernel_ms = []
     barrier()
+    sampler.begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     kev = []
@@ -241,7 +254,19 @@ def main():
     e1.record(stream)
     barrier()
     it.sync()
-    clocks = sampler.stop()
+    sampler.end()
+    window = "timed region"
+    if sampler.in_window() < 3:
+        # the timed region was shorter than a few sampling periods: keep the same load running (untimed)
+        # until the sampler has seen it, and say so
+        t_probe = time.monotonic()
+        while time.monotonic() - t_probe < 0.6:
+            for _ in range(50):
+                step_device()
+            it.sync()
+        sampler.end()
+        window = "timed region + 0.6 s of identical untimed steps (region shorter than 3 sampling periods)"
+    clocks = sampler.stop(window)
     step_ms = e0.elapsed_time(e1) / args.steps
     kernel_ms = [a.elapsed_time(b) for a, b in kev]
     step_ms_max = max_over_ranks(step_ms)

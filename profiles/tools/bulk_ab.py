@@ -31,6 +31,12 @@ def run(name, masks, values, depth, budget, dtype=vx.U8, steps=20):
         del it
     print(name, json.dumps(out), flush=True)
 which = sys.argv[1:] or ["perlin", "checker", "random", "below", "d7", "i32"]
+if "sizes" in which:      # where the two builders cross over (auto threshold in use_bulk_builder)
+    m, v = wl.terrain_world((16, 4, 16), 5, "surface_only", wl.U8)
+    keep = np.flatnonzero(m[:, :, 0].any(1))
+    for n in (16, 64, 128, 256, 1024):
+        idx = keep[:n] if len(keep) >= n else np.arange(n)
+        run(f"perlin_nonempty_x{n}", m[idx].copy(), v[idx].copy(), 5, 256 << 20)
 if "perlin" in which:
     m, v = wl.terrain_world((64, 8, 64), 5, "surface_only", wl.U8); run("perlin", m, v, 5, 256 << 20)
 if "below" in which:

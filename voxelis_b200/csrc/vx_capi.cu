@@ -425,7 +425,7 @@ bool use_bulk_builder(int depth, size_t n, const u8* d_masks, const u8* d_flags,
         if (!strcmp(e, "bulk")) return true;
         if (!strcmp(e, "fused")) return false;
     }
-    return nb >= (size_t(1) << 18);  // 64 chunks of 32^3: below that one fused launch is cheaper than six
+    return nb >= (size_t(1) << 16);  // 16 chunks of 32^3 (measured: the pipeline already wins there, profiles/README.md)
 }
 
 // d_old_roots == nullptr: every tree is fresh (the north-star path).
