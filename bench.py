@@ -88,6 +88,29 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm), "window": window}
 
 
+# stdout carries exactly ONE JSON line.  Native libraries (NCCL's version banner, driver notices) write to
+# file descriptor 1 behind Python's back, so fd 1 is pointed at stderr for the whole run and the JSON line
+# goes to a private duplicate of the original stdout.
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def log(msg: str):
     print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
 
@@ -141,7 +164,7 @@ def run_reference(args):
         "e2e": {"value": v, "unit": "chunks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
@@ -158,6 +181,7 @@ def main():
     ap.add_argument("--workload", default="perlin", help="profiling only: time another workload in the main loop "
                     "(checkerboard | sum | sum_per_chunk | random255 | below); the headline is 'perlin'")
     args = ap.parse_args()
+    claim_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         return run_reference(args)
@@ -456,7 +480,7 @@ def main():
             line["others"] = others
         if dedup_info:
             line["global_dedup"] = dedup_info
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -182,6 +182,11 @@ int vx_tree_get_many(const vx_interner*, const vx_tree*, size_t n, const int32_t
 int vx_tree_to_vec(const vx_interner*, const vx_tree*, void* dense);
 /* to_vec for n bare roots of one depth: dense[n][N^3]; roots host or device, dense host or device. */
 int vx_roots_to_vec(const vx_interner*, uint8_t max_depth, size_t n, const vx_block_id* roots, void* dense);
+/* to_vec at a level of detail — to_vec(interner, root, max_depth.for_lod(lod)), world/voxchunk.rs:267 with
+ * core/max_depth.rs:137-140: only max_depth - lod levels (saturating) are unfolded and a branch standing at
+ * that depth contributes its LOD value (calc_average, core/voxel.rs:96-141).  dense[n][M^3], M = 2^(max_depth-lod). */
+int vx_roots_to_vec_lod(const vx_interner*, uint8_t max_depth, uint8_t lod, size_t n, const vx_block_id* roots,
+                        void* dense);
 
 /* VoxTree::fill / clear — voxtree.rs:264-292. */
 int vx_tree_fill(vx_interner*, vx_tree*, int64_t value);

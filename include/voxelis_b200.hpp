@@ -155,6 +155,15 @@ public:
         detail::check(vx_tree_to_vec(i.raw(), h_, dense.data()));
         return dense;
     }
+    /// to_vec(interner, root, max_depth.for_lod(lod)) — world/voxchunk.rs:267, core/max_depth.rs:137-140
+    std::vector<T> to_vec(const VoxInterner<T>& i, uint8_t lod) const {
+        const uint8_t d = vx_tree_max_depth(h_);
+        size_t n = size_t(1) << (d > lod ? d - lod : 0);
+        std::vector<T> dense(n * n * n);
+        vx_block_id root = vx_tree_root_id(h_);
+        detail::check(vx_roots_to_vec_lod(i.raw(), d, lod, 1, &root, dense.data()));
+        return dense;
+    }
     void fill(VoxInterner<T>& i, T value) { detail::check(vx_tree_fill(i.raw(), h_, int64_t(value))); }  // voxtree.rs:264
     void clear(VoxInterner<T>& i) { detail::check(vx_tree_clear(i.raw(), h_)); }                         // voxtree.rs:283
     BlockId get_root_id() const { return BlockId{vx_tree_root_id(h_)}; }

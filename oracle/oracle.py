@@ -78,6 +78,7 @@ def lib():
     L.orc_tree_get.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, i64p]
     L.orc_tree_to_vec.argtypes = [vp, vp, vp]
     L.orc_root_to_vec.argtypes = [vp, C.c_uint64, C.c_int, vp]
+    L.orc_root_to_vec_lod.argtypes = [vp, C.c_uint64, C.c_int, C.c_int, vp]
     L.orc_interner_ref.restype = C.c_uint32
     L.orc_interner_ref.argtypes = [vp, C.c_uint64]
     L.orc_interner_next_index.restype = C.c_uint32
@@ -194,10 +195,10 @@ class VoxInterner:
             None if hp is None else _ptr(hp), _ptr(roots), _ptr(changed)))
         return roots, changed
 
-    def root_to_vec(self, root: int, depth: int):
-        n = 1 << depth
+    def root_to_vec(self, root: int, depth: int, lod: int = 0):
+        n = 1 << max(depth - lod, 0)
         out = np.zeros((n, n, n), _NP[self.dtype])  # [y][z][x]
-        _check(lib().orc_root_to_vec(self.h, int(root), depth, _ptr(out)))
+        _check(lib().orc_root_to_vec_lod(self.h, int(root), depth, lod, _ptr(out)))
         return out
 
 

@@ -199,6 +199,21 @@ int orc_root_to_vec(void* ih, uint64_t root, int depth, void* dense) {
     return orc_tree_to_vec(ih, &t, dense);
 }
 
+// to_vec at a level of detail: depth - lod levels are unfolded (saturating, core/max_depth.rs:137-140)
+int orc_root_to_vec_lod(void* ih, uint64_t root, int depth, int lod, void* dense) {
+    AnyInterner* a = (AnyInterner*)ih;
+    Tree t(depth);
+    t.root_id = root;
+    const int md = depth > lod ? depth - lod : 0;
+    return guarded([&] {
+        if (a->dtype == 0)
+            tree_to_vec(*a->i8, t, (u8*)dense, md);
+        else
+            tree_to_vec(*a->i32, t, (int32_t*)dense, md);
+        return 0;
+    });
+}
+
 uint32_t orc_interner_ref(void* ih, uint64_t id) {
     AnyInterner* a = (AnyInterner*)ih;
     return a->dtype == 0 ? a->i8->get_ref(id) : a->i32->get_ref(id);

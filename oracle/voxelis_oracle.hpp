@@ -777,10 +777,12 @@ bool tree_get(const Interner<T>& in, const Tree& t, int x, int y, int z, T* out)
     return false;
 }
 
-// to_vec — utils/common.rs:158-246.  Dense layout index = y*N*N + z*N + x (:229-238).
+// to_vec — utils/common.rs:158-246.  Dense layout index = y*N*N + z*N + x (:229-238).  `md` is the depth the
+// caller asks for: MaxDepth::for_lod (core/max_depth.rs:137-140, used by world/voxchunk.rs:267) — branches
+// standing at that depth contribute their LOD value.
 template <class T>
-void tree_to_vec(const Interner<T>& in, const Tree& t, T* data) {
-    int md = t.max_depth;
+void tree_to_vec(const Interner<T>& in, const Tree& t, T* data, int md = -1) {
+    if (md < 0) md = t.max_depth;
     size_t n = size_t(1) << md;
     size_t size = n * n * n;
     if (!id_is_branch(t.root_id)) {  // :172-174

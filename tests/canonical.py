@@ -112,3 +112,34 @@ class CanonicalDag:
                     deg[c] = deg.get(c, 0) + 1
                     stack.append(c)
         return deg
+
+
+def lod_pyramid(dense_yzx: np.ndarray):
+    """Independent restatement of what to_vec returns at every level of detail (pure numpy).
+
+    A branch's value is calc_average of its eight children's values (core/voxel.rs:96-141): the most
+    frequent value; on a tie a non-default value wins, then the earliest first occurrence in child order
+    i = x | y<<1 | z<<2.  EMPTY children count as the default (0); a uniform-collapsed Leaf keeps its value,
+    which is what the same rule gives.  Returns [lod 0 (input), lod 1, ...] down to one voxel."""
+    out = [dense_yzx]
+    cur = dense_yzx.astype(np.int64)
+    while cur.shape[0] > 1:
+        m = cur.shape[0] // 2
+        # children of cell (Y, Z, X) in child order i = x | y<<1 | z<<2
+        kids = np.stack([cur[(i >> 1 & 1)::2, (i >> 2 & 1)::2, (i & 1)::2] for i in range(8)], axis=-1)  # [Y][Z][X][8]
+        flat = kids.reshape(-1, 8)
+        best = flat[:, 0].copy()
+        best_score = np.full(len(flat), -1, np.int64)
+        for i in range(8):
+            v = flat[:, i]
+            cnt = (flat == v[:, None]).sum(1)
+            first = np.ones(len(flat), bool)
+            for j in range(i):
+                first &= flat[:, j] != v
+            score = np.where(first, cnt * 2 + (v != 0), -1)   # count, then non-default; earlier i wins ties
+            take = score > best_score
+            best = np.where(take, v, best)
+            best_score = np.where(take, score, best_score)
+        cur = best.reshape(m, m, m)
+        out.append(cur.astype(dense_yzx.dtype))
+    return out

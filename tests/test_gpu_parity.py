@@ -218,3 +218,21 @@ def test_full_size_configs_properties(gpu_api, oracle_api):
     for i in np.flatnonzero(changed)[:2000]:
         k = (masks[i].tobytes(), values[i].tobytes())
         assert key.setdefault(k, roots[i]) == roots[i]
+
+
+@pytest.mark.parametrize("dtype", [wl.U8, wl.I32], ids=["u8", "i32"])
+def test_to_vec_at_every_lod(gpu_api, oracle_api, dtype):
+    """vx_roots_to_vec_lod == to_vec(interner, root, max_depth.for_lod(lod)) (world/voxchunk.rs:267)."""
+    for depth in (3, 5):
+        parts = [wl.batch_from_function(depth, wl.p_random(4), dtype, 3),
+                 wl.batch_from_function(depth, wl.p_random(255, cell=2), dtype, 2),
+                 wl.named_workload("hollow", 1, depth, dtype), wl.named_workload("uniform", 1, depth, dtype),
+                 wl.batch_from_function(depth, wl.p_sparse(), dtype, 2)]
+        masks = np.concatenate([p[0] for p in parts])
+        values = np.concatenate([p[1] for p in parts])
+        masks[1] = 0
+        g, groots, _, c, croots, _ = parity.build_both(gpu_api, oracle_api, depth, masks, values, dtype)
+        for lod in range(depth + 2):
+            gd = g.roots_to_vec(groots, depth, lod)
+            for i in range(len(groots)):
+                assert np.array_equal(gd[i], c.root_to_vec(int(croots[i]), depth, lod)), (depth, lod, i)

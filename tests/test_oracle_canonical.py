@@ -136,3 +136,22 @@ def test_alternating_batches_recycle(oracle_api):
         assert st["alive_nodes"] - 1 == 177
     assert it.next_index == 355
     assert it.free_count == 177
+
+
+@pytest.mark.parametrize("dtype", [wl.U8, wl.I32], ids=["u8", "i32"])
+def test_to_vec_at_every_lod_matches_numpy_pyramid(oracle_api, dtype):
+    """to_vec(interner, root, max_depth.for_lod(lod)) (world/voxchunk.rs:267): branches at the cut-off depth
+    contribute their LOD value = calc_average of their children (core/voxel.rs:96-141)."""
+    from canonical import lod_pyramid
+    o = oracle_api
+    for name, pat in (("random4", wl.p_random(4)), ("cell2", wl.p_random(255, cell=2)), ("sparse", wl.p_sparse()),
+                      ("hollow", wl.p_hollow_cube()), ("uniform", wl.p_uniform(3))):
+        depth = 4
+        masks, values = wl.batch_from_function(depth, pat, dtype, 1)
+        c = o.VoxInterner(64 << 20, dtype)
+        roots, _ = c.apply_batches_fresh(depth, masks, values)
+        pyr = lod_pyramid(wl.dense_expected(masks[0], values[0]))
+        for lod in range(depth + 2):
+            got = c.root_to_vec(int(roots[0]), depth, lod)
+            want = pyr[min(lod, depth)]
+            assert np.array_equal(got, want), (name, lod)

@@ -44,7 +44,7 @@ ABI_SYMBOLS = [
     "vx_tree_voxels_per_axis", "vx_tree_is_empty", "vx_tree_is_leaf", "vx_tree_is_dirty",
     "vx_tree_mark_dirty", "vx_tree_clear_dirty", "vx_tree_apply_batch", "vx_apply_batches",
     "vx_apply_batches_slab", "vx_apply_batches_device", "vx_tree_get", "vx_tree_get_many",
-    "vx_tree_to_vec", "vx_roots_to_vec", "vx_tree_fill", "vx_tree_clear",
+    "vx_tree_to_vec", "vx_roots_to_vec", "vx_roots_to_vec_lod", "vx_tree_fill", "vx_tree_clear",
     "vx_dedup_heights", "vx_dedup_pack", "vx_dedup_scatter", "vx_dedup_map_roots", "vx_interner_intern_records",
 ]
 
@@ -139,6 +139,7 @@ def lib():
     L.vx_tree_get_many.argtypes = [vp, vp, sz, vp, vp, vp]
     L.vx_tree_to_vec.argtypes = [vp, vp, vp]
     L.vx_roots_to_vec.argtypes = [vp, C.c_uint8, sz, vp, vp]
+    L.vx_roots_to_vec_lod.argtypes = [vp, C.c_uint8, C.c_uint8, sz, vp, vp]
     L.vx_tree_fill.argtypes = [vp, vp, i64]
     L.vx_tree_clear.argtypes = [vp, vp]
     L.vx_dedup_heights.argtypes = [vp, vp]
@@ -292,11 +293,12 @@ class VoxInterner:
                                           C.c_void_p(d_roots), C.c_void_p(d_changed or None),
                                           C.c_void_p(stream or None)))
 
-    def roots_to_vec(self, roots, depth: int):
+    def roots_to_vec(self, roots, depth: int, lod: int = 0):
+        """to_vec for bare roots; ``lod`` > 0 unfolds only depth - lod levels (world/voxchunk.rs:267)."""
         roots = np.ascontiguousarray(roots, np.uint64)
-        n = 1 << depth
+        n = 1 << max(depth - lod, 0)
         out = np.zeros((len(roots), n, n, n), _NP[self.dtype])  # [r][y][z][x]
-        _ck(lib().vx_roots_to_vec(self.h, depth, len(roots), _ptr(roots), _ptr(out)))
+        _ck(lib().vx_roots_to_vec_lod(self.h, depth, lod, len(roots), _ptr(roots), _ptr(out)))
         return out
 
 

@@ -1287,10 +1287,16 @@ int vx_tree_get(const vx_interner* it, const vx_tree* t, int x, int y, int z, in
 }
 
 int vx_roots_to_vec(const vx_interner* cit, uint8_t depth, size_t n, const vx_block_id* roots, void* dense) {
+    return vx_roots_to_vec_lod(cit, depth, 0, n, roots, dense);
+}
+
+int vx_roots_to_vec_lod(const vx_interner* cit, uint8_t max_depth, uint8_t lod, size_t n, const vx_block_id* roots,
+                        void* dense) {
     vx_interner* it = const_cast<vx_interner*>(cit);
     if (!it || !roots || !dense) return fail(VX_E_INVALID, "null argument");
-    if (!valid_depth(depth)) return fail(VX_E_INVALID, "max_depth must be in [2,7]");
+    if (!valid_depth(max_depth)) return fail(VX_E_INVALID, "max_depth must be in [2,7]");
     if (n == 0) return VX_OK;
+    const int depth = max_depth > lod ? int(max_depth) - int(lod) : 0;  // MaxDepth::for_lod saturates
     std::lock_guard<std::mutex> lk(it->mu);
     DeviceGuard g(it->device);
     const size_t vol = size_t(1) << (3 * depth), esz = dtype_size(it->dtype);
