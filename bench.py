@@ -6,8 +6,9 @@ Contract (see the task brief): one JSON line on rank 0.
               launch over 64x8x64 = 32 768 chunks of 32^3 voxels (u8), batches resident in HBM.
   value     = chunks/s, whole job (sum over ranks / max-over-ranks device time), weak scaling:
               every rank builds its own 64x8x64 world (X offset = rank * 64 chunks).
-  e2e       = the same through the C ABI with HOST (pinned) batches: H2D of masks+values and D2H of
-              the root ids inside the timed region (vx_apply_batches_slab).
+  e2e       = the same through the reference-facing C-ABI call on HOST batches: vx_apply_batches over
+              n Batch + n VoxTree handles; bus traffic of the batches and D2H of roots/changed inside the
+              timed region (the dense two-array slab entry is reported beside it).
   roofline  = algorithmic bytes per launch / CUDA-event duration of the apply kernel,
               against MEASURED_PEAKS.json:hbm_gbs.
   cpu_baseline / --impl reference = the CPU oracle (a C++ restatement of the reference's Rust
@@ -314,27 +315,78 @@ def main():
     dom = max(stages, key=stages.get) if stages else "apply_kernel"
     log("stages: " + ", ".join(f"{k} {v * 1e3:.1f} us" for k, v in stages.items()))
     # ---------------------------------------------------------------- end to end (host batches)
-    e2e_value, e2e_ms_max = None, None
+    e2e_value, e2e_ms_max, e2e_slab, touched_units, e2e_trace = None, None, None, 0, None
     if not args.no_e2e:
+        # (1) the reference-facing call: n Batch handles (pinned host memory, filled by the caller before the
+        # timed region, as a reference user fills Batch objects with set()) + n VoxTree handles ->
+        # vx_apply_batches.  Inside the timed region: interner reset, the bus traffic of every touched unit,
+        # the build, roots + changed flags back to the host, VoxTree handles updated.
+        log("end-to-end: creating batch handles")
+        trees = [vx.VoxTree(DEPTH, vx.U8) for _ in range(n)]
+        batches = [t.create_batch() for t in trees]
+        for b, m, v in zip(batches, masks, values):
+            b.assign(m, v)
+        touched_units = sum(b.touched_units for b in batches)
+        cs = vx.ChunkSet(trees, batches)
+        for _ in range(3):
+            it.reset()
+            cs.forget()
+            cs.apply(it)
+        e2e_steps = max(5, min(args.steps, 50))
+        barrier()
+        parts = [0.0, 0.0, 0.0]
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            ta = time.perf_counter()
+            it.reset_async()            # queued on the interner's stream, ahead of the apply
+            tb = time.perf_counter()
+            cs.forget()
+            tc = time.perf_counter()
+            cs.apply(it)                # synchronous: returns with every VoxTree handle updated
+            td = time.perf_counter()
+            parts[0] += tb - ta
+            parts[1] += tc - tb
+            parts[2] += td - tc
+        torch.cuda.synchronize()
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+        barrier()
+        log("end-to-end host view per step: reset %.0f us, forget %.0f us, apply %.0f us"
+            % tuple(1e6 * p / e2e_steps for p in parts))
+        e2e_ms_max = max_over_ranks(e2e_ms)
+        e2e_value = total_chunks / (e2e_ms_max * 1e-3)
+        assert np.array_equal(cs.changed != 0, d_changed.cpu().numpy() != 0), "handle path and device path disagree"
+        log(f"end-to-end (batch handles, {touched_units} touched units): {e2e_ms_max:.3f} ms/step")
+        it.profile_stages(True)
+        it.reset()
+        cs.forget()
+        cs.apply(it)
+        e2e_trace = it.host_trace()
+        it.profile_stages(False)
+        log(f"end-to-end phases: {e2e_trace}")
+        # (2) the same world as two dense host arrays with no per-batch summary (vx_apply_batches_slab):
+        # every mask byte has to cross the bus
         roots_host = np.zeros(n, np.uint64)
         changed_host = np.zeros(n, np.uint8)
         for _ in range(2):
             it.reset()
             it.apply_batches_slab(DEPTH, h_masks.numpy(), h_values.numpy(), roots_out=roots_host,
                                   changed_out=changed_host)
-        e2e_steps = max(3, min(args.steps, 5))
+        slab_steps = max(3, min(args.steps, 5))
         barrier()
         t0 = time.perf_counter()
-        for _ in range(e2e_steps):
+        for _ in range(slab_steps):
             it.reset()
             it.apply_batches_slab(DEPTH, h_masks.numpy(), h_values.numpy(), roots_out=roots_host,
                                   changed_out=changed_host)
         torch.cuda.synchronize()
-        e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+        slab_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / slab_steps)
         barrier()
-        e2e_ms_max = max_over_ranks(e2e_ms)
-        e2e_value = total_chunks / (e2e_ms_max * 1e-3)
-        log(f"end-to-end (host batches): {e2e_ms_max:.3f} ms/step")
+        e2e_slab = {"value": total_chunks / (slab_ms * 1e-3), "unit": "chunks/s", "ms_per_step": slab_ms,
+                    "h2d_bytes_per_step": int(masks.nbytes + 0),
+                    "path": "vx_apply_batches_slab on two dense pinned arrays (masks H2D by copy engine in slabs, "
+                            "values zero-copy for blocks with a set bit)"}
+        log(f"end-to-end (dense slab): {slab_ms:.3f} ms/step")
+        del cs, trees, batches
 
     # ---------------------------------------------------------------- roofline of the apply kernel
     peak, peak_src = peaks()
@@ -451,13 +503,17 @@ def main():
                        "step": "vx_interner_reset_async + one vx_apply_batches_device call",
                        "per_step_counters": dbg},
             "e2e": {"value": e2e_value, "unit": "chunks/s", "ms_per_step": e2e_ms_max,
-                    # masks are DMA-copied; values stay in pinned host memory and the kernel reads, over PCIe,
-                    # only those of blocks with a set bit (lower bound: 8 B each, fetched as 32 B sectors)
-                    "h2d_bytes_per_step": int(masks.nbytes + touched_blocks * 8),
+                    # per step: descriptors (8 B per chunk + 4 B per touched unit) by the copy engine; touched
+                    # units' masks (1 KiB each) and the values of blocks with a set bit (8 B each, lower bound:
+                    # the bus moves 32-byte sectors) by loads the staging kernel issues on pinned host memory
+                    "h2d_bytes_per_step": int(n * 8 + touched_units * 4 + touched_units * 1024 + touched_blocks * 8),
                     "host_input_bytes_per_step": int(masks.nbytes + values.nbytes),
                     "d2h_bytes_per_step": int(n * 9),
-                    "path": "vx_apply_batches_slab on pinned host batches (masks H2D by copy engine in slabs, "
-                            "values zero-copy), roots + changed flags D2H"},
+                    "touched_units": int(touched_units),
+                    "path": "vx_apply_batches on n Batch + n VoxTree handles (batches in pinned host memory; "
+                            "stage_units_kernel pulls touched units over PCIe, builders run on the device slab), "
+                            "roots + changed flags D2H into the VoxTree handles",
+                    "phases_us": e2e_trace, "dense_slab_variant": e2e_slab},
             "gpu_launches": args.steps * launches_per_step,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,

@@ -125,6 +125,15 @@ int vx_batch_to_fill(const vx_batch*, int64_t* out); /* 1 = Some(*out), 0 = None
 size_t vx_batch_size(const vx_batch*);
 int vx_batch_has_patches(const vx_batch*);
 void vx_batch_mark_patched(vx_batch*);
+/* Array form of Batch::set (one FFI crossing for n voxels): xyz[n][3], voxels[n]; stops at the first error. */
+int vx_batch_set_many(vx_batch*, size_t n, const int32_t* xyz, const int64_t* voxels);
+/* Replaces the batch's content with dense arrays in Batch layout (masks[B][2], values[B][8]) — what a
+ * caller holding a reference `Batch` hands over (`batch.masks()`, `batch.values()`, batch.rs:86-105);
+ * to_fill becomes None, has_patches = any mask bit. */
+int vx_batch_assign(vx_batch*, const uint8_t* masks, const void* values);
+/* Next to has_patches (batch.rs:44) a batch records which units of 512 Morton-consecutive blocks
+ * Batch::set ever touched; vx_apply_batches moves only those across the bus.  Returns their number. */
+int vx_batch_touched_units(const vx_batch*);
 uint8_t vx_batch_max_depth(const vx_batch*);
 vx_dtype vx_batch_dtype(const vx_batch*);
 
@@ -143,6 +152,9 @@ int vx_tree_is_leaf(const vx_tree*);
 int vx_tree_is_dirty(const vx_tree*);                 /* VoxOpsDirty   voxtree.rs:355-370 */
 void vx_tree_mark_dirty(vx_tree*);
 void vx_tree_clear_dirty(vx_tree*);
+/* After vx_interner_reset every tree built in that interner dangles; this makes n of them empty again
+ * without touching the interner (what dropping and re-creating the VoxTrees does in the reference). */
+int vx_trees_forget(vx_tree* const* trees, size_t n);
 
 /* VoxTree::apply_batch — voxtree.rs:303-328 (set_batch_at_root :708-722,
  * set_batch_at_depth_iterative :724-1118).  Returns 1 = changed, 0 = unchanged, <0 error.
@@ -154,6 +166,9 @@ int vx_tree_apply_batch(vx_interner*, vx_tree*, const vx_batch*);
  * permutation of node indices.  `changed` (may be NULL) receives 1/0 per tree. */
 int vx_apply_batches(vx_interner*, vx_tree* const* trees, const vx_batch* const* batches, size_t n,
                      uint8_t* changed);
+/* Host batches are read in place (pinned + mapped arena slots): only the touched units' masks and the
+ * values of blocks with a set bit cross PCIe (vx_stage.cuh), so a sparse world moves a few percent of its
+ * batch bytes.  The device slab is bounded by VX_STAGE_MAX_BYTES (default 4 GiB; larger calls are sliced). */
 
 /* Slab form of the same for FRESH trees: n chunks of depth `max_depth`, arrays laid out
  * masks[n][B][2], values[n][B][8].  `flags` (may be NULL = patches, no fill): bit0 = to_fill is

@@ -40,6 +40,7 @@ ABI_SYMBOLS = [
     "vx_batch_create", "vx_batch_destroy", "vx_batch_set", "vx_batch_fill", "vx_batch_clear",
     "vx_batch_masks", "vx_batch_values", "vx_batch_blocks", "vx_batch_to_fill", "vx_batch_size",
     "vx_batch_has_patches", "vx_batch_mark_patched", "vx_batch_max_depth", "vx_batch_dtype",
+    "vx_batch_set_many", "vx_batch_assign", "vx_batch_touched_units", "vx_trees_forget",
     "vx_tree_create", "vx_tree_destroy", "vx_tree_root_id", "vx_tree_set_root_id", "vx_tree_max_depth",
     "vx_tree_voxels_per_axis", "vx_tree_is_empty", "vx_tree_is_leaf", "vx_tree_is_dirty",
     "vx_tree_mark_dirty", "vx_tree_clear_dirty", "vx_tree_apply_batch", "vx_apply_batches",
@@ -87,6 +88,7 @@ def lib():
     L.vx_interner_debug_counters.argtypes = [vp, vp]
     L.vx_interner_profile_stages.argtypes = [vp, C.c_int]
     L.vx_interner_stage_ms.argtypes = [vp, vp, vp]
+    L.vx_interner_host_trace.argtypes = [vp, vp]
     L.vx_interner_download.restype = i64
     L.vx_interner_download.argtypes = [vp, sz, vp, vp, vp, vp, vp]
     L.vx_interner_sync.argtypes = [vp]
@@ -111,6 +113,10 @@ def lib():
     L.vx_batch_has_patches.argtypes = [vp]
     L.vx_batch_mark_patched.argtypes = [vp]
     L.vx_batch_mark_patched.restype = None
+    L.vx_batch_set_many.argtypes = [vp, sz, vp, vp]
+    L.vx_batch_assign.argtypes = [vp, vp, vp]
+    L.vx_batch_touched_units.argtypes = [vp]
+    L.vx_trees_forget.argtypes = [vp, sz]
     L.vx_batch_max_depth.restype = C.c_uint8
     L.vx_batch_max_depth.argtypes = [vp]
     L.vx_batch_dtype.argtypes = [vp]
@@ -253,6 +259,14 @@ class VoxInterner:
         k = _ck(lib().vx_interner_stage_ms(self.h, ms, names))
         return [(names[i].decode(), float(ms[i])) for i in range(k)]
 
+    def host_trace(self) -> dict:
+        """Phases of the last vx_apply_batches call made while profile_stages was on (microseconds)."""
+        a = np.zeros(8, np.float64)
+        _ck(lib().vx_interner_host_trace(self.h, _ptr(a)))
+        keys = ["host_lists_us", "host_enqueue_us", "host_wait_us", "dev_descriptors_memset_us", "dev_stage_us",
+                "dev_build_us", "touched_units"]
+        return {k: float(v) for k, v in zip(keys, a)}
+
     def download(self) -> dict:
         n = self.next_index
         ch = np.zeros((n, 8), np.uint64)
@@ -310,15 +324,30 @@ class Batch:
         self.h = lib().vx_batch_create(max_depth, dtype)
         if not self.h:
             raise VoxelisError(-1, lib().vx_last_error().decode())
-        B = lib().vx_batch_blocks(self.h)
-        self.masks = np.ctypeslib.as_array(C.cast(lib().vx_batch_masks(self.h), C.POINTER(C.c_uint8)), (B, 2))
-        ct = C.c_uint8 if dtype == U8 else C.c_int32
-        self.values = np.ctypeslib.as_array(C.cast(lib().vx_batch_values(self.h), C.POINTER(ct)), (B, 8))
+        self._masks = self._values = None
+
+    # Raw views of the batch's arrays (Batch::masks / values, batch.rs:86-105).  Asking for them tells the
+    # library that the caller may write the arrays directly: such a batch must be mark_patched() after
+    # writing, and apply then moves its masks over the bus instead of the one-bit-per-block map.
+    @property
+    def masks(self):
+        if self._masks is None:
+            B = lib().vx_batch_blocks(self.h)
+            self._masks = np.ctypeslib.as_array(C.cast(lib().vx_batch_masks(self.h), C.POINTER(C.c_uint8)), (B, 2))
+        return self._masks
+
+    @property
+    def values(self):
+        if self._values is None:
+            B = lib().vx_batch_blocks(self.h)
+            ct = C.c_uint8 if self.dtype == U8 else C.c_int32
+            self._values = np.ctypeslib.as_array(C.cast(lib().vx_batch_values(self.h), C.POINTER(ct)), (B, 8))
+        return self._values
 
     def __del__(self):
         try:
             if getattr(self, "h", None):
-                self.masks = self.values = None
+                self._masks = self._values = None
                 lib().vx_batch_destroy(self.h)
                 self.h = None
         except Exception:
@@ -326,6 +355,23 @@ class Batch:
 
     def set(self, interner, pos, v) -> bool:          # batch.rs:211-213
         return _ck(lib().vx_batch_set(self.h, int(pos[0]), int(pos[1]), int(pos[2]), int(v))) == 1
+
+    def set_many(self, xyz, values) -> bool:
+        """Array form of set(): xyz [n][3], values [n]."""
+        xyz = np.ascontiguousarray(xyz, np.int32)
+        values = np.ascontiguousarray(values, np.int64)
+        return _ck(lib().vx_batch_set_many(self.h, xyz.shape[0], _ptr(xyz), _ptr(values))) == 1
+
+    def assign(self, masks, values):
+        """Takes over dense arrays in Batch layout (masks [B][2], values [B][8])."""
+        masks = np.ascontiguousarray(masks, np.uint8)
+        values = np.ascontiguousarray(values, _NP[self.dtype])
+        B = lib().vx_batch_blocks(self.h)
+        assert masks.size == 2 * B and values.size == 8 * B
+        _ck(lib().vx_batch_assign(self.h, _ptr(masks), _ptr(values)))
+
+    @property
+    def touched_units(self) -> int: return _ck(lib().vx_batch_touched_units(self.h))
 
     def fill(self, interner, v): _ck(lib().vx_batch_fill(self.h, int(v)))   # batch.rs:218-221
     def clear(self, interner=None): _ck(lib().vx_batch_clear(self.h))       # batch.rs:223-225
@@ -393,12 +439,36 @@ class VoxTree:
     def voxels_per_axis(self) -> int: return lib().vx_tree_voxels_per_axis(self.h)
 
 
+class ChunkSet:
+    """n (tree, batch) pairs with their handle arrays built once — the grid driver's view of a world
+    (world/voxmodel.rs:27-59 keeps coord -> chunk; voxelis-voxelize/src/lib.rs:357-361 loops over it)."""
+
+    def __init__(self, trees, batches):
+        assert len(trees) == len(batches)
+        self.trees, self.batches, self.n = list(trees), list(batches), len(trees)
+        self.th = (C.c_void_p * self.n)(*[t.h for t in self.trees])
+        self.bh = (C.c_void_p * self.n)(*[b.h for b in self.batches])
+        self.changed = np.zeros(self.n, np.uint8)
+
+    def apply(self, interner: VoxInterner):
+        _ck(lib().vx_apply_batches(interner.h, self.th, self.bh, self.n, _ptr(self.changed)))
+        return self.changed
+
+    def forget(self):
+        """After interner.reset(): every tree is empty again."""
+        _ck(lib().vx_trees_forget(self.th, self.n))
+
+    def roots(self) -> np.ndarray:
+        f = lib().vx_tree_root_id
+        return np.array([f(h) for h in self.th], np.uint64)
+
+
 def apply_batches(interner: VoxInterner, trees, batches):
     """New multi-chunk entry (vx_apply_batches): result == serial application in index order."""
+    return ChunkSet(trees, batches).apply(interner).astype(bool)
+
+
+def trees_forget(trees):
+    """After interner.reset(): make the trees empty again (vx_trees_forget)."""
     n = len(trees)
-    assert n == len(batches)
-    th = (C.c_void_p * n)(*[t.h for t in trees])
-    bh = (C.c_void_p * n)(*[b.h for b in batches])
-    changed = np.zeros(n, np.uint8)
-    _ck(lib().vx_apply_batches(interner.h, th, bh, n, _ptr(changed)))
-    return changed.astype(bool)
+    _ck(lib().vx_trees_forget((C.c_void_p * n)(*[t.h for t in trees]), n))

@@ -44,6 +44,8 @@ struct BulkArgs {
     u32* cube_flag;   // [U/8] == epoch: some unit of this group of eight is not empty (no per-call clearing)
     u32 epoch;        // call counter of the interner's bulk scratch, never 0
     u32* cube_list;   // [<= U/8] those groups, in the order they were first seen (count in cnt[5])
+    const u32* unit_list;  // optional: the only units that can hold a set bit (host batches know, vx_stage.cuh);
+    u32 n_listed;          // the others are neither read nor planned (their unit_cm / roots were zeroed by memsets)
     unsigned long long units;  // U
     u32 n;
     u32 depth;
@@ -85,27 +87,35 @@ __global__ void __launch_bounds__(256) bulk_plan_kernel(BulkArgs a) {
     // register queue: the masks of the next PLAN_AHEAD units of this warp are in flight while one is planned
     constexpr int PLAN_AHEAD = 1;
     uint4 qa[PLAN_AHEAD], qb[PLAN_AHEAD];
+    unsigned long long qw[PLAN_AHEAD];
+    const bool listed = a.unit_list != nullptr;
+    const unsigned long long total = listed ? a.n_listed : a.units;
 #pragma unroll
     for (int d = 0; d < PLAN_AHEAD; ++d) {
         qa[d] = qb[d] = make_uint4(0, 0, 0, 0);
-        if (warp + d * nwarps < a.units) {
-            ld_stream_v8(a.masks + (warp + d * nwarps) * (UNIT_BLOCKS * 2) + lane * 32, &qa[d], &qb[d]);
+        qw[d] = 0;
+        if (warp + d * nwarps < total) {
+            qw[d] = listed ? a.unit_list[warp + d * nwarps] : warp + d * nwarps;
+            ld_stream_v8(a.masks + qw[d] * (UNIT_BLOCKS * 2) + lane * 32, &qa[d], &qb[d]);
         }
     }
-    for (unsigned long long w = warp; w < a.units; w += nwarps) {
+    for (unsigned long long e = warp; e < total; e += nwarps) {
         const uint4 q0 = qa[0], q1 = qb[0];
+        const unsigned long long w = qw[0];
 #pragma unroll
         for (int d = 0; d + 1 < PLAN_AHEAD; ++d) {
             qa[d] = qa[d + 1];
             qb[d] = qb[d + 1];
+            qw[d] = qw[d + 1];
         }
-        if (w + PLAN_AHEAD * nwarps < a.units) {
-            ld_stream_v8(a.masks + (w + PLAN_AHEAD * nwarps) * (UNIT_BLOCKS * 2) + lane * 32, &qa[PLAN_AHEAD - 1],
+        if (e + PLAN_AHEAD * nwarps < total) {
+            qw[PLAN_AHEAD - 1] = listed ? a.unit_list[e + PLAN_AHEAD * nwarps] : e + PLAN_AHEAD * nwarps;
+            ld_stream_v8(a.masks + qw[PLAN_AHEAD - 1] * (UNIT_BLOCKS * 2) + lane * 32, &qa[PLAN_AHEAD - 1],
                          &qb[PLAN_AHEAD - 1]);
         }
         // the first upper launch only visits groups of eight units that hold something; the first unit of
         // every group says "empty" for it beforehand (roots / changed for D = 5, the dense level above else)
-        if (lane == 0 && (w & 7) == 0 && a.blocks > UNIT_BLOCKS) {
+        if (!listed && lane == 0 && (w & 7) == 0 && a.blocks > UNIT_BLOCKS) {
             if (a.blocks == 8 * UNIT_BLOCKS) {
                 a.roots[w >> 3] = 0;
                 if (a.changed) a.changed[w >> 3] = 0;

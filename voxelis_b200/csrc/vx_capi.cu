@@ -7,9 +7,12 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -20,6 +23,7 @@
 #include "vx_read.cuh"
 #include "vx_release.cuh"
 #include "vx_dedup.cuh"
+#include "vx_stage.cuh"
 
 using namespace vx;
 
@@ -98,6 +102,9 @@ struct vx_interner {
     cudaEvent_t pev[10]{};
     const char* pname[9]{};
     int pstages = 0;
+    // diagnostic: phases of the last vx_apply_batches call (host microseconds / device milliseconds)
+    std::vector<cudaEvent_t> tevs;
+    double trace[8]{};
     uint64_t free_host = 0;      // entries in the free list
     uint64_t tombs_host = 0;     // deleted table slots since the last rehash
     std::mutex mu;
@@ -105,19 +112,28 @@ struct vx_interner {
 
 struct vx_tree {
     uint8_t depth;
-    vx_block_id root;
     bool dirty;
+    uint32_t stamp;  // last vx_apply_batches call that listed this tree (duplicate detection)
+    vx_block_id root;
 };
 
+// Field order: everything vx_apply_batches reads per batch sits in the first cache line (D <= 6).
 struct vx_batch {
-    uint8_t depth;
-    vx_dtype dtype;
-    size_t blocks;
-    uint8_t* masks;  // pinned
-    void* values;    // pinned
-    bool has_fill;
+    uint64_t alias;   // device-visible address of the slot
     int64_t fill;
-    bool has_patches;
+    uint8_t* masks;   // one slot of the pinned + mapped batch arena: masks[B][2], values[B][8], occ[B/8]
+    void* values;
+    uint8_t* occ;     // one bit per block: some voxel of the block was set to a non-default value
+    // host-side occupancy summary next to has_patches (core/batch.rs:44): one bit per unit of
+    // `unit_blocks` Morton-consecutive blocks that Batch::set ever touched.  apply moves only those
+    // units across the bus (vx_stage.cuh).
+    uint32_t units, unit_blocks;
+    uint8_t depth;
+    bool has_fill, has_patches;
+    bool raw_exposed;     // the caller holds raw array pointers: clear() wipes everything, apply trusts only the masks
+    vx_dtype dtype;
+    uint64_t touched[8];  // <= 512 units (D = 7), inline
+    size_t blocks, slot_bytes;
 };
 
 namespace {
@@ -269,6 +285,20 @@ size_t bulk_scratch_bytes(size_t n, size_t blocks) {
     need += units * 5 + 2 * 256 + units * 8 + units + 2 * 256 + units * 4 + 256 + units + 2 * 256;
     return need;
 }
+size_t stage_max_bytes() {  // device slab of vx_apply_batches (host batches are staged in slices of this size)
+    if (const char* e = getenv("VX_STAGE_MAX_BYTES")) {
+        unsigned long long v = strtoull(e, nullptr, 10);
+        if (v >= (1ull << 16)) return size_t(v);
+    }
+    return size_t(4) << 30;
+}
+size_t stage_slices() {
+    if (const char* e = getenv("VX_STAGE_SLICES")) {
+        long v = strtol(e, nullptr, 10);
+        if (v >= 1 && v <= 64) return size_t(v);
+    }
+    return 0;  // default: geometric cuts, see vx_apply_batches
+}
 size_t bulk_max_bytes() {
     if (const char* e = getenv("VX_BULK_MAX_BYTES")) return size_t(strtoull(e, nullptr, 10));
     return size_t(8) << 30;
@@ -294,7 +324,7 @@ cudaError_t launch_chained(void (*kernel)(P...), unsigned grid, unsigned block, 
 
 template <class T>
 int launch_bulk_t(vx_interner* it, int depth, size_t n, const u8* d_masks, const void* d_values, u64* d_roots,
-                  u8* d_changed, cudaStream_t s) {
+                  u8* d_changed, cudaStream_t s, const u32* d_unit_list = nullptr, u32 n_listed = 0) {
     const size_t blocks = blocks_for_depth(depth), nb = n * blocks, units = nb / UNIT_BLOCKS;
     const size_t need = bulk_scratch_bytes(n, blocks);
     if (need > it->bulk_bytes) {
@@ -356,15 +386,27 @@ int launch_bulk_t(vx_interner* it, int depth, size_t n, const u8* d_masks, const
     a.dense_units = (u32*)take(units * 4);
     a.cube_flag = it->bulk_flags;
     a.cube_list = (u32*)take(units / 8 * 4 + 4);
+    a.unit_list = d_unit_list;
+    a.n_listed = n_listed;
     prof_begin(it, s);
     CU_TRY(cudaMemsetAsync(a.cnt, 0, 32, s));
+    if (d_unit_list) {  // what the plan kernel writes for every unit / group it visits, for the ones it will not visit
+        CU_TRY(cudaMemsetAsync(a.unit_cm, 0, units, s));
+        CU_TRY(cudaMemsetAsync(d_roots, 0, n * 8, s));
+        if (d_changed) CU_TRY(cudaMemsetAsync(d_changed, 0, n, s));
+        if (blocks > 8 * UNIT_BLOCKS) CU_TRY(cudaMemsetAsync(a.dense[1], 0, units, s));
+    }
     const size_t smem = apply_smem_bytes<T>();
-    int occ = 0;
-    CU_TRY(cudaFuncSetAttribute(bulk_blocks_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    CU_TRY(cudaFuncSetAttribute(bulk_level_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    CU_TRY(cudaFuncSetAttribute(bulk_upper_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    CU_TRY(cudaFuncSetAttribute(bulk_dense_units_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bulk_level_kernel<T>, CTA_THREADS, smem));
+    static thread_local int occ_for_device[64] = {};  // function attributes are per device: set them once each
+    int& occ = occ_for_device[it->device & 63];
+    if (occ == 0) {
+        CU_TRY(cudaFuncSetAttribute(bulk_blocks_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        CU_TRY(cudaFuncSetAttribute(bulk_level_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        CU_TRY(cudaFuncSetAttribute(bulk_upper_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        CU_TRY(cudaFuncSetAttribute(bulk_dense_units_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bulk_level_kernel<T>, CTA_THREADS, smem));
+        occ = std::max(occ, 1);
+    }
     const size_t max_ctas = size_t(std::max(occ, 1)) * it->sm_count;
     auto grid_for = [&](size_t threads) {
         return unsigned(std::max<size_t>(1, std::min<size_t>((threads + CTA_THREADS - 1) / CTA_THREADS, max_ctas)));
@@ -372,7 +414,8 @@ int launch_bulk_t(vx_interner* it, int depth, size_t n, const u8* d_masks, const
     {   // plan: a warp per unit, enough warps to keep the memory system full
         // ~8 units per warp: short CTAs that the hardware scheduler balances (units differ a lot in cost)
         static const size_t upw = getenv("VX_PLAN_UPW") ? size_t(atoi(getenv("VX_PLAN_UPW"))) : 8;
-        const size_t ctas = std::max<size_t>((units + 8 * upw - 1) / (8 * upw), std::min<size_t>((units + 7) / 8, size_t(it->sm_count) * 8));
+        const size_t pu = d_unit_list ? size_t(n_listed) : units;
+        const size_t ctas = std::max<size_t>((pu + 8 * upw - 1) / (8 * upw), std::min<size_t>((pu + 7) / 8, size_t(it->sm_count) * 8));
         bulk_plan_kernel<<<unsigned(std::max<size_t>(ctas, 1)), 256, 0, s>>>(a);
         CU_TRY(cudaGetLastError());
         prof_mark(it, s, "bulk_plan_kernel");
@@ -431,8 +474,12 @@ bool use_bulk_builder(int depth, size_t n, const u8* d_masks, const u8* d_flags,
 // d_old_roots == nullptr: every tree is fresh (the north-star path).
 int launch_apply(vx_interner* it, int depth, size_t n, const u8* d_masks, const void* d_values, const u8* d_flags,
                  const int64_t* d_fills, u64* d_roots, u8* d_changed, cudaStream_t s,
-                 const u64* d_old_roots = nullptr) {
+                 const u64* d_old_roots = nullptr, const u32* d_unit_list = nullptr, u32 n_listed = 0) {
     if (n > 0xFFFFFFFFull) return fail(VX_E_INVALID, "too many chunks in one call");
+    if (d_unit_list) {  // the caller checked with bulk_takes_listed(): one bulk call, only the listed units hold anything
+        return it->dtype == VX_U8 ? launch_bulk_t<u8>(it, depth, n, d_masks, d_values, d_roots, d_changed, s, d_unit_list, n_listed)
+                                  : launch_bulk_t<int32_t>(it, depth, n, d_masks, d_values, d_roots, d_changed, s, d_unit_list, n_listed);
+    }
     if (n > 0 && use_bulk_builder(depth, n, d_masks, d_flags, d_old_roots)) {
         // bound the level lists: very large calls go through in slices (any order gives the same DAG)
         const size_t blocks = blocks_for_depth(depth);
@@ -460,6 +507,12 @@ int launch_apply(vx_interner* it, int depth, size_t n, const u8* d_masks, const 
                                              d_changed, s);
     return launch_apply_t<int32_t, false>(it, depth, n, d_masks, d_values, d_flags, d_fills, nullptr, d_roots,
                                           d_changed, s);
+}
+
+// True when a call of this shape goes to the bulk builder in ONE piece, so it can take a list of units.
+bool bulk_takes_listed(int depth, size_t n, const u8* d_masks, const u8* d_flags, const u64* d_old_roots) {
+    return n > 0 && n <= 0xFFFFFFFFull && use_bulk_builder(depth, n, d_masks, d_flags, d_old_roots) &&
+           bulk_scratch_bytes(n, blocks_for_depth(depth)) <= bulk_max_bytes();
 }
 
 int valid_depth(int d) { return d >= 2 && d <= 7; }
@@ -678,6 +731,8 @@ void vx_interner_destroy(vx_interner* it) {
     cudaFree(it->bulk_flags);
     for (auto& e : it->pev)
         if (e) cudaEventDestroy(e);
+    for (auto& e : it->tevs)
+        if (e) cudaEventDestroy(e);
     for (int i = 0; i < 2; ++i) {
         cudaFree(it->stage[i]);
         if (it->ev_copied[i]) cudaEventDestroy(it->ev_copied[i]);
@@ -814,6 +869,11 @@ int vx_interner_profile_stages(vx_interner* it, int on) {
     return VX_OK;
 }
 // ms[i] / names[i] for i < return value (<= 9); synchronises the interner's last launches.
+int vx_interner_host_trace(const vx_interner* it, double out[8]) {
+    if (!it || !out) return fail(VX_E_INVALID, "null argument");
+    memcpy(out, it->trace, sizeof(it->trace));
+    return VX_OK;
+}
 int vx_interner_stage_ms(vx_interner* it, float ms[9], const char* names[9]) {
     if (!it || !ms) return fail(VX_E_INVALID, "null argument");
     if (!it->prof) return 0;
@@ -871,6 +931,81 @@ int64_t vx_interner_download(const vx_interner* cit, size_t cap, vx_block_id* ch
 }
 
 // ------------------------------------------------------------------------------- batch
+namespace {
+
+// Pinned + mapped host memory for batches, carved into equal slots per (depth, dtype) size class.
+// One cudaHostAlloc per batch would cost ~100 us each and thousands of pinned regions; slabs grow
+// geometrically to 64 MiB.  Slabs are never returned to the OS (slots are recycled), and are
+// deliberately not freed at process exit (the CUDA context may already be gone).
+struct BatchArena {
+    struct Class {
+        std::vector<u8*> free_slots;
+        size_t next_slab = 0;
+    };
+    std::mutex mu;
+    std::map<size_t, Class> classes;
+    std::map<u8*, std::pair<size_t, u64>> slabs;  // host base -> (bytes, device-visible base)
+
+    u8* take(size_t slot, u64* alias) {
+        std::lock_guard<std::mutex> lk(mu);
+        Class& c = classes[slot];
+        if (c.free_slots.empty()) {
+            if (c.next_slab == 0) c.next_slab = std::max<size_t>(slot, size_t(1) << 20);
+            size_t count = std::max<size_t>(1, c.next_slab / slot);
+            u8* base = nullptr;
+            if (cudaHostAlloc((void**)&base, count * slot, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+                cudaGetLastError();
+                return nullptr;
+            }
+            void* dv = nullptr;
+            if (cudaHostGetDevicePointer(&dv, base, 0) != cudaSuccess) {
+                cudaGetLastError();
+                cudaFreeHost(base);
+                return nullptr;
+            }
+            slabs[base] = {count * slot, u64(reinterpret_cast<uintptr_t>(dv))};
+            for (size_t i = count; i-- > 0;) c.free_slots.push_back(base + i * slot);
+            c.next_slab = std::min<size_t>(c.next_slab * 2, std::max<size_t>(slot, size_t(64) << 20));
+        }
+        u8* p = c.free_slots.back();
+        c.free_slots.pop_back();
+        auto it = slabs.upper_bound(p);
+        --it;
+        *alias = it->second.second + u64(p - it->first);
+        return p;
+    }
+    void give(u8* p, size_t slot) {
+        std::lock_guard<std::mutex> lk(mu);
+        classes[slot].free_slots.push_back(p);
+    }
+};
+BatchArena& arena() {
+    static BatchArena* a = new BatchArena();
+    return *a;
+}
+
+inline void batch_touch(vx_batch* b, size_t block) {
+    size_t u = block / b->unit_blocks;
+    b->touched[u >> 6] |= uint64_t(1) << (u & 63);
+    b->occ[block >> 3] |= u8(1u << (block & 7));
+}
+// Rebuilds the occupancy summary from the arrays (after the caller bulk-wrote them).
+void batch_rescan(vx_batch* b) {
+    memset(b->touched, 0, sizeof(b->touched));
+    memset(b->occ, 0, (b->blocks + 7) / 8);
+    for (uint32_t u = 0; u < b->units; ++u) {
+        const uint64_t* w = reinterpret_cast<const uint64_t*>(b->masks + size_t(u) * b->unit_blocks * 2);
+        uint64_t any = 0;
+        for (size_t k = 0, e = size_t(b->unit_blocks) * 2 / 8; k < e; ++k) any |= w[k];
+        if (!(any & 0x00FF00FF00FF00FFull)) continue;  // set_mask bytes
+        b->touched[u >> 6] |= uint64_t(1) << (u & 63);
+        for (size_t p = size_t(u) * b->unit_blocks, e = p + b->unit_blocks; p < e; ++p)
+            if (b->masks[2 * p]) b->occ[p >> 3] |= u8(1u << (p & 7));
+    }
+}
+
+}  // namespace
+
 vx_batch* vx_batch_create(uint8_t max_depth, vx_dtype dtype) {
     if (!valid_depth(max_depth) || (dtype != VX_U8 && dtype != VX_I32)) {
         fail(VX_E_INVALID, "vx_batch_create: max_depth must be in [2,7] and dtype u8/i32");
@@ -883,22 +1018,28 @@ vx_batch* vx_batch_create(uint8_t max_depth, vx_dtype dtype) {
     b->has_fill = false;
     b->fill = 0;
     b->has_patches = false;
-    // pinned so apply can DMA straight from the batch; falls back to pageable if no device
+    b->raw_exposed = false;
+    b->unit_blocks = uint32_t(std::min<size_t>(b->blocks, 512));
+    b->units = uint32_t(b->blocks / b->unit_blocks);
+    memset(b->touched, 0, sizeof(b->touched));
+    // pinned + mapped so apply can read the batch in place over PCIe; no device, no batch
     size_t mb = b->blocks * 2, vb = b->blocks * 8 * dtype_size(dtype);
-    if (cudaMallocHost((void**)&b->masks, mb + vb) != cudaSuccess) {
-        cudaGetLastError();
-        fail(VX_E_CUDA, "vx_batch_create: cudaMallocHost failed (no CUDA device?)");
+    const size_t ob = (b->blocks + 7) / 8;
+    b->slot_bytes = (mb + vb + ob + 3 + 255) & ~size_t(255);  // +3: the staging kernel reads the bitmap as 32-bit words
+    b->masks = arena().take(b->slot_bytes, &b->alias);
+    if (!b->masks) {
+        fail(VX_E_CUDA, "vx_batch_create: cudaHostAlloc failed (no CUDA device?)");
         delete b;
         return nullptr;
     }
     b->values = b->masks + mb;
-    memset(b->masks, 0, mb + vb);
+    b->occ = b->masks + mb + vb;
+    memset(b->masks, 0, b->slot_bytes);
     return b;
 }
 void vx_batch_destroy(vx_batch* b) {
     if (!b) return;
-    cudaFreeHost(b->masks);
-    cudaGetLastError();
+    arena().give(b->masks, b->slot_bytes);
     delete b;
 }
 
@@ -932,6 +1073,7 @@ int vx_batch_set(vx_batch* b, int x, int y, int z, int64_t voxel) {
     if (nonzero) {  // batch.rs:162-168
         b->masks[2 * p] |= bit;
         b->masks[2 * p + 1] &= u8(~bit);
+        batch_touch(b, p);
     } else {
         b->masks[2 * p] &= u8(~bit);
         b->masks[2 * p + 1] |= bit;
@@ -941,7 +1083,19 @@ int vx_batch_set(vx_batch* b, int x, int y, int z, int64_t voxel) {
 }
 int vx_batch_clear(vx_batch* b) {
     if (!b) return fail(VX_E_INVALID, "null batch");
-    memset(b->masks, 0, b->blocks * 2 + b->blocks * 8 * dtype_size(b->dtype));
+    const size_t vsz = 8 * dtype_size(b->dtype);
+    if (b->raw_exposed) {
+        memset(b->masks, 0, b->blocks * 2 + b->blocks * vsz);
+    } else if (b->has_patches) {
+        // only set() wrote into the arrays.  Units with a set bit are known; a clear_mask bit (value 0,
+        // batch.rs:165-168) can sit anywhere, so the masks are wiped whole and the values per touched unit.
+        memset(b->masks, 0, b->blocks * 2);
+        for (uint32_t u = 0; u < b->units; ++u)
+            if (b->touched[u >> 6] >> (u & 63) & 1)
+                memset((u8*)b->values + size_t(u) * b->unit_blocks * vsz, 0, size_t(b->unit_blocks) * vsz);
+    }
+    memset(b->touched, 0, sizeof(b->touched));
+    memset(b->occ, 0, (b->blocks + 7) / 8);
     b->has_fill = false;
     b->fill = 0;
     b->has_patches = false;
@@ -954,8 +1108,14 @@ int vx_batch_fill(vx_batch* b, int64_t value) {
     b->fill = b->dtype == VX_U8 ? int64_t(u8(value)) : int64_t(int32_t(value));
     return VX_OK;
 }
-uint8_t* vx_batch_masks(vx_batch* b) { return b ? b->masks : nullptr; }
-void* vx_batch_values(vx_batch* b) { return b ? b->values : nullptr; }
+uint8_t* vx_batch_masks(vx_batch* b) {
+    if (b) b->raw_exposed = true;
+    return b ? b->masks : nullptr;
+}
+void* vx_batch_values(vx_batch* b) {
+    if (b) b->raw_exposed = true;
+    return b ? b->values : nullptr;
+}
 size_t vx_batch_blocks(const vx_batch* b) { return b ? b->blocks : 0; }
 int vx_batch_to_fill(const vx_batch* b, int64_t* out) {
     if (!b) return fail(VX_E_INVALID, "null batch");
@@ -970,7 +1130,56 @@ size_t vx_batch_size(const vx_batch* b) {  // batch.rs:110-121
 }
 int vx_batch_has_patches(const vx_batch* b) { return b && b->has_patches; }
 void vx_batch_mark_patched(vx_batch* b) {
-    if (b) b->has_patches = true;
+    if (!b) return;
+    b->has_patches = true;
+    batch_rescan(b);
+}
+int vx_batch_set_many(vx_batch* b, size_t n, const int32_t* xyz, const int64_t* voxels) {
+    if (!b || (n && (!xyz || !voxels))) return fail(VX_E_INVALID, "null argument");
+    for (size_t i = 0; i < n; ++i) {
+        int rc = vx_batch_set(b, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], voxels[i]);
+        if (rc < 0) return rc;
+    }
+    return int(n > 0);
+}
+int vx_batch_assign(vx_batch* b, const uint8_t* masks, const void* values) {
+    if (!b || !masks || !values) return fail(VX_E_INVALID, "null argument");
+    // same state as replaying Batch::set for every recorded voxel (batch.rs:145-175): a value is kept only
+    // under its set bit, and a set bit whose value is the default cannot come from set() and is dropped
+    const size_t B = b->blocks;
+    bool any = false;
+    for (size_t p = 0; p < B; ++p) {
+        u8 set = masks[2 * p], keep = 0;
+        if (b->dtype == VX_U8) {
+            const u8* v = (const u8*)values + p * 8;
+            u8* o = (u8*)b->values + p * 8;
+            for (int i = 0; i < 8; ++i) {
+                o[i] = (set >> i & 1) ? v[i] : 0;
+                keep |= u8((o[i] != 0) << i);
+            }
+        } else {
+            const int32_t* v = (const int32_t*)values + p * 8;
+            int32_t* o = (int32_t*)b->values + p * 8;
+            for (int i = 0; i < 8; ++i) {
+                o[i] = (set >> i & 1) ? v[i] : 0;
+                keep |= u8((o[i] != 0) << i);
+            }
+        }
+        b->masks[2 * p] = keep;
+        b->masks[2 * p + 1] = masks[2 * p + 1];
+        any = any || (masks[2 * p] | masks[2 * p + 1]) != 0;
+    }
+    b->has_fill = false;
+    b->fill = 0;
+    b->has_patches = any;
+    batch_rescan(b);
+    return VX_OK;
+}
+int vx_batch_touched_units(const vx_batch* b) {
+    if (!b) return fail(VX_E_INVALID, "null batch");
+    int c = 0;
+    for (uint64_t w : b->touched) c += __builtin_popcountll(w);
+    return c;
 }
 uint8_t vx_batch_max_depth(const vx_batch* b) { return b ? b->depth : 0; }
 vx_dtype vx_batch_dtype(const vx_batch* b) { return b ? b->dtype : VX_U8; }
@@ -981,7 +1190,7 @@ vx_tree* vx_tree_create(uint8_t max_depth) {
         fail(VX_E_INVALID, "Max depth exceeds allowed limit (supported: 2..7)");  // max_depth.rs:77-83
         return nullptr;
     }
-    return new vx_tree{max_depth, VX_BLOCK_EMPTY, false};
+    return new vx_tree{max_depth, false, 0u, VX_BLOCK_EMPTY};
 }
 void vx_tree_destroy(vx_tree* t) { delete t; }
 vx_block_id vx_tree_root_id(const vx_tree* t) { return t ? t->root : VX_BLOCK_INVALID; }
@@ -995,6 +1204,15 @@ void vx_tree_mark_dirty(vx_tree* t) {
 }
 void vx_tree_clear_dirty(vx_tree* t) {
     if (t) t->dirty = false;
+}
+int vx_trees_forget(vx_tree* const* trees, size_t n) {
+    if (n && !trees) return fail(VX_E_INVALID, "null argument");
+    for (size_t i = 0; i < n; ++i)
+        if (trees[i]) {
+            trees[i]->root = VX_BLOCK_EMPTY;
+            trees[i]->dirty = false;
+        }
+    return VX_OK;
 }
 
 // ------------------------------------------------------------------------------- apply
@@ -1160,17 +1378,20 @@ int vx_apply_batches(vx_interner* it, vx_tree* const* trees, const vx_batch* con
     if (!it || (n && (!trees || !batches))) return fail(VX_E_INVALID, "null argument");
     if (n == 0) return VX_OK;
     bool fused = true, any_old = false;
+    static std::atomic<uint32_t> g_call{0};
+    const uint32_t stamp = ++g_call;  // a tree may appear only once in the fused path: stamp and compare
     for (size_t i = 0; i < n; ++i) {
+        if (i + 8 < n) {  // the handles are separate heap objects: keep the misses in flight
+            __builtin_prefetch(trees[i + 8]);
+            __builtin_prefetch(batches[i + 8]);
+            __builtin_prefetch((const char*)batches[i + 8] + 64);
+        }
         if (!trees[i] || !batches[i]) return fail(VX_E_INVALID, "null tree or batch");
         if (batches[i]->depth != trees[i]->depth) return fail(VX_E_INVALID, "batch and tree depths differ");
         if (batches[i]->dtype != it->dtype) return fail(VX_E_INVALID, "batch and interner voxel types differ");
-        fused = fused && batches[i]->depth == batches[0]->depth;
+        fused = fused && batches[i]->depth == batches[0]->depth && trees[i]->stamp != stamp;
+        trees[i]->stamp = stamp;
         any_old = any_old || trees[i]->root != VX_BLOCK_EMPTY;
-    }
-    if (fused) {  // a tree may appear only once in the fused path
-        std::vector<const vx_tree*> seen(trees, trees + n);
-        std::sort(seen.begin(), seen.end());
-        fused = std::adjacent_find(seen.begin(), seen.end()) == seen.end();
     }
     if (!fused) {  // mixed depths or repeated trees: the reference's serial loop (lib.rs:357-361)
         for (size_t i = 0; i < n; ++i) {
@@ -1186,43 +1407,179 @@ int vx_apply_batches(vx_interner* it, vx_tree* const* trees, const vx_batch* con
     const int depth = batches[0]->depth;
     const size_t B = blocks_for_depth(depth), mbytes = B * 2, vbytes = B * 8 * dtype_size(it->dtype);
     const size_t per = mbytes + vbytes;
-    // one contiguous device slab for all batches + options + results
-    size_t dev_need = n * per + n * 8 * 3 + n + n + 256;
-    size_t host_need = n * 8 * 3 + n + n;
+    const uint32_t upc = batches[0]->units, ub = batches[0]->unit_blocks;
+    uint32_t upc_log2 = 0;
+    while ((1u << upc_log2) < upc) ++upc_log2;
+    // The batches sit in pinned host memory, each with its list of touched units.  Only those units cross
+    // the bus: per slice, the device slab's masks are zeroed in HBM, stage_units_kernel pulls the touched
+    // units' masks and the values of blocks with a set bit (vx_stage.cuh), and the builders run on the slab.
+    auto now_us = [] {
+        return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    };
+    const double t_begin = now_us();
+    // Slices: a big call is cut so that the bus traffic of slice k+1 (copy_stream) overlaps the build of
+    // slice k (the interner's stream) and the host's list building for slice k+2; two slabs.  By default
+    // the cuts are at n/8 and n/2: a small first slice puts the bus to work early, while the host is still
+    // listing the rest.  VX_STAGE_SLICES=k asks for k equal slices instead.
+    size_t slice = std::max<size_t>(1, std::min<size_t>(n, stage_max_bytes() / (2 * per)));
+    slice = std::min<size_t>(slice, size_t(0xFFFFFFF0u) >> upc_log2);
+    std::vector<size_t> cut{0};
+    if (n >= 8192 && stage_slices() == 0 && (n + 1) / 2 <= slice) {
+        cut.push_back(n / 8);
+        cut.push_back(n / 2);
+        slice = n - n / 2;
+    } else {
+        if (n >= 8192 && stage_slices() > 0) slice = std::min(slice, (n + stage_slices() - 1) / stage_slices());
+        for (size_t lo = slice; lo < n; lo += slice) cut.push_back(lo);
+    }
+    cut.push_back(n);
+    const size_t n_slices = cut.size() - 1;
+    const int n_slabs = n_slices > 1 ? 2 : 1;
+    auto up = [](size_t v) { return (v + 255) & ~size_t(255); };
+    const size_t max_units = n * upc;
+    const size_t slab_bytes = up(slice * mbytes) + up(slice * vbytes);
+    const size_t o_roots = n_slabs * slab_bytes, o_fills = o_roots + up(n * 8), o_old = o_fills + up(n * 8),
+                 o_src = o_old + up(n * 8), o_units = o_src + up(n * 8), o_changed = o_units + up(max_units * 4),
+                 o_flags = o_changed + up(n), dev_need = o_flags + up(n);
+    const size_t h_fills_o = up(n * 8), h_old_o = h_fills_o + up(n * 8), h_src_o = h_old_o + up(n * 8),
+                 h_units_o = h_src_o + up(n * 8), h_changed_o = h_units_o + up(max_units * 4),
+                 h_flags_o = h_changed_o + up(n), host_need = h_flags_o + up(n);
     int rc = ensure_scratch(it, dev_need, host_need);
     if (rc != VX_OK) return rc;
-    u8* dm = (u8*)it->scratch;
-    u8* dv = dm + n * mbytes;
-    u64* d_roots = (u64*)(dv + n * vbytes);
-    int64_t* d_fills = (int64_t*)(d_roots + n);
-    u64* d_old = (u64*)(d_fills + n);
-    u8* d_changed = (u8*)(d_old + n);
-    u8* d_flags = d_changed + n;
-    u64* h_roots = (u64*)it->hscratch;
-    int64_t* h_fills = (int64_t*)(h_roots + n);
-    u64* h_old = (u64*)(h_fills + n);
-    u8* h_changed = (u8*)(h_old + n);
-    u8* h_flags = h_changed + n;
-    cudaStream_t s = it->stream;
-    for (size_t i = 0; i < n; ++i) {
-        const vx_batch* b = batches[i];
-        h_flags[i] = (b->has_fill ? VX_FLAG_FILL : 0) | (b->has_patches ? VX_FLAG_PATCHES : 0);
-        h_fills[i] = b->fill;
-        h_old[i] = trees[i]->root;
-        if (b->has_patches) {
-            CU_TRY(cudaMemcpyAsync(dm + i * mbytes, b->masks, mbytes, cudaMemcpyHostToDevice, s));
-            CU_TRY(cudaMemcpyAsync(dv + i * vbytes, b->values, vbytes, cudaMemcpyHostToDevice, s));
-        }
+    u8* dbase = (u8*)it->scratch;
+    u64* d_roots = (u64*)(dbase + o_roots);
+    int64_t* d_fills = (int64_t*)(dbase + o_fills);
+    u64* d_old = (u64*)(dbase + o_old);
+    u64* d_src = (u64*)(dbase + o_src);
+    u32* d_units = (u32*)(dbase + o_units);
+    u8* d_changed = dbase + o_changed;
+    u8* d_flags = dbase + o_flags;
+    u8* hbase = (u8*)it->hscratch;
+    u64* h_roots = (u64*)hbase;
+    int64_t* h_fills = (int64_t*)(hbase + h_fills_o);
+    u64* h_old = (u64*)(hbase + h_old_o);
+    u64* h_src = (u64*)(hbase + h_src_o);
+    u32* h_units = (u32*)(hbase + h_units_o);
+    u8* h_changed = hbase + h_changed_o;
+    u8* h_flags = hbase + h_flags_o;
+    cudaStream_t s = it->stream, cs = it->copy_stream;
+    const bool trace = it->prof;
+    if (trace) {
+        it->tevs.resize(4 * n_slices, nullptr);
+        for (auto& e : it->tevs)
+            if (!e) CU_TRY(cudaEventCreate(&e));
     }
-    CU_TRY(cudaMemcpyAsync(d_flags, h_flags, n, cudaMemcpyHostToDevice, s));
-    CU_TRY(cudaMemcpyAsync(d_fills, h_fills, n * 8, cudaMemcpyHostToDevice, s));
-    if (any_old) CU_TRY(cudaMemcpyAsync(d_old, h_old, n * 8, cudaMemcpyHostToDevice, s));
-    rc = launch_apply(it, depth, n, dm, dv, d_flags, d_fills, d_roots, d_changed, s, any_old ? d_old : nullptr);
-    if (rc != VX_OK) return rc;
+    // a batch that only ever went through set/fill/clear/assign has value != 0 <=> set bit, so its masks
+    // stay on the host and the one-bit-per-block map travels instead (vx_stage.cuh)
+    bool use_occ = getenv("VX_STAGE_MASKS") == nullptr;
+    for (size_t i = 0; i < n && use_occ; ++i) use_occ = !batches[i]->raw_exposed;
+    CU_TRY(cudaEventRecord(it->ev_done[0], s));  // the stage stream starts after whatever is queued (a reset, say)
+    CU_TRY(cudaEventRecord(it->ev_done[1], s));
+    double host_lists = 0;
+    size_t k = 0;
+    for (size_t sl = 0; sl < n_slices; ++sl) {
+        const size_t lo = cut[sl], cnt = cut[sl + 1] - lo;
+        const double t0 = now_us();
+        const size_t k0 = k;
+        bool any_fill = false, old_here = false;
+        for (size_t i = lo; i < lo + cnt; ++i) {
+            const vx_batch* b = batches[i];
+            h_flags[i] = (b->has_fill ? VX_FLAG_FILL : 0) | (b->has_patches ? VX_FLAG_PATCHES : 0);
+            h_fills[i] = b->fill;
+            h_old[i] = trees[i]->root;
+            h_src[i] = b->alias;
+            any_fill = any_fill || b->has_fill;
+            old_here = old_here || h_old[i] != VX_BLOCK_EMPTY;
+            if (!b->has_patches) continue;
+            const u32 first = u32(i - lo) << upc_log2;
+            for (uint32_t w = 0; w * 64 < b->units; ++w)
+                for (uint64_t bits = b->touched[w]; bits; bits &= bits - 1)
+                    h_units[k++] = first + w * 64 + u32(__builtin_ctzll(bits));
+        }
+        const size_t nu = k - k0;
+        host_lists += now_us() - t0;
+        const int sb = int(sl & 1);
+        u8* dm = dbase + size_t(sb) * slab_bytes;
+        u8* dv = dm + up(slice * mbytes);
+        CU_TRY(cudaStreamWaitEvent(cs, it->ev_done[sb], 0));  // slab sb is free again
+        if (trace) CU_TRY(cudaEventRecord(it->tevs[4 * sl], cs));
+        CU_TRY(cudaMemcpyAsync(d_src + lo, h_src + lo, cnt * 8, cudaMemcpyHostToDevice, cs));
+        if (nu) CU_TRY(cudaMemcpyAsync(d_units + k0, h_units + k0, nu * 4, cudaMemcpyHostToDevice, cs));
+        if (any_fill) {  // without a fill the flags add nothing: an untouched batch stages all-zero masks
+            CU_TRY(cudaMemcpyAsync(d_flags + lo, h_flags + lo, cnt, cudaMemcpyHostToDevice, cs));
+            CU_TRY(cudaMemcpyAsync(d_fills + lo, h_fills + lo, cnt * 8, cudaMemcpyHostToDevice, cs));
+        }
+        if (old_here) CU_TRY(cudaMemcpyAsync(d_old + lo, h_old + lo, cnt * 8, cudaMemcpyHostToDevice, cs));
+        const u8* k_flags = any_fill ? d_flags + lo : nullptr;
+        const u64* k_old = (any_old && old_here) ? d_old + lo : nullptr;
+        // the bulk builder plans from the unit list and never looks at another unit; the fused kernel scans
+        // every unit, so for it the slab's masks are zeroed first (in HBM)
+        const bool listed = bulk_takes_listed(depth, cnt, dm, k_flags, k_old) && getenv("VX_STAGE_NO_LIST") == nullptr;
+        if (getenv("VX_STAGE_POISON")) {  // tests: nothing outside the staged units / flagged blocks may be consumed
+            CU_TRY(cudaMemsetAsync(dv, 0xA5, cnt * vbytes, cs));
+            CU_TRY(cudaMemsetAsync(dm, 0xA5, cnt * mbytes, cs));
+        }
+        if (!listed) CU_TRY(cudaMemsetAsync(dm, 0, cnt * mbytes, cs));
+        if (nu) {
+            // one CTA per SM keeps enough loads on the bus and leaves the SMs to the build of the previous slice
+            static const size_t per_sm = getenv("VX_STAGE_CTAS") ? size_t(atoi(getenv("VX_STAGE_CTAS"))) : 1;
+            const unsigned grid = unsigned(std::min<size_t>((nu + STAGE_WARPS - 1) / STAGE_WARPS, size_t(it->sm_count) * per_sm));
+            if (use_occ) {
+                if (it->dtype == VX_U8)
+                    stage_units_occ_kernel<8><<<grid, STAGE_THREADS, 0, cs>>>(d_src + lo, d_units + k0, u32(nu), upc_log2, ub,
+                                                                            dm, dv, mbytes, vbytes);
+                else
+                    stage_units_occ_kernel<32><<<grid, STAGE_THREADS, 0, cs>>>(d_src + lo, d_units + k0, u32(nu), upc_log2, ub,
+                                                                             dm, dv, mbytes, vbytes);
+            } else {
+                if (it->dtype == VX_U8)
+                    stage_units_kernel<8><<<grid, STAGE_THREADS, 0, cs>>>(d_src + lo, d_units + k0, u32(nu), upc_log2, ub, dm,
+                                                                        dv, mbytes, vbytes);
+                else
+                    stage_units_kernel<32><<<grid, STAGE_THREADS, 0, cs>>>(d_src + lo, d_units + k0, u32(nu), upc_log2, ub, dm,
+                                                                         dv, mbytes, vbytes);
+            }
+            CU_TRY(cudaGetLastError());
+        }
+        if (trace) CU_TRY(cudaEventRecord(it->tevs[4 * sl + 1], cs));
+        CU_TRY(cudaEventRecord(it->ev_copied[sb], cs));
+        CU_TRY(cudaStreamWaitEvent(s, it->ev_copied[sb], 0));
+        if (trace) CU_TRY(cudaEventRecord(it->tevs[4 * sl + 2], s));
+        const bool prof = it->prof;
+        it->prof = false;  // the builders' own stage events would reuse the markers
+        rc = launch_apply(it, depth, cnt, dm, dv, k_flags, any_fill ? d_fills + lo : nullptr, d_roots + lo,
+                          d_changed + lo, s, k_old, listed ? d_units + k0 : nullptr, u32(nu));
+        it->prof = prof;
+        if (rc != VX_OK) return rc;
+        if (trace) CU_TRY(cudaEventRecord(it->tevs[4 * sl + 3], s));
+        CU_TRY(cudaEventRecord(it->ev_done[sb], s));
+    }
     CU_TRY(cudaMemcpyAsync(h_roots, d_roots, n * 8, cudaMemcpyDeviceToHost, s));
     CU_TRY(cudaMemcpyAsync(h_changed, d_changed, n, cudaMemcpyDeviceToHost, s));
+    const double t_queued = now_us();
     rc = check_device_error(it);
     if (rc != VX_OK) return rc;
+    const double t_synced = now_us();
+    if (trace) {
+        double stage = 0, build = 0;
+        for (size_t sl = 0; sl < n_slices; ++sl) {
+            float a = 0, b = 0;
+            cudaEventElapsedTime(&a, it->tevs[4 * sl], it->tevs[4 * sl + 1]);
+            cudaEventElapsedTime(&b, it->tevs[4 * sl + 2], it->tevs[4 * sl + 3]);
+            stage += a;
+            build += b;
+        }
+        float span = 0;
+        cudaEventElapsedTime(&span, it->tevs[0], it->tevs[4 * n_slices - 1]);
+        it->trace[0] = host_lists;                          // host: unit lists + descriptors (all slices)
+        it->trace[1] = t_queued - t_begin - host_lists;     // host: enqueue
+        it->trace[2] = t_synced - t_queued;                 // host: wait for the device
+        it->trace[3] = span * 1e3;                          // device: first stage start .. last build end
+        it->trace[4] = stage * 1e3;                         // device: descriptors + memset + stage kernel, summed
+        it->trace[5] = build * 1e3;                         // device: builds, summed (they overlap the stages)
+        it->trace[6] = double(k);
+        it->trace[7] = double(n_slices);
+    }
     if (it->free_host > 0) {
         rc = refresh_free_count(it);
         if (rc != VX_OK) return rc;
