@@ -164,3 +164,27 @@ def test_bulk_repeated_calls_varied_sizes(gpu_api, monkeypatch):
         dense = g.roots_to_vec(roots[check], depth)
         for j, i in enumerate(check):
             assert np.array_equal(dense[j], wl.dense_expected(masks[i], values[i])), (step, i)
+
+
+def test_bulk_lod_values_are_stable(gpu_api, oracle_api, monkeypatch):
+    """Regression: the chained level launches once read child values through L1 and could see a line cached
+    before a neighbouring node's value was written (rare wrong LOD value).  Same input many times: the
+    branch LOD values must equal the oracle's every time."""
+    vx, o = gpu_api, oracle_api
+    monkeypatch.setenv("VX_BUILDER", "bulk")
+    masks, values = _mixed(6, wl.U8, 3)
+    c = o.VoxInterner(512 << 20, wl.U8)
+    flags, fills = parity.flags_from(masks.shape[0])
+    croots, cchanged = c.apply_batches_fresh(6, masks, values, flags & 1, fills, (flags >> 1) & 1)
+    cd = c.download()
+    cs = o.dag_signature(cd["children"], cd["values"], croots, 6, want_stream=True)
+    corder = np.argsort(cs["numbers"], kind="stable")[np.count_nonzero(cs["numbers"] == 0):]
+    g = vx.VoxInterner.with_memory_budget(512 << 20, wl.U8)
+    for rep in range(12):
+        g.reset()
+        groots, _ = g.apply_batches_slab(6, masks, values)
+        gd = g.download()
+        gs = o.dag_signature(gd["children"], gd["values"], groots, 6, want_stream=True)
+        gorder = np.argsort(gs["numbers"], kind="stable")[np.count_nonzero(gs["numbers"] == 0):]
+        assert np.array_equal(gs["stream"], cs["stream"]), rep
+        assert np.array_equal(gd["values"][gorder], cd["values"][corder]), rep

@@ -205,8 +205,12 @@ __global__ void __launch_bounds__(256) bulk_plan_kernel(BulkArgs a) {
     }
 }
 
-// Values of the eight children of a key (leaf value / branch LOD value; 0 for EMPTY), loaded with plain
-// cached loads: the children were created by earlier launches.  u8 packs them into one register pair.
+// Values of the eight children of a key (leaf value / branch LOD value; 0 for EMPTY).  The children were
+// created by earlier launches, but the loads must still bypass L1 (ld.relaxed.gpu): with programmatic
+// stream serialization this kernel's CTAs share an SM with the tail of the previous launch, whose own
+// reads may have left a line of `values` in L1 from before a neighbouring node's value was written — a
+// plain load after griddepcontrol.wait could hit that stale line (seen as a rare wrong LOD value at D = 6).
+// u8 packs the eight values into one register pair.
 template <class T>
 struct ChildValues;
 template <>
@@ -215,7 +219,7 @@ struct ChildValues<u8> {
     __device__ __forceinline__ void load(const InternerDev& in, const u64 (&ch)[8], bool need) {
         u32 b[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) b[i] = (need && ch[i] != 0) ? u32(((const u8*)in.values)[id_index(ch[i])]) : 0;
+        for (int i = 0; i < 8; ++i) b[i] = (need && ch[i] != 0) ? ld_strong_u8((const u8*)in.values + id_index(ch[i])) : 0;
         w = 0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) w |= u64(b[i]) << (8 * i);
@@ -227,7 +231,7 @@ struct ChildValues<int32_t> {
     u32 v[8];
     __device__ __forceinline__ void load(const InternerDev& in, const u64 (&ch)[8], bool need) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = (need && ch[i] != 0) ? ((const u32*)in.values)[id_index(ch[i])] : 0;
+        for (int i = 0; i < 8; ++i) v[i] = (need && ch[i] != 0) ? ld_strong((const u32*)in.values + id_index(ch[i])) : 0;
     }
     __device__ __forceinline__ u32 get(int i) const { return v[i]; }
 };
