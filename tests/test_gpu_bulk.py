@@ -167,9 +167,10 @@ def test_bulk_repeated_calls_varied_sizes(gpu_api, monkeypatch):
 
 
 def test_bulk_lod_values_are_stable(gpu_api, oracle_api, monkeypatch):
-    """Regression: the chained level launches once read child values through L1 and could see a line cached
-    before a neighbouring node's value was written (rare wrong LOD value).  Same input many times: the
-    branch LOD values must equal the oracle's every time."""
+    """Regression: the second level of bulk_upper_kernel read the values of children created in the SAME
+    launch through L1 and could hit a line cached before another SM wrote the value (rare wrong LOD value,
+    about one run in three at D = 6).  Same input many times: the branch LOD values must equal the oracle's
+    every time."""
     vx, o = gpu_api, oracle_api
     monkeypatch.setenv("VX_BUILDER", "bulk")
     masks, values = _mixed(6, wl.U8, 3)

@@ -205,21 +205,25 @@ __global__ void __launch_bounds__(256) bulk_plan_kernel(BulkArgs a) {
     }
 }
 
-// Values of the eight children of a key (leaf value / branch LOD value; 0 for EMPTY).  The children were
-// created by earlier launches, but the loads must still bypass L1 (ld.relaxed.gpu): with programmatic
-// stream serialization this kernel's CTAs share an SM with the tail of the previous launch, whose own
-// reads may have left a line of `values` in L1 from before a neighbouring node's value was written — a
-// plain load after griddepcontrol.wait could hit that stale line (seen as a rare wrong LOD value at D = 6).
-// u8 packs the eight values into one register pair.
+// Values of the eight children of a key (leaf value / branch LOD value; 0 for EMPTY), loaded with plain
+// cached loads when the children were created by EARLIER launches (bulk_prologue() has dropped whatever
+// this SM's L1 held from before).  STRONG = the children may have been created by another SM during THIS
+// launch (second level of bulk_upper_kernel): L1 can hold their line from before the value was written,
+// so the loads go to L2 (ld.relaxed.gpu) — a plain load there gave a rare wrong LOD value at D = 6,
+// tests/test_gpu_bulk.py::test_bulk_lod_values_are_stable.  u8 packs them into one register pair.
 template <class T>
 struct ChildValues;
 template <>
 struct ChildValues<u8> {
     u64 w;
+    template <bool STRONG>
     __device__ __forceinline__ void load(const InternerDev& in, const u64 (&ch)[8], bool need) {
         u32 b[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) b[i] = (need && ch[i] != 0) ? ld_strong_u8((const u8*)in.values + id_index(ch[i])) : 0;
+        for (int i = 0; i < 8; ++i) {
+            const u8* p = (const u8*)in.values + id_index(ch[i]);
+            b[i] = (need && ch[i] != 0) ? (STRONG ? ld_strong_u8(p) : u32(*p)) : 0;
+        }
         w = 0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) w |= u64(b[i]) << (8 * i);
@@ -229,9 +233,13 @@ struct ChildValues<u8> {
 template <>
 struct ChildValues<int32_t> {
     u32 v[8];
+    template <bool STRONG>
     __device__ __forceinline__ void load(const InternerDev& in, const u64 (&ch)[8], bool need) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = (need && ch[i] != 0) ? ld_strong((const u32*)in.values + id_index(ch[i])) : 0;
+        for (int i = 0; i < 8; ++i) {
+            const u32* p = (const u32*)in.values + id_index(ch[i]);
+            v[i] = (need && ch[i] != 0) ? (STRONG ? ld_strong(p) : *p) : 0;
+        }
     }
     __device__ __forceinline__ u32 get(int i) const { return v[i]; }
 };
@@ -240,7 +248,7 @@ struct ChildValues<int32_t> {
 // get_or_create_branch (interner/mod.rs:716-829), thread-per-key with the eight child ids in
 // registers — the probing protocol of intern_block with the children given directly.
 // ------------------------------------------------------------------------------------------------
-template <class T>
+template <class T, bool STRONG = false>
 __device__ inline u64 intern_node(Ctx<T>& c, bool need, const u64 (&ch)[8], u32 types, u32 mask) {
     const InternerDev& in = c.in;
     if (!__any_sync(FULL, need)) return 0;
@@ -269,7 +277,7 @@ __device__ inline u64 intern_node(Ctx<T>& c, bool need, const u64 (&ch)[8], u32 
     // with the first bucket, not after the claim: in a warp step some lane almost always creates a node,
     // so the step would pay that round trip anyway.  Children were published by earlier launches.
     ChildValues<T> cv;
-    cv.load(in, ch, went_global);
+    cv.template load<STRONG>(in, ch, went_global);
     u32 skip = 0;
     int guard = 0;
     while (__any_sync(FULL, !done)) {
@@ -394,7 +402,7 @@ __device__ inline u64 intern_node(Ctx<T>& c, bool need, const u64 (&ch)[8], u32 
 
 // One parent of phase 2 (voxtree.rs:905-1106) on a fresh tree, one thread: absent if no child entered
 // `paths`, the shared Leaf if eight identical leaves (:1050, :1062-1075), else the interned branch.
-template <class T>
+template <class T, bool STRONG = false>
 __device__ inline u64 parent_tpk(Ctx<T>& c, bool active, const u64 (&ch)[8]) {
     u32 pres = 0, leafb = 0;
     bool same = true;
@@ -412,7 +420,7 @@ __device__ inline u64 parent_tpk(Ctx<T>& c, bool active, const u64 (&ch)[8]) {
         else
             c.t.branch_calls++;
     }
-    u64 id = intern_node<T>(c, any && !collapse, ch, leafb, pres);
+    u64 id = intern_node<T, STRONG>(c, any && !collapse, ch, leafb, pres);
     if (collapse) id = ch[0];
     return any ? id : 0;
 }
@@ -427,6 +435,11 @@ __device__ __forceinline__ void bulk_prologue(Ctx<T>& c, const BulkArgs& a, unsi
     smem_init<T>(ws, csp);
     ctx_init<T>(c, a.in, ws, csp, a.use_free != 0);
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    // This CTA may share its SM with the tail of the previous launch, whose reads can have left lines in L1
+    // from before other SMs wrote into them (a line of `values` around a node created later, say).  The
+    // acquire side of the fence drops those lines (CCTL.IVALL), once per thread, so the plain cached loads
+    // below (ChildValues) see what the previous launches wrote.
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
 // CTAs of a list kernel that have no element to process leave right after the prologue (the grids are
 // sized for the worst case the call allows; the real counts only exist on the device).
@@ -658,7 +671,7 @@ bulk_upper_kernel(BulkArgs a, unsigned long long nodes, const u64* below, u64* o
 #pragma unroll
         for (int i = 0; i < 8; ++i) ch[i] = __shfl_sync(FULL, id, c.gs + i);
         const bool act2 = active && c.li == 0;
-        const u64 id2 = parent_tpk<T>(c, act2, ch);
+        const u64 id2 = parent_tpk<T, true>(c, act2, ch);  // children of this level were created in this launch
         if ((listed ? active : k < nodes) && c.li == 0) {
             if (top_is_root)
                 bulk_write_root<T>(c, a, k >> 3, id2);
