@@ -76,13 +76,17 @@ def test_handles_match_oracle_and_slab(gpu_api, oracle_api, depth, dtype, builde
     groots = cs.roots()
     c = o.VoxInterner(64 << 20, dtype)
     flags, fills = parity.flags_from(n)
-    croots, cchanged = c.apply_batches_fresh(depth, masks, values, flags & 1, fills, (flags >> 1) & 1)
+    # a batch nobody wrote to has has_patches == false and the reference answers "changed" for it with the
+    # root still EMPTY (voxtree.rs:756-758, :303-328); assign() leaves an all-zero chunk in that state
+    hp = np.array([b.has_patches for b in cs.batches], np.uint8)
+    assert hp[1] == (1 if raw else 0) and hp.any()
+    croots, cchanged = c.apply_batches_fresh(depth, masks, values, flags & 1, fills, hp)
     groots = np.where(gchanged.astype(bool), groots, croots)     # an unchanged tree keeps its (empty) root
     parity.assert_parity(vx, o, depth, g, groots, gchanged, c, croots, cchanged)
     # the slab entry on the same arrays: same counters, same voxels
     g2 = vx.VoxInterner.with_memory_budget(64 << 20, dtype)
     r2, ch2 = g2.apply_batches_slab(depth, masks, values)
-    assert np.array_equal(ch2, gchanged)
+    assert np.array_equal(ch2[hp == 1], gchanged[hp == 1])
     for k, v in g.stats().items():
         assert g2.stats()[k] == v, k
     assert np.array_equal(g.roots_to_vec(groots, depth), g2.roots_to_vec(np.where(ch2.astype(bool), r2, 0), depth))
@@ -99,7 +103,8 @@ def test_small_slices(gpu_api, oracle_api, monkeypatch):
     gchanged = cs.apply(g).copy()
     c = o.VoxInterner(64 << 20, wl.U8)
     flags, fills = parity.flags_from(n)
-    croots, cchanged = c.apply_batches_fresh(5, masks, values, flags & 1, fills, (flags >> 1) & 1)
+    hp = np.array([b.has_patches for b in cs.batches], np.uint8)
+    croots, cchanged = c.apply_batches_fresh(5, masks, values, flags & 1, fills, hp)
     groots = np.where(gchanged.astype(bool), cs.roots(), croots)
     parity.assert_parity(vx, o, 5, g, groots, gchanged, c, croots, cchanged)
 
@@ -168,3 +173,80 @@ def test_fill_and_edit_through_handles(gpu_api, oracle_api):
         assert list(gch) == och
         for i in range(n):
             assert np.array_equal(gt[i].to_vec(g), ot[i].to_vec(c)), (rnd, i)
+
+
+def _many_small(vx, o, depth, n, seed):
+    """n small chunks filled through set_many, the same voxels recorded in oracle batches."""
+    rng = np.random.default_rng(seed)
+    N = 1 << depth
+    gtrees = [vx.VoxTree(depth, wl.U8) for _ in range(n)]
+    gb = [t.create_batch() for t in gtrees]
+    ob = []
+    oi = o.VoxInterner(64 << 20, wl.U8)
+    for i in range(n):
+        k = int(rng.integers(0, 6))
+        xyz = rng.integers(0, N, (k, 3)).astype(np.int32)
+        vals = rng.integers(1, 4, k).astype(np.int64)
+        b = o.Batch(depth, wl.U8)
+        for p, v in zip(xyz, vals):
+            b.set(oi, p, int(v))
+        if k:
+            gb[i].set_many(xyz, vals)
+        ob.append(b)
+    return gtrees, gb, ob, oi
+
+
+def test_big_call_is_sliced_and_late_errors_leave_the_interner_alone(gpu_api, oracle_api):
+    """n >= 8192: the first slice's bus traffic is queued before the remaining handles are checked."""
+    vx, o = gpu_api, oracle_api
+    depth, n = 3, 9000
+    gtrees, gb, ob, oi = _many_small(vx, o, depth, n, 11)
+    g = vx.VoxInterner.with_memory_budget(64 << 20, wl.U8)
+    # a handle of the wrong depth far into the call: VX_E_INVALID, nothing applied
+    bad = vx.VoxTree(4, wl.U8).create_batch()
+    with pytest.raises(vx.VoxelisError):
+        vx.apply_batches(g, gtrees, gb[:8500] + [bad] + gb[8501:])
+    assert g.stats()["alive_nodes"] == 1 and all(t.is_empty() for t in gtrees[::97])
+    # the real call
+    cs = vx.ChunkSet(gtrees, gb)
+    changed = cs.apply(g).copy()
+    otrees = [o.VoxTree(depth, wl.U8) for _ in range(n)]
+    och = [otrees[i].apply_batch(oi, ob[i]) for i in range(n)]
+    assert list(changed.astype(bool)) == och
+    dense = g.roots_to_vec(cs.roots(), depth)
+    for i in range(0, n, 7):
+        assert np.array_equal(dense[i], otrees[i].to_vec(oi)), i
+    assert g.stats()["alive_nodes"] == oi.stats()["alive_nodes"]
+
+
+def test_repeated_tree_in_a_late_slice_takes_the_serial_loop(gpu_api, oracle_api):
+    vx, o = gpu_api, oracle_api
+    depth, n = 3, 8300
+    gtrees, gb, ob, oi = _many_small(vx, o, depth, n, 12)
+    g = vx.VoxInterner.with_memory_budget(64 << 20, wl.U8)
+    gtrees[8250] = gtrees[10]                       # batch 10, then batch 8250, on the same tree
+    vx.apply_batches(g, gtrees, gb)
+    otrees = [o.VoxTree(depth, wl.U8) for _ in range(n)]
+    otrees[8250] = otrees[10]
+    for i in range(n):
+        otrees[i].apply_batch(oi, ob[i])
+    for i in (9, 10, 11, 8249, 8251, 8299):
+        assert np.array_equal(gtrees[i].to_vec(g), otrees[i].to_vec(oi)), i
+
+
+def test_untouched_batch_reports_changed_like_the_reference(gpu_api, oracle_api):
+    """voxtree.rs:756-758 hands back the initial node when the batch has no patches; for an EMPTY tree that
+    is EMPTY != INVALID, so apply_batch answers true and marks the tree dirty.  All three entries agree."""
+    vx, o = gpu_api, oracle_api
+    g, c = vx.VoxInterner.with_memory_budget(16 << 20), o.VoxInterner(16 << 20)
+    gt, ot = vx.VoxTree(4), o.VoxTree(4)
+    assert gt.apply_batch(g, gt.create_batch()) is True and ot.apply_batch(c, ot.create_batch()) is True
+    assert gt.is_empty() and gt.is_dirty() and ot.is_empty() and ot.is_dirty()
+    trees = [vx.VoxTree(4) for _ in range(3)]
+    assert list(vx.apply_batches(g, trees, [t.create_batch() for t in trees])) == [True] * 3
+    assert all(t.is_empty() and t.is_dirty() for t in trees)
+    B = wl.blocks_per_chunk(4)
+    roots, changed = g.apply_batches_slab(4, np.zeros((2, B, 2), np.uint8), np.zeros((2, B, 8), np.uint8),
+                                          flags=np.zeros(2, np.uint8), fills=np.zeros(2, np.int64))
+    assert list(changed) == [1, 1] and list(roots) == [0, 0]
+    assert g.stats()["alive_nodes"] == 1

@@ -1303,10 +1303,15 @@ __global__ void __launch_bounds__(CTA_THREADS, VX_MIN_CTAS) apply_kernel(ApplyAr
             chunk_flags<T>(a, chunk, &has_fill, &fill, &has_patches);
             // phase 0 once per chunk (unit 0 takes the reference); every unit needs the fill leaf's id
             u64 fl = phase0_fill<T>(c, has_fill, fill, has_patches && unit == 0);
-            if (!has_patches) {  // :756-758 — the tree becomes Leaf(fill), or nothing happens
+            if (!has_patches) {
+                // :756-758 returns the initial node: Leaf(fill), or — no fill either — the tree's own root.  On
+                // an EMPTY tree that root is EMPTY, which is not INVALID, so apply_batch (:303-328) reports
+                // "changed" and marks the tree dirty with nothing built.  On a non-empty tree the reference
+                // trips its assert_ne!(new_root, old_root) (:310); here that case is "unchanged".
                 if (lane == 0 && unit == 0) {
                     if (has_fill) c.t.leaf_calls++;
-                    write_root<T>(c, a, chunk, fl, has_fill);
+                    const bool old_empty = !(OLD && a.old_roots && a.old_roots[chunk] != 0);
+                    write_root<T>(c, a, chunk, fl, has_fill || old_empty);
                 }
                 continue;
             }

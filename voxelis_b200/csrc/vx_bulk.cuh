@@ -77,6 +77,20 @@ __device__ __forceinline__ void ld_stream_v8(const void* p, uint4* a, uint4* b) 
                  : "l"(p));
 }
 
+// With a unit list the plan kernel does not visit every unit, so what it would have written for the ones it
+// skips is zeroed here in one launch: the counters, unit_cm, the roots / changed flags (D = 5) or the dense
+// level above the units (D >= 6).
+__global__ void __launch_bounds__(256) bulk_zero_kernel(BulkArgs a, u32 dense1_bytes) {
+    const size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x, nt = size_t(gridDim.x) * blockDim.x;
+    if (t < 8) a.cnt[t] = 0;
+    for (size_t i = t; i < a.units; i += nt) a.unit_cm[i] = 0;
+    for (size_t i = t; i < a.n; i += nt) {
+        a.roots[i] = 0;
+        if (a.changed) a.changed[i] = 0;
+    }
+    for (size_t i = t; i * 8 < dense1_bytes; i += nt) a.dense[1][i] = 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // plan: one warp per unit of 512 Morton-consecutive blocks (lane = 16 blocks = 32 B of masks).
 // ------------------------------------------------------------------------------------------------

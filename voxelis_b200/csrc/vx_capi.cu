@@ -389,12 +389,13 @@ int launch_bulk_t(vx_interner* it, int depth, size_t n, const u8* d_masks, const
     a.unit_list = d_unit_list;
     a.n_listed = n_listed;
     prof_begin(it, s);
-    CU_TRY(cudaMemsetAsync(a.cnt, 0, 32, s));
     if (d_unit_list) {  // what the plan kernel writes for every unit / group it visits, for the ones it will not visit
-        CU_TRY(cudaMemsetAsync(a.unit_cm, 0, units, s));
-        CU_TRY(cudaMemsetAsync(d_roots, 0, n * 8, s));
-        if (d_changed) CU_TRY(cudaMemsetAsync(d_changed, 0, n, s));
-        if (blocks > 8 * UNIT_BLOCKS) CU_TRY(cudaMemsetAsync(a.dense[1], 0, units, s));
+        const size_t items = std::max(units, n);
+        bulk_zero_kernel<<<unsigned(std::min<size_t>((items + 255) / 256, size_t(it->sm_count) * 8)), 256, 0, s>>>(
+            a, blocks > 8 * UNIT_BLOCKS ? u32(units) : 0u);
+        CU_TRY(cudaGetLastError());
+    } else {
+        CU_TRY(cudaMemsetAsync(a.cnt, 0, 32, s));
     }
     const size_t smem = apply_smem_bytes<T>();
     static thread_local int occ_for_device[64] = {};  // function attributes are per device: set them once each
@@ -1377,34 +1378,23 @@ int vx_apply_batches(vx_interner* it, vx_tree* const* trees, const vx_batch* con
                      uint8_t* changed) {
     if (!it || (n && (!trees || !batches))) return fail(VX_E_INVALID, "null argument");
     if (n == 0) return VX_OK;
-    bool fused = true, any_old = false;
+    bool fused = true;
     static std::atomic<uint32_t> g_call{0};
     const uint32_t stamp = ++g_call;  // a tree may appear only once in the fused path: stamp and compare
-    for (size_t i = 0; i < n; ++i) {
-        if (i + 8 < n) {  // the handles are separate heap objects: keep the misses in flight
-            __builtin_prefetch(trees[i + 8]);
-            __builtin_prefetch(batches[i + 8]);
-            __builtin_prefetch((const char*)batches[i + 8] + 64);
-        }
-        if (!trees[i] || !batches[i]) return fail(VX_E_INVALID, "null tree or batch");
-        if (batches[i]->depth != trees[i]->depth) return fail(VX_E_INVALID, "batch and tree depths differ");
-        if (batches[i]->dtype != it->dtype) return fail(VX_E_INVALID, "batch and interner voxel types differ");
-        fused = fused && batches[i]->depth == batches[0]->depth && trees[i]->stamp != stamp;
-        trees[i]->stamp = stamp;
-        any_old = any_old || trees[i]->root != VX_BLOCK_EMPTY;
-    }
-    if (!fused) {  // mixed depths or repeated trees: the reference's serial loop (lib.rs:357-361)
+    if (!trees[0] || !batches[0]) return fail(VX_E_INVALID, "null tree or batch");
+    const uint8_t depth0 = batches[0]->depth;
+    auto serial = [&]() -> int {  // mixed depths or repeated trees: the reference's serial loop (lib.rs:357-361)
         for (size_t i = 0; i < n; ++i) {
             int rc = vx_tree_apply_batch(it, trees[i], batches[i]);
             if (rc < 0) return rc;
             if (changed) changed[i] = uint8_t(rc);
         }
         return VX_OK;
-    }
+    };
     if (it->poisoned) return fail(VX_E_POISONED, "interner overflowed earlier; reset it");
     std::unique_lock<std::mutex> lk(it->mu);
     DeviceGuard g(it->device);
-    const int depth = batches[0]->depth;
+    const int depth = depth0;
     const size_t B = blocks_for_depth(depth), mbytes = B * 2, vbytes = B * 8 * dtype_size(it->dtype);
     const size_t per = mbytes + vbytes;
     const uint32_t upc = batches[0]->units, ub = batches[0]->unit_blocks;
@@ -1491,91 +1481,183 @@ int vx_apply_batches(vx_interner* it, vx_tree* const* trees, const vx_batch* con
         for (auto& e : it->tevs)
             if (!e) CU_TRY(cudaEventCreate(&e));
     }
-    // a batch that only ever went through set/fill/clear/assign has value != 0 <=> set bit, so its masks
-    // stay on the host and the one-bit-per-block map travels instead (vx_stage.cuh)
-    bool use_occ = getenv("VX_STAGE_MASKS") == nullptr;
-    for (size_t i = 0; i < n && use_occ; ++i) use_occ = !batches[i]->raw_exposed;
+    // Per slice, on the host: check the handles, fill the per-chunk descriptors and list the touched units, in
+    // one pass.  The bus is at work after ~1/8 of that pass; nothing touches the interner before every slice
+    // has been checked.
+    struct Prep {
+        int rc = VX_OK;
+        const char* err = nullptr;
+        bool fused = true, any_fill = false, old_here = false, raw = false;
+        size_t nu = 0;
+    };
+    std::vector<Prep> prep(n_slices);
+    auto prepare = [&](size_t sl) {
+        Prep& P = prep[sl];
+        const size_t lo = cut[sl], hi = cut[sl + 1];
+        u32* out = h_units + lo * upc;
+        size_t k = 0;
+        for (size_t i = lo; i < hi; ++i) {
+            if (i + 8 < hi) {  // the handles are separate heap objects: keep the misses in flight
+                __builtin_prefetch(trees[i + 8]);
+                __builtin_prefetch(batches[i + 8]);
+                __builtin_prefetch((const char*)batches[i + 8] + 64);
+            }
+            vx_tree* t = trees[i];
+            const vx_batch* b = batches[i];
+            if (!t || !b) {
+                P.rc = VX_E_INVALID, P.err = "null tree or batch";
+                return;
+            }
+            if (b->depth != t->depth) {
+                P.rc = VX_E_INVALID, P.err = "batch and tree depths differ";
+                return;
+            }
+            if (b->dtype != it->dtype) {
+                P.rc = VX_E_INVALID, P.err = "batch and interner voxel types differ";
+                return;
+            }
+            // a tree may appear only once in the fused path: stamp and compare
+            if (b->depth != depth0 || t->stamp == stamp) P.fused = false;
+            t->stamp = stamp;
+            h_flags[i] = (b->has_fill ? VX_FLAG_FILL : 0) | (b->has_patches ? VX_FLAG_PATCHES : 0);
+            h_fills[i] = b->fill;
+            h_old[i] = t->root;
+            h_src[i] = b->alias;
+            P.any_fill = P.any_fill || b->has_fill;
+            P.old_here = P.old_here || t->root != VX_BLOCK_EMPTY;
+            P.raw = P.raw || b->raw_exposed;
+            if (!b->has_patches || !P.fused) continue;
+            const u32 first = u32(i - lo) << upc_log2;
+            for (uint32_t w = 0; w * 64 < b->units; ++w)
+                for (uint64_t bits = b->touched[w]; bits; bits &= bits - 1) out[k++] = first + w * 64 + u32(__builtin_ctzll(bits));
+        }
+        P.nu = k;
+    };
+    // (One short-lived thread per later slice was tried for this pass: creating and joining them cost more than
+    // the ~0.2 ms they took off the critical path — 1.25-1.5 ms per perlin world against 1.05 ms inline.)
+    std::vector<char> prepared(n_slices, 0);
+    auto ready = [&](size_t sl) {
+        if (prepared[sl]) return;
+        prepare(sl);
+        prepared[sl] = 1;
+    };
+    const bool force_masks = getenv("VX_STAGE_MASKS") != nullptr, poison = getenv("VX_STAGE_POISON") != nullptr,
+               no_list = getenv("VX_STAGE_NO_LIST") != nullptr;
     CU_TRY(cudaEventRecord(it->ev_done[0], s));  // the stage stream starts after whatever is queued (a reset, say)
     CU_TRY(cudaEventRecord(it->ev_done[1], s));
     double host_lists = 0;
-    size_t k = 0;
-    for (size_t sl = 0; sl < n_slices; ++sl) {
-        const size_t lo = cut[sl], cnt = cut[sl + 1] - lo;
+    size_t total_listed = 0;
+    struct Slice {
+        u8 *dm, *dv;
+        const u8* k_flags;
+        const u64* k_old;
+        bool listed;
+    };
+    std::vector<Slice> sls(n_slices);
+    // bus traffic of slice sl: descriptors by the copy engine, then the staging kernel, on the copy stream
+    auto enqueue_stage = [&](size_t sl) -> int {
         const double t0 = now_us();
-        const size_t k0 = k;
-        bool any_fill = false, old_here = false;
-        for (size_t i = lo; i < lo + cnt; ++i) {
-            const vx_batch* b = batches[i];
-            h_flags[i] = (b->has_fill ? VX_FLAG_FILL : 0) | (b->has_patches ? VX_FLAG_PATCHES : 0);
-            h_fills[i] = b->fill;
-            h_old[i] = trees[i]->root;
-            h_src[i] = b->alias;
-            any_fill = any_fill || b->has_fill;
-            old_here = old_here || h_old[i] != VX_BLOCK_EMPTY;
-            if (!b->has_patches) continue;
-            const u32 first = u32(i - lo) << upc_log2;
-            for (uint32_t w = 0; w * 64 < b->units; ++w)
-                for (uint64_t bits = b->touched[w]; bits; bits &= bits - 1)
-                    h_units[k++] = first + w * 64 + u32(__builtin_ctzll(bits));
-        }
-        const size_t nu = k - k0;
+        ready(sl);
         host_lists += now_us() - t0;
+        const Prep& P = prep[sl];
+        if (P.rc != VX_OK || !P.fused) return VX_OK;  // settled by the caller once every slice has been looked at
+        const size_t lo = cut[sl], cnt = cut[sl + 1] - lo, k0 = lo * upc, nu = P.nu;
+        total_listed += nu;
         const int sb = int(sl & 1);
-        u8* dm = dbase + size_t(sb) * slab_bytes;
-        u8* dv = dm + up(slice * mbytes);
+        Slice& S = sls[sl];
+        S.dm = dbase + size_t(sb) * slab_bytes;
+        S.dv = S.dm + up(slice * mbytes);
         CU_TRY(cudaStreamWaitEvent(cs, it->ev_done[sb], 0));  // slab sb is free again
         if (trace) CU_TRY(cudaEventRecord(it->tevs[4 * sl], cs));
         CU_TRY(cudaMemcpyAsync(d_src + lo, h_src + lo, cnt * 8, cudaMemcpyHostToDevice, cs));
         if (nu) CU_TRY(cudaMemcpyAsync(d_units + k0, h_units + k0, nu * 4, cudaMemcpyHostToDevice, cs));
-        if (any_fill) {  // without a fill the flags add nothing: an untouched batch stages all-zero masks
+        if (P.any_fill) {  // without a fill the flags add nothing: an untouched batch stages all-zero masks
             CU_TRY(cudaMemcpyAsync(d_flags + lo, h_flags + lo, cnt, cudaMemcpyHostToDevice, cs));
             CU_TRY(cudaMemcpyAsync(d_fills + lo, h_fills + lo, cnt * 8, cudaMemcpyHostToDevice, cs));
         }
-        if (old_here) CU_TRY(cudaMemcpyAsync(d_old + lo, h_old + lo, cnt * 8, cudaMemcpyHostToDevice, cs));
-        const u8* k_flags = any_fill ? d_flags + lo : nullptr;
-        const u64* k_old = (any_old && old_here) ? d_old + lo : nullptr;
+        if (P.old_here) CU_TRY(cudaMemcpyAsync(d_old + lo, h_old + lo, cnt * 8, cudaMemcpyHostToDevice, cs));
+        S.k_flags = P.any_fill ? d_flags + lo : nullptr;
+        S.k_old = P.old_here ? d_old + lo : nullptr;
         // the bulk builder plans from the unit list and never looks at another unit; the fused kernel scans
         // every unit, so for it the slab's masks are zeroed first (in HBM)
-        const bool listed = bulk_takes_listed(depth, cnt, dm, k_flags, k_old) && getenv("VX_STAGE_NO_LIST") == nullptr;
-        if (getenv("VX_STAGE_POISON")) {  // tests: nothing outside the staged units / flagged blocks may be consumed
-            CU_TRY(cudaMemsetAsync(dv, 0xA5, cnt * vbytes, cs));
-            CU_TRY(cudaMemsetAsync(dm, 0xA5, cnt * mbytes, cs));
+        S.listed = bulk_takes_listed(depth, cnt, S.dm, S.k_flags, S.k_old) && !no_list;
+        if (poison) {  // tests: nothing outside the staged units / flagged blocks may be consumed
+            CU_TRY(cudaMemsetAsync(S.dv, 0xA5, cnt * vbytes, cs));
+            CU_TRY(cudaMemsetAsync(S.dm, 0xA5, cnt * mbytes, cs));
         }
-        if (!listed) CU_TRY(cudaMemsetAsync(dm, 0, cnt * mbytes, cs));
+        if (!S.listed) CU_TRY(cudaMemsetAsync(S.dm, 0, cnt * mbytes, cs));
         if (nu) {
             // one CTA per SM keeps enough loads on the bus and leaves the SMs to the build of the previous slice
             static const size_t per_sm = getenv("VX_STAGE_CTAS") ? size_t(atoi(getenv("VX_STAGE_CTAS"))) : 1;
             const unsigned grid = unsigned(std::min<size_t>((nu + STAGE_WARPS - 1) / STAGE_WARPS, size_t(it->sm_count) * per_sm));
-            if (use_occ) {
+            // a batch that only ever went through set/fill/clear/assign has value != 0 <=> set bit, so its masks
+            // stay on the host and the one-bit-per-block map travels instead (vx_stage.cuh)
+            if (!P.raw && !force_masks) {
                 if (it->dtype == VX_U8)
                     stage_units_occ_kernel<8><<<grid, STAGE_THREADS, 0, cs>>>(d_src + lo, d_units + k0, u32(nu), upc_log2, ub,
-                                                                            dm, dv, mbytes, vbytes);
+                                                                            S.dm, S.dv, mbytes, vbytes);
                 else
                     stage_units_occ_kernel<32><<<grid, STAGE_THREADS, 0, cs>>>(d_src + lo, d_units + k0, u32(nu), upc_log2, ub,
-                                                                             dm, dv, mbytes, vbytes);
+                                                                             S.dm, S.dv, mbytes, vbytes);
             } else {
                 if (it->dtype == VX_U8)
-                    stage_units_kernel<8><<<grid, STAGE_THREADS, 0, cs>>>(d_src + lo, d_units + k0, u32(nu), upc_log2, ub, dm,
-                                                                        dv, mbytes, vbytes);
+                    stage_units_kernel<8><<<grid, STAGE_THREADS, 0, cs>>>(d_src + lo, d_units + k0, u32(nu), upc_log2, ub, S.dm,
+                                                                        S.dv, mbytes, vbytes);
                 else
-                    stage_units_kernel<32><<<grid, STAGE_THREADS, 0, cs>>>(d_src + lo, d_units + k0, u32(nu), upc_log2, ub, dm,
-                                                                         dv, mbytes, vbytes);
+                    stage_units_kernel<32><<<grid, STAGE_THREADS, 0, cs>>>(d_src + lo, d_units + k0, u32(nu), upc_log2, ub, S.dm,
+                                                                         S.dv, mbytes, vbytes);
             }
             CU_TRY(cudaGetLastError());
         }
         if (trace) CU_TRY(cudaEventRecord(it->tevs[4 * sl + 1], cs));
         CU_TRY(cudaEventRecord(it->ev_copied[sb], cs));
+        return VX_OK;
+    };
+    auto enqueue_build = [&](size_t sl) -> int {
+        const size_t lo = cut[sl], cnt = cut[sl + 1] - lo;
+        const int sb = int(sl & 1);
+        const Slice& S = sls[sl];
         CU_TRY(cudaStreamWaitEvent(s, it->ev_copied[sb], 0));
         if (trace) CU_TRY(cudaEventRecord(it->tevs[4 * sl + 2], s));
         const bool prof = it->prof;
         it->prof = false;  // the builders' own stage events would reuse the markers
-        rc = launch_apply(it, depth, cnt, dm, dv, k_flags, any_fill ? d_fills + lo : nullptr, d_roots + lo,
-                          d_changed + lo, s, k_old, listed ? d_units + k0 : nullptr, u32(nu));
+        int r = launch_apply(it, depth, cnt, S.dm, S.dv, S.k_flags, prep[sl].any_fill ? d_fills + lo : nullptr, d_roots + lo,
+                             d_changed + lo, s, S.k_old, S.listed ? d_units + lo * upc : nullptr, u32(prep[sl].nu));
         it->prof = prof;
-        if (rc != VX_OK) return rc;
+        if (r != VX_OK) return r;
         if (trace) CU_TRY(cudaEventRecord(it->tevs[4 * sl + 3], s));
         CU_TRY(cudaEventRecord(it->ev_done[sb], s));
+        return VX_OK;
+    };
+    // Order of the enqueues: the first two slices' bus traffic goes out before anything else (each into its own
+    // slab); then every slice must have been checked; from there on build k is followed by the traffic of k+2,
+    // which reuses build k's slab.
+    rc = enqueue_stage(0);
+    if (rc == VX_OK && n_slices > 1) rc = enqueue_stage(1);
+    if (rc != VX_OK) return rc;
+    {
+        const double t0 = now_us();
+        for (size_t sl = 0; sl < n_slices; ++sl) ready(sl);
+        host_lists += now_us() - t0;
+        for (size_t sl = 0; sl < n_slices; ++sl) {
+            fused = fused && prep[sl].fused;
+            if (prep[sl].rc != VX_OK) {  // nothing has touched the interner yet
+                cudaStreamSynchronize(cs);
+                return fail(prep[sl].rc, prep[sl].err);
+            }
+        }
+        if (!fused) {
+            cudaStreamSynchronize(cs);
+            lk.unlock();
+            return serial();
+        }
     }
+    for (size_t sl = 0; sl < n_slices; ++sl) {
+        rc = enqueue_build(sl);
+        if (rc == VX_OK && sl + 2 < n_slices) rc = enqueue_stage(sl + 2);
+        if (rc != VX_OK) return rc;
+    }
+    const size_t k = total_listed;
     CU_TRY(cudaMemcpyAsync(h_roots, d_roots, n * 8, cudaMemcpyDeviceToHost, s));
     CU_TRY(cudaMemcpyAsync(h_changed, d_changed, n, cudaMemcpyDeviceToHost, s));
     const double t_queued = now_us();
@@ -1608,6 +1690,13 @@ int vx_apply_batches(vx_interner* it, vx_tree* const* trees, const vx_batch* con
     }
     std::vector<u64> dead;
     for (size_t i = 0; i < n; ++i) {
+        // a batch with neither patches nor a fill hands the tree's own root back (voxtree.rs:756-758): on an
+        // EMPTY tree apply_batch still answers true and marks it dirty (:303-328).  The device saw such a
+        // batch as all-zero masks ("unchanged"), so the reference's answer is put in here.
+        if (!(h_flags[i] & (VX_FLAG_FILL | VX_FLAG_PATCHES)) && trees[i]->root == VX_BLOCK_EMPTY) {
+            h_changed[i] = 1;
+            h_roots[i] = VX_BLOCK_EMPTY;
+        }
         if (h_changed[i]) {
             if (trees[i]->root != VX_BLOCK_EMPTY) dead.push_back(trees[i]->root);
             trees[i]->root = h_roots[i];
