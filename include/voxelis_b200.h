@@ -207,6 +207,21 @@ int vx_roots_to_vec_lod(const vx_interner*, uint8_t max_depth, uint8_t lod, size
 int vx_tree_fill(vx_interner*, vx_tree*, int64_t value);
 int vx_tree_clear(vx_interner*, vx_tree*);
 
+/* ---------------------------------------------------------------- VTM export -------------- */
+/* VoxModel::serialize — world/voxmodel.rs:177-294 (+ serialize_chunk, world/voxchunk.rs:382-405): the VTM payload
+ * of n chunks (positions[n][3] chunk coordinates, roots[n], both host) sharing this interner, written from the
+ * device pools: every alive node renumbered leaves-first in index order, records as the reference writes them,
+ * then the chunk table in the order given (the reference walks a hash map).  Returns the payload size (also when
+ * `out` is NULL or `cap` is too small, in which case nothing is written), <0 on error. */
+int64_t vx_model_serialize(const vx_interner*, size_t n, const int32_t* positions, const vx_block_id* roots,
+                           uint8_t* out, size_t cap);
+/* export_model_to_vtm — io/export.rs:90-151: header, MD5 of the payload, payload (zstd level 7 when `compress`,
+ * Flags::COMPRESSED; libzstd is looked up at run time, VX_E_UNSUPPORTED if absent) -> `path`.  The file opens
+ * with the reference's import_model_from_vtm (io/import.rs:14-98). */
+int vx_export_vtm(const vx_interner*, const char* path, const char* name, uint8_t max_depth, float chunk_world_size,
+                  const int32_t world_bounds[3], size_t n, const int32_t* positions, const vx_block_id* roots,
+                  int compress);
+
 /* ---------------------------------------------------------------- global dedup (new) ------ */
 /* Optional merge of per-GPU interners into hash-partitioned global shards (the Voxelis Bible's
  * "shard the pattern map by hash % N", §3.9/§13).  Height-synchronous rounds: pack the local

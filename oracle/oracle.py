@@ -92,6 +92,10 @@ def lib():
     L.orc_dag_signature.restype = C.c_longlong
     L.orc_dag_signature.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, C.c_int, vp, vp, vp, vp,
                                     C.c_size_t, vp, vp]
+    L.orc_model_serialize.restype = C.c_int64
+    L.orc_model_serialize.argtypes = [vp, C.c_size_t, vp, vp, vp, C.c_size_t]
+    L.orc_model_deserialize.restype = C.c_int64
+    L.orc_model_deserialize.argtypes = [vp, vp, C.c_size_t, vp, vp, C.c_size_t]
     L.orc_time_apply_fresh.restype = C.c_double
     L.orc_time_apply_fresh.argtypes = [C.c_int, C.c_int, C.c_size_t, C.c_size_t, vp, vp, C.c_int, vp]
     _lib = L
@@ -194,6 +198,25 @@ class VoxInterner:
             None if hf is None else _ptr(hf), None if fv is None else _ptr(fv),
             None if hp is None else _ptr(hp), _ptr(roots), _ptr(changed)))
         return roots, changed
+
+    def model_serialize(self, positions, roots) -> bytes:
+        """VoxModel::serialize (world/voxmodel.rs:177-294): the VTM payload for chunks (positions[n][3], roots[n])."""
+        positions = np.ascontiguousarray(positions, np.int32)
+        roots = np.ascontiguousarray(roots, np.uint64)
+        n = len(roots)
+        size = _check(lib().orc_model_serialize(self.h, n, _ptr(positions), _ptr(roots), None, 0))
+        out = np.zeros(max(size, 1), np.uint8)
+        _check(lib().orc_model_serialize(self.h, n, _ptr(positions), _ptr(roots), _ptr(out), size))
+        return out[:size].tobytes()
+
+    def model_deserialize(self, data: bytes):
+        """VoxModel::deserialize (world/voxmodel.rs:296-408) into this (fresh) interner -> (positions, roots)."""
+        buf = np.frombuffer(data, np.uint8)
+        cap = len(buf) // 25 + 1                     # a chunk record is at least 12 + 12 + 1 bytes
+        pos = np.zeros((cap, 3), np.int32)
+        roots = np.zeros(cap, np.uint64)
+        n = _check(lib().orc_model_deserialize(self.h, _ptr(buf), len(buf), _ptr(pos), _ptr(roots), cap))
+        return pos[:n].copy(), roots[:n].copy()
 
     def root_to_vec(self, root: int, depth: int, lod: int = 0):
         n = 1 << max(depth - lod, 0)

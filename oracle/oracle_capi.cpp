@@ -423,4 +423,42 @@ double orc_time_apply_fresh(int dtype, int depth, size_t budget, size_t n, const
     return std::chrono::duration<double>(t1 - t0).count();
 }
 
+// VoxModel::serialize (world/voxmodel.rs:177-294): the VTM payload of n chunks (positions[n][3], roots[n]).
+// Returns the payload size; writes it when it fits in `cap`.
+int64_t orc_model_serialize(void* ih, size_t n, const int32_t* positions, const uint64_t* roots, uint8_t* out, size_t cap) {
+    AnyInterner* a = (AnyInterner*)ih;
+    std::vector<u8> buf;
+    int rc = guarded([&] {
+        if (a->dtype == 0)
+            model_serialize<u8>(*a->i8, n, positions, roots, buf);
+        else
+            model_serialize<int32_t>(*a->i32, n, positions, roots, buf);
+        return 0;
+    });
+    if (rc != 0) return rc;
+    if (out && buf.size() <= cap) memcpy(out, buf.data(), buf.size());
+    return int64_t(buf.size());
+}
+// VoxModel::deserialize (world/voxmodel.rs:296-408) into a FRESH interner.  Returns the number of chunks;
+// positions_out[cap][3] / roots_out[cap] receive them.
+int64_t orc_model_deserialize(void* ih, const uint8_t* data, size_t len, int32_t* positions_out, uint64_t* roots_out,
+                              size_t cap) {
+    AnyInterner* a = (AnyInterner*)ih;
+    std::vector<int32_t> pos;
+    std::vector<u64> roots;
+    int rc = guarded([&] {
+        if (a->dtype == 0)
+            model_deserialize<u8>(*a->i8, data, len, pos, roots);
+        else
+            model_deserialize<int32_t>(*a->i32, data, len, pos, roots);
+        return 0;
+    });
+    if (rc != 0) return rc;
+    if (roots.size() <= cap) {
+        if (positions_out) memcpy(positions_out, pos.data(), pos.size() * 4);
+        if (roots_out) memcpy(roots_out, roots.data(), roots.size() * 8);
+    }
+    return int64_t(roots.size());
+}
+
 }  // extern "C"

@@ -27,11 +27,13 @@
 //     The oracle compares full keys, so it differs from the reference only where the
 //     reference would silently alias two different nodes on a 64-bit hash collision.
 #pragma once
+#include <algorithm>
 #include <array>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
 #include <stdexcept>
+#include <type_traits>
 #include <vector>
 
 namespace vxo {
@@ -822,4 +824,185 @@ void tree_to_vec(const Interner<T>& in, const Tree& t, T* data, int md = -1) {
     }
 }
 
+// ---------------------------------------------------------------------------------
+// VTM payload — VoxModel::serialize / deserialize (world/voxmodel.rs:177-294, :296-408),
+// serialize_chunk / deserialize_chunk (world/voxchunk.rs:382-440), varints (io/varint.rs),
+// interner side: deserialize_leaf / preallocate_branch_id / deserialize_branch
+// (interner/mod.rs:930-1000), VoxTree::set_root_id (spatial/voxtree.rs:135-141).
+// The reference walks `self.chunks` (a hash map, arbitrary order); here the chunks are
+// written in the order given.
+// ---------------------------------------------------------------------------------
+inline void put_varint(std::vector<u8>& o, u64 v) {  // io/varint.rs:5-32 (u32 and usize forms agree)
+    while (v >= 0x80) {
+        o.push_back(u8((v & 0x7F) | 0x80));
+        v >>= 7;
+    }
+    o.push_back(u8(v));
+}
+inline void put_be32(std::vector<u8>& o, u32 v) {
+    for (int s = 24; s >= 0; s -= 8) o.push_back(u8(v >> s));
+}
+template <class T>
+inline void put_value_be(std::vector<u8>& o, T v) {  // core/voxel.rs:26-28 (to_be_bytes)
+    for (int s = int(sizeof(T)) * 8 - 8; s >= 0; s -= 8) o.push_back(u8(u64(typename std::make_unsigned<T>::type(v)) >> s));
+}
+inline const u8 VTC_MAGIC[12] = {'V', 'o', 'x', 'T', 'r', 'e', 'e', 'C', 'h', 'u', 'n', 'k'};  // io/consts.rs:3
+
+template <class T>
+void model_serialize(const Interner<T>& in, size_t n, const int32_t* pos, const u64* roots, std::vector<u8>& out) {
+    std::vector<u64> leaves, branches;  // :189-195 every id the two pattern maps hold
+    for (const auto& s : in.patterns[1].slots)
+        if (s.id != ID_INVALID) leaves.push_back(s.id);
+    for (const auto& s : in.patterns[0].slots)
+        if (s.id != ID_INVALID) branches.push_back(s.id);
+    auto by_index = [](u64 a, u64 b) { return id_index(a) < id_index(b); };
+    std::sort(leaves.begin(), leaves.end(), by_index);      // :199-200
+    std::sort(branches.begin(), branches.end(), by_index);
+    std::vector<u32> id_map(in.next_index, 0);              // :186-187 id_map[0] = 0
+    u32 next_id = 1;
+    for (u64 id : leaves) id_map[id_index(id)] = next_id++;  // :202-205
+    for (u64 id : branches)                                   // :207-215
+        if (id_index(id) != 0) id_map[id_index(id)] = next_id++;
+    put_be32(out, u32(leaves.size()));                        // :231
+    for (u64 id : leaves) {                                   // :232-240
+        put_varint(out, id_map[id_index(id)]);
+        put_value_be<T>(out, in.values[id_index(id)]);
+    }
+    put_be32(out, u32(branches.size()) - 1);                  // :242 (slot 0, the empty branch, is not written)
+    for (u64 id : branches) {                                 // :243-268
+        if (id_index(id) == 0) continue;
+        put_varint(out, id_map[id_index(id)]);
+        out.push_back(id_mask(id));
+        for (int k = 0; k < 8; ++k) {
+            u64 ch = in.children[id_index(id)][k];
+            if (id_is_empty(ch)) continue;
+            put_varint(out, id_map[id_index(ch)]);
+        }
+        put_value_be<T>(out, in.values[id_index(id)]);
+    }
+    std::vector<u8> chunks;
+    for (size_t c = 0; c < n; ++c) {                          // voxchunk.rs:382-405
+        chunks.insert(chunks.end(), VTC_MAGIC, VTC_MAGIC + 12);
+        for (int a = 0; a < 3; ++a) put_be32(chunks, u32(pos[3 * c + a]));
+        put_varint(chunks, id_map[id_index(roots[c])]);
+    }
+    put_be32(out, u32(n));                                    // :281-284
+    out.insert(out.end(), chunks.begin(), chunks.end());      // :286-288
+}
+
+struct VtmReader {
+    const u8* p;
+    const u8* end;
+    u8 byte() {
+        if (p >= end) throw RefPanic("unexpected end of VTM data");
+        return *p++;
+    }
+    u32 be32() {
+        u32 v = 0;
+        for (int i = 0; i < 4; ++i) v = (v << 8) | byte();
+        return v;
+    }
+    u32 varint() {  // io/varint.rs:62-96
+        u32 r = 0;
+        int shift = 0;
+        for (;;) {
+            u8 b = byte();
+            r |= u32(b & 0x7F) << shift;
+            if (!(b & 0x80)) break;
+            shift += 7;
+            if (shift >= 32) throw RefPanic("varint too long");
+        }
+        return r;
+    }
+    template <class T>
+    T value_be() {
+        u64 v = 0;
+        for (size_t i = 0; i < sizeof(T); ++i) v = (v << 8) | byte();
+        return T(v);
+    }
+};
+
+// Into a FRESH interner (the reference asserts that file id == next index, mod.rs:933,948).
+// Returns the chunks' positions and root ids.
+template <class T>
+void model_deserialize(Interner<T>& in, const u8* data, size_t len, std::vector<int32_t>& pos, std::vector<u64>& roots) {
+    VtmReader r{data, data + len};
+    const u32 leaf_size = r.be32();  // :310
+    std::vector<u64> by_file_id(1, ID_EMPTY);
+    std::vector<u8> is_leaf(1, 0);
+    auto place = [&](u32 id, u64 block, bool leaf) {
+        if (id >= by_file_id.size()) {
+            by_file_id.resize(id + 1, ID_INVALID);
+            is_leaf.resize(id + 1, 0);
+        }
+        by_file_id[id] = block;
+        is_leaf[id] = leaf;
+    };
+    for (u32 k = 0; k < leaf_size; ++k) {  // :317-326 + mod.rs:941-964
+        u32 id = r.varint();
+        T value = r.template value_be<T>();
+        u32 index = in.next_free_index();
+        if (index != id) throw RefPanic("Invalid block id");
+        if (in.generations[index] != 0) throw RefPanic("Invalid generation");
+        u64 block = id_leaf(index, 0);
+        in.values[index] = value;
+        in.hashes[index] = fx_leaf_hash(value);
+        in.patterns[1].insert(in.hashes[index], block);
+        in.stats.patterns += 1;
+        in.stats.leaf_nodes += 1;
+        place(id, block, true);
+    }
+    const u32 branch_size = r.be32();  // :328
+    struct Rec {
+        u32 id;
+        u32 children[8];
+        T lod;
+    };
+    std::vector<Rec> recs(branch_size);
+    for (u32 k = 0; k < branch_size; ++k) {  // :335-364 + mod.rs:930-939
+        Rec& rec = recs[k];
+        rec.id = r.varint();
+        if (rec.id == 0) throw RefPanic("branch id 0");
+        u8 mask = r.byte(), types = 0;
+        if (mask == 0) throw RefPanic("empty branch mask");
+        for (int c = 0; c < 8; ++c) {
+            rec.children[c] = 0;
+            if (!(mask >> c & 1)) continue;
+            rec.children[c] = r.varint();
+            if (rec.children[c] < is_leaf.size() && is_leaf[rec.children[c]]) types |= u8(1u << c);
+        }
+        rec.lod = r.template value_be<T>();
+        u32 index = in.next_free_index();
+        if (index != rec.id) throw RefPanic("Invalid block id");
+        if (in.generations[index] != 0) throw RefPanic("Invalid generation");
+        place(rec.id, id_branch(index, 0, types, mask), false);
+    }
+    for (const Rec& rec : recs) {  // :366-394 + mod.rs:966-1000
+        u64 block = by_file_id[rec.id];
+        u64 ch[8];
+        for (int c = 0; c < 8; ++c) ch[c] = (id_mask(block) >> c & 1) ? by_file_id[rec.children[c]] : ID_EMPTY;
+        u32 index = id_index(block);
+        memcpy(in.children[index], ch, 64);
+        in.values[index] = rec.lod;
+        in.hashes[index] = fx_branch_hash(ch, id_types(block), id_mask(block));
+        in.patterns[0].insert(in.hashes[index], block);
+        in.stats.patterns += 1;
+        in.stats.branch_nodes += 1;
+        for (int c = 0; c < 8; ++c)
+            if (!id_is_empty(ch[c])) in.inc_ref(ch[c]);  // inc_all_child_refs
+    }
+    const u32 n = r.be32();  // :410
+    for (u32 c = 0; c < n; ++c) {  // voxchunk.rs:407-440
+        for (int k = 0; k < 12; ++k)
+            if (r.byte() != VTC_MAGIC[k]) throw RefPanic("bad chunk magic");
+        for (int a = 0; a < 3; ++a) pos.push_back(int32_t(r.be32()));
+        u32 root = r.varint();
+        if (root >= by_file_id.size() || by_file_id[root] == ID_INVALID) throw RefPanic("unknown root id");
+        u64 block = by_file_id[root];
+        in.inc_ref(block);  // set_root_id, voxtree.rs:135-141 (an EMPTY root bumps slot 0, as in the reference)
+        roots.push_back(block);
+    }
+}
+
 }  // namespace vxo
+

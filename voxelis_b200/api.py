@@ -41,6 +41,7 @@ ABI_SYMBOLS = [
     "vx_batch_masks", "vx_batch_values", "vx_batch_blocks", "vx_batch_to_fill", "vx_batch_size",
     "vx_batch_has_patches", "vx_batch_mark_patched", "vx_batch_max_depth", "vx_batch_dtype",
     "vx_batch_set_many", "vx_batch_assign", "vx_batch_touched_units", "vx_trees_forget",
+    "vx_model_serialize", "vx_export_vtm",
     "vx_tree_create", "vx_tree_destroy", "vx_tree_root_id", "vx_tree_set_root_id", "vx_tree_max_depth",
     "vx_tree_voxels_per_axis", "vx_tree_is_empty", "vx_tree_is_leaf", "vx_tree_is_dirty",
     "vx_tree_mark_dirty", "vx_tree_clear_dirty", "vx_tree_apply_batch", "vx_apply_batches",
@@ -148,6 +149,9 @@ def lib():
     L.vx_roots_to_vec_lod.argtypes = [vp, C.c_uint8, C.c_uint8, sz, vp, vp]
     L.vx_tree_fill.argtypes = [vp, vp, i64]
     L.vx_tree_clear.argtypes = [vp, vp]
+    L.vx_model_serialize.restype = i64
+    L.vx_model_serialize.argtypes = [vp, sz, vp, vp, vp, sz]
+    L.vx_export_vtm.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_uint8, C.c_float, vp, sz, vp, vp, C.c_int]
     L.vx_dedup_heights.argtypes = [vp, vp]
     L.vx_dedup_pack.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp, vp, vp]
     L.vx_dedup_scatter.argtypes = [vp, sz, vp, vp, vp]
@@ -306,6 +310,26 @@ class VoxInterner:
                                           C.c_void_p(d_flags or None), C.c_void_p(d_fills or None),
                                           C.c_void_p(d_roots), C.c_void_p(d_changed or None),
                                           C.c_void_p(stream or None)))
+
+    def model_serialize(self, positions, roots) -> bytes:
+        """VoxModel::serialize (world/voxmodel.rs:177-294): VTM payload of chunks (positions[n][3], roots[n])."""
+        positions = np.ascontiguousarray(positions, np.int32)
+        roots = np.ascontiguousarray(roots, np.uint64)
+        n = len(roots)
+        size = _ck(lib().vx_model_serialize(self.h, n, _ptr(positions), _ptr(roots), None, 0))
+        out = np.zeros(max(size, 1), np.uint8)
+        got = _ck(lib().vx_model_serialize(self.h, n, _ptr(positions), _ptr(roots), _ptr(out), size))
+        assert got == size
+        return out[:size].tobytes()
+
+    def export_vtm(self, path: str, name: str, max_depth: int, chunk_world_size: float, world_bounds, positions, roots,
+                   compress: bool = True):
+        """export_model_to_vtm (io/export.rs:90-151)."""
+        positions = np.ascontiguousarray(positions, np.int32)
+        roots = np.ascontiguousarray(roots, np.uint64)
+        wb = np.ascontiguousarray(world_bounds, np.int32)
+        _ck(lib().vx_export_vtm(self.h, path.encode(), name.encode(), max_depth, float(chunk_world_size), _ptr(wb),
+                                len(roots), _ptr(positions), _ptr(roots), 1 if compress else 0))
 
     def roots_to_vec(self, roots, depth: int, lod: int = 0):
         """to_vec for bare roots; ``lod`` > 0 unfolds only depth - lod levels (world/voxchunk.rs:267)."""

@@ -24,6 +24,10 @@
 #include "vx_release.cuh"
 #include "vx_dedup.cuh"
 #include "vx_stage.cuh"
+#include "vx_vtm.cuh"
+
+#include <cub/device/device_scan.cuh>
+#include <dlfcn.h>
 
 using namespace vx;
 
@@ -678,7 +682,13 @@ vx_interner* vx_interner_create(size_t budget, vx_dtype dtype, int device) {
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail("cudaGetDeviceProperties");
     it->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&it->stream, cudaStreamNonBlocking) != cudaSuccess) return bail("stream");
-    if (cudaStreamCreateWithFlags(&it->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return bail("stream");
+    {
+        // the copy stream carries the staging kernels of host batches (vx_stage.cuh): one CTA per SM that must
+        // not queue behind the builders' full-occupancy grids, so its CTAs are placed first when slots free up
+        int lo_prio = 0, hi_prio = 0;
+        cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio);
+        if (cudaStreamCreateWithPriority(&it->copy_stream, cudaStreamNonBlocking, hi_prio) != cudaSuccess) return bail("stream");
+    }
     for (int i = 0; i < 2; ++i) {
         if (cudaEventCreateWithFlags(&it->ev_copied[i], cudaEventDisableTiming) != cudaSuccess) return bail("event");
         if (cudaEventCreateWithFlags(&it->ev_done[i], cudaEventDisableTiming) != cudaSuccess) return bail("event");
@@ -1978,6 +1988,225 @@ int vx_interner_intern_records(vx_interner* shard, size_t n, const uint64_t* d_r
     if (rc != VX_OK) return rc;
     if (created_out) *created_out = created;
     return VX_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------- VTM (world/voxmodel.rs, io/export.rs)
+namespace {
+
+struct DevBuf {  // scoped device allocation
+    void* p = nullptr;
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+};
+
+// MD5 (RFC 1321) of the payload: io/export.rs:124-128 stores it ahead of the (compressed) data.
+void md5_digest(const u8* data, size_t len, u8 out[16]) {
+    static const u32 K[64] = {
+        0xd76aa478, 0xe8c7b756, 0x242070db, 0xc1bdceee, 0xf57c0faf, 0x4787c62a, 0xa8304613, 0xfd469501, 0x698098d8, 0x8b44f7af,
+        0xffff5bb1, 0x895cd7be, 0x6b901122, 0xfd987193, 0xa679438e, 0x49b40821, 0xf61e2562, 0xc040b340, 0x265e5a51, 0xe9b6c7aa,
+        0xd62f105d, 0x02441453, 0xd8a1e681, 0xe7d3fbc8, 0x21e1cde6, 0xc33707d6, 0xf4d50d87, 0x455a14ed, 0xa9e3e905, 0xfcefa3f8,
+        0x676f02d9, 0x8d2a4c8a, 0xfffa3942, 0x8771f681, 0x6d9d6122, 0xfde5380c, 0xa4beea44, 0x4bdecfa9, 0xf6bb4b60, 0xbebfbc70,
+        0x289b7ec6, 0xeaa127fa, 0xd4ef3085, 0x04881d05, 0xd9d4d039, 0xe6db99e5, 0x1fa27cf8, 0xc4ac5665, 0xf4292244, 0x432aff97,
+        0xab9423a7, 0xfc93a039, 0x655b59c3, 0x8f0ccc92, 0xffeff47d, 0x85845dd1, 0x6fa87e4f, 0xfe2ce6e0, 0xa3014314, 0x4e0811a1,
+        0xf7537e82, 0xbd3af235, 0x2ad7d2bb, 0xeb86d391};
+    static const u8 R[64] = {7, 12, 17, 22, 7, 12, 17, 22, 7, 12, 17, 22, 7, 12, 17, 22, 5, 9,  14, 20, 5, 9,  14, 20, 5, 9,  14, 20, 5, 9,  14, 20,
+                             4, 11, 16, 23, 4, 11, 16, 23, 4, 11, 16, 23, 4, 11, 16, 23, 6, 10, 15, 21, 6, 10, 15, 21, 6, 10, 15, 21, 6, 10, 15, 21};
+    u32 h[4] = {0x67452301, 0xefcdab89, 0x98badcfe, 0x10325476};
+    std::vector<u8> msg(data, data + len);
+    msg.push_back(0x80);
+    while (msg.size() % 64 != 56) msg.push_back(0);
+    const u64 bits = u64(len) * 8;
+    for (int i = 0; i < 8; ++i) msg.push_back(u8(bits >> (8 * i)));
+    for (size_t off = 0; off < msg.size(); off += 64) {
+        u32 w[16];
+        for (int i = 0; i < 16; ++i)
+            w[i] = u32(msg[off + 4 * i]) | u32(msg[off + 4 * i + 1]) << 8 | u32(msg[off + 4 * i + 2]) << 16 | u32(msg[off + 4 * i + 3]) << 24;
+        u32 a = h[0], b = h[1], c = h[2], d = h[3];
+        for (int i = 0; i < 64; ++i) {
+            u32 f, g;
+            if (i < 16)
+                f = (b & c) | (~b & d), g = u32(i);
+            else if (i < 32)
+                f = (d & b) | (~d & c), g = u32(5 * i + 1) & 15;
+            else if (i < 48)
+                f = b ^ c ^ d, g = u32(3 * i + 5) & 15;
+            else
+                f = c ^ (b | ~d), g = u32(7 * i) & 15;
+            const u32 t = d;
+            d = c;
+            c = b;
+            const u32 x = a + f + K[i] + w[g];
+            b = b + ((x << R[i]) | (x >> (32 - R[i])));
+            a = t;
+        }
+        h[0] += a, h[1] += b, h[2] += c, h[3] += d;
+    }
+    for (int i = 0; i < 4; ++i)
+        for (int k = 0; k < 4; ++k) out[4 * i + k] = u8(h[i] >> (8 * k));
+}
+
+void be32(std::vector<u8>& o, u32 v) {
+    for (int sft = 24; sft >= 0; sft -= 8) o.push_back(u8(v >> sft));
+}
+void host_varint(std::vector<u8>& o, u64 v) {
+    while (v >= 0x80) {
+        o.push_back(u8((v & 0x7F) | 0x80));
+        v >>= 7;
+    }
+    o.push_back(u8(v));
+}
+
+int model_serialize_impl(vx_interner* it, size_t n, const int32_t* positions, const vx_block_id* roots, std::vector<u8>& payload) {
+    std::lock_guard<std::mutex> lk(it->mu);
+    DeviceGuard g(it->device);
+    cudaStream_t s = it->stream;
+    Scalars sc;
+    int rc = read_scalars(it, &sc);
+    if (rc != VX_OK) return rc;
+    const u32 nn = sc.next_index;
+    auto up = [](size_t v) { return (v + 255) & ~size_t(255); };
+    const size_t words = up(size_t(nn + 1) * 4);
+    size_t scan_tmp = 0;
+    CU_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, (const u32*)nullptr, (u32*)nullptr, int(nn + 1), s));
+    DevBuf work;
+    CU_TRY(cudaMalloc(&work.p, 7 * words + up(scan_tmp) + up(n * 8) + up(n * 4)));
+    u8* base = (u8*)work.p;
+    VtmArgs a{};
+    a.children = it->dev.children;
+    a.values = it->dev.values;
+    a.refs = it->dev.refs;
+    a.n = nn;
+    a.vsize = u32(dtype_size(it->dtype));
+    a.leaf_flag = (u32*)(base + 0 * words);
+    a.branch_flag = (u32*)(base + 1 * words);
+    a.leaf_rank = (u32*)(base + 2 * words);
+    a.branch_rank = (u32*)(base + 3 * words);
+    a.newid = (u32*)(base + 4 * words);
+    a.sizes = (u32*)(base + 5 * words);
+    a.offs = (u32*)(base + 6 * words);
+    void* tmp = base + 7 * words;
+    u64* d_roots = (u64*)(base + 7 * words + up(scan_tmp));
+    u32* d_root_ids = (u32*)((u8*)d_roots + up(n * 8));
+    const unsigned grid = (nn + 255) / 256;
+    CU_TRY(cudaMemsetAsync(a.sizes, 0, size_t(nn + 1) * 4, s));
+    vtm_classify_kernel<<<grid, 256, 0, s>>>(a);
+    CU_TRY(cub::DeviceScan::ExclusiveSum(tmp, scan_tmp, a.leaf_flag, a.leaf_rank, int(nn), s));
+    CU_TRY(cub::DeviceScan::ExclusiveSum(tmp, scan_tmp, a.branch_flag, a.branch_rank, int(nn), s));
+    vtm_newid_kernel<<<grid, 256, 0, s>>>(a);
+    vtm_sizes_kernel<<<grid, 256, 0, s>>>(a);
+    CU_TRY(cub::DeviceScan::ExclusiveSum(tmp, scan_tmp, a.sizes, a.offs, int(nn + 1), s));
+    CU_TRY(cudaGetLastError());
+    // counts: leaves, branches, bytes of the leaf records, bytes of all records
+    u32 last[4] = {0, 0, 0, 0};
+    CU_TRY(cudaMemcpyAsync(&last[0], a.leaf_rank + nn - 1, 4, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(&last[1], a.leaf_flag + nn - 1, 4, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(&last[2], a.branch_rank + nn - 1, 4, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(&last[3], a.branch_flag + nn - 1, 4, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    const u32 n_leaves = last[0] + last[1], n_branches = last[2] + last[3];
+    u32 leaf_bytes = 0, node_bytes = 0;
+    CU_TRY(cudaMemcpyAsync(&leaf_bytes, a.offs + n_leaves, 4, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(&node_bytes, a.offs + n_leaves + n_branches, 4, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    DevBuf out;
+    CU_TRY(cudaMalloc(&out.p, size_t(node_bytes) + 8));
+    a.out = (u8*)out.p;
+    vtm_write_kernel<<<grid, 256, 0, s>>>(a);
+    CU_TRY(cudaGetLastError());
+    std::vector<u32> root_ids(n);
+    if (n) {
+        CU_TRY(cudaMemcpyAsync(d_roots, roots, n * 8, cudaMemcpyHostToDevice, s));
+        vtm_roots_kernel<<<unsigned((n + 255) / 256), 256, 0, s>>>(a.newid, d_roots, u32(n), d_root_ids);
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaMemcpyAsync(root_ids.data(), d_root_ids, n * 4, cudaMemcpyDeviceToHost, s));
+    }
+    payload.assign(size_t(node_bytes) + 8, 0);
+    CU_TRY(cudaMemcpyAsync(payload.data(), out.p, payload.size(), cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    auto poke_be32 = [&](size_t at, u32 v) {
+        for (int k = 0; k < 4; ++k) payload[at + k] = u8(v >> (24 - 8 * k));
+    };
+    poke_be32(0, n_leaves);                       // voxmodel.rs:231
+    poke_be32(4 + size_t(leaf_bytes), n_branches);  // :242 (the reference's count includes slot 0 and writes count - 1)
+    be32(payload, u32(n));                        // :281-284
+    static const char VTC_MAGIC[] = "VoxTreeChunk";  // io/consts.rs:3
+    for (size_t c = 0; c < n; ++c) {              // world/voxchunk.rs:382-405
+        payload.insert(payload.end(), VTC_MAGIC, VTC_MAGIC + 12);
+        for (int k = 0; k < 3; ++k) be32(payload, u32(positions[3 * c + k]));
+        host_varint(payload, root_ids[c]);
+    }
+    return VX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t vx_model_serialize(const vx_interner* cit, size_t n, const int32_t* positions, const vx_block_id* roots, uint8_t* out,
+                           size_t cap) {
+    vx_interner* it = const_cast<vx_interner*>(cit);
+    if (!it || (n && (!positions || !roots))) return fail(VX_E_INVALID, "null argument");
+    if (n > 0xFFFFFFFFull) return fail(VX_E_INVALID, "too many chunks");
+    std::vector<u8> payload;
+    int rc = model_serialize_impl(it, n, positions, roots, payload);
+    if (rc != VX_OK) return rc;
+    if (out && payload.size() <= cap) memcpy(out, payload.data(), payload.size());
+    return int64_t(payload.size());
+}
+
+int vx_export_vtm(const vx_interner* cit, const char* path, const char* name, uint8_t max_depth, float chunk_world_size,
+                  const int32_t world_bounds[3], size_t n, const int32_t* positions, const vx_block_id* roots, int compress) {
+    vx_interner* it = const_cast<vx_interner*>(cit);
+    if (!it || !path || !name || !world_bounds || (n && (!positions || !roots))) return fail(VX_E_INVALID, "null argument");
+    if (strlen(name) > 255) return fail(VX_E_INVALID, "model name longer than 255 bytes");  // export.rs:121 (u8 length)
+    std::vector<u8> payload;
+    int rc = model_serialize_impl(it, n, positions, roots, payload);
+    if (rc != VX_OK) return rc;
+    u8 digest[16];
+    md5_digest(payload.data(), payload.size(), digest);  // export.rs:124-128: over the UNcompressed payload
+    std::vector<u8> packed;
+    bool compressed = false;
+    if (compress) {  // Flags::DEFAULT = COMPRESSED, zstd level 7 (export.rs:132-136); libzstd is looked up at run time
+        typedef size_t (*bound_fn)(size_t);
+        typedef size_t (*comp_fn)(void*, size_t, const void*, size_t, int);
+        typedef unsigned (*err_fn)(size_t);
+        void* h = dlopen("libzstd.so.1", RTLD_NOW | RTLD_LOCAL);
+        if (!h) h = dlopen("libzstd.so", RTLD_NOW | RTLD_LOCAL);
+        bound_fn bound = h ? (bound_fn)dlsym(h, "ZSTD_compressBound") : nullptr;
+        comp_fn comp = h ? (comp_fn)dlsym(h, "ZSTD_compress") : nullptr;
+        err_fn is_err = h ? (err_fn)dlsym(h, "ZSTD_isError") : nullptr;
+        if (!bound || !comp || !is_err) return fail(VX_E_UNSUPPORTED, "libzstd not found: export with compress = 0 (Flags::NONE)");
+        packed.resize(bound(payload.size()));
+        const size_t got = comp(packed.data(), packed.size(), payload.data(), payload.size(), 7);
+        if (is_err(got)) return fail(VX_E_INVALID, "zstd compression failed");
+        packed.resize(got);
+        compressed = true;
+    }
+    const std::vector<u8>& data = compressed ? packed : payload;
+    if (data.size() > 0xFFFFFFFFull) return fail(VX_E_INVALID, "VTM data larger than 4 GiB");
+    std::vector<u8> head;
+    static const char VTM_MAGIC[] = "VoxTreeModel";  // io/consts.rs:1-2
+    head.insert(head.end(), VTM_MAGIC, VTM_MAGIC + 12);
+    head.push_back(0x01), head.push_back(0x00);             // VTM_VERSION 0x0100, big endian
+    head.push_back(0), head.push_back(compressed ? 1 : 0);  // Flags (io/flags.rs)
+    head.push_back(max_depth);                              // export.rs:111
+    u32 fbits;
+    memcpy(&fbits, &chunk_world_size, 4);
+    be32(head, fbits);                                      // :112-114
+    be32(head, 0), be32(head, 0);                           // RESERVED_1 / RESERVED_2
+    for (int k = 0; k < 3; ++k) be32(head, u32(world_bounds[k]));
+    head.push_back(u8(strlen(name)));
+    head.insert(head.end(), name, name + strlen(name));
+    head.insert(head.end(), digest, digest + 16);
+    be32(head, u32(data.size()));
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(VX_E_INVALID, std::string("cannot open ") + path);
+    const bool ok = fwrite(head.data(), 1, head.size(), f) == head.size() && fwrite(data.data(), 1, data.size(), f) == data.size();
+    fclose(f);
+    return ok ? VX_OK : fail(VX_E_INVALID, std::string("short write to ") + path);
 }
 
 }  // extern "C"
