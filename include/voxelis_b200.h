@@ -152,6 +152,9 @@ int vx_tree_is_leaf(const vx_tree*);
 int vx_tree_is_dirty(const vx_tree*);                 /* VoxOpsDirty   voxtree.rs:355-370 */
 void vx_tree_mark_dirty(vx_tree*);
 void vx_tree_clear_dirty(vx_tree*);
+/* Hands the tree a root whose reference the caller already holds (the roots vx_model_deserialize returns carry
+ * the reference VoxTree::set_root_id took for them, voxtree.rs:135-141).  No refcount change; marks the tree dirty. */
+int vx_tree_adopt_root(vx_tree*, vx_block_id root);
 /* After vx_interner_reset every tree built in that interner dangles; this makes n of them empty again
  * without touching the interner (what dropping and re-creating the VoxTrees does in the reference). */
 int vx_trees_forget(vx_tree* const* trees, size_t n);
@@ -221,6 +224,23 @@ int64_t vx_model_serialize(const vx_interner*, size_t n, const int32_t* position
 int vx_export_vtm(const vx_interner*, const char* path, const char* name, uint8_t max_depth, float chunk_world_size,
                   const int32_t world_bounds[3], size_t n, const int32_t* positions, const vx_block_id* roots,
                   int compress);
+
+/* VoxModel::deserialize — world/voxmodel.rs:296-408 (+ deserialize_chunk, world/voxchunk.rs:407-440; interner side
+ * interner/mod.rs:930-1000) into a FRESH interner: node k of the file becomes pool index k, as the reference asserts.
+ * Returns the number of chunks and writes positions_out[n][3] / roots_out[n] (host; each root holds one reference,
+ * voxtree.rs:135-141); fails with VX_E_INVALID before touching the interner when `cap` < n or the data is malformed. */
+int64_t vx_model_deserialize(vx_interner*, const uint8_t* data, size_t len, int32_t* positions_out,
+                             vx_block_id* roots_out, size_t cap);
+typedef struct vx_vtm_info {
+    uint16_t flags;          /* io/flags.rs: bit 0 = COMPRESSED */
+    uint8_t max_depth;       /* "lod_level" in io/import.rs:36 */
+    float chunk_world_size;
+    int32_t world_bounds[3];
+    char name[256];
+} vx_vtm_info;
+/* import_model_from_vtm — io/import.rs:14-98: header, zstd (when flagged), MD5 check, then vx_model_deserialize. */
+int64_t vx_import_vtm(vx_interner*, const char* path, vx_vtm_info* info_out, int32_t* positions_out,
+                      vx_block_id* roots_out, size_t cap);
 
 /* ---------------------------------------------------------------- global dedup (new) ------ */
 /* Optional merge of per-GPU interners into hash-partitioned global shards (the Voxelis Bible's

@@ -62,6 +62,8 @@ def lib():
     L.orc_tree_root.restype = C.c_uint64
     L.orc_tree_root.argtypes = [vp]
     L.orc_tree_dirty.argtypes = [vp]
+    L.orc_tree_adopt_root.argtypes = [vp, C.c_uint64]
+    L.orc_tree_adopt_root.restype = None
     L.orc_batch_blocks.restype = C.c_size_t
     L.orc_batch_blocks.argtypes = [C.c_int]
     L.orc_batch_set.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64]
@@ -294,6 +296,7 @@ class VoxTree:
     def fill(self, interner, v): _check(lib().orc_tree_fill(interner.h, self.h, int(v)))
     def clear(self, interner): _check(lib().orc_tree_clear(interner.h, self.h))
     def get_root_id(self) -> int: return lib().orc_tree_root(self.h)
+    def adopt_root(self, root: int): lib().orc_tree_adopt_root(self.h, int(root))
     def is_empty(self) -> bool: return self.get_root_id() == 0
     def is_leaf(self) -> bool: return id_is_leaf(self.get_root_id())
     def is_dirty(self) -> bool: return bool(lib().orc_tree_dirty(self.h))

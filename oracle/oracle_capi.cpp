@@ -81,6 +81,11 @@ void* orc_tree_create(int depth) {
 }
 void orc_tree_destroy(void* t) { delete (Tree*)t; }
 uint64_t orc_tree_root(void* t) { return ((Tree*)t)->root_id; }
+// the tree takes over a root whose reference already exists (roots returned by orc_model_deserialize)
+void orc_tree_adopt_root(void* t, uint64_t root) {
+    ((Tree*)t)->root_id = root;
+    ((Tree*)t)->dirty = true;
+}
 int orc_tree_dirty(void* t) { return ((Tree*)t)->dirty; }
 
 size_t orc_batch_blocks(int depth) { return batch_blocks(depth); }

@@ -947,9 +947,7 @@ void model_deserialize(Interner<T>& in, const u8* data, size_t len, std::vector<
         u64 block = id_leaf(index, 0);
         in.values[index] = value;
         in.hashes[index] = fx_leaf_hash(value);
-        in.patterns[1].insert(in.hashes[index], block);
-        in.stats.patterns += 1;
-        in.stats.leaf_nodes += 1;
+        in.patterns[1].insert(in.hashes[index], block);  // (no stats besides the allocation's: mod.rs:941-964)
         place(id, block, true);
     }
     const u32 branch_size = r.be32();  // :328
@@ -986,8 +984,6 @@ void model_deserialize(Interner<T>& in, const u8* data, size_t len, std::vector<
         in.values[index] = rec.lod;
         in.hashes[index] = fx_branch_hash(ch, id_types(block), id_mask(block));
         in.patterns[0].insert(in.hashes[index], block);
-        in.stats.patterns += 1;
-        in.stats.branch_nodes += 1;
         for (int c = 0; c < 8; ++c)
             if (!id_is_empty(ch[c])) in.inc_ref(ch[c]);  // inc_all_child_refs
     }

@@ -114,3 +114,77 @@ def test_vtm_file(gpu_api, oracle_api, tmp_path, compress):
     c2 = o.VoxInterner(64 << 20)
     _, roots2 = c2.model_deserialize(f["payload"])
     assert np.array_equal(g.roots_to_vec(groots[:3], 5)[2], c2.root_to_vec(int(roots2[2]), 5))
+
+
+@pytest.mark.parametrize("dtype", [wl.U8, wl.I32], ids=["u8", "i32"])
+def test_import_installs_a_working_interner(gpu_api, oracle_api, dtype):
+    """vx_model_deserialize: same voxels, refcount == in-degree, and the hash tables really hold the imported
+    nodes — further edits on the imported trees find them (same live-node count as the oracle doing the same
+    on its own import of the same payload)."""
+    vx, o = gpu_api, oracle_api
+    depth = 4
+    g, groots, c, croots, positions = build(vx, o, depth, dtype)
+    payload = g.model_serialize(positions, groots)
+    g2, c2 = vx.VoxInterner.with_memory_budget(64 << 20, dtype), o.VoxInterner(64 << 20, dtype)
+    pos_g, roots_g = g2.model_deserialize(payload)
+    pos_c, roots_c = c2.model_deserialize(payload)
+    assert np.array_equal(pos_g, positions) and np.array_equal(pos_c, positions)
+    assert np.array_equal(roots_g, roots_c)                     # file id == pool index on both sides
+    assert np.array_equal(g2.roots_to_vec(roots_g, depth), g.roots_to_vec(groots, depth))
+    d2, dc = g2.download(), c2.download()
+    assert d2["n"] == dc["n"]
+    assert np.array_equal(d2["children"], dc["children"]) and np.array_equal(d2["values"], dc["values"])
+    assert np.array_equal(d2["refs"][1:], dc["refs"][1:])
+    # a second interner state: export of the import is the same file
+    assert g2.model_serialize(pos_g, roots_g) == payload
+    # edits on top: the batch of chunk 0 applied to every imported tree
+    masks, values = wl.batch_from_function(depth, wl.p_random(4), dtype, 1)
+    # (each imported root already holds its tree's reference, voxtree.rs:135-141: the handles adopt it)
+    b = vx.Batch(depth, dtype)
+    b.assign(masks[0], values[0])
+    gtrees = [vx.VoxTree(depth, dtype) for _ in roots_g]
+    for t, rg in zip(gtrees, roots_g):
+        t.adopt_root(int(rg))
+    vx.apply_batches(g2, gtrees, [b] * len(gtrees))
+    ob = o.Batch(depth, dtype)
+    ob.masks[:], ob.values[:], ob.has_patches = masks[0], values[0], True
+    for i, rc in enumerate(roots_c):
+        t = o.VoxTree(depth, dtype)
+        t.adopt_root(int(rc))
+        t.apply_batch(c2, ob)
+        assert np.array_equal(gtrees[i].to_vec(g2), t.to_vec(c2)), i
+    assert g2.stats()["alive_nodes"] == c2.stats()["alive_nodes"]
+
+
+def test_import_vtm_file_and_errors(gpu_api, oracle_api, tmp_path):
+    vx, o = gpu_api, oracle_api
+    g, groots, c, croots, positions = build(vx, o, 5, wl.U8)
+    for compress in (False, True):
+        path = os.path.join(tmp_path, f"w{int(compress)}.vtm")
+        try:
+            g.export_vtm(path, "dunes", 5, 2.5, (3, 2, 3), positions, groots, compress=compress)
+        except vx.VoxelisError as e:
+            if compress and e.code == -4:
+                continue
+            raise
+        g2 = vx.VoxInterner.with_memory_budget(64 << 20)
+        meta, pos, roots = g2.import_vtm(path)
+        assert meta == {"flags": int(compress), "max_depth": 5, "chunk_world_size": 2.5, "world_bounds": (3, 2, 3),
+                        "name": "dunes"}
+        assert np.array_equal(pos, positions)
+        assert np.array_equal(g2.roots_to_vec(roots, 5), g.roots_to_vec(groots, 5))
+        # not fresh any more: a second import is refused (the reference would trip its index assertion)
+        with pytest.raises(vx.VoxelisError):
+            g2.import_vtm(path)
+    # a corrupted payload fails the MD5 check before anything is installed
+    raw = bytearray(open(os.path.join(tmp_path, "w0.vtm"), "rb").read())
+    raw[-5] ^= 0x40
+    bad = os.path.join(tmp_path, "bad.vtm")
+    open(bad, "wb").write(raw)
+    g3 = vx.VoxInterner.with_memory_budget(64 << 20)
+    with pytest.raises(vx.VoxelisError):
+        g3.import_vtm(bad)
+    assert g3.stats()["alive_nodes"] == 1
+    with pytest.raises(vx.VoxelisError):
+        g3.model_deserialize(g.model_serialize(positions, groots)[:-3])      # truncated
+    assert g3.stats()["alive_nodes"] == 1

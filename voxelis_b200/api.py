@@ -41,7 +41,7 @@ ABI_SYMBOLS = [
     "vx_batch_masks", "vx_batch_values", "vx_batch_blocks", "vx_batch_to_fill", "vx_batch_size",
     "vx_batch_has_patches", "vx_batch_mark_patched", "vx_batch_max_depth", "vx_batch_dtype",
     "vx_batch_set_many", "vx_batch_assign", "vx_batch_touched_units", "vx_trees_forget",
-    "vx_model_serialize", "vx_export_vtm",
+    "vx_model_serialize", "vx_export_vtm", "vx_model_deserialize", "vx_import_vtm", "vx_tree_adopt_root",
     "vx_tree_create", "vx_tree_destroy", "vx_tree_root_id", "vx_tree_set_root_id", "vx_tree_max_depth",
     "vx_tree_voxels_per_axis", "vx_tree_is_empty", "vx_tree_is_leaf", "vx_tree_is_dirty",
     "vx_tree_mark_dirty", "vx_tree_clear_dirty", "vx_tree_apply_batch", "vx_apply_batches",
@@ -118,6 +118,7 @@ def lib():
     L.vx_batch_assign.argtypes = [vp, vp, vp]
     L.vx_batch_touched_units.argtypes = [vp]
     L.vx_trees_forget.argtypes = [vp, sz]
+    L.vx_tree_adopt_root.argtypes = [vp, u64]
     L.vx_batch_max_depth.restype = C.c_uint8
     L.vx_batch_max_depth.argtypes = [vp]
     L.vx_batch_dtype.argtypes = [vp]
@@ -152,6 +153,10 @@ def lib():
     L.vx_model_serialize.restype = i64
     L.vx_model_serialize.argtypes = [vp, sz, vp, vp, vp, sz]
     L.vx_export_vtm.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_uint8, C.c_float, vp, sz, vp, vp, C.c_int]
+    L.vx_model_deserialize.restype = i64
+    L.vx_model_deserialize.argtypes = [vp, vp, sz, vp, vp, sz]
+    L.vx_import_vtm.restype = i64
+    L.vx_import_vtm.argtypes = [vp, C.c_char_p, vp, vp, vp, sz]
     L.vx_dedup_heights.argtypes = [vp, vp]
     L.vx_dedup_pack.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp, vp, vp]
     L.vx_dedup_scatter.argtypes = [vp, sz, vp, vp, vp]
@@ -331,6 +336,28 @@ class VoxInterner:
         _ck(lib().vx_export_vtm(self.h, path.encode(), name.encode(), max_depth, float(chunk_world_size), _ptr(wb),
                                 len(roots), _ptr(positions), _ptr(roots), 1 if compress else 0))
 
+    def model_deserialize(self, data: bytes):
+        """VoxModel::deserialize (world/voxmodel.rs:296-408) into this FRESH interner -> (positions, roots)."""
+        buf = np.frombuffer(data, np.uint8)
+        cap = len(buf) // 25 + 1                     # a chunk record is at least 12 + 12 + 1 bytes
+        pos = np.zeros((cap, 3), np.int32)
+        roots = np.zeros(cap, np.uint64)
+        n = _ck(lib().vx_model_deserialize(self.h, _ptr(buf), len(buf), _ptr(pos), _ptr(roots), cap))
+        return pos[:n].copy(), roots[:n].copy()
+
+    def import_vtm(self, path: str, max_chunks: int = 1 << 20):
+        """import_model_from_vtm (io/import.rs:14-98) -> (info dict, positions, roots)."""
+        class Info(C.Structure):
+            _fields_ = [("flags", C.c_uint16), ("max_depth", C.c_uint8), ("chunk_world_size", C.c_float),
+                        ("world_bounds", C.c_int32 * 3), ("name", C.c_char * 256)]
+        info = Info()
+        pos = np.zeros((max_chunks, 3), np.int32)
+        roots = np.zeros(max_chunks, np.uint64)
+        n = _ck(lib().vx_import_vtm(self.h, path.encode(), C.byref(info), _ptr(pos), _ptr(roots), max_chunks))
+        meta = {"flags": info.flags, "max_depth": info.max_depth, "chunk_world_size": info.chunk_world_size,
+                "world_bounds": tuple(info.world_bounds), "name": info.name.decode()}
+        return meta, pos[:n].copy(), roots[:n].copy()
+
     def roots_to_vec(self, roots, depth: int, lod: int = 0):
         """to_vec for bare roots; ``lod`` > 0 unfolds only depth - lod levels (world/voxchunk.rs:267)."""
         roots = np.ascontiguousarray(roots, np.uint64)
@@ -455,6 +482,7 @@ class VoxTree:
     def fill(self, interner, v): _ck(lib().vx_tree_fill(interner.h, self.h, int(v)))
     def clear(self, interner): _ck(lib().vx_tree_clear(interner.h, self.h))
     def get_root_id(self) -> int: return lib().vx_tree_root_id(self.h)
+    def adopt_root(self, root: int): _ck(lib().vx_tree_adopt_root(self.h, int(root)))
     def is_empty(self) -> bool: return bool(lib().vx_tree_is_empty(self.h))
     def is_leaf(self) -> bool: return bool(lib().vx_tree_is_leaf(self.h))
     def is_dirty(self) -> bool: return bool(lib().vx_tree_is_dirty(self.h))

@@ -1216,6 +1216,12 @@ void vx_tree_mark_dirty(vx_tree* t) {
 void vx_tree_clear_dirty(vx_tree* t) {
     if (t) t->dirty = false;
 }
+int vx_tree_adopt_root(vx_tree* t, vx_block_id root) {
+    if (!t || root == VX_BLOCK_INVALID) return fail(VX_E_INVALID, "null tree or invalid root");
+    t->root = root;
+    t->dirty = true;
+    return VX_OK;
+}
 int vx_trees_forget(vx_tree* const* trees, size_t n) {
     if (n && !trees) return fail(VX_E_INVALID, "null argument");
     for (size_t i = 0; i < n; ++i)
@@ -2141,6 +2147,176 @@ int model_serialize_impl(vx_interner* it, size_t n, const int32_t* positions, co
     return VX_OK;
 }
 
+
+struct VtmCursor {
+    const u8* p;
+    const u8* end;
+    bool ok = true;
+    u8 byte() {
+        if (p >= end) {
+            ok = false;
+            return 0;
+        }
+        return *p++;
+    }
+    u32 be() {
+        u32 v = 0;
+        for (int i = 0; i < 4; ++i) v = (v << 8) | byte();
+        return v;
+    }
+    u32 varint() {  // io/varint.rs:56-77
+        u32 r = 0;
+        for (int shift = 0; shift < 35; shift += 7) {
+            const u8 b = byte();
+            r |= u32(b & 0x7F) << shift;
+            if (!(b & 0x80)) return r;
+        }
+        ok = false;
+        return 0;
+    }
+    int64_t value(size_t bytes) {
+        u32 v = 0;
+        for (size_t i = 0; i < bytes; ++i) v = (v << 8) | byte();
+        return bytes == 1 ? int64_t(v) : int64_t(int32_t(v));
+    }
+};
+
+int model_deserialize_impl(vx_interner* it, const u8* data, size_t len, int32_t* positions_out, vx_block_id* roots_out, size_t cap,
+                           int64_t* n_out) {
+    const size_t vs = dtype_size(it->dtype);
+    VtmCursor r{data, data + len};
+    // ---- parse (voxmodel.rs:310-364, 410; voxchunk.rs:407-440).  File ids must be 1..L for the leaves and
+    // L+1.. for the branches, in order: the reference asserts id == next pool index (mod.rs:933,948).
+    const u32 L = r.be();
+    if (!r.ok || size_t(L) > len) return fail(VX_E_INVALID, "VTM payload: bad leaf count");
+    std::vector<u8> values;  // pool image from index 1: [L + Bc] values in device layout
+    values.reserve((size_t(L) + 16) * vs);
+    auto push_value = [&](int64_t v) {
+        if (vs == 1)
+            values.push_back(u8(v));
+        else {
+            const int32_t w = int32_t(v);
+            values.insert(values.end(), (const u8*)&w, (const u8*)&w + 4);
+        }
+    };
+    for (u32 k = 0; k < L; ++k) {
+        if (r.varint() != k + 1) return fail(VX_E_INVALID, "VTM payload: Invalid block id");
+        push_value(r.value(vs));
+    }
+    const u32 Bc = r.be();
+    if (!r.ok || size_t(Bc) > len) return fail(VX_E_INVALID, "VTM payload: bad branch count");
+    const size_t N = size_t(L) + Bc;
+    if (N + 1 > it->capacity) return fail(VX_E_OOM, "Out of memory");
+    std::vector<u32> kids(size_t(Bc) * 8, 0);  // file ids of the children
+    std::vector<u8> masks(Bc), types(Bc);
+    for (u32 k = 0; k < Bc; ++k) {
+        if (r.varint() != L + k + 1) return fail(VX_E_INVALID, "VTM payload: Invalid block id");
+        const u8 m = r.byte();
+        if (m == 0) return fail(VX_E_INVALID, "VTM payload: branch without children");  // voxmodel.rs:363
+        u8 t = 0;
+        for (int c = 0; c < 8; ++c) {
+            if (!(m >> c & 1)) continue;
+            const u32 id = r.varint();
+            if (id == 0 || id > N) return fail(VX_E_INVALID, "VTM payload: unknown child id");
+            kids[size_t(k) * 8 + c] = id;
+            if (id <= L) t |= u8(1u << c);  // leaf_patterns.contains_key (:352-354)
+        }
+        masks[k] = m;
+        types[k] = t;
+        push_value(r.value(vs));
+    }
+    const u32 n = r.be();
+    if (!r.ok) return fail(VX_E_INVALID, "VTM payload: truncated");
+    if (size_t(n) > cap) return fail(VX_E_INVALID, "vx_model_deserialize: caller arrays too small");
+    auto block_of = [&](u32 id) -> u64 {
+        if (id == 0) return 0;
+        return id <= L ? id_leaf(id) : id_branch(id, types[id - L - 1], masks[id - L - 1]);
+    };
+    std::vector<u64> rows(size_t(Bc) * 8);
+    std::vector<u32> refs(N + 1, 0);
+    for (size_t k = 0; k < size_t(Bc) * 8; ++k) {
+        rows[k] = block_of(kids[k]);
+        if (kids[k]) refs[kids[k]] += 1;  // inc_all_child_refs (mod.rs:999)
+    }
+    std::vector<u64> roots(n);
+    for (u32 c = 0; c < n; ++c) {
+        for (int k = 0; k < 12; ++k)
+            if (r.byte() != u8("VoxTreeChunk"[k])) return fail(VX_E_INVALID, "VTM payload: bad chunk magic");
+        for (int a = 0; a < 3; ++a) {
+            const u32 v = r.be();
+            if (positions_out) positions_out[3 * size_t(c) + a] = int32_t(v);
+        }
+        const u32 id = r.varint();
+        if (!r.ok || id > N) return fail(VX_E_INVALID, "VTM payload: unknown root id");
+        roots[c] = block_of(id);
+        if (id) refs[id] += 1;  // set_root_id (voxtree.rs:135-141)
+    }
+    if (!r.ok) return fail(VX_E_INVALID, "VTM payload: truncated");
+    // ---- install
+    std::lock_guard<std::mutex> lk(it->mu);
+    DeviceGuard g(it->device);
+    cudaStream_t s = it->stream;
+    Scalars sc;
+    int rc = read_scalars(it, &sc);
+    if (rc != VX_OK) return rc;
+    if (sc.next_index != 1 || sc.free_count != 0)
+        return fail(VX_E_INVALID, "vx_model_deserialize needs a fresh interner (the reference asserts file id == pool index)");
+    if (N) {
+        CU_TRY(cudaMemcpyAsync((u8*)it->dev.values + vs, values.data(), N * vs, cudaMemcpyHostToDevice, s));
+        CU_TRY(cudaMemcpyAsync(it->dev.refs + 1, refs.data() + 1, N * 4, cudaMemcpyHostToDevice, s));
+        CU_TRY(cudaMemsetAsync(it->dev.children + 8, 0, size_t(L) * 64, s));
+        if (Bc) CU_TRY(cudaMemcpyAsync(it->dev.children + (size_t(L) + 1) * 8, rows.data(), size_t(Bc) * 64, cudaMemcpyHostToDevice, s));
+        const unsigned grid = unsigned((N + 255) / 256);
+        if (it->dtype == VX_U8)
+            vtm_install_kernel<u8><<<grid, 256, 0, s>>>(it->dev, L, u32(N));
+        else
+            vtm_install_kernel<int32_t><<<grid, 256, 0, s>>>(it->dev, L, u32(N));
+        CU_TRY(cudaGetLastError());
+        const u32 next = u32(N + 1);
+        CU_TRY(cudaMemcpyAsync(&it->d_scalars->next_index, &next, 4, cudaMemcpyHostToDevice, s));
+    }
+    rc = check_device_error(it);
+    if (rc != VX_OK) return rc;
+    if (roots_out) memcpy(roots_out, roots.data(), size_t(n) * 8);
+    *n_out = int64_t(n);
+    return VX_OK;
+}
+
+// zstd stream -> bytes through libzstd looked up at run time (the reference writes with the streaming encoder,
+// io/export.rs:132-136, so the frame need not carry its content size)
+int zstd_decompress(const u8* src, size_t len, std::vector<u8>& out) {
+    struct InBuf { const void* src; size_t size, pos; };
+    struct OutBuf { void* dst; size_t size, pos; };
+    typedef void* (*create_fn)();
+    typedef size_t (*free_fn)(void*);
+    typedef size_t (*step_fn)(void*, OutBuf*, InBuf*);
+    typedef unsigned (*err_fn)(size_t);
+    void* h = dlopen("libzstd.so.1", RTLD_NOW | RTLD_LOCAL);
+    if (!h) h = dlopen("libzstd.so", RTLD_NOW | RTLD_LOCAL);
+    create_fn create = h ? (create_fn)dlsym(h, "ZSTD_createDStream") : nullptr;
+    free_fn destroy = h ? (free_fn)dlsym(h, "ZSTD_freeDStream") : nullptr;
+    step_fn step = h ? (step_fn)dlsym(h, "ZSTD_decompressStream") : nullptr;
+    err_fn is_err = h ? (err_fn)dlsym(h, "ZSTD_isError") : nullptr;
+    if (!create || !destroy || !step || !is_err) return fail(VX_E_UNSUPPORTED, "libzstd not found: cannot read a compressed VTM file");
+    void* ds = create();
+    if (!ds) return fail(VX_E_INVALID, "ZSTD_createDStream failed");
+    InBuf in{src, len, 0};
+    std::vector<u8> chunk(size_t(1) << 20);
+    size_t hint = 1;
+    while (in.pos < in.size || hint != 0) {
+        OutBuf ob{chunk.data(), chunk.size(), 0};
+        hint = step(ds, &ob, &in);
+        if (is_err(hint)) {
+            destroy(ds);
+            return fail(VX_E_INVALID, "corrupt zstd stream in VTM file");
+        }
+        out.insert(out.end(), chunk.data(), chunk.data() + ob.pos);
+        if (in.pos == in.size && ob.pos == 0) break;
+    }
+    destroy(ds);
+    return VX_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -2207,6 +2383,60 @@ int vx_export_vtm(const vx_interner* cit, const char* path, const char* name, ui
     const bool ok = fwrite(head.data(), 1, head.size(), f) == head.size() && fwrite(data.data(), 1, data.size(), f) == data.size();
     fclose(f);
     return ok ? VX_OK : fail(VX_E_INVALID, std::string("short write to ") + path);
+}
+
+int64_t vx_model_deserialize(vx_interner* it, const uint8_t* data, size_t len, int32_t* positions_out, vx_block_id* roots_out,
+                             size_t cap) {
+    if (!it || !data) return fail(VX_E_INVALID, "null argument");
+    if (it->poisoned) return fail(VX_E_POISONED, "interner overflowed earlier; reset it");
+    int64_t n = 0;
+    int rc = model_deserialize_impl(it, data, len, positions_out, roots_out, cap, &n);
+    return rc != VX_OK ? rc : n;
+}
+
+int64_t vx_import_vtm(vx_interner* it, const char* path, vx_vtm_info* info, int32_t* positions_out, vx_block_id* roots_out,
+                      size_t cap) {
+    if (!it || !path) return fail(VX_E_INVALID, "null argument");
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(VX_E_INVALID, std::string("cannot open ") + path);
+    std::vector<u8> raw;
+    u8 buf[1 << 16];
+    for (size_t got; (got = fread(buf, 1, sizeof(buf), f)) > 0;) raw.insert(raw.end(), buf, buf + got);
+    fclose(f);
+    VtmCursor r{raw.data(), raw.data() + raw.size()};
+    for (int k = 0; k < 12; ++k)
+        if (r.byte() != u8("VoxTreeModel"[k])) return fail(VX_E_INVALID, "not a VTM file");  // import.rs:25-27
+    const u32 version = (u32(r.byte()) << 8) | r.byte();
+    if (version != 0x0100) return fail(VX_E_INVALID, "unsupported VTM version");              // :29-30
+    const u32 flags = (u32(r.byte()) << 8) | r.byte();
+    if (flags & ~1u) return fail(VX_E_INVALID, "unknown VTM flags");                          // :33 Flags::from_bits
+    vx_vtm_info local{};
+    local.flags = uint16_t(flags);
+    local.max_depth = r.byte();
+    const u32 fbits = r.be();
+    memcpy(&local.chunk_world_size, &fbits, 4);
+    r.be(), r.be();  // reserved
+    for (int k = 0; k < 3; ++k) local.world_bounds[k] = int32_t(r.be());
+    const u8 name_len = r.byte();
+    for (u32 k = 0; k < name_len; ++k) local.name[k] = char(r.byte());
+    local.name[name_len] = 0;
+    u8 digest[16], check[16];
+    for (int k = 0; k < 16; ++k) digest[k] = r.byte();
+    const u32 size = r.be();
+    if (!r.ok || size_t(r.end - r.p) < size) return fail(VX_E_INVALID, "truncated VTM file");
+    std::vector<u8> plain;
+    const u8* payload = r.p;
+    size_t payload_len = size;
+    if (flags & 1u) {
+        int rc = zstd_decompress(r.p, size, plain);
+        if (rc != VX_OK) return rc;
+        payload = plain.data();
+        payload_len = plain.size();
+    }
+    md5_digest(payload, payload_len, check);
+    if (memcmp(digest, check, 16) != 0) return fail(VX_E_INVALID, "VTM payload does not match its MD5");  // :87
+    if (info) *info = local;
+    return vx_model_deserialize(it, payload, payload_len, positions_out, roots_out, cap);
 }
 
 }  // extern "C"

@@ -117,4 +117,49 @@ __global__ void vtm_roots_kernel(const u32* newid, const u64* roots, u32 n, u32*
     if (i < n) out[i] = roots[i] == 0 ? 0u : newid[id_index(roots[i])];
 }
 
+// ---- import: VoxModel::deserialize (world/voxmodel.rs:296-408) into a FRESH interner.  The reference gives
+// node k of the file pool index k (interner/mod.rs:933,948 assert it), so the host parses the records into
+// pool-shaped arrays — children rows as BlockIds, values, in-degree refcounts — copies them in place, and
+// this kernel does what deserialize_leaf / deserialize_branch do besides storing: hash and enter every node
+// into the tables (mod.rs:941-1000).  One thread per node.
+template <class T>
+__global__ void vtm_install_kernel(InternerDev in, u32 n_leaves, u32 n_nodes) {
+    const u32 idx = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx > n_nodes) return;
+    if (idx <= n_leaves) {
+        const u32 v = sizeof(T) == 1 ? u32(reinterpret_cast<const u8*>(in.values)[idx]) : reinterpret_cast<const u32*>(in.values)[idx];
+        in.hashes[idx] = leaf_hash(v);
+        const u64 id = id_leaf(idx);
+        if (sizeof(T) == 1) {
+            in.leaf_u8[v] = id;
+        } else {
+            const u64 mykey = u64(v) | (1ull << 32);
+            u32 s = u32(leaf_hash(v)) & in.leaf_mask;
+            for (u32 guard = 0; guard <= in.leaf_mask; ++guard) {
+                const u64 old = atomicCAS((ull*)&in.leaf_keys[s], 0ull, (ull)mykey);
+                if (old == 0 || old == mykey) {
+                    in.leaf_ids[s] = id;
+                    return;
+                }
+                s = (s + 1) & in.leaf_mask;
+            }
+            set_error(in, ERR_TABLE_FULL);
+        }
+        return;
+    }
+    u64 h = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) h += child_hash(in.children[size_t(idx) * 8 + i], i);
+    h = finish_hash(h);
+    in.hashes[idx] = h;
+    const u64 slot = (u64(u32(h >> 47)) << 47) | idx;  // generation 0
+    u32 bucket = u32(h) & in.bucket_mask;
+    for (u32 guard = 0; guard <= in.bucket_mask; ++guard) {
+        for (int k = 0; k < 8; ++k)
+            if (atomicCAS((ull*)&in.slots[size_t(bucket) * 8 + k], 0ull, (ull)slot) == 0) return;
+        bucket = (bucket + 1) & in.bucket_mask;
+    }
+    set_error(in, ERR_TABLE_FULL);
+}
+
 }  // namespace vx
