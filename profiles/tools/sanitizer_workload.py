@@ -17,3 +17,24 @@ b.masks[:] = masks[21]; b.values[:] = values[21]; t.apply_batch(it, b); t.clear(
 m2, v2 = wl.batch_from_function(6, wl.p_random(4), wl.I32, 1)
 it2 = vx.VoxInterner.with_memory_budget(64 << 20, vx.I32); it2.apply_batches_slab(6, m2, v2)
 print("sanitizer workload done", it.stats()["alive_nodes"], it2.stats()["alive_nodes"])
+# host batch handles: staging kernels (occupancy-bitmap and mask variants), listed plan kernel, slices
+trees = [vx.VoxTree(5) for _ in range(24)]
+batches = [t.create_batch() for t in trees]
+for i, b in enumerate(batches):
+    if i % 3 == 0:
+        b.masks[:] = masks[i % len(masks)]; b.values[:] = values[i % len(values)]; b.mark_patched()
+    elif i % 3 == 1:
+        b.assign(masks[i % len(masks)], values[i % len(values)])
+    else:
+        b.set_many(np.random.default_rng(i).integers(0, 32, (300, 3)), np.random.default_rng(i).integers(0, 4, 300))
+it3 = vx.VoxInterner.with_memory_budget(64 << 20)
+vx.apply_batches(it3, trees[1::3] + trees[2::3], batches[1::3] + batches[2::3])      # API-only batches: occ kernel
+vx.apply_batches(it3, trees[0::3], batches[0::3])                                    # raw batches: masks kernel
+# VTM export / import
+r3 = np.array([t.get_root_id() for t in trees], np.uint64)
+pos = np.zeros((len(trees), 3), np.int32)
+payload = it3.model_serialize(pos, r3)
+it4 = vx.VoxInterner.with_memory_budget(64 << 20)
+_, r4 = it4.model_deserialize(payload)
+assert np.array_equal(it4.roots_to_vec(r4[:2], 5), it3.roots_to_vec(r3[:2], 5))
+print("sanitizer workload (handles + VTM) done", it3.stats()["alive_nodes"], len(payload))

@@ -2065,7 +2065,9 @@ void host_varint(std::vector<u8>& o, u64 v) {
     o.push_back(u8(v));
 }
 
-int model_serialize_impl(vx_interner* it, size_t n, const int32_t* positions, const vx_block_id* roots, std::vector<u8>& payload) {
+// size_only: *size_out = payload bytes, nothing is written or copied back.
+int model_serialize_impl(vx_interner* it, size_t n, const int32_t* positions, const vx_block_id* roots, std::vector<u8>& payload,
+                         bool size_only = false, size_t* size_out = nullptr) {
     std::lock_guard<std::mutex> lk(it->mu);
     DeviceGuard g(it->device);
     cudaStream_t s = it->stream;
@@ -2077,9 +2079,12 @@ int model_serialize_impl(vx_interner* it, size_t n, const int32_t* positions, co
     const size_t words = up(size_t(nn + 1) * 4);
     size_t scan_tmp = 0;
     CU_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, (const u32*)nullptr, (u32*)nullptr, int(nn + 1), s));
-    DevBuf work;
-    CU_TRY(cudaMalloc(&work.p, 7 * words + up(scan_tmp) + up(n * 8) + up(n * 4)));
-    u8* base = (u8*)work.p;
+    // work arrays + output live in the interner's scratch (grown once, kept): no allocation per export
+    const size_t work_bytes = 7 * words + up(scan_tmp) + up(n * 8) + up(n * 4);
+    const size_t out_max = up(8 + size_t(nn) * (5 + 1 + 8 * 5 + 4));  // every record at its longest
+    rc = ensure_scratch(it, work_bytes + out_max, 0);
+    if (rc != VX_OK) return rc;
+    u8* base = (u8*)it->scratch;
     VtmArgs a{};
     a.children = it->dev.children;
     a.values = it->dev.values;
@@ -2117,20 +2122,32 @@ int model_serialize_impl(vx_interner* it, size_t n, const int32_t* positions, co
     CU_TRY(cudaMemcpyAsync(&leaf_bytes, a.offs + n_leaves, 4, cudaMemcpyDeviceToHost, s));
     CU_TRY(cudaMemcpyAsync(&node_bytes, a.offs + n_leaves + n_branches, 4, cudaMemcpyDeviceToHost, s));
     CU_TRY(cudaStreamSynchronize(s));
-    DevBuf out;
-    CU_TRY(cudaMalloc(&out.p, size_t(node_bytes) + 8));
-    a.out = (u8*)out.p;
+    std::vector<u32> root_ids(n);
+    if (size_only) {  // the chunk table's size needs the roots' new ids (varints)
+        if (n) {
+            CU_TRY(cudaMemcpyAsync(d_roots, roots, n * 8, cudaMemcpyHostToDevice, s));
+            vtm_roots_kernel<<<unsigned((n + 255) / 256), 256, 0, s>>>(a.newid, d_roots, u32(n), d_root_ids);
+            CU_TRY(cudaGetLastError());
+            CU_TRY(cudaMemcpyAsync(root_ids.data(), d_root_ids, n * 4, cudaMemcpyDeviceToHost, s));
+            CU_TRY(cudaStreamSynchronize(s));
+        }
+        size_t total = size_t(node_bytes) + 8 + 4;
+        for (size_t c = 0; c < n; ++c) total += 24 + (root_ids[c] < (1u << 7) ? 1 : root_ids[c] < (1u << 14) ? 2 : root_ids[c] < (1u << 21) ? 3 : root_ids[c] < (1u << 28) ? 4 : 5);
+        *size_out = total;
+        return VX_OK;
+    }
+    a.out = base + work_bytes;
     vtm_write_kernel<<<grid, 256, 0, s>>>(a);
     CU_TRY(cudaGetLastError());
-    std::vector<u32> root_ids(n);
     if (n) {
         CU_TRY(cudaMemcpyAsync(d_roots, roots, n * 8, cudaMemcpyHostToDevice, s));
         vtm_roots_kernel<<<unsigned((n + 255) / 256), 256, 0, s>>>(a.newid, d_roots, u32(n), d_root_ids);
         CU_TRY(cudaGetLastError());
         CU_TRY(cudaMemcpyAsync(root_ids.data(), d_root_ids, n * 4, cudaMemcpyDeviceToHost, s));
     }
+    payload.reserve(size_t(node_bytes) + 12 + n * 29);
     payload.assign(size_t(node_bytes) + 8, 0);
-    CU_TRY(cudaMemcpyAsync(payload.data(), out.p, payload.size(), cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(payload.data(), a.out, payload.size(), cudaMemcpyDeviceToHost, s));
     CU_TRY(cudaStreamSynchronize(s));
     auto poke_be32 = [&](size_t at, u32 v) {
         for (int k = 0; k < 4; ++k) payload[at + k] = u8(v >> (24 - 8 * k));
@@ -2327,9 +2344,14 @@ int64_t vx_model_serialize(const vx_interner* cit, size_t n, const int32_t* posi
     if (!it || (n && (!positions || !roots))) return fail(VX_E_INVALID, "null argument");
     if (n > 0xFFFFFFFFull) return fail(VX_E_INVALID, "too many chunks");
     std::vector<u8> payload;
+    if (!out) {  // size query
+        size_t total = 0;
+        int rc = model_serialize_impl(it, n, positions, roots, payload, true, &total);
+        return rc != VX_OK ? rc : int64_t(total);
+    }
     int rc = model_serialize_impl(it, n, positions, roots, payload);
     if (rc != VX_OK) return rc;
-    if (out && payload.size() <= cap) memcpy(out, payload.data(), payload.size());
+    if (payload.size() <= cap) memcpy(out, payload.data(), payload.size());
     return int64_t(payload.size());
 }
 
