@@ -237,10 +237,8 @@ def main():
         budget = 2 << 30
     n = masks.shape[0]
     log(f"{n} chunks generated; uploading")
-    h_masks = torch.from_numpy(masks).pin_memory()
-    h_values = torch.from_numpy(values).pin_memory()
-    d_masks = h_masks.to(dev)
-    d_values = h_values.to(dev)
+    d_masks = torch.from_numpy(masks).to(dev)
+    d_values = torch.from_numpy(values).to(dev)
     d_roots = torch.zeros(n, dtype=torch.int64, device=dev)
     d_changed = torch.zeros(n, dtype=torch.uint8, device=dev)
     it = vx.VoxInterner.with_memory_budget(budget, vx.U8, local_rank)
@@ -366,6 +364,9 @@ def main():
         log(f"end-to-end phases: {e2e_trace}")
         # (2) the same world as two dense host arrays with no per-batch summary (vx_apply_batches_slab):
         # every mask byte has to cross the bus
+        del cs, trees, batches                      # their pinned arena slots go back to the pool first
+        h_masks = torch.from_numpy(masks).pin_memory()
+        h_values = torch.from_numpy(values).pin_memory()
         roots_host = np.zeros(n, np.uint64)
         changed_host = np.zeros(n, np.uint8)
         for _ in range(2):
@@ -387,7 +388,7 @@ def main():
                     "path": "vx_apply_batches_slab on two dense pinned arrays (masks H2D by copy engine in slabs, "
                             "values zero-copy for blocks with a set bit)"}
         log(f"end-to-end (dense slab): {slab_ms:.3f} ms/step")
-        del cs, trees, batches
+        del h_masks, h_values
 
     # ---------------------------------------------------------------- roofline of the apply kernel
     peak, peak_src = peaks()
