@@ -206,6 +206,23 @@ int vx_roots_to_vec(const vx_interner*, uint8_t max_depth, size_t n, const vx_bl
 int vx_roots_to_vec_lod(const vx_interner*, uint8_t max_depth, uint8_t lod, size_t n, const vx_block_id* roots,
                         void* dense);
 
+/* generate_occupancy_masks — utils/mesh.rs:515-596 (+ fill_masks_for_region :418-513 and the ordering of
+ * OccupancyDataBuilder::build :263-285): the greedy mesher's bit planes, computed from the device pools.
+ * n chunks (roots[n], host) are unfolded to max_depth - lod levels (saturating, <= 6: a builder covers 64^3 voxels,
+ * mesh.rs:50) and placed at offsets[n][3] (host; voxels at that level of detail, multiples of the chunk side — the
+ * `offset` argument of the reference) of builder builder_of[n] (host, NULL = all in builder 0); each call of the
+ * reference with the same builder = one entry with the same builder index.  Outputs, all host or all device:
+ *   global[nb][3*4096]           YZ word[y*64+z] bit x | XZ 4096 + word[z*64+x] bit y | XY 8192 + word[y*64+x] bit z
+ *   active[nb][6]                global_active (mesh.rs:451-461)
+ *   n_materials[nb], material_ids[nb][max_materials], material_counts[nb][max_materials]
+ *                                `materials` sorted by id (id = value as usize, core/voxel.rs:85-87), voxel counts
+ *   per_material[nb][max_materials][3*4096]   only the first n_materials[b] planes of builder b are written
+ * VX_E_BOUNDS when a builder holds more than max_materials (<= 1024) materials; n_materials[] is valid then. */
+int vx_occupancy_masks(const vx_interner*, uint8_t max_depth, uint8_t lod, size_t n, const vx_block_id* roots,
+                       const uint32_t* offsets, const uint32_t* builder_of, size_t n_builders, uint32_t max_materials,
+                       uint64_t* global, uint64_t* active, uint32_t* n_materials, uint64_t* material_ids,
+                       uint64_t* material_counts, uint64_t* per_material);
+
 /* VoxTree::fill / clear — voxtree.rs:264-292. */
 int vx_tree_fill(vx_interner*, vx_tree*, int64_t value);
 int vx_tree_clear(vx_interner*, vx_tree*);

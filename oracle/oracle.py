@@ -81,6 +81,8 @@ def lib():
     L.orc_tree_to_vec.argtypes = [vp, vp, vp]
     L.orc_root_to_vec.argtypes = [vp, C.c_uint64, C.c_int, vp]
     L.orc_root_to_vec_lod.argtypes = [vp, C.c_uint64, C.c_int, C.c_int, vp]
+    L.orc_occupancy_masks.restype = C.c_longlong
+    L.orc_occupancy_masks.argtypes = [vp, C.c_size_t, vp, C.c_int, vp, vp, vp, C.c_size_t, vp, vp, vp]
     L.orc_interner_ref.restype = C.c_uint32
     L.orc_interner_ref.argtypes = [vp, C.c_uint64]
     L.orc_interner_next_index.restype = C.c_uint32
@@ -225,6 +227,22 @@ class VoxInterner:
         out = np.zeros((n, n, n), _NP[self.dtype])  # [y][z][x]
         _check(lib().orc_root_to_vec_lod(self.h, int(root), depth, lod, _ptr(out)))
         return out
+
+    def occupancy_masks(self, roots, depth: int, offsets, lod: int = 0, max_materials: int = 256):
+        """generate_occupancy_masks (utils/mesh.rs:515-596) of every root into one OccupancyDataBuilder + build()
+        (:263-285) -> dict(global[3*4096], active[6], materials[(id, count)], per_material[m][3*4096])."""
+        roots = np.ascontiguousarray(roots, np.uint64)
+        offsets = np.ascontiguousarray(offsets, np.uint32).reshape(len(roots), 3)
+        glob = np.zeros(3 * 4096, np.uint64)
+        active = np.zeros(6, np.uint64)
+        ids = np.zeros(max_materials, np.uint64)
+        counts = np.zeros(max_materials, np.uint64)
+        pm = np.zeros((max_materials, 3 * 4096), np.uint64)
+        n = _check(lib().orc_occupancy_masks(self.h, len(roots), _ptr(roots), max(depth - lod, 0), _ptr(offsets),
+                                             _ptr(glob), _ptr(active), max_materials, _ptr(ids), _ptr(counts),
+                                             _ptr(pm)))
+        return {"global": glob, "active": active, "material_ids": ids[:n].copy(), "material_counts": counts[:n].copy(),
+                "per_material": pm[:n].copy()}
 
 
 class Batch:

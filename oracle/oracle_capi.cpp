@@ -219,6 +219,38 @@ int orc_root_to_vec_lod(void* ih, uint64_t root, int depth, int lod, void* dense
     });
 }
 
+// generate_occupancy_masks (utils/mesh.rs:515-596) of n roots into ONE OccupancyDataBuilder, then build()'s
+// ordering (:263-285).  `depth` = the depth unfolded (MaxDepth::for_lod); offsets[n][3] in voxels of that depth.
+// Returns the number of materials; ids / counts / per_material (max_mat x 12288 words) are filled in id order.
+long long orc_occupancy_masks(void* ih, size_t n, const uint64_t* roots, int depth, const uint32_t* offsets,
+                              uint64_t* global, uint64_t* active, size_t max_mat, uint64_t* mat_ids,
+                              uint64_t* mat_counts, uint64_t* per_material) {
+    AnyInterner* a = (AnyInterner*)ih;
+    long long out = 0;
+    int rc = guarded([&] {
+        OccupancyBuilder b;
+        for (size_t i = 0; i < n; ++i) {
+            const uint32_t* o = offsets + 3 * i;
+            if (a->dtype == 0)
+                generate_occupancy_masks(*a->i8, b, roots[i], depth, o[0], o[1], o[2]);
+            else
+                generate_occupancy_masks(*a->i32, b, roots[i], depth, o[0], o[1], o[2]);
+        }
+        b.sort_materials();
+        if (b.materials.size() > max_mat) throw std::runtime_error("more materials than max_mat");
+        memcpy(global, b.global.data(), OCC_ALL * 8);
+        memcpy(active, b.global_active, 48);
+        for (size_t m = 0; m < b.materials.size(); ++m) {
+            mat_ids[m] = b.materials[m].first;
+            mat_counts[m] = b.materials[m].second;
+            memcpy(per_material + m * OCC_ALL, b.per_material[m].second.data(), OCC_ALL * 8);
+        }
+        out = (long long)b.materials.size();
+        return 0;
+    });
+    return rc < 0 ? rc : out;
+}
+
 uint32_t orc_interner_ref(void* ih, uint64_t id) {
     AnyInterner* a = (AnyInterner*)ih;
     return a->dtype == 0 ? a->i8->get_ref(id) : a->i32->get_ref(id);

@@ -1000,5 +1000,126 @@ void model_deserialize(Interner<T>& in, const u8* data, size_t len, std::vector<
     }
 }
 
-}  // namespace vxo
+// ---------------------------------------------------------------------------------
+// Occupancy masks — the greedy mesher's input.  OccupancyDataBuilder (utils/mesh.rs:181-193,
+// :247-285), fill_masks_for_region (:418-513), generate_occupancy_masks (:515-596).
+// Planes (mesh.rs:50-67): MAX_VOXELS_PER_AXIS = 64, PLANE_SIZE = 64*64,
+//   YZ at 0          word[y*64 + z], bit x
+//   XZ at PLANE_SIZE word[z*64 + x], bit y
+//   XY at 2*PLANE    word[y*64 + x], bit z
+// `external` / `external_exists` belong to generate_external_occupancy_mask (:318-416), not restated.
+// ---------------------------------------------------------------------------------
+constexpr size_t OCC_AXIS = 64;                       // mesh.rs:50
+constexpr size_t OCC_PLANE = OCC_AXIS * OCC_AXIS;     // :51
+constexpr size_t OCC_ALL = OCC_PLANE * 3;             // :52
+constexpr size_t OCC_YZ = 0, OCC_XZ = OCC_PLANE, OCC_XY = OCC_PLANE * 2;  // :65-67
 
+struct OccupancyBuilder {  // mesh.rs:181-193, Default :247-261
+    std::vector<u64> global = std::vector<u64>(OCC_ALL, 0);
+    u64 global_active[6] = {0, 0, 0, 0, 0, 0};
+    std::vector<std::pair<u64, std::vector<u64>>> per_material;  // HashMap<usize, Vec<u64>>
+    std::vector<std::pair<u64, u64>> materials;                  // HashMap<usize, usize> (id -> voxel count)
+
+    std::vector<u64>* find_masks(u64 id) {
+        for (auto& e : per_material)
+            if (e.first == id) return &e.second;
+        return nullptr;
+    }
+    // build(): materials sorted by id, per_material in the same order — mesh.rs:263-285
+    void sort_materials() {
+        std::sort(materials.begin(), materials.end());
+        std::sort(per_material.begin(), per_material.end(),
+                  [](const auto& a, const auto& b) { return a.first < b.first; });
+    }
+};
+
+// fill_masks_for_region — mesh.rs:418-513
+inline void fill_masks_for_region(OccupancyBuilder& b, u32 ox, u32 oy, u32 oz, u32 side_u, u64 material_id) {
+    const size_t side = side_u;
+    const u64 volume = u64(side) * side * side;
+    bool seen = false;  // :428-432
+    for (auto& m : b.materials)
+        if (m.first == material_id) {
+            m.second += volume;
+            seen = true;
+        }
+    if (!seen) b.materials.push_back({material_id, volume});
+    if (side != OCC_AXIS) {  // :434
+        std::vector<u64>* pm = b.find_masks(material_id);  // :435-438
+        if (!pm) {
+            b.per_material.push_back({material_id, std::vector<u64>(OCC_ALL, 0)});
+            pm = &b.per_material.back().second;
+        }
+        if (ox + side > OCC_AXIS || oy + side > OCC_AXIS || oz + side > OCC_AXIS)
+            throw RefPanic("region outside the 64^3 occupancy volume");  // Rust: shift overflow / index panic
+        const u64 run = (u64(1) << side) - 1;  // :440
+        const u64 x_mask = run << ox, y_mask = run << oy, z_mask = run << oz;
+        b.global_active[0] |= y_mask;  // :451-461
+        b.global_active[1] |= z_mask;
+        b.global_active[2] |= z_mask;
+        b.global_active[3] |= x_mask;
+        b.global_active[4] |= y_mask;
+        b.global_active[5] |= x_mask;
+        for (size_t i = 0; i < side; ++i) {  // :463-486
+            const size_t z = oz + i, y = oy + i;
+            const size_t base_y = OCC_XZ + z * OCC_AXIS + ox;
+            const size_t base_z = OCC_XY + y * OCC_AXIS + ox;
+            const size_t base_x = OCC_YZ + y * OCC_AXIS + oz;
+            for (size_t j = 0; j < side; ++j) {
+                b.global[base_y + j] |= y_mask;
+                (*pm)[base_y + j] |= y_mask;
+                b.global[base_z + j] |= z_mask;
+                (*pm)[base_z + j] |= z_mask;
+                b.global[base_x + j] |= x_mask;
+                (*pm)[base_x + j] |= x_mask;
+            }
+        }
+    } else {  // :487-512 — one region covers the whole volume
+        std::vector<u64>* pm = b.find_masks(material_id);
+        if (pm)
+            std::fill(pm->begin(), pm->end(), ~u64(0));
+        else
+            b.per_material.push_back({material_id, std::vector<u64>(OCC_ALL, ~u64(0))});
+        std::fill(b.global.begin(), b.global.end(), ~u64(0));
+        for (int k = 0; k < 6; ++k) b.global_active[k] = ~u64(0);
+    }
+}
+
+// generate_occupancy_masks — mesh.rs:515-596.  `max_depth` is the depth the caller unfolds to
+// (MaxDepth::for_lod at the call sites, world/voxchunk.rs); material_id = value as usize (core/voxel.rs:85-87).
+template <class T>
+void generate_occupancy_masks(const Interner<T>& in, OccupancyBuilder& b, u64 root_id, int max_depth, u32 offx,
+                              u32 offy, u32 offz) {
+    if (id_is_empty(root_id)) return;  // :530-537
+    auto mat = [](T v) { return u64(int64_t(v)); };  // `*self as usize`: sign-extending for signed T
+    if (!id_is_branch(root_id)) {  // :543-556
+        T v = in.get_value(root_id);
+        if (v != T(0)) fill_masks_for_region(b, offx, offy, offz, u32(1) << max_depth, mat(v));
+        return;
+    }
+    struct Item {
+        u64 id;
+        u32 x, y, z, depth;
+    };
+    std::vector<Item> stack;  // :558-559
+    stack.push_back({root_id, 0, 0, 0, 0});
+    while (!stack.empty()) {
+        Item it = stack.back();
+        stack.pop_back();
+        if (id_is_branch(it.id) && it.depth < u32(max_depth)) {  // :562-579
+            const u32 half = u32(1) << (max_depth - it.depth - 1);
+            const u64* ch = in.children[id_index(it.id)];
+            for (int i = 7; i >= 0; --i)
+                if (!id_is_empty(ch[i]))
+                    stack.push_back({ch[i], it.x + (u32(i) & 1) * half, it.y + ((u32(i) & 2) >> 1) * half,
+                                     it.z + ((u32(i) & 4) >> 2) * half, it.depth + 1});
+        } else {  // :580-589
+            T v = in.get_value(it.id);
+            if (v != T(0))
+                fill_masks_for_region(b, offx + it.x, offy + it.y, offz + it.z, u32(1) << (max_depth - it.depth),
+                                      mat(v));
+        }
+    }
+}
+
+}  // namespace vxo

@@ -46,7 +46,7 @@ ABI_SYMBOLS = [
     "vx_tree_voxels_per_axis", "vx_tree_is_empty", "vx_tree_is_leaf", "vx_tree_is_dirty",
     "vx_tree_mark_dirty", "vx_tree_clear_dirty", "vx_tree_apply_batch", "vx_apply_batches",
     "vx_apply_batches_slab", "vx_apply_batches_device", "vx_tree_get", "vx_tree_get_many",
-    "vx_tree_to_vec", "vx_roots_to_vec", "vx_roots_to_vec_lod", "vx_tree_fill", "vx_tree_clear",
+    "vx_tree_to_vec", "vx_roots_to_vec", "vx_roots_to_vec_lod", "vx_occupancy_masks", "vx_tree_fill", "vx_tree_clear",
     "vx_dedup_heights", "vx_dedup_pack", "vx_dedup_scatter", "vx_dedup_map_roots", "vx_interner_intern_records",
 ]
 
@@ -148,6 +148,7 @@ def lib():
     L.vx_tree_to_vec.argtypes = [vp, vp, vp]
     L.vx_roots_to_vec.argtypes = [vp, C.c_uint8, sz, vp, vp]
     L.vx_roots_to_vec_lod.argtypes = [vp, C.c_uint8, C.c_uint8, sz, vp, vp]
+    L.vx_occupancy_masks.argtypes = [vp, C.c_uint8, C.c_uint8, sz, vp, vp, vp, sz, C.c_uint32, vp, vp, vp, vp, vp, vp]
     L.vx_tree_fill.argtypes = [vp, vp, i64]
     L.vx_tree_clear.argtypes = [vp, vp]
     L.vx_model_serialize.restype = i64
@@ -364,6 +365,25 @@ class VoxInterner:
         n = 1 << max(depth - lod, 0)
         out = np.zeros((len(roots), n, n, n), _NP[self.dtype])  # [r][y][z][x]
         _ck(lib().vx_roots_to_vec_lod(self.h, depth, lod, len(roots), _ptr(roots), _ptr(out)))
+        return out
+
+    def occupancy_masks(self, roots, depth: int, offsets, builder_of=None, n_builders: int = 1, lod: int = 0,
+                        max_materials: int = 8):
+        """generate_occupancy_masks (reference voxelis/src/utils/mesh.rs:515-596) of every root, chunk i into
+        builder ``builder_of[i]`` at ``offsets[i]`` -> dict of host arrays: global[nb][3*4096], active[nb][6],
+        n_materials[nb], material_ids / material_counts[nb][max_materials], per_material[nb][max_materials][3*4096]
+        (rows past n_materials[b] are left zero)."""
+        roots = np.ascontiguousarray(roots, np.uint64)
+        offsets = np.ascontiguousarray(offsets, np.uint32).reshape(len(roots), 3)
+        bo = None if builder_of is None else np.ascontiguousarray(builder_of, np.uint32)
+        nb, M = n_builders, max_materials
+        out = {"global": np.zeros((nb, 3 * 4096), np.uint64), "active": np.zeros((nb, 6), np.uint64),
+               "n_materials": np.zeros(nb, np.uint32), "material_ids": np.zeros((nb, M), np.uint64),
+               "material_counts": np.zeros((nb, M), np.uint64), "per_material": np.zeros((nb, M, 3 * 4096), np.uint64)}
+        _ck(lib().vx_occupancy_masks(self.h, depth, lod, len(roots), _ptr(roots), _ptr(offsets),
+                                     None if bo is None else _ptr(bo), nb, M, _ptr(out["global"]), _ptr(out["active"]),
+                                     _ptr(out["n_materials"]), _ptr(out["material_ids"]), _ptr(out["material_counts"]),
+                                     _ptr(out["per_material"])))
         return out
 
 

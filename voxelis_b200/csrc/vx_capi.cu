@@ -25,6 +25,7 @@
 #include "vx_dedup.cuh"
 #include "vx_stage.cuh"
 #include "vx_vtm.cuh"
+#include "vx_occupancy.cuh"
 
 #include <cub/device/device_scan.cuh>
 #include <dlfcn.h>
@@ -1807,6 +1808,107 @@ int vx_roots_to_vec_lod(const vx_interner* cit, uint8_t max_depth, uint8_t lod, 
     CU_TRY(cudaGetLastError());
     if (!dev_dense) CU_TRY(cudaMemcpyAsync(dense, d_dense, total * esz, cudaMemcpyDeviceToHost, s));
     CU_TRY(cudaStreamSynchronize(s));
+    return VX_OK;
+}
+
+// generate_occupancy_masks — utils/mesh.rs:515-596 for n chunks spread over n_builders OccupancyDataBuilders.
+int vx_occupancy_masks(const vx_interner* cit, uint8_t max_depth, uint8_t lod, size_t n, const vx_block_id* roots,
+                       const uint32_t* offsets, const uint32_t* builder_of, size_t n_builders, uint32_t max_materials,
+                       uint64_t* global, uint64_t* active, uint32_t* n_materials, uint64_t* material_ids,
+                       uint64_t* material_counts, uint64_t* per_material) {
+    vx_interner* it = const_cast<vx_interner*>(cit);
+    if (!it || (n && (!roots || !offsets)) || !global || !active || !n_materials || !material_ids ||
+        !material_counts || (max_materials && !per_material))
+        return fail(VX_E_INVALID, "null argument");
+    if (!valid_depth(max_depth)) return fail(VX_E_INVALID, "max_depth must be in [2,7]");
+    const int ld = max_depth > lod ? int(max_depth) - int(lod) : 0;  // MaxDepth::for_lod saturates
+    if (ld > 6) return fail(VX_E_UNSUPPORTED, "an occupancy volume is 64 voxels per axis (utils/mesh.rs:50): depth - lod <= 6");
+    if (n_builders == 0) return n ? fail(VX_E_INVALID, "chunks but no builder") : VX_OK;
+    if (max_materials > 1024) return fail(VX_E_INVALID, "max_materials <= 1024");
+    const bool dev_out = is_device_ptr(global);
+    if (dev_out != is_device_ptr(active) || dev_out != is_device_ptr(n_materials) ||
+        dev_out != is_device_ptr(material_ids) || dev_out != is_device_ptr(material_counts) ||
+        (max_materials && dev_out != is_device_ptr(per_material)))
+        return fail(VX_E_INVALID, "all outputs must live in the same memory space");
+    const size_t S = size_t(1) << ld, G = 64 >> ld, cells_per = G * G * G, ncell = n_builders * cells_per;
+    // host: place every chunk in its builder's cell grid (offsets are multiples of the chunk side, one chunk per cell)
+    std::vector<u64> cells(ncell, 0);
+    std::vector<u8> taken(ncell, 0);
+    for (size_t i = 0; i < n; ++i) {
+        const size_t b = builder_of ? builder_of[i] : 0;
+        const uint32_t* o = offsets + 3 * i;
+        if (b >= n_builders) return fail(VX_E_INVALID, "builder index out of range");
+        if (o[0] % S || o[1] % S || o[2] % S || o[0] + S > 64 || o[1] + S > 64 || o[2] + S > 64)
+            return fail(VX_E_BOUNDS, "chunk offset must be a multiple of the chunk side inside the 64^3 volume");
+        if (roots[i] == VX_BLOCK_INVALID || id_index(roots[i]) >= it->capacity)
+            return fail(VX_E_INVALID, "invalid block id");
+        const size_t c = b * cells_per + ((o[1] >> ld) * G + (o[2] >> ld)) * G + (o[0] >> ld);
+        if (taken[c]) return fail(VX_E_INVALID, "two chunks at the same offset of one builder");
+        taken[c] = 1;
+        cells[c] = roots[i];
+    }
+    std::lock_guard<std::mutex> lk(it->mu);
+    DeviceGuard g(it->device);
+    const size_t M = max_materials, plane_bytes = size_t(OCC_ALL) * 8;
+    auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+    size_t need = up(ncell * 8) + 256;
+    if (!dev_out)
+        need += up(n_builders * plane_bytes) + up(n_builders * 48) + up(n_builders * 4) + 2 * up(n_builders * M * 8) +
+                up(n_builders * M * plane_bytes);
+    int rc = ensure_scratch(it, need, 0);
+    if (rc != VX_OK) return rc;
+    cudaStream_t s = it->stream;
+    u8* p = (u8*)it->scratch;
+    auto take = [&](size_t bytes) { u8* r = p; p += up(bytes); return r; };
+    u32* d_err = (u32*)take(256);
+    u64* d_cells = (u64*)take(ncell * 8);
+    u64 *d_global = global, *d_active = active, *d_ids = material_ids, *d_counts = material_counts, *d_pm = per_material;
+    u32* d_nmat = n_materials;
+    if (!dev_out) {
+        d_global = (u64*)take(n_builders * plane_bytes);
+        d_active = (u64*)take(n_builders * 48);
+        d_nmat = (u32*)take(n_builders * 4);
+        d_ids = (u64*)take(n_builders * M * 8);
+        d_counts = (u64*)take(n_builders * M * 8);
+        d_pm = (u64*)take(n_builders * M * plane_bytes);
+    }
+    CU_TRY(cudaMemsetAsync(d_err, 0, 4, s));
+    CU_TRY(cudaMemcpyAsync(d_cells, cells.data(), ncell * 8, cudaMemcpyHostToDevice, s));
+    const dim3 grid_masks(OCC_ALL / 256, unsigned(n_builders));
+    if (it->dtype == VX_U8) {
+        occ_materials_kernel<u8><<<unsigned(n_builders), 256, 0, s>>>(it->dev.children, (const u8*)it->dev.values,
+                                                                       d_cells, ld, max_materials, d_nmat, d_ids,
+                                                                       d_counts, d_active, d_err);
+        occ_masks_kernel<u8><<<grid_masks, 256, 0, s>>>(it->dev.children, (const u8*)it->dev.values, d_cells, ld,
+                                                         max_materials, d_nmat, d_ids, d_global, d_active, d_pm);
+    } else {
+        occ_materials_kernel<int32_t><<<unsigned(n_builders), 256, 0, s>>>(
+            it->dev.children, (const int32_t*)it->dev.values, d_cells, ld, max_materials, d_nmat, d_ids, d_counts,
+            d_active, d_err);
+        occ_masks_kernel<int32_t><<<grid_masks, 256, 0, s>>>(it->dev.children, (const int32_t*)it->dev.values,
+                                                              d_cells, ld, max_materials, d_nmat, d_ids, d_global,
+                                                              d_active, d_pm);
+    }
+    CU_TRY(cudaGetLastError());
+    u32 err = 0;
+    CU_TRY(cudaMemcpyAsync(&err, d_err, 4, cudaMemcpyDeviceToHost, s));
+    if (!dev_out) {
+        CU_TRY(cudaMemcpyAsync(n_materials, d_nmat, n_builders * 4, cudaMemcpyDeviceToHost, s));
+        CU_TRY(cudaMemcpyAsync(global, d_global, n_builders * plane_bytes, cudaMemcpyDeviceToHost, s));
+        CU_TRY(cudaMemcpyAsync(active, d_active, n_builders * 48, cudaMemcpyDeviceToHost, s));
+        CU_TRY(cudaMemcpyAsync(material_ids, d_ids, n_builders * M * 8, cudaMemcpyDeviceToHost, s));
+        CU_TRY(cudaMemcpyAsync(material_counts, d_counts, n_builders * M * 8, cudaMemcpyDeviceToHost, s));
+    }
+    CU_TRY(cudaStreamSynchronize(s));
+    if (err == OCC_ERR_MATERIALS)
+        return fail(VX_E_BOUNDS, "a builder holds more materials than max_materials (n_materials[] has the counts)");
+    if (!dev_out) {  // only the planes of materials that exist travel back
+        for (size_t b = 0; b < n_builders; ++b)
+            if (n_materials[b])
+                CU_TRY(cudaMemcpyAsync(per_material + b * M * OCC_ALL, d_pm + b * M * OCC_ALL,
+                                       size_t(n_materials[b]) * plane_bytes, cudaMemcpyDeviceToHost, s));
+        CU_TRY(cudaStreamSynchronize(s));
+    }
     return VX_OK;
 }
 

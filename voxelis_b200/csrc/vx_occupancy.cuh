@@ -1,0 +1,295 @@
+// vx_occupancy.cuh — the greedy mesher's input, straight from the device pools.
+//
+// Replaces  generate_occupancy_masks   utils/mesh.rs:515-596  (stack walk of one chunk's DAG)
+//           fill_masks_for_region      utils/mesh.rs:418-513  (OR a cube into 3 bit planes, global + per material)
+//           OccupancyDataBuilder::build utils/mesh.rs:263-285 (materials sorted by id, masks in that order)
+//
+// One OccupancyDataBuilder covers a 64^3 voxel volume (mesh.rs:50-67): three bit planes of 64x64 words,
+//   YZ  word[y*64 + z] bit x        XZ  4096 + word[z*64 + x] bit y        XY  8192 + word[y*64 + x] bit z
+// filled from up to (64/S)^3 chunks of side S = 2^depth placed at multiples of S.  The reference scatters:
+// every leaf region ORs S'^2 words in each plane.  Here the work is turned around so that no word is ever
+// touched by two threads: one thread OWNS one word of one builder and walks the DAG along the word's bit axis,
+// run by run (a node standing at depth k answers 2^(depth-k) bits at once, so collapsed subtrees cost one
+// step).  Results are OR / sum reductions, hence independent of the visiting order -> bit-identical to the
+// reference's scatter.  HBM traffic = the output planes written once (no memset, no atomics on them) + the
+// DAG nodes on the way (L1/L2 hits: neighbouring words share their paths).
+//
+//   occ_materials_kernel   one CTA per builder: voxel count per material (mesh.rs:428-432) from the YZ rows,
+//                          ids sorted ascending as build() does; also clears the builder's global_active
+//   occ_masks_kernel       48 CTAs per builder x 256 threads = 12288 words: global plane word, per-material
+//                          words (written once each, for every material of the builder), global_active by a
+//                          CTA-wide OR + one atomicOr per CTA
+#pragma once
+#include "vx_device.cuh"
+
+namespace vx {
+
+constexpr int OCC_AXIS = 64;
+constexpr int OCC_PLANE = OCC_AXIS * OCC_AXIS;
+constexpr int OCC_ALL = 3 * OCC_PLANE;
+constexpr u32 OCC_ERR_MATERIALS = 1;  // more materials in a builder than the caller made room for
+
+// material_id = `*self as usize` (core/voxel.rs:85-87): sign-extending for signed T
+template <class T>
+__host__ __device__ __forceinline__ u64 occ_material_of(T v) {
+    return u64((long long)v);
+}
+
+// Walk one line of 2^ld voxels of the tree `root` along axis `caxis` (0 = x, 1 = y, 2 = z); p / q are the
+// local coordinates on the two other axes, (pax, qax) their bit positions in a child index
+// (child = x | y<<1 | z<<2, utils/common.rs:104-111).  emit(value, bits) gets each non-default run, bits
+// relative to the start of the line.  A branch standing at depth ld answers with its LOD value, like
+// `node_id.is_branch() && depth < max_depth` in mesh.rs:562,580.
+#ifdef __CUDA_ARCH__
+#define VX_OCC_LD(p) __ldg(p)
+#define VX_OCC_FFS(c) __ffs(c)
+#else  // host instantiation: tests/cpp/occ_host_check.cu steps the same per-word code without a GPU
+#define VX_OCC_LD(p) (*(p))
+#define VX_OCC_FFS(c) __builtin_ffs(c)
+#endif
+
+template <class T, class F>
+__host__ __device__ __forceinline__ void occ_walk_line(const u64* __restrict__ children, const T* __restrict__ values,
+                                              u64 root, int ld, int caxis, int pax, int qax, int p, int q, F emit) {
+    if (root == 0) return;
+    u64 path[7];
+    path[0] = root;
+    const int S = 1 << ld;
+    int c = 0;
+    while (c < S) {
+        // deepest stored node that still contains voxel c: the previous run ended on a 2^ctz(c) boundary
+        int d = c ? ld - VX_OCC_FFS(c) : 0;
+        u64 node = path[d];
+        while (node != 0 && !id_is_leaf(node) && d < ld) {
+            const int sh = ld - 1 - d;
+            const int ci = (((c >> sh) & 1) << caxis) | (((p >> sh) & 1) << pax) | (((q >> sh) & 1) << qax);
+            node = VX_OCC_LD(&children[size_t(id_index(node)) * 8 + ci]);
+            ++d;
+            path[d] = node;
+        }
+        const int len = 1 << (ld - d);
+        if (node != 0) {
+            const T v = values[id_index(node)];
+            if (v != T(0)) emit(v, (len == 64 ? ~0ull : ((1ull << len) - 1)) << c);
+        }
+        c += len;
+    }
+}
+
+template <class T>
+struct OccTable {
+    static constexpr int SIZE = sizeof(T) == 1 ? 256 : 2048;  // u8: direct-mapped by value; wider T: hashed
+};
+
+// cells[b][(cy*G + cz)*G + cx] = root of the chunk placed at cell (cx, cy, cz) of builder b, 0 = none.
+template <class T>
+__global__ void __launch_bounds__(256)
+occ_materials_kernel(const u64* __restrict__ children, const T* __restrict__ values, const u64* __restrict__ cells,
+                     int ld, u32 max_materials, u32* __restrict__ n_materials, u64* __restrict__ material_ids,
+                     u64* __restrict__ material_counts, u64* __restrict__ active, u32* __restrict__ err) {
+    constexpr int TS = OccTable<T>::SIZE;
+    __shared__ u32 s_key[TS];   // raw value bits, 0 = free (the default value is never a material)
+    __shared__ u32 s_cnt[TS];
+    __shared__ u32 s_over;
+    const int b = blockIdx.x, G = OCC_AXIS >> ld, gsh = 6 - ld;
+    const u64* cell = cells + (size_t(b) << (3 * gsh));
+    for (int i = threadIdx.x; i < TS; i += blockDim.x) {
+        s_key[i] = 0;
+        s_cnt[i] = 0;
+    }
+    if (threadIdx.x == 0) s_over = 0;
+    if (threadIdx.x < 6) active[size_t(b) * 6 + threadIdx.x] = 0;
+    __syncthreads();
+
+    auto add = [&](T v, u64 bits) {
+        const u32 n = u32(__popcll(bits));
+        if (sizeof(T) == 1) {
+            const u32 k = u32(v) & 0xFFu;
+            s_key[k] = k;
+            atomicAdd(&s_cnt[k], n);
+        } else {
+            const u32 k = u32(v);
+            u32 h = u32(mix64(k)) & (TS - 1);
+            for (int probe = 0; probe < TS; ++probe) {
+                u32 cur = s_key[h];
+                if (cur == 0) {
+                    const u32 prev = atomicCAS(&s_key[h], 0u, k);
+                    cur = prev == 0 ? k : prev;
+                }
+                if (cur == k) {
+                    atomicAdd(&s_cnt[h], n);
+                    return;
+                }
+                h = (h + 1) & (TS - 1);
+            }
+            s_over = 1;
+        }
+    };
+    // YZ rows: y = r >> 6, z = r & 63, bits along x — every voxel of the volume is seen exactly once
+    for (int r = threadIdx.x; r < OCC_PLANE; r += blockDim.x) {
+        const int y = r >> 6, z = r & 63;
+        const int cy = y >> ld, cz = z >> ld, ly = y & ((1 << ld) - 1), lz = z & ((1 << ld) - 1);
+        for (int cx = 0; cx < G; ++cx) {
+            const u64 root = __ldg(&cell[(size_t(cy) * G + cz) * G + cx]);
+            occ_walk_line<T>(children, values, root, ld, 0, 1, 2, ly, lz, add);
+        }
+    }
+    __syncthreads();
+    // build(): sort by material id (as usize).  Rank of an entry = number of smaller ids present.
+    u32 mine = 0;
+    for (int i = threadIdx.x; i < TS; i += blockDim.x) mine += s_key[i] != 0;
+    __shared__ u32 s_total;
+    if (threadIdx.x == 0) s_total = 0;
+    __syncthreads();
+    if (mine) atomicAdd(&s_total, mine);
+    __syncthreads();
+    const u32 total = s_total;
+    if (threadIdx.x == 0) {
+        n_materials[b] = total;
+        if (total > max_materials || s_over) atomicExch(err, OCC_ERR_MATERIALS);
+    }
+    if (total > max_materials || s_over) return;
+    for (int i = threadIdx.x; i < TS; i += blockDim.x) {
+        const u32 k = s_key[i];
+        if (k == 0) continue;
+        const u64 id = occ_material_of<T>(T(k));
+        u32 rank = 0;
+        for (int j = 0; j < TS; ++j) {
+            const u32 o = s_key[j];
+            rank += (o != 0 && occ_material_of<T>(T(o)) < id);
+        }
+        material_ids[size_t(b) * max_materials + rank] = id;
+        material_counts[size_t(b) * max_materials + rank] = s_cnt[i];
+    }
+}
+
+// One word of one builder: walks the word's line through every cell along the bit axis, returns the global
+// plane word and writes the word's column of the per-material planes (pm + slot * OCC_ALL), each exactly once
+// when the line holds <= K materials.  slot_of(value) = index in the builder's sorted material list.
+template <class T, class SlotOf>
+__host__ __device__ __forceinline__ u64 occ_word(const u64* __restrict__ children, const T* __restrict__ values,
+                                                 const u64* __restrict__ cell, int ld, int w, int nmat, u64* pm,
+                                                 SlotOf slot_of) {
+    constexpr int K = 4;  // materials of one word kept in registers; more spill to read-modify-write
+    const int G = OCC_AXIS >> ld, S = 1 << ld;
+    const int plane = w >> 12, a = (w >> 6) & 63, bb = w & 63;
+    // plane 0 (YZ): a = y, bb = z, bits x | plane 1 (XZ): a = z, bb = x, bits y | plane 2 (XY): a = y, bb = x, bits z
+    const int caxis = plane == 0 ? 0 : plane == 1 ? 1 : 2;
+    const int pax = plane == 0 ? 1 : plane == 1 ? 2 : 1;   // axis of `a`
+    const int qax = plane == 0 ? 2 : 0;                    // axis of `bb`
+    const int ca = a >> ld, cb = bb >> ld, la = a & (S - 1), lb = bb & (S - 1);
+
+    u64 gmask = 0;
+    int ns = 0, sl[K];
+    u64 mk[K];
+    bool spilled = false;
+    int last_slot = -1;
+    T last_v = T(0);
+#pragma unroll
+    for (int i = 0; i < K; ++i) sl[i] = -1, mk[i] = 0;
+
+    for (int cc = 0; cc < G; ++cc) {
+        int cx, cy, cz;
+        if (plane == 0) cx = cc, cy = ca, cz = cb;
+        else if (plane == 1) cx = cb, cy = cc, cz = ca;
+        else cx = cb, cy = ca, cz = cc;
+        const u64 root = VX_OCC_LD(&cell[(size_t(cy) * G + cz) * G + cx]);
+        const int base = cc << ld;
+        occ_walk_line<T>(children, values, root, ld, caxis, pax, qax, la, lb, [&](T v, u64 bits) {
+            bits <<= base;
+            gmask |= bits;
+            if (v != last_v) {
+                last_v = v;
+                last_slot = slot_of(v);
+            }
+            const int slot = last_slot;
+            if (slot < 0 || slot >= nmat) return;  // only after OCC_ERR_MATERIALS
+            if (spilled) {
+                pm[size_t(slot) * OCC_ALL] |= bits;
+                return;
+            }
+            bool done = false;
+#pragma unroll
+            for (int i = 0; i < K; ++i)
+                if (!done && sl[i] == slot) mk[i] |= bits, done = true;
+            if (done) return;
+            if (ns < K) {
+#pragma unroll
+                for (int i = 0; i < K; ++i)
+                    if (i == ns) sl[i] = slot, mk[i] = bits;
+                ++ns;
+                return;
+            }
+            // a fifth material on this word: the word's column goes to memory and is OR-ed in place from now on
+            for (int s = 0; s < nmat; ++s) pm[size_t(s) * OCC_ALL] = 0;
+#pragma unroll
+            for (int i = 0; i < K; ++i) pm[size_t(sl[i]) * OCC_ALL] = mk[i];
+            pm[size_t(slot) * OCC_ALL] = bits;
+            spilled = true;
+        });
+    }
+    if (!spilled)
+        for (int s = 0; s < nmat; ++s) {
+            u64 m = 0;
+#pragma unroll
+            for (int i = 0; i < K; ++i)
+                if (sl[i] == s) m = mk[i];
+            pm[size_t(s) * OCC_ALL] = m;
+        }
+    return gmask;
+}
+
+// slot of a material id in a sorted id list
+__host__ __device__ __forceinline__ int occ_search(const u64* __restrict__ ids, int n, u64 id) {
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (VX_OCC_LD(&ids[mid]) < id) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+template <class T>
+__global__ void __launch_bounds__(256)
+occ_masks_kernel(const u64* __restrict__ children, const T* __restrict__ values, const u64* __restrict__ cells,
+                 int ld, u32 max_materials, const u32* __restrict__ n_materials,
+                 const u64* __restrict__ material_ids, u64* __restrict__ global, u64* __restrict__ active,
+                 u64* __restrict__ per_material) {
+    __shared__ u8 s_lut[256];
+    __shared__ u64 s_or[8];
+    const int b = blockIdx.y, gsh = 6 - ld;
+    const int nmat = int(min(n_materials[b], max_materials));
+    const u64* ids = material_ids + size_t(b) * max_materials;
+    if (sizeof(T) == 1) {
+        for (int i = threadIdx.x; i < nmat; i += blockDim.x) s_lut[u32(ids[i]) & 0xFFu] = u8(i);
+        __syncthreads();
+    }
+    const u64* cell = cells + (size_t(b) << (3 * gsh));
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;  // word of the builder, 0 .. 12287; one plane per CTA
+    const int plane = w >> 12;
+    u64* pm = per_material + (size_t(b) * max_materials) * OCC_ALL + w;  // + slot * OCC_ALL
+    const u64 gmask = occ_word<T>(children, values, cell, ld, w, nmat, pm, [&](T v) -> int {
+        if (sizeof(T) == 1) return int(s_lut[u32(v) & 0xFFu]);
+        return occ_search(ids, nmat, occ_material_of<T>(v));
+    });
+    global[size_t(b) * OCC_ALL + w] = gmask;
+    // global_active (mesh.rs:451-461): [0] y, [1] z, [2] z, [3] x, [4] y, [5] x = OR of the run masks, i.e. the OR of
+    // every word whose bits run along that axis
+    u64 o = gmask;
+#pragma unroll
+    for (int k = 16; k; k >>= 1) o |= __shfl_xor_sync(FULL, o, k);
+    if ((threadIdx.x & 31) == 0) s_or[threadIdx.x >> 5] = o;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u64 t = 0;
+        for (int i = 0; i < int(blockDim.x >> 5); ++i) t |= s_or[i];
+        if (t) {
+            const int i0 = plane == 0 ? 3 : plane == 1 ? 0 : 1;
+            const int i1 = plane == 0 ? 5 : plane == 1 ? 4 : 2;
+            atomicOr((ull*)&active[size_t(b) * 6 + i0], (ull)t);
+            atomicOr((ull*)&active[size_t(b) * 6 + i1], (ull)t);
+        }
+    }
+}
+
+}  // namespace vx
