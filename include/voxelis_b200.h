@@ -190,6 +190,21 @@ int vx_apply_batches_device(vx_interner*, uint8_t max_depth, size_t n, const uin
                             const void* d_values, const uint8_t* d_flags, const int64_t* d_fills,
                             vx_block_id* d_roots_out, uint8_t* d_changed_out, void* stream);
 
+/* Batch generation in device memory (the step before the path): generate_terrain_batch /
+ * generate_terrain_batch_3_mats — utils/shapes.rs:273-357 for a whole grid of chunks, writing the Batch arrays of
+ * vx_apply_batches_device directly in HBM.  Both calls are asynchronous on `stream` (NULL = the interner's stream).
+ *   vx_terrain_heights_device  d_heights[nx][nz] (int32) in [0, height): this library's seeded integer value noise
+ *                              (the reference samples fastnoise-lite OpenSimplex2, a float third-party noise that is
+ *                              input synthesis, not part of the path); column (x0 + i, z0 + j)
+ *   vx_terrain_batches_device  grid = chunks along (x, y, z), chunk index (cx*gy + cy)*gz + cz, d_heights sized
+ *                              [gx*N][gz*N]; surface_only: the voxel at Y == h (shapes.rs:302-304), else every voxel
+ *                              with Y <= h (:306-309); materials 3: 1 at the surface, 2 for the next three, 3 below
+ *                              (:340-355); masks[n][B][2], values[n][B][8] of the interner's dtype */
+int vx_terrain_heights_device(vx_interner*, uint32_t nx, uint32_t nz, uint64_t seed, uint32_t height, int64_t x0,
+                              int64_t z0, int32_t* d_heights, void* stream);
+int vx_terrain_batches_device(vx_interner*, uint8_t max_depth, const uint32_t grid[3], const int32_t* d_heights,
+                              int surface_only, int materials, uint8_t* d_masks, void* d_values, void* stream);
+
 /* VoxTree::get — voxtree.rs:144-160 -> get_at_depth utils/common.rs:122-156.
  * Returns 1 = Some(*out), 0 = None, VX_E_BOUNDS outside the chunk (reference: assert!). */
 int vx_tree_get(const vx_interner*, const vx_tree*, int x, int y, int z, int64_t* out);

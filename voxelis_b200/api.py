@@ -46,7 +46,7 @@ ABI_SYMBOLS = [
     "vx_tree_voxels_per_axis", "vx_tree_is_empty", "vx_tree_is_leaf", "vx_tree_is_dirty",
     "vx_tree_mark_dirty", "vx_tree_clear_dirty", "vx_tree_apply_batch", "vx_apply_batches",
     "vx_apply_batches_slab", "vx_apply_batches_device", "vx_tree_get", "vx_tree_get_many",
-    "vx_tree_to_vec", "vx_roots_to_vec", "vx_roots_to_vec_lod", "vx_occupancy_masks", "vx_tree_fill", "vx_tree_clear",
+    "vx_tree_to_vec", "vx_roots_to_vec", "vx_roots_to_vec_lod", "vx_occupancy_masks", "vx_terrain_heights_device", "vx_terrain_batches_device", "vx_tree_fill", "vx_tree_clear",
     "vx_dedup_heights", "vx_dedup_pack", "vx_dedup_scatter", "vx_dedup_map_roots", "vx_interner_intern_records",
 ]
 
@@ -149,6 +149,8 @@ def lib():
     L.vx_roots_to_vec.argtypes = [vp, C.c_uint8, sz, vp, vp]
     L.vx_roots_to_vec_lod.argtypes = [vp, C.c_uint8, C.c_uint8, sz, vp, vp]
     L.vx_occupancy_masks.argtypes = [vp, C.c_uint8, C.c_uint8, sz, vp, vp, vp, sz, C.c_uint32, vp, vp, vp, vp, vp, vp]
+    L.vx_terrain_heights_device.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, i64, i64, vp, vp]
+    L.vx_terrain_batches_device.argtypes = [vp, C.c_uint8, vp, vp, C.c_int, C.c_int, vp, vp, vp]
     L.vx_tree_fill.argtypes = [vp, vp, i64]
     L.vx_tree_clear.argtypes = [vp, vp]
     L.vx_model_serialize.restype = i64
@@ -316,6 +318,21 @@ class VoxInterner:
                                           C.c_void_p(d_flags or None), C.c_void_p(d_fills or None),
                                           C.c_void_p(d_roots), C.c_void_p(d_changed or None),
                                           C.c_void_p(stream or None)))
+
+    def terrain_heights_device(self, nx: int, nz: int, d_heights: int, seed: int = 0x5EED0000, height: int = 256,
+                               x0: int = 0, z0: int = 0, stream: int = 0):
+        """vx_terrain_heights_device: int32 heights[nx][nz] in device memory (== workloads.height_field)."""
+        _ck(lib().vx_terrain_heights_device(self.h, nx, nz, seed, height, x0, z0, C.c_void_p(d_heights),
+                                            C.c_void_p(stream or None)))
+
+    def terrain_batches_device(self, depth: int, grid, d_heights: int, d_masks: int, d_values: int,
+                               surface_only: bool = True, materials: int = 1, stream: int = 0):
+        """vx_terrain_batches_device: the Batch arrays of a whole grid of terrain chunks, written in device memory
+        (generate_terrain_batch[_3_mats], reference voxelis/src/utils/shapes.rs:273-357; == workloads.terrain_world)."""
+        g = (C.c_uint32 * 3)(*[int(v) for v in grid])
+        _ck(lib().vx_terrain_batches_device(self.h, depth, g, C.c_void_p(d_heights), int(bool(surface_only)),
+                                            materials, C.c_void_p(d_masks), C.c_void_p(d_values),
+                                            C.c_void_p(stream or None)))
 
     def model_serialize(self, positions, roots) -> bytes:
         """VoxModel::serialize (world/voxmodel.rs:177-294): VTM payload of chunks (positions[n][3], roots[n])."""

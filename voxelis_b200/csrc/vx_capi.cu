@@ -26,6 +26,7 @@
 #include "vx_stage.cuh"
 #include "vx_vtm.cuh"
 #include "vx_occupancy.cuh"
+#include "vx_terrain.cuh"
 
 #include <cub/device/device_scan.cuh>
 #include <dlfcn.h>
@@ -1245,6 +1246,46 @@ int vx_apply_batches_device(vx_interner* it, uint8_t depth, size_t n, const uint
     DeviceGuard g(it->device);
     cudaStream_t s = stream ? (cudaStream_t)stream : it->stream;
     return launch_apply(it, depth, n, d_masks, d_values, d_flags, d_fills, d_roots, d_changed, s);
+}
+
+// ------------------------------------------------------------------------------- device batch generation
+int vx_terrain_heights_device(vx_interner* it, uint32_t nx, uint32_t nz, uint64_t seed, uint32_t height, int64_t x0,
+                              int64_t z0, int32_t* d_heights, void* stream) {
+    if (!it || !d_heights) return fail(VX_E_INVALID, "null argument");
+    if (!nx || !nz) return VX_OK;
+    if (x0 < 0 || z0 < 0 || height > 65536) return fail(VX_E_INVALID, "x0, z0 >= 0 and height <= 65536");
+    if (!is_device_ptr(d_heights)) return fail(VX_E_INVALID, "d_heights must be device memory");
+    DeviceGuard g(it->device);
+    cudaStream_t s = stream ? (cudaStream_t)stream : it->stream;
+    const size_t total = size_t(nx) * nz;
+    terrain_heights_kernel<<<unsigned((total + 255) / 256), 256, 0, s>>>(nx, nz, seed, height, x0, z0, d_heights);
+    CU_TRY(cudaGetLastError());
+    return VX_OK;
+}
+
+int vx_terrain_batches_device(vx_interner* it, uint8_t max_depth, const uint32_t grid[3], const int32_t* d_heights,
+                              int surface_only, int materials, uint8_t* d_masks, void* d_values, void* stream) {
+    if (!it || !grid || !d_heights || !d_masks || !d_values) return fail(VX_E_INVALID, "null argument");
+    if (!valid_depth(max_depth)) return fail(VX_E_INVALID, "max_depth must be in [2,7]");
+    if (materials != 1 && materials != 3) return fail(VX_E_INVALID, "materials must be 1 or 3 (utils/shapes.rs:273-357)");
+    if ((reinterpret_cast<uintptr_t>(d_masks) | reinterpret_cast<uintptr_t>(d_values)) & 15)
+        return fail(VX_E_INVALID, "device masks/values must be 16-byte aligned");
+    if (!is_device_ptr(d_heights) || !is_device_ptr(d_masks) || !is_device_ptr(d_values))
+        return fail(VX_E_INVALID, "heights, masks and values must be device memory");
+    const size_t n = size_t(grid[0]) * grid[1] * grid[2];
+    if (n == 0) return VX_OK;
+    DeviceGuard g(it->device);
+    cudaStream_t s = stream ? (cudaStream_t)stream : it->stream;
+    const size_t total = n * blocks_for_depth(max_depth);
+    const unsigned blocks = unsigned(std::min<size_t>((total + 255) / 256, size_t(it->sm_count) * 32));
+    if (it->dtype == VX_U8)
+        terrain_batches_kernel<u8><<<blocks, 256, 0, s>>>(max_depth, grid[0], grid[1], grid[2], d_heights,
+                                                           surface_only, materials, d_masks, (u8*)d_values);
+    else
+        terrain_batches_kernel<int32_t><<<blocks, 256, 0, s>>>(max_depth, grid[0], grid[1], grid[2], d_heights,
+                                                                surface_only, materials, d_masks, (int32_t*)d_values);
+    CU_TRY(cudaGetLastError());
+    return VX_OK;
 }
 
 static int apply_slab_impl(vx_interner* it, uint8_t depth, size_t n, const uint8_t* masks, const void* values,
