@@ -21,7 +21,7 @@ B = wl.blocks_per_chunk(depth)
 n = gx * gy * gz
 dev = torch.device("cuda", 0)
 it = vx.VoxInterner.with_memory_budget(256 << 20, vx.U8, 0)
-stream = torch.cuda.ExternalStream(it.stream(), device=dev)
+stream = torch.cuda.ExternalStream(it.stream, device=dev)
 h = torch.empty((gx * N, gz * N), dtype=torch.int32, device=dev)
 m = torch.empty((n, B, 2), dtype=torch.uint8, device=dev)
 v = torch.empty((n, B, 8), dtype=torch.uint8, device=dev)

@@ -3,6 +3,7 @@
 // pools downloaded from the CPU oracle, so that the line walk, the plane / axis mapping and the register-vs-spill
 // bookkeeping are checked against the oracle before any GPU time is spent.  The kernels themselves are checked on
 // the B200 by tests/test_gpu_occupancy.py.
+#include <cstring>
 #include <map>
 #include <vector>
 
@@ -29,6 +30,55 @@ static int run(const u64* children, const T* values, const u64* cell, int ld, in
         global[w] = occ_word<T>(children, values, cell, ld, w, n, pm + w,
                                 [&](T v) { return occ_search(ids, n, occ_material_of<T>(v)); });
     return n;
+}
+
+// The shared-memory path's index math: occ_walk_item (Morton node walk, ownership, coordinates) and
+// occ_region_words (cube -> half words of one plane), stepped item by item; big cubes go through the lane-strided
+// form the kernel's warps use.  Materials take slots in the order met and leave in id order.
+template <class T>
+static int run_planes(const u64* children, const T* values, const u64* cell, int ld, int max_mat, u64* ids,
+                      u64* counts, u64* global, u64* pm) {
+    std::vector<u64> seen;  // slot -> material id
+    std::vector<u64> vol;
+    std::vector<std::vector<uint32_t>> planes;  // [plane][(1 + slot) * OCC_HALVES]
+    for (int plane = 0; plane < 3; ++plane) {
+        std::vector<uint32_t> g(OCC_HALVES, 0);
+        std::vector<std::vector<uint32_t>> mats;
+        for (u32 item = 0; item < occ_items_per_builder(ld); ++item)
+            occ_walk_item<T>(children, values, cell, ld, item, [&](T v, u32 x, u32 y, u32 z, u32 ls) {
+                const u64 id = occ_material_of<T>(v);
+                size_t slot = 0;
+                while (slot < seen.size() && seen[slot] != id) ++slot;
+                if (slot == seen.size()) seen.push_back(id), vol.push_back(0);
+                if (mats.size() <= slot) mats.resize(slot + 1, std::vector<uint32_t>(OCC_HALVES, 0));
+                if (plane == 0) vol[slot] += u64(1) << (3 * ls);
+                auto orfn = [&](u32 i, u32 bits) { g[i] |= bits, mats[slot][i] |= bits; };
+                if (ls >= 3)
+                    for (u32 lane = 0; lane < 32; ++lane) occ_region_words(plane, x, y, z, ls, lane, 32, orfn);
+                else
+                    occ_region_words(plane, x, y, z, ls, 0, 1, orfn);
+            });
+        mats.resize(seen.size(), std::vector<uint32_t>(OCC_HALVES, 0));
+        if (int(seen.size()) > max_mat) return -1;
+        std::vector<size_t> order(seen.size());
+        for (size_t k = 0; k < seen.size(); ++k) {
+            size_t rank = 0;
+            for (size_t j = 0; j < seen.size(); ++j) rank += seen[j] < seen[k];
+            order[rank] = k;
+        }
+        memcpy(global + plane * OCC_PLANE, g.data(), OCC_PLANE * 8);
+        for (size_t r = 0; r < order.size(); ++r) {
+            memcpy(pm + r * OCC_ALL + plane * OCC_PLANE, mats[order[r]].data(), OCC_PLANE * 8);
+            ids[r] = seen[order[r]], counts[r] = vol[order[r]];
+        }
+    }
+    return int(seen.size());
+}
+
+extern "C" int occ_host_check_planes(const u64* children, const void* values, int dtype, const u64* cell, int ld,
+                                     int max_mat, u64* ids, u64* counts, u64* global, u64* pm) {
+    return dtype == 0 ? run_planes<u8>(children, (const u8*)values, cell, ld, max_mat, ids, counts, global, pm)
+                      : run_planes<int32_t>(children, (const int32_t*)values, cell, ld, max_mat, ids, counts, global, pm);
 }
 
 extern "C" int occ_host_check(const u64* children, const void* values, int dtype, const u64* cell, int ld, int max_mat,

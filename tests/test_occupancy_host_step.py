@@ -29,6 +29,7 @@ def stepper():
         assert res.returncode == 0, res.stderr
     L = C.CDLL(out)
     L.occ_host_check.argtypes = [C.c_void_p] * 2 + [C.c_int] + [C.c_void_p] + [C.c_int] * 2 + [C.c_void_p] * 4
+    L.occ_host_check_planes.argtypes = L.occ_host_check.argtypes
     return L
 
 
@@ -36,9 +37,10 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+@pytest.mark.parametrize("entry", ["occ_host_check", "occ_host_check_planes"], ids=["word_owner", "morton_planes"])
 @pytest.mark.parametrize("dtype", [wl.U8, wl.I32], ids=["u8", "i32"])
 @pytest.mark.parametrize("depth", [3, 5, 6])
-def test_per_word_source_matches_oracle(stepper, oracle_api, depth, dtype):
+def test_per_word_source_matches_oracle(stepper, oracle_api, depth, dtype, entry):
     masks, values = chunk_set(depth, dtype)
     it, roots, _ = oracle_build(oracle_api, depth, masks, values, dtype, budget=256 << 20)
     dl = it.download()
@@ -60,7 +62,7 @@ def test_per_word_source_matches_oracle(stepper, oracle_api, depth, dtype):
             ids, counts = np.zeros(M, np.uint64), np.zeros(M, np.uint64)
             glob = np.zeros(3 * 4096, np.uint64)
             pm = np.full((M, 3 * 4096), 0xDEADBEEF, np.uint64)      # every word of a live plane must be WRITTEN
-            nm = stepper.occ_host_check(_p(children), _p(vals), dtype, _p(cell), ld, M, _p(ids), _p(counts), _p(glob),
+            nm = getattr(stepper, entry)(_p(children), _p(vals), dtype, _p(cell), ld, M, _p(ids), _p(counts), _p(glob),
                                         _p(pm))
             assert nm == len(want["material_ids"]), (depth, lod, b0)
             assert np.array_equal(ids[:nm], want["material_ids"]) and np.array_equal(counts[:nm], want["material_counts"])

@@ -1276,14 +1276,13 @@ int vx_terrain_batches_device(vx_interner* it, uint8_t max_depth, const uint32_t
     if (n == 0) return VX_OK;
     DeviceGuard g(it->device);
     cudaStream_t s = stream ? (cudaStream_t)stream : it->stream;
-    const size_t total = n * blocks_for_depth(max_depth);
-    const unsigned blocks = unsigned(std::min<size_t>((total + 255) / 256, size_t(it->sm_count) * 32));
-    if (it->dtype == VX_U8)
-        terrain_batches_kernel<u8><<<blocks, 256, 0, s>>>(max_depth, grid[0], grid[1], grid[2], d_heights,
-                                                           surface_only, materials, d_masks, (u8*)d_values);
-    else
-        terrain_batches_kernel<int32_t><<<blocks, 256, 0, s>>>(max_depth, grid[0], grid[1], grid[2], d_heights,
-                                                                surface_only, materials, d_masks, (int32_t*)d_values);
+    const size_t total = n * blocks_for_depth(max_depth);  // >= 8 blocks per chunk: divisible by 4
+    if (it->dtype == VX_U8)   // 4 Morton-consecutive blocks per thread: one 32-byte value store each
+        terrain_batches_kernel<u8, 4><<<unsigned((total / 4 + 255) / 256), 256, 0, s>>>(
+            max_depth, grid[0], grid[1], grid[2], d_heights, surface_only, materials, d_masks, (u8*)d_values);
+    else                      // one block per thread: 32 bytes of i32 values each
+        terrain_batches_kernel<int32_t, 1><<<unsigned((total + 255) / 256), 256, 0, s>>>(
+            max_depth, grid[0], grid[1], grid[2], d_heights, surface_only, materials, d_masks, (int32_t*)d_values);
     CU_TRY(cudaGetLastError());
     return VX_OK;
 }
@@ -1892,7 +1891,7 @@ int vx_occupancy_masks(const vx_interner* cit, uint8_t max_depth, uint8_t lod, s
     DeviceGuard g(it->device);
     const size_t M = max_materials, plane_bytes = size_t(OCC_ALL) * 8;
     auto up = [](size_t v) { return (v + 255) / 256 * 256; };
-    size_t need = up(ncell * 8) + 256;
+    size_t need = up(ncell * 8) + 256 + up(n_builders * 4);
     if (!dev_out)
         need += up(n_builders * plane_bytes) + up(n_builders * 48) + up(n_builders * 4) + 2 * up(n_builders * M * 8) +
                 up(n_builders * M * plane_bytes);
@@ -1903,6 +1902,7 @@ int vx_occupancy_masks(const vx_interner* cit, uint8_t max_depth, uint8_t lod, s
     auto take = [&](size_t bytes) { u8* r = p; p += up(bytes); return r; };
     u32* d_err = (u32*)take(256);
     u64* d_cells = (u64*)take(ncell * 8);
+    u32* d_over = (u32*)take(n_builders * 4);
     u64 *d_global = global, *d_active = active, *d_ids = material_ids, *d_counts = material_counts, *d_pm = per_material;
     u32* d_nmat = n_materials;
     if (!dev_out) {
@@ -1913,24 +1913,49 @@ int vx_occupancy_masks(const vx_interner* cit, uint8_t max_depth, uint8_t lod, s
         d_counts = (u64*)take(n_builders * M * 8);
         d_pm = (u64*)take(n_builders * M * plane_bytes);
     }
-    CU_TRY(cudaMemsetAsync(d_err, 0, 4, s));
+    u32* d_over_count = d_err + 1;
+    CU_TRY(cudaMemsetAsync(d_err, 0, 8, s));
     CU_TRY(cudaMemcpyAsync(d_cells, cells.data(), ncell * 8, cudaMemcpyHostToDevice, s));
-    const dim3 grid_masks(OCC_ALL / 256, unsigned(n_builders));
+    // 1. shared-memory path: every builder with <= ms materials (vx_occupancy.cuh: occ_planes_kernel)
+    const int ms = int(std::min<uint32_t>(max_materials, OCC_MS_MAX));
+    const size_t smem = size_t(1 + ms) * OCC_HALVES * 4;
+    const dim3 grid_planes(3, unsigned(n_builders));
     if (it->dtype == VX_U8) {
-        occ_materials_kernel<u8><<<unsigned(n_builders), 256, 0, s>>>(it->dev.children, (const u8*)it->dev.values,
-                                                                       d_cells, ld, max_materials, d_nmat, d_ids,
-                                                                       d_counts, d_active, d_err);
-        occ_masks_kernel<u8><<<grid_masks, 256, 0, s>>>(it->dev.children, (const u8*)it->dev.values, d_cells, ld,
-                                                         max_materials, d_nmat, d_ids, d_global, d_active, d_pm);
+        CU_TRY(cudaFuncSetAttribute(occ_planes_kernel<u8>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        occ_planes_kernel<u8><<<grid_planes, 1024, smem, s>>>(it->dev.children, (const u8*)it->dev.values, d_cells, ld,
+                                                               ms, max_materials, d_nmat, d_ids, d_counts, d_global,
+                                                               d_active, d_pm, d_over, d_over_count);
     } else {
-        occ_materials_kernel<int32_t><<<unsigned(n_builders), 256, 0, s>>>(
-            it->dev.children, (const int32_t*)it->dev.values, d_cells, ld, max_materials, d_nmat, d_ids, d_counts,
-            d_active, d_err);
-        occ_masks_kernel<int32_t><<<grid_masks, 256, 0, s>>>(it->dev.children, (const int32_t*)it->dev.values,
-                                                              d_cells, ld, max_materials, d_nmat, d_ids, d_global,
-                                                              d_active, d_pm);
+        CU_TRY(cudaFuncSetAttribute(occ_planes_kernel<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        occ_planes_kernel<int32_t><<<grid_planes, 1024, smem, s>>>(it->dev.children, (const int32_t*)it->dev.values,
+                                                                    d_cells, ld, ms, max_materials, d_nmat, d_ids,
+                                                                    d_counts, d_global, d_active, d_pm, d_over,
+                                                                    d_over_count);
     }
     CU_TRY(cudaGetLastError());
+    u32 n_over = 0;
+    CU_TRY(cudaMemcpyAsync(&n_over, d_over_count, 4, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    // 2. builders with more materials than fit in shared memory: word-owner kernels, only for the flagged ones
+    if (n_over) {
+        const dim3 grid_masks(OCC_ALL / 256, unsigned(n_builders));
+        if (it->dtype == VX_U8) {
+            occ_materials_kernel<u8><<<unsigned(n_builders), 256, 0, s>>>(it->dev.children, (const u8*)it->dev.values,
+                                                                           d_cells, ld, max_materials, d_nmat, d_ids,
+                                                                           d_counts, d_active, d_err, d_over);
+            occ_masks_kernel<u8><<<grid_masks, 256, 0, s>>>(it->dev.children, (const u8*)it->dev.values, d_cells, ld,
+                                                             max_materials, d_nmat, d_ids, d_global, d_active, d_pm,
+                                                             d_over);
+        } else {
+            occ_materials_kernel<int32_t><<<unsigned(n_builders), 256, 0, s>>>(
+                it->dev.children, (const int32_t*)it->dev.values, d_cells, ld, max_materials, d_nmat, d_ids, d_counts,
+                d_active, d_err, d_over);
+            occ_masks_kernel<int32_t><<<grid_masks, 256, 0, s>>>(it->dev.children, (const int32_t*)it->dev.values,
+                                                                  d_cells, ld, max_materials, d_nmat, d_ids, d_global,
+                                                                  d_active, d_pm, d_over);
+        }
+        CU_TRY(cudaGetLastError());
+    }
     u32 err = 0;
     CU_TRY(cudaMemcpyAsync(&err, d_err, 4, cudaMemcpyDeviceToHost, s));
     if (!dev_out) {

@@ -14,6 +14,9 @@
 // reference's scatter.  HBM traffic = the output planes written once (no memset, no atomics on them) + the
 // DAG nodes on the way (L1/L2 hits: neighbouring words share their paths).
 //
+// These two kernels serve builders with MANY materials (> 5); the usual case goes through occ_planes_kernel
+// (shared-memory planes, Morton node walk) at the end of this file.
+//
 //   occ_materials_kernel   one CTA per builder: voxel count per material (mesh.rs:428-432) from the YZ rows,
 //                          ids sorted ascending as build() does; also clears the builder's global_active
 //   occ_masks_kernel       48 CTAs per builder x 256 threads = 12288 words: global plane word, per-material
@@ -86,8 +89,10 @@ template <class T>
 __global__ void __launch_bounds__(256)
 occ_materials_kernel(const u64* __restrict__ children, const T* __restrict__ values, const u64* __restrict__ cells,
                      int ld, u32 max_materials, u32* __restrict__ n_materials, u64* __restrict__ material_ids,
-                     u64* __restrict__ material_counts, u64* __restrict__ active, u32* __restrict__ err) {
+                     u64* __restrict__ material_counts, u64* __restrict__ active, u32* __restrict__ err,
+                     const u32* __restrict__ only) {
     constexpr int TS = OccTable<T>::SIZE;
+    if (only && !only[blockIdx.x]) return;  // this builder went through occ_planes_kernel
     __shared__ u32 s_key[TS];   // raw value bits, 0 = free (the default value is never a material)
     __shared__ u32 s_cnt[TS];
     __shared__ u32 s_over;
@@ -254,7 +259,8 @@ __global__ void __launch_bounds__(256)
 occ_masks_kernel(const u64* __restrict__ children, const T* __restrict__ values, const u64* __restrict__ cells,
                  int ld, u32 max_materials, const u32* __restrict__ n_materials,
                  const u64* __restrict__ material_ids, u64* __restrict__ global, u64* __restrict__ active,
-                 u64* __restrict__ per_material) {
+                 u64* __restrict__ per_material, const u32* __restrict__ only) {
+    if (only && !only[blockIdx.y]) return;
     __shared__ u8 s_lut[256];
     __shared__ u64 s_or[8];
     const int b = blockIdx.y, gsh = 6 - ld;
@@ -289,6 +295,235 @@ occ_masks_kernel(const u64* __restrict__ children, const T* __restrict__ values,
             atomicOr((ull*)&active[size_t(b) * 6 + i0], (ull)t);
             atomicOr((ull*)&active[size_t(b) * 6 + i1], (ull)t);
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Shared-memory path: builders with at most `ms` (<= 5) materials — the mesher's normal case.
+//
+// One CTA per (builder, plane) keeps the plane of the builder in shared memory: 32 KiB for the global plane +
+// 32 KiB per material.  The DAG is walked in MORTON order, node by node (not row by row): a node standing at
+// depth k answers 8^(depth-k) voxels at once, so every tree node of the builder is visited once per plane and
+// ORs its side^2 words (32-bit shared atomics: an aligned run of <= 32 bits lives in one half word).  Regions of
+// side >= 8 are queued and filled by whole warps.  Materials take slots in the order the CTA meets them; the
+// planes leave in id order (build(), mesh.rs:263-285) through a permutation applied while they are streamed out
+// with 16-byte coalesced stores — each output byte is written exactly once, nothing is read back from HBM.
+// The YZ CTA also delivers the material list and voxel counts; every CTA stores its two global_active words.
+// A builder with more than `ms` materials is flagged in overflow[] and left to the word-owner kernels above.
+
+// Walk the Morton range [m0, m0 + len) of the tree `root` (len = 8^k, m0 aligned to len): visit(node, d, start)
+// for every maximal node (leaf, empty, or branch standing at depth ld) — `start` = first Morton index it covers
+// (<= m0 only for the first one, when the range lies inside a bigger node).
+template <class F>
+__host__ __device__ __forceinline__ void occ_walk_morton(const u64* __restrict__ children, u64 root, int ld, u32 m0,
+                                                         u32 len, F visit) {
+    u64 path[7];
+    path[0] = root;
+    u32 m = m0;
+    const u32 end = m0 + len;
+    bool first = true;
+    while (m < end) {
+        int d = first ? 0 : ld - 1 - (VX_OCC_FFS(int(m)) - 1) / 3;
+        u64 node = path[d];
+        while (node != 0 && !id_is_leaf(node) && d < ld) {
+            const int ci = int(m >> (3 * (ld - 1 - d))) & 7;
+            node = VX_OCC_LD(&children[size_t(id_index(node)) * 8 + ci]);
+            ++d;
+            path[d] = node;
+        }
+        const u32 span = 1u << (3 * (ld - d));
+        const u32 start = m & ~(span - 1);
+        visit(node, d, start);
+        m = start + span;
+        first = false;
+    }
+}
+
+__host__ __device__ __forceinline__ u32 occ_compact3(u32 v) {  // every third bit of a Morton index (<= 6 bits out)
+    v &= 0x09249249u;
+    v = (v | (v >> 2)) & 0x030C30C3u;
+    v = (v | (v >> 4)) & 0x0300F00Fu;
+    v = (v | (v >> 8)) & 0x030000FFu;
+    v = (v | (v >> 16)) & 0x000003FFu;
+    return v;
+}
+
+// OR the cube (x, y, z, side) into one plane held as 32-bit half words: half word 2*w + (bit >> 5) of word w.
+// or32(index, bits) does the OR (a shared atomic on the device, a plain OR in the host stepping test).
+template <class F>
+__host__ __device__ __forceinline__ void occ_region_words(int plane, u32 x, u32 y, u32 z, u32 ls, u32 k0,
+                                                          u32 kstep, F or32) {
+    const u32 side = 1u << ls;
+    const u32 r0 = plane == 1 ? z : y, r1 = plane == 0 ? z : x, rb = plane == 0 ? x : plane == 1 ? y : z;
+    const u32 bits = side >= 32 ? 0xFFFFFFFFu : (((1u << side) - 1) << (rb & 31));
+    const u32 half = (rb >> 5) & 1;
+    for (u32 k = k0; k < side * side; k += kstep) {
+        const u32 w = (r0 + (k >> ls)) * 64 + r1 + (k & (side - 1));
+        if (side == 64) {
+            or32(2 * w, bits);
+            or32(2 * w + 1, bits);
+        } else {
+            or32(2 * w + half, bits);
+        }
+    }
+}
+
+// Item `item` of a builder = 8^min(ld,2) Morton positions of one cell: emit(value, x, y, z, ls) for every maximal
+// non-default node the item owns (x, y, z in builder voxels, side 2^ls).  A node bigger than the item belongs to
+// the item that starts it.
+template <class T, class Emit>
+__host__ __device__ __forceinline__ void occ_walk_item(const u64* __restrict__ children, const T* __restrict__ values,
+                                                       const u64* __restrict__ cell, int ld, u32 item, Emit emit) {
+    const int gsh = 6 - ld, G = 1 << gsh;
+    const int isz_log = 3 * (ld < 2 ? ld : 2);
+    const u32 ipc_log = u32(3 * ld - isz_log);                  // items per cell (log2)
+    const u32 c = item >> ipc_log, m0 = (item & ((1u << ipc_log) - 1)) << isz_log;
+    const u64 root = VX_OCC_LD(&cell[c]);
+    if (root == 0) return;
+    const u32 ox = (c & (G - 1)) << ld, oz = ((c >> gsh) & (G - 1)) << ld, oy = (c >> (2 * gsh)) << ld;
+    occ_walk_morton(children, root, ld, m0, 1u << isz_log, [&](u64 node, int d, u32 start) {
+        if (node == 0 || start < m0) return;
+        const T v = values[id_index(node)];
+        if (v == T(0)) return;
+        emit(v, ox + occ_compact3(start), oy + occ_compact3(start >> 1), oz + occ_compact3(start >> 2), u32(ld - d));
+    });
+}
+__host__ __device__ inline u32 occ_items_per_builder(int ld) {
+    return u32(1) << (3 * (6 - ld) + 3 * ld - 3 * (ld < 2 ? ld : 2));
+}
+
+constexpr int OCC_MS_MAX = 5;        // materials per builder on the shared-memory path
+constexpr int OCC_QUEUE = 512;       // regions of side >= 8 in one 64^3 volume
+constexpr int OCC_HALVES = 2 * OCC_PLANE;  // u32 half words per plane
+
+template <class T>
+__global__ void __launch_bounds__(1024)
+occ_planes_kernel(const u64* __restrict__ children, const T* __restrict__ values, const u64* __restrict__ cells,
+                  int ld, int ms, u32 max_materials, u32* __restrict__ n_materials, u64* __restrict__ material_ids,
+                  u64* __restrict__ material_counts, u64* __restrict__ global, u64* __restrict__ active,
+                  u64* __restrict__ per_material, u32* __restrict__ overflow, u32* __restrict__ overflow_count) {
+    extern __shared__ uint4 occ_smem[];
+    u32* planes = reinterpret_cast<u32*>(occ_smem);  // [1 + ms][OCC_HALVES]: global plane, then one per slot
+    __shared__ u32 s_mat[OCC_MS_MAX];                // raw value bits of the material in each slot, 0 = free
+    __shared__ u32 s_cnt[OCC_MS_MAX];
+    __shared__ u32 s_queue[OCC_QUEUE];
+    __shared__ u32 s_qn, s_over, s_act[2];
+    __shared__ int s_order[OCC_MS_MAX], s_n;
+    const int plane = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, nthr = blockDim.x;
+    const u64* cell = cells + (size_t(b) << (3 * (6 - ld)));
+    for (int i = tid; i < (1 + ms) * (OCC_HALVES / 4); i += nthr) occ_smem[i] = make_uint4(0, 0, 0, 0);
+    if (tid < OCC_MS_MAX) s_mat[tid] = 0, s_cnt[tid] = 0;
+    if (tid == 0) s_qn = 0, s_over = 0, s_act[0] = 0, s_act[1] = 0;
+    __syncthreads();
+
+    const u32 items = occ_items_per_builder(ld);
+    T last_v = T(0);
+    int last_slot = -1;
+    for (u32 item = tid; item < items; item += nthr)
+        occ_walk_item<T>(children, values, cell, ld, item, [&](T v, u32 x, u32 y, u32 z, u32 ls) {
+            if (v != last_v) {                                  // slot of the material, claimed on first sight
+                const u32 key = sizeof(T) == 1 ? (u32(v) & 0xFFu) : u32(v);
+                int slot = -1;
+                for (int k = 0; k < ms && slot < 0; ++k) {
+                    u32 cur = s_mat[k];
+                    if (cur == 0) {
+                        const u32 prev = atomicCAS(&s_mat[k], 0u, key);
+                        cur = prev == 0 ? key : prev;
+                    }
+                    if (cur == key) slot = k;
+                }
+                last_v = v;
+                last_slot = slot;
+                if (slot < 0) s_over = 1;
+            }
+            const int slot = last_slot;
+            if (slot < 0) return;
+            if (plane == 0) atomicAdd(&s_cnt[slot], 1u << (3 * ls));
+            if (ls >= 3) {                                      // side >= 8: filled by whole warps after the walk
+                const u32 q = atomicAdd(&s_qn, 1u);
+                if (q < OCC_QUEUE) s_queue[q] = x | (y << 6) | (z << 12) | (ls << 18) | (u32(slot) << 21);
+                return;
+            }
+            u32* pg = planes;
+            u32* pmat = planes + size_t(1 + slot) * OCC_HALVES;
+            occ_region_words(plane, x, y, z, ls, 0, 1, [&](u32 i, u32 bits) {
+                atomicOr(&pg[i], bits);
+                atomicOr(&pmat[i], bits);
+            });
+        });
+    __syncthreads();
+    if (s_over) {                                               // too many materials for shared memory
+        if (tid == 0 && plane == 0) {
+            overflow[b] = 1;
+            atomicAdd(overflow_count, 1u);
+        }
+        return;
+    }
+    {
+        const u32 qn = min(s_qn, u32(OCC_QUEUE));
+        const int warp = tid >> 5, lane = tid & 31, nwarp = nthr >> 5;
+        for (u32 q = warp; q < qn; q += nwarp) {
+            const u32 e = s_queue[q];
+            u32* pg = planes;
+            u32* pmat = planes + size_t(1 + (e >> 21)) * OCC_HALVES;
+            occ_region_words(plane, e & 63, (e >> 6) & 63, (e >> 12) & 63, (e >> 18) & 7, lane, 32,
+                             [&](u32 i, u32 bits) {
+                                 atomicOr(&pg[i], bits);
+                                 atomicOr(&pmat[i], bits);
+                             });
+        }
+    }
+    if (tid == 0) {                                             // build(): materials in id order
+        int n = 0;
+        for (int k = 0; k < ms; ++k) n += s_mat[k] != 0;
+        for (int k = 0; k < n; ++k) {
+            const u64 id = occ_material_of<T>(T(s_mat[k]));
+            int rank = 0;
+            for (int j = 0; j < n; ++j) rank += occ_material_of<T>(T(s_mat[j])) < id;
+            s_order[rank] = k;
+        }
+        s_n = n;
+        if (plane == 0) {
+            overflow[b] = 0;
+            n_materials[b] = u32(n);
+        }
+    }
+    __syncthreads();
+    const int n = s_n;
+    if (plane == 0 && tid < n) {
+        const int k = s_order[tid];
+        material_ids[size_t(b) * max_materials + tid] = occ_material_of<T>(T(s_mat[k]));
+        material_counts[size_t(b) * max_materials + tid] = s_cnt[k];
+    }
+    // stream the planes out: 16 bytes per thread and step, global plane first, then the materials in id order
+    u32 alo = 0, ahi = 0;
+    uint4* gout = reinterpret_cast<uint4*>(global + size_t(b) * OCC_ALL + size_t(plane) * OCC_PLANE);
+    for (int i = tid; i < OCC_HALVES / 4; i += nthr) {
+        const uint4 v = occ_smem[i];
+        alo |= v.x | v.z;
+        ahi |= v.y | v.w;
+        gout[i] = v;
+    }
+    for (int r = 0; r < n; ++r) {
+        const uint4* src = occ_smem + size_t(1 + s_order[r]) * (OCC_HALVES / 4);
+        uint4* dst = reinterpret_cast<uint4*>(per_material + (size_t(b) * max_materials + r) * OCC_ALL +
+                                              size_t(plane) * OCC_PLANE);
+        for (int i = tid; i < OCC_HALVES / 4; i += nthr) dst[i] = src[i];
+    }
+    // global_active (mesh.rs:451-461): the OR of every word of this plane = the mask of its bit axis
+#pragma unroll
+    for (int k = 16; k; k >>= 1) alo |= __shfl_xor_sync(FULL, alo, k), ahi |= __shfl_xor_sync(FULL, ahi, k);
+    if ((tid & 31) == 0) {
+        if (alo) atomicOr(&s_act[0], alo);
+        if (ahi) atomicOr(&s_act[1], ahi);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const u64 t = u64(s_act[0]) | (u64(s_act[1]) << 32);
+        const int i0 = plane == 0 ? 3 : plane == 1 ? 0 : 1;
+        const int i1 = plane == 0 ? 5 : plane == 1 ? 4 : 2;
+        active[size_t(b) * 6 + i0] = t;
+        active[size_t(b) * 6 + i1] = t;
     }
 }
 

@@ -14,8 +14,8 @@
 //   splitmix64(seed << 40 ^ o << 36 ^ (ix & 0x3FFFF) << 18 ^ (iz & 0x3FFFF)); 16.16 fixed-point smoothstep.
 //
 //   terrain_heights_kernel   one thread per column, heights[x][z] (int32), coalesced along z
-//   terrain_batches_kernel   one thread per block of 2x2x2 voxels: 4 heights in, 2 mask bytes + 8 values out;
-//                            consecutive threads write consecutive blocks -> fully coalesced stores
+//   terrain_batches_kernel   one thread per 4 Morton-consecutive blocks (u8) / per block (i32): column heights in,
+//                            mask bytes + values out; consecutive threads write consecutive bytes
 #pragma once
 #include "vx_device.cuh"
 
@@ -68,43 +68,89 @@ __device__ __forceinline__ u32 compact10(u32 v) {  // inverse of spread10 (utils
     return v;
 }
 
-// chunk linear index = (cx * gy + cy) * gz + cz; heights[(cx*n + x) * (gz*n) + cz*n + z]
-template <class T>
-__global__ void terrain_batches_kernel(int depth, u32 gx, u32 gy, u32 gz, const int* __restrict__ heights,
-                                       int surface_only, int materials, u8* __restrict__ masks,
-                                       T* __restrict__ values) {
+__device__ __forceinline__ void st_v8(void* p, uint4 a, uint4 b) {  // one 32-byte store (sm_100+)
+    asm volatile("st.global.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+                 "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+}
+
+// value of a voxel standing d = h - Y below the surface of its column (shapes.rs:302-309,340-355)
+__device__ __forceinline__ int terrain_value(int d, bool surface_only, bool three) {
+    if (surface_only) return d == 0;
+    if (d < 0) return 0;
+    return !three ? 1 : d == 0 ? 1 : d <= 3 ? 2 : 3;
+}
+
+// chunk linear index = (cx * gy + cy) * gz + cz; heights[(cx*n + x) * (gz*n) + cz*n + z].
+// One thread = QUAD Morton-consecutive blocks (QUAD = 4: the 2x2 blocks (bx, by) in {0,1}^2 of one bz, i.e. a
+// 4 x 4 x 2 voxel tile; QUAD = 1: one block): its 2*QUAD column heights are read once, its 8*QUAD values leave as
+// one 32-byte store (u8, QUAD 4) / two 16-byte stores (i32, QUAD 1).  Tiles wholly above the surface or wholly
+// in the deep material skip the per-voxel evaluation.
+template <class T, int QUAD>
+__global__ void __launch_bounds__(256)
+terrain_batches_kernel(int depth, u32 gx, u32 gy, u32 gz, const int* __restrict__ heights, int surface_only,
+                       int materials, u8* __restrict__ masks, T* __restrict__ values) {
+    constexpr int NX = QUAD == 4 ? 4 : 2, NY = QUAD == 4 ? 2 : 1;  // columns along x, block rows along y
     const int bshift = 3 * (depth - 1);
-    const size_t total = (size_t(gx) * gy * gz) << bshift;
+    const size_t total = ((size_t(gx) * gy * gz) << bshift) / QUAD;
+    const size_t t = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+    if (t >= total) return;
+    const size_t i = t * QUAD;                                   // first block of the tile (global block index)
+    const size_t c = i >> bshift;
+    const u32 p = u32(i & ((size_t(1) << bshift) - 1));
     const u32 n = 1u << depth, hz = gz * n;
-    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
-        const size_t c = i >> bshift;
-        const u32 p = u32(i & ((size_t(1) << bshift) - 1));
-        const u32 cz = u32(c % gz), cy = u32((c / gz) % gy), cx = u32(c / (size_t(gz) * gy));
-        const u32 x = compact10(p) * 2, y = compact10(p >> 1) * 2, z = compact10(p >> 2) * 2;
-        const int* hp = heights + size_t(cx * n + x) * hz + cz * n + z;
-        const int h00 = hp[0], h01 = hp[1], h10 = hp[hz], h11 = hp[hz + 1];  // [dx][dz]
-        const int Y0 = int(cy * n + y);
-        u32 set = 0;
-        T v[8];
+    const u32 cz = u32(c % gz), cy = u32((c / gz) % gy), cx = u32(c / (size_t(gz) * gy));
+    const u32 x = compact10(p) * 2, y = compact10(p >> 1) * 2, z = compact10(p >> 2) * 2;
+    const int2* hp = reinterpret_cast<const int2*>(heights + size_t(cx * n + x) * hz + cz * n + z);  // z is even
+    int h[NX][2], hmin = 0x7FFFFFFF, hmax = -0x7FFFFFFF - 1;
 #pragma unroll
-        for (int l = 0; l < 8; ++l) {
-            const int h = (l & 1) ? ((l & 4) ? h11 : h10) : ((l & 4) ? h01 : h00);
-            const int d = h - (Y0 + ((l >> 1) & 1));
-            const bool s = surface_only ? d == 0 : d >= 0;
-            const int val = !s ? 0 : (surface_only || materials != 3) ? 1 : d == 0 ? 1 : d <= 3 ? 2 : 3;
-            set |= u32(s) << l;
-            v[l] = T(val);
+    for (int k = 0; k < NX; ++k) {
+        const int2 v = __ldg(hp + size_t(k) * (hz / 2));
+        h[k][0] = v.x, h[k][1] = v.y;
+        hmin = min(hmin, min(v.x, v.y)), hmax = max(hmax, max(v.x, v.y));
+    }
+    const int Y0 = int(cy * n + y), Y1 = Y0 + 2 * NY - 1;        // the tile spans Y0 .. Y1
+    const bool three = materials == 3, so = surface_only != 0;
+    u32 set[QUAD];
+    u32 val[QUAD][2];  // 8 lanes x 8 bits per block (values are 0..3)
+    if (Y0 > hmax || (so && Y1 < hmin)) {                         // nothing of this tile is set
+#pragma unroll
+        for (int q = 0; q < QUAD; ++q) set[q] = 0, val[q][0] = val[q][1] = 0;
+    } else if (!so && hmin - Y1 >= (three ? 4 : 0)) {             // every voxel is the deep material
+        const u32 f = three ? 0x03030303u : 0x01010101u;
+#pragma unroll
+        for (int q = 0; q < QUAD; ++q) set[q] = 0xFF, val[q][0] = val[q][1] = f;
+    } else {
+#pragma unroll
+        for (int q = 0; q < QUAD; ++q) {                          // block q: bx = q & 1, by = q >> 1
+            u32 sb = 0, lo = 0, hi = 0;
+#pragma unroll
+            for (int l = 0; l < 8; ++l) {
+                const int d = h[2 * (q & 1) + (l & 1)][l >> 2] - (Y0 + 2 * (q >> 1) + ((l >> 1) & 1));
+                const u32 vv = u32(terrain_value(d, so, three));
+                sb |= u32(vv != 0) << l;
+                if (l < 4) lo |= vv << (8 * l); else hi |= vv << (8 * (l - 4));
+            }
+            set[q] = sb, val[q][0] = lo, val[q][1] = hi;
         }
-        reinterpret_cast<uchar2*>(masks)[i] = make_uchar2((unsigned char)set, 0);
-        if (sizeof(T) == 1) {
-            u64 pack = 0;
-#pragma unroll
-            for (int l = 0; l < 8; ++l) pack |= u64(u8(v[l])) << (8 * l);
-            reinterpret_cast<u64*>(values)[i] = pack;
+    }
+    if (QUAD == 4) {
+        *reinterpret_cast<uint2*>(masks + i * 2) = make_uint2(set[0] | (set[1] << 16), set[2] | (set[3] << 16));
+    } else {
+        reinterpret_cast<uchar2*>(masks)[i] = make_uchar2((unsigned char)set[0], 0);
+    }
+    if (sizeof(T) == 1) {
+        if (QUAD == 4) {
+            st_v8(values + i * 8, make_uint4(val[0][0], val[0][1], val[1][0], val[1][1]),
+                  make_uint4(val[2][0], val[2][1], val[3][0], val[3][1]));
         } else {
-            int4* dst = reinterpret_cast<int4*>(values + i * 8);
-            dst[0] = make_int4(int(v[0]), int(v[1]), int(v[2]), int(v[3]));
-            dst[1] = make_int4(int(v[4]), int(v[5]), int(v[6]), int(v[7]));
+            *reinterpret_cast<uint2*>(values + i * 8) = make_uint2(val[0][0], val[0][1]);
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < QUAD; ++q) {
+            int4* dst = reinterpret_cast<int4*>(values + (i + q) * 8);
+            dst[0] = make_int4(val[q][0] & 255, (val[q][0] >> 8) & 255, (val[q][0] >> 16) & 255, val[q][0] >> 24);
+            dst[1] = make_int4(val[q][1] & 255, (val[q][1] >> 8) & 255, (val[q][1] >> 16) & 255, val[q][1] >> 24);
         }
     }
 }
