@@ -32,8 +32,8 @@ static int run(const u64* children, const T* values, const u64* cell, int ld, in
     return n;
 }
 
-// The shared-memory path's index math: occ_walk_item (Morton node walk, ownership, coordinates) and
-// occ_region_words (cube -> half words of one plane), stepped item by item; big cubes go through the lane-strided
+// The shared-memory path's index math: occ_walk_item (Morton node walk, ownership, coordinates, whole blocks),
+// occ_region_words (cube -> half words of one plane) and occ_block_words (voxel pairs), stepped item by item; big cubes go through the lane-strided
 // form the kernel's warps use.  Materials take slots in the order met and leave in id order.
 template <class T>
 static int run_planes(const u64* children, const T* values, const u64* cell, int ld, int max_mat, u64* ids,
@@ -44,20 +44,33 @@ static int run_planes(const u64* children, const T* values, const u64* cell, int
     for (int plane = 0; plane < 3; ++plane) {
         std::vector<uint32_t> g(OCC_HALVES, 0);
         std::vector<std::vector<uint32_t>> mats;
+        auto slot_of = [&](T v) {
+            const u64 id = occ_material_of<T>(v);
+            size_t slot = 0;
+            while (slot < seen.size() && seen[slot] != id) ++slot;
+            if (slot == seen.size()) seen.push_back(id), vol.push_back(0);
+            if (mats.size() <= slot) mats.resize(slot + 1, std::vector<uint32_t>(OCC_HALVES, 0));
+            return slot;
+        };
         for (u32 item = 0; item < occ_items_per_builder(ld); ++item)
-            occ_walk_item<T>(children, values, cell, ld, item, [&](T v, u32 x, u32 y, u32 z, u32 ls) {
-                const u64 id = occ_material_of<T>(v);
-                size_t slot = 0;
-                while (slot < seen.size() && seen[slot] != id) ++slot;
-                if (slot == seen.size()) seen.push_back(id), vol.push_back(0);
-                if (mats.size() <= slot) mats.resize(slot + 1, std::vector<uint32_t>(OCC_HALVES, 0));
-                if (plane == 0) vol[slot] += u64(1) << (3 * ls);
-                auto orfn = [&](u32 i, u32 bits) { g[i] |= bits, mats[slot][i] |= bits; };
-                if (ls >= 3)
-                    for (u32 lane = 0; lane < 32; ++lane) occ_region_words(plane, x, y, z, ls, lane, 32, orfn);
-                else
-                    occ_region_words(plane, x, y, z, ls, 0, 1, orfn);
-            });
+            occ_walk_item<T>(
+                children, values, cell, ld, item,
+                [&](T v, u32 x, u32 y, u32 z, u32 ls) {
+                    const size_t slot = slot_of(v);
+                    if (plane == 0) vol[slot] += u64(1) << (3 * ls);
+                    auto orfn = [&](u32 i, u32 bits) { g[i] |= bits, mats[slot][i] |= bits; };
+                    if (ls >= 3)
+                        for (u32 lane = 0; lane < 32; ++lane) occ_region_words(plane, x, y, z, ls, lane, 32, orfn);
+                    else
+                        occ_region_words(plane, x, y, z, ls, 0, 1, orfn);
+                },
+                [&](const T* v, u32 x, u32 y, u32 z) {
+                    occ_block_words<T>(plane, x, y, z, v, [&](T val, u32 i, u32 bits) {
+                        const size_t slot = slot_of(val);
+                        if (plane == 0) vol[slot] += u64(__builtin_popcount(bits));
+                        g[i] |= bits, mats[slot][i] |= bits;
+                    });
+                });
         mats.resize(seen.size(), std::vector<uint32_t>(OCC_HALVES, 0));
         if (int(seen.size()) > max_mat) return -1;
         std::vector<size_t> order(seen.size());

@@ -1918,7 +1918,7 @@ int vx_occupancy_masks(const vx_interner* cit, uint8_t max_depth, uint8_t lod, s
     CU_TRY(cudaMemcpyAsync(d_cells, cells.data(), ncell * 8, cudaMemcpyHostToDevice, s));
     // 1. shared-memory path: every builder with <= ms materials (vx_occupancy.cuh: occ_planes_kernel)
     const int ms = int(std::min<uint32_t>(max_materials, OCC_MS_MAX));
-    const size_t smem = size_t(1 + ms) * OCC_HALVES * 4;
+    const size_t smem = size_t(std::max(ms, 1)) * OCC_HALVES * 4;  // <= 3 materials: two CTAs per SM
     const dim3 grid_planes(3, unsigned(n_builders));
     if (it->dtype == VX_U8) {
         CU_TRY(cudaFuncSetAttribute(occ_planes_kernel<u8>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));

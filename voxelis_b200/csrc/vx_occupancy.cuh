@@ -301,45 +301,21 @@ occ_masks_kernel(const u64* __restrict__ children, const T* __restrict__ values,
 // ---------------------------------------------------------------------------------------------------------
 // Shared-memory path: builders with at most `ms` (<= 5) materials — the mesher's normal case.
 //
-// One CTA per (builder, plane) keeps the plane of the builder in shared memory: 32 KiB for the global plane +
-// 32 KiB per material.  The DAG is walked in MORTON order, node by node (not row by row): a node standing at
-// depth k answers 8^(depth-k) voxels at once, so every tree node of the builder is visited once per plane and
-// ORs its side^2 words (32-bit shared atomics: an aligned run of <= 32 bits lives in one half word).  Regions of
-// side >= 8 are queued and filled by whole warps.  Materials take slots in the order the CTA meets them; the
-// planes leave in id order (build(), mesh.rs:263-285) through a permutation applied while they are streamed out
-// with 16-byte coalesced stores — each output byte is written exactly once, nothing is read back from HBM.
+// One CTA per (builder, plane) keeps the builder's per-material planes of that axis in shared memory (32 KiB per
+// material; the global plane is their OR and is formed while streaming out).  The DAG is walked in MORTON order,
+// node by node instead of row by row: a node standing at depth k answers 8^(depth-k) voxels at once, so every
+// tree node of the builder is visited once per plane.  A branch one level above the voxels is handled as a whole
+// block: its 8 child ids and their 8 values are fetched as independent loads and the two voxels that share a word
+// leave as one 32-bit shared atomic when they agree.  Cubes of side 2 / 4 OR their side^2 half words directly
+// (an aligned run of <= 32 bits lives in one half word); cubes of side >= 8 are queued and filled by whole warps.
+// Warps draw 32 Morton-consecutive items (4^3 voxels each) at a time from a CTA counter, so the surface-crossing
+// parts of the volume spread over all warps.  Materials take slots in the order the CTA meets them; the planes
+// leave in id order (build(), mesh.rs:263-285) through a permutation applied while they are streamed out with
+// 16-byte coalesced stores — each output byte is written exactly once, nothing is read back from HBM.
 // The YZ CTA also delivers the material list and voxel counts; every CTA stores its two global_active words.
 // A builder with more than `ms` materials is flagged in overflow[] and left to the word-owner kernels above.
 
-// Walk the Morton range [m0, m0 + len) of the tree `root` (len = 8^k, m0 aligned to len): visit(node, d, start)
-// for every maximal node (leaf, empty, or branch standing at depth ld) — `start` = first Morton index it covers
-// (<= m0 only for the first one, when the range lies inside a bigger node).
-template <class F>
-__host__ __device__ __forceinline__ void occ_walk_morton(const u64* __restrict__ children, u64 root, int ld, u32 m0,
-                                                         u32 len, F visit) {
-    u64 path[7];
-    path[0] = root;
-    u32 m = m0;
-    const u32 end = m0 + len;
-    bool first = true;
-    while (m < end) {
-        int d = first ? 0 : ld - 1 - (VX_OCC_FFS(int(m)) - 1) / 3;
-        u64 node = path[d];
-        while (node != 0 && !id_is_leaf(node) && d < ld) {
-            const int ci = int(m >> (3 * (ld - 1 - d))) & 7;
-            node = VX_OCC_LD(&children[size_t(id_index(node)) * 8 + ci]);
-            ++d;
-            path[d] = node;
-        }
-        const u32 span = 1u << (3 * (ld - d));
-        const u32 start = m & ~(span - 1);
-        visit(node, d, start);
-        m = start + span;
-        first = false;
-    }
-}
-
-__host__ __device__ __forceinline__ u32 occ_compact3(u32 v) {  // every third bit of a Morton index (<= 6 bits out)
+__host__ __device__ __forceinline__ u32 occ_compact3(u32 v) {  // every third bit of a Morton index (<= 10 bits out)
     v &= 0x09249249u;
     v = (v | (v >> 2)) & 0x030C30C3u;
     v = (v | (v >> 4)) & 0x0300F00Fu;
@@ -348,7 +324,63 @@ __host__ __device__ __forceinline__ u32 occ_compact3(u32 v) {  // every third bi
     return v;
 }
 
-// OR the cube (x, y, z, side) into one plane held as 32-bit half words: half word 2*w + (bit >> 5) of word w.
+// Item `item` of a builder = 8^min(ld,2) Morton positions of one cell.  For every maximal non-default node the
+// item owns: cube(value, x, y, z, ls) — x, y, z in builder voxels, side 2^ls; a node bigger than the item belongs
+// to the item that starts it.  A branch at depth ld - 1 is delivered whole: block(v[8], x, y, z) with
+// v[dx | dy<<1 | dz<<2] the value of voxel (x+dx, y+dy, z+dz), default where the child is empty.
+template <class T, class Cube, class Block>
+__host__ __device__ __forceinline__ void occ_walk_item(const u64* __restrict__ children, const T* __restrict__ values,
+                                                       const u64* __restrict__ cell, int ld, u32 item, Cube cube,
+                                                       Block block) {
+    const int gsh = 6 - ld, G = 1 << gsh;
+    const int isz_log = 3 * (ld < 2 ? ld : 2);
+    const u32 ipc_log = u32(3 * ld - isz_log);                  // items per cell (log2)
+    const u32 c = item >> ipc_log, m0 = (item & ((1u << ipc_log) - 1)) << isz_log;
+    const u64 root = VX_OCC_LD(&cell[c]);
+    if (root == 0) return;
+    const u32 ox = (c & (G - 1)) << ld, oz = ((c >> gsh) & (G - 1)) << ld, oy = (c >> (2 * gsh)) << ld;
+    u64 path[7];
+    path[0] = root;
+    u32 m = m0;
+    const u32 end = m0 + (1u << isz_log);
+    bool first = true;
+    while (m < end) {
+        int d = first ? 0 : ld - 1 - (VX_OCC_FFS(int(m)) - 1) / 3;  // deepest stored ancestor still containing m
+        u64 node = path[d];
+        while (node != 0 && !id_is_leaf(node) && d < ld - 1) {
+            const int ci = int(m >> (3 * (ld - 1 - d))) & 7;
+            node = VX_OCC_LD(&children[size_t(id_index(node)) * 8 + ci]);
+            ++d;
+            path[d] = node;
+        }
+        first = false;
+        if (node != 0 && !id_is_leaf(node) && d == ld - 1) {    // a block: 8 voxel-level children at once
+            const u64* row = &children[size_t(id_index(node)) * 8];
+            u64 ch[8];
+            T v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ch[i] = VX_OCC_LD(&row[i]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = ch[i] != 0 ? values[id_index(ch[i])] : T(0);
+            const u32 start = m & ~7u;
+            block(v, ox + occ_compact3(start), oy + occ_compact3(start >> 1), oz + occ_compact3(start >> 2));
+            m = start + 8;
+            continue;
+        }
+        const u32 span = 1u << (3 * (ld - d));
+        const u32 start = m & ~(span - 1);
+        m = start + span;
+        if (node == 0 || start < m0) continue;
+        const T v = values[id_index(node)];
+        if (v == T(0)) continue;
+        cube(v, ox + occ_compact3(start), oy + occ_compact3(start >> 1), oz + occ_compact3(start >> 2), u32(ld - d));
+    }
+}
+__host__ __device__ inline u32 occ_items_per_builder(int ld) {
+    return u32(1) << (3 * (6 - ld) + 3 * ld - 3 * (ld < 2 ? ld : 2));
+}
+
+// OR the cube (x, y, z, side 2^ls) into one plane held as 32-bit half words: half word 2*w + (bit >> 5) of word w.
 // or32(index, bits) does the OR (a shared atomic on the device, a plain OR in the host stepping test).
 template <class F>
 __host__ __device__ __forceinline__ void occ_region_words(int plane, u32 x, u32 y, u32 z, u32 ls, u32 k0,
@@ -368,33 +400,93 @@ __host__ __device__ __forceinline__ void occ_region_words(int plane, u32 x, u32 
     }
 }
 
-// Item `item` of a builder = 8^min(ld,2) Morton positions of one cell: emit(value, x, y, z, ls) for every maximal
-// non-default node the item owns (x, y, z in builder voxels, side 2^ls).  A node bigger than the item belongs to
-// the item that starts it.
-template <class T, class Emit>
-__host__ __device__ __forceinline__ void occ_walk_item(const u64* __restrict__ children, const T* __restrict__ values,
-                                                       const u64* __restrict__ cell, int ld, u32 item, Emit emit) {
-    const int gsh = 6 - ld, G = 1 << gsh;
-    const int isz_log = 3 * (ld < 2 ? ld : 2);
-    const u32 ipc_log = u32(3 * ld - isz_log);                  // items per cell (log2)
-    const u32 c = item >> ipc_log, m0 = (item & ((1u << ipc_log) - 1)) << isz_log;
-    const u64 root = VX_OCC_LD(&cell[c]);
-    if (root == 0) return;
-    const u32 ox = (c & (G - 1)) << ld, oz = ((c >> gsh) & (G - 1)) << ld, oy = (c >> (2 * gsh)) << ld;
-    occ_walk_morton(children, root, ld, m0, 1u << isz_log, [&](u64 node, int d, u32 start) {
-        if (node == 0 || start < m0) return;
-        const T v = values[id_index(node)];
-        if (v == T(0)) return;
-        emit(v, ox + occ_compact3(start), oy + occ_compact3(start >> 1), oz + occ_compact3(start >> 2), u32(ld - d));
-    });
-}
-__host__ __device__ inline u32 occ_items_per_builder(int ld) {
-    return u32(1) << (3 * (6 - ld) + 3 * ld - 3 * (ld < 2 ? ld : 2));
+// The 8 voxels of a block -> 4 half words of one plane; the two voxels along the bit axis share a half word and
+// leave together when they hold the same material.  orv(value, index, bits).
+template <class T, class F>
+__host__ __device__ __forceinline__ void occ_block_words(int plane, u32 x, u32 y, u32 z, const T* v, F orv) {
+    const u32 rb = plane == 0 ? x : plane == 1 ? y : z;         // even: the pair sits at bits rb, rb + 1
+    const u32 half = (rb >> 5) & 1, sh = rb & 31;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        if ((i >> plane) & 1) continue;                         // i = the voxel of the pair at bit rb
+        const int j = i | (1 << plane);
+        const u32 dx = i & 1, dy = (i >> 1) & 1, dz = i >> 2;
+        const u32 r0 = plane == 1 ? z + dz : y + dy, r1 = plane == 0 ? z + dz : x + dx;
+        const u32 idx = 2 * (r0 * 64 + r1) + half;
+        if (v[i] != T(0) && v[i] == v[j]) {
+            orv(v[i], idx, 3u << sh);
+        } else {
+            if (v[i] != T(0)) orv(v[i], idx, 1u << sh);
+            if (v[j] != T(0)) orv(v[j], idx, 2u << sh);
+        }
+    }
 }
 
 constexpr int OCC_MS_MAX = 5;        // materials per builder on the shared-memory path
-constexpr int OCC_QUEUE = 512;       // regions of side >= 8 in one 64^3 volume
+constexpr int OCC_QUEUE = 512;       // cubes of side >= 8 in one 64^3 volume
 constexpr int OCC_HALVES = 2 * OCC_PLANE;  // u32 half words per plane
+
+template <class T, int PLANE>
+__device__ __forceinline__ void occ_planes_body(const u64* __restrict__ children, const T* __restrict__ values,
+                                                const u64* __restrict__ cell, int ld, int ms, u32* planes,
+                                                u32* s_mat, u32* s_cnt, u32* s_queue, u32* s_qn, u32* s_over,
+                                                u32* s_next) {
+    const int lane = threadIdx.x & 31;
+    const u32 items = occ_items_per_builder(ld);
+    T last_v = T(0);
+    int last_slot = -1;
+    u32 cnt_acc = 0;
+    auto slot_of = [&](T v) -> int {                             // slot of the material, claimed on first sight
+        if (v == last_v) return last_slot;
+        if (PLANE == 0 && cnt_acc && last_slot >= 0) atomicAdd(&s_cnt[last_slot], cnt_acc);
+        cnt_acc = 0;
+        const u32 key = sizeof(T) == 1 ? (u32(v) & 0xFFu) : u32(v);
+        int slot = -1;
+        for (int k = 0; k < ms && slot < 0; ++k) {
+            u32 cur = s_mat[k];
+            if (cur == 0) {
+                const u32 prev = atomicCAS(&s_mat[k], 0u, key);
+                cur = prev == 0 ? key : prev;
+            }
+            if (cur == key) slot = k;
+        }
+        if (slot < 0) *s_over = 1;
+        last_v = v;
+        last_slot = slot;
+        return slot;
+    };
+    for (;;) {
+        u32 base = 0;
+        if (lane == 0) base = atomicAdd(s_next, 32u);
+        base = __shfl_sync(FULL, base, 0);
+        if (base >= items) break;
+        const u32 item = base + lane;
+        if (item >= items) continue;
+        occ_walk_item<T>(
+            children, values, cell, ld, item,
+            [&](T v, u32 x, u32 y, u32 z, u32 ls) {
+                const int slot = slot_of(v);
+                if (slot < 0) return;
+                if (PLANE == 0) cnt_acc += 1u << (3 * ls);
+                if (ls >= 3) {                                  // side >= 8: filled by whole warps after the walk
+                    const u32 q = atomicAdd(s_qn, 1u);
+                    if (q < OCC_QUEUE) s_queue[q] = x | (y << 6) | (z << 12) | (ls << 18) | (u32(slot) << 21);
+                    return;
+                }
+                u32* pmat = planes + size_t(slot) * OCC_HALVES;
+                occ_region_words(PLANE, x, y, z, ls, 0, 1, [&](u32 i, u32 bits) { atomicOr(&pmat[i], bits); });
+            },
+            [&](const T* v, u32 x, u32 y, u32 z) {
+                occ_block_words<T>(PLANE, x, y, z, v, [&](T val, u32 i, u32 bits) {
+                    const int slot = slot_of(val);
+                    if (slot < 0) return;
+                    if (PLANE == 0) cnt_acc += u32(__popc(bits));
+                    atomicOr(&planes[size_t(slot) * OCC_HALVES + i], bits);
+                });
+            });
+    }
+    if (PLANE == 0 && cnt_acc && last_slot >= 0) atomicAdd(&s_cnt[last_slot], cnt_acc);
+}
 
 template <class T>
 __global__ void __launch_bounds__(1024)
@@ -403,54 +495,24 @@ occ_planes_kernel(const u64* __restrict__ children, const T* __restrict__ values
                   u64* __restrict__ material_counts, u64* __restrict__ global, u64* __restrict__ active,
                   u64* __restrict__ per_material, u32* __restrict__ overflow, u32* __restrict__ overflow_count) {
     extern __shared__ uint4 occ_smem[];
-    u32* planes = reinterpret_cast<u32*>(occ_smem);  // [1 + ms][OCC_HALVES]: global plane, then one per slot
+    u32* planes = reinterpret_cast<u32*>(occ_smem);  // [ms][OCC_HALVES]: one plane per material slot
     __shared__ u32 s_mat[OCC_MS_MAX];                // raw value bits of the material in each slot, 0 = free
     __shared__ u32 s_cnt[OCC_MS_MAX];
     __shared__ u32 s_queue[OCC_QUEUE];
-    __shared__ u32 s_qn, s_over, s_act[2];
+    __shared__ u32 s_qn, s_over, s_next, s_act[2];
     __shared__ int s_order[OCC_MS_MAX], s_n;
     const int plane = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, nthr = blockDim.x;
     const u64* cell = cells + (size_t(b) << (3 * (6 - ld)));
-    for (int i = tid; i < (1 + ms) * (OCC_HALVES / 4); i += nthr) occ_smem[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < ms * (OCC_HALVES / 4); i += nthr) occ_smem[i] = make_uint4(0, 0, 0, 0);
     if (tid < OCC_MS_MAX) s_mat[tid] = 0, s_cnt[tid] = 0;
-    if (tid == 0) s_qn = 0, s_over = 0, s_act[0] = 0, s_act[1] = 0;
+    if (tid == 0) s_qn = 0, s_over = 0, s_next = 0, s_act[0] = 0, s_act[1] = 0;
     __syncthreads();
-
-    const u32 items = occ_items_per_builder(ld);
-    T last_v = T(0);
-    int last_slot = -1;
-    for (u32 item = tid; item < items; item += nthr)
-        occ_walk_item<T>(children, values, cell, ld, item, [&](T v, u32 x, u32 y, u32 z, u32 ls) {
-            if (v != last_v) {                                  // slot of the material, claimed on first sight
-                const u32 key = sizeof(T) == 1 ? (u32(v) & 0xFFu) : u32(v);
-                int slot = -1;
-                for (int k = 0; k < ms && slot < 0; ++k) {
-                    u32 cur = s_mat[k];
-                    if (cur == 0) {
-                        const u32 prev = atomicCAS(&s_mat[k], 0u, key);
-                        cur = prev == 0 ? key : prev;
-                    }
-                    if (cur == key) slot = k;
-                }
-                last_v = v;
-                last_slot = slot;
-                if (slot < 0) s_over = 1;
-            }
-            const int slot = last_slot;
-            if (slot < 0) return;
-            if (plane == 0) atomicAdd(&s_cnt[slot], 1u << (3 * ls));
-            if (ls >= 3) {                                      // side >= 8: filled by whole warps after the walk
-                const u32 q = atomicAdd(&s_qn, 1u);
-                if (q < OCC_QUEUE) s_queue[q] = x | (y << 6) | (z << 12) | (ls << 18) | (u32(slot) << 21);
-                return;
-            }
-            u32* pg = planes;
-            u32* pmat = planes + size_t(1 + slot) * OCC_HALVES;
-            occ_region_words(plane, x, y, z, ls, 0, 1, [&](u32 i, u32 bits) {
-                atomicOr(&pg[i], bits);
-                atomicOr(&pmat[i], bits);
-            });
-        });
+    if (plane == 0)
+        occ_planes_body<T, 0>(children, values, cell, ld, ms, planes, s_mat, s_cnt, s_queue, &s_qn, &s_over, &s_next);
+    else if (plane == 1)
+        occ_planes_body<T, 1>(children, values, cell, ld, ms, planes, s_mat, s_cnt, s_queue, &s_qn, &s_over, &s_next);
+    else
+        occ_planes_body<T, 2>(children, values, cell, ld, ms, planes, s_mat, s_cnt, s_queue, &s_qn, &s_over, &s_next);
     __syncthreads();
     if (s_over) {                                               // too many materials for shared memory
         if (tid == 0 && plane == 0) {
@@ -464,13 +526,9 @@ occ_planes_kernel(const u64* __restrict__ children, const T* __restrict__ values
         const int warp = tid >> 5, lane = tid & 31, nwarp = nthr >> 5;
         for (u32 q = warp; q < qn; q += nwarp) {
             const u32 e = s_queue[q];
-            u32* pg = planes;
-            u32* pmat = planes + size_t(1 + (e >> 21)) * OCC_HALVES;
+            u32* pmat = planes + size_t(e >> 21) * OCC_HALVES;
             occ_region_words(plane, e & 63, (e >> 6) & 63, (e >> 12) & 63, (e >> 18) & 7, lane, 32,
-                             [&](u32 i, u32 bits) {
-                                 atomicOr(&pg[i], bits);
-                                 atomicOr(&pmat[i], bits);
-                             });
+                             [&](u32 i, u32 bits) { atomicOr(&pmat[i], bits); });
         }
     }
     if (tid == 0) {                                             // build(): materials in id order
@@ -495,20 +553,20 @@ occ_planes_kernel(const u64* __restrict__ children, const T* __restrict__ values
         material_ids[size_t(b) * max_materials + tid] = occ_material_of<T>(T(s_mat[k]));
         material_counts[size_t(b) * max_materials + tid] = s_cnt[k];
     }
-    // stream the planes out: 16 bytes per thread and step, global plane first, then the materials in id order
+    // stream the planes out, 16 bytes per thread and step: the materials in id order, and their OR = the global plane
     u32 alo = 0, ahi = 0;
     uint4* gout = reinterpret_cast<uint4*>(global + size_t(b) * OCC_ALL + size_t(plane) * OCC_PLANE);
     for (int i = tid; i < OCC_HALVES / 4; i += nthr) {
-        const uint4 v = occ_smem[i];
-        alo |= v.x | v.z;
-        ahi |= v.y | v.w;
-        gout[i] = v;
-    }
-    for (int r = 0; r < n; ++r) {
-        const uint4* src = occ_smem + size_t(1 + s_order[r]) * (OCC_HALVES / 4);
-        uint4* dst = reinterpret_cast<uint4*>(per_material + (size_t(b) * max_materials + r) * OCC_ALL +
-                                              size_t(plane) * OCC_PLANE);
-        for (int i = tid; i < OCC_HALVES / 4; i += nthr) dst[i] = src[i];
+        uint4 g = make_uint4(0, 0, 0, 0);
+        for (int r = 0; r < n; ++r) {
+            const uint4 v = occ_smem[size_t(s_order[r]) * (OCC_HALVES / 4) + i];
+            reinterpret_cast<uint4*>(per_material + (size_t(b) * max_materials + r) * OCC_ALL +
+                                     size_t(plane) * OCC_PLANE)[i] = v;
+            g.x |= v.x, g.y |= v.y, g.z |= v.z, g.w |= v.w;
+        }
+        gout[i] = g;
+        alo |= g.x | g.z;
+        ahi |= g.y | g.w;
     }
     // global_active (mesh.rs:451-461): the OR of every word of this plane = the mask of its bit axis
 #pragma unroll
