@@ -11,6 +11,65 @@
 
 using namespace vx;
 
+// Morton enumeration of a builder's maximal nodes (host side of the test only): drives occ_region_words and
+// occ_block_words, the index functions the shared-memory kernel scatters with.
+// Item `item` of a builder = 8^min(ld,2) Morton positions of one cell.  For every maximal non-default node the
+// item owns: cube(value, x, y, z, ls) — x, y, z in builder voxels, side 2^ls; a node bigger than the item belongs
+// to the item that starts it.  A branch at depth ld - 1 is delivered whole: block(v[8], x, y, z) with
+// v[dx | dy<<1 | dz<<2] the value of voxel (x+dx, y+dy, z+dz), default where the child is empty.
+template <class T, class Cube, class Block>
+__host__ __device__ __forceinline__ void occ_walk_item(const u64* __restrict__ children, const T* __restrict__ values,
+                                                       const u64* __restrict__ cell, int ld, u32 item, Cube cube,
+                                                       Block block) {
+    const int gsh = 6 - ld, G = 1 << gsh;
+    const int isz_log = 3 * (ld < 2 ? ld : 2);
+    const u32 ipc_log = u32(3 * ld - isz_log);                  // items per cell (log2)
+    const u32 c = item >> ipc_log, m0 = (item & ((1u << ipc_log) - 1)) << isz_log;
+    const u64 root = VX_OCC_LD(&cell[c]);
+    if (root == 0) return;
+    const u32 ox = (c & (G - 1)) << ld, oz = ((c >> gsh) & (G - 1)) << ld, oy = (c >> (2 * gsh)) << ld;
+    u64 path[7];
+    path[0] = root;
+    u32 m = m0;
+    const u32 end = m0 + (1u << isz_log);
+    bool first = true;
+    while (m < end) {
+        int d = first ? 0 : ld - 1 - (VX_OCC_FFS(int(m)) - 1) / 3;  // deepest stored ancestor still containing m
+        u64 node = path[d];
+        while (node != 0 && !id_is_leaf(node) && d < ld - 1) {
+            const int ci = int(m >> (3 * (ld - 1 - d))) & 7;
+            node = VX_OCC_LD(&children[size_t(id_index(node)) * 8 + ci]);
+            ++d;
+            path[d] = node;
+        }
+        first = false;
+        if (node != 0 && !id_is_leaf(node) && d == ld - 1) {    // a block: 8 voxel-level children at once
+            const u64* row = &children[size_t(id_index(node)) * 8];
+            u64 ch[8];
+            T v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ch[i] = VX_OCC_LD(&row[i]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = ch[i] != 0 ? values[id_index(ch[i])] : T(0);
+            const u32 start = m & ~7u;
+            block(v, ox + occ_compact3(start), oy + occ_compact3(start >> 1), oz + occ_compact3(start >> 2));
+            m = start + 8;
+            continue;
+        }
+        const u32 span = 1u << (3 * (ld - d));
+        const u32 start = m & ~(span - 1);
+        m = start + span;
+        if (node == 0 || start < m0) continue;
+        const T v = values[id_index(node)];
+        if (v == T(0)) continue;
+        cube(v, ox + occ_compact3(start), oy + occ_compact3(start >> 1), oz + occ_compact3(start >> 2), u32(ld - d));
+    }
+}
+__host__ __device__ inline u32 occ_items_per_builder(int ld) {
+    return u32(1) << (3 * (6 - ld) + 3 * ld - 3 * (ld < 2 ? ld : 2));
+}
+
+
 template <class T>
 static int run(const u64* children, const T* values, const u64* cell, int ld, int max_mat, u64* ids, u64* counts,
                u64* global, u64* pm) {

@@ -1916,43 +1916,47 @@ int vx_occupancy_masks(const vx_interner* cit, uint8_t max_depth, uint8_t lod, s
     u32* d_over_count = d_err + 1;
     CU_TRY(cudaMemsetAsync(d_err, 0, 8, s));
     CU_TRY(cudaMemcpyAsync(d_cells, cells.data(), ncell * 8, cudaMemcpyHostToDevice, s));
-    // 1. shared-memory path: every builder with <= ms materials (vx_occupancy.cuh: occ_planes_kernel)
+    // 1. shared-memory path: every builder with <= ms materials (vx_occupancy.cuh: occ_planes_kernel), chunks >= 8^3
     const int ms = int(std::min<uint32_t>(max_materials, OCC_MS_MAX));
-    const size_t smem = size_t(std::max(ms, 1)) * OCC_HALVES * 4;  // <= 3 materials: two CTAs per SM
-    const dim3 grid_planes(3, unsigned(n_builders));
-    if (it->dtype == VX_U8) {
-        CU_TRY(cudaFuncSetAttribute(occ_planes_kernel<u8>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        occ_planes_kernel<u8><<<grid_planes, 1024, smem, s>>>(it->dev.children, (const u8*)it->dev.values, d_cells, ld,
-                                                               ms, max_materials, d_nmat, d_ids, d_counts, d_global,
-                                                               d_active, d_pm, d_over, d_over_count);
-    } else {
-        CU_TRY(cudaFuncSetAttribute(occ_planes_kernel<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        occ_planes_kernel<int32_t><<<grid_planes, 1024, smem, s>>>(it->dev.children, (const int32_t*)it->dev.values,
-                                                                    d_cells, ld, ms, max_materials, d_nmat, d_ids,
-                                                                    d_counts, d_global, d_active, d_pm, d_over,
-                                                                    d_over_count);
+    u32 n_over = u32(n_builders);
+    const u32* d_only = nullptr;  // word-owner kernels: every builder
+    if (ld >= 3) {
+        const size_t smem = size_t(std::max(ms, 1)) * OCC_HALVES * 4;
+        const dim3 grid_planes(3, unsigned(n_builders));
+        if (it->dtype == VX_U8) {
+            CU_TRY(cudaFuncSetAttribute(occ_planes_kernel<u8>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+            occ_planes_kernel<u8><<<grid_planes, 1024, smem, s>>>(it->dev.children, (const u8*)it->dev.values, d_cells,
+                                                                   ld, ms, max_materials, d_nmat, d_ids, d_counts,
+                                                                   d_global, d_active, d_pm, d_over, d_over_count);
+        } else {
+            CU_TRY(cudaFuncSetAttribute(occ_planes_kernel<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+            occ_planes_kernel<int32_t><<<grid_planes, 1024, smem, s>>>(it->dev.children, (const int32_t*)it->dev.values,
+                                                                        d_cells, ld, ms, max_materials, d_nmat, d_ids,
+                                                                        d_counts, d_global, d_active, d_pm, d_over,
+                                                                        d_over_count);
+        }
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaMemcpyAsync(&n_over, d_over_count, 4, cudaMemcpyDeviceToHost, s));
+        CU_TRY(cudaStreamSynchronize(s));
+        d_only = d_over;
     }
-    CU_TRY(cudaGetLastError());
-    u32 n_over = 0;
-    CU_TRY(cudaMemcpyAsync(&n_over, d_over_count, 4, cudaMemcpyDeviceToHost, s));
-    CU_TRY(cudaStreamSynchronize(s));
     // 2. builders with more materials than fit in shared memory: word-owner kernels, only for the flagged ones
     if (n_over) {
         const dim3 grid_masks(OCC_ALL / 256, unsigned(n_builders));
         if (it->dtype == VX_U8) {
             occ_materials_kernel<u8><<<unsigned(n_builders), 256, 0, s>>>(it->dev.children, (const u8*)it->dev.values,
                                                                            d_cells, ld, max_materials, d_nmat, d_ids,
-                                                                           d_counts, d_active, d_err, d_over);
+                                                                           d_counts, d_active, d_err, d_only);
             occ_masks_kernel<u8><<<grid_masks, 256, 0, s>>>(it->dev.children, (const u8*)it->dev.values, d_cells, ld,
                                                              max_materials, d_nmat, d_ids, d_global, d_active, d_pm,
-                                                             d_over);
+                                                             d_only);
         } else {
             occ_materials_kernel<int32_t><<<unsigned(n_builders), 256, 0, s>>>(
                 it->dev.children, (const int32_t*)it->dev.values, d_cells, ld, max_materials, d_nmat, d_ids, d_counts,
-                d_active, d_err, d_over);
+                d_active, d_err, d_only);
             occ_masks_kernel<int32_t><<<grid_masks, 256, 0, s>>>(it->dev.children, (const int32_t*)it->dev.values,
                                                                   d_cells, ld, max_materials, d_nmat, d_ids, d_global,
-                                                                  d_active, d_pm, d_over);
+                                                                  d_active, d_pm, d_only);
         }
         CU_TRY(cudaGetLastError());
     }

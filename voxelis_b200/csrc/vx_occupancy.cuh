@@ -302,14 +302,13 @@ occ_masks_kernel(const u64* __restrict__ children, const T* __restrict__ values,
 // Shared-memory path: builders with at most `ms` (<= 5) materials — the mesher's normal case.
 //
 // One CTA per (builder, plane) keeps the builder's per-material planes of that axis in shared memory (32 KiB per
-// material; the global plane is their OR and is formed while streaming out).  The DAG is walked in MORTON order,
-// node by node instead of row by row: a node standing at depth k answers 8^(depth-k) voxels at once, so every
-// tree node of the builder is visited once per plane.  A branch one level above the voxels is handled as a whole
-// block: its 8 child ids and their 8 values are fetched as independent loads and the two voxels that share a word
-// leave as one 32-bit shared atomic when they agree.  Cubes of side 2 / 4 OR their side^2 half words directly
-// (an aligned run of <= 32 bits lives in one half word); cubes of side >= 8 are queued and filled by whole warps.
-// Warps draw 32 Morton-consecutive items (4^3 voxels each) at a time from a CTA counter, so the surface-crossing
-// parts of the volume spread over all warps.  Materials take slots in the order the CTA meets them; the planes
+// material; the global plane is their OR and is formed while streaming out).  The DAG is unfolded level by level,
+// node by node instead of row by row, with the frontier in shared memory: 8 lanes read the 64-byte child row of a
+// node (one child each), uniform cubes of side >= 8 are queued and later filled by whole warps (an aligned run
+// of <= 32 bits lives in one 32-bit half word), branches go to the next frontier.  Below the 4^3 nodes every lane
+// owns one 2^3 block: its 8 child ids and their 8 values are independent loads, and the two voxels that share a
+// half word leave as one shared atomic when they agree — all lanes run the same code, whatever the tree looks
+// like.  Needs depth - lod >= 3.  Materials take slots in the order the CTA meets them; the planes
 // leave in id order (build(), mesh.rs:263-285) through a permutation applied while they are streamed out with
 // 16-byte coalesced stores — each output byte is written exactly once, nothing is read back from HBM.
 // The YZ CTA also delivers the material list and voxel counts; every CTA stores its two global_active words.
@@ -322,62 +321,6 @@ __host__ __device__ __forceinline__ u32 occ_compact3(u32 v) {  // every third bi
     v = (v | (v >> 8)) & 0x030000FFu;
     v = (v | (v >> 16)) & 0x000003FFu;
     return v;
-}
-
-// Item `item` of a builder = 8^min(ld,2) Morton positions of one cell.  For every maximal non-default node the
-// item owns: cube(value, x, y, z, ls) — x, y, z in builder voxels, side 2^ls; a node bigger than the item belongs
-// to the item that starts it.  A branch at depth ld - 1 is delivered whole: block(v[8], x, y, z) with
-// v[dx | dy<<1 | dz<<2] the value of voxel (x+dx, y+dy, z+dz), default where the child is empty.
-template <class T, class Cube, class Block>
-__host__ __device__ __forceinline__ void occ_walk_item(const u64* __restrict__ children, const T* __restrict__ values,
-                                                       const u64* __restrict__ cell, int ld, u32 item, Cube cube,
-                                                       Block block) {
-    const int gsh = 6 - ld, G = 1 << gsh;
-    const int isz_log = 3 * (ld < 2 ? ld : 2);
-    const u32 ipc_log = u32(3 * ld - isz_log);                  // items per cell (log2)
-    const u32 c = item >> ipc_log, m0 = (item & ((1u << ipc_log) - 1)) << isz_log;
-    const u64 root = VX_OCC_LD(&cell[c]);
-    if (root == 0) return;
-    const u32 ox = (c & (G - 1)) << ld, oz = ((c >> gsh) & (G - 1)) << ld, oy = (c >> (2 * gsh)) << ld;
-    u64 path[7];
-    path[0] = root;
-    u32 m = m0;
-    const u32 end = m0 + (1u << isz_log);
-    bool first = true;
-    while (m < end) {
-        int d = first ? 0 : ld - 1 - (VX_OCC_FFS(int(m)) - 1) / 3;  // deepest stored ancestor still containing m
-        u64 node = path[d];
-        while (node != 0 && !id_is_leaf(node) && d < ld - 1) {
-            const int ci = int(m >> (3 * (ld - 1 - d))) & 7;
-            node = VX_OCC_LD(&children[size_t(id_index(node)) * 8 + ci]);
-            ++d;
-            path[d] = node;
-        }
-        first = false;
-        if (node != 0 && !id_is_leaf(node) && d == ld - 1) {    // a block: 8 voxel-level children at once
-            const u64* row = &children[size_t(id_index(node)) * 8];
-            u64 ch[8];
-            T v[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) ch[i] = VX_OCC_LD(&row[i]);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = ch[i] != 0 ? values[id_index(ch[i])] : T(0);
-            const u32 start = m & ~7u;
-            block(v, ox + occ_compact3(start), oy + occ_compact3(start >> 1), oz + occ_compact3(start >> 2));
-            m = start + 8;
-            continue;
-        }
-        const u32 span = 1u << (3 * (ld - d));
-        const u32 start = m & ~(span - 1);
-        m = start + span;
-        if (node == 0 || start < m0) continue;
-        const T v = values[id_index(node)];
-        if (v == T(0)) continue;
-        cube(v, ox + occ_compact3(start), oy + occ_compact3(start >> 1), oz + occ_compact3(start >> 2), u32(ld - d));
-    }
-}
-__host__ __device__ inline u32 occ_items_per_builder(int ld) {
-    return u32(1) << (3 * (6 - ld) + 3 * ld - 3 * (ld < 2 ? ld : 2));
 }
 
 // OR the cube (x, y, z, side 2^ls) into one plane held as 32-bit half words: half word 2*w + (bit >> 5) of word w.
@@ -426,19 +369,37 @@ constexpr int OCC_MS_MAX = 5;        // materials per builder on the shared-memo
 constexpr int OCC_QUEUE = 512;       // cubes of side >= 8 in one 64^3 volume
 constexpr int OCC_HALVES = 2 * OCC_PLANE;  // u32 half words per plane
 
-template <class T, int PLANE>
-__device__ __forceinline__ void occ_planes_body(const u64* __restrict__ children, const T* __restrict__ values,
-                                                const u64* __restrict__ cell, int ld, int ms, u32* planes,
-                                                u32* s_mat, u32* s_cnt, u32* s_queue, u32* s_qn, u32* s_over,
-                                                u32* s_next) {
-    const int lane = threadIdx.x & 31;
-    const u32 items = occ_items_per_builder(ld);
+template <class T>
+__global__ void __launch_bounds__(1024)
+occ_planes_kernel(const u64* __restrict__ children, const T* __restrict__ values, const u64* __restrict__ cells,
+                  int ld, int ms, u32 max_materials, u32* __restrict__ n_materials, u64* __restrict__ material_ids,
+                  u64* __restrict__ material_counts, u64* __restrict__ global, u64* __restrict__ active,
+                  u64* __restrict__ per_material, u32* __restrict__ overflow, u32* __restrict__ overflow_count) {
+    extern __shared__ uint4 occ_smem[];
+    u32* planes = reinterpret_cast<u32*>(occ_smem);  // [ms][OCC_HALVES]: one plane per material slot
+    __shared__ u32 f_idx[4096];                      // the 4^3 nodes (depth ld - 2) that are not empty
+    __shared__ u16 f_pos[4096];                      // x4 | y4 << 4 | z4 << 8 in units of 4 voxels; bit 15: a leaf
+    __shared__ u32 u_idx[2][512];                    // upper levels, ping-pong (<= 512 nodes of side >= 8)
+    __shared__ u16 u_pos[2][512];
+    __shared__ u32 s_mat[OCC_MS_MAX];                // raw value bits of the material in each slot, 0 = free
+    __shared__ u32 s_cnt[OCC_MS_MAX];
+    __shared__ u32 s_queue[OCC_QUEUE];
+    __shared__ u32 s_qn, s_over, s_nf, s_nu[2], s_act[2];
+    __shared__ int s_order[OCC_MS_MAX], s_n;
+    const int plane = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, nthr = blockDim.x;
+    const int gsh = 6 - ld, G = 1 << gsh;
+    const u64* cell = cells + (size_t(b) << (3 * gsh));
+    for (int i = tid; i < ms * (OCC_HALVES / 4); i += nthr) occ_smem[i] = make_uint4(0, 0, 0, 0);
+    if (tid < OCC_MS_MAX) s_mat[tid] = 0, s_cnt[tid] = 0;
+    if (tid == 0) s_qn = 0, s_over = 0, s_nf = 0, s_nu[0] = 0, s_nu[1] = 0, s_act[0] = 0, s_act[1] = 0;
+    __syncthreads();
+
     T last_v = T(0);
     int last_slot = -1;
     u32 cnt_acc = 0;
     auto slot_of = [&](T v) -> int {                             // slot of the material, claimed on first sight
         if (v == last_v) return last_slot;
-        if (PLANE == 0 && cnt_acc && last_slot >= 0) atomicAdd(&s_cnt[last_slot], cnt_acc);
+        if (plane == 0 && cnt_acc && last_slot >= 0) atomicAdd(&s_cnt[last_slot], cnt_acc);
         cnt_acc = 0;
         const u32 key = sizeof(T) == 1 ? (u32(v) & 0xFFu) : u32(v);
         int slot = -1;
@@ -450,69 +411,108 @@ __device__ __forceinline__ void occ_planes_body(const u64* __restrict__ children
             }
             if (cur == key) slot = k;
         }
-        if (slot < 0) *s_over = 1;
+        if (slot < 0) s_over = 1;
         last_v = v;
         last_slot = slot;
         return slot;
     };
-    for (;;) {
-        u32 base = 0;
-        if (lane == 0) base = atomicAdd(s_next, 32u);
-        base = __shfl_sync(FULL, base, 0);
-        if (base >= items) break;
-        const u32 item = base + lane;
-        if (item >= items) continue;
-        occ_walk_item<T>(
-            children, values, cell, ld, item,
-            [&](T v, u32 x, u32 y, u32 z, u32 ls) {
-                const int slot = slot_of(v);
-                if (slot < 0) return;
-                if (PLANE == 0) cnt_acc += 1u << (3 * ls);
-                if (ls >= 3) {                                  // side >= 8: filled by whole warps after the walk
-                    const u32 q = atomicAdd(s_qn, 1u);
-                    if (q < OCC_QUEUE) s_queue[q] = x | (y << 6) | (z << 12) | (ls << 18) | (u32(slot) << 21);
-                    return;
-                }
-                u32* pmat = planes + size_t(slot) * OCC_HALVES;
-                occ_region_words(PLANE, x, y, z, ls, 0, 1, [&](u32 i, u32 bits) { atomicOr(&pmat[i], bits); });
-            },
-            [&](const T* v, u32 x, u32 y, u32 z) {
-                occ_block_words<T>(PLANE, x, y, z, v, [&](T val, u32 i, u32 bits) {
-                    const int slot = slot_of(val);
-                    if (slot < 0) return;
-                    if (PLANE == 0) cnt_acc += u32(__popc(bits));
-                    atomicOr(&planes[size_t(slot) * OCC_HALVES + i], bits);
-                });
-            });
+    // a uniform cube of side 2^ls >= 8 at (x4, y4, z4) * 4: filled by whole warps after the walk
+    auto big_cube = [&](u64 id, u32 pos, u32 ls) {
+        const T v = values[id_index(id)];
+        if (v == T(0)) return;
+        const int slot = slot_of(v);
+        if (slot < 0) return;
+        cnt_acc += 1u << (3 * ls);
+        const u32 q = atomicAdd(&s_qn, 1u);
+        if (q < OCC_QUEUE)
+            s_queue[q] = ((pos & 15) << 2) | (((pos >> 4) & 15) << 8) | (((pos >> 8) & 15) << 14) | (ls << 18) |
+                         (u32(slot) << 21);
+    };
+    // 1. the cells' roots (depth 0, side 2^ld >= 8)
+    for (int c = tid; c < G * G * G; c += nthr) {
+        const u64 root = __ldg(&cell[c]);
+        if (root == 0) continue;
+        const u32 un = u32(ld - 2);                              // log2 of the cell side in units of 4 voxels
+        const u32 pos = ((c & (G - 1)) << un) | ((u32(c >> (2 * gsh)) << un) << 4) | ((((c >> gsh) & (G - 1)) << un) << 8);
+        if (id_is_leaf(root)) {
+            big_cube(root, pos, u32(ld));
+        } else {
+            const u32 q = atomicAdd(&s_nu[0], 1u);
+            u_idx[0][q] = id_index(root);
+            u_pos[0][q] = u16(pos);
+        }
     }
-    if (PLANE == 0 && cnt_acc && last_slot >= 0) atomicAdd(&s_cnt[last_slot], cnt_acc);
-}
-
-template <class T>
-__global__ void __launch_bounds__(1024)
-occ_planes_kernel(const u64* __restrict__ children, const T* __restrict__ values, const u64* __restrict__ cells,
-                  int ld, int ms, u32 max_materials, u32* __restrict__ n_materials, u64* __restrict__ material_ids,
-                  u64* __restrict__ material_counts, u64* __restrict__ global, u64* __restrict__ active,
-                  u64* __restrict__ per_material, u32* __restrict__ overflow, u32* __restrict__ overflow_count) {
-    extern __shared__ uint4 occ_smem[];
-    u32* planes = reinterpret_cast<u32*>(occ_smem);  // [ms][OCC_HALVES]: one plane per material slot
-    __shared__ u32 s_mat[OCC_MS_MAX];                // raw value bits of the material in each slot, 0 = free
-    __shared__ u32 s_cnt[OCC_MS_MAX];
-    __shared__ u32 s_queue[OCC_QUEUE];
-    __shared__ u32 s_qn, s_over, s_next, s_act[2];
-    __shared__ int s_order[OCC_MS_MAX], s_n;
-    const int plane = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, nthr = blockDim.x;
-    const u64* cell = cells + (size_t(b) << (3 * (6 - ld)));
-    for (int i = tid; i < ms * (OCC_HALVES / 4); i += nthr) occ_smem[i] = make_uint4(0, 0, 0, 0);
-    if (tid < OCC_MS_MAX) s_mat[tid] = 0, s_cnt[tid] = 0;
-    if (tid == 0) s_qn = 0, s_over = 0, s_next = 0, s_act[0] = 0, s_act[1] = 0;
     __syncthreads();
-    if (plane == 0)
-        occ_planes_body<T, 0>(children, values, cell, ld, ms, planes, s_mat, s_cnt, s_queue, &s_qn, &s_over, &s_next);
-    else if (plane == 1)
-        occ_planes_body<T, 1>(children, values, cell, ld, ms, planes, s_mat, s_cnt, s_queue, &s_qn, &s_over, &s_next);
-    else
-        occ_planes_body<T, 2>(children, values, cell, ld, ms, planes, s_mat, s_cnt, s_queue, &s_qn, &s_over, &s_next);
+    // 2. level by level down to the 4^3 nodes: 8 lanes per node, one child each (one 64-byte row per node)
+    for (int k = 0; k <= ld - 3; ++k) {
+        const int src = k & 1, dst = src ^ 1;
+        const u32 nsrc = s_nu[src];
+        const bool to_f = k + 1 == ld - 2;                      // the children are the 4^3 nodes
+        const u32 cls = u32(ld - k - 1);                         // log2 of the child side
+        for (u32 t = tid; t < nsrc * 8; t += nthr) {
+            const u32 e = t >> 3, ci = t & 7;
+            const u64 id = __ldg(&children[size_t(u_idx[src][e]) * 8 + ci]);
+            if (id == 0) continue;
+            const u32 un = cls - 2;
+            const u32 pos = u32(u_pos[src][e]) + (((ci & 1) << un) | ((((ci >> 1) & 1) << un) << 4) | (((ci >> 2) << un) << 8));
+            if (id_is_leaf(id) && !to_f) {
+                big_cube(id, pos, cls);
+            } else if (to_f) {
+                const u32 q = atomicAdd(&s_nf, 1u);
+                f_idx[q] = id_index(id);
+                f_pos[q] = u16(pos | (id_is_leaf(id) ? 0x8000u : 0u));
+            } else {
+                const u32 q = atomicAdd(&s_nu[dst], 1u);
+                u_idx[dst][q] = id_index(id);
+                u_pos[dst][q] = u16(pos);
+            }
+        }
+        __syncthreads();
+        if (tid == 0) s_nu[src] = 0;
+        __syncthreads();
+    }
+    // 3. one lane per 2^3 block of every 4^3 node: the block's 8 voxel values, then its 4 half words of this plane
+    {
+        const u32 nf = s_nf;
+        for (u32 t = tid; t < nf * 8; t += nthr) {
+            const u32 e = t >> 3, ci = t & 7;
+            const u32 pos = f_pos[e], idx4 = f_idx[e];
+            T v[8];
+            if (pos & 0x8000u) {                                // the whole 4^3 node is one leaf
+                const T vv = values[idx4];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = vv;
+            } else {
+                const u64 bid = __ldg(&children[size_t(idx4) * 8 + ci]);
+                if (bid == 0) continue;
+                if (id_is_leaf(bid)) {
+                    const T vv = values[id_index(bid)];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = vv;
+                } else {                                        // depth ld - 1: its children are the voxels
+                    const uint4* row = reinterpret_cast<const uint4*>(&children[size_t(id_index(bid)) * 8]);
+                    u64 ch[8];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint4 r = __ldg(row + i);
+                        ch[2 * i] = u64(r.x) | (u64(r.y) << 32);
+                        ch[2 * i + 1] = u64(r.z) | (u64(r.w) << 32);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = ch[i] != 0 ? values[id_index(ch[i])] : T(0);
+                }
+            }
+            const u32 x = ((pos & 15) << 2) + 2 * (ci & 1), y = (((pos >> 4) & 15) << 2) + 2 * ((ci >> 1) & 1),
+                      z = (((pos >> 8) & 15) << 2) + 2 * (ci >> 2);
+            occ_block_words<T>(plane, x, y, z, v, [&](T val, u32 i, u32 bits) {
+                const int slot = slot_of(val);
+                if (slot < 0) return;
+                cnt_acc += u32(__popc(bits));
+                atomicOr(&planes[size_t(slot) * OCC_HALVES + i], bits);
+            });
+        }
+    }
+    if (plane == 0 && cnt_acc && last_slot >= 0) atomicAdd(&s_cnt[last_slot], cnt_acc);
     __syncthreads();
     if (s_over) {                                               // too many materials for shared memory
         if (tid == 0 && plane == 0) {
