@@ -168,6 +168,75 @@ def run_reference(args):
     emit(line)
 
 
+def around_the_path(vx, dev, local_rank, peak):
+    """Headline world generated IN device memory (vx_terrain_*_device), built, and unfolded into the greedy mesher's
+    occupancy planes (vx_occupancy_masks, 2x2x2 chunks per 64^3 builder, device outputs).  CUDA events on the
+    interner's stream; occupancy is a synchronous call (host placement of the roots included), so it is wall time."""
+    import ctypes as C
+    import torch
+    from voxelis_b200 import workloads as wl
+    gx, gy, gz = GRID
+    N, B, n = 1 << DEPTH, 8 ** (DEPTH - 1), GRID[0] * GRID[1] * GRID[2]
+    it = vx.VoxInterner.with_memory_budget(BUDGET, vx.U8, local_rank)
+    st = torch.cuda.ExternalStream(it.stream, device=dev)
+    h = torch.empty((gx * N, gz * N), dtype=torch.int32, device=dev)
+    m = torch.empty((n, B, 2), dtype=torch.uint8, device=dev)
+    v = torch.empty((n, B, 8), dtype=torch.uint8, device=dev)
+    roots = torch.zeros(n, dtype=torch.int64, device=dev)
+    torch.cuda.synchronize()
+
+    def gen():
+        it.terrain_heights_device(gx * N, gz * N, h.data_ptr(), wl.SEED_BASE, gy * N)
+        it.terrain_batches_device(DEPTH, GRID, h.data_ptr(), m.data_ptr(), v.data_ptr(), True, 1)
+
+    def build():
+        it.reset_async()
+        it.apply_batches_device(DEPTH, n, m.data_ptr(), v.data_ptr(), roots.data_ptr())
+
+    def timed(f, reps=20):
+        for _ in range(3):
+            f()
+        it.sync()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(st)
+        for _ in range(reps):
+            f()
+        b.record(st)
+        it.sync()
+        return a.elapsed_time(b) / reps
+
+    ms_gen = timed(gen)
+    ms_both = timed(lambda: (gen(), build()))
+    hroots = roots.cpu().numpy().astype(np.uint64)
+    idx = np.arange(n)
+    cx, cy, cz = idx // (gy * gz), (idx // gz) % gy, idx % gz
+    bo = np.ascontiguousarray(((cx // 2) * (gy // 2) + cy // 2) * (gz // 2) + cz // 2, np.uint32)
+    offs = np.ascontiguousarray(np.stack([(cx % 2) * N, (cy % 2) * N, (cz % 2) * N], 1), np.uint32)
+    nb, M = n // 8, 2
+    outs = [torch.empty(s, dtype=t, device=dev) for s, t in (((nb, 3 * 4096), torch.int64), ((nb, 6), torch.int64),
+            ((nb,), torch.int32), ((nb, M), torch.int64), ((nb, M), torch.int64), ((nb, M, 3 * 4096), torch.int64))]
+    torch.cuda.synchronize()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+
+    def occ():
+        rc = vx.lib().vx_occupancy_masks(it.h, DEPTH, 0, n, p(hroots), p(offs), p(bo), nb, M,
+                                         *[C.c_void_p(t.data_ptr()) for t in outs])
+        if rc != 0:
+            raise RuntimeError(vx.lib().vx_last_error().decode())
+    occ()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        occ()
+    ms_occ = (time.perf_counter() - t0) / 5 * 1e3
+    gen_bytes = m.numel() + v.numel()
+    occ_bytes = int(nb * (3 * 4096 * 8 + 48) + int(outs[2].sum().item()) * 3 * 4096 * 8)
+    return {"world": "perlin 64x8x64 d5 u8 surface_only, generated on the device",
+            "generate_ms": ms_gen, "generate_gbs_written": gen_bytes / ms_gen / 1e6, "generate_frac_hbm": gen_bytes / ms_gen / 1e6 / peak,
+            "generate_plus_build_ms": ms_both, "generate_plus_build_chunks_per_s": n / ms_both * 1e3,
+            "occupancy_builders": nb, "occupancy_ms_wall": ms_occ, "occupancy_chunks_per_s": n / ms_occ * 1e3,
+            "occupancy_gbs_written": occ_bytes / ms_occ / 1e6, "occupancy_frac_hbm": occ_bytes / ms_occ / 1e6 / peak}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -454,6 +523,13 @@ def main():
                 del dm, dv, dr, it2
             except Exception as e:  # a secondary workload must never take the headline line down
                 others[name] = {"error": str(e)}
+
+        # the steps either side of the path, device-resident: batch generation before, mesher planes after
+        try:
+            log("secondary: device batch generation + occupancy planes")
+            others["around_the_path"] = around_the_path(vx, dev, local_rank, peak)
+        except Exception as e:
+            others["around_the_path"] = {"error": str(e)}
 
     # ---------------------------------------------------------------- global dedup variant (config 5)
     dedup_info = None

@@ -385,22 +385,34 @@ occ_planes_kernel(const u64* __restrict__ children, const T* __restrict__ values
     __shared__ u32 s_cnt[OCC_MS_MAX];
     __shared__ u32 s_queue[OCC_QUEUE];
     __shared__ u32 s_qn, s_over, s_nf, s_nu[2], s_act[2];
+    __shared__ u8 s_lut[256];                        // u8 values: slot + 1 of a material already met, 0 = not yet
     __shared__ int s_order[OCC_MS_MAX], s_n;
     const int plane = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, nthr = blockDim.x;
     const int gsh = 6 - ld, G = 1 << gsh;
     const u64* cell = cells + (size_t(b) << (3 * gsh));
     for (int i = tid; i < ms * (OCC_HALVES / 4); i += nthr) occ_smem[i] = make_uint4(0, 0, 0, 0);
     if (tid < OCC_MS_MAX) s_mat[tid] = 0, s_cnt[tid] = 0;
+    if (tid < 256) s_lut[tid] = 0;
     if (tid == 0) s_qn = 0, s_over = 0, s_nf = 0, s_nu[0] = 0, s_nu[1] = 0, s_act[0] = 0, s_act[1] = 0;
     __syncthreads();
 
     T last_v = T(0);
     int last_slot = -1;
-    u32 cnt_acc = 0;
+    u32 cnt[OCC_MS_MAX];                                         // voxels per slot seen by this thread (YZ CTA only)
+#pragma unroll
+    for (int k = 0; k < OCC_MS_MAX; ++k) cnt[k] = 0;
+    auto count = [&](int slot, u32 n) {
+#pragma unroll
+        for (int k = 0; k < OCC_MS_MAX; ++k)
+            if (k == slot) cnt[k] += n;
+    };
     auto slot_of = [&](T v) -> int {                             // slot of the material, claimed on first sight
-        if (v == last_v) return last_slot;
-        if (plane == 0 && cnt_acc && last_slot >= 0) atomicAdd(&s_cnt[last_slot], cnt_acc);
-        cnt_acc = 0;
+        if (sizeof(T) == 1) {
+            const int s = s_lut[u32(v) & 0xFFu];
+            if (s) return s - 1;
+        } else if (v == last_v) {
+            return last_slot;
+        }
         const u32 key = sizeof(T) == 1 ? (u32(v) & 0xFFu) : u32(v);
         int slot = -1;
         for (int k = 0; k < ms && slot < 0; ++k) {
@@ -412,6 +424,7 @@ occ_planes_kernel(const u64* __restrict__ children, const T* __restrict__ values
             if (cur == key) slot = k;
         }
         if (slot < 0) s_over = 1;
+        if (sizeof(T) == 1 && slot >= 0) s_lut[key] = u8(slot + 1);  // every writer stores the same byte
         last_v = v;
         last_slot = slot;
         return slot;
@@ -422,7 +435,7 @@ occ_planes_kernel(const u64* __restrict__ children, const T* __restrict__ values
         if (v == T(0)) return;
         const int slot = slot_of(v);
         if (slot < 0) return;
-        cnt_acc += 1u << (3 * ls);
+        if (plane == 0) count(slot, 1u << (3 * ls));
         const u32 q = atomicAdd(&s_qn, 1u);
         if (q < OCC_QUEUE)
             s_queue[q] = ((pos & 15) << 2) | (((pos >> 4) & 15) << 8) | (((pos >> 8) & 15) << 14) | (ls << 18) |
@@ -507,12 +520,20 @@ occ_planes_kernel(const u64* __restrict__ children, const T* __restrict__ values
             occ_block_words<T>(plane, x, y, z, v, [&](T val, u32 i, u32 bits) {
                 const int slot = slot_of(val);
                 if (slot < 0) return;
-                cnt_acc += u32(__popc(bits));
+                if (plane == 0) count(slot, u32(__popc(bits)));
                 atomicOr(&planes[size_t(slot) * OCC_HALVES + i], bits);
             });
         }
     }
-    if (plane == 0 && cnt_acc && last_slot >= 0) atomicAdd(&s_cnt[last_slot], cnt_acc);
+    if (plane == 0) {                                            // voxel counts: one shared atomic per warp and slot
+#pragma unroll
+        for (int k = 0; k < OCC_MS_MAX; ++k) {
+            u32 c = cnt[k];
+#pragma unroll
+            for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
+            if ((tid & 31) == 0 && c) atomicAdd(&s_cnt[k], c);
+        }
+    }
     __syncthreads();
     if (s_over) {                                               // too many materials for shared memory
         if (tid == 0 && plane == 0) {
