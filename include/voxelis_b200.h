@@ -205,6 +205,27 @@ int vx_terrain_heights_device(vx_interner*, uint32_t nx, uint32_t nz, uint64_t s
 int vx_terrain_batches_device(vx_interner*, uint8_t max_depth, const uint32_t grid[3], const int32_t* d_heights,
                               int surface_only, int materials, uint8_t* d_masks, void* d_values, void* stream);
 
+/* The voxeliser's two steps (voxelis-voxelize/src/lib.rs), SURVEY §8f-4:
+ *   vx_voxelize_plan           Voxelizer::build_face_to_chunk_map (:113-156), host work as in the reference: which faces
+ *                              (faces[nf][3], 1-based vertex indices, vertices[nv][3] f64) touch which chunk.  Returns
+ *                              the number of chunks and *n_pairs_out; positions_out[n][3] (chunks in first-seen order —
+ *                              the reference keeps a hash map) and the flat (chunk, face) pair lists are filled when
+ *                              the capacities suffice (call once with NULL outputs for the sizes).
+ *   vx_voxelize_chunks_device  Voxelizer::voxelize_chunk (:159-249) with triangle_cube_intersection
+ *                              (voxelis-math/src/lib.rs:3-214, f64, the reference's order of operations) for ALL planned
+ *                              chunks: zeroes and fills the device slab masks[n][B][2] / values[n][B][8] (value 1, of
+ *                              the interner's dtype) that vx_apply_batches_device reads; d_has_patches[n] (device, may
+ *                              be NULL) = Batch::has_patches — the reference drops chunks without patches (:245-249).
+ *                              Host arrays are copied in; the call synchronises. */
+int64_t vx_voxelize_plan(uint8_t max_depth, double chunk_world_size, const double mesh_min[3], size_t n_vertices,
+                         const double* vertices, size_t n_faces, const int32_t* faces, int32_t* positions_out,
+                         size_t cap_chunks, uint32_t* pair_chunk_out, uint32_t* pair_face_out, size_t cap_pairs,
+                         size_t* n_pairs_out);
+int vx_voxelize_chunks_device(vx_interner*, uint8_t max_depth, double chunk_world_size, const double mesh_min[3],
+                              size_t n_vertices, const double* vertices, size_t n_faces, const int32_t* faces,
+                              size_t n_chunks, const int32_t* positions, size_t n_pairs, const uint32_t* pair_chunk,
+                              const uint32_t* pair_face, uint8_t* d_masks, void* d_values, uint8_t* d_has_patches);
+
 /* VoxTree::get — voxtree.rs:144-160 -> get_at_depth utils/common.rs:122-156.
  * Returns 1 = Some(*out), 0 = None, VX_E_BOUNDS outside the chunk (reference: assert!). */
 int vx_tree_get(const vx_interner*, const vx_tree*, int x, int y, int z, int64_t* out);

@@ -83,6 +83,10 @@ def lib():
     L.orc_root_to_vec_lod.argtypes = [vp, C.c_uint64, C.c_int, C.c_int, vp]
     L.orc_occupancy_masks.restype = C.c_longlong
     L.orc_occupancy_masks.argtypes = [vp, C.c_size_t, vp, C.c_int, vp, vp, vp, C.c_size_t, vp, vp, vp]
+    for f in ("orc_point_in_or_on_cube", "orc_point_in_or_on_triangle", "orc_edge_quad_intersection",
+              "orc_triangle_cube_intersection"):
+        getattr(L, f).argtypes = [vp, vp]
+    L.orc_voxelize_chunk.argtypes = [C.c_int, vp, C.c_int, C.c_double, vp, C.c_size_t, vp, vp, vp, vp]
     L.orc_interner_ref.restype = C.c_uint32
     L.orc_interner_ref.argtypes = [vp, C.c_uint64]
     L.orc_interner_next_index.restype = C.c_uint32
@@ -104,6 +108,65 @@ def lib():
     L.orc_time_apply_fresh.argtypes = [C.c_int, C.c_int, C.c_size_t, C.c_size_t, vp, vp, C.c_int, vp]
     _lib = L
     return L
+
+
+def _f64(*vals):
+    return np.ascontiguousarray(np.array(vals, np.float64).ravel())
+
+
+def point_in_or_on_cube(p, cube):
+    """voxelis-math/src/lib.rs:129-151; cube = (min, max)."""
+    return bool(lib().orc_point_in_or_on_cube(_ptr(_f64(p)), _ptr(_f64(*cube))))
+
+
+def point_in_or_on_triangle(p, tri):
+    """voxelis-math/src/lib.rs:153-178."""
+    return bool(lib().orc_point_in_or_on_triangle(_ptr(_f64(p)), _ptr(_f64(*tri))))
+
+
+def edge_quad_intersection(edge, quad):
+    """voxelis-math/src/lib.rs:180-204."""
+    return bool(lib().orc_edge_quad_intersection(_ptr(_f64(*edge)), _ptr(_f64(*quad))))
+
+
+def triangle_cube_intersection(tri, cube):
+    """voxelis-math/src/lib.rs:3-127."""
+    return bool(lib().orc_triangle_cube_intersection(_ptr(_f64(*tri)), _ptr(_f64(*cube))))
+
+
+def face_chunk_map(depth, chunk_world_size, mesh_min, vertices, faces):
+    """Voxelizer::build_face_to_chunk_map (voxelis-voxelize/src/lib.rs:113-156) in plain Python: chunk position ->
+    list of face indices, chunks in first-seen order (the reference keeps a hash map)."""
+    vpa = 1 << depth
+    voxel_size = float(chunk_world_size) / vpa
+    inv = 1.0 / voxel_size
+    out = {}
+    v = np.asarray(vertices, np.float64) - np.asarray(mesh_min, np.float64)
+    for fi, f in enumerate(np.asarray(faces)):
+        tri = v[np.asarray(f) - 1]
+        lo = np.floor(tri.min(0) * inv).astype(np.int64)
+        hi = np.ceil(tri.max(0) * inv).astype(np.int64)
+        cl = np.sign(lo) * (np.abs(lo) // vpa)                      # IVec3 / i32 truncates toward zero
+        ch = np.sign(hi) * (np.abs(hi) // vpa)
+        for cy in range(cl[1], ch[1] + 1):
+            for cz in range(cl[2], ch[2] + 1):
+                for cx in range(cl[0], ch[0] + 1):
+                    out.setdefault((int(cx), int(cy), int(cz)), []).append(fi)
+    return out
+
+
+def voxelize_chunk(dtype, chunk_position, depth, chunk_world_size, mesh_min, faces, vertices):
+    """Voxelizer::voxelize_chunk (voxelis-voxelize/src/lib.rs:159-249) -> (has_patches, masks[B][2], values[B][8])."""
+    B = lib().orc_batch_blocks(depth)
+    masks = np.zeros((B, 2), np.uint8)
+    values = np.zeros((B, 8), _NP[dtype])
+    faces = np.ascontiguousarray(faces, np.int32).reshape(-1, 3)
+    vertices = np.ascontiguousarray(vertices, np.float64).reshape(-1, 3)
+    pos = np.ascontiguousarray(chunk_position, np.int32)
+    mm = np.ascontiguousarray(mesh_min, np.float64)
+    rc = _check(lib().orc_voxelize_chunk(dtype, _ptr(pos), depth, float(chunk_world_size), _ptr(mm), len(faces),
+                                         _ptr(faces), _ptr(vertices), _ptr(masks), _ptr(values)))
+    return bool(rc), masks, values
 
 
 class OracleError(RuntimeError):

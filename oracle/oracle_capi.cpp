@@ -251,6 +251,33 @@ long long orc_occupancy_masks(void* ih, size_t n, const uint64_t* roots, int dep
     return rc < 0 ? rc : out;
 }
 
+// voxelis-math known-answer entry points (tests/test_oracle_voxelize.py ports the crate's unit tests)
+int orc_point_in_or_on_cube(const double* p, const double* cube) {
+    return point_in_or_on_cube(dv(p[0], p[1], p[2]), dv(cube[0], cube[1], cube[2]), dv(cube[3], cube[4], cube[5]));
+}
+int orc_point_in_or_on_triangle(const double* p, const double* t) {
+    return point_in_or_on_triangle(dv(p[0], p[1], p[2]), dv(t[0], t[1], t[2]), dv(t[3], t[4], t[5]), dv(t[6], t[7], t[8]));
+}
+int orc_edge_quad_intersection(const double* e, const double* q) {
+    const DV3 quad[4] = {dv(q[0], q[1], q[2]), dv(q[3], q[4], q[5]), dv(q[6], q[7], q[8]), dv(q[9], q[10], q[11])};
+    return edge_quad_intersection(dv(e[0], e[1], e[2]), dv(e[3], e[4], e[5]), quad);
+}
+int orc_triangle_cube_intersection(const double* t, const double* cube) {
+    return triangle_cube_intersection(dv(t[0], t[1], t[2]), dv(t[3], t[4], t[5]), dv(t[6], t[7], t[8]),
+                                      dv(cube[0], cube[1], cube[2]), dv(cube[3], cube[4], cube[5]));
+}
+// Voxelizer::voxelize_chunk (voxelis-voxelize/src/lib.rs:159-249) into zeroed Batch arrays; returns has_patches
+int orc_voxelize_chunk(int dtype, const int* chunk_position, int depth, double chunk_world_size,
+                       const double* mesh_min, size_t nfaces, const int32_t* faces, const double* vertices,
+                       uint8_t* masks, void* values) {
+    return guarded([&] {
+        return int(dtype == 0 ? voxelize_chunk<u8>(chunk_position, depth, chunk_world_size, mesh_min, nfaces, faces,
+                                                    vertices, masks, (u8*)values)
+                              : voxelize_chunk<int32_t>(chunk_position, depth, chunk_world_size, mesh_min, nfaces, faces,
+                                                         vertices, masks, (int32_t*)values));
+    });
+}
+
 uint32_t orc_interner_ref(void* ih, uint64_t id) {
     AnyInterner* a = (AnyInterner*)ih;
     return a->dtype == 0 ? a->i8->get_ref(id) : a->i32->get_ref(id);

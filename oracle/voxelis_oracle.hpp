@@ -29,6 +29,7 @@
 #pragma once
 #include <algorithm>
 #include <array>
+#include <cmath>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -1120,6 +1121,148 @@ void generate_occupancy_masks(const Interner<T>& in, OccupancyBuilder& b, u64 ro
                                       mat(v));
         }
     }
+}
+
+
+// ---------------------------------------------------------------------------------
+// Voxeliser — triangle -> voxel tests that fill a Batch (the step before the path).
+//   voxelis-math/src/lib.rs:3-127     triangle_cube_intersection
+//                          :129-151   point_in_or_on_cube
+//                          :153-178   point_in_or_on_triangle
+//                          :180-204   edge_quad_intersection      :206-214 point_in_quad
+//   voxelis-voxelize/src/lib.rs:159-249   Voxelizer::voxelize_chunk
+// All arithmetic is f64 in the reference's order of operations; the vector helpers restate glam 0.29.3
+// (Cargo.lock; not vendored under /root/reference — "glam operation order: parity unpinned", pinned only through
+// the known answers of the reference's own voxelis-math unit tests, tests/test_oracle_voxelize.py):
+//   dot = x*x' + y*y' + z*z' (left to right), cross = (y*z' - y'*z, z*x' - z'*x, x*y' - x'*y),
+//   length = sqrt(dot(v, v)), normalize = v * (1 / length).  Built with -ffp-contract=off (oracle/Makefile).
+// ---------------------------------------------------------------------------------
+struct DV3 {
+    double x, y, z;
+};
+inline DV3 dv(double x, double y, double z) { return DV3{x, y, z}; }
+inline DV3 operator+(DV3 a, DV3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+inline DV3 operator-(DV3 a, DV3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline DV3 operator*(DV3 a, double s) { return {a.x * s, a.y * s, a.z * s}; }
+inline DV3 operator*(double s, DV3 a) { return {s * a.x, s * a.y, s * a.z}; }
+inline DV3 operator/(DV3 a, double s) { return {a.x / s, a.y / s, a.z / s}; }
+inline DV3 vmin(DV3 a, DV3 b) { return {a.x < b.x ? a.x : b.x, a.y < b.y ? a.y : b.y, a.z < b.z ? a.z : b.z}; }
+inline DV3 vmax(DV3 a, DV3 b) { return {a.x > b.x ? a.x : b.x, a.y > b.y ? a.y : b.y, a.z > b.z ? a.z : b.z}; }
+inline double vdot(DV3 a, DV3 b) { return (a.x * b.x) + (a.y * b.y) + (a.z * b.z); }
+inline DV3 vcross(DV3 a, DV3 b) { return {a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y}; }
+inline double vlength(DV3 a) { return std::sqrt(vdot(a, a)); }
+inline DV3 vnormalize(DV3 a) { return a * (1.0 / vlength(a)); }
+inline double f64_signum(double v) { return v != v ? v : (std::signbit(v) ? -1.0 : 1.0); }  // f64::signum
+
+inline bool point_in_or_on_cube(DV3 p, DV3 cmin, DV3 cmax) {  // voxelis-math lib.rs:129-151
+    const double cube_size = vlength(cmax - cmin);
+    const double epsilon = cube_size * 1e-8;
+    if (cube_size < 1e-8) return vlength(p - cmin) < epsilon;
+    return p.x >= cmin.x - epsilon && p.x <= cmax.x + epsilon && p.y >= cmin.y - epsilon && p.y <= cmax.y + epsilon &&
+           p.z >= cmin.z - epsilon && p.z <= cmax.z + epsilon;
+}
+
+inline bool point_in_or_on_triangle(DV3 p, DV3 a, DV3 b, DV3 c) {  // :153-178
+    const DV3 v0 = b - a, v1 = c - a, v2 = p - a;
+    const double dot00 = vdot(v0, v0), dot01 = vdot(v0, v1), dot02 = vdot(v0, v2), dot11 = vdot(v1, v1),
+                 dot12 = vdot(v1, v2);
+    const double denom = dot00 * dot11 - dot01 * dot01;
+    if (std::fabs(denom) < 1e-8) return false;
+    const double inv = 1.0 / denom;
+    const double u = (dot11 * dot02 - dot01 * dot12) * inv;
+    const double v = (dot00 * dot12 - dot01 * dot02) * inv;
+    return u >= 0.0 && v >= 0.0 && (u + v) <= 1.0;
+}
+
+inline bool point_in_quad(DV3 p, const DV3* q) {  // :206-214
+    return point_in_or_on_triangle(p, q[0], q[1], q[2]) || point_in_or_on_triangle(p, q[0], q[2], q[3]);
+}
+
+inline bool edge_quad_intersection(DV3 e1, DV3 e2, const DV3* q) {  // :180-204
+    const DV3 normal = vnormalize(vcross(q[1] - q[0], q[2] - q[0]));
+    const double denom = vdot(normal, e2 - e1);
+    if (std::fabs(denom) < 1e-8) return false;
+    const double t = vdot(normal, q[0] - e1) / denom;
+    if (!(t >= 0.0 && t <= 1.0)) return false;
+    return point_in_quad(e1 + t * (e2 - e1), q);
+}
+
+inline bool triangle_cube_intersection(DV3 tv0, DV3 tv1, DV3 tv2, DV3 cmin, DV3 cmax) {  // :3-127
+    const DV3 tri_min = vmin(vmin(tv0, tv1), tv2), tri_max = vmax(vmax(tv0, tv1), tv2);
+    const double epsilon = 1e-5;
+    if (tri_max.x < cmin.x - epsilon || tri_min.x > cmax.x + epsilon || tri_max.y < cmin.y - epsilon ||
+        tri_min.y > cmax.y + epsilon || tri_max.z < cmin.z - epsilon || tri_min.z > cmax.z + epsilon)
+        return false;
+    const DV3 normal = vcross(tv1 - tv0, tv2 - tv0);
+    const double d = -vdot(normal, tv0);
+    const DV3 cp[8] = {dv(cmin.x, cmin.y, cmin.z), dv(cmax.x, cmin.y, cmin.z), dv(cmax.x, cmax.y, cmin.z),
+                       dv(cmin.x, cmax.y, cmin.z), dv(cmin.x, cmin.y, cmax.z), dv(cmax.x, cmin.y, cmax.z),
+                       dv(cmax.x, cmax.y, cmax.z), dv(cmin.x, cmax.y, cmax.z)};
+    const double sign = f64_signum(vdot(normal, cp[0]) + d);
+    for (int i = 1; i < 8; ++i) {  // :41-50
+        const double s = vdot(normal, cp[i]) + d;
+        const double new_sign = f64_signum(s);
+        if (std::fabs(s) < epsilon) continue;
+        if (new_sign != sign) return true;
+    }
+    if (point_in_or_on_cube(tv0, cmin, cmax) || point_in_or_on_cube(tv1, cmin, cmax) ||
+        point_in_or_on_cube(tv2, cmin, cmax))
+        return true;  // :53-58
+    for (int i = 0; i < 8; ++i)
+        if (point_in_or_on_triangle(cp[i], tv0, tv1, tv2)) return true;  // :60-64
+    const DV3 edges[3][2] = {{tv0, tv1}, {tv1, tv2}, {tv2, tv0}};  // :67
+    const int fq[6][4] = {{0, 1, 2, 3}, {4, 5, 6, 7}, {0, 1, 5, 4}, {2, 3, 7, 6}, {0, 3, 7, 4}, {1, 2, 6, 5}};  // :68-111
+    for (int e = 0; e < 3; ++e)
+        for (int f = 0; f < 6; ++f) {
+            const DV3 q[4] = {cp[fq[f][0]], cp[fq[f][1]], cp[fq[f][2]], cp[fq[f][3]]};
+            if (edge_quad_intersection(edges[e][0], edges[e][1], q)) return true;
+        }
+    return false;
+}
+
+inline int f64_as_i32(double v) {  // Rust `as i32`: saturating, NaN -> 0
+    if (v != v) return 0;
+    if (v >= 2147483647.0) return 2147483647;
+    if (v <= -2147483648.0) return int(-2147483647 - 1);
+    return int(v);
+}
+
+// Voxelizer::voxelize_chunk — voxelis-voxelize/src/lib.rs:159-249.  faces[n][3] are 1-based vertex indices.
+// Returns batch.has_patches(); masks / values are the Batch<T> arrays (zeroed by the caller = Batch::new).
+template <class T>
+bool voxelize_chunk(const int* chunk_position, int depth, double chunk_world_size, const double* mesh_min_,
+                    size_t nfaces, const int32_t* faces, const double* vertices, u8* masks, T* values) {
+    const int vpa = 1 << depth;
+    const double voxel_size = chunk_world_size / double(vpa);  // voxelize_mesh :262
+    const double epsilon = voxel_size * 1e-7;
+    const DV3 splat = dv(epsilon, epsilon, epsilon);
+    const DV3 mesh_min = dv(mesh_min_[0], mesh_min_[1], mesh_min_[2]);
+    const DV3 cw_min = dv(double(chunk_position[0]), double(chunk_position[1]), double(chunk_position[2])) * chunk_world_size;
+    const DV3 cw_max = cw_min + dv(chunk_world_size, chunk_world_size, chunk_world_size);
+    bool has_patches = false;
+    auto vert = [&](int32_t i) { return dv(vertices[3 * size_t(i - 1)], vertices[3 * size_t(i - 1) + 1], vertices[3 * size_t(i - 1) + 2]); };
+    auto clampi = [&](int v) { return v < 0 ? 0 : v > vpa - 1 ? vpa - 1 : v; };
+    for (size_t f = 0; f < nfaces; ++f) {
+        const DV3 v1 = vert(faces[3 * f]) - mesh_min, v2 = vert(faces[3 * f + 1]) - mesh_min, v3 = vert(faces[3 * f + 2]) - mesh_min;
+        const DV3 face_min = vmin(vmin(v1, v2), v3), face_max = vmax(vmax(v1, v2), v3);
+        const DV3 omin = vmax(face_min, cw_min) - splat, omax = vmin(face_max, cw_max) + splat;
+        if (omin.x >= omax.x || omin.y >= omax.y || omin.z >= omax.z) continue;  // :200-206
+        const DV3 lo = (omin - cw_min) / voxel_size, hi = (omax - cw_min) / voxel_size;
+        const int x0 = clampi(f64_as_i32(std::floor(lo.x))), y0 = clampi(f64_as_i32(std::floor(lo.y))), z0 = clampi(f64_as_i32(std::floor(lo.z)));
+        const int x1 = clampi(f64_as_i32(std::ceil(hi.x))), y1 = clampi(f64_as_i32(std::ceil(hi.y))), z1 = clampi(f64_as_i32(std::ceil(hi.z)));
+        for (int y = y0; y <= y1; ++y)
+            for (int z = z0; z <= z1; ++z)
+                for (int x = x0; x <= x1; ++x) {
+                    const DV3 wp = cw_min + dv(double(x), double(y), double(z)) * voxel_size;  // :227-228
+                    const DV3 wmin = wp - splat;
+                    const DV3 wmax = wp + dv(voxel_size, voxel_size, voxel_size) + splat;
+                    if (triangle_cube_intersection(v1, v2, v3, wmin, wmax)) {
+                        batch_just_set<T>(masks, values, x, y, z, T(1));  // :239
+                        has_patches = true;
+                    }
+                }
+    }
+    return has_patches;
 }
 
 }  // namespace vxo

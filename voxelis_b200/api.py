@@ -46,7 +46,7 @@ ABI_SYMBOLS = [
     "vx_tree_voxels_per_axis", "vx_tree_is_empty", "vx_tree_is_leaf", "vx_tree_is_dirty",
     "vx_tree_mark_dirty", "vx_tree_clear_dirty", "vx_tree_apply_batch", "vx_apply_batches",
     "vx_apply_batches_slab", "vx_apply_batches_device", "vx_tree_get", "vx_tree_get_many",
-    "vx_tree_to_vec", "vx_roots_to_vec", "vx_roots_to_vec_lod", "vx_occupancy_masks", "vx_terrain_heights_device", "vx_terrain_batches_device", "vx_tree_fill", "vx_tree_clear",
+    "vx_tree_to_vec", "vx_roots_to_vec", "vx_roots_to_vec_lod", "vx_occupancy_masks", "vx_terrain_heights_device", "vx_terrain_batches_device", "vx_voxelize_plan", "vx_voxelize_chunks_device", "vx_tree_fill", "vx_tree_clear",
     "vx_dedup_heights", "vx_dedup_pack", "vx_dedup_scatter", "vx_dedup_map_roots", "vx_interner_intern_records",
 ]
 
@@ -151,6 +151,9 @@ def lib():
     L.vx_occupancy_masks.argtypes = [vp, C.c_uint8, C.c_uint8, sz, vp, vp, vp, sz, C.c_uint32, vp, vp, vp, vp, vp, vp]
     L.vx_terrain_heights_device.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, i64, i64, vp, vp]
     L.vx_terrain_batches_device.argtypes = [vp, C.c_uint8, vp, vp, C.c_int, C.c_int, vp, vp, vp]
+    L.vx_voxelize_plan.restype = i64
+    L.vx_voxelize_plan.argtypes = [C.c_uint8, C.c_double, vp, sz, vp, sz, vp, vp, sz, vp, vp, sz, vp]
+    L.vx_voxelize_chunks_device.argtypes = [vp, C.c_uint8, C.c_double, vp, sz, vp, sz, vp, sz, vp, sz, vp, vp, vp, vp, vp]
     L.vx_tree_fill.argtypes = [vp, vp, i64]
     L.vx_tree_clear.argtypes = [vp, vp]
     L.vx_model_serialize.restype = i64
@@ -334,6 +337,19 @@ class VoxInterner:
                                             materials, C.c_void_p(d_masks), C.c_void_p(d_values),
                                             C.c_void_p(stream or None)))
 
+    def voxelize_chunks_device(self, depth: int, chunk_world_size: float, mesh_min, vertices, faces, plan,
+                               d_masks: int, d_values: int, d_has_patches: int = 0):
+        """Voxelizer::voxelize_chunk (reference voxelis-voxelize/src/lib.rs:159-249) for every chunk of ``plan``
+        (from voxelize_plan) into the device slab masks[n][B][2] / values[n][B][8]."""
+        positions, pair_chunk, pair_face = plan
+        vertices = np.ascontiguousarray(vertices, np.float64).reshape(-1, 3)
+        faces = np.ascontiguousarray(faces, np.int32).reshape(-1, 3)
+        mm = np.ascontiguousarray(mesh_min, np.float64)
+        _ck(lib().vx_voxelize_chunks_device(self.h, depth, float(chunk_world_size), _ptr(mm), len(vertices),
+                                            _ptr(vertices), len(faces), _ptr(faces), len(positions), _ptr(positions),
+                                            len(pair_chunk), _ptr(pair_chunk), _ptr(pair_face), C.c_void_p(d_masks),
+                                            C.c_void_p(d_values), C.c_void_p(d_has_patches or None)))
+
     def model_serialize(self, positions, roots) -> bytes:
         """VoxModel::serialize (world/voxmodel.rs:177-294): VTM payload of chunks (positions[n][3], roots[n])."""
         positions = np.ascontiguousarray(positions, np.int32)
@@ -402,6 +418,23 @@ class VoxInterner:
                                      _ptr(out["n_materials"]), _ptr(out["material_ids"]), _ptr(out["material_counts"]),
                                      _ptr(out["per_material"])))
         return out
+
+
+def voxelize_plan(depth: int, chunk_world_size: float, mesh_min, vertices, faces):
+    """Voxelizer::build_face_to_chunk_map (reference voxelis-voxelize/src/lib.rs:113-156) ->
+    (positions[n][3] int32, pair_chunk[np] uint32, pair_face[np] uint32); host work, no device needed."""
+    vertices = np.ascontiguousarray(vertices, np.float64).reshape(-1, 3)
+    faces = np.ascontiguousarray(faces, np.int32).reshape(-1, 3)
+    mm = np.ascontiguousarray(mesh_min, np.float64)
+    npairs = C.c_size_t(0)
+    n = _ck(lib().vx_voxelize_plan(depth, float(chunk_world_size), _ptr(mm), len(vertices), _ptr(vertices), len(faces),
+                                   _ptr(faces), None, 0, None, None, 0, C.byref(npairs)))
+    positions = np.zeros((n, 3), np.int32)
+    pc = np.zeros(npairs.value, np.uint32)
+    pf = np.zeros(npairs.value, np.uint32)
+    _ck(lib().vx_voxelize_plan(depth, float(chunk_world_size), _ptr(mm), len(vertices), _ptr(vertices), len(faces),
+                               _ptr(faces), _ptr(positions), n, _ptr(pc), _ptr(pf), npairs.value, C.byref(npairs)))
+    return positions, pc, pf
 
 
 class Batch:
