@@ -28,7 +28,7 @@ idx = np.arange(n)
 cx, cy, cz = idx // (gy * gz), (idx // gz) % gy, idx % gz
 bo = np.ascontiguousarray(((cx // 2) * (gy // 2) + cy // 2) * (gz // 2) + cz // 2, np.uint32)
 offsets = np.stack([(cx % 2) * 32, (cy % 2) * 32, (cz % 2) * 32], 1).astype(np.uint32)
-nb, M = n // 8, 4
+nb, M = n // 8, (3 if materials == 3 else 2)
 outs = [torch.empty(s, dtype=t, device=dev) for s, t in (((nb, 3 * 4096), torch.int64), ((nb, 6), torch.int64),
         ((nb,), torch.int32), ((nb, M), torch.int64), ((nb, M), torch.int64), ((nb, M, 3 * 4096), torch.int64))]
 torch.cuda.synchronize()

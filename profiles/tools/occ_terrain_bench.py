@@ -62,7 +62,7 @@ cx, cy, cz = idx // (gy * gz), (idx // gz) % gy, idx % gz
 builder_of = ((cx // 2) * (gy // 2) + cy // 2) * (gz // 2) + cz // 2
 offsets = np.stack([(cx % 2) * 32, (cy % 2) * 32, (cz % 2) * 32], 1).astype(np.uint32)
 nb = n // 8
-M = 4
+M = 3 if materials == 3 else 2
 L = vx.lib()
 import ctypes as C
 d_global = torch.empty((nb, 3 * 4096), dtype=torch.int64, device=dev)

@@ -2043,14 +2043,16 @@ int vx_occupancy_masks(const vx_interner* cit, uint8_t max_depth, uint8_t lod, s
     if (ld >= 3) {
         const size_t smem = size_t(std::max(ms, 1)) * OCC_HALVES * 4;
         const dim3 grid_planes(3, unsigned(n_builders));
+        // <= 3 materials: 96 KiB of planes -> two CTAs of 512 threads per SM (their barriers overlap); else one of 1024
+        const unsigned nthr = ms <= 3 ? 512u : 1024u;
         if (it->dtype == VX_U8) {
             CU_TRY(cudaFuncSetAttribute(occ_planes_kernel<u8>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-            occ_planes_kernel<u8><<<grid_planes, 1024, smem, s>>>(it->dev.children, (const u8*)it->dev.values, d_cells,
+            occ_planes_kernel<u8><<<grid_planes, nthr, smem, s>>>(it->dev.children, (const u8*)it->dev.values, d_cells,
                                                                    ld, ms, max_materials, d_nmat, d_ids, d_counts,
                                                                    d_global, d_active, d_pm, d_over, d_over_count);
         } else {
             CU_TRY(cudaFuncSetAttribute(occ_planes_kernel<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-            occ_planes_kernel<int32_t><<<grid_planes, 1024, smem, s>>>(it->dev.children, (const int32_t*)it->dev.values,
+            occ_planes_kernel<int32_t><<<grid_planes, nthr, smem, s>>>(it->dev.children, (const int32_t*)it->dev.values,
                                                                         d_cells, ld, ms, max_materials, d_nmat, d_ids,
                                                                         d_counts, d_global, d_active, d_pm, d_over,
                                                                         d_over_count);

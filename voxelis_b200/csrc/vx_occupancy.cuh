@@ -305,8 +305,9 @@ occ_masks_kernel(const u64* __restrict__ children, const T* __restrict__ values,
 // material; the global plane is their OR and is formed while streaming out).  The DAG is unfolded level by level,
 // node by node instead of row by row, with the frontier in shared memory: 8 lanes read the 64-byte child row of a
 // node (one child each), uniform cubes of side >= 8 are queued and later filled by whole warps (an aligned run
-// of <= 32 bits lives in one 32-bit half word), branches go to the next frontier.  Below the 4^3 nodes every lane
-// owns one 2^3 block: its 8 child ids and their 8 values are independent loads, and the two voxels that share a
+// of <= 32 bits lives in one 32-bit half word), branches go to the next frontier.  Below the 8^3 nodes 64 lanes
+// take one node, every lane one 2^3 block (4^3 child -> block): its 8 child ids and their 8 values are independent
+// loads, and the two voxels that share a
 // half word leave as one shared atomic when they agree — all lanes run the same code, whatever the tree looks
 // like.  Needs depth - lod >= 3.  Materials take slots in the order the CTA meets them; the planes
 // leave in id order (build(), mesh.rs:263-285) through a permutation applied while they are streamed out with
@@ -377,14 +378,12 @@ occ_planes_kernel(const u64* __restrict__ children, const T* __restrict__ values
                   u64* __restrict__ per_material, u32* __restrict__ overflow, u32* __restrict__ overflow_count) {
     extern __shared__ uint4 occ_smem[];
     u32* planes = reinterpret_cast<u32*>(occ_smem);  // [ms][OCC_HALVES]: one plane per material slot
-    __shared__ u32 f_idx[4096];                      // the 4^3 nodes (depth ld - 2) that are not empty
-    __shared__ u16 f_pos[4096];                      // x4 | y4 << 4 | z4 << 8 in units of 4 voxels; bit 15: a leaf
-    __shared__ u32 u_idx[2][512];                    // upper levels, ping-pong (<= 512 nodes of side >= 8)
-    __shared__ u16 u_pos[2][512];
+    __shared__ u32 u_idx[2][512];                    // frontier, ping-pong: branch nodes of side >= 8 (<= 512 per level)
+    __shared__ u16 u_pos[2][512];                    // x4 | y4 << 4 | z4 << 8: the node's origin in units of 4 voxels
     __shared__ u32 s_mat[OCC_MS_MAX];                // raw value bits of the material in each slot, 0 = free
     __shared__ u32 s_cnt[OCC_MS_MAX];
     __shared__ u32 s_queue[OCC_QUEUE];
-    __shared__ u32 s_qn, s_over, s_nf, s_nu[2], s_act[2];
+    __shared__ u32 s_qn, s_over, s_nu[2], s_act[2];
     __shared__ u8 s_lut[256];                        // u8 values: slot + 1 of a material already met, 0 = not yet
     __shared__ int s_order[OCC_MS_MAX], s_n;
     const int plane = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, nthr = blockDim.x;
@@ -393,7 +392,7 @@ occ_planes_kernel(const u64* __restrict__ children, const T* __restrict__ values
     for (int i = tid; i < ms * (OCC_HALVES / 4); i += nthr) occ_smem[i] = make_uint4(0, 0, 0, 0);
     if (tid < OCC_MS_MAX) s_mat[tid] = 0, s_cnt[tid] = 0;
     if (tid < 256) s_lut[tid] = 0;
-    if (tid == 0) s_qn = 0, s_over = 0, s_nf = 0, s_nu[0] = 0, s_nu[1] = 0, s_act[0] = 0, s_act[1] = 0;
+    if (tid == 0) s_qn = 0, s_over = 0, s_nu[0] = 0, s_nu[1] = 0, s_act[0] = 0, s_act[1] = 0;
     __syncthreads();
 
     T last_v = T(0);
@@ -456,24 +455,19 @@ occ_planes_kernel(const u64* __restrict__ children, const T* __restrict__ values
         }
     }
     __syncthreads();
-    // 2. level by level down to the 4^3 nodes: 8 lanes per node, one child each (one 64-byte row per node)
-    for (int k = 0; k <= ld - 3; ++k) {
+    // 2. level by level down to the 8^3 nodes: 8 lanes per node, one child each (one 64-byte row per node)
+    for (int k = 0; k <= ld - 4; ++k) {
         const int src = k & 1, dst = src ^ 1;
         const u32 nsrc = s_nu[src];
-        const bool to_f = k + 1 == ld - 2;                      // the children are the 4^3 nodes
-        const u32 cls = u32(ld - k - 1);                         // log2 of the child side
+        const u32 cls = u32(ld - k - 1);                         // log2 of the child side, >= 3
         for (u32 t = tid; t < nsrc * 8; t += nthr) {
             const u32 e = t >> 3, ci = t & 7;
             const u64 id = __ldg(&children[size_t(u_idx[src][e]) * 8 + ci]);
             if (id == 0) continue;
             const u32 un = cls - 2;
             const u32 pos = u32(u_pos[src][e]) + (((ci & 1) << un) | ((((ci >> 1) & 1) << un) << 4) | (((ci >> 2) << un) << 8));
-            if (id_is_leaf(id) && !to_f) {
+            if (id_is_leaf(id)) {
                 big_cube(id, pos, cls);
-            } else if (to_f) {
-                const u32 q = atomicAdd(&s_nf, 1u);
-                f_idx[q] = id_index(id);
-                f_pos[q] = u16(pos | (id_is_leaf(id) ? 0x8000u : 0u));
             } else {
                 const u32 q = atomicAdd(&s_nu[dst], 1u);
                 u_idx[dst][q] = id_index(id);
@@ -484,24 +478,26 @@ occ_planes_kernel(const u64* __restrict__ children, const T* __restrict__ values
         if (tid == 0) s_nu[src] = 0;
         __syncthreads();
     }
-    // 3. one lane per 2^3 block of every 4^3 node: the block's 8 voxel values, then its 4 half words of this plane
+    // 3. 64 lanes per 8^3 node, one 2^3 block each: 4^3 child -> block -> the block's 8 voxel values, then its 4 half
+    //    words of this plane.  A 4^3 or 2^3 leaf is spread over its blocks' lanes the same way.
     {
-        const u32 nf = s_nf;
-        for (u32 t = tid; t < nf * 8; t += nthr) {
-            const u32 e = t >> 3, ci = t & 7;
-            const u32 pos = f_pos[e], idx4 = f_idx[e];
+        const int fin = (ld - 3) & 1;
+        const u32 n8 = s_nu[fin];
+        for (u32 t = tid; t < n8 * 64; t += nthr) {
+            const u32 e = t >> 6, c4 = (t >> 3) & 7, ci = t & 7;
+            const u32 pos = u_pos[fin][e];
+            const u64 id4 = __ldg(&children[size_t(u_idx[fin][e]) * 8 + c4]);
+            if (id4 == 0) continue;
             T v[8];
-            if (pos & 0x8000u) {                                // the whole 4^3 node is one leaf
-                const T vv = values[idx4];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = vv;
+            T uni = T(0);                                       // != 0: the block is one uniform 2^3 cube of that value
+            bool voxels = false;                                // v[] holds the block's 8 voxel values
+            if (id_is_leaf(id4)) {                              // the whole 4^3 node is one leaf
+                uni = values[id_index(id4)];
             } else {
-                const u64 bid = __ldg(&children[size_t(idx4) * 8 + ci]);
+                const u64 bid = __ldg(&children[size_t(id_index(id4)) * 8 + ci]);
                 if (bid == 0) continue;
                 if (id_is_leaf(bid)) {
-                    const T vv = values[id_index(bid)];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = vv;
+                    uni = values[id_index(bid)];
                 } else {                                        // depth ld - 1: its children are the voxels
                     const uint4* row = reinterpret_cast<const uint4*>(&children[size_t(id_index(bid)) * 8]);
                     u64 ch[8];
@@ -513,10 +509,21 @@ occ_planes_kernel(const u64* __restrict__ children, const T* __restrict__ values
                     }
 #pragma unroll
                     for (int i = 0; i < 8; ++i) v[i] = ch[i] != 0 ? values[id_index(ch[i])] : T(0);
+                    voxels = true;
                 }
             }
-            const u32 x = ((pos & 15) << 2) + 2 * (ci & 1), y = (((pos >> 4) & 15) << 2) + 2 * ((ci >> 1) & 1),
-                      z = (((pos >> 8) & 15) << 2) + 2 * (ci >> 2);
+            const u32 x = ((pos & 15) << 2) + 4 * (c4 & 1) + 2 * (ci & 1),
+                      y = (((pos >> 4) & 15) << 2) + 4 * ((c4 >> 1) & 1) + 2 * ((ci >> 1) & 1),
+                      z = (((pos >> 8) & 15) << 2) + 4 * (c4 >> 2) + 2 * (ci >> 2);
+            if (uni != T(0)) {                                  // one slot, four half words of two bits
+                const int slot = slot_of(uni);
+                if (slot < 0) continue;
+                if (plane == 0) count(slot, 8u);
+                u32* pmat = planes + size_t(slot) * OCC_HALVES;
+                occ_region_words(plane, x, y, z, 1, 0, 1, [&](u32 i, u32 bits) { atomicOr(&pmat[i], bits); });
+                continue;
+            }
+            if (!voxels) continue;                              // a leaf holding the default value: nothing to set
             occ_block_words<T>(plane, x, y, z, v, [&](T val, u32 i, u32 bits) {
                 const int slot = slot_of(val);
                 if (slot < 0) return;
