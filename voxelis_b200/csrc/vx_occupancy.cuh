@@ -515,13 +515,10 @@ occ_planes_kernel(const u64* __restrict__ children, const T* __restrict__ values
             const u32 x = ((pos & 15) << 2) + 4 * (c4 & 1) + 2 * (ci & 1),
                       y = (((pos >> 4) & 15) << 2) + 4 * ((c4 >> 1) & 1) + 2 * ((ci >> 1) & 1),
                       z = (((pos >> 8) & 15) << 2) + 4 * (c4 >> 2) + 2 * (ci >> 2);
-            if (uni != T(0)) {                                  // one slot, four half words of two bits
-                const int slot = slot_of(uni);
-                if (slot < 0) continue;
-                if (plane == 0) count(slot, 8u);
-                u32* pmat = planes + size_t(slot) * OCC_HALVES;
-                occ_region_words(plane, x, y, z, 1, 0, 1, [&](u32 i, u32 bits) { atomicOr(&pmat[i], bits); });
-                continue;
+            if (uni != T(0)) {                                  // same code path as a mixed block: the warp stays together
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = uni;
+                voxels = true;
             }
             if (!voxels) continue;                              // a leaf holding the default value: nothing to set
             occ_block_words<T>(plane, x, y, z, v, [&](T val, u32 i, u32 bits) {
