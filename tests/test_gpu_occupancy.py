@@ -86,3 +86,43 @@ def test_occupancy_argument_errors(gpu_api, oracle_api):
     with pytest.raises(gpu_api.VoxelisError) as e:       # 128^3 does not fit an occupancy volume
         g.occupancy_masks(groots, 7, [(0, 0, 0)])
     assert e.value.code == -4
+
+
+def test_occupancy_device_outputs_equal_host_outputs(gpu_api, oracle_api):
+    """All-device output pointers (what a renderer keeping the planes on the GPU passes) give the same bytes."""
+    import ctypes as C
+    import torch
+    masks, values = wl.terrain_world((2, 4, 2), 5, "surface_and_below", wl.U8, materials=3)
+    g, groots, _, _, _, _ = parity.build_both(gpu_api, oracle_api, 5, masks, values, wl.U8)
+    n = len(groots)
+    idx = np.arange(n)
+    cx, cy, cz = idx // 8, (idx // 2) % 4, idx % 2
+    bo = np.ascontiguousarray(cy // 2, np.uint32)
+    offs = np.ascontiguousarray(np.stack([cx * 32, (cy % 2) * 32, cz * 32], 1), np.uint32)
+    nb, M = 2, 3
+    host = g.occupancy_masks(groots, 5, offs, bo, nb, max_materials=M)
+    dev = torch.device("cuda", 0)
+    outs = [torch.full(s, -1, dtype=t, device=dev) for s, t in (((nb, 3 * 4096), torch.int64), ((nb, 6), torch.int64),
+            ((nb,), torch.int32), ((nb, M), torch.int64), ((nb, M), torch.int64), ((nb, M, 3 * 4096), torch.int64))]
+    torch.cuda.synchronize()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    r = np.ascontiguousarray(groots, np.uint64)
+    rc = gpu_api.lib().vx_occupancy_masks(g.h, 5, 0, n, p(r), p(offs), p(bo), nb, M,
+                                         *[C.c_void_p(t.data_ptr()) for t in outs])
+    assert rc == 0
+    nm = outs[2].cpu().numpy()
+    assert np.array_equal(nm, host["n_materials"])
+    assert np.array_equal(outs[0].cpu().numpy().view(np.uint64), host["global"])
+    assert np.array_equal(outs[1].cpu().numpy().view(np.uint64), host["active"])
+    for b in range(nb):
+        k = int(nm[b])
+        assert np.array_equal(outs[3][b, :k].cpu().numpy().view(np.uint64), host["material_ids"][b, :k])
+        assert np.array_equal(outs[4][b, :k].cpu().numpy().view(np.uint64), host["material_counts"][b, :k])
+        assert np.array_equal(outs[5][b, :k].cpu().numpy().view(np.uint64), host["per_material"][b, :k])
+    with pytest.raises(gpu_api.VoxelisError):                     # outputs split between host and device memory
+        gpu_api.lib().vx_occupancy_masks.restype = C.c_int
+        rc = gpu_api.lib().vx_occupancy_masks(g.h, 5, 0, n, p(r), p(offs), p(bo), nb, M, C.c_void_p(outs[0].data_ptr()),
+                                             p(host["active"]), p(host["n_materials"]), p(host["material_ids"]),
+                                             p(host["material_counts"]), p(host["per_material"]))
+        if rc < 0:
+            raise gpu_api.VoxelisError(rc, gpu_api.lib().vx_last_error().decode())
