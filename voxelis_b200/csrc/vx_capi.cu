@@ -1364,6 +1364,7 @@ int vx_voxelize_chunks_device(vx_interner* it, uint8_t max_depth, double chunk_w
         return fail(VX_E_INVALID, "masks, values and has_patches must be device memory");
     if ((reinterpret_cast<uintptr_t>(d_masks) | reinterpret_cast<uintptr_t>(d_values)) & 15)
         return fail(VX_E_INVALID, "device masks/values must be 16-byte aligned");
+    if (n_pairs > 0xFFFFFFFFull) return fail(VX_E_INVALID, "more than 2^32 (chunk, face) pairs");
     for (size_t k = 0; k < n_pairs; ++k)
         if (pair_chunk[k] >= n_chunks || pair_face[k] >= n_faces) return fail(VX_E_BOUNDS, "pair out of range");
     for (size_t k = 0; k < n_faces * 3; ++k)
@@ -1393,14 +1394,11 @@ int vx_voxelize_chunks_device(vx_interner* it, uint8_t max_depth, double chunk_w
         CU_TRY(cudaMemcpyAsync(dpc, pair_chunk, n_pairs * 4, cudaMemcpyHostToDevice, s));
         CU_TRY(cudaMemcpyAsync(dpf, pair_face, n_pairs * 4, cudaMemcpyHostToDevice, s));
         const unsigned blocks = unsigned(std::min<size_t>((n_pairs + 7) / 8, size_t(it->sm_count) * 8));
+        VoxelizeArgs va{int(max_depth), chunk_world_size, mesh_min[0], mesh_min[1], mesh_min[2], dv, df, dp, dpc, dpf, n_pairs};
         if (it->dtype == VX_U8)
-            voxelize_pairs_kernel<u8><<<blocks, 256, 0, s>>>(max_depth, chunk_world_size, mesh_min[0], mesh_min[1],
-                                                              mesh_min[2], dv, df, dp, dpc, dpf, n_pairs, d_masks,
-                                                              (u8*)d_values, dh);
+            voxelize_pairs_kernel<u8><<<blocks, 256, 0, s>>>(va, d_masks, (u8*)d_values, dh);
         else
-            voxelize_pairs_kernel<int32_t><<<blocks, 256, 0, s>>>(max_depth, chunk_world_size, mesh_min[0], mesh_min[1],
-                                                                   mesh_min[2], dv, df, dp, dpc, dpf, n_pairs, d_masks,
-                                                                   (int32_t*)d_values, dh);
+            voxelize_pairs_kernel<int32_t><<<blocks, 256, 0, s>>>(va, d_masks, (int32_t*)d_values, dh);
         CU_TRY(cudaGetLastError());
     }
     CU_TRY(cudaStreamSynchronize(s));

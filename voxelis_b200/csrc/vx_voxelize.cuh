@@ -12,9 +12,12 @@
 // one the CPU restatement takes.  The triangle's normal and plane offset do not depend on the voxel and are computed
 // once per (chunk, face) pair.
 //
-//   voxelize_pairs_kernel   one warp per (chunk, face) pair: the 32 lanes stride over the voxels of the clipped box;
-//                           a hit ORs the voxel's bit into the block's set_mask (32-bit atomicOr on the word holding
-//                           the byte — several faces and lanes meet in one block) and stores the value 1.
+//   voxelize_pairs_kernel   one warp per (chunk, face) pair for the cheap first part of the test (bounding boxes,
+//                           plane straddle): the 32 lanes stride over the voxels of the clipped box; undecided voxels
+//                           are parked per warp across pairs and the long part (vertex in cube, corner in triangle,
+//                           18 edge / face tests) always runs on a full warp.  A hit ORs the voxel's bit into the
+//                           block's set_mask (32-bit atomicOr on the word holding the byte — several faces and lanes
+//                           meet in one block) and stores the value 1.
 #pragma once
 #include "vx_device.cuh"
 
@@ -65,24 +68,34 @@ __device__ __forceinline__ bool edge_quad(D3 e1, D3 e2, D3 q0, D3 q1, D3 q2, D3 
     return pt_in_or_on_triangle(p, q0, q1, q2) || pt_in_or_on_triangle(p, q0, q2, q3);
 }
 
-// triangle_cube_intersection — voxelis-math lib.rs:3-127; tri_min / tri_max / normal / d hoisted by the caller
-__device__ __noinline__ bool tri_cube(D3 tv0, D3 tv1, D3 tv2, D3 tri_min, D3 tri_max, D3 normal, double d, D3 cmin,
-                                      D3 cmax) {
+// triangle_cube_intersection — voxelis-math lib.rs:3-127, cut in two at :52.  tri_min / tri_max / normal / d do not
+// depend on the cube and are hoisted by the caller.
+//   tri_cube_quick  :9-50   bounding boxes apart -> 0 (no); the triangle's plane separates two cube corners -> 1 (yes);
+//                           otherwise 2: undecided, the long part has to run
+//   tri_cube_slow   :52-126 a triangle vertex in the cube, a cube corner in the triangle, an edge through a cube face
+__device__ __forceinline__ int tri_cube_quick(D3 tri_min, D3 tri_max, D3 normal, double d, D3 cmin, D3 cmax) {
     const double eps = 1e-5;
     if (tri_max.x < cmin.x - eps || tri_min.x > cmax.x + eps || tri_max.y < cmin.y - eps || tri_min.y > cmax.y + eps ||
         tri_max.z < cmin.z - eps || tri_min.z > cmax.z + eps)
-        return false;
+        return 0;
+    const double sign = signum64(dot3(normal, d3(cmin.x, cmin.y, cmin.z)) + d);
+#pragma unroll
+    for (int i = 1; i < 8; ++i) {  // corners in the reference's order: (x: i in {1,2,5,6}, y: {2,3,6,7}, z: i >= 4) max
+        const D3 p = d3((i == 1 || i == 2 || i == 5 || i == 6) ? cmax.x : cmin.x,
+                        (i == 2 || i == 3 || i == 6 || i == 7) ? cmax.y : cmin.y, i >= 4 ? cmax.z : cmin.z);
+        const double s = dot3(normal, p) + d;
+        if (fabs(s) < eps) continue;
+        if (signum64(s) != sign) return 1;
+    }
+    return 2;
+}
+
+__device__ __noinline__ bool tri_cube_slow(D3 tv0, D3 tv1, D3 tv2, D3 cmin, D3 cmax) {
+    if (pt_in_or_on_cube(tv0, cmin, cmax) || pt_in_or_on_cube(tv1, cmin, cmax) || pt_in_or_on_cube(tv2, cmin, cmax))
+        return true;
     D3 cp[8] = {d3(cmin.x, cmin.y, cmin.z), d3(cmax.x, cmin.y, cmin.z), d3(cmax.x, cmax.y, cmin.z),
                 d3(cmin.x, cmax.y, cmin.z), d3(cmin.x, cmin.y, cmax.z), d3(cmax.x, cmin.y, cmax.z),
                 d3(cmax.x, cmax.y, cmax.z), d3(cmin.x, cmax.y, cmax.z)};
-    const double sign = signum64(dot3(normal, cp[0]) + d);
-    for (int i = 1; i < 8; ++i) {
-        const double s = dot3(normal, cp[i]) + d;
-        if (fabs(s) < eps) continue;
-        if (signum64(s) != sign) return true;
-    }
-    if (pt_in_or_on_cube(tv0, cmin, cmax) || pt_in_or_on_cube(tv1, cmin, cmax) || pt_in_or_on_cube(tv2, cmin, cmax))
-        return true;
     for (int i = 0; i < 8; ++i)
         if (pt_in_or_on_triangle(cp[i], tv0, tv1, tv2)) return true;
     const int fq[6][4] = {{0, 1, 2, 3}, {4, 5, 6, 7}, {0, 1, 5, 4}, {2, 3, 7, 6}, {0, 3, 7, 4}, {1, 2, 6, 5}};
@@ -108,52 +121,120 @@ __device__ __forceinline__ int clamp_voxel(double v, int vpa) {  // `as i32` (sa
     return i < 0 ? 0 : i > vpa - 1 ? vpa - 1 : i;
 }
 
+// Everything about one (chunk, face) pair that does not depend on the voxel.
+struct PairCtx {
+    D3 v1, v2, v3, fmin, fmax, normal, cw_min;
+    double d;
+    int x0, y0, z0, nx, nz, total;
+    u32 c;
+};
+
+struct VoxelizeArgs {
+    int depth;
+    double chunk_world_size, mmx, mmy, mmz;
+    const double* vertices;
+    const int* faces;
+    const int* positions;
+    const u32* pair_chunk;
+    const u32* pair_face;
+    size_t n_pairs;
+};
+
+// voxelize_chunk, lib.rs:184-221: the face's bounding box clipped to the chunk -> the voxel range to test
+__device__ __forceinline__ bool pair_context(const VoxelizeArgs& a, size_t pr, PairCtx& P) {
+    const int vpa = 1 << a.depth;
+    const double voxel_size = a.chunk_world_size / double(vpa);  // voxelize_mesh, lib.rs:262
+    const double epsilon = voxel_size * 1e-7;
+    const D3 splat = d3(epsilon, epsilon, epsilon), mesh_min = d3(a.mmx, a.mmy, a.mmz);
+    P.c = a.pair_chunk[pr];
+    const int* fi = a.faces + 3 * size_t(a.pair_face[pr]);
+    auto vert = [&](int i) { const double* p = a.vertices + 3 * size_t(i - 1); return d3(p[0], p[1], p[2]); };
+    P.v1 = vert(fi[0]) - mesh_min, P.v2 = vert(fi[1]) - mesh_min, P.v3 = vert(fi[2]) - mesh_min;
+    P.cw_min = d3(double(a.positions[3 * P.c]), double(a.positions[3 * P.c + 1]), double(a.positions[3 * P.c + 2])) * a.chunk_world_size;
+    const D3 cw_max = P.cw_min + d3(a.chunk_world_size, a.chunk_world_size, a.chunk_world_size);
+    P.fmin = min3(min3(P.v1, P.v2), P.v3), P.fmax = max3(max3(P.v1, P.v2), P.v3);
+    const D3 omin = max3(P.fmin, P.cw_min) - splat, omax = min3(P.fmax, cw_max) + splat;
+    if (omin.x >= omax.x || omin.y >= omax.y || omin.z >= omax.z) return false;  // lib.rs:200-206
+    const D3 lo = (omin - P.cw_min) / voxel_size, hi = (omax - P.cw_min) / voxel_size;
+    P.x0 = clamp_voxel(floor(lo.x), vpa), P.y0 = clamp_voxel(floor(lo.y), vpa), P.z0 = clamp_voxel(floor(lo.z), vpa);
+    const int x1 = clamp_voxel(ceil(hi.x), vpa), y1 = clamp_voxel(ceil(hi.y), vpa), z1 = clamp_voxel(ceil(hi.z), vpa);
+    if (x1 < P.x0 || y1 < P.y0 || z1 < P.z0) return false;
+    P.nx = x1 - P.x0 + 1, P.nz = z1 - P.z0 + 1, P.total = P.nx * P.nz * (y1 - P.y0 + 1);
+    P.normal = cross3(P.v2 - P.v1, P.v3 - P.v1);
+    P.d = -dot3(P.normal, P.v1);
+    return true;
+}
+
+// voxel k of the pair's box (x fastest, then z, then y — the reference's loop nest :224-226) and its cube :227-233
+__device__ __forceinline__ void pair_voxel(const VoxelizeArgs& a, const PairCtx& P, int k, int* x, int* y, int* z, D3* wmin,
+                                           D3* wmax) {
+    const double voxel_size = a.chunk_world_size / double(1 << a.depth), epsilon = voxel_size * 1e-7;
+    const D3 splat = d3(epsilon, epsilon, epsilon);
+    *x = P.x0 + k % P.nx, *z = P.z0 + (k / P.nx) % P.nz, *y = P.y0 + k / (P.nx * P.nz);
+    const D3 wp = P.cw_min + d3(double(*x), double(*y), double(*z)) * voxel_size;
+    *wmin = wp - splat;
+    *wmax = wp + d3(voxel_size, voxel_size, voxel_size) + splat;
+}
+
+template <class T>
+__device__ __forceinline__ void voxel_hit(int depth, u32 c, int x, int y, int z, u8* masks, T* values, u8* has_patches) {
+    const size_t B = size_t(1) << (3 * (depth - 1));
+    const u32 full = spread10_dev(u32(x)) | (spread10_dev(u32(y)) << 1) | (spread10_dev(u32(z)) << 2);
+    const size_t blk = size_t(c) * B + (full >> 3);
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(masks + blk * 2);   // set_mask byte of the block
+    atomicOr(reinterpret_cast<u32*>(addr & ~uintptr_t(3)), (1u << (full & 7)) << (8 * (addr & 3)));
+    values[blk * 8 + (full & 7)] = T(1);  // batch.just_set(pos, 1), lib.rs:239
+    has_patches[c] = 1;
+}
+
+// One warp per (chunk, face) pair for the quick part of the test (lanes stride over the voxels of the clipped box);
+// voxels the quick part leaves undecided are parked in a per-warp queue ACROSS pairs and the long part runs on 32 of
+// them at a time, every lane rebuilding its own pair's context — so the expensive code always has a full warp,
+// however small the boxes are.
 template <class T>
 __global__ void __launch_bounds__(256)
-voxelize_pairs_kernel(int depth, double chunk_world_size, double mmx, double mmy, double mmz,
-                      const double* __restrict__ vertices, const int* __restrict__ faces,
-                      const int* __restrict__ positions, const u32* __restrict__ pair_chunk,
-                      const u32* __restrict__ pair_face, size_t n_pairs, u8* __restrict__ masks, T* __restrict__ values,
-                      u8* __restrict__ has_patches) {
-    const int lane = threadIdx.x & 31;
+voxelize_pairs_kernel(VoxelizeArgs a, u8* __restrict__ masks, T* __restrict__ values, u8* __restrict__ has_patches) {
+    __shared__ u32 q_pair[8][64], q_k[8][64];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const size_t warp0 = (blockIdx.x * size_t(blockDim.x) + threadIdx.x) >> 5, nwarps = (size_t(gridDim.x) * blockDim.x) >> 5;
-    const int vpa = 1 << depth;
-    const size_t B = size_t(1) << (3 * (depth - 1));
-    const double voxel_size = chunk_world_size / double(vpa);  // voxelize_mesh, lib.rs:262
-    const double epsilon = voxel_size * 1e-7;
-    const D3 splat = d3(epsilon, epsilon, epsilon), mesh_min = d3(mmx, mmy, mmz);
-    for (size_t pr = warp0; pr < n_pairs; pr += nwarps) {
-        const u32 c = pair_chunk[pr], f = pair_face[pr];
-        const int* fi = faces + 3 * size_t(f);
-        auto vert = [&](int i) { const double* p = vertices + 3 * size_t(i - 1); return d3(p[0], p[1], p[2]); };
-        const D3 v1 = vert(fi[0]) - mesh_min, v2 = vert(fi[1]) - mesh_min, v3 = vert(fi[2]) - mesh_min;
-        const D3 cw_min = d3(double(positions[3 * c]), double(positions[3 * c + 1]), double(positions[3 * c + 2])) * chunk_world_size;
-        const D3 cw_max = cw_min + d3(chunk_world_size, chunk_world_size, chunk_world_size);
-        const D3 face_min = min3(min3(v1, v2), v3), face_max = max3(max3(v1, v2), v3);
-        const D3 omin = max3(face_min, cw_min) - splat, omax = min3(face_max, cw_max) + splat;
-        if (omin.x >= omax.x || omin.y >= omax.y || omin.z >= omax.z) continue;  // lib.rs:200-206
-        const D3 lo = (omin - cw_min) / voxel_size, hi = (omax - cw_min) / voxel_size;
-        const int x0 = clamp_voxel(floor(lo.x), vpa), y0 = clamp_voxel(floor(lo.y), vpa), z0 = clamp_voxel(floor(lo.z), vpa);
-        const int x1 = clamp_voxel(ceil(hi.x), vpa), y1 = clamp_voxel(ceil(hi.y), vpa), z1 = clamp_voxel(ceil(hi.z), vpa);
-        if (x1 < x0 || y1 < y0 || z1 < z0) continue;
-        const int nx = x1 - x0 + 1, nz = z1 - z0 + 1, total = nx * nz * (y1 - y0 + 1);
-        const D3 normal = cross3(v2 - v1, v3 - v1);
-        const double d = -dot3(normal, v1);
-        bool any = false;
-        for (int k = lane; k < total; k += 32) {
-            const int x = x0 + k % nx, z = z0 + (k / nx) % nz, y = y0 + k / (nx * nz);
-            const D3 wp = cw_min + d3(double(x), double(y), double(z)) * voxel_size;
-            const D3 wmin = wp - splat, wmax = wp + d3(voxel_size, voxel_size, voxel_size) + splat;
-            if (!tri_cube(v1, v2, v3, face_min, face_max, normal, d, wmin, wmax)) continue;
-            const u32 full = spread10_dev(u32(x)) | (spread10_dev(u32(y)) << 1) | (spread10_dev(u32(z)) << 2);
-            const size_t blk = size_t(c) * B + (full >> 3);
-            const uintptr_t addr = reinterpret_cast<uintptr_t>(masks + blk * 2);   // set_mask byte of the block
-            atomicOr(reinterpret_cast<u32*>(addr & ~uintptr_t(3)), (1u << (full & 7)) << (8 * (addr & 3)));
-            values[blk * 8 + (full & 7)] = T(1);
-            any = true;
+    int qn = 0;  // entries parked by this warp (same value in every lane)
+    auto slow_round = [&](int count) {  // the last `count` (<= 32) parked voxels
+        if (lane < count) {
+            PairCtx Q;
+            pair_context(a, q_pair[w][qn - count + lane], Q);
+            int x, y, z;
+            D3 wmin, wmax;
+            pair_voxel(a, Q, int(q_k[w][qn - count + lane]), &x, &y, &z, &wmin, &wmax);
+            if (tri_cube_slow(Q.v1, Q.v2, Q.v3, wmin, wmax)) voxel_hit<T>(a.depth, Q.c, x, y, z, masks, values, has_patches);
         }
-        if (any) has_patches[c] = 1;
+        qn -= count;
+        __syncwarp();
+    };
+    for (size_t pr = warp0; pr < a.n_pairs; pr += nwarps) {
+        PairCtx P;
+        if (!pair_context(a, pr, P)) continue;
+        for (int base = 0; base < P.total; base += 32) {
+            const int k = base + lane;
+            int st = 0;
+            if (k < P.total) {
+                int x, y, z;
+                D3 wmin, wmax;
+                pair_voxel(a, P, k, &x, &y, &z, &wmin, &wmax);
+                st = tri_cube_quick(P.fmin, P.fmax, P.normal, P.d, wmin, wmax);
+                if (st == 1) voxel_hit<T>(a.depth, P.c, x, y, z, masks, values, has_patches);
+            }
+            const unsigned pend = __ballot_sync(FULL, st == 2);
+            if (st == 2) {
+                const int slot = qn + __popc(pend & ((1u << lane) - 1));
+                q_pair[w][slot] = u32(pr);
+                q_k[w][slot] = u32(k);
+            }
+            qn += __popc(pend);
+            __syncwarp();
+            if (qn >= 32) slow_round(32);
+        }
     }
+    if (qn > 0) slow_round(qn);
 }
 
 }  // namespace vx
