@@ -126,3 +126,74 @@ def test_occupancy_device_outputs_equal_host_outputs(gpu_api, oracle_api):
                                              p(host["material_counts"]), p(host["per_material"]))
         if rc < 0:
             raise gpu_api.VoxelisError(rc, gpu_api.lib().vx_last_error().decode())
+
+
+def _popcount64(t):
+    """Per-element population count of an int64 tensor holding u64 words (SWAR; masks undo the arithmetic shifts)."""
+    m1, m2, m4 = 0x5555555555555555, 0x3333333333333333, 0x0F0F0F0F0F0F0F0F
+    t = t - ((t >> 1) & m1)
+    t = (t & m2) + ((t >> 2) & m2)
+    t = (t + (t >> 4)) & m4
+    return ((t * 0x0101010101010101) >> 56) & 0xFF
+
+
+def _or_reduce(t):
+    while t.shape[-1] > 1:
+        h = t.shape[-1] // 2
+        t = t[..., :h] | t[..., h:]
+    return t[..., 0]
+
+
+def test_occupancy_full_world_properties(gpu_api):
+    """BASELINE.json's full world (64x8x64 chunks of 32^3, surface-and-below, 3 materials), generated, built and
+    unfolded on the device into 4 096 builders; checked through properties that do not need the oracle at this size:
+    per-material planes are pairwise disjoint and OR to the global plane; the three planes of a material hold the same
+    number of bits = its voxel count; counts per material id sum to the number of such voxels in the generated
+    batches; global_active is the OR of the words whose bits run along that axis (mesh.rs:451-461)."""
+    import ctypes as C
+    import torch
+    depth, grid, M = 5, (64, 8, 64), 3
+    gx, gy, gz = grid
+    N, B, n = 32, 4096, gx * gy * gz
+    dev = torch.device("cuda", 0)
+    g = gpu_api.VoxInterner.with_memory_budget(256 << 20, wl.U8)
+    h = torch.empty((gx * N, gz * N), dtype=torch.int32, device=dev)
+    m = torch.empty((n, B, 2), dtype=torch.uint8, device=dev)
+    v = torch.empty((n, B, 8), dtype=torch.uint8, device=dev)
+    roots = torch.zeros(n, dtype=torch.int64, device=dev)
+    torch.cuda.synchronize()
+    g.terrain_heights_device(gx * N, gz * N, h.data_ptr(), wl.SEED_BASE, gy * N)
+    g.terrain_batches_device(depth, grid, h.data_ptr(), m.data_ptr(), v.data_ptr(), False, 3)
+    g.apply_batches_device(depth, n, m.data_ptr(), v.data_ptr(), roots.data_ptr())
+    g.sync()
+    hroots = roots.cpu().numpy().astype(np.uint64)
+    idx = np.arange(n)
+    cx, cy, cz = idx // (gy * gz), (idx // gz) % gy, idx % gz
+    bo = np.ascontiguousarray(((cx // 2) * (gy // 2) + cy // 2) * (gz // 2) + cz // 2, np.uint32)
+    offs = np.ascontiguousarray(np.stack([(cx % 2) * N, (cy % 2) * N, (cz % 2) * N], 1), np.uint32)
+    nb = n // 8
+    glob = torch.empty((nb, 3, 4096), dtype=torch.int64, device=dev)
+    active = torch.empty((nb, 6), dtype=torch.int64, device=dev)
+    nmat = torch.empty(nb, dtype=torch.int32, device=dev)
+    ids = torch.empty((nb, M), dtype=torch.int64, device=dev)
+    counts = torch.empty((nb, M), dtype=torch.int64, device=dev)
+    pm = torch.empty((nb, M, 3, 4096), dtype=torch.int64, device=dev)
+    torch.cuda.synchronize()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = gpu_api.lib().vx_occupancy_masks(g.h, depth, 0, n, p(hroots), p(offs), p(bo), nb, M,
+                                         *[C.c_void_p(t.data_ptr()) for t in (glob, active, nmat, ids, counts, pm)])
+    assert rc == 0, gpu_api.lib().vx_last_error()
+    valid = torch.arange(M, device=dev)[None, :] < nmat[:, None]                     # [nb][M]
+    pmv = torch.where(valid[:, :, None, None], pm, torch.zeros_like(pm))
+    cv = torch.where(valid, counts, torch.zeros_like(counts))
+    assert torch.equal(pmv[:, 0] | pmv[:, 1] | pmv[:, 2], glob)                      # OR of the materials = global
+    assert not ((pmv[:, 0] & pmv[:, 1]) | (pmv[:, 0] & pmv[:, 2]) | (pmv[:, 1] & pmv[:, 2])).any()   # disjoint
+    bits = _popcount64(pmv).sum(-1)                                                  # [nb][M][3]
+    assert torch.equal(bits, cv[:, :, None].expand(-1, -1, 3))                       # every plane: the voxel count
+    assert torch.equal(_popcount64(glob).sum(-1), cv.sum(1)[:, None].expand(-1, 3))
+    for k in (1, 2, 3):                                                              # ids ascending, totals exact
+        assert int(cv[valid & (ids == k)].sum()) == int((v == k).sum())
+    assert bool(((ids[:, 1:] > ids[:, :-1]) | ~valid[:, 1:]).all())
+    xm, ym, zm = _or_reduce(glob[:, 0]), _or_reduce(glob[:, 1]), _or_reduce(glob[:, 2])
+    assert torch.equal(active, torch.stack([ym, zm, zm, xm, ym, xm], 1))
+    assert int(nmat.max()) == 3 and int((nmat == 0).sum()) > 0                       # surface, deep and empty builders
