@@ -253,7 +253,9 @@ int vx_roots_to_vec_lod(const vx_interner*, uint8_t max_depth, uint8_t lod, size
  *   n_materials[nb], material_ids[nb][max_materials], material_counts[nb][max_materials]
  *                                `materials` sorted by id (id = value as usize, core/voxel.rs:85-87), voxel counts
  *   per_material[nb][max_materials][3*4096]   only the first n_materials[b] planes of builder b are written
- * VX_E_BOUNDS when a builder holds more than max_materials (<= 1024) materials; n_materials[] is valid then. */
+ * VX_E_BOUNDS when a builder holds more than max_materials (<= 1024) materials; n_materials[] is valid then.
+ * At most 65535 builders per call.  Builders with <= min(max_materials, 5) materials and chunks of at least 8^3 voxels
+ * take the shared-memory kernel (pass the smallest max_materials that fits: <= 3 keeps two CTAs per SM). */
 int vx_occupancy_masks(const vx_interner*, uint8_t max_depth, uint8_t lod, size_t n, const vx_block_id* roots,
                        const uint32_t* offsets, const uint32_t* builder_of, size_t n_builders, uint32_t max_materials,
                        uint64_t* global, uint64_t* active, uint32_t* n_materials, uint64_t* material_ids,

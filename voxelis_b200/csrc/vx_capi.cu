@@ -1983,6 +1983,7 @@ int vx_occupancy_masks(const vx_interner* cit, uint8_t max_depth, uint8_t lod, s
     if (ld > 6) return fail(VX_E_UNSUPPORTED, "an occupancy volume is 64 voxels per axis (utils/mesh.rs:50): depth - lod <= 6");
     if (n_builders == 0) return n ? fail(VX_E_INVALID, "chunks but no builder") : VX_OK;
     if (max_materials > 1024) return fail(VX_E_INVALID, "max_materials <= 1024");
+    if (n_builders > 65535) return fail(VX_E_UNSUPPORTED, "at most 65535 builders per call (one grid row each)");
     const bool dev_out = is_device_ptr(global);
     if (dev_out != is_device_ptr(active) || dev_out != is_device_ptr(n_materials) ||
         dev_out != is_device_ptr(material_ids) || dev_out != is_device_ptr(material_counts) ||
