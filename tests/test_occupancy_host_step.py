@@ -17,8 +17,7 @@ from voxelis_b200 import workloads as wl
 HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cpp")
 
 
-@pytest.fixture(scope="module")
-def stepper():
+def load_stepper():
     out = os.path.join(HERE, "libocc_host_check.so")
     src = os.path.join(HERE, "occ_host_check.cu")
     hdr = os.path.join(HERE, "..", "..", "voxelis_b200", "csrc", "vx_occupancy.cuh")
@@ -31,6 +30,11 @@ def stepper():
     L.occ_host_check.argtypes = [C.c_void_p] * 2 + [C.c_int] + [C.c_void_p] + [C.c_int] * 2 + [C.c_void_p] * 4
     L.occ_host_check_planes.argtypes = L.occ_host_check.argtypes
     return L
+
+
+@pytest.fixture(scope="module")
+def stepper():
+    return load_stepper()
 
 
 def _p(a):

@@ -61,3 +61,53 @@ def test_oracle_occupancy_empty_root(oracle_api):
     it = oracle_api.VoxInterner(1 << 20, wl.U8)
     got = it.occupancy_masks(np.zeros(1, np.uint64), 5, [(0, 0, 0)])
     assert not got["global"].any() and not got["active"].any() and len(got["material_ids"]) == 0
+
+
+def random_box_volume(rng, n, materials):
+    """A chunk of side n built from random axis-aligned boxes of random materials (and some carved holes): a mix of
+    large uniform regions, thin plates and single voxels, i.e. nodes at every depth of the tree."""
+    vol = np.zeros((n, n, n), np.int64)                                   # [x][y][z]
+    for _ in range(int(rng.integers(1, 10))):
+        lo = rng.integers(0, n, 3)
+        hi = np.minimum(lo + rng.integers(1, n + 1, 3), n)
+        vol[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]] = 0 if rng.random() < 0.2 else int(rng.choice(materials))
+    return vol
+
+
+@pytest.mark.parametrize("dtype", [wl.U8, wl.I32], ids=["u8", "i32"])
+def test_occupancy_random_boxes_oracle_numpy_and_kernel_index_code(oracle_api, dtype):
+    """Seeded random box worlds at D = 4 and 5: the oracle's planes equal the dense numpy definition, and the kernels'
+    host-steppable index code (both families, tests/cpp/occ_host_check.cu) equals the oracle."""
+    from test_occupancy_host_step import _p, load_stepper
+    step = load_stepper()
+    rng = np.random.default_rng(20261017 + dtype)
+    mats = [1, 2, 3, 200] if dtype == wl.U8 else [1, -3, 70000, 5]
+    for depth in (4, 5):
+        n = 1 << depth
+        G = 64 >> depth
+        vols = [random_box_volume(rng, n, mats) for _ in range(6)]
+        batches = [wl.batch_from_dense(v.astype(wl.NP_DTYPE[dtype]), None, dtype) for v in vols]
+        masks = np.stack([b[0] for b in batches])
+        values = np.stack([b[1] for b in batches])
+        it, roots, _ = oracle_build(oracle_api, depth, masks, values, dtype, budget=128 << 20)
+        offs = cell_offsets(n, len(roots), seed=depth)
+        got = it.occupancy_masks(roots, depth, offs)
+        dense = [it.root_to_vec(int(r), depth) for r in roots]
+        for d, v in zip(dense, vols):
+            assert np.array_equal(d, np.transpose(v, (1, 2, 0)).astype(d.dtype))     # [y][z][x] of the [x][y][z] input
+        oref.assert_same(got, oref.occupancy_from_dense(oref.place(dense, offs)), depth)
+        dl = it.download()
+        children = np.ascontiguousarray(dl["children"], np.uint64)
+        vals = np.ascontiguousarray(dl["values"].astype(wl.NP_DTYPE[dtype]))
+        cell = np.zeros(G ** 3, np.uint64)
+        for r, (ox, oy, oz) in zip(roots, offs):
+            cell[((oy >> depth) * G + (oz >> depth)) * G + (ox >> depth)] = r
+        for entry in ("occ_host_check", "occ_host_check_planes"):
+            M = 16
+            ids, counts = np.zeros(M, np.uint64), np.zeros(M, np.uint64)
+            glob = np.zeros(3 * 4096, np.uint64)
+            pm = np.full((M, 3 * 4096), 0xDEADBEEF, np.uint64)
+            nm = getattr(step, entry)(_p(children), _p(vals), dtype, _p(cell), depth, M, _p(ids), _p(counts), _p(glob), _p(pm))
+            assert nm == len(got["material_ids"]), (entry, depth)
+            assert np.array_equal(ids[:nm], got["material_ids"]) and np.array_equal(counts[:nm], got["material_counts"])
+            assert np.array_equal(glob, got["global"]) and np.array_equal(pm[:nm], got["per_material"]), (entry, depth)
