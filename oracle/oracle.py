@@ -84,7 +84,7 @@ def lib():
     L.orc_occupancy_masks.restype = C.c_longlong
     L.orc_occupancy_masks.argtypes = [vp, C.c_size_t, vp, C.c_int, vp, vp, vp, C.c_size_t, vp, vp, vp]
     for f in ("orc_point_in_or_on_cube", "orc_point_in_or_on_triangle", "orc_edge_quad_intersection",
-              "orc_triangle_cube_intersection"):
+              "orc_triangle_cube_intersection", "orc_point_in_quad"):
         getattr(L, f).argtypes = [vp, vp]
     L.orc_voxelize_chunk.argtypes = [C.c_int, vp, C.c_int, C.c_double, vp, C.c_size_t, vp, vp, vp, vp]
     L.orc_interner_ref.restype = C.c_uint32
@@ -127,6 +127,11 @@ def point_in_or_on_triangle(p, tri):
 def edge_quad_intersection(edge, quad):
     """voxelis-math/src/lib.rs:180-204."""
     return bool(lib().orc_edge_quad_intersection(_ptr(_f64(*edge)), _ptr(_f64(*quad))))
+
+
+def point_in_quad(p, quad):
+    """voxelis-math/src/lib.rs:206-214."""
+    return bool(lib().orc_point_in_quad(_ptr(_f64(p)), _ptr(_f64(*quad))))
 
 
 def triangle_cube_intersection(tri, cube):

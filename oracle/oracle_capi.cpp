@@ -262,6 +262,10 @@ int orc_edge_quad_intersection(const double* e, const double* q) {
     const DV3 quad[4] = {dv(q[0], q[1], q[2]), dv(q[3], q[4], q[5]), dv(q[6], q[7], q[8]), dv(q[9], q[10], q[11])};
     return edge_quad_intersection(dv(e[0], e[1], e[2]), dv(e[3], e[4], e[5]), quad);
 }
+int orc_point_in_quad(const double* p, const double* q) {
+    const DV3 quad[4] = {dv(q[0], q[1], q[2]), dv(q[3], q[4], q[5]), dv(q[6], q[7], q[8]), dv(q[9], q[10], q[11])};
+    return point_in_quad(dv(p[0], p[1], p[2]), quad);
+}
 int orc_triangle_cube_intersection(const double* t, const double* cube) {
     return triangle_cube_intersection(dv(t[0], t[1], t[2]), dv(t[3], t[4], t[5]), dv(t[6], t[7], t[8]),
                                       dv(cube[0], cube[1], cube[2]), dv(cube[3], cube[4], cube[5]));

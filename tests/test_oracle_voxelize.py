@@ -46,6 +46,20 @@ def test_edge_quad_intersection_known_answers(oracle_api):
         assert f(((x, y, -1.0), (x, y, 1.0)), QUAD) == hit, (x, y)        # a vertical edge through (x, y, 0)
 
 
+def test_point_in_quad_known_answers(oracle_api):
+    """voxelis-math/src/lib.rs:469-652."""
+    f = oracle_api.point_in_quad
+    yes = [(0.5, 0.5, 0.0), (0.5, 0.0, 0.0), (1.0, 0.5, 0.0), (0.5, 1.0, 0.0), (0.0, 0.5, 0.0), (0.0, 0.0, 0.0),
+           (1.0, 0.0, 0.0), (1.0, 1.0, 0.0), (0.0, 1.0, 0.0), (1.0 - 1e-6, 0.5, 0.0)]
+    no = [(-0.5, 0.5, 0.0), (1.5, 0.5, 0.0), (0.5, -0.5, 0.0), (0.5, 1.5, 0.0), (-0.5, -0.5, 0.0), (10.0, 10.0, 10.0),
+          (1.0 + 1e-4, 0.5, 0.0)]
+    assert all(f(p, QUAD) for p in yes)
+    assert not any(f(p, QUAD) for p in no)
+    bent = ((0.0, 0.0, 0.0), (1.0, 0.0, 0.0), (1.0, 1.0, 1.0), (0.0, 1.0, 0.0))            # :524-545 non-planar quad
+    assert f((0.5, 0.5, 0.25), bent)
+    assert not f((0.5, 0.5, 1.0), bent)
+
+
 def test_triangle_cube_intersection_known_answers(oracle_api):
     """voxelis-math/src/lib.rs:657-812."""
     f = oracle_api.triangle_cube_intersection
