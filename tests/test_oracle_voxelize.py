@@ -114,5 +114,11 @@ def test_host_plan_equals_face_chunk_map(oracle_api):
             assert [tuple(p) for p in pos.tolist()] == list(want.keys())
             for c, key in enumerate(want):
                 assert pf[pc == c].tolist() == want[key]
+    # one triangle across hundreds of chunks: the binding's capacity guess fails and the second call fills the lists
+    verts = np.array([[0.0, 0.0, 0.0], [9.7, 0.3, 0.2], [0.4, 9.1, 8.8]], np.float64)
+    faces = np.array([[1, 2, 3]], np.int32)
+    pos, pc, pf = vx.voxelize_plan(4, 0.5, verts.min(0), verts, faces)
+    want = oracle_api.face_chunk_map(4, 0.5, verts.min(0), verts, faces)
+    assert len(pos) == len(want) > 66 and [tuple(p) for p in pos.tolist()] == list(want.keys()) and not pf.any()
     with __import__("pytest").raises(vx.VoxelisError):
         vx.voxelize_plan(5, 1.0, (0, 0, 0), np.zeros((2, 3)), np.array([[1, 2, 3]], np.int32))   # vertex 3 does not exist

@@ -427,13 +427,19 @@ def voxelize_plan(depth: int, chunk_world_size: float, mesh_min, vertices, faces
     faces = np.ascontiguousarray(faces, np.int32).reshape(-1, 3)
     mm = np.ascontiguousarray(mesh_min, np.float64)
     npairs = C.c_size_t(0)
-    n = _ck(lib().vx_voxelize_plan(depth, float(chunk_world_size), _ptr(mm), len(vertices), _ptr(vertices), len(faces),
-                                   _ptr(faces), None, 0, None, None, 0, C.byref(npairs)))
-    positions = np.zeros((n, 3), np.int32)
-    pc = np.zeros(npairs.value, np.uint32)
-    pf = np.zeros(npairs.value, np.uint32)
-    _ck(lib().vx_voxelize_plan(depth, float(chunk_world_size), _ptr(mm), len(vertices), _ptr(vertices), len(faces),
-                               _ptr(faces), _ptr(positions), n, _ptr(pc), _ptr(pf), npairs.value, C.byref(npairs)))
+    cap_pairs = 2 * len(faces) + 64                     # one call when the guess holds (small faces), else a second
+    cap_chunks = cap_pairs
+    while True:
+        positions = np.zeros((cap_chunks, 3), np.int32)
+        pc = np.zeros(cap_pairs, np.uint32)
+        pf = np.zeros(cap_pairs, np.uint32)
+        n = _ck(lib().vx_voxelize_plan(depth, float(chunk_world_size), _ptr(mm), len(vertices), _ptr(vertices),
+                                       len(faces), _ptr(faces), _ptr(positions), cap_chunks, _ptr(pc), _ptr(pf),
+                                       cap_pairs, C.byref(npairs)))
+        if n <= cap_chunks and npairs.value <= cap_pairs:
+            break
+        cap_chunks, cap_pairs = max(n, 1), max(npairs.value, 1)
+    positions, pc, pf = positions[:n].copy(), pc[:npairs.value].copy(), pf[:npairs.value].copy()
     return positions, pc, pf
 
 

@@ -1306,6 +1306,10 @@ int64_t vx_voxelize_plan(uint8_t max_depth, double chunk_world_size, const doubl
     std::unordered_map<uint64_t, uint32_t> index;
     std::vector<int32_t> pos;
     std::vector<uint32_t> pc, pf;
+    pc.reserve(n_faces + n_faces / 2);
+    pf.reserve(n_faces + n_faces / 2);
+    uint64_t last_key = ~uint64_t(0);  // neighbouring faces of a mesh mostly fall in the chunk of the previous pair
+    uint32_t last_index = 0;
     for (size_t f = 0; f < n_faces; ++f) {
         double mn[3], mx[3];
         for (int a = 0; a < 3; ++a) mn[a] = INFINITY, mx[a] = -INFINITY;
@@ -1328,13 +1332,17 @@ int64_t vx_voxelize_plan(uint8_t max_depth, double chunk_world_size, const doubl
             for (int64_t cz = c0[2]; cz <= c1[2]; ++cz)
                 for (int64_t cx = c0[0]; cx <= c1[0]; ++cx) {
                     const uint64_t key = uint64_t(cx + (1 << 20)) | (uint64_t(cy + (1 << 20)) << 21) | (uint64_t(cz + (1 << 20)) << 42);
-                    auto ins = index.emplace(key, uint32_t(pos.size() / 3));
-                    if (ins.second) {
-                        pos.push_back(int32_t(cx));
-                        pos.push_back(int32_t(cy));
-                        pos.push_back(int32_t(cz));
+                    if (key != last_key) {
+                        auto ins = index.emplace(key, uint32_t(pos.size() / 3));
+                        if (ins.second) {
+                            pos.push_back(int32_t(cx));
+                            pos.push_back(int32_t(cy));
+                            pos.push_back(int32_t(cz));
+                        }
+                        last_key = key;
+                        last_index = ins.first->second;
                     }
-                    pc.push_back(ins.first->second);
+                    pc.push_back(last_index);
                     pf.push_back(uint32_t(f));
                 }
     }
