@@ -9,10 +9,16 @@ Contract (see the task brief): one JSON line on rank 0.
   e2e       = the same through the reference-facing C-ABI call on HOST batches: vx_apply_batches over
               n Batch + n VoxTree handles; bus traffic of the batches and D2H of roots/changed inside the
               timed region (the dense two-array slab entry is reported beside it).
-  roofline  = algorithmic bytes per launch / CUDA-event duration of the apply kernel,
-              against MEASURED_PEAKS.json:hbm_gbs.
+  roofline  = frac: algorithmic bytes per launch (SURVEY §8d formula) / CUDA-event duration of the apply call,
+              against MEASURED_PEAKS.json:hbm_gbs.  The headline input is 1 % dense and the kernels skip the values
+              of untouched blocks, so the line also carries frac_compulsory (bytes this input really needs) and
+              frac_dram (DRAM bytes of the call measured IN THIS RUN by an ncu replay of the same step,
+              profiles/tools/ncu_traffic.py) — the honest figures.
   cpu_baseline / --impl reference = the CPU oracle (a C++ restatement of the reference's Rust
               apply_batch; the Rust reference cannot be built in this image) on the host cores.
+Beside the headline: `headline_dense` (surface-and-below terrain, the dense variant), `others` (BASELINE config 2
+and friends), `latency_single_chunk` (config 1), `strong` (ONE world split across the ranks, config 3), `d7`
+(config 4's per-GPU share) and `global_dedup` (config 5) — the last three every time N > 1.
 Inputs are synthetic (seeded integer value-noise height field); input size 1.34 GB per step is larger
 than the 126 MB L2, so no explicit L2 flush is needed between steps.
 """
@@ -23,6 +29,7 @@ import json
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -36,6 +43,14 @@ DEPTH = 5
 BUDGET = 256 << 20          # VoxInterner memory budget per GPU (README quick-start value)
 NODE_BYTES = 87             # 78 + sizeof(u8) payload + 8 B table slot per NEW node
 CHUNK_BYTES = 2 * 4096 + 8 * 4096 + 8   # masks + values read once + root id written
+WORKLOAD = "perlin_dunes_surface_only_64x8x64_d5_u8"
+METRIC = "chunks/s built+interned (perlin 32^3)"
+D7_CHUNKS_PER_GPU = 2048    # BASELINE config 4: 16 k chunks of 128^3 over 8 GPUs
+
+
+def base_config(n):
+    """Identical in both arms (the driver compares the two config objects)."""
+    return {"workload": WORKLOAD, "chunks_per_step": int(n), "depth": DEPTH, "interner_budget_bytes": BUDGET}
 
 
 def peaks():
@@ -116,9 +131,10 @@ def log(msg: str):
     print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
 
 
-def make_world(rank: int, variant="surface_only"):
+def make_world(rank: int, variant="surface_only", grid=GRID, x_chunk_offset=None):
     from voxelis_b200 import workloads as wl
-    return wl.terrain_world(GRID, DEPTH, variant, wl.U8, x_chunk_offset=rank * GRID[0],
+    return wl.terrain_world(grid, DEPTH, variant, wl.U8,
+                            x_chunk_offset=rank * GRID[0] if x_chunk_offset is None else x_chunk_offset,
                             materials=3 if variant != "surface_only" else 1)
 
 
@@ -153,12 +169,14 @@ def run_reference(args):
     times = [oracle.time_apply_fresh(0, DEPTH, BUDGET, masks, values, threads)[0] for _ in range(args.steps)]
     total = sum(times)
     v = n * args.steps / total
+    nonempty = int(np.count_nonzero(masks[:, :, 0].any(axis=1)))
     line = {
-        "impl": "reference", "metric": "chunks/s built+interned (perlin 32^3)", "value": v, "unit": "chunks/s",
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "chunks/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "perlin_dunes_surface_only_64x8x64_d5_u8", "chunks_per_step": n, "depth": DEPTH,
-                   "interner_budget_bytes": BUDGET},
+        "config": base_config(n),
+        "workload_detail": {"nonempty_chunks": nonempty},
+        "value_nonempty": v * nonempty / n,
         "cpu_baseline": {"value": v, "unit": "chunks/s", "cores": threads, "kind": "port",
                          "sample": f"full {n}-chunk world per step, {threads} threads x private interner; "
                                    "C++ oracle port (Rust reference not buildable here)"},
@@ -166,6 +184,35 @@ def run_reference(args):
         "gpu_launches": 0,
     }
     emit(line)
+
+
+def measure_dram_traffic(workload: str, timeout_s: int = 420):
+    """DRAM bytes of ONE apply call of `workload`, measured now on this GPU: profiles/tools/ncu_traffic.py under ncu
+    (two metrics, one replay pass).  Returns the parsed dict or {"error": ...}."""
+    tool = os.path.join(ROOT, "profiles", "tools", "ncu_traffic.py")
+    out = tempfile.NamedTemporaryFile(prefix="vx_ncu_", suffix=".csv", delete=False).name
+    cmd = ["ncu", "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum", "--print-units", "base",
+           "--clock-control", "none", "--csv", "--log-file", out, sys.executable, tool, workload]
+    try:
+        env = dict(os.environ)
+        for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+            env.pop(k, None)
+        res = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s, env=env)
+        if res.returncode != 0:
+            return {"error": f"ncu rc {res.returncode}: {(res.stderr or res.stdout)[-300:]}"}
+        sys.path.insert(0, os.path.dirname(tool))
+        import ncu_traffic
+        r = ncu_traffic.parse(out)
+        if not r["launches"]:
+            return {"error": "ncu produced no launch rows"}
+        return r
+    except Exception as e:  # ncu missing, counters not permitted, timeout: say so, never fake a number
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
+    finally:
+        try:
+            os.unlink(out)
+        except OSError:
+            pass
 
 
 def around_the_path(vx, dev, local_rank, peak):
@@ -246,8 +293,13 @@ def main():
     ap.add_argument("--no-others", action="store_true", help="skip the secondary workloads")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (profiling runs)")
-    ap.add_argument("--dedup", action="store_true", help="also run the global-dedup variant (BASELINE config 5) "
-                    "after the timed build and report it under 'global_dedup'")
+    ap.add_argument("--no-traffic", action="store_true", help="skip the in-run ncu replay that measures DRAM bytes")
+    ap.add_argument("--traffic-all", action="store_true", help="ncu replay for the dense secondary workloads too")
+    ap.add_argument("--no-d7", action="store_true", help="skip the MaxDepth-7 leg (BASELINE config 4)")
+    ap.add_argument("--no-dedup", action="store_true", help="skip the global-dedup leg when N > 1")
+    ap.add_argument("--dedup", action="store_true", help="run the global-dedup leg at N = 1 too (it is on for N > 1)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="'strong' only runs the one-world legs faster at N = 1; both values are always in the line for N > 1")
     ap.add_argument("--workload", default="perlin", help="profiling only: time another workload in the main loop "
                     "(checkerboard | sum | sum_per_chunk | random255 | below); the headline is 'perlin'")
     args = ap.parse_args()
@@ -260,6 +312,8 @@ def main():
     import torch.distributed as dist
 
     import voxelis_b200 as vx
+    from voxelis_b200 import sharding
+    from voxelis_b200 import workloads as wl
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -293,6 +347,44 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
+    peak, peak_src = peaks()
+    stream = torch.cuda.Stream(dev)          # a real (non-default) stream: events on it bracket our launches
+
+    def time_device(it, depth, n, dm, dv, dr, dc, steps, warmup=3):
+        """`steps` x (reset + one apply call) on `stream`; -> (ms per step, mean ms of the apply call alone)."""
+        for _ in range(warmup):
+            it.reset_async(stream.cuda_stream)
+            it.apply_batches_device(depth, n, dm.data_ptr(), dv.data_ptr(), dr.data_ptr(), dc.data_ptr() if dc is not None else 0,
+                                    stream=stream.cuda_stream)
+        torch.cuda.synchronize()
+        it.sync()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        kev = []
+        for _ in range(steps):
+            it.reset_async(stream.cuda_stream)
+            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            k0.record(stream)
+            it.apply_batches_device(depth, n, dm.data_ptr(), dv.data_ptr(), dr.data_ptr(), dc.data_ptr() if dc is not None else 0,
+                                    stream=stream.cuda_stream)
+            k1.record(stream)
+            kev.append((k0, k1))
+        e1.record(stream)
+        barrier()
+        it.sync()
+        return e0.elapsed_time(e1) / steps, float(np.mean([a.elapsed_time(b) for a, b in kev]))
+
+    def stage_times(it, step, reps=30):
+        it.profile_stages(True)
+        acc = {}
+        for _ in range(reps):
+            step()
+            for name, ms in it.stage_ms():
+                acc[name] = acc.get(name, 0.0) + ms
+        it.profile_stages(False)
+        return {k: v / reps for k, v in acc.items()}
+
     # ---------------------------------------------------------------- inputs
     log("generating the perlin-dunes world")
     budget = BUDGET
@@ -301,17 +393,16 @@ def main():
     elif args.workload == "below":
         masks, values = make_world(rank, "surface_and_below")
     else:
-        from voxelis_b200 import workloads as wl
         masks, values = wl.named_workload(args.workload, 4096)
         budget = 2 << 30
     n = masks.shape[0]
-    log(f"{n} chunks generated; uploading")
+    nonempty = int(np.count_nonzero(masks[:, :, 0].any(axis=1)))
+    log(f"{n} chunks generated ({nonempty} non-empty); uploading")
     d_masks = torch.from_numpy(masks).to(dev)
     d_values = torch.from_numpy(values).to(dev)
     d_roots = torch.zeros(n, dtype=torch.int64, device=dev)
     d_changed = torch.zeros(n, dtype=torch.uint8, device=dev)
     it = vx.VoxInterner.with_memory_budget(budget, vx.U8, local_rank)
-    stream = torch.cuda.Stream(dev)          # a real (non-default) stream: events on it bracket our launches
     torch.cuda.synchronize()
 
     def step_device():
@@ -329,23 +420,8 @@ def main():
     it.sync()
     new_nodes = it.stats()["total_cache_misses"]
     dbg = it.debug_counters()
-    kernel_ms = []
-    barrier()
     sampler.begin()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    kev = []
-    for _ in range(args.steps):
-        it.reset_async(stream.cuda_stream)
-        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        k0.record(stream)
-        it.apply_batches_device(DEPTH, n, d_masks.data_ptr(), d_values.data_ptr(), d_roots.data_ptr(),
-                                d_changed.data_ptr(), stream=stream.cuda_stream)
-        k1.record(stream)
-        kev.append((k0, k1))
-    e1.record(stream)
-    barrier()
-    it.sync()
+    step_ms, kern_ms = time_device(it, DEPTH, n, d_masks, d_values, d_roots, d_changed, args.steps, warmup=0)
     sampler.end()
     window = "timed region"
     if sampler.in_window() < 3:
@@ -359,25 +435,15 @@ def main():
         sampler.end()
         window = "timed region + 0.6 s of identical untimed steps (region shorter than 3 sampling periods)"
     clocks = sampler.stop(window)
-    step_ms = e0.elapsed_time(e1) / args.steps
-    kernel_ms = [a.elapsed_time(b) for a, b in kev]
     step_ms_max = max_over_ranks(step_ms)
     total_chunks = sum_over_ranks(float(n))
+    total_nonempty = sum_over_ranks(float(nonempty))
     value = total_chunks / (step_ms_max * 1e-3)
-    kern_ms = float(np.mean(kernel_ms))
 
     log(f"device-resident: {step_ms_max:.3f} ms/step, apply {kern_ms:.3f} ms")
     # per-launch device times of the apply pipeline (CUDA events between its launches, outside the timed
     # region above: the extra event records would perturb it)
-    it.profile_stages(True)
-    acc = {}
-    prof_steps = 30
-    for _ in range(prof_steps):
-        step_device()
-        for name, ms in it.stage_ms():
-            acc[name] = acc.get(name, 0.0) + ms
-    it.profile_stages(False)
-    stages = {k: v / prof_steps for k, v in acc.items()}
+    stages = stage_times(it, step_device)
     launches_per_step = len(stages) + 1               # + the reset's init kernel
     dom = max(stages, key=stages.get) if stages else "apply_kernel"
     log("stages: " + ", ".join(f"{k} {v * 1e3:.1f} us" for k, v in stages.items()))
@@ -459,8 +525,7 @@ def main():
         log(f"end-to-end (dense slab): {slab_ms:.3f} ms/step")
         del h_masks, h_values
 
-    # ---------------------------------------------------------------- roofline of the apply kernel
-    peak, peak_src = peaks()
+    # ---------------------------------------------------------------- roofline of the apply call
     # SURVEY §8(d) / BASELINE.md §3: masks + values read once + root written + 87 B per NEW node
     algo_bytes = n * CHUNK_BYTES + new_nodes * NODE_BYTES
     achieved = algo_bytes / (kern_ms * 1e-3) / 1e9
@@ -468,26 +533,99 @@ def main():
     # skips them, voxtree.rs:779-781) and the kernel does not load them
     touched_blocks = int(np.count_nonzero(masks[:, :, 0]))
     compulsory = n * (2 * 4096 + 8) + touched_blocks * 8 + new_nodes * NODE_BYTES
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tp) and args.workload == "perlin":
-        traffic = json.load(open(tp)).get("perlin_dunes_surface_only", {}).get("dram_bytes_per_launch")
+    stats_mem = it.memory()
+    del it
+    traffic, traffic_detail = None, None
+    if rank == 0 and not args.no_traffic:
+        log("measuring DRAM traffic of one apply call (ncu replay of the same step)")
+        t = measure_dram_traffic(args.workload if args.workload in ("perlin", "below") else f"{args.workload}:4096")
+        if "error" in t:
+            traffic_detail = {"source": "unavailable", "error": t["error"]}
+            log("ncu replay failed: " + t["error"])
+        else:
+            traffic = t["dram_bytes"]
+            traffic_detail = {"source": "ncu replay in this run (profiles/tools/ncu_traffic.py)", "read": t["read"], "write": t["write"],
+                              "launches": t["launches"]}
+            log(f"DRAM traffic per apply call: {traffic / 1e6:.1f} MB")
+
+    # ---------------------------------------------------------------- the dense headline: surface-and-below terrain
+    headline_dense = None
+    if rank == 0 and not args.no_others and args.workload == "perlin":
+        try:
+            log("dense headline: perlin surface-and-below (3 materials)")
+            m2, v2 = make_world(0, "surface_and_below")
+            ne2 = int(np.count_nonzero(m2[:, :, 0].any(axis=1)))
+            tb2 = int(np.count_nonzero(m2[:, :, 0]))
+            dm2, dv2 = torch.from_numpy(m2).to(dev), torch.from_numpy(v2).to(dev)
+            itb = vx.VoxInterner.with_memory_budget(BUDGET, vx.U8, local_rank)
+            sms, kms = time_device(itb, DEPTH, n, dm2, dv2, d_roots, None, max(20, min(args.steps, 200)))
+            nn2 = itb.stats()["total_cache_misses"]
+
+            def step2():
+                itb.reset_async(stream.cuda_stream)
+                itb.apply_batches_device(DEPTH, n, dm2.data_ptr(), dv2.data_ptr(), d_roots.data_ptr(), stream=stream.cuda_stream)
+            st2 = stage_times(itb, step2, 10)
+            ab2 = n * CHUNK_BYTES + nn2 * NODE_BYTES
+            comp2 = n * (2 * 4096 + 8) + tb2 * 8 + nn2 * NODE_BYTES
+            headline_dense = {"workload": "perlin_dunes_surface_and_below_3mat_64x8x64_d5_u8", "chunks": n, "nonempty_chunks": ne2,
+                              "touched_blocks": tb2, "value": n / (sms * 1e-3), "value_nonempty": ne2 / (sms * 1e-3),
+                              "unit": "chunks/s", "ms_per_step": sms, "kernel_ms": kms, "new_nodes": nn2,
+                              "roofline": {"frac": ab2 / (kms * 1e-3) / 1e9 / peak, "achieved": ab2 / (kms * 1e-3) / 1e9,
+                                           "algorithmic_bytes_per_launch": ab2, "compulsory_bytes_per_launch": comp2,
+                                           "frac_compulsory": comp2 / (kms * 1e-3) / 1e9 / peak, "stages_ms": st2}}
+            del dm2, dv2, itb
+            if not args.no_traffic:
+                t = measure_dram_traffic("below")
+                if "error" not in t:
+                    headline_dense["roofline"]["traffic"] = t["dram_bytes"]
+                    headline_dense["roofline"]["frac_dram"] = t["dram_bytes"] / (kms * 1e-3) / 1e9 / peak
+        except Exception as e:
+            headline_dense = {"error": str(e)}
+
+    # ---------------------------------------------------------------- config 1: one 32^3 set_uniform chunk, host Batch
+    latency = None
+    if rank == 0 and not args.no_others:
+        try:
+            log("config 1: single-chunk latency")
+            itl = vx.VoxInterner.with_memory_budget(BUDGET, vx.U8, local_rank)
+            mu, vu = wl.named_workload("uniform", 1)
+            tr = vx.VoxTree(DEPTH, vx.U8)
+            b = tr.create_batch()
+            b.assign(mu[0], vu[0])
+            ts = []
+            for i in range(260):
+                itl.reset()
+                vx.trees_forget([tr])
+                t0 = time.perf_counter()
+                tr.apply_batch(itl, b)            # synchronous: H2D of the touched units, launches, root back in the handle
+                ts.append(time.perf_counter() - t0)
+            ts = np.array(ts[10:]) * 1e6
+            assert tr.is_leaf()
+            from oracle import oracle
+            to = []
+            for i in range(200):
+                t1, _ = oracle.time_apply_fresh(0, DEPTH, BUDGET, mu, vu, 1)
+                to.append(t1 * 1e6)
+            latency = {"workload": "single 32^3 chunk, set_uniform, u8, 256 MiB interner (BASELINE config 1)",
+                       "gpu_us_median": float(np.median(ts)), "gpu_us_p10": float(np.percentile(ts, 10)),
+                       "what_gpu": "vx_tree_apply_batch on a host Batch handle, wall clock around the synchronous call",
+                       "oracle_us_median": float(np.median(to)), "oracle_note": "C++ port on one host core, apply only (interner creation excluded)",
+                       "reference_published_us": 23.11, "reference_source": "docs/benches.md:221-222 (M3 Max, i32, includes old-tree teardown)"}
+            del itl
+        except Exception as e:
+            latency = {"error": str(e)}
 
     # ---------------------------------------------------------------- secondary workloads (rank 0)
     others = {}
     if rank == 0 and not args.no_others:
-        from voxelis_b200 import workloads as wl
-        del it                                    # one interner at a time: free the headline one first
         # (name, generator, interner budget): random255 creates ~4 936 new nodes per chunk
-        sets = [("checkerboard_x4096", lambda: wl.named_workload("checkerboard", 4096), BUDGET),
-                ("set_sum_x4096", lambda: wl.named_workload("sum", 4096), BUDGET),
-                ("sum_per_chunk_x4096", lambda: wl.named_workload("sum_per_chunk", 4096), BUDGET),
-                ("random255_x4096", lambda: wl.named_workload("random255", 4096), 2 << 30),
-                ("perlin_surface_and_below_3mat", lambda: make_world(0, "surface_and_below"), BUDGET)]
-        sets.append(("set_sum_i32_x4096", lambda: wl.named_workload("sum", 4096, dtype=wl.I32), BUDGET))
-        sets.append(("d7_128cube_random255_x24", lambda: wl.named_workload("random255", 24, depth=7), 3 << 30))
-        sets.append(("d6_64cube_cell4_random255_x256", lambda: wl.named_workload("cell4_random255", 256, depth=6), 1 << 30))
-        for name, gen, budget in sets:
+        sets = [("checkerboard_x4096", lambda: wl.named_workload("checkerboard", 4096), BUDGET, "checkerboard:4096"),
+                ("set_sum_x4096", lambda: wl.named_workload("sum", 4096), BUDGET, "sum:4096"),
+                ("sum_per_chunk_x4096", lambda: wl.named_workload("sum_per_chunk", 4096), BUDGET, "sum_per_chunk:4096"),
+                ("random255_x4096", lambda: wl.named_workload("random255", 4096), 2 << 30, "random255:4096"),
+                ("set_sum_i32_x4096", lambda: wl.named_workload("sum", 4096, dtype=wl.I32), BUDGET, None),
+                ("d6_64cube_cell4_random255_x256", lambda: wl.named_workload("cell4_random255", 256, depth=6), 1 << 30, None)]
+        for name, gen, budget2, tname in sets:
             try:
                 log(f"secondary workload {name}")
                 m2, v2 = gen()
@@ -496,31 +634,30 @@ def main():
                 chunk_bytes2 = 2 * m2.shape[1] + 8 * m2.shape[1] * (4 if v2.dtype == np.int32 else 1) + 8
                 dt2 = vx.I32 if v2.dtype == np.int32 else vx.U8
                 esz = 4 if dt2 == vx.I32 else 1
-                it2 = vx.VoxInterner.with_memory_budget(budget, dt2, local_rank)
+                it2 = vx.VoxInterner.with_memory_budget(budget2, dt2, local_rank)
                 dm, dv = torch.from_numpy(m2).to(dev), torch.from_numpy(v2).to(dev)
                 dr = torch.zeros(n2, dtype=torch.int64, device=dev)
-                ts = []
-                for i in range(6):
-                    it2.reset_async(stream.cuda_stream)
-                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    a.record(stream)
-                    it2.apply_batches_device(depth2, n2, dm.data_ptr(), dv.data_ptr(), dr.data_ptr(),
-                                             stream=stream.cuda_stream)
-                    b.record(stream)
-                    torch.cuda.synchronize()
-                    it2.sync()
-                    if i >= 2:
-                        ts.append(a.elapsed_time(b))
+                _, ms = time_device(it2, depth2, n2, dm, dv, dr, None, 20)
                 nn = it2.stats()["total_cache_misses"]
                 d2 = it2.debug_counters()
-                ms = float(np.mean(ts))
+
+                def step2():
+                    it2.reset_async(stream.cuda_stream)
+                    it2.apply_batches_device(depth2, n2, dm.data_ptr(), dv.data_ptr(), dr.data_ptr(), stream=stream.cuda_stream)
+                st2 = stage_times(it2, step2, 5)
                 ab = n2 * chunk_bytes2 + nn * (NODE_BYTES + esz - 1)
                 others[name] = {"depth": depth2, "chunks": n2, "chunks_per_s": n2 / (ms * 1e-3), "kernel_ms": ms,
-                                "new_nodes": nn,
+                                "new_nodes": nn, "algorithmic_bytes": ab,
                                 "achieved_gbs": ab / (ms * 1e-3) / 1e9, "frac": ab / (ms * 1e-3) / 1e9 / peak,
                                 "branch_calls": d2["branch_calls"], "probe_steps": d2["probe_steps"],
-                                "cache_hits_local": d2["cache_hits_local"]}
+                                "cache_hits_local": d2["cache_hits_local"], "stages_ms": st2}
                 del dm, dv, dr, it2
+                if args.traffic_all and tname and not args.no_traffic:
+                    t = measure_dram_traffic(tname)
+                    if "error" not in t:
+                        others[name]["traffic"] = t["dram_bytes"]
+                        others[name]["traffic_over_algorithmic"] = t["dram_bytes"] / ab
+                        others[name]["frac_dram"] = t["dram_bytes"] / (ms * 1e-3) / 1e9 / peak
             except Exception as e:  # a secondary workload must never take the headline line down
                 others[name] = {"error": str(e)}
 
@@ -531,55 +668,118 @@ def main():
         except Exception as e:
             others["around_the_path"] = {"error": str(e)}
 
+    # ---------------------------------------------------------------- strong scaling: ONE world over the ranks (config 3)
+    strong = None
+    if world > 1 or args.scaling == "strong":
+        log("strong scaling: one 64x8x64 world split into X slabs")
+        lo, hi = sharding.slab_bounds(rank, world, GRID[0])
+        per = GRID[1] * GRID[2]
+        ms_, vs_ = make_world(0, grid=(hi - lo, GRID[1], GRID[2]), x_chunk_offset=lo)   # the slab of rank 0's world this rank owns
+        ns = ms_.shape[0]
+        assert ns == (hi - lo) * per
+        its = vx.VoxInterner.with_memory_budget(BUDGET, vx.U8, local_rank)
+        dms, dvs = torch.from_numpy(ms_).to(dev), torch.from_numpy(vs_).to(dev)
+        drs = torch.zeros(ns, dtype=torch.int64, device=dev)
+        s_ms, s_k = time_device(its, DEPTH, ns, dms, dvs, drs, None, max(50, min(args.steps, 500)))
+        s_ms_max = max_over_ranks(s_ms)
+        tot = sum_over_ranks(float(ns))
+        one_gpu_ms = max_over_ranks(step_ms)       # every rank also timed a FULL world above (the weak leg)
+        strong = {"world": WORLD_NAME, "chunks_total": int(tot), "chunks_per_gpu": ns, "slab_x": [lo, hi],
+                  "ms_per_step": s_ms_max, "value": tot / (s_ms_max * 1e-3), "unit": "chunks/s",
+                  "one_gpu_full_world_ms": one_gpu_ms, "speedup_vs_one_gpu": one_gpu_ms / s_ms_max,
+                  "efficiency": one_gpu_ms / s_ms_max / world,
+                  "note": "per-GPU interners, no data-path collective; a slab of 1/N of the world is a small call: the "
+                          "level-synchronous pipeline has a floor of a few dependent round trips per launch"}
+        del its, dms, dvs, drs
+
+    # ---------------------------------------------------------------- config 4: MaxDepth 7, 2048 chunks per GPU
+    d7 = None
+    if not args.no_d7 and not args.no_others:
+        try:
+            log("config 4: 128^3 chunks, per-GPU share generated on the device")
+            D7, n7 = 7, D7_CHUNKS_PER_GPU
+            B7 = 8 ** (D7 - 1)
+            budget7 = 56 << 30                     # 2048 x 299 593 new branches x 79 B
+            it7 = vx.VoxInterner.with_memory_budget(budget7, vx.U8, local_rank)
+            dm7 = torch.empty((n7, B7, 2), dtype=torch.uint8, device=dev)
+            dv7 = torch.empty((n7, B7, 8), dtype=torch.uint8, device=dev)
+            dr7 = torch.zeros(n7, dtype=torch.int64, device=dev)
+            d7 = {"chunks_per_gpu": n7, "depth": D7, "bytes_of_batches_per_gpu": int(dm7.numel() + dv7.numel()),
+                  "interner_budget_bytes": budget7, "per_gpu_interners": True, "distributions": {}}
+            for name, k, cell in (("k255", 255, 1), ("k4", 4, 1), ("cell4_k255", 255, 4)):
+                it7.random_batches_device(D7, n7, dm7.data_ptr(), dv7.data_ptr(), k, cell, chunk0=rank * n7, stream=stream.cuda_stream)
+                torch.cuda.synchronize()
+                s_ms, s_k = time_device(it7, D7, n7, dm7, dv7, dr7, None, 3, warmup=1)
+                nn = it7.stats()["total_cache_misses"]
+                s_ms_max = max_over_ranks(s_ms)
+                ab = n7 * (10 * B7 + 8) + nn * NODE_BYTES
+                d7["distributions"][name] = {"ms_per_step": s_ms_max, "chunks_per_s": world * n7 / (s_ms_max * 1e-3),
+                                             "new_nodes_per_gpu": nn, "kernel_ms": s_k,
+                                             "frac": ab / (s_k * 1e-3) / 1e9 / peak, "new_nodes_per_s_per_gpu": nn / (s_k * 1e-3)}
+                log(f"  d7 {name}: {s_ms_max:.2f} ms/step, {nn} new nodes")
+            d7["chunks_per_s"] = d7["distributions"]["k255"]["chunks_per_s"]
+            d7["note"] = (f"BASELINE config 4 is 16 384 chunks over 8 GPUs = {n7} per GPU; every rank builds that share "
+                          "(weak in N), batches generated in HBM by vx_random_batches_device, interner reset every step")
+            del it7, dm7, dv7, dr7
+        except Exception as e:
+            d7 = {"error": str(e)}
+            log(f"d7 leg failed: {e}")
+
     # ---------------------------------------------------------------- global dedup variant (config 5)
     dedup_info = None
-    if args.dedup:
-        from voxelis_b200 import dedup as vd
-        log("global dedup variant")
-        itd = vx.VoxInterner.with_memory_budget(BUDGET, vx.U8, local_rank)
-        rts, _ = itd.apply_batches_slab(DEPTH, d_masks.data_ptr(), d_values.data_ptr(), n=n)
-        local_unique = itd.next_index - 1
-        barrier()
-        t0 = time.perf_counter()
-        if world > 1:
-            shard, groots, summ = vd.global_dedup_dist(itd, rts, BUDGET, vx.U8, local_rank)
-        else:
-            shards, groots_l, summ = vd.global_dedup_local([itd], [rts], BUDGET, vx.U8, local_rank)
-        torch.cuda.synchronize()
-        barrier()
-        dd_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
-        dedup_info = {"ms": dd_ms, "rounds": summ["rounds"], "global_unique_branches": summ["branches"],
-                      "global_unique_leaves": summ["leaves"], "bytes_sent_all_ranks": summ["bytes_sent"],
-                      "sum_of_per_gpu_unique_nodes": int(sum_over_ranks(float(local_unique))),
-                      "exchange": "torch.distributed.all_to_all_single over NCCL" if world > 1 else "single rank (no exchange)"}
-        del itd
-        if rank == 0:   # the reference's model: ONE interner for every chunk of every rank (oracle, CPU)
-            from oracle import oracle
-            ref = oracle.VoxInterner(4 * BUDGET)
-            for r in range(world):
-                mr, vr = (masks, values) if r == 0 else make_world(r)
-                ref.apply_batches_fresh(DEPTH, mr, vr)
-            st = ref.stats()
-            dedup_info["oracle_single_interner"] = {"branches": st["branch_nodes"] - 1, "leaves": st["leaf_nodes"]}
-            dedup_info["matches_oracle"] = (st["branch_nodes"] - 1 == summ["branches"] and st["leaf_nodes"] == summ["leaves"])
+    if (world > 1 and not args.no_dedup) or args.dedup:
+        try:
+            from voxelis_b200 import dedup as vd
+            log("global dedup variant")
+            itd = vx.VoxInterner.with_memory_budget(BUDGET, vx.U8, local_rank)
+            rts, _ = itd.apply_batches_slab(DEPTH, d_masks.data_ptr(), d_values.data_ptr(), n=n)
+            local_unique = itd.next_index - 1
+            summ, dd_ms = None, None
+            for rep in range(2):                   # second run timed (first: allocations, NCCL channel setup)
+                barrier()
+                t0 = time.perf_counter()
+                shard, groots, summ = vd.global_dedup(itd, rts, BUDGET, vx.U8, local_rank)
+                torch.cuda.synchronize()
+                barrier()
+                dd_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+                del shard, groots
+            dedup_info = {"ms": dd_ms, "rounds": summ["rounds"], "global_unique_branches": summ["branches"],
+                          "global_unique_leaves": summ["leaves"], "bytes_sent_all_ranks": summ["bytes_sent"],
+                          "sum_of_per_gpu_unique_nodes": int(sum_over_ranks(float(local_unique))),
+                          "exchange": summ.get("exchange", "single rank (no exchange)")}
+            del itd
+            if rank == 0:   # the reference's model: ONE interner for every chunk of every rank (oracle, CPU)
+                from oracle import oracle
+                ref = oracle.VoxInterner(4 * BUDGET)
+                for r in range(world):
+                    mr, vr = (masks, values) if r == 0 else make_world(r)
+                    ref.apply_batches_fresh(DEPTH, mr, vr)
+                st = ref.stats()
+                dedup_info["oracle_single_interner"] = {"branches": st["branch_nodes"] - 1, "leaves": st["leaf_nodes"]}
+                dedup_info["matches_oracle"] = bool(st["branch_nodes"] - 1 == summ["branches"] and st["leaf_nodes"] == summ["leaves"])
+        except Exception as e:
+            dedup_info = {"error": str(e)}
+            log(f"dedup leg failed: {e}")
 
     cpu = None
-    log("cpu baseline")
     if rank == 0 and world == 1 and not args.no_cpu:
+        log("cpu baseline")
         cpu = cpu_baseline(masks, values, 1)
         cpu["all_cores"] = cpu_baseline(masks, values, os.cpu_count() or 1, target_s=6.0)
 
     if rank == 0:
         line = {
-            "metric": "chunks/s built+interned (perlin 32^3)", "value": value, "unit": "chunks/s",
+            "metric": METRIC, "value": value, "unit": "chunks/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms_max,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "perlin_dunes_surface_only_64x8x64_d5_u8" if args.workload == "perlin" else args.workload,
-                       "chunks_per_step_per_gpu": n,
-                       "depth": DEPTH, "interner_budget_bytes": BUDGET, "new_nodes_per_step": new_nodes,
-                       "l2": "inputs (1.34 GB/step) exceed the 126 MB L2; interner reset every step",
-                       "step": "vx_interner_reset_async + one vx_apply_batches_device call",
-                       "per_step_counters": dbg},
+            "config": base_config(n) if args.workload == "perlin" else dict(base_config(n), workload=args.workload),
+            "workload_detail": {"chunks_per_step_per_gpu": n, "nonempty_chunks": nonempty, "touched_blocks": touched_blocks,
+                                "new_nodes_per_step": new_nodes,
+                                "l2": "inputs (1.34 GB/step) exceed the 126 MB L2; interner reset every step",
+                                "step": "vx_interner_reset_async + one vx_apply_batches_device call",
+                                "per_step_counters": dbg,
+                                "device_memory": stats_mem},
+            "value_nonempty": total_nonempty / (step_ms_max * 1e-3),
             "e2e": {"value": e2e_value, "unit": "chunks/s", "ms_per_step": e2e_ms_max,
                     # per step: descriptors (8 B per chunk + 4 B per touched unit) by the copy engine; touched
                     # units' masks (1 KiB each) and the values of blocks with a set bit (8 B each, lower bound:
@@ -594,7 +794,9 @@ def main():
                     "phases_us": e2e_trace, "dense_slab_variant": e2e_slab},
             "gpu_launches": args.steps * launches_per_step,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src,
+                         "traffic": traffic, "traffic_detail": traffic_detail, "peak_source": peak_src,
+                         "frac_compulsory": compulsory / (kern_ms * 1e-3) / 1e9 / peak,
+                         "frac_dram": (traffic / (kern_ms * 1e-3) / 1e9 / peak) if traffic else None,
                          # the path is a pipeline of dependent launches (vx_bulk.cuh): the roofline is taken over
                          # the whole apply call, the per-launch times are listed beside it
                          "kernel": "apply call = " + " + ".join(stages) if stages else "apply_kernel<u8,false>",
@@ -603,21 +805,32 @@ def main():
                          "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": algo_bytes,
                          "compulsory_bytes_per_launch": compulsory,
                          "achieved_compulsory": compulsory / (kern_ms * 1e-3) / 1e9,
-                         "note": "achieved uses the dense SURVEY 8(d) formula; the input is sparse "
-                                 f"({touched_blocks} of {n * 4096} blocks have a set bit) and the kernel skips the "
-                                 "values of untouched blocks, so DRAM traffic is below the formula"},
+                         "note": "frac follows the SURVEY 8(d) dense formula; the input is sparse "
+                                 f"({touched_blocks} of {n * 4096} blocks have a set bit, {nonempty} of {n} chunks are "
+                                 "non-empty) and the kernels skip the values of untouched blocks: frac_compulsory counts "
+                                 "only the bytes this input needs, frac_dram the DRAM bytes ncu measured for the same step"},
             "clocks": clocks,
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if headline_dense:
+            line["headline_dense"] = headline_dense
+        if latency:
+            line["latency_single_chunk"] = latency
         if others:
             line["others"] = others
+        if strong:
+            line["strong"] = strong
+        if d7:
+            line["d7"] = d7
         if dedup_info:
             line["global_dedup"] = dedup_info
         emit(line)
     if world > 1:
         dist.destroy_process_group()
 
+
+WORLD_NAME = "perlin_dunes_surface_only_64x8x64_d5_u8 (rank 0's world)"
 
 if __name__ == "__main__":
     main()

@@ -65,6 +65,14 @@ typedef struct vx_stats {
     uint64_t max_generation, generations_overflows;
 } vx_stats;
 
+/* Device memory an interner really holds (the reference's `actual_budget` only counts the node pools): pools =
+ * capacity x (78 + sizeof T + 4 B free-list entry), the hash tables on top of the budget, and the scratch the builders
+ * have grown to (level lists of the bulk builder, staging slabs of host batches, release frontiers). */
+typedef struct vx_memory {
+    uint64_t pools_bytes, table_bytes, leaf_table_bytes, bulk_scratch_bytes, stage_bytes, other_scratch_bytes;
+    uint64_t pinned_host_bytes, total_device_bytes;
+} vx_memory;
+
 const char* vx_last_error(void);
 int vx_abi_version(void);
 int vx_device_count(void); /* number of CUDA devices, <0 on error */
@@ -92,6 +100,10 @@ int vx_interner_get_value(const vx_interner*, vx_block_id id, int64_t* out);
 int vx_interner_get_children(const vx_interner*, vx_block_id id, vx_block_id out[8]);
 /* InternerStats (feature memory_stats) */
 int vx_interner_stats(const vx_interner*, vx_stats* out);
+int vx_interner_memory(const vx_interner*, vx_memory* out);
+/* Diagnostic: the bulk builder's unit memo — out[0] entries inserted since the last wipe, out[1] occupied slots,
+ * out[2], out[3] the first occupied entry. */
+int vx_interner_debug_memo(const vx_interner*, uint64_t out[4]);
 /* Copies the first `next_index` entries of each pool to HOST arrays (any may be NULL):
  * children[n][8], values[n] (widened to int64), ref_counts[n], generations[n], hashes[n].
  * `cap` = entries available in the caller's arrays; returns next_index or <0. */
@@ -198,12 +210,18 @@ int vx_apply_batches_device(vx_interner*, uint8_t max_depth, size_t n, const uin
  *                              input synthesis, not part of the path); column (x0 + i, z0 + j)
  *   vx_terrain_batches_device  grid = chunks along (x, y, z), chunk index (cx*gy + cy)*gz + cz, d_heights sized
  *                              [gx*N][gz*N]; surface_only: the voxel at Y == h (shapes.rs:302-304), else every voxel
- *                              with Y <= h (:306-309); materials 3: 1 at the surface, 2 for the next three, 3 below
- *                              (:340-355); masks[n][B][2], values[n][B][8] of the interner's dtype */
+ *                              with Y <= h (:306-309); materials 3: 1 for Y >= h-2, 2 for Y >= h-4, 3 deeper
+ *                              (:344-350); masks[n][B][2], values[n][B][8] of the interner's dtype */
 int vx_terrain_heights_device(vx_interner*, uint32_t nx, uint32_t nz, uint64_t seed, uint32_t height, int64_t x0,
                               int64_t z0, int32_t* d_heights, void* stream);
 int vx_terrain_batches_device(vx_interner*, uint8_t max_depth, const uint32_t grid[3], const int32_t* d_heights,
                               int surface_only, int materials, uint8_t* d_masks, void* d_values, void* stream);
+/* High-entropy benchmark batches written in device memory (BASELINE config 2 "high-entropy" / config 4; the reference
+ * fills such batches voxel by voxel from a PRNG before timing, voxtree_bench.rs:553-563 pattern): n chunks,
+ * v = 1 + splitmix64(cell_index + ((seed_base + chunk0 + i) << 32)) mod k per cell of cell^3 voxels; k == 4 gives
+ * splitmix64 mod 4 with 0 recorded as a clear.  Asynchronous on `stream`. */
+int vx_random_batches_device(vx_interner*, uint8_t max_depth, size_t n, uint64_t seed_base, uint64_t chunk0, uint32_t k,
+                             uint32_t cell, uint8_t* d_masks, void* d_values, void* stream);
 
 /* The voxeliser's two steps (voxelis-voxelize/src/lib.rs), SURVEY §8f-4:
  *   vx_voxelize_plan           Voxelizer::build_face_to_chunk_map (:113-156), host work as in the reference: which faces
@@ -296,6 +314,38 @@ typedef struct vx_vtm_info {
 /* import_model_from_vtm — io/import.rs:14-98: header, zstd (when flagged), MD5 check, then vx_model_deserialize. */
 int64_t vx_import_vtm(vx_interner*, const char* path, vx_vtm_info* info_out, int32_t* positions_out,
                       vx_block_id* roots_out, size_t cap);
+
+/* ---------------------------------------------------------------- multi-GPU world (new) ---- */
+/* One process per GPU.  The reference keeps ONE interner for the whole world (world/voxmodel.rs:31-32); here every
+ * GPU builds its chunks into a private interner with no communication (vx_apply_batches*), and
+ * vx_world_global_dedup optionally merges the private interners into hash-partitioned GLOBAL shards — the Voxelis
+ * Bible's "shard the pattern map by hash % N" (§3.9, §13): height-synchronous rounds, records travel to
+ * owner = hash(children as global ids) mod G over NCCL send / recv (NVLink), owners intern them
+ * (get_or_create_branch / _leaf, interner/mod.rs:627-829) and answer with 8-byte global ids.
+ *   global id = the owner shard's BlockId with the owner's rank in generation bits [44..46].
+ * NCCL is loaded at run time (libnccl.so.2); without it these entries return VX_E_UNSUPPORTED.
+ *   vx_world_unique_id     rank 0 makes the 128-byte rendezvous id; the host passes it to the other processes
+ *   vx_world_create        collective over the n_ranks processes (ncclCommInitRank), n_ranks <= 8
+ *   vx_world_barrier       device-side barrier across the ranks on `stream`, no host synchronisation
+ *   vx_world_global_dedup  collective: `local` = this rank's private interner, `shard` = this rank's (empty) global
+ *                          shard, roots[n_roots] = this rank's chunk roots (host) -> global_roots_out (host).
+ *                          Sum over ranks of the shard sizes == the node count of ONE shared interner. */
+#define VX_WORLD_ID_BYTES 128
+typedef struct vx_world vx_world;
+typedef struct vx_dedup_summary {
+    uint64_t rounds, branches, leaves;          /* global unique nodes over all shards */
+    uint64_t bytes_sent;                        /* all ranks, records + ids */
+    uint64_t local_nodes_all_ranks;             /* sum of the private interners' node counts (before the merge) */
+    uint64_t this_shard_branches, this_shard_leaves;
+} vx_dedup_summary;
+int vx_world_unique_id(uint8_t out[VX_WORLD_ID_BYTES]);
+vx_world* vx_world_create(int n_ranks, int rank, const uint8_t id[VX_WORLD_ID_BYTES], int device);
+void vx_world_destroy(vx_world*);
+int vx_world_size(const vx_world*);
+int vx_world_rank(const vx_world*);
+int vx_world_barrier(vx_world*, void* stream);
+int vx_world_global_dedup(vx_world*, vx_interner* local, vx_interner* shard, size_t n_roots, const vx_block_id* roots,
+                          vx_block_id* global_roots_out, vx_dedup_summary* out);
 
 /* ---------------------------------------------------------------- global dedup (new) ------ */
 /* Optional merge of per-GPU interners into hash-partitioned global shards (the Voxelis Bible's

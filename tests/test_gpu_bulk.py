@@ -189,3 +189,61 @@ def test_bulk_lod_values_are_stable(gpu_api, oracle_api, monkeypatch):
         gorder = np.argsort(gs["numbers"], kind="stable")[np.count_nonzero(gs["numbers"] == 0):]
         assert np.array_equal(gs["stream"], cs["stream"]), rep
         assert np.array_equal(gd["values"][gorder], cd["values"][corder]), rep
+
+
+# ---------------------------------------------------------------------------------------------- unit memo
+def _repeating_world(dtype):
+    """Busy units whose content repeats: identical chunks (checkerboard, sum), 255-periodic chunks, solid rock next
+    to them, and unique high-entropy chunks in between (every unit of those is its own representative)."""
+    parts = [wl.named_workload("checkerboard", 40, 5, dtype),
+             wl.named_workload("sum", 24, 5, dtype),
+             wl.batch_from_function(5, wl.p_random(255), dtype, 3),
+             wl.named_workload("sum_per_chunk", 300, 5, dtype),      # chunk c and c + 255 are identical
+             wl.named_workload("uniform", 6, 5, dtype),
+             wl.named_workload("checkerboard", 9, 5, dtype),
+             wl.terrain_world((3, 2, 3), 5, "surface_and_below", dtype, materials=3)]
+    return np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])
+
+
+@pytest.mark.parametrize("dtype", [wl.U8, wl.I32], ids=["u8", "i32"])
+@pytest.mark.parametrize("memo", ["1", "0"])
+def test_unit_memo_matches_oracle(gpu_api, oracle_api, dtype, memo, monkeypatch):
+    """Aliased units take the node AND the counters of the first unit with their content: DAG, refcounts and every
+    InternerStats counter equal the oracle's serial application, with the memo on and off."""
+    monkeypatch.setenv("VX_BUILDER", "bulk")
+    monkeypatch.setenv("VX_UNIT_MEMO", memo)
+    masks, values = _repeating_world(dtype)
+    r = parity.build_both(gpu_api, oracle_api, 5, masks, values, dtype, budget=256 << 20)
+    parity.assert_parity(gpu_api, oracle_api, 5, *r)
+
+
+def test_unit_memo_is_per_call(gpu_api, oracle_api, monkeypatch):
+    """Entries of one call never serve another (they name units of that call): three calls into one interner with
+    overlapping content, a reset in between, and a call large enough to trigger the table wipe."""
+    vx, o = gpu_api, oracle_api
+    monkeypatch.setenv("VX_BUILDER", "bulk")
+    g = vx.VoxInterner.with_memory_budget(2 << 30)
+    c = o.VoxInterner(2 << 30)
+    m1, v1 = wl.named_workload("checkerboard", 20, 5)
+    m2, v2 = wl.named_workload("sum", 20, 5)
+    m3, v3 = wl.batch_from_function(5, wl.p_random(255), wl.U8, 4200)     # 33 600 distinct busy units: beyond MEMO_CLEAR_AT
+    groots, croots, gch, cch = [], [], [], []
+    for m, v in ((m1, v1), (m2, v2), (np.concatenate([m2, m1]), np.concatenate([v2, v1])), (m3[:16], v3[:16]), (m1, v1)):
+        r, ch = g.apply_batches_slab(5, m, v)
+        groots.append(r)
+        gch.append(ch)
+        r, ch = c.apply_batches_fresh(5, m, v)
+        croots.append(r)
+        cch.append(ch)
+    parity.assert_parity(vx, o, 5, g, np.concatenate(groots), np.concatenate(gch), c, np.concatenate(croots), np.concatenate(cch))
+    # the big call: wipes the table at its end; the calls after it still alias correctly
+    g.reset()
+    r3, _ = g.apply_batches_slab(5, m3, v3)
+    ra, _ = g.apply_batches_slab(5, np.concatenate([m1, m2]), np.concatenate([v1, v2]))
+    rb, _ = g.apply_batches_slab(5, m2, v2)
+    assert len(set(ra[:20].tolist())) == 1 and len(set(ra[20:].tolist())) == 1 and ra[20] == rb[0]
+    dense = g.roots_to_vec(np.concatenate([r3[:4], ra[:1], rb[:1]]), 5)
+    for i, (m, v) in enumerate([(m3[0], v3[0]), (m3[1], v3[1]), (m3[2], v3[2]), (m3[3], v3[3]), (m1[0], v1[0]), (m2[0], v2[0])]):
+        assert np.array_equal(dense[i], wl.dense_expected(m, v))
+    st = g.stats()
+    assert st["branch_nodes"] - 1 == 4200 * 4681 + 5 + 83       # all-miss chunks + checkerboard + sum (SURVEY §8c)

@@ -57,3 +57,22 @@ def test_generated_world_builds_like_the_numpy_world(gpu_api, oracle_api):
     croots, cchanged = c.apply_batches_fresh(depth, em, ev, flags & 1, fills, (flags >> 1) & 1)
     parity.assert_parity(gpu_api, oracle_api, depth, g, roots.cpu().numpy().astype(np.uint64),
                          changed.cpu().numpy(), c, croots, cchanged)
+
+
+@pytest.mark.parametrize("dtype", [wl.U8, wl.I32], ids=["u8", "i32"])
+@pytest.mark.parametrize("depth,k,cell", [(5, 255, 1), (5, 4, 1), (6, 255, 4), (4, 17, 2)])
+def test_random_batches_equal_numpy_generator(gpu_api, depth, k, cell, dtype):
+    """vx_random_batches_device is workloads.p_random byte for byte (masks incl. the clear bits of k = 4)."""
+    import torch
+    vx = gpu_api
+    n, c0 = 3, 5
+    B = wl.blocks_per_chunk(depth)
+    want_m, want_v = wl.batch_from_function(depth, wl.p_random(k, cell), dtype, n, chunk_arg=[c0 + i for i in range(n)])
+    g = vx.VoxInterner.with_memory_budget(64 << 20, dtype)
+    dm = torch.empty((n, B, 2), dtype=torch.uint8, device="cuda")
+    dv = torch.empty((n, B, 8), dtype=torch.uint8 if dtype == wl.U8 else torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    g.random_batches_device(depth, n, dm.data_ptr(), dv.data_ptr(), k, cell, chunk0=c0)
+    g.sync()
+    assert np.array_equal(dm.cpu().numpy(), want_m)
+    assert np.array_equal(dv.cpu().numpy(), want_v)

@@ -6,8 +6,8 @@ call runs hand-written sm_100a kernels in libvoxelis_b200.so.  There is no CPU f
 importing works anywhere, but ``lib()`` raises if the CUDA library is missing and interner
 creation fails without a CUDA device.
 """
-from .api import (I32, U8, Batch, ChunkSet, VoxelisError, VoxInterner, VoxTree, apply_batches, device_count, voxelize_plan,  # noqa: F401
+from .api import (I32, U8, Batch, ChunkSet, VoxelisError, VoxInterner, VoxTree, World, apply_batches, device_count, voxelize_plan,  # noqa: F401
                   trees_forget,
                   id_index, id_is_branch, id_is_leaf, id_mask, id_types, lib)
 
-__all__ = ["U8", "I32", "Batch", "VoxInterner", "VoxTree", "VoxelisError", "apply_batches", "trees_forget", "ChunkSet", "device_count", "voxelize_plan", "lib"]
+__all__ = ["U8", "I32", "Batch", "VoxInterner", "VoxTree", "VoxelisError", "apply_batches", "trees_forget", "ChunkSet", "device_count", "voxelize_plan", "lib", "World"]

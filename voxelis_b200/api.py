@@ -46,8 +46,9 @@ ABI_SYMBOLS = [
     "vx_tree_voxels_per_axis", "vx_tree_is_empty", "vx_tree_is_leaf", "vx_tree_is_dirty",
     "vx_tree_mark_dirty", "vx_tree_clear_dirty", "vx_tree_apply_batch", "vx_apply_batches",
     "vx_apply_batches_slab", "vx_apply_batches_device", "vx_tree_get", "vx_tree_get_many",
-    "vx_tree_to_vec", "vx_roots_to_vec", "vx_roots_to_vec_lod", "vx_occupancy_masks", "vx_terrain_heights_device", "vx_terrain_batches_device", "vx_voxelize_plan", "vx_voxelize_chunks_device", "vx_tree_fill", "vx_tree_clear",
-    "vx_dedup_heights", "vx_dedup_pack", "vx_dedup_scatter", "vx_dedup_map_roots", "vx_interner_intern_records",
+    "vx_tree_to_vec", "vx_roots_to_vec", "vx_roots_to_vec_lod", "vx_occupancy_masks", "vx_terrain_heights_device", "vx_terrain_batches_device", "vx_random_batches_device", "vx_voxelize_plan", "vx_voxelize_chunks_device", "vx_tree_fill", "vx_tree_clear",
+    "vx_interner_memory", "vx_interner_debug_memo", "vx_world_unique_id", "vx_world_create", "vx_world_destroy", "vx_world_size", "vx_world_rank",
+    "vx_world_barrier", "vx_world_global_dedup", "vx_dedup_heights", "vx_dedup_pack", "vx_dedup_scatter", "vx_dedup_map_roots", "vx_interner_intern_records",
 ]
 
 
@@ -86,6 +87,17 @@ def lib():
     L.vx_interner_get_value.argtypes = [vp, u64, vp]
     L.vx_interner_get_children.argtypes = [vp, u64, vp]
     L.vx_interner_stats.argtypes = [vp, vp]
+    L.vx_interner_memory.argtypes = [vp, vp]
+    L.vx_interner_debug_memo.argtypes = [vp, vp]
+    L.vx_world_unique_id.argtypes = [vp]
+    L.vx_world_create.restype = vp
+    L.vx_world_create.argtypes = [C.c_int, C.c_int, vp, C.c_int]
+    L.vx_world_destroy.restype = None
+    L.vx_world_destroy.argtypes = [vp]
+    L.vx_world_size.argtypes = [vp]
+    L.vx_world_rank.argtypes = [vp]
+    L.vx_world_barrier.argtypes = [vp, vp]
+    L.vx_world_global_dedup.argtypes = [vp, vp, vp, sz, vp, vp, vp]
     L.vx_interner_debug_counters.argtypes = [vp, vp]
     L.vx_interner_profile_stages.argtypes = [vp, C.c_int]
     L.vx_interner_stage_ms.argtypes = [vp, vp, vp]
@@ -151,6 +163,7 @@ def lib():
     L.vx_occupancy_masks.argtypes = [vp, C.c_uint8, C.c_uint8, sz, vp, vp, vp, sz, C.c_uint32, vp, vp, vp, vp, vp, vp]
     L.vx_terrain_heights_device.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, i64, i64, vp, vp]
     L.vx_terrain_batches_device.argtypes = [vp, C.c_uint8, vp, vp, C.c_int, C.c_int, vp, vp, vp]
+    L.vx_random_batches_device.argtypes = [vp, C.c_uint8, C.c_size_t, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, vp, vp, vp]
     L.vx_voxelize_plan.restype = i64
     L.vx_voxelize_plan.argtypes = [C.c_uint8, C.c_double, vp, sz, vp, sz, vp, vp, sz, vp, vp, sz, vp]
     L.vx_voxelize_chunks_device.argtypes = [vp, C.c_uint8, C.c_double, vp, sz, vp, sz, vp, sz, vp, sz, vp, vp, vp, vp, vp]
@@ -256,6 +269,19 @@ class VoxInterner:
         _ck(lib().vx_interner_stats(self.h, _ptr(a)))
         return {k: int(v) for k, v in zip(STATS_FIELDS, a)}
 
+    def memory(self) -> dict:
+        """vx_interner_memory: bytes of device memory behind this interner (pools, tables, builder scratch)."""
+        m = (C.c_uint64 * 8)()
+        _ck(lib().vx_interner_memory(self.h, m))
+        keys = ("pools_bytes", "table_bytes", "leaf_table_bytes", "bulk_scratch_bytes", "stage_bytes", "other_scratch_bytes",
+                "pinned_host_bytes", "total_device_bytes")
+        return {k: int(v) for k, v in zip(keys, m)}
+
+    def debug_memo(self):
+        m = (C.c_uint64 * 4)()
+        _ck(lib().vx_interner_debug_memo(self.h, m))
+        return [int(v) for v in m]
+
     def debug_counters(self) -> dict:
         a = np.zeros(8, np.uint64)
         _ck(lib().vx_interner_debug_counters(self.h, _ptr(a)))
@@ -336,6 +362,13 @@ class VoxInterner:
         _ck(lib().vx_terrain_batches_device(self.h, depth, g, C.c_void_p(d_heights), int(bool(surface_only)),
                                             materials, C.c_void_p(d_masks), C.c_void_p(d_values),
                                             C.c_void_p(stream or None)))
+
+    def random_batches_device(self, depth: int, n: int, d_masks: int, d_values: int, k: int = 255, cell: int = 1,
+                              chunk0: int = 0, seed_base: int = 0x5EED0000, stream: int = 0):
+        """vx_random_batches_device: n high-entropy chunks written in device memory (== workloads.p_random(k, cell) for
+        chunk indices chunk0 .. chunk0 + n)."""
+        _ck(lib().vx_random_batches_device(self.h, depth, n, seed_base, chunk0, k, cell, C.c_void_p(d_masks),
+                                           C.c_void_p(d_values), C.c_void_p(stream or None)))
 
     def voxelize_chunks_device(self, depth: int, chunk_world_size: float, mesh_min, vertices, faces, plan,
                                d_masks: int, d_values: int, d_has_patches: int = 0):
@@ -418,6 +451,61 @@ class VoxInterner:
                                      _ptr(out["n_materials"]), _ptr(out["material_ids"]), _ptr(out["material_counts"]),
                                      _ptr(out["per_material"])))
         return out
+
+
+class World:
+    """vx_world: this process's membership in a group of one-process-per-GPU ranks (NCCL underneath, loaded by the
+    library).  ``unique_id()`` on rank 0, ship the 128 bytes to the other ranks with whatever the host has, then
+    ``World(n_ranks, rank, uid, device)`` everywhere (collective)."""
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = (C.c_uint8 * 128)()
+        _ck(lib().vx_world_unique_id(buf))
+        return bytes(buf)
+
+    def __init__(self, n_ranks: int, rank: int, uid: bytes, device: int = 0):
+        self.n_ranks, self.rank, self.device = n_ranks, rank, device
+        buf = (C.c_uint8 * 128).from_buffer_copy(uid)
+        self.h = lib().vx_world_create(n_ranks, rank, buf, device)
+        if not self.h:
+            raise VoxelisError(-1, lib().vx_last_error().decode())
+
+    @classmethod
+    def from_torch_distributed(cls, device: int):
+        """Rendezvous through an initialised torch.distributed group (plumbing only: 128 bytes broadcast)."""
+        import torch
+        import torch.distributed as dist
+        n, r = (dist.get_world_size(), dist.get_rank()) if dist.is_initialized() else (1, 0)
+        uid = cls.unique_id() if r == 0 else bytes(128)
+        if n > 1:
+            t = torch.tensor(list(uid), dtype=torch.uint8, device=torch.device("cuda", device))
+            dist.broadcast(t, 0)
+            uid = bytes(t.cpu().tolist())
+        return cls(n, r, uid, device)
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().vx_world_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def barrier(self, stream: int = 0):
+        _ck(lib().vx_world_barrier(self.h, C.c_void_p(stream or None)))
+
+    def global_dedup(self, local: "VoxInterner", shard: "VoxInterner", roots):
+        """vx_world_global_dedup (collective).  Returns (global_roots uint64[n], summary dict)."""
+        roots = np.ascontiguousarray(roots, np.uint64)
+        out = np.zeros_like(roots)
+        summ = (C.c_uint64 * 7)()
+        _ck(lib().vx_world_global_dedup(self.h, local.h, shard.h, roots.size, _ptr(roots), _ptr(out), summ))
+        keys = ("rounds", "branches", "leaves", "bytes_sent", "local_nodes_all_ranks", "this_shard_branches", "this_shard_leaves")
+        return out, {k: int(v) for k, v in zip(keys, summ)}
 
 
 def voxelize_plan(depth: int, chunk_world_size: float, mesh_min, vertices, faces):

@@ -240,6 +240,7 @@ struct CtaSmem {
     u32 rcnt[RH];      // ... and how many; hot children (flat ground, solid rock) would otherwise take
                        // thousands of same-address RED.ADDs that serialise in one L2 slice
     u32 warps_done;    // exit arrival counter (the last warp flushes leafref / rkey,rcnt)
+    u32 memo_stat[2];  // bulk builder's unit memo: units of this CTA that were aliased / that were new (vx_bulk.cuh)
 };
 
 struct Tally {  // per-lane statistics, reduced once at kernel exit

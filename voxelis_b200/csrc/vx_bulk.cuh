@@ -53,11 +53,21 @@ struct BulkArgs {
     u32 dense_min;
     u32 tpk_only;
     u32 use_free;
+    // unit memo (busy units only): content digest -> the first unit of THIS call seen with that content
+    u64* memo;        // [MEMO_SLOTS][2], own allocation; entries are salted with `epoch`, so old ones never match
+    u32* memo_count;  // entries inserted since the table was last cleared (persists across calls)
+    u32* unit_delta;  // [U][3] leaf_calls / branch_calls / collapsed of a unit built by bulk_dense_units_kernel
+    u32 memo_on;
+    u32 merge_dense;  // busy units are built by the warps of bulk_blocks_kernel once their share of the block list is done
 };
 #ifndef VX_BULK_MIN_CTAS
 #define VX_BULK_MIN_CTAS 3
 #endif
 constexpr u32 UNIT_PREBUILT = 0xFFFFFFFFu;  // unit_first marker: the unit's node is already in dense[0]
+constexpr u32 UNIT_ALIAS = 0xFFFFFFFEu;     // unit_first marker: dense[0] holds the index of the unit with the same content
+constexpr u32 MEMO_SLOTS = 1u << 17;        // 16-byte entries (2 MiB)
+constexpr u32 MEMO_CLEAR_AT = MEMO_SLOTS / 4;
+constexpr int MEMO_PROBES = 8;
 
 __device__ __forceinline__ u32 ld_stream_u32(const void* p) {
     u32 v;
@@ -104,6 +114,19 @@ __global__ void __launch_bounds__(256) bulk_plan_kernel(BulkArgs a) {
     unsigned long long qw[PLAN_AHEAD];
     const bool listed = a.unit_list != nullptr;
     const unsigned long long total = listed ? a.n_listed : a.units;
+    // the previous call's last launch wiped the unit memo if the count stood at MEMO_CLEAR_AT or more
+    if (a.memo_on && blockIdx.x == 0 && threadIdx.x == 0 && *a.memo_count >= MEMO_CLEAR_AT) *a.memo_count = 0;
+    // busy units of this warp wait in the lanes' registers (lane k holds the k-th) and enter the queue with ONE
+    // atomic per warp: a dense world would otherwise put one same-address atomic per unit on a single L2 slice
+    u32 my_busy = 0, n_busy = 0;
+    auto flush_busy = [&]() {
+        if (n_busy == 0) return;
+        u32 base = 0;
+        if (lane == 0) base = atomicAdd(&a.cnt[3], n_busy);
+        base = __shfl_sync(FULL, base, 0);
+        if (lane < n_busy) a.dense_units[base + lane] = my_busy;
+        n_busy = 0;
+    };
 #pragma unroll
     for (int d = 0; d < PLAN_AHEAD; ++d) {
         qa[d] = qb[d] = make_uint4(0, 0, 0, 0);
@@ -165,8 +188,9 @@ __global__ void __launch_bounds__(256) bulk_plan_kernel(BulkArgs a) {
         if (c0 >= a.dense_min) {
             // a busy unit: thread-per-block lists would cost more than they save; one warp builds it the
             // way apply_kernel does (lane = block, siblings in neighbouring lanes)
+            if (lane == n_busy) my_busy = u32(w);
+            if (++n_busy == 32) flush_busy();
             if (lane == 0) {
-                a.dense_units[atomicAdd(&a.cnt[3], 1u)] = u32(w);
                 a.unit_first[w] = UNIT_PREBUILT;
                 a.unit_cm[w] = 0xFF;
             }
@@ -217,6 +241,7 @@ __global__ void __launch_bounds__(256) bulk_plan_kernel(BulkArgs a) {
             a.unit_cm[w] = u8(cm3);
         }
     }
+    flush_busy();
 }
 
 // Values of the eight children of a key (leaf value / branch LOD value; 0 for EMPTY), loaded with plain
@@ -471,6 +496,9 @@ __device__ __forceinline__ u32 bulk_span(u32 cnt) {
 // blocks: thread per candidate block.
 // ------------------------------------------------------------------------------------------------
 template <class T>
+__device__ __forceinline__ void dense_units_loop(Ctx<T>& c, const BulkArgs& a);
+
+template <class T>
 __global__ void __launch_bounds__(CTA_THREADS, VX_BULK_MIN_CTAS) bulk_blocks_kernel(BulkArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using V = VT<T>;
@@ -479,7 +507,8 @@ __global__ void __launch_bounds__(CTA_THREADS, VX_BULK_MIN_CTAS) bulk_blocks_ker
     c.tpk_only = a.tpk_only != 0;
     const u32 cnt = a.cnt[0];
     const u32 span = bulk_span(cnt);
-    if (bulk_cta_idle(&a.cnt[0], WARPS_PER_CTA * span)) return;
+    const bool idle = bulk_cta_idle(&a.cnt[0], WARPS_PER_CTA * span);
+    if (idle && !(a.merge_dense && a.cnt[3] != 0)) return;
     const u64 first = u64(blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5)) * span;
     const u32 base0 = u32(min(first, u64(cnt)));
     const u32 end = u32(min(first + span, u64(cnt)));
@@ -517,66 +546,242 @@ __global__ void __launch_bounds__(CTA_THREADS, VX_BULK_MIN_CTAS) bulk_blocks_ker
         if (active) a.ids[0][k] = present ? id : 0;
         if (__any_sync(FULL, errw != ERR_NONE)) break;
     }
+    // busy units (queued by the plan kernel) are independent of the lists: the warps take them as they run out of
+    // list blocks, so a dense world costs no launch of its own and a mixed one balances itself
+    if (a.merge_dense) {
+        c.tpk_only = false;
+        dense_units_loop<T>(c, a);
+    }
     cta_finish<T>(c);
 }
 
 // ------------------------------------------------------------------------------------------------
-// busy units: one warp per unit, the fused kernel's phase 1 + in-unit phase 2 (vx_build.cuh); the unit's
-// node goes straight into the dense array the upper levels read.
+// Unit memo.  A busy unit's node is a pure function of its 1 KiB of set_masks and 8·sizeof(T)·512 bytes of
+// values (fresh tree, no fill), and so are the leaf / branch / collapse counts the reference would have
+// run up building it.  Worlds repeat themselves at this granularity (every chunk of a checkerboard, every
+// slab of rock, the 255 distinct chunks of the "sum per chunk" benchmark), so the warp that is handed a
+// busy unit first streams the unit once, forms a 96-bit content digest on the way, and asks a small
+// table whether a unit with that content has been seen in THIS call.  If so the unit becomes an alias of
+// that unit (the upper kernel copies its node and its counts); if not the warp enters itself and builds
+// the unit the usual way.  A hit costs the 5 KiB read and ~300 instructions per lane instead of 16
+// iterations of phase 1 + 73 interned parents.
+//   entry (16 B, one 128-bit CAS):  x = digest A (salted with the call's epoch, bit 0 forced),
+//                                   y = digest B[63:32] << 32 | unit index of the first unit with that content
+//                                   (B is salted too and picks the slot: entries of earlier calls lie elsewhere)
+// Two units alias only if both 64-bit mum-hash chains agree (A, and the top half of B): 2^-96 per pair of
+// distinct units; the reference itself keys its maps on a 64-bit hash with no key comparison
+// (interner/hash.rs:15-38).  Entries of earlier calls carry another salt and never match; the table is
+// wiped by the call's last launch once MEMO_CLEAR_AT entries have gone in, and inserts stop at half full.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ u64 mum64(u64 a, u64 b) { return (a * b) ^ __umul64hi(a, b); }
+struct UnitDigest {
+    u64 a, b;
+    __device__ __forceinline__ void init(u32 lane) {  // the lane (= position in the unit) seeds both chains
+        a = 0xA0761D6478BD642Full ^ (u64(lane + 1) * 0x9E3779B97F4A7C15ull);
+        b = 0xE7037ED1A0B428DBull ^ (u64(lane + 1) * 0xD6E8FEB86659FD93ull);
+    }
+    __device__ __forceinline__ void absorb(u64 x, u64 y) {
+        a = mum64(x ^ 0x8EBC6AF09C88C6E3ull, y ^ a);
+        b = mum64(y ^ 0x589965CC75374CC3ull, x ^ b);
+    }
+};
+__device__ __forceinline__ bool cas128(u64* p, u64 n0, u64 n1, u64* o0, u64* o1) {  // expects (0, 0)
+    asm volatile(
+        "{\n .reg .b128 c, n, d;\n mov.b128 c, {%2, %2};\n mov.b128 n, {%3, %4};\n"
+        " atom.relaxed.gpu.global.cas.b128 d, [%5], c, n;\n mov.b128 {%0, %1}, d;\n}"
+        : "=l"(*o0), "=l"(*o1) : "l"(0ull), "l"(n0), "l"(n1), "l"(p) : "memory");
+    return *o0 == 0 && *o1 == 0;
+}
+// lane 0 only.  Returns 1 = alias of unit *rep, 0 = this unit is the first with its content.
+__device__ __forceinline__ int memo_lookup(const BulkArgs& a, u64 A, u64 B, u32 w, bool may_insert, u32* rep) {
+    const u64 hi = B & 0xFFFFFFFF00000000ull;
+    u32 slot = u32(B) & (MEMO_SLOTS - 1);
+#pragma unroll 1
+    for (int p = 0; p < MEMO_PROBES; ++p) {
+        u64* e = a.memo + size_t(slot) * 2;
+        u64 x, y;
+        ld_strong_v2(e, &x, &y);
+        if (x == 0 && y == 0) {
+            if (!may_insert) return 0;
+            if (cas128(e, A, hi | w, &x, &y)) {
+                atomicAdd(a.memo_count, 1u);
+                return 0;
+            }
+        }
+        if (x == A && (y & 0xFFFFFFFF00000000ull) == hi) {
+            *rep = u32(y);
+            return 1;
+        }
+        slot = (slot + 1) & (MEMO_SLOTS - 1);
+    }
+    return 0;  // crowded neighbourhood: build it, nobody will alias it
+}
+
+// ------------------------------------------------------------------------------------------------
+// busy units: one warp per unit.  Stream the unit (masks + values, every byte once), then either: a solid
+// unit -> its leaf; content seen before in this call -> alias; else the fused kernel's phase 1 + in-unit
+// phase 2 (vx_build.cuh).  The unit's node goes straight into the dense array the upper levels read.
+// ------------------------------------------------------------------------------------------------
+constexpr u32 DENSE_GRAB = 4;  // units taken from the queue per atomic
+template <class T>
+__device__ __forceinline__ void dense_units_loop(Ctx<T>& c, const BulkArgs& a) {
+    const u32 cnt = a.cnt[3];
+    if (cnt == 0) return;
+    const u32 upc = a.blocks / UNIT_BLOCKS;
+    const int upc_log = 31 - __clz(upc);
+    const int D = int(a.depth);
+    const u64 salt = mix64(u64(a.epoch) * VX_HC0 + VX_HC1), salt_b = mix64(salt + VX_HC2);
+    bool memo_on = a.memo_on != 0;
+    bool may_insert = false;
+    if (memo_on && c.lane == 0) may_insert = ld_strong(a.memo_count) < MEMO_SLOTS / 2;
+    // per-warp memo cache in registers: lane l holds one (A, y) entry.  A world that repeats itself repeats itself
+    // nearby, so most units never reach the global table (whose hot entries sit in a single L2 slice).
+    u64 cA = 0, cY = 0;
+    // units are drawn one at a time while they have to be built (they differ a lot in cost) and DENSE_GRAB at a time
+    // while they turn out cheap (solid, or seen before): 10^5 same-address atomics would be the kernel's bound
+    bool cheap = false;
+    auto grab = [&](u32 k) -> u32 {
+        u32 i = 0;
+        if (c.lane == 0) i = atomicAdd(&a.cnt[4], k);
+        return __shfl_sync(FULL, i, 0);
+    };
+    u32 take = 1, base = grab(take);
+    while (base < cnt) {
+        const u32 take_next = cheap ? DENSE_GRAB : 1u;
+        const u32 base_next = grab(take_next);  // the next batch is on its way while this one is processed
+        if (__any_sync(FULL, c.lane == 0 && ld_strong(a.in.error) != ERR_NONE)) break;
+        for (u32 i = base; i < min(base + take, cnt); ++i) {
+            cheap = true;
+            const u32 w = a.dense_units[i];
+            const u32 chunk = w >> upc_log, unit = w & (upc - 1);
+            u64 mlo, mhi;
+            load_unit_masks(a.masks + size_t(chunk) * a.blocks * 2, size_t(unit) * UNIT_BLOCKS, UNIT_BLOCKS, c.lane, &mlo, &mhi);
+            const Under u{0, 0, 0, D};
+            const void* cv = (const u8*)a.values + size_t(chunk) * a.blocks * 8 * sizeof(T);
+            const uint4* vp = reinterpret_cast<const uint4*>((const u8*)cv + (size_t(unit) * UNIT_BLOCKS + 16 * c.lane) * 8 * sizeof(T));
+            constexpr int NV = 8 * int(sizeof(T));  // 16-byte vectors holding this lane's 16 blocks
+            const bool full = __all_sync(FULL, (mlo & mhi) == ~0ull);
+            // the CTA's warps share what they learn about the world: once misses outnumber hits 4 : 1 nobody asks
+            if (memo_on && (i & 3) == 0) {
+                const u32 mh = ((volatile u32*)c.cs->memo_stat)[0], mm = ((volatile u32*)c.cs->memo_stat)[1];
+                if (mm >= 8 && mh * 4 < mm) memo_on = false;
+            }
+            if (full || memo_on) {
+                // ---- one streaming pass over the unit's values: "solid" test first, then (not solid) the content digest
+                uint4 q[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) q[j] = ld_stream_v4(vp + j);
+                const u32 v0 = __shfl_sync(FULL, sizeof(T) == 1 ? (q[0].x & 0xFFu) : q[0].x, 0);
+                const u32 splat = sizeof(T) == 1 ? v0 * 0x01010101u : v0;
+                bool uni = full && v0 != 0;
+                if (uni) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        uni = uni && q[j].x == splat && q[j].y == splat && q[j].z == splat && q[j].w == splat;
+#pragma unroll 1
+                    for (int j0 = 8; j0 < NV && uni; j0 += 4) {  // wider T: the rest of the lane's 16 blocks
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint4 r = ld_stream_v4(vp + j0 + j);
+                            uni = uni && r.x == splat && r.y == splat && r.z == splat && r.w == splat;
+                        }
+                    }
+                }
+                // Solid unit (underground rock, filled volumes): every voxel set to the same non-default value.
+                // Phase 1 makes 512 identical leaves, phase 2 collapses 64 + 8 + 1 parents (:826, :1050) — the
+                // outcome is that one leaf.
+                if (__all_sync(FULL, uni)) {
+                    u64 leaf = leaf_get(c, v0, c.lane == 0);
+                    if (c.lane == 0) {
+                        c.t.leaf_calls += UNIT_BLOCKS;                                    // one per all_same block
+                        c.t.collapsed += UNIT_BLOCKS + UNIT_BLOCKS / 8 + UNIT_BLOCKS / 64 + 1;  // blocks + 3 levels
+                        a.dense[0][w] = leaf;
+                    }
+                    continue;
+                }
+                if (memo_on) {
+                    UnitDigest dg;
+                    dg.init(c.lane);
+                    dg.absorb(mlo, mhi);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        dg.absorb(u64(q[j].x) | (u64(q[j].y) << 32), u64(q[j].z) | (u64(q[j].w) << 32));
+#pragma unroll 1
+                    for (int j0 = 8; j0 < NV; j0 += 4) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint4 r = ld_stream_v4(vp + j0 + j);
+                            dg.absorb(u64(r.x) | (u64(r.y) << 32), u64(r.z) | (u64(r.w) << 32));
+                        }
+                    }
+                    u64 A = mix64(dg.a), B = mix64(dg.b ^ 0x1D8E4E27C47D124Full);
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) {
+                        A += __shfl_xor_sync(FULL, A, o);
+                        B += __shfl_xor_sync(FULL, B, o);
+                    }
+                    A = (A ^ salt) | 1ull;   // both halves salted with the call: entries of earlier calls lie elsewhere
+                    B ^= salt_b;
+                    const u64 hi = B & 0xFFFFFFFF00000000ull;
+                    int alias = 0;
+                    u32 rep = 0;
+                    const u32 hit = __ballot_sync(FULL, cA == A && (cY & 0xFFFFFFFF00000000ull) == hi);
+                    if (hit) {
+                        rep = u32(__shfl_sync(FULL, cY, __ffs(hit) - 1));
+                        alias = 1;
+                    } else {
+                        if (c.lane == 0) alias = memo_lookup(a, A, B, w, may_insert, &rep);
+                        alias = __shfl_sync(FULL, alias, 0);
+                        rep = alias ? __shfl_sync(FULL, rep, 0) : w;
+                        if (c.lane == int((A >> 8) & 31)) {
+                            cA = A;
+                            cY = hi | rep;
+                        }
+                    }
+                    if (c.lane == 0) atomicAdd(&c.cs->memo_stat[alias ? 0 : 1], 1u);
+                    if (alias) {
+                        if (c.lane == 0) {
+                            a.unit_first[w] = UNIT_ALIAS;
+                            a.dense[0][w] = rep;
+                        }
+                        continue;
+                    }
+                }
+            }
+            cheap = false;
+            const u32 lc0 = c.t.leaf_calls, bc0 = c.t.branch_calls, co0 = c.t.collapsed;
+            const bool some = build_blocks<T, false>(c, mlo, mhi, cv, unit * UNIT_BLOCKS, UNIT_BLOCKS, u);
+            u64 node = 0;
+            bool present = false;
+            if (some) node = reduce_levels<T>(c, UNIT_BLOCKS / 8, D - 2, (unit * UNIT_BLOCKS) >> 3, u, false, &present);
+            if (a.memo_on) {  // what an alias of this unit has to add to the counters
+                u32 d0 = c.t.leaf_calls - lc0, d1 = c.t.branch_calls - bc0, d2 = c.t.collapsed - co0;
+#pragma unroll
+                for (int o = 16; o; o >>= 1) {
+                    d0 += __shfl_xor_sync(FULL, d0, o);
+                    d1 += __shfl_xor_sync(FULL, d1, o);
+                    d2 += __shfl_xor_sync(FULL, d2, o);
+                }
+                if (c.lane == 0) {
+                    a.unit_delta[size_t(w) * 3 + 0] = d0;
+                    a.unit_delta[size_t(w) * 3 + 1] = d1;
+                    a.unit_delta[size_t(w) * 3 + 2] = d2;
+                }
+            }
+            if (c.lane == 0) a.dense[0][w] = present ? node : 0;
+        }
+        base = base_next;
+        take = take_next;
+    }
+}
+
 template <class T>
 __global__ void __launch_bounds__(CTA_THREADS, VX_MIN_CTAS) bulk_dense_units_kernel(BulkArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Ctx<T> c;
     bulk_prologue<T>(c, a, smem_raw);
     if (bulk_cta_idle(&a.cnt[3], WARPS_PER_CTA)) return;
-    const u32 cnt = a.cnt[3];
-    const u32 upc = a.blocks / UNIT_BLOCKS;
-    const int upc_log = 31 - __clz(upc);
-    const int D = int(a.depth);
-    for (;;) {
-        u32 i = 0;
-        if (c.lane == 0) i = atomicAdd(&a.cnt[4], 1u);
-        i = __shfl_sync(FULL, i, 0);
-        if (i >= cnt) break;
-        if (__any_sync(FULL, c.lane == 0 && ld_strong(a.in.error) != ERR_NONE)) break;
-        const u32 w = a.dense_units[i];
-        const u32 chunk = w >> upc_log, unit = w & (upc - 1);
-        u64 mlo, mhi;
-        load_unit_masks(a.masks + size_t(chunk) * a.blocks * 2, size_t(unit) * UNIT_BLOCKS, UNIT_BLOCKS, c.lane, &mlo, &mhi);
-        const Under u{0, 0, 0, D};
-        const void* cv = (const u8*)a.values + size_t(chunk) * a.blocks * 8 * sizeof(T);
-        // Solid unit (underground rock, filled volumes): every voxel set to the same non-default value.
-        // Phase 1 makes 512 identical leaves, phase 2 collapses 64 + 8 + 1 parents (:826, :1050) — the
-        // outcome is that one leaf, so the unit costs one streaming pass over its values.
-        if (__all_sync(FULL, (mlo & mhi) == ~0ull)) {
-            const uint4* vp = reinterpret_cast<const uint4*>((const u8*)cv + (size_t(unit) * UNIT_BLOCKS + 16 * c.lane) * 8 * sizeof(T));
-            constexpr int NV = 8 * int(sizeof(T));  // 16-byte vectors holding this lane's 16 blocks
-            uint4 q = ld_stream_v4(vp);
-            const u32 v0 = __shfl_sync(FULL, sizeof(T) == 1 ? (q.x & 0xFFu) : q.x, 0);
-            const u32 splat = sizeof(T) == 1 ? v0 * 0x01010101u : v0;
-            bool uni = v0 != 0;
-#pragma unroll 4
-            for (int j = 0; j < NV; ++j) {
-                if (j) q = ld_stream_v4(vp + j);
-                uni = uni && q.x == splat && q.y == splat && q.z == splat && q.w == splat;
-            }
-            if (__all_sync(FULL, uni)) {
-                u64 leaf = leaf_get(c, v0, c.lane == 0);
-                if (c.lane == 0) {
-                    c.t.leaf_calls += UNIT_BLOCKS;                                    // one per all_same block
-                    c.t.collapsed += UNIT_BLOCKS + UNIT_BLOCKS / 8 + UNIT_BLOCKS / 64 + 1;  // blocks + 3 levels
-                    a.dense[0][w] = leaf;
-                }
-                continue;
-            }
-        }
-        const bool some = build_blocks<T, false>(c, mlo, mhi, cv, unit * UNIT_BLOCKS, UNIT_BLOCKS, u);
-        u64 node = 0;
-        bool present = false;
-        if (some) node = reduce_levels<T>(c, UNIT_BLOCKS / 8, D - 2, (unit * UNIT_BLOCKS) >> 3, u, false, &present);
-        if (c.lane == 0) a.dense[0][w] = present ? node : 0;
-    }
+    dense_units_loop<T>(c, a);
     cta_finish<T>(c);
 }
 
@@ -625,7 +830,10 @@ __device__ __forceinline__ void bulk_write_root(Ctx<T>& c, const BulkArgs& a, un
     // apply_batch (voxtree.rs:303-328): nothing entered `paths` -> INVALID -> false, root stays EMPTY
     a.roots[chunk] = id;
     if (a.changed) a.changed[chunk] = id != 0;
-    if (id != 0) atomicAdd(&c.in.refs[id_index(id)], 1u);  // the tree's root handle
+    if (id != 0) {  // the tree's root handle; identical chunks share a root: one atomic per distinct root and warp
+        const u32 peers = __match_any_sync(__activemask(), id);
+        if ((__ffs(peers) - 1) == c.lane) atomicAdd(&c.in.refs[id_index(id)], u32(__popc(peers)));
+    }
 }
 
 // levels: 1 = the nodes are one level; 2 = lane 0 of every 8-lane group goes on to build the parent of the
@@ -657,6 +865,14 @@ bulk_upper_kernel(BulkArgs a, unsigned long long nodes, const u64* below, u64* o
             if (cm && f == UNIT_PREBUILT) {  // built by bulk_dense_units_kernel
                 prebuilt = true;
                 pre_id = a.dense[0][k];
+                cm = 0;
+            } else if (cm && f == UNIT_ALIAS) {  // same content as an earlier unit of this call: its node, its counts
+                prebuilt = true;
+                const u32 rep = u32(a.dense[0][k]);
+                pre_id = a.dense[0][rep];
+                c.t.leaf_calls += a.unit_delta[size_t(rep) * 3 + 0];
+                c.t.branch_calls += a.unit_delta[size_t(rep) * 3 + 1];
+                c.t.collapsed += a.unit_delta[size_t(rep) * 3 + 2];
                 cm = 0;
             }
 #pragma unroll
@@ -692,6 +908,12 @@ bulk_upper_kernel(BulkArgs a, unsigned long long nodes, const u64* below, u64* o
             else
                 out[k >> 3] = id2;
         }
+    }
+    // the call's last launch wipes the unit memo once enough entries have gone in (the plan kernel of the
+    // next call resets the count; nothing touches either in between)
+    if (top_is_root && a.memo_on && ld_strong(a.memo_count) >= MEMO_CLEAR_AT) {
+        ulonglong2* m = reinterpret_cast<ulonglong2*>(a.memo);
+        for (size_t e = size_t(blockIdx.x) * CTA_THREADS + threadIdx.x; e < MEMO_SLOTS; e += stride) m[e] = make_ulonglong2(0, 0);
     }
     cta_finish<T>(c);
 }

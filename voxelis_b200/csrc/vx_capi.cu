@@ -106,6 +106,7 @@ struct vx_interner {
     uint32_t* bulk_flags = nullptr;  // epoch-tagged "group of units is not empty" flags (own allocation:
     size_t bulk_flags_n = 0;         // they must only ever hold tags, whatever the call sizes were)
     uint32_t bulk_epoch = 0;         // tag of the current call
+    uint64_t* bulk_memo = nullptr;   // unit memo of the bulk builder (vx_bulk.cuh): MEMO_SLOTS x 16 B + the insert count
     // diagnostic: CUDA events between the launches of the last apply (vx_interner_profile_stages)
     bool prof = false;
     cudaEvent_t pev[10]{};
@@ -286,12 +287,23 @@ int launch_apply_t(vx_interner* it, int depth, size_t n, const u8* d_masks, cons
 }
 
 // ---- bulk builder (vx_bulk.cuh): n fresh trees, no flags, depth >= 4 ------------------------------
+// candidate blocks (of 512) from which a unit is built by one warp instead of going through the level lists
+u32 bulk_dense_min() {
+    if (const char* e = getenv("VX_BULK_DENSE_MIN")) return u32(std::max(1, atoi(e)));
+    return 128;
+}
+// entries of sparse level l: a unit only enters the lists with fewer than dense_min candidate blocks
+size_t bulk_level_entries(size_t nb, int l) {
+    if (l == 0) return (nb / UNIT_BLOCKS) * std::min<size_t>(UNIT_BLOCKS, bulk_dense_min() - 1) + 32;
+    return nb >> (3 * l);
+}
 size_t bulk_scratch_bytes(size_t n, size_t blocks) {
     const size_t nb = n * blocks;
     size_t need = 256;
-    for (int l = 0; l < 3; ++l) need += ((nb >> (3 * l)) * 13 + 3 * 256);
+    for (int l = 0; l < 3; ++l) need += bulk_level_entries(nb, l) * 13 + 3 * 256;
     const size_t units = nb / UNIT_BLOCKS;
     need += units * 5 + 2 * 256 + units * 8 + units + 2 * 256 + units * 4 + 256 + units + 2 * 256;
+    need += units * 12 + 256;  // unit_delta
     return need;
 }
 size_t stage_max_bytes() {  // device slab of vx_apply_batches (host batches are staged in slices of this size)
@@ -354,10 +366,17 @@ int launch_bulk_t(vx_interner* it, int depth, size_t n, const u8* d_masks, const
         CU_TRY(cudaMalloc(&it->bulk_flags, (units / 8 + 1) * 4));
         it->bulk_flags_n = units / 8 + 1;
         CU_TRY(cudaMemsetAsync(it->bulk_flags, 0, it->bulk_flags_n * 4, s));
+        if (it->bulk_memo) CU_TRY(cudaMemsetAsync(it->bulk_memo, 0, size_t(MEMO_SLOTS) * 16 + 256, s));  // epochs restart
         it->bulk_epoch = 0;
+    }
+    const size_t memo_bytes = size_t(MEMO_SLOTS) * 16 + 256;
+    if (!it->bulk_memo) {
+        CU_TRY(cudaMalloc(&it->bulk_memo, memo_bytes));
+        CU_TRY(cudaMemsetAsync(it->bulk_memo, 0, memo_bytes, s));
     }
     if (++it->bulk_epoch == 0) {  // wrapped: the tags of 2^32 calls ago could alias
         CU_TRY(cudaMemsetAsync(it->bulk_flags, 0, it->bulk_flags_n * 4, s));
+        CU_TRY(cudaMemsetAsync(it->bulk_memo, 0, memo_bytes, s));
         it->bulk_epoch = 1;
     }
     BulkArgs a{};
@@ -371,8 +390,7 @@ int launch_bulk_t(vx_interner* it, int depth, size_t n, const u8* d_masks, const
     a.depth = u32(depth);
     a.blocks = u32(blocks);
     a.epoch = it->bulk_epoch;
-    a.dense_min = 128;  // candidate blocks (of 512) from which a unit is built by one warp instead
-    if (const char* e = getenv("VX_BULK_DENSE_MIN")) a.dense_min = u32(atoi(e));
+    a.dense_min = bulk_dense_min();
     a.tpk_only = getenv("VX_BULK_TPK") ? u32(atoi(getenv("VX_BULK_TPK"))) : 0u;
     a.use_free = it->free_host > 0 ? 1u : 0u;
     u8* p = (u8*)it->bulk;
@@ -383,7 +401,7 @@ int launch_bulk_t(vx_interner* it, int depth, size_t n, const u8* d_masks, const
     };
     a.cnt = (u32*)take(32);
     for (int l = 0; l < 3; ++l) {
-        const size_t m = nb >> (3 * l);
+        const size_t m = bulk_level_entries(nb, l);
         a.ids[l] = (u64*)take(m * 8);
         a.first[l] = (u32*)take(m * 4);
         a.cm[l] = take(m);
@@ -395,6 +413,13 @@ int launch_bulk_t(vx_interner* it, int depth, size_t n, const u8* d_masks, const
     a.dense_units = (u32*)take(units * 4);
     a.cube_flag = it->bulk_flags;
     a.cube_list = (u32*)take(units / 8 * 4 + 4);
+    a.unit_delta = (u32*)take(units * 12);
+    a.memo = it->bulk_memo;
+    a.memo_count = (u32*)(it->bulk_memo + size_t(MEMO_SLOTS) * 2);
+    const char* memo_env = getenv("VX_UNIT_MEMO");  // 0 switches the unit memo off (tests, A/B runs)
+    a.memo_on = (memo_env && atoi(memo_env) == 0) ? 0u : 1u;
+    const char* merge_env = getenv("VX_BULK_MERGE_DENSE");  // 0: busy units get a launch of their own (A/B runs)
+    a.merge_dense = (merge_env && atoi(merge_env) == 0) ? 0u : 1u;
     a.unit_list = d_unit_list;
     a.n_listed = n_listed;
     prof_begin(it, s);
@@ -434,13 +459,15 @@ int launch_bulk_t(vx_interner* it, int depth, size_t n, const u8* d_masks, const
     // capped at one resident wave (the kernels are grid-stride loops)
     static const bool chained = getenv("VX_BULK_NO_PDL") == nullptr;
     CU_TRY(launch_chained(bulk_blocks_kernel<T>, grid_for(nb), CTA_THREADS, smem, s, chained, a));
-    prof_mark(it, s, "bulk_blocks_kernel");
+    prof_mark(it, s, a.merge_dense ? "bulk_blocks_kernel[+busy units]" : "bulk_blocks_kernel");
     CU_TRY(launch_chained(bulk_level_kernel<T>, grid_for(nb >> 3), CTA_THREADS, smem, s, chained, a, 1));
     prof_mark(it, s, "bulk_level_kernel[1]");
     CU_TRY(launch_chained(bulk_level_kernel<T>, grid_for(nb >> 6), CTA_THREADS, smem, s, chained, a, 2));
     prof_mark(it, s, "bulk_level_kernel[2]");
-    CU_TRY(launch_chained(bulk_dense_units_kernel<T>, grid_for(units * 32), CTA_THREADS, smem, s, chained, a));
-    prof_mark(it, s, "bulk_dense_units_kernel");
+    if (!a.merge_dense) {
+        CU_TRY(launch_chained(bulk_dense_units_kernel<T>, grid_for(units * 32), CTA_THREADS, smem, s, chained, a));
+        prof_mark(it, s, "bulk_dense_units_kernel");
+    }
     // dense levels: units (depth D-4) up to the roots, two levels per launch where there are two
     size_t nodes = units;
     int pp = 1;  // dense[0] holds the prebuilt unit nodes
@@ -745,6 +772,7 @@ void vx_interner_destroy(vx_interner* it) {
     cudaFree(it->d_scalars);
     cudaFree(it->bulk);
     cudaFree(it->bulk_flags);
+    cudaFree(it->bulk_memo);
     for (auto& e : it->pev)
         if (e) cudaEventDestroy(e);
     for (auto& e : it->tevs)
@@ -875,6 +903,42 @@ int vx_interner_stats(const vx_interner* it, vx_stats* out) {
 
 // diagnostic counters not part of InternerStats: probe_steps, cache_hits_local
 // Diagnostics (not part of the reference-facing ABI): per-launch device times of the LAST apply call.
+int vx_interner_memory(const vx_interner* it, vx_memory* out) {
+    if (!it || !out) return fail(VX_E_INVALID, "null argument");
+    memset(out, 0, sizeof(*out));
+    const size_t esz = dtype_size(it->dtype);
+    out->pools_bytes = it->capacity * (64 + esz + 4 + 2 + 8 + 4);  // children, values, refs, gens, hashes, free list
+    out->table_bytes = it->nbuckets * 64;
+    out->leaf_table_bytes = it->dtype == VX_U8 ? 256 * 8 : it->leaf_slots * 16;
+    out->bulk_scratch_bytes = it->bulk_bytes + it->bulk_flags_n * 4 + (it->bulk_memo ? size_t(MEMO_SLOTS) * 16 + 256 : 0);
+    out->stage_bytes = it->stage_bytes * ((it->stage[0] ? 1 : 0) + (it->stage[1] ? 1 : 0));
+    out->other_scratch_bytes = it->scratch_bytes + it->join_bytes + (it->rel_cap[0] + it->rel_cap[1]) * 8 + sizeof(Scalars);
+    out->pinned_host_bytes = it->hscratch_bytes;
+    out->total_device_bytes = out->pools_bytes + out->table_bytes + out->leaf_table_bytes + out->bulk_scratch_bytes +
+                              out->stage_bytes + out->other_scratch_bytes;
+    return VX_OK;
+}
+
+// diagnostic: state of the bulk builder's unit memo — out[0] entries inserted since the last wipe, out[1] occupied
+// slots, out[2..3] the first occupied entry
+int vx_interner_debug_memo(const vx_interner* cit, uint64_t out[4]) {
+    vx_interner* it = const_cast<vx_interner*>(cit);
+    if (!it || !out) return fail(VX_E_INVALID, "null argument");
+    out[0] = out[1] = out[2] = out[3] = 0;
+    if (!it->bulk_memo) return VX_OK;
+    DeviceGuard g(it->device);
+    std::vector<u64> h(size_t(MEMO_SLOTS) * 2 + 1);
+    CU_TRY(cudaStreamSynchronize(it->stream));
+    CU_TRY(cudaMemcpy(h.data(), it->bulk_memo, h.size() * 8, cudaMemcpyDeviceToHost));
+    out[0] = u32(h[size_t(MEMO_SLOTS) * 2]);
+    for (size_t e = 0; e < MEMO_SLOTS; ++e)
+        if (h[2 * e] | h[2 * e + 1]) {
+            if (!out[1]) out[2] = h[2 * e], out[3] = h[2 * e + 1];
+            ++out[1];
+        }
+    return VX_OK;
+}
+
 int vx_interner_profile_stages(vx_interner* it, int on) {
     if (!it) return fail(VX_E_INVALID, "null interner");
     DeviceGuard g(it->device);
@@ -1286,6 +1350,29 @@ int vx_terrain_batches_device(vx_interner* it, uint8_t max_depth, const uint32_t
     else                      // one block per thread: 32 bytes of i32 values each
         terrain_batches_kernel<int32_t, 1><<<unsigned((total + 255) / 256), 256, 0, s>>>(
             max_depth, grid[0], grid[1], grid[2], d_heights, surface_only, materials, d_masks, (int32_t*)d_values);
+    CU_TRY(cudaGetLastError());
+    return VX_OK;
+}
+
+int vx_random_batches_device(vx_interner* it, uint8_t max_depth, size_t n, uint64_t seed_base, uint64_t chunk0, uint32_t k,
+                             uint32_t cell, uint8_t* d_masks, void* d_values, void* stream) {
+    if (!it || !d_masks || !d_values) return fail(VX_E_INVALID, "null argument");
+    if (!valid_depth(max_depth)) return fail(VX_E_INVALID, "max_depth must be in [2,7]");
+    if (k < 1 || (it->dtype == VX_U8 && k > 255) || cell < 1) return fail(VX_E_INVALID, "1 <= k (<= 255 for u8), cell >= 1");
+    if ((reinterpret_cast<uintptr_t>(d_masks) | reinterpret_cast<uintptr_t>(d_values)) & 15)
+        return fail(VX_E_INVALID, "device masks/values must be 16-byte aligned");
+    if (!is_device_ptr(d_masks) || !is_device_ptr(d_values)) return fail(VX_E_INVALID, "masks and values must be device memory");
+    if (n == 0) return VX_OK;
+    DeviceGuard g(it->device);
+    cudaStream_t s = stream ? (cudaStream_t)stream : it->stream;
+    const size_t blocks = blocks_for_depth(max_depth), total = n * blocks;
+    const u32 blocks_log = u32(3 * (max_depth - 1));
+    const unsigned grid = unsigned((total + 255) / 256);
+    if (it->dtype == VX_U8)
+        random_batches_kernel<u8><<<grid, 256, 0, s>>>(max_depth, total, blocks_log, seed_base, chunk0, k, cell, d_masks, (u8*)d_values);
+    else
+        random_batches_kernel<int32_t><<<grid, 256, 0, s>>>(max_depth, total, blocks_log, seed_base, chunk0, k, cell, d_masks,
+                                                            (int32_t*)d_values);
     CU_TRY(cudaGetLastError());
     return VX_OK;
 }
@@ -2763,3 +2850,5 @@ int64_t vx_import_vtm(vx_interner* it, const char* path, vx_vtm_info* info, int3
 }
 
 }  // extern "C"
+
+#include "vx_world.cuh"

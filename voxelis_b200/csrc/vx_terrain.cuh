@@ -77,7 +77,7 @@ __device__ __forceinline__ void st_v8(void* p, uint4 a, uint4 b) {  // one 32-by
 __device__ __forceinline__ int terrain_value(int d, bool surface_only, bool three) {
     if (surface_only) return d == 0;
     if (d < 0) return 0;
-    return !three ? 1 : d == 0 ? 1 : d <= 3 ? 2 : 3;
+    return !three ? 1 : d <= 2 ? 1 : d <= 4 ? 2 : 3;  // shapes.rs:344-350: y >= h-2 -> 1, y >= h-4 -> 2, else 3
 }
 
 // chunk linear index = (cx * gy + cy) * gz + cz; heights[(cx*n + x) * (gz*n) + cz*n + z].
@@ -115,7 +115,7 @@ terrain_batches_kernel(int depth, u32 gx, u32 gy, u32 gz, const int* __restrict_
     if (Y0 > hmax || (so && Y1 < hmin)) {                         // nothing of this tile is set
 #pragma unroll
         for (int q = 0; q < QUAD; ++q) set[q] = 0, val[q][0] = val[q][1] = 0;
-    } else if (!so && hmin - Y1 >= (three ? 4 : 0)) {             // every voxel is the deep material
+    } else if (!so && hmin - Y1 >= (three ? 5 : 0)) {             // every voxel is the deep material (d >= 5)
         const u32 f = three ? 0x03030303u : 0x01010101u;
 #pragma unroll
         for (int q = 0; q < QUAD; ++q) set[q] = 0xFF, val[q][0] = val[q][1] = f;
@@ -152,6 +152,48 @@ terrain_batches_kernel(int depth, u32 gx, u32 gy, u32 gz, const int* __restrict_
             dst[0] = make_int4(val[q][0] & 255, (val[q][0] >> 8) & 255, (val[q][0] >> 16) & 255, val[q][0] >> 24);
             dst[1] = make_int4(val[q][1] & 255, (val[q][1] >> 8) & 255, (val[q][1] >> 16) & 255, val[q][1] >> 24);
         }
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// High-entropy benchmark batches in device memory: bit-identical to
+// voxelis_b200/workloads.py:p_random —  v = 1 + splitmix64(lin + (seed_base + chunk) << 32) mod k  per cell of
+// `cell`^3 voxels (lin = ((x/cell)*N + y/cell)*N + z/cell), or, with k == 4, splitmix64 mod 4 with 0 = "set to the
+// default value" (clear bit, batch.rs:162-168).  One thread per block of 2^3 voxels: 2 mask bytes + 8 values.
+// ------------------------------------------------------------------------------------------------
+template <class T>
+__global__ void random_batches_kernel(u32 depth, u64 total_blocks, u32 blocks_log, u64 seed_base, u64 chunk0, u32 k, u32 cell,
+                                      u8* __restrict__ masks, T* __restrict__ values) {
+    const u64 t = blockIdx.x * u64(blockDim.x) + threadIdx.x;
+    if (t >= total_blocks) return;
+    const u64 chunk = t >> blocks_log;
+    const u32 p = u32(t & ((1ull << blocks_log) - 1));
+    const u32 bx = compact10(p), by = compact10(p >> 1), bz = compact10(p >> 2);
+    const u64 N = 1ull << depth;
+    const u64 key = (seed_base + chunk0 + chunk) << 32;
+    u32 setm = 0, clrm = 0;
+    T v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const u64 x = 2 * bx + (i & 1), y = 2 * by + ((i >> 1) & 1), z = 2 * bz + (i >> 2);
+        const u64 lin = ((x / cell) * N + (y / cell)) * N + (z / cell);
+        const u64 r = splitmix64(lin + key);
+        const u32 val = k == 4 ? u32(r % 4) : 1u + u32(r % k);
+        v[i] = T(val);
+        setm |= u32(val != 0) << i;
+        clrm |= u32(val == 0) << i;
+    }
+    *reinterpret_cast<uchar2*>(masks + t * 2) = make_uchar2(u8(setm), u8(clrm));
+    if (sizeof(T) == 1) {
+        u64 w = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w |= u64(u8(v[i])) << (8 * i);
+        *reinterpret_cast<u64*>(values + t * 8) = w;
+    } else {
+        uint4* o = reinterpret_cast<uint4*>(values + t * 8);
+        o[0] = make_uint4(u32(v[0]), u32(v[1]), u32(v[2]), u32(v[3]));
+        o[1] = make_uint4(u32(v[4]), u32(v[5]), u32(v[6]), u32(v[7]));
     }
 }
 

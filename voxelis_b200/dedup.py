@@ -139,37 +139,41 @@ def global_dedup_local(locals_, roots_list, shard_budget: int, dtype: int, devic
     return [r.shard for r in ranks], groots, summary
 
 
-def global_dedup_dist(local: VoxInterner, roots: np.ndarray, shard_budget: int, dtype: int, device: int):
-    """One process per GPU: the exchange is torch.distributed.all_to_all_single over NCCL.
-    Returns (shard, global_roots, summary) for this rank; summary counts are all-reduced."""
+_WORLDS: dict = {}
+
+
+def world_for(device: int):
+    """The process's vx_world (created once per device: ncclCommInitRank is a collective and not cheap)."""
+    from .api import World
+    if device not in _WORLDS:
+        _WORLDS[device] = World.from_torch_distributed(device)
+    return _WORLDS[device]
+
+
+def global_dedup_dist(local: VoxInterner, roots: np.ndarray, shard_budget: int, dtype: int, device: int, world=None):
+    """One process per GPU: ONE C-ABI call, vx_world_global_dedup (pack kernel, NCCL send / recv of the records and of
+    the ids, owner-side interning — voxelis_b200/csrc/vx_world.cuh).  torch.distributed is only used to hand the
+    128-byte NCCL id to the other processes when no ``world`` is given.  Returns (shard, global_roots, summary)."""
+    world = world or world_for(device)
+    shard = VoxInterner.with_memory_budget(shard_budget, dtype, device)
+    groots, summ = world.global_dedup(local, shard, roots)
+    summary = {"G": world.n_ranks, "rounds": summ["rounds"], "bytes_sent": summ["bytes_sent"], "branches": summ["branches"],
+               "leaves": summ["leaves"], "this_shard": (summ["this_shard_branches"], summ["this_shard_leaves"]),
+               "local_nodes_all_ranks": summ["local_nodes_all_ranks"],
+               "exchange": "vx_world_global_dedup: grouped ncclSend/ncclRecv issued by the library"}
+    return shard, groots, summary
+
+
+def global_dedup(local: VoxInterner, roots: np.ndarray, shard_budget: int, dtype: int, device: int):
+    """The merge for THIS process: the NCCL exchange when torch.distributed runs with more than one rank, else the
+    single-rank form.  Returns (shard, global_roots, summary)."""
     import torch.distributed as dist
-    G, rank = dist.get_world_size(), dist.get_rank()
-    dev = torch.device("cuda", device)
-    me = _Rank(rank, local, VoxInterner.with_memory_budget(shard_budget, dtype, device), dev)
-    mh = torch.tensor([me.max_height], dtype=torch.int64, device=dev)
-    dist.all_reduce(mh, op=dist.ReduceOp.MAX)
-    sent = 0
-    for h in range(int(mh.item()) + 1):
-        counts, records, src = me.pack(h, G)
-        send_counts = torch.from_numpy(counts).to(dev)
-        recv_counts = torch.empty_like(send_counts)
-        dist.all_to_all_single(recv_counts, send_counts)              # how many records each peer sends me
-        rc = recv_counts.cpu().tolist()
-        sc = counts.tolist()
-        inbox = torch.empty(max(sum(rc), 1) * REC_WORDS, dtype=torch.int64, device=dev)[: sum(rc) * REC_WORDS]
-        dist.all_to_all_single(inbox, records.contiguous(), [c * REC_WORDS for c in rc], [c * REC_WORDS for c in sc])
-        sent += records.numel() * 8
-        ids = me.intern(inbox, leaf_round=(h == 0))
-        back = torch.empty(max(sum(sc), 1), dtype=torch.int64, device=dev)[: sum(sc)]
-        dist.all_to_all_single(back, ids.contiguous(), sc, rc)        # global ids return to the senders
-        me.scatter(src, back)
-    rt = torch.from_numpy(np.ascontiguousarray(roots).view(np.int64)).to(dev)
-    groots = me.map_roots(rt).cpu().numpy().view(np.uint64)
-    tot = torch.tensor([me.created[0], me.created[1], sent], dtype=torch.int64, device=dev)
-    dist.all_reduce(tot)
-    summary = {"G": G, "rounds": int(mh.item()) + 1, "bytes_sent": int(tot[2]), "branches": int(tot[0]),
-               "leaves": int(tot[1]), "this_shard": tuple(me.created)}
-    return me.shard, groots, summary
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        shard, groots, summ = global_dedup_dist(local, roots, shard_budget, dtype, device)
+        return shard, groots, summ
+    shards, groots_l, summ = global_dedup_local([local], [roots], shard_budget, dtype, device)
+    summ.setdefault("exchange", "single rank (no exchange)")
+    return shards[0], groots_l[0], summ
 
 
 def merged_pools(shards):

@@ -231,7 +231,7 @@ def terrain_world(grid=(64, 8, 64), depth=5, variant="surface_only", dtype=U8, s
 
     surface_only       one voxel per (X, Z) column at Y = h   (benches :1265-1278; shapes.rs:302-304)
     surface_and_below  every voxel with Y <= h                 (shapes.rs:306-309); with
-                       ``materials=3``: 1 at the surface, 2 for the next 3 voxels, 3 below (:349-355)
+                       ``materials=3``: 1 for the surface voxel and the two below it, 2 for the next two, 3 deeper (:344-350)
     """
     gx, gy, gz = grid
     n = 1 << depth
@@ -258,7 +258,7 @@ def terrain_world(grid=(64, 8, 64), depth=5, variant="surface_only", dtype=U8, s
                         continue
                     if materials == 3:
                         d = hc - Y
-                        v = np.where(d == 0, 1, np.where(d <= 3, 2, 3)) * s
+                        v = np.where(d <= 2, 1, np.where(d <= 4, 2, 3)) * s      # shapes.rs:344-350
                     else:
                         v = s.astype(NP_DTYPE[dtype])
                 c = (cx * gy + cy) * gz + cz
