@@ -302,6 +302,8 @@ def main():
                     help="'strong' only runs the one-world legs faster at N = 1; both values are always in the line for N > 1")
     ap.add_argument("--workload", default="perlin", help="profiling only: time another workload in the main loop "
                     "(checkerboard | sum | sum_per_chunk | random255 | below); the headline is 'perlin'")
+    ap.add_argument("--secondary-multi", action="store_true", help="run the rank-0-only secondary legs at N > 1 too "
+                    "(they are in the N = 1 line; at N > 1 the other ranks would only wait for rank 0)")
     args = ap.parse_args()
     claim_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -318,6 +320,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    solo_legs = rank == 0 and (world == 1 or args.secondary_multi)   # legs that only rank 0 runs
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: voxelis_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -326,12 +329,16 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: stdout is ONE JSON line
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a short collective timeout: a rank that fell out of step must fail the run in minutes, not hang the box
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    barrier_all = barrier
 
     def max_over_ranks(x: float) -> float:
         if world == 1:
@@ -350,8 +357,10 @@ def main():
     peak, peak_src = peaks()
     stream = torch.cuda.Stream(dev)          # a real (non-default) stream: events on it bracket our launches
 
-    def time_device(it, depth, n, dm, dv, dr, dc, steps, warmup=3):
-        """`steps` x (reset + one apply call) on `stream`; -> (ms per step, mean ms of the apply call alone)."""
+    def time_device(it, depth, n, dm, dv, dr, dc, steps, warmup=3, all_ranks=True):
+        """`steps` x (reset + one apply call) on `stream`; -> (ms per step, mean ms of the apply call alone).
+        all_ranks=False in the legs only rank 0 runs (no cross-rank barrier there: the other ranks are elsewhere)."""
+        barrier = barrier_all if all_ranks else torch.cuda.synchronize
         for _ in range(warmup):
             it.reset_async(stream.cuda_stream)
             it.apply_batches_device(depth, n, dm.data_ptr(), dv.data_ptr(), dr.data_ptr(), dc.data_ptr() if dc is not None else 0,
@@ -536,7 +545,7 @@ def main():
     stats_mem = it.memory()
     del it
     traffic, traffic_detail = None, None
-    if rank == 0 and not args.no_traffic:
+    if solo_legs and not args.no_traffic:
         log("measuring DRAM traffic of one apply call (ncu replay of the same step)")
         t = measure_dram_traffic(args.workload if args.workload in ("perlin", "below") else f"{args.workload}:4096")
         if "error" in t:
@@ -550,7 +559,7 @@ def main():
 
     # ---------------------------------------------------------------- the dense headline: surface-and-below terrain
     headline_dense = None
-    if rank == 0 and not args.no_others and args.workload == "perlin":
+    if solo_legs and not args.no_others and args.workload == "perlin":
         try:
             log("dense headline: perlin surface-and-below (3 materials)")
             m2, v2 = make_world(0, "surface_and_below")
@@ -558,7 +567,7 @@ def main():
             tb2 = int(np.count_nonzero(m2[:, :, 0]))
             dm2, dv2 = torch.from_numpy(m2).to(dev), torch.from_numpy(v2).to(dev)
             itb = vx.VoxInterner.with_memory_budget(BUDGET, vx.U8, local_rank)
-            sms, kms = time_device(itb, DEPTH, n, dm2, dv2, d_roots, None, max(20, min(args.steps, 200)))
+            sms, kms = time_device(itb, DEPTH, n, dm2, dv2, d_roots, None, max(20, min(args.steps, 200)), all_ranks=False)
             nn2 = itb.stats()["total_cache_misses"]
 
             def step2():
@@ -584,7 +593,7 @@ def main():
 
     # ---------------------------------------------------------------- config 1: one 32^3 set_uniform chunk, host Batch
     latency = None
-    if rank == 0 and not args.no_others:
+    if solo_legs and not args.no_others:
         try:
             log("config 1: single-chunk latency")
             itl = vx.VoxInterner.with_memory_budget(BUDGET, vx.U8, local_rank)
@@ -617,7 +626,7 @@ def main():
 
     # ---------------------------------------------------------------- secondary workloads (rank 0)
     others = {}
-    if rank == 0 and not args.no_others:
+    if solo_legs and not args.no_others:
         # (name, generator, interner budget): random255 creates ~4 936 new nodes per chunk
         sets = [("checkerboard_x4096", lambda: wl.named_workload("checkerboard", 4096), BUDGET, "checkerboard:4096"),
                 ("set_sum_x4096", lambda: wl.named_workload("sum", 4096), BUDGET, "sum:4096"),
@@ -637,7 +646,7 @@ def main():
                 it2 = vx.VoxInterner.with_memory_budget(budget2, dt2, local_rank)
                 dm, dv = torch.from_numpy(m2).to(dev), torch.from_numpy(v2).to(dev)
                 dr = torch.zeros(n2, dtype=torch.int64, device=dev)
-                _, ms = time_device(it2, depth2, n2, dm, dv, dr, None, 20)
+                _, ms = time_device(it2, depth2, n2, dm, dv, dr, None, 20, all_ranks=False)
                 nn = it2.stats()["total_cache_misses"]
                 d2 = it2.debug_counters()
 

@@ -165,7 +165,9 @@ int vx_tree_is_dirty(const vx_tree*);                 /* VoxOpsDirty   voxtree.r
 void vx_tree_mark_dirty(vx_tree*);
 void vx_tree_clear_dirty(vx_tree*);
 /* Hands the tree a root whose reference the caller already holds (the roots vx_model_deserialize returns carry
- * the reference VoxTree::set_root_id took for them, voxtree.rs:135-141).  No refcount change; marks the tree dirty. */
+ * the reference VoxTree::set_root_id took for them, voxtree.rs:135-141).  No refcount change; marks the tree dirty.
+ * The id is NOT checked (there is no interner in this call): use vx_tree_set_root_id for ids of unknown provenance —
+ * it verifies that the slot is live and of the id's generation (is_valid_block_id, interner/mod.rs:997-1008). */
 int vx_tree_adopt_root(vx_tree*, vx_block_id root);
 /* After vx_interner_reset every tree built in that interner dangles; this makes n of them empty again
  * without touching the interner (what dropping and re-creating the VoxTrees does in the reference). */

@@ -1,4 +1,4 @@
-"""Writes tests/golden/around_the_path.json: SHA-256 digests of the oracle's outputs for fixed, seeded inputs of the
+"""Writes tests/golden/self_regression_digests.json: SHA-256 digests of the oracle's outputs for fixed, seeded inputs of the
 steps either side of the path (occupancy planes, voxeliser, terrain generator).  The reference itself cannot be run
 here (Rust, no cargo), so these are REGRESSION vectors of the pinned oracle, not reference outputs: they freeze today's
 answers so that a later change to the oracle or the generators cannot go unnoticed.
@@ -57,6 +57,6 @@ def compute():
 
 
 if __name__ == "__main__":
-    path = os.path.join(HERE, "around_the_path.json")
+    path = os.path.join(HERE, "self_regression_digests.json")
     json.dump(compute(), open(path, "w"), indent=1, sort_keys=True)
     print(open(path).read())

@@ -181,3 +181,89 @@ def test_set_root_id_shares_a_tree(gpu_api):
     assert np.array_equal(t2.to_vec(it), wl.dense_expected(m[0], v[0]))
     t2.clear(it)
     assert it.stats()["alive_nodes"] == 1
+
+
+# ---------------------------------------------------------------------------------------------- ADVICE (round 1)
+@pytest.mark.parametrize("builder", ["fused", "bulk"])
+def test_i32_out_of_memory_with_repeated_values_returns(gpu_api, builder, monkeypatch):
+    """i32 leaves live in an open-addressing table whose key is claimed before the index is allocated.  When the
+    allocation fails ("Out of memory", interner/macros.rs:38) every lane / warp waiting for the same value must be
+    told, not left spinning: the call has to come back with VX_E_OOM."""
+    vx = gpu_api
+    monkeypatch.setenv("VX_BUILDER", builder)
+    # ~200 distinct values, each shared by many uniform 2^3 cells (= many lanes ask for the same new leaf at once)
+    masks, values = wl.batch_from_function(5, wl.p_random(200, cell=2), wl.I32, 16 if builder == "bulk" else 2)
+    g = vx.VoxInterner.with_memory_budget(82 * 48, wl.I32)          # 48 nodes
+    with pytest.raises(vx.VoxelisError) as e:
+        g.apply_batches_slab(5, masks, values)
+    assert e.value.code == -2
+    g.reset()
+    m2, v2 = wl.batch_from_function(5, wl.p_uniform(-7), wl.I32, 1)
+    roots, changed = g.apply_batches_slab(5, m2, v2)
+    assert changed[0] == 1 and vx.id_is_leaf(roots[0])
+
+
+def test_i32_dedup_shard_out_of_memory_returns(gpu_api):
+    """The same for the owner side of the global dedup (intern_records_kernel, leaf round)."""
+    from voxelis_b200 import dedup
+    vx = gpu_api
+    masks, values = wl.batch_from_function(4, wl.p_random(200, cell=2), wl.I32, 8)
+    locals_, roots = [], []
+    for r in range(2):
+        it = vx.VoxInterner.with_memory_budget(32 << 20, wl.I32)
+        rt, _ = it.apply_batches_slab(4, masks, values)
+        locals_.append(it)
+        roots.append(rt)
+    with pytest.raises(vx.VoxelisError) as e:
+        dedup.global_dedup_local(locals_, roots, 82 * 24, wl.I32)   # shards of 24 nodes
+    assert e.value.code == -2
+
+
+def test_i32_leaf_tombstones_are_reclaimed(gpu_api, oracle_api, monkeypatch):
+    """Releasing an i32 leaf leaves a tombstone in the leaf table; the periodic table rebuild re-inserts the live
+    leaves too, so create / release cycles never eat the table (the reference's map removes the entry,
+    interner/mod.rs:276-281).  VX_REHASH_AT forces a rebuild every few releases."""
+    vx, o = gpu_api, oracle_api
+    monkeypatch.setenv("VX_REHASH_AT", "40")
+    g = vx.VoxInterner.with_memory_budget(8 << 20, wl.I32)
+    keep = vx.VoxTree(4, wl.I32)
+    kb = keep.create_batch()
+    km, kv = wl.batch_from_function(4, wl.p_random(9, cell=2), wl.I32, 1)
+    kb.assign(km[0], kv[0])
+    assert keep.apply_batch(g, kb)
+    want_keep = wl.dense_expected(km[0], kv[0])
+    for cycle in range(40):
+        t = vx.VoxTree(4, wl.I32)
+        b = t.create_batch()
+        m, v = wl.batch_from_function(4, wl.p_random(60, cell=2), wl.I32, 1, chunk_arg=[1000 + cycle])
+        v = (v * 1000 + cycle).astype(np.int32) * (m[:, :, :1] != 0)      # values nobody else uses: fresh leaves every cycle
+        b.assign(m[0], v[0])
+        assert t.apply_batch(g, b)
+        assert np.array_equal(t.to_vec(g), wl.dense_expected(m[0], v[0]))
+        t.clear(g)                                                        # releases the cycle's leaves -> tombstones
+        assert np.array_equal(keep.to_vec(g), want_keep)                  # the tree that stays is untouched by rebuilds
+    st = g.stats()
+    c = o.VoxInterner(8 << 20, wl.I32)
+    cr, _ = c.apply_batches_fresh(4, km, kv)
+    assert st["alive_nodes"] == c.stats()["alive_nodes"]
+    # a fresh build after all the churn still finds (not duplicates) the surviving leaves
+    roots, _ = g.apply_batches_slab(4, km, kv)
+    assert int(roots[0]) == keep.get_root_id() and g.stats()["alive_nodes"] == st["alive_nodes"]
+
+
+def test_set_root_id_rejects_stale_ids(gpu_api):
+    """A released id (free slot / bumped generation), an index never allocated, or a forged generation must be refused
+    (reference: assert is_valid_block_id, interner/mod.rs:997-1008) instead of putting a reference on a dead slot."""
+    vx = gpu_api
+    it = vx.VoxInterner.with_memory_budget(8 << 20)
+    t1, t2 = vx.VoxTree(4), vx.VoxTree(4)
+    m, v = wl.batch_from_function(4, wl.p_sum(1), wl.U8, 1)
+    b = t1.create_batch()
+    set_batch_arrays(b, m[0], v[0])
+    assert t1.apply_batch(it, b)
+    root = t1.get_root_id()
+    assert vx.lib().vx_tree_set_root_id(it.h, t2.h, root ^ (1 << 32)) == -1          # wrong generation
+    assert vx.lib().vx_tree_set_root_id(it.h, t2.h, (root & ~0xFFFFFFFF) | 60000) == -1   # never allocated
+    t1.clear(it)
+    assert vx.lib().vx_tree_set_root_id(it.h, t2.h, root) == -1                       # released
+    assert t2.is_empty() and it.stats()["alive_nodes"] == 1

@@ -188,3 +188,31 @@ def test_import_vtm_file_and_errors(gpu_api, oracle_api, tmp_path):
     with pytest.raises(vx.VoxelisError):
         g3.model_deserialize(g.model_serialize(positions, groots)[:-3])      # truncated
     assert g3.stats()["alive_nodes"] == 1
+
+
+def test_import_rejects_cycles_and_duplicate_nodes(gpu_api):
+    """A payload whose graph is not a DAG of distinct nodes is refused before the interner is touched (the reference
+    trusts the file and would loop or panic; a GPU walk over a cycle never ends)."""
+    import struct
+    vx = gpu_api
+    be = lambda v: struct.pack(">I", v)
+    chunk = b"VoxTreeChunk" + be(0) + be(0) + be(0)
+    # ids: 1 = Leaf(1); 2, 3 = branches.  (a) branch 2 -> child 3, branch 3 -> child 2: a cycle
+    cyc = be(1) + b"\x01\x01" + be(2) + b"\x02\x01\x03\x01" + b"\x03\x01\x02\x01" + be(1) + chunk + b"\x02"
+    # (b) branch 2 lists itself
+    selfref = be(1) + b"\x01\x01" + be(1) + b"\x02\x03\x01\x02\x01" + be(1) + chunk + b"\x02"
+    # (c) two leaves with one value
+    dup_leaf = be(2) + b"\x01\x05" + b"\x02\x05" + be(0) + be(1) + chunk + b"\x01"
+    # (d) two branches with the same children
+    dup_branch = be(1) + b"\x01\x01" + be(2) + b"\x02\x01\x01\x01" + b"\x03\x01\x01\x01" + be(1) + chunk + b"\x03"
+    for name, data in (("cycle", cyc), ("self", selfref), ("dup leaf", dup_leaf), ("dup branch", dup_branch)):
+        g = vx.VoxInterner.with_memory_budget(1 << 20)
+        with pytest.raises(vx.VoxelisError) as e:
+            g.model_deserialize(data)
+        assert e.value.code == -1, name
+        assert g.next_index == 1, name                       # nothing was installed
+    # the well-formed sibling of (d) goes through
+    ok = be(1) + b"\x01\x01" + be(2) + b"\x02\x01\x01\x01" + b"\x03\x03\x01\x02\x01" + be(1) + chunk + b"\x03"
+    g = vx.VoxInterner.with_memory_budget(1 << 20)
+    pos, roots = g.model_deserialize(ok)
+    assert len(roots) == 1 and g.next_index == 4

@@ -353,6 +353,7 @@ __device__ inline u64 leaf_get(Ctx<int32_t>& c, u32 v, bool need) {
     u64 mykey = u64(v) | (1ull << 32);
     u32 s = u32(leaf_hash(v)) & c.in.leaf_mask;
     int guard = 0;
+    u32 spins = 0;
     while (__any_sync(FULL, miss)) {
         if (miss) {
             u64 k = ld_strong(&c.in.leaf_keys[s]);
@@ -362,7 +363,10 @@ __device__ inline u64 leaf_get(Ctx<int32_t>& c, u32 v, bool need) {
                     u32 gen;
                     u32 idx = alloc_one(c.in, c.use_free, &gen);
                     if (idx >= c.in.capacity) {
+                        // "Out of memory" (interner/macros.rs:38).  The key stays claimed (probes may have walked past
+                        // it), so the id word tells everyone waiting for this value that it will never come
                         set_error(c.in, ERR_OOM);
+                        st_strong(&c.in.leaf_ids[s], ID_PENDING);
                         miss = false;
                     } else {
                         leaf_payload<int32_t>(c.in, idx, v);
@@ -378,8 +382,10 @@ __device__ inline u64 leaf_get(Ctx<int32_t>& c, u32 v, bool need) {
             } else if (k == mykey) {
                 u64 g = ld_strong(&c.in.leaf_ids[s]);
                 if (g != 0) {
-                    id = g;
+                    id = g == ID_PENDING ? 0 : g;  // ID_PENDING: its creator ran out of memory (the interner is poisoned)
                     miss = false;
+                } else if (((++spins) & 0xFFF) == 0 && ld_strong(c.in.error) != ERR_NONE) {
+                    miss = false;  // whoever claimed the key may have left the kernel on an error: do not wait for ever
                 }
             } else {
                 s = (s + 1) & c.in.leaf_mask;

@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <array>
 #include <atomic>
 #include <chrono>
 #include <cstdio>
@@ -640,14 +641,24 @@ int release_roots(vx_interner* it, const u64* h_roots, size_t n) {
     it->tombs_host += freed;
     rc = refresh_free_count(it);
     if (rc != VX_OK) return rc;
-    // rebuild the branch table once deleted slots take a quarter of it
-    if (it->tombs_host > it->nbuckets * 2) {
+    // rebuild the tables once deleted slots may take a quarter of one of them (tombs_host counts every freed node,
+    // so it bounds the tombstones of either table from above)
+    size_t rehash_at = it->nbuckets * 2;
+    if (it->dtype != VX_U8) rehash_at = std::min(rehash_at, it->leaf_slots / 4);
+    if (const char* e = getenv("VX_REHASH_AT")) rehash_at = size_t(strtoull(e, nullptr, 10));  // tests
+    if (it->tombs_host > rehash_at) {
         Scalars sc{};
         CU_TRY(cudaMemcpyAsync(&sc, it->d_scalars, sizeof(sc), cudaMemcpyDeviceToHost, s));
         CU_TRY(cudaStreamSynchronize(s));
         u32 next = std::min<u32>(sc.next_index, u32(it->capacity));
         CU_TRY(cudaMemsetAsync(it->dev.slots, 0, it->nbuckets * 64, s));
-        rehash_kernel<<<(next + 255) / 256, 256, 0, s>>>(it->dev, next);
+        if (it->dtype == VX_U8) {
+            rehash_kernel<u8><<<(next + 255) / 256, 256, 0, s>>>(it->dev, next);
+        } else {
+            CU_TRY(cudaMemsetAsync(it->dev.leaf_keys, 0, it->leaf_slots * 8, s));
+            CU_TRY(cudaMemsetAsync(it->dev.leaf_ids, 0, it->leaf_slots * 8, s));
+            rehash_kernel<int32_t><<<(next + 255) / 256, 256, 0, s>>>(it->dev, next);
+        }
         CU_TRY(cudaGetLastError());
         CU_TRY(cudaStreamSynchronize(s));
         it->tombs_host = 0;
@@ -2209,6 +2220,24 @@ int vx_tree_set_root_id(vx_interner* it, vx_tree* t, vx_block_id root) {
     if (root == VX_BLOCK_INVALID || id_index(root) >= it->capacity) return fail(VX_E_INVALID, "invalid block id");
     std::lock_guard<std::mutex> lk(it->mu);
     DeviceGuard g(it->device);
+    if (root != VX_BLOCK_EMPTY) {
+        // is_valid_block_id (interner/mod.rs:997-1008): the slot must be live and of the id's generation — a stale id
+        // would put a reference on a free or recycled slot, which is later freed a second time
+        Scalars sc;
+        int rc = read_scalars(it, &sc);
+        if (rc != VX_OK) return rc;
+        const u32 idx = id_index(root);
+        u16 gen = 0;
+        u64 hash = 0;
+        u32 ref = 0;
+        if (idx == 0 || idx >= sc.next_index) return fail(VX_E_INVALID, "invalid block id (index was never allocated)");
+        CU_TRY(cudaMemcpyAsync(&gen, it->dev.gens + idx, 2, cudaMemcpyDeviceToHost, it->stream));
+        CU_TRY(cudaMemcpyAsync(&hash, it->dev.hashes + idx, 8, cudaMemcpyDeviceToHost, it->stream));
+        CU_TRY(cudaMemcpyAsync(&ref, it->dev.refs + idx, 4, cudaMemcpyDeviceToHost, it->stream));
+        CU_TRY(cudaStreamSynchronize(it->stream));
+        if (hash == 0 || ref == 0 || gen != u16((root >> 32) & 0x7FFF))
+            return fail(VX_E_INVALID, "invalid block id (slot is free or belongs to another generation)");
+    }
     t->root = root;  // voxtree.rs:135-141: adopt + inc_ref (the previous root is NOT released, as in the reference)
     add_ref_kernel<<<1, 1, 0, it->stream>>>(it->dev, root, 1u);
     CU_TRY(cudaGetLastError());
@@ -2463,6 +2492,9 @@ int model_serialize_impl(vx_interner* it, size_t n, const int32_t* positions, co
     int rc = read_scalars(it, &sc);
     if (rc != VX_OK) return rc;
     const u32 nn = sc.next_index;
+    // record sizes and offsets are scanned as u32 (the format's own size field is a u32, io/export.rs:141-143): refuse
+    // up front what could wrap — a record is at most varint(5) + mask(1) + 8 child varints(40) + value(4) bytes
+    if (size_t(nn) * 50 + size_t(n) * 29 + 12 > 0xFFFFFFFFull) return fail(VX_E_INVALID, "VTM data could exceed 4 GiB");
     auto up = [](size_t v) { return (v + 255) & ~size_t(255); };
     const size_t words = up(size_t(nn + 1) * 4);
     size_t scan_tmp = 0;
@@ -2657,6 +2689,56 @@ int model_deserialize_impl(vx_interner* it, const u8* data, size_t len, int32_t*
         if (id) refs[id] += 1;  // set_root_id (voxtree.rs:135-141)
     }
     if (!r.ok) return fail(VX_E_INVALID, "VTM payload: truncated");
+    // ---- the graph must be a DAG of DISTINCT nodes before anything touches the interner.  The reference trusts the
+    // file (a missing map entry panics, voxmodel.rs:352-360); a crafted or damaged payload could otherwise install a
+    // branch that reaches itself (walks never end, refcounts never reach zero) or two nodes with one key (the
+    // install kernel's table entries would race and canonicity is lost).  The MD5 only guards against accidents.
+    {
+        std::unordered_map<int64_t, u32> leaf_seen;
+        leaf_seen.reserve(size_t(L) * 2);
+        for (u32 k = 0; k < L; ++k) {
+            int64_t v = vs == 1 ? int64_t(values[k]) : int64_t(*reinterpret_cast<const int32_t*>(&values[size_t(k) * 4]));
+            if (!leaf_seen.emplace(v, k).second) return fail(VX_E_INVALID, "VTM payload: two leaves with the same value");
+        }
+        // heights by repeated relaxation in file order would be quadratic on a hostile file: iterative DFS instead
+        std::vector<u8> state(size_t(Bc), 0);  // 0 = unvisited, 1 = on the stack, 2 = done
+        std::vector<std::pair<u32, u8>> stack;
+        for (u32 b0 = 0; b0 < Bc; ++b0) {
+            if (state[b0]) continue;
+            stack.push_back({b0, 0});
+            state[b0] = 1;
+            while (!stack.empty()) {
+                auto& top = stack.back();
+                if (top.second == 8) {
+                    state[top.first] = 2;
+                    stack.pop_back();
+                    continue;
+                }
+                const u32 id = kids[size_t(top.first) * 8 + top.second++];
+                if (id <= L) continue;  // EMPTY or a leaf
+                const u32 cb = id - L - 1;
+                if (state[cb] == 1) return fail(VX_E_INVALID, "VTM payload: a branch reaches itself (cycle)");
+                if (state[cb] == 0) {
+                    state[cb] = 1;
+                    stack.push_back({cb, 0});
+                }
+            }
+        }
+        struct RowHash {
+            size_t operator()(const std::array<u32, 8>& a) const {
+                u64 h = 0;
+                for (int i = 0; i < 8; ++i) h = mix64(h + a[i] + 0x9E3779B97F4A7C15ull * (i + 1));
+                return size_t(h);
+            }
+        };
+        std::unordered_map<std::array<u32, 8>, u32, RowHash> row_seen;
+        row_seen.reserve(size_t(Bc) * 2);
+        for (u32 k = 0; k < Bc; ++k) {
+            std::array<u32, 8> row;
+            for (int c = 0; c < 8; ++c) row[c] = kids[size_t(k) * 8 + c];
+            if (!row_seen.emplace(row, k).second) return fail(VX_E_INVALID, "VTM payload: two branches with the same children");
+        }
+    }
     // ---- install
     std::lock_guard<std::mutex> lk(it->mu);
     DeviceGuard g(it->device);

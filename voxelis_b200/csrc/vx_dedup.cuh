@@ -162,6 +162,7 @@ __global__ void intern_records_kernel(InternerDev in, u32 n, const u64* records,
                             u32 idx = atomicAdd(in.next_index, 1u);
                             if (idx >= in.capacity) {
                                 set_error(in, ERR_OOM);
+                                st_strong(&in.leaf_ids[s], ID_PENDING);  // waiters for this value must not spin for ever
                             } else {
                                 ((u32*)in.values)[idx] = v;
                                 in.hashes[idx] = leaf_hash(v);
@@ -177,7 +178,7 @@ __global__ void intern_records_kernel(InternerDev in, u32 n, const u64* records,
                     } else if (k == mykey) {
                         u64 g = ld_strong(&in.leaf_ids[s]);
                         if (g != 0) {
-                            result = g;
+                            result = g == ID_PENDING ? 0 : g;  // ID_PENDING: the creator ran out of memory
                             done = true;
                         }
                     } else {

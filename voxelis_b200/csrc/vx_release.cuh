@@ -109,7 +109,10 @@ __global__ void release_level_kernel(InternerDev in, const u64* frontier, u32 co
     }
 }
 
-// Re-inserts every live branch into a cleared table (drops accumulated tombstones).
+// Re-inserts every live node into cleared tables (drops accumulated tombstones): branches into the bucketised branch
+// table, wide-T leaves into the open-addressing leaf table (released leaves leave tombstones there too — the
+// reference's pattern map simply removes the entry, interner/mod.rs:276-281).  u8 leaves sit in a direct-mapped table.
+template <class T>
 __global__ void rehash_kernel(InternerDev in, u32 next_index) {
     u32 idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx == 0 || idx >= next_index) return;
@@ -117,7 +120,19 @@ __global__ void rehash_kernel(InternerDev in, u32 next_index) {
     if (h == 0) return;  // free slot
     bool branch = false;
     for (int k = 0; k < 8; ++k) branch = branch || in.children[size_t(idx) * 8 + k] != 0;
-    if (!branch) return;  // leaf
+    if (!branch) {
+        if (sizeof(T) == 1) return;
+        const u32 v = ((const u32*)in.values)[idx];
+        const u64 key = u64(v) | (1ull << 32);
+        u32 s = u32(leaf_hash(v)) & in.leaf_mask;
+        for (;;) {
+            if (atomicCAS((ull*)&in.leaf_keys[s], 0ull, (ull)key) == 0ull) {
+                in.leaf_ids[s] = id_leaf((u64(in.gens[idx]) << 32) | idx);
+                return;
+            }
+            s = (s + 1) & in.leaf_mask;
+        }
+    }
     u64 word = (u64(u32(h >> 47)) << 47) | (u64(in.gens[idx]) << 32) | idx;
     u32 bucket = u32(h) & in.bucket_mask;
     for (;;) {
