@@ -104,54 +104,130 @@ __global__ void __launch_bounds__(256) bulk_zero_kernel(BulkArgs a, u32 dense1_b
 // ------------------------------------------------------------------------------------------------
 // plan: one warp per unit of 512 Morton-consecutive blocks (lane = 16 blocks = 32 B of masks).
 // ------------------------------------------------------------------------------------------------
+// busy units of a warp wait in the lanes' registers (lane k holds the k-th) and enter the queue with ONE atomic per
+// 32 of them: a dense world would otherwise put one same-address atomic per unit on a single L2 slice
+__device__ __forceinline__ void plan_flush_busy(const BulkArgs& a, u32 lane, u32 my_busy, u32& n_busy) {
+    if (n_busy == 0) return;
+    u32 base = 0;
+    if (lane == 0) base = atomicAdd(&a.cnt[3], n_busy);
+    base = __shfl_sync(FULL, base, 0);
+    if (lane < n_busy) a.dense_units[base + lane] = my_busy;
+    n_busy = 0;
+}
+
+// One NON-EMPTY unit w whose 1 KiB of masks sits in the warp's registers (lane = 16 blocks = q0, q1).
+__device__ __forceinline__ void plan_unit(const BulkArgs& a, u32 lane, unsigned long long w, const uint4& q0, const uint4& q1,
+                                          u32& my_busy, u32& n_busy) {
+    // set_mask bytes (even positions; clear_mask is never read by the reference)
+    const u64 sa = u64(__byte_perm(q0.x, q0.y, 0x6420)) | (u64(__byte_perm(q0.z, q0.w, 0x6420)) << 32);
+    const u64 sb = u64(__byte_perm(q1.x, q1.y, 0x6420)) | (u64(__byte_perm(q1.z, q1.w, 0x6420)) << 32);
+    const u32 bits = nzbytes(sa) | (nzbytes(sb) << 8);  // candidate blocks of this lane
+    const u32 pa = (bits & 0xFF) != 0, pb = (bits >> 8) != 0;  // this lane's two level-1 parents
+    // exclusive prefix sums over the lanes: candidates at level 0 (r0) and level 1 (r1), packed
+    const u32 mine = u32(__popc(bits)) | ((pa + pb) << 16);
+    u32 incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        u32 t = __shfl_up_sync(FULL, incl, o);
+        if (lane >= u32(o)) incl += t;
+    }
+    const u32 tot = __shfl_sync(FULL, incl, 31);
+    const u32 r0 = (incl - mine) & 0xFFFF, r1 = (incl - mine) >> 16;
+    const u32 c0 = tot & 0xFFFF, c1 = tot >> 16;
+    if (lane == 0 && a.blocks > UNIT_BLOCKS) {  // the group of eight units this one belongs to has work above it
+        const u32 cube = u32(w >> 3);
+        if (atomicExch(&a.cube_flag[cube], a.epoch) != a.epoch) a.cube_list[atomicAdd(&a.cnt[5], 1u)] = cube;
+    }
+    if (c0 >= a.dense_min) {
+        // a busy unit: thread-per-block lists would cost more than they save; one warp builds it the
+        // way apply_kernel does (lane = block, siblings in neighbouring lanes)
+        if (lane == n_busy) my_busy = u32(w);
+        if (++n_busy == 32) plan_flush_busy(a, lane, my_busy, n_busy);
+        if (lane == 0) {
+            a.unit_first[w] = UNIT_PREBUILT;
+            a.unit_cm[w] = 0xFF;
+        }
+        return;
+    }
+    // level 2: node q = lanes 4q..4q+3 (eight level-1 parents)
+    u32 cm2 = (pa | (pb << 1)) << (2 * (lane & 3));
+    cm2 |= __shfl_xor_sync(FULL, cm2, 1);
+    cm2 |= __shfl_xor_sync(FULL, cm2, 2);
+    const u32 b2 = __ballot_sync(FULL, (lane & 3) == 0 && cm2 != 0);  // bits at lanes 0,4,..,28
+    const u32 c2 = __popc(b2);
+    u32 base = 0;
+    if (lane < 3) base = atomicAdd(&a.cnt[lane], lane == 0 ? c0 : lane == 1 ? c1 : c2);
+    const u32 base0 = __shfl_sync(FULL, base, 0), base1 = __shfl_sync(FULL, base, 1), base2 = __shfl_sync(FULL, base, 2);
+    // level 0 entries: global block index + set_mask
+    {
+        u32 bb = bits, k = base0 + r0;
+        const u32 blk0 = u32(w * UNIT_BLOCKS) + lane * 16;
+        while (bb) {
+            const int j = __ffs(bb) - 1;
+            bb &= bb - 1;
+            a.first[0][k] = blk0 + j;
+            a.cm[0][k] = u8((j < 8 ? sa >> (8 * j) : sb >> (8 * (j - 8))) & 0xFF);
+            ++k;
+        }
+    }
+    // level 1 entries: first child slot in level 0 + which of the eight blocks are candidates
+    if (pa) {
+        a.first[1][base1 + r1] = base0 + r0;
+        a.cm[1][base1 + r1] = u8(bits & 0xFF);
+    }
+    if (pb) {
+        a.first[1][base1 + r1 + pa] = base0 + r0 + __popc(bits & 0xFF);
+        a.cm[1][base1 + r1 + pa] = u8(bits >> 8);
+    }
+    // level 2 entries
+    if ((lane & 3) == 0 && cm2 != 0) {
+        const u32 k2 = base2 + __popc(b2 & ((1u << lane) - 1));
+        a.first[2][k2] = base1 + r1;
+        a.cm[2][k2] = u8(cm2);
+    }
+    // the unit node (dense): children = the unit's level-2 candidates
+    if (lane == 0) {
+        u32 cm3 = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) cm3 |= ((b2 >> (4 * q)) & 1u) << q;
+        a.unit_first[w] = base2;
+        a.unit_cm[w] = u8(cm3);
+    }
+}
+
+__device__ __forceinline__ bool plan_any_set(const uint4& q0, const uint4& q1) {
+    return ((q0.x | q0.y | q0.z | q0.w | q1.x | q1.y | q1.z | q1.w) & 0x00FF00FFu) != 0;  // set_mask bytes only
+}
+
+// plan: one warp per unit of 512 Morton-consecutive blocks (lane = 16 blocks = 32 B of masks: one LDG.256), the masks of
+// the warp's next unit in flight while one is planned.  Measured and dropped (profiles/README.md): a cp.async.bulk +
+// mbarrier ring of 4 KiB per warp (76 us against 70), a warp per group of eight units with all 8 KiB in flight (87 us; 98
+// registers) — the launch is not short of bytes in flight; what it has on top of the streaming read is the per-unit
+// list allocation of the non-empty units.
 __global__ void __launch_bounds__(256) bulk_plan_kernel(BulkArgs a) {
     const u32 lane = threadIdx.x & 31;
     const unsigned long long warp = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const unsigned long long nwarps = (size_t(gridDim.x) * blockDim.x) >> 5;
-    // register queue: the masks of the next PLAN_AHEAD units of this warp are in flight while one is planned
-    constexpr int PLAN_AHEAD = 1;
-    uint4 qa[PLAN_AHEAD], qb[PLAN_AHEAD];
-    unsigned long long qw[PLAN_AHEAD];
     const bool listed = a.unit_list != nullptr;
-    const unsigned long long total = listed ? a.n_listed : a.units;
     // the previous call's last launch wiped the unit memo if the count stood at MEMO_CLEAR_AT or more
     if (a.memo_on && blockIdx.x == 0 && threadIdx.x == 0 && *a.memo_count >= MEMO_CLEAR_AT) *a.memo_count = 0;
-    // busy units of this warp wait in the lanes' registers (lane k holds the k-th) and enter the queue with ONE
-    // atomic per warp: a dense world would otherwise put one same-address atomic per unit on a single L2 slice
     u32 my_busy = 0, n_busy = 0;
-    auto flush_busy = [&]() {
-        if (n_busy == 0) return;
-        u32 base = 0;
-        if (lane == 0) base = atomicAdd(&a.cnt[3], n_busy);
-        base = __shfl_sync(FULL, base, 0);
-        if (lane < n_busy) a.dense_units[base + lane] = my_busy;
-        n_busy = 0;
-    };
-#pragma unroll
-    for (int d = 0; d < PLAN_AHEAD; ++d) {
-        qa[d] = qb[d] = make_uint4(0, 0, 0, 0);
-        qw[d] = 0;
-        if (warp + d * nwarps < total) {
-            qw[d] = listed ? a.unit_list[warp + d * nwarps] : warp + d * nwarps;
-            ld_stream_v8(a.masks + qw[d] * (UNIT_BLOCKS * 2) + lane * 32, &qa[d], &qb[d]);
-        }
+    // unit by unit, the masks of the next unit of this warp in flight while one is planned
+    const unsigned long long total = listed ? a.n_listed : a.units;
+    auto unit_at = [&](unsigned long long e) -> unsigned long long { return listed ? a.unit_list[e] : e; };
+    uint4 na = make_uint4(0, 0, 0, 0), nb = na;
+    unsigned long long nw = 0;
+    if (warp < total) {
+        nw = unit_at(warp);
+        ld_stream_v8(a.masks + nw * (UNIT_BLOCKS * 2) + lane * 32, &na, &nb);
     }
     for (unsigned long long e = warp; e < total; e += nwarps) {
-        const uint4 q0 = qa[0], q1 = qb[0];
-        const unsigned long long w = qw[0];
-#pragma unroll
-        for (int d = 0; d + 1 < PLAN_AHEAD; ++d) {
-            qa[d] = qa[d + 1];
-            qb[d] = qb[d + 1];
-            qw[d] = qw[d + 1];
+        const uint4 q0 = na, q1 = nb;
+        const unsigned long long w = nw;
+        if (e + nwarps < total) {
+            nw = unit_at(e + nwarps);
+            ld_stream_v8(a.masks + nw * (UNIT_BLOCKS * 2) + lane * 32, &na, &nb);
         }
-        if (e + PLAN_AHEAD * nwarps < total) {
-            qw[PLAN_AHEAD - 1] = listed ? a.unit_list[e + PLAN_AHEAD * nwarps] : e + PLAN_AHEAD * nwarps;
-            ld_stream_v8(a.masks + qw[PLAN_AHEAD - 1] * (UNIT_BLOCKS * 2) + lane * 32, &qa[PLAN_AHEAD - 1],
-                         &qb[PLAN_AHEAD - 1]);
-        }
-        // the first upper launch only visits groups of eight units that hold something; the first unit of
-        // every group says "empty" for it beforehand (roots / changed for D = 5, the dense level above else)
         if (!listed && lane == 0 && (w & 7) == 0 && a.blocks > UNIT_BLOCKS) {
             if (a.blocks == 8 * UNIT_BLOCKS) {
                 a.roots[w >> 3] = 0;
@@ -160,88 +236,13 @@ __global__ void __launch_bounds__(256) bulk_plan_kernel(BulkArgs a) {
                 a.dense[1][w >> 3] = 0;
             }
         }
-        // most units of a sparse world are empty: one OR over the set_mask bytes settles those
-        if (!__any_sync(FULL, ((q0.x | q0.y | q0.z | q0.w | q1.x | q1.y | q1.z | q1.w) & 0x00FF00FFu) != 0)) {
+        if (!__any_sync(FULL, plan_any_set(q0, q1))) {
             if (lane == 0) a.unit_cm[w] = 0;
             continue;
         }
-        // set_mask bytes (even positions; clear_mask is never read by the reference)
-        const u64 sa = u64(__byte_perm(q0.x, q0.y, 0x6420)) | (u64(__byte_perm(q0.z, q0.w, 0x6420)) << 32);
-        const u64 sb = u64(__byte_perm(q1.x, q1.y, 0x6420)) | (u64(__byte_perm(q1.z, q1.w, 0x6420)) << 32);
-        const u32 bits = nzbytes(sa) | (nzbytes(sb) << 8);  // candidate blocks of this lane
-        const u32 pa = (bits & 0xFF) != 0, pb = (bits >> 8) != 0;  // this lane's two level-1 parents
-        // exclusive prefix sums over the lanes: candidates at level 0 (r0) and level 1 (r1), packed
-        const u32 mine = u32(__popc(bits)) | ((pa + pb) << 16);
-        u32 incl = mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            u32 t = __shfl_up_sync(FULL, incl, o);
-            if (lane >= u32(o)) incl += t;
-        }
-        const u32 tot = __shfl_sync(FULL, incl, 31);
-        const u32 r0 = (incl - mine) & 0xFFFF, r1 = (incl - mine) >> 16;
-        const u32 c0 = tot & 0xFFFF, c1 = tot >> 16;
-        if (lane == 0 && a.blocks > UNIT_BLOCKS) {  // the group of eight units this one belongs to has work above it
-            const u32 cube = u32(w >> 3);
-            if (atomicExch(&a.cube_flag[cube], a.epoch) != a.epoch) a.cube_list[atomicAdd(&a.cnt[5], 1u)] = cube;
-        }
-        if (c0 >= a.dense_min) {
-            // a busy unit: thread-per-block lists would cost more than they save; one warp builds it the
-            // way apply_kernel does (lane = block, siblings in neighbouring lanes)
-            if (lane == n_busy) my_busy = u32(w);
-            if (++n_busy == 32) flush_busy();
-            if (lane == 0) {
-                a.unit_first[w] = UNIT_PREBUILT;
-                a.unit_cm[w] = 0xFF;
-            }
-            continue;
-        }
-        // level 2: node q = lanes 4q..4q+3 (eight level-1 parents)
-        u32 cm2 = (pa | (pb << 1)) << (2 * (lane & 3));
-        cm2 |= __shfl_xor_sync(FULL, cm2, 1);
-        cm2 |= __shfl_xor_sync(FULL, cm2, 2);
-        const u32 b2 = __ballot_sync(FULL, (lane & 3) == 0 && cm2 != 0);  // bits at lanes 0,4,..,28
-        const u32 c2 = __popc(b2);
-        u32 base = 0;
-        if (lane < 3) base = atomicAdd(&a.cnt[lane], lane == 0 ? c0 : lane == 1 ? c1 : c2);
-        const u32 base0 = __shfl_sync(FULL, base, 0), base1 = __shfl_sync(FULL, base, 1), base2 = __shfl_sync(FULL, base, 2);
-        // level 0 entries: global block index + set_mask
-        {
-            u32 bb = bits, k = base0 + r0;
-            const u32 blk0 = u32(w * UNIT_BLOCKS) + lane * 16;
-            while (bb) {
-                const int j = __ffs(bb) - 1;
-                bb &= bb - 1;
-                a.first[0][k] = blk0 + j;
-                a.cm[0][k] = u8((j < 8 ? sa >> (8 * j) : sb >> (8 * (j - 8))) & 0xFF);
-                ++k;
-            }
-        }
-        // level 1 entries: first child slot in level 0 + which of the eight blocks are candidates
-        if (pa) {
-            a.first[1][base1 + r1] = base0 + r0;
-            a.cm[1][base1 + r1] = u8(bits & 0xFF);
-        }
-        if (pb) {
-            a.first[1][base1 + r1 + pa] = base0 + r0 + __popc(bits & 0xFF);
-            a.cm[1][base1 + r1 + pa] = u8(bits >> 8);
-        }
-        // level 2 entries
-        if ((lane & 3) == 0 && cm2 != 0) {
-            const u32 k2 = base2 + __popc(b2 & ((1u << lane) - 1));
-            a.first[2][k2] = base1 + r1;
-            a.cm[2][k2] = u8(cm2);
-        }
-        // the unit node (dense): children = the unit's level-2 candidates
-        if (lane == 0) {
-            u32 cm3 = 0;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) cm3 |= ((b2 >> (4 * q)) & 1u) << q;
-            a.unit_first[w] = base2;
-            a.unit_cm[w] = u8(cm3);
-        }
+        plan_unit(a, lane, w, q0, q1, my_busy, n_busy);
     }
-    flush_busy();
+    plan_flush_busy(a, lane, my_busy, n_busy);
 }
 
 // Values of the eight children of a key (leaf value / branch LOD value; 0 for EMPTY), loaded with plain

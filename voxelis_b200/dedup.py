@@ -150,12 +150,12 @@ def world_for(device: int):
     return _WORLDS[device]
 
 
-def global_dedup_dist(local: VoxInterner, roots: np.ndarray, shard_budget: int, dtype: int, device: int, world=None):
+def global_dedup_dist(local: VoxInterner, roots: np.ndarray, shard_budget: int, dtype: int, device: int, world=None, shard=None):
     """One process per GPU: ONE C-ABI call, vx_world_global_dedup (pack kernel, NCCL send / recv of the records and of
     the ids, owner-side interning — voxelis_b200/csrc/vx_world.cuh).  torch.distributed is only used to hand the
     128-byte NCCL id to the other processes when no ``world`` is given.  Returns (shard, global_roots, summary)."""
     world = world or world_for(device)
-    shard = VoxInterner.with_memory_budget(shard_budget, dtype, device)
+    shard = shard or VoxInterner.with_memory_budget(shard_budget, dtype, device)   # a FRESH interner: this rank's global shard
     groots, summ = world.global_dedup(local, shard, roots)
     summary = {"G": world.n_ranks, "rounds": summ["rounds"], "bytes_sent": summ["bytes_sent"], "branches": summ["branches"],
                "leaves": summ["leaves"], "this_shard": (summ["this_shard_branches"], summ["this_shard_leaves"]),
@@ -164,12 +164,12 @@ def global_dedup_dist(local: VoxInterner, roots: np.ndarray, shard_budget: int, 
     return shard, groots, summary
 
 
-def global_dedup(local: VoxInterner, roots: np.ndarray, shard_budget: int, dtype: int, device: int):
+def global_dedup(local: VoxInterner, roots: np.ndarray, shard_budget: int, dtype: int, device: int, shard=None):
     """The merge for THIS process: the NCCL exchange when torch.distributed runs with more than one rank, else the
     single-rank form.  Returns (shard, global_roots, summary)."""
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        shard, groots, summ = global_dedup_dist(local, roots, shard_budget, dtype, device)
+        shard, groots, summ = global_dedup_dist(local, roots, shard_budget, dtype, device, shard=shard)
         return shard, groots, summ
     shards, groots_l, summ = global_dedup_local([local], [roots], shard_budget, dtype, device)
     summ.setdefault("exchange", "single rank (no exchange)")
