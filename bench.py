@@ -794,10 +794,12 @@ def main():
                                 "device_memory": stats_mem},
             "value_nonempty": total_nonempty / (step_ms_max * 1e-3),
             "e2e": {"value": e2e_value, "unit": "chunks/s", "ms_per_step": e2e_ms_max,
-                    # per step: descriptors (8 B per chunk + 4 B per touched unit) by the copy engine; touched
-                    # units' masks (1 KiB each) and the values of blocks with a set bit (8 B each, lower bound:
-                    # the bus moves 32-byte sectors) by loads the staging kernel issues on pinned host memory
-                    "h2d_bytes_per_step": int(n * 8 + touched_units * 4 + touched_units * 1024 + touched_blocks * 8),
+                    # per step: descriptors (8 B per chunk + 4 B per touched unit) by the copy engine; the touched units'
+                    # occupancy bits and the values of blocks with a set bit by loads the staging kernel issues on
+                    # pinned host memory (batches written through the API never send their masks, vx_stage.cuh)
+                    "h2d_bytes_per_step": int(n * 8 + touched_units * 4 + touched_units * 64 + touched_blocks * 8),
+                    "h2d_bytes_note": "descriptors + 64 B of per-block occupancy per touched unit + 8 B per flagged block; the bus "
+                                      "moves 32-byte sectors, so the traffic ncu sees (pcie__read_bytes) is 2-3x this lower bound",
                     "host_input_bytes_per_step": int(masks.nbytes + values.nbytes),
                     "d2h_bytes_per_step": int(n * 9),
                     "touched_units": int(touched_units),

@@ -3,6 +3,8 @@
 import numpy as np
 import pytest
 
+import parity
+
 from voxelis_b200 import workloads as wl
 
 pytestmark = pytest.mark.gpu
@@ -267,3 +269,37 @@ def test_set_root_id_rejects_stale_ids(gpu_api):
     t1.clear(it)
     assert vx.lib().vx_tree_set_root_id(it.h, t2.h, root) == -1                       # released
     assert t2.is_empty() and it.stats()["alive_nodes"] == 1
+
+
+@pytest.mark.parametrize("dtype", [wl.U8, wl.I32], ids=["u8", "i32"])
+def test_reset_of_used_state_only_is_a_full_reset(gpu_api, oracle_api, dtype):
+    """vx_interner_reset clears only what the nodes in [1, next_index) put into the tables when nothing was ever released
+    (reset_used_kernel); every build after such a reset must come out as in a brand-new interner — same DAG, same
+    counters, no stale table entry answering a lookup — also after a release (full clear again) and after an overflow."""
+    vx, o = gpu_api, oracle_api
+    g = vx.VoxInterner.with_memory_budget(64 << 20, dtype)
+    worlds = [wl.terrain_world((4, 2, 4), 5, "surface_and_below", dtype, materials=3),
+              wl.batch_from_function(5, wl.p_random(200, cell=2), dtype, 6),
+              wl.named_workload("sum", 3, 5, dtype),
+              wl.batch_from_function(5, wl.p_random(4), dtype, 5)]
+    for rnd in range(2):
+        for m, v in worlds:
+            g.reset()
+            roots, changed = g.apply_batches_slab(5, m, v)
+            c = o.VoxInterner(64 << 20, dtype)
+            cr, cc = c.apply_batches_fresh(5, m, v)
+            parity.assert_parity(vx, o, 5, g, roots, changed, c, cr, cc)
+        # a release in between: the next reset has generations and tombstones to clear
+        t = vx.VoxTree(5, dtype)
+        b = t.create_batch()
+        b.assign(*[a[0] for a in worlds[2]])
+        t.apply_batch(g, b)
+        t.clear(g)
+    # an interner that overflowed is cleared completely as well
+    small = vx.VoxInterner.with_memory_budget(82 * 48, dtype)
+    with pytest.raises(vx.VoxelisError):
+        small.apply_batches_slab(5, *worlds[1])
+    small.reset()
+    m, v = wl.batch_from_function(5, wl.p_uniform(3), dtype, 1)
+    r, ch = small.apply_batches_slab(5, m, v)
+    assert ch[0] == 1 and vx.id_is_leaf(r[0]) and small.stats()["alive_nodes"] == 2

@@ -302,6 +302,11 @@ template <class T>
 __device__ __forceinline__ void leaf_payload(const InternerDev& in, u32 idx, u32 v) {
     ((T*)in.values)[idx] = T(v);
     in.hashes[idx] = leaf_hash(v);
+    // "no children" is how every later pass tells a leaf from a branch (release, rehash, heights, VTM, reset): the row
+    // may still hold the ids of a branch that lived at this index before the last vx_interner_reset
+    ulonglong2* row = reinterpret_cast<ulonglong2*>(in.children + size_t(idx) * 8);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) row[k] = make_ulonglong2(0, 0);
 }
 
 __device__ inline u64 leaf_get(Ctx<u8>& c, u32 v, bool need) {

@@ -116,6 +116,8 @@ struct vx_interner {
     // diagnostic: phases of the last vx_apply_batches call (host microseconds / device milliseconds)
     std::vector<cudaEvent_t> tevs;
     double trace[8]{};
+    bool ever_initialised = false;  // the full clear has run at least once
+    bool ever_released = false;     // some node was released since the last full clear (generations / tombstones exist)
     uint64_t free_host = 0;      // entries in the free list
     uint64_t tombs_host = 0;     // deleted table slots since the last rehash
     std::mutex mu;
@@ -560,6 +562,23 @@ __global__ void init_scalars_kernel(u32* words, u32 n) {
 }
 
 int init_state(vx_interner* it, cudaStream_t s, bool sync) {
+    // Nothing has ever been released and no error is known: undo only what the nodes in [1, next_index) did to the
+    // tables (reset_used_kernel, vx_release.cuh) instead of clearing tables sized for the whole budget.
+    static const bool sparse_ok = !(getenv("VX_RESET_FULL") && atoi(getenv("VX_RESET_FULL")) != 0);
+    if (sparse_ok && it->ever_initialised && !it->poisoned && it->free_host == 0 && it->tombs_host == 0 && !it->ever_released) {
+        const unsigned grid = unsigned(it->sm_count) * 8;
+        if (it->dtype == VX_U8)
+            reset_used_kernel<u8><<<grid, 256, 0, s>>>(it->dev, it->nbuckets, it->leaf_slots);
+        else
+            reset_used_kernel<int32_t><<<grid, 256, 0, s>>>(it->dev, it->nbuckets, it->leaf_slots);
+        CU_TRY(cudaGetLastError());
+        init_scalars_kernel<<<1, 32, 0, s>>>((u32*)it->d_scalars, u32(sizeof(Scalars) / 4));
+        CU_TRY(cudaGetLastError());
+        if (sync) CU_TRY(cudaStreamSynchronize(s));
+        return VX_OK;
+    }
+    it->ever_initialised = true;
+    it->ever_released = false;
     CU_TRY(cudaMemsetAsync(it->dev.slots, 0, it->nbuckets * 64, s));
     CU_TRY(cudaMemsetAsync(it->dev.refs, 0, it->capacity * 4, s));
     CU_TRY(cudaMemsetAsync(it->dev.gens, 0, it->capacity * 2, s));
@@ -593,6 +612,7 @@ int refresh_free_count(vx_interner* it) {
 // dec_ref_recursive (interner/mod.rs:419-534) for `n` root handles at once; synchronous.
 int release_roots(vx_interner* it, const u64* h_roots, size_t n) {
     if (n == 0) return VX_OK;
+    it->ever_released = true;  // generations and tombstones may exist from here on: the next reset clears everything
     cudaStream_t s = it->stream;
     auto ensure = [&](int b, size_t entries) -> int {
         if (entries <= it->rel_cap[b]) return VX_OK;

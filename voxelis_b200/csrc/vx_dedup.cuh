@@ -143,6 +143,7 @@ __global__ void intern_records_kernel(InternerDev in, u32 n, const u64* records,
                             } else {
                                 ((u8*)in.values)[idx] = u8(v);
                                 in.hashes[idx] = leaf_hash(v);
+                                for (int q = 0; q < 8; ++q) in.children[size_t(idx) * 8 + q] = 0;  // a leaf has no children row
                                 result = id_leaf(u64(idx));
                                 fence_release_gpu();
                                 st_strong(keyp, result);
@@ -166,6 +167,7 @@ __global__ void intern_records_kernel(InternerDev in, u32 n, const u64* records,
                             } else {
                                 ((u32*)in.values)[idx] = v;
                                 in.hashes[idx] = leaf_hash(v);
+                                for (int q = 0; q < 8; ++q) in.children[size_t(idx) * 8 + q] = 0;  // a leaf has no children row
                                 result = id_leaf(u64(idx));
                                 fence_release_gpu();
                                 st_strong(&in.leaf_ids[s], result);

@@ -142,4 +142,78 @@ __global__ void rehash_kernel(InternerDev in, u32 next_index) {
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// vx_interner_reset without touching what was never used.  A fresh-build loop (build a world, reset, build the next)
+// fills a small part of a table sized for the budget; clearing the whole table and the refcount pool costs 87 MB of
+// stores per reset of a 256 MiB interner, 33 us next to a 0.26 ms build.  When no node has ever been released (no
+// tombstones, no free list, generations all 0 — the host knows) the state to undo is exactly: the table slot of every
+// branch in [1, next_index), the leaf-table entry of every leaf, and the refcounts.  One thread per node finds its own
+// slot by its stored hash (it must exist, so the scan does not stop at empties other threads have just made).
+// Falls back to clearing everything, in this same launch, when the interner is more than a few per cent full or its
+// error word is set (an aborted insert may have left a claimed key behind).
+// ------------------------------------------------------------------------------------------------
+template <class T>
+__global__ void __launch_bounds__(256) reset_used_kernel(InternerDev in, size_t nbuckets, size_t leaf_slots) {
+    const size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x, nt = size_t(gridDim.x) * blockDim.x;
+    const u32 next = min(*in.next_index, in.capacity);
+    const bool everything = *in.error != ERR_NONE || size_t(next) * 170 > nbuckets * 64 + size_t(in.capacity) * 6;
+    if (sizeof(T) == 1)
+        for (size_t i = t; i < 256; i += nt) in.leaf_u8[i] = 0;
+    if (everything) {
+        ulonglong2* sl = reinterpret_cast<ulonglong2*>(in.slots);
+        for (size_t i = t; i < nbuckets * 4; i += nt) sl[i] = make_ulonglong2(0, 0);
+        for (size_t i = t; i < in.capacity; i += nt) {
+            in.refs[i] = 0;
+            in.gens[i] = 0;
+        }
+        if (sizeof(T) != 1)
+            for (size_t i = t; i < leaf_slots; i += nt) {
+                in.leaf_keys[i] = 0;
+                in.leaf_ids[i] = 0;
+            }
+        return;
+    }
+    for (size_t idx = t + 1; idx < next; idx += nt) {
+        const u64 h = in.hashes[idx];
+        in.refs[idx] = 0;
+        if (h == 0) continue;
+        bool branch = false;
+        const ulonglong2* row = reinterpret_cast<const ulonglong2*>(in.children + idx * 8);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const ulonglong2 q = row[k];
+            branch = branch || (q.x | q.y) != 0;
+        }
+        if (branch) {
+            u32 bucket = u32(h) & in.bucket_mask;
+            for (u32 guard = 0; guard <= in.bucket_mask; ++guard) {
+                bool found = false;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const u64 slot = ld_strong(&in.slots[size_t(bucket) * 8 + k]);
+                    if (slot != 0 && u32(slot) == u32(idx)) {
+                        st_strong(&in.slots[size_t(bucket) * 8 + k], 0);
+                        found = true;
+                    }
+                }
+                if (found) break;
+                bucket = (bucket + 1) & in.bucket_mask;
+            }
+        } else if (sizeof(T) != 1) {
+            const u32 v = ((const u32*)in.values)[idx];
+            const u64 key = u64(v) | (1ull << 32);
+            u32 s = u32(leaf_hash(v)) & in.leaf_mask;
+            for (u32 guard = 0; guard <= in.leaf_mask; ++guard) {
+                if (ld_strong(&in.leaf_keys[s]) == key) {
+                    st_strong(&in.leaf_ids[s], 0);
+                    st_strong(&in.leaf_keys[s], 0);
+                    break;
+                }
+                s = (s + 1) & in.leaf_mask;
+            }
+        }
+    }
+}
+
 }  // namespace vx
