@@ -280,6 +280,11 @@ __device__ __forceinline__ void ref_add(Ctx<T>& c, u32 idx) {
     atomicAdd(&c.in.refs[idx], 1u);
 }
 
+// one index allocation for n new nodes (aggregated per warp step).  Measured and dropped: 64 striped cursors instead of
+// this single counter — 2.68 ms against 2.69 on the all-miss input: the wait on this atomic is its round trip, not
+// same-address throughput (profiles/README.md).
+__device__ __forceinline__ u32 alloc_n(const InternerDev& in, u32 n) { return atomicAdd(in.next_index, n); }
+
 // get_next_index_macro! (interner/macros.rs:1-41) for one node: recycled index first (LIFO), else
 // next_index++.  `*gen` = generation to stamp into the BlockId.  Indices >= capacity mean "Out of memory".
 __device__ __forceinline__ u32 alloc_one(const InternerDev& in, bool use_free, u32* gen) {
@@ -509,7 +514,7 @@ u64 intern_branch(Ctx<T>& c, bool need, u64 child, bool block_level, u32 cval) {
             u32 idx, gen = 0;
             if (!c.use_free) {  // one aggregated atomic for all nodes the warp creates this round
                 u32 base = 0;
-                if (lane == 0) base = atomicAdd(in.next_index, u32(__popc(cb)));
+                if (lane == 0) base = alloc_n(in, u32(__popc(cb)));
                 base = __shfl_sync(FULL, base, 0);
                 idx = base + __popc(cb & ((1u << gs) - 1));
             } else {
@@ -739,7 +744,7 @@ __device__ inline u64 intern_block(Ctx<T>& c, bool need, const typename VT<T>::K
             u32 idx = 0, gen = 0;
             if (!c.use_free) {
                 u32 base = 0;
-                if (c.lane == 0) base = atomicAdd(in.next_index, u32(__popc(cb)));
+                if (c.lane == 0) base = alloc_n(in, u32(__popc(cb)));
                 base = __shfl_sync(FULL, base, 0);
                 idx = base + __popc(cb & ((1u << c.lane) - 1));
             } else if (claimed) {

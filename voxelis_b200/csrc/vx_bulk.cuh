@@ -381,7 +381,7 @@ __device__ inline u64 intern_node(Ctx<T>& c, bool need, const u64 (&ch)[8], u32 
             u32 idx = 0, gen = 0;
             if (!c.use_free) {
                 u32 base = 0;
-                if (c.lane == 0) base = atomicAdd(in.next_index, u32(__popc(cb)));
+                if (c.lane == 0) base = alloc_n(in, u32(__popc(cb)));
                 base = __shfl_sync(FULL, base, 0);
                 idx = base + __popc(cb & ((1u << c.lane) - 1));
             } else if (claimed) {
