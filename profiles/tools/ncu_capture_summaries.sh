@@ -7,6 +7,14 @@ for w in "$@"; do
   { python profiles/tools/ncu_summary.py /tmp/${tag}_$name.ncu-rep
     echo; echo "== stall samples per source line: bulk_blocks_kernel<u8> (+ busy units)"
     NCU_ARGS="-k regex:bulk_blocks" python profiles/tools/ncu_lines.py /tmp/${tag}_$name.ncu-rep voxelis_b200/libvoxelis_b200.so bulk_blocks_kernelIh 28
+    if [ "$name" = perlin ]; then
+      echo; echo "== stall samples per source line: bulk_level_kernel<u8>, level 1"
+      NCU_ARGS="-k regex:bulk_level" NCU_CHUNK=0 python profiles/tools/ncu_lines.py /tmp/${tag}_$name.ncu-rep voxelis_b200/libvoxelis_b200.so bulk_level_kernelIh 24
+      echo; echo "== stall samples per source line: bulk_upper_kernel<u8> (units .. roots)"
+      NCU_ARGS="-k regex:bulk_upper" python profiles/tools/ncu_lines.py /tmp/${tag}_$name.ncu-rep voxelis_b200/libvoxelis_b200.so bulk_upper_kernelIh 24
+      echo; echo "== stall samples per source line: bulk_plan_kernel"
+      NCU_ARGS="-k regex:bulk_plan" python profiles/tools/ncu_lines.py /tmp/${tag}_$name.ncu-rep voxelis_b200/libvoxelis_b200.so bulk_plan_kernel 16
+    fi
   } > gpurun_out/${tag}_ncu_${name}_summary.txt 2>&1
 done
 ls -la gpurun_out/

@@ -31,6 +31,8 @@
 #pragma once
 #include "vx_device.cuh"
 
+#include <cstddef>
+
 namespace vx {
 
 constexpr int WARPS_PER_CTA = 8;
@@ -1138,10 +1140,18 @@ __device__ __forceinline__ void ctx_init(Ctx<T>& c, const InternerDev& in, WarpS
     c.cs = cs;
 }
 
+// block_level = false: the kernel never looks a block up by its value word (level / upper kernels of the bulk builder),
+// so the per-warp block cache — 60 % of the shared memory — is left as it is.
 template <class T>
-__device__ inline void smem_init(WarpSmem<T>* ws, CtaSmem* cs) {
-    u32* w = (u32*)ws;
-    for (u32 i = threadIdx.x; i < sizeof(WarpSmem<T>) * WARPS_PER_CTA / 4; i += blockDim.x) w[i] = 0;
+__device__ inline void smem_init(WarpSmem<T>* ws, CtaSmem* cs, bool block_level = true) {
+    if (block_level) {
+        u32* w = (u32*)ws;
+        for (u32 i = threadIdx.x; i < sizeof(WarpSmem<T>) * WARPS_PER_CTA / 4; i += blockDim.x) w[i] = 0;
+    } else {
+        constexpr u32 words = u32((sizeof(WarpSmem<T>) - offsetof(WarpSmem<T>, ukey)) / 4);
+        for (u32 i = threadIdx.x; i < words * WARPS_PER_CTA; i += blockDim.x)
+            ((u32*)((unsigned char*)(ws + i / words) + offsetof(WarpSmem<T>, ukey)))[i % words] = 0;
+    }
     u32* q = (u32*)cs;
     for (u32 i = threadIdx.x; i < sizeof(CtaSmem) / 4; i += blockDim.x) q[i] = 0;
     __syncthreads();

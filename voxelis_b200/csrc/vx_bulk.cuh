@@ -469,10 +469,10 @@ __device__ inline u64 parent_tpk(Ctx<T>& c, bool active, const u64 (&ch)[8]) {
 // this prologue, which touches only shared memory and the argument block) while the previous launch is
 // draining; griddepcontrol.wait then blocks until that launch has completed and its writes are visible.
 template <class T>
-__device__ __forceinline__ void bulk_prologue(Ctx<T>& c, const BulkArgs& a, unsigned char* smem_raw) {
+__device__ __forceinline__ void bulk_prologue(Ctx<T>& c, const BulkArgs& a, unsigned char* smem_raw, bool block_level = true) {
     WarpSmem<T>* ws = reinterpret_cast<WarpSmem<T>*>(smem_raw);
     CtaSmem* csp = reinterpret_cast<CtaSmem*>(smem_raw + sizeof(WarpSmem<T>) * WARPS_PER_CTA);
-    smem_init<T>(ws, csp);
+    smem_init<T>(ws, csp, block_level);
     ctx_init<T>(c, a.in, ws, csp, a.use_free != 0);
     asm volatile("griddepcontrol.wait;" ::: "memory");
     // This CTA may share its SM with the tail of the previous launch, whose reads can have left lines in L1
@@ -527,9 +527,10 @@ __global__ void __launch_bounds__(CTA_THREADS, VX_BULK_MIN_CTAS) bulk_blocks_ker
         set2 = ld_stream_u8(a.cm[0] + base0 + stride + c.lane);
     }
     for (u32 base = base0; base < end; base += stride) {
-        // poisoned interner: stop (the host reports it).  The word is requested here and tested at the end
-        // of the iteration, so its round trip hides behind the work
-        const u32 errw = c.lane == 0 ? ld_strong(a.in.error) : u32(ERR_NONE);
+        // poisoned interner: stop (the host reports it).  The word is requested here and tested at the end of the
+        // iteration, so its round trip hides behind the work — every eighth iteration only: every warp of the grid
+        // polling ONE address each iteration made that load the slowest of the iteration (15.7 % of the stall samples)
+        const u32 errw = (c.lane == 0 && (((base - base0) / stride) & 7) == 7) ? ld_strong(a.in.error) : u32(ERR_NONE);
         const u32 k = base + c.lane;
         const bool active = k < end;
         const u32 set = set1;
@@ -793,7 +794,7 @@ template <class T>
 __global__ void __launch_bounds__(CTA_THREADS, VX_BULK_MIN_CTAS) bulk_level_kernel(BulkArgs a, int level) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Ctx<T> c;
-    bulk_prologue<T>(c, a, smem_raw);
+    bulk_prologue<T>(c, a, smem_raw, false);
     const u32 cnt = a.cnt[level];
     const u32 span = bulk_span(cnt);
     if (bulk_cta_idle(&a.cnt[level], WARPS_PER_CTA * span)) return;
@@ -805,7 +806,7 @@ __global__ void __launch_bounds__(CTA_THREADS, VX_BULK_MIN_CTAS) bulk_level_kern
     const u32 base0 = u32(min(wfirst, u64(cnt)));
     const u32 end = u32(min(wfirst + span, u64(cnt)));
     for (u32 base = base0; base < end; base += 32) {
-        const u32 errw = c.lane == 0 ? ld_strong(a.in.error) : u32(ERR_NONE);
+        const u32 errw = (c.lane == 0 && (((base - base0) >> 5) & 7) == 7) ? ld_strong(a.in.error) : u32(ERR_NONE);  // see bulk_blocks_kernel
         const u32 k = base + c.lane;
         const bool active = k < end;
         const u32 f = active ? ld_stream_u32(first + k) : 0;
@@ -846,7 +847,7 @@ bulk_upper_kernel(BulkArgs a, unsigned long long nodes, const u64* below, u64* o
                   int top_is_root) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Ctx<T> c;
-    bulk_prologue<T>(c, a, smem_raw);
+    bulk_prologue<T>(c, a, smem_raw, false);
     const unsigned long long stride = size_t(gridDim.x) * CTA_THREADS;
     const bool poisoned0 = ld_strong(a.in.error) != ERR_NONE;
     // from_units with two levels: only the groups of eight units that hold something are visited (list
@@ -912,7 +913,7 @@ bulk_upper_kernel(BulkArgs a, unsigned long long nodes, const u64* below, u64* o
     }
     // the call's last launch wipes the unit memo once enough entries have gone in (the plan kernel of the
     // next call resets the count; nothing touches either in between)
-    if (top_is_root && a.memo_on && ld_strong(a.memo_count) >= MEMO_CLEAR_AT) {
+    if (top_is_root && a.memo_on && __shfl_sync(FULL, c.lane == 0 ? ld_strong(a.memo_count) : 0u, 0) >= MEMO_CLEAR_AT) {
         ulonglong2* m = reinterpret_cast<ulonglong2*>(a.memo);
         for (size_t e = size_t(blockIdx.x) * CTA_THREADS + threadIdx.x; e < MEMO_SLOTS; e += stride) m[e] = make_ulonglong2(0, 0);
     }
