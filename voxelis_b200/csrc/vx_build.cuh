@@ -257,6 +257,7 @@ struct Ctx {
     int lane, li, gs;  // lane, lane within 8-group, first lane of my group
     bool use_free;     // the free list holds recycled indices: pop them before next_index (macros.rs:1-41)
     bool tpk_only;     // block level: always thread-per-key (bulk builder); the fused kernel uses the hybrid
+    bool weak_first;   // first look at a bucket / row through L1 (hot keys are read by every warp of the grid; vx_device.cuh)
     Tally t;
 };
 
@@ -477,9 +478,10 @@ u64 intern_branch(Ctx<T>& c, bool need, u64 child, bool block_level, u32 cval) {
     const bool went_global = !done;
     u32 skip = 0;
     int guard = 0;
+    bool first = c.weak_first;
     while (__any_sync(FULL, !done)) {
         u64 slot = 0;
-        if (!done) slot = ld_strong(&in.slots[size_t(bucket) * 8 + li]);
+        if (!done) slot = first ? ld_weak(&in.slots[size_t(bucket) * 8 + li]) : ld_strong(&in.slots[size_t(bucket) * 8 + li]);
         const u32 lo = u32(slot);
         bool fpm = !done && slot != 0 && lo != IDX_TOMB && u32(slot >> 47) == fp && !((skip >> li) & 1);
         u32 mb = (__ballot_sync(FULL, fpm) >> gs) & 0xFF;
@@ -492,15 +494,15 @@ u64 intern_branch(Ctx<T>& c, bool need, u64 child, bool block_level, u32 cval) {
         const bool cand_pending = u32(cslot) == IDX_PENDING;
         const bool do_cmp = !done && has_cand && !cand_pending;
         u64 stored = 0;
-        if (do_cmp) stored = ld_strong(&in.children[size_t(u32(cslot)) * 8 + li]);
+        if (do_cmp) stored = first ? ld_weak(&in.children[size_t(u32(cslot)) * 8 + li]) : ld_strong(&in.children[size_t(u32(cslot)) * 8 + li]);
         u32 eqb = (__ballot_sync(FULL, do_cmp && stored == child) >> gs) & 0xFF;
         if (do_cmp) {
             if (eqb == 0xFF) {
                 result = id_branch(cslot, leafb, presb);  // hit
                 done = true;
-            } else {
+            } else if (!first) {
                 skip |= 1u << k;
-            }
+            }  // a mismatch seen through L1 proves nothing (the row may be stale): the next round looks again at L2
         }
         // -- no candidate: claim the first empty slot of the bucket, or move on
         const bool want_claim = !done && !has_cand && eb != 0;
@@ -568,7 +570,7 @@ u64 intern_branch(Ctx<T>& c, bool need, u64 child, bool block_level, u32 cval) {
                 done = true;
             }
         }
-        if (!done && !has_cand && eb == 0) {  // bucket full and no match: next bucket
+        if (!done && !has_cand && eb == 0 && !first) {  // bucket full and no match: next bucket
             bucket = (bucket + 1) & in.bucket_mask;
             skip = 0;
             if (++guard > (1 << 22)) {
@@ -576,6 +578,7 @@ u64 intern_branch(Ctx<T>& c, bool need, u64 child, bool block_level, u32 cval) {
                 done = true;
             }
         }
+        first = false;
     }
     if (!block_level) {
         // refresh the parent cache; among groups mapping to the same entry only the lowest writes,
@@ -619,6 +622,28 @@ __device__ __noinline__ u32 mode8(u32 v0, u32 v1, u32 v2, u32 v3, u32 v4, u32 v5
         }
     }
     return best;
+}
+
+// calc_average with at most ONE distinct non-default value among the eight (most terrain nodes): that value wins when
+// it holds at least as many children as the default does — a tie goes to the non-default value (core/voxel.rs:128-136).
+// Returns false when two different non-default values are present (-> mode8).
+__device__ __forceinline__ bool mode8_two_valued(u32 v0, u32 v1, u32 v2, u32 v3, u32 v4, u32 v5, u32 v6, u32 v7, u32* out) {
+    const u32 x = v0 ? v0 : v1 ? v1 : v2 ? v2 : v3 ? v3 : v4 ? v4 : v5 ? v5 : v6 ? v6 : v7;  // first non-default value
+    const u32 v[8] = {v0, v1, v2, v3, v4, v5, v6, v7};
+    u32 cnt = 0;
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        cnt += v[i] == x;
+        ok = ok && (v[i] == x || v[i] == 0);
+    }
+    *out = (x != 0 && cnt >= 4) ? x : 0;   // x == 0: all default
+    return ok;
+}
+__device__ __forceinline__ u32 lod_value(u32 v0, u32 v1, u32 v2, u32 v3, u32 v4, u32 v5, u32 v6, u32 v7) {
+    u32 r;
+    if (mode8_two_valued(v0, v1, v2, v3, v4, v5, v6, v7, &r)) return r;
+    return mode8(v0, v1, v2, v3, v4, v5, v6, v7);
 }
 
 // Ids of the eight voxel children (Leaf(value) / EMPTY) of a block key.  u8: re-derived on demand from
@@ -683,6 +708,7 @@ __device__ inline u64 intern_block(Ctx<T>& c, bool need, const typename VT<T>::K
     bool done = !need;
     u32 skip = 0;
     int guard = 0;
+    bool first = c.weak_first;
     while (__any_sync(FULL, !done)) {
         bool claimed = false;
         int ek = 0;
@@ -691,8 +717,13 @@ __device__ inline u64 intern_block(Ctx<T>& c, bool need, const typename VT<T>::K
             c.t.probes++;
             // the whole 64-byte bucket first (four independent 16-byte loads in flight), then the scan
             u64 sl[8];
+            if (first) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) ld_strong_v2(bp + 2 * j, &sl[2 * j], &sl[2 * j + 1]);
+                for (int j = 0; j < 4; ++j) ld_weak_v2(bp + 2 * j, &sl[2 * j], &sl[2 * j + 1]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) ld_strong_v2(bp + 2 * j, &sl[2 * j], &sl[2 * j + 1]);
+            }
             u32 mb = 0, eb = 0, pb = 0;
             u64 cand = 0;
 #pragma unroll
@@ -713,24 +744,29 @@ __device__ inline u64 intern_block(Ctx<T>& c, bool need, const typename VT<T>::K
             if (mb) {  // compare the stored children row with the key (row loaded in one go as well)
                 const u64* rp = &in.children[size_t(u32(cand)) * 8];
                 u64 r[8];
+                if (first) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) ld_strong_v2(rp + 2 * j, &r[2 * j], &r[2 * j + 1]);
+                    for (int j = 0; j < 4; ++j) ld_weak_v2(rp + 2 * j, &r[2 * j], &r[2 * j + 1]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) ld_strong_v2(rp + 2 * j, &r[2 * j], &r[2 * j + 1]);
+                }
                 bool eq = true;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) eq = eq && r[i] == ch.get(i);
                 if (eq) {
                     result = id_branch(cand, nzm, nzm);
                     done = true;
-                } else {
+                } else if (!first) {
                     skip |= 1u << (__ffs(mb) - 1);
-                }
+                }  // a mismatch seen through L1 proves nothing: the next round looks again at L2
             } else if (pb) {
                 // a slot with my fingerprint is being published (possibly my key): look again
             } else if (eb) {
                 ek = __ffs(eb) - 1;
                 u64 old = atomicCAS((ull*)&in.slots[size_t(bucket) * 8 + ek], 0ull, (ull)((u64(fp) << 47) | IDX_PENDING));
                 claimed = old == 0;
-            } else {
+            } else if (!first) {
                 bucket = (bucket + 1) & in.bucket_mask;
                 skip = 0;
                 if (++guard > (1 << 22)) {
@@ -772,7 +808,7 @@ __device__ inline u64 intern_block(Ctx<T>& c, bool need, const typename VT<T>::K
                                 atomicAdd(&in.refs[id_index(ch.get(i))], 1u);
                         }
                     }
-                    ((T*)in.values)[idx] = T(mode8(V::get(eff, 0), V::get(eff, 1), V::get(eff, 2), V::get(eff, 3),
+                    ((T*)in.values)[idx] = T(lod_value(V::get(eff, 0), V::get(eff, 1), V::get(eff, 2), V::get(eff, 3),
                                                    V::get(eff, 4), V::get(eff, 5), V::get(eff, 6), V::get(eff, 7)));
                     in.hashes[idx] = h;
                     c.t.branch_miss++;
@@ -784,6 +820,7 @@ __device__ inline u64 intern_block(Ctx<T>& c, bool need, const typename VT<T>::K
                 done = true;
             }
         }
+        first = false;
     }
     return result;
 }
@@ -1133,6 +1170,7 @@ __device__ __forceinline__ void ctx_init(Ctx<T>& c, const InternerDev& in, WarpS
     c.in = in;
     c.use_free = use_free;
     c.tpk_only = false;
+    c.weak_first = false;
     c.lane = threadIdx.x & 31;
     c.li = c.lane & 7;
     c.gs = c.lane & 24;

@@ -58,6 +58,7 @@ struct BulkArgs {
     u32* memo_count;  // entries inserted since the table was last cleared (persists across calls)
     u32* unit_delta;  // [U][3] leaf_calls / branch_calls / collapsed of a unit built by bulk_dense_units_kernel
     u32 memo_on;
+    u32 weak_first;   // first look at a bucket / stored row through L1 (vx_device.cuh: ld_weak)
     u32 merge_dense;  // busy units are built by the warps of bulk_blocks_kernel once their share of the block list is done
 };
 #ifndef VX_BULK_MIN_CTAS
@@ -320,6 +321,7 @@ __device__ inline u64 intern_node(Ctx<T>& c, bool need, const u64 (&ch)[8], u32 
     cv.template load<STRONG>(in, ch, went_global);
     u32 skip = 0;
     int guard = 0;
+    bool first = c.weak_first;
     while (__any_sync(FULL, !done)) {
         bool claimed = false;
         int ek = 0;
@@ -327,8 +329,13 @@ __device__ inline u64 intern_node(Ctx<T>& c, bool need, const u64 (&ch)[8], u32 
             const u64* bp = &in.slots[size_t(bucket) * 8];
             c.t.probes++;
             u64 sl[8];
+            if (first) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) ld_strong_v2(bp + 2 * j, &sl[2 * j], &sl[2 * j + 1]);
+                for (int j = 0; j < 4; ++j) ld_weak_v2(bp + 2 * j, &sl[2 * j], &sl[2 * j + 1]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) ld_strong_v2(bp + 2 * j, &sl[2 * j], &sl[2 * j + 1]);
+            }
             u32 mb = 0, eb = 0, pb = 0;
             u64 cand = 0;
 #pragma unroll
@@ -349,24 +356,29 @@ __device__ inline u64 intern_node(Ctx<T>& c, bool need, const u64 (&ch)[8], u32 
             if (mb) {
                 const u64* rp = &in.children[size_t(u32(cand)) * 8];
                 u64 r[8];
+                if (first) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) ld_strong_v2(rp + 2 * j, &r[2 * j], &r[2 * j + 1]);
+                    for (int j = 0; j < 4; ++j) ld_weak_v2(rp + 2 * j, &r[2 * j], &r[2 * j + 1]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) ld_strong_v2(rp + 2 * j, &r[2 * j], &r[2 * j + 1]);
+                }
                 bool eq = true;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) eq = eq && r[i] == ch[i];
                 if (eq) {
                     result = id_branch(cand, types, mask);
                     done = true;
-                } else {
+                } else if (!first) {
                     skip |= 1u << (__ffs(mb) - 1);
-                }
+                }  // a mismatch seen through L1 proves nothing: the next round looks again at L2
             } else if (pb) {
                 // a slot with my fingerprint is being published (possibly my key): look again
             } else if (eb) {
                 ek = __ffs(eb) - 1;
                 u64 old = atomicCAS((ull*)&in.slots[size_t(bucket) * 8 + ek], 0ull, (ull)((u64(fp) << 47) | IDX_PENDING));
                 claimed = old == 0;
-            } else {
+            } else if (!first) {
                 bucket = (bucket + 1) & in.bucket_mask;
                 skip = 0;
                 if (++guard > (1 << 22)) {
@@ -412,7 +424,7 @@ __device__ inline u64 intern_node(Ctx<T>& c, bool need, const u64 (&ch)[8], u32 
                             }
                         }
                     }
-                    ((T*)in.values)[idx] = T(mode8(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]));
+                    ((T*)in.values)[idx] = T(lod_value(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]));
                     in.hashes[idx] = h;
                     c.t.branch_miss++;
                 }
@@ -423,6 +435,7 @@ __device__ inline u64 intern_node(Ctx<T>& c, bool need, const u64 (&ch)[8], u32 
                 done = true;
             }
         }
+        first = false;
     }
     // refresh the parent cache: one writer per entry, so an entry is never a mix of two keys
     const bool wr = went_global && result != 0;
@@ -474,6 +487,7 @@ __device__ __forceinline__ void bulk_prologue(Ctx<T>& c, const BulkArgs& a, unsi
     CtaSmem* csp = reinterpret_cast<CtaSmem*>(smem_raw + sizeof(WarpSmem<T>) * WARPS_PER_CTA);
     smem_init<T>(ws, csp, block_level);
     ctx_init<T>(c, a.in, ws, csp, a.use_free != 0);
+    c.weak_first = a.weak_first != 0;
     asm volatile("griddepcontrol.wait;" ::: "memory");
     // This CTA may share its SM with the tail of the previous launch, whose reads can have left lines in L1
     // from before other SMs wrote into them (a line of `values` around a node created later, say).  The

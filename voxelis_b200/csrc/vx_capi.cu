@@ -421,6 +421,8 @@ int launch_bulk_t(vx_interner* it, int depth, size_t n, const u8* d_masks, const
     a.memo_count = (u32*)(it->bulk_memo + size_t(MEMO_SLOTS) * 2);
     const char* memo_env = getenv("VX_UNIT_MEMO");  // 0 switches the unit memo off (tests, A/B runs)
     a.memo_on = (memo_env && atoi(memo_env) == 0) ? 0u : 1u;
+    const char* weak_env = getenv("VX_WEAK_FIRST");  // 0: every look at the table goes to L2 (A/B runs)
+    a.weak_first = (weak_env && atoi(weak_env) == 0) ? 0u : 1u;
     const char* merge_env = getenv("VX_BULK_MERGE_DENSE");  // 0: busy units get a launch of their own (A/B runs)
     a.merge_dense = (merge_env && atoi(merge_env) == 0) ? 0u : 1u;
     a.unit_list = d_unit_list;
@@ -577,6 +579,7 @@ int init_state(vx_interner* it, cudaStream_t s, bool sync) {
         if (sync) CU_TRY(cudaStreamSynchronize(s));
         return VX_OK;
     }
+    if (!it->ever_initialised) CU_TRY(cudaMemsetAsync(it->dev.children, 0, it->capacity * 64, s));  // once: no garbage rows
     it->ever_initialised = true;
     it->ever_released = false;
     CU_TRY(cudaMemsetAsync(it->dev.slots, 0, it->nbuckets * 64, s));

@@ -108,6 +108,26 @@ __device__ __forceinline__ u32 ld_strong_u16(const u16* p) {
 __device__ __forceinline__ void ld_strong_v2(const u64* p, u64* a, u64* b) {
     asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(*a), "=l"(*b) : "l"(p) : "memory");
 }
+// Weak (L1-cacheable) forms for the FIRST look at a bucket / stored row: hot keys are asked for by every warp of the
+// grid, and strong loads send all of them to the one L2 slice that holds the line.  What a weak read returns may be
+// stale, so only what cannot be wrong is concluded from it:
+//   * bucket: a final entry never changes while a build kernel runs; a stale "empty" is validated by the CAS at L2; a
+//     stale "pending", a full bucket or a fingerprint match whose row differs conclude nothing — the next round looks
+//     again with strong loads;
+//   * stored row: a row is exactly two 32-byte sectors of its own, L1 fills sector by sector, and a row is only ever
+//     read through a published slot, i.e. after its one and only write of this life — so a cached row is the final
+//     row.  A row match is a hit; a mismatch concludes nothing (strong reads next round).  Belt and braces: dead
+//     indices are given all-zero rows where that is cheap (pool creation, release, the sparse reset), and an all-zero
+//     row equals no key.
+// The level kernels drop the SM's L1 in their prologue (bulk_prologue), so nothing cached is older than the launch.
+__device__ __forceinline__ void ld_weak_v2(const u64* p, u64* a, u64* b) {
+    asm volatile("ld.global.ca.v2.u64 {%0, %1}, [%2];" : "=l"(*a), "=l"(*b) : "l"(p) : "memory");
+}
+__device__ __forceinline__ u64 ld_weak(const u64* p) {
+    u64 v;
+    asm volatile("ld.global.ca.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void st_strong(u64* p, u64 v) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }

@@ -186,6 +186,9 @@ __global__ void __launch_bounds__(256) reset_used_kernel(InternerDev in, size_t 
             branch = branch || (q.x | q.y) != 0;
         }
         if (branch) {
+            ulonglong2* wrow = reinterpret_cast<ulonglong2*>(in.children + idx * 8);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) wrow[k] = make_ulonglong2(0, 0);  // a dead index keeps no old key (see ld_weak, vx_device.cuh)
             u32 bucket = u32(h) & in.bucket_mask;
             for (u32 guard = 0; guard <= in.bucket_mask; ++guard) {
                 bool found = false;
