@@ -321,9 +321,11 @@ __device__ inline u64 leaf_get(Ctx<u8>& c, u32 v, bool need) {
     need = need && v != 0;
     u64 id = need ? lds_relaxed(&c.cs->leaf[v]) : 0;
     bool miss = need && id == 0;
+    bool first = c.weak_first;  // every CTA of the grid asks for the same few leaves at its start: first look through L1
     while (__any_sync(FULL, miss)) {
         if (miss) {
-            u64 g = ld_strong(&c.in.leaf_u8[v]);
+            u64 g = first ? ld_weak(&c.in.leaf_u8[v]) : ld_strong(&c.in.leaf_u8[v]);
+            first = false;
             if (g == 0) {
                 u64 old = atomicCAS((ull*)&c.in.leaf_u8[v], 0ull, (ull)ID_PENDING);
                 if (old == 0) {  // this lane creates the leaf
@@ -1187,8 +1189,8 @@ __device__ inline void smem_init(WarpSmem<T>* ws, CtaSmem* cs, bool block_level 
         for (u32 i = threadIdx.x; i < sizeof(WarpSmem<T>) * WARPS_PER_CTA / 4; i += blockDim.x) w[i] = 0;
     } else {
         constexpr u32 words = u32((sizeof(WarpSmem<T>) - offsetof(WarpSmem<T>, ukey)) / 4);
-        for (u32 i = threadIdx.x; i < words * WARPS_PER_CTA; i += blockDim.x)
-            ((u32*)((unsigned char*)(ws + i / words) + offsetof(WarpSmem<T>, ukey)))[i % words] = 0;
+        u32* tail = (u32*)((unsigned char*)(ws + (threadIdx.x >> 5)) + offsetof(WarpSmem<T>, ukey));  // every warp its own
+        for (u32 i = threadIdx.x & 31; i < words; i += 32) tail[i] = 0;
     }
     u32* q = (u32*)cs;
     for (u32 i = threadIdx.x; i < sizeof(CtaSmem) / 4; i += blockDim.x) q[i] = 0;

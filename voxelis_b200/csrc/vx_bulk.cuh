@@ -544,7 +544,8 @@ __global__ void __launch_bounds__(CTA_THREADS, VX_BULK_MIN_CTAS) bulk_blocks_ker
         // poisoned interner: stop (the host reports it).  The word is requested here and tested at the end of the
         // iteration, so its round trip hides behind the work — every eighth iteration only: every warp of the grid
         // polling ONE address each iteration made that load the slowest of the iteration (15.7 % of the stall samples)
-        const u32 errw = (c.lane == 0 && (((base - base0) / stride) & 7) == 7) ? ld_strong(a.in.error) : u32(ERR_NONE);
+        // (and the warps of a CTA take turns, so that the polls of the grid do not all fall into the same iteration)
+        const u32 errw = (c.lane == 0 && (((base - base0) / stride + (threadIdx.x >> 5)) & 7) == 7) ? ld_strong(a.in.error) : u32(ERR_NONE);
         const u32 k = base + c.lane;
         const bool active = k < end;
         const u32 set = set1;
@@ -820,7 +821,7 @@ __global__ void __launch_bounds__(CTA_THREADS, VX_BULK_MIN_CTAS) bulk_level_kern
     const u32 base0 = u32(min(wfirst, u64(cnt)));
     const u32 end = u32(min(wfirst + span, u64(cnt)));
     for (u32 base = base0; base < end; base += 32) {
-        const u32 errw = (c.lane == 0 && (((base - base0) >> 5) & 7) == 7) ? ld_strong(a.in.error) : u32(ERR_NONE);  // see bulk_blocks_kernel
+        const u32 errw = (c.lane == 0 && ((((base - base0) >> 5) + (threadIdx.x >> 5)) & 7) == 7) ? ld_strong(a.in.error) : u32(ERR_NONE);  // see bulk_blocks_kernel
         const u32 k = base + c.lane;
         const bool active = k < end;
         const u32 f = active ? ld_stream_u32(first + k) : 0;
