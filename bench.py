@@ -453,7 +453,7 @@ def main():
     # per-launch device times of the apply pipeline (CUDA events between its launches, outside the timed
     # region above: the extra event records would perturb it)
     stages = stage_times(it, step_device)
-    launches_per_step = len(stages) + 1               # + the reset's init kernel
+    launches_per_step = len(stages) + 2               # + the reset's two kernels (reset_used_kernel, init_scalars_kernel)
     dom = max(stages, key=stages.get) if stages else "apply_kernel"
     log("stages: " + ", ".join(f"{k} {v * 1e3:.1f} us" for k, v in stages.items()))
     # ---------------------------------------------------------------- end to end (host batches)
