@@ -250,3 +250,58 @@ def test_untouched_batch_reports_changed_like_the_reference(gpu_api, oracle_api)
                                           flags=np.zeros(2, np.uint8), fills=np.zeros(2, np.int64))
     assert list(changed) == [1, 1] and list(roots) == [0, 0]
     assert g.stats()["alive_nodes"] == 1
+
+
+# ---------------------------------------------------------------------------------------------- journal path
+def _set_world(vx, depth, dtype, n, seed, dense_every=0):
+    """n batches written voxel by voxel through Batch::set (repeats, later clears, rewrites), returned with the dense
+    volumes they must build: sparse ones keep a journal, every `dense_every`-th one overflows it."""
+    rng = np.random.default_rng(seed)
+    N = 1 << depth
+    trees = [vx.VoxTree(depth, dtype) for _ in range(n)]
+    batches = [t.create_batch() for t in trees]
+    vols = np.zeros((n, N, N, N), np.int64)                                    # [i][x][y][z]
+    for i, b in enumerate(batches):
+        k = (N ** 3 // 3) if dense_every and i % dense_every == dense_every - 1 else int(rng.integers(0, 300))
+        xyz = rng.integers(0, N, (k, 3))
+        vals = rng.integers(-3 if dtype == wl.I32 else 0, 6, k)               # zeros are clears (batch.rs:165-168)
+        for (x, y, z), v in zip(xyz, vals):
+            b.set(None, (int(x), int(y), int(z)), int(v))
+            vols[i, x, y, z] = v
+        for (x, y, z) in xyz[: k // 4]:                                        # a second write to a quarter of them
+            b.set(None, (int(x), int(y), int(z)), 4)
+            vols[i, x, y, z] = 4
+    return trees, batches, vols
+
+
+@pytest.mark.parametrize("dtype", [wl.U8, wl.I32], ids=["u8", "i32"])
+@pytest.mark.parametrize("depth", [3, 5])
+def test_journal_path_matches_dense_expectation(gpu_api, depth, dtype, monkeypatch):
+    """Batches written through set() travel as packed (block, values) journals; ones that outgrow the journal fall back
+    to the occupancy bitmap for their whole slice.  Voxels must equal what was set, whichever path a slice took, and
+    both staging paths must build the same DAG."""
+    vx = gpu_api
+    outs = {}
+    for mode in ("journal", "occupancy", "mixed"):
+        if mode == "occupancy":
+            monkeypatch.setenv("VX_STAGE_NO_JOURNAL", "1")
+        else:
+            monkeypatch.delenv("VX_STAGE_NO_JOURNAL", raising=False)
+        trees, batches, vols = _set_world(vx, depth, dtype, 40, seed=depth * 10 + dtype, dense_every=7 if mode == "mixed" else 0)
+        g = vx.VoxInterner.with_memory_budget(128 << 20, dtype)
+        changed = vx.apply_batches(g, trees, batches)
+        for i, t in enumerate(trees):
+            want = np.transpose(vols[i], (1, 2, 0))                            # [y][z][x]
+            assert np.array_equal(t.to_vec(g).astype(np.int64), want), (mode, i)
+            assert bool(changed[i]) == bool((vols[i] != 0).any()) or not (vols[i] != 0).any()
+        outs[mode] = g.stats()["alive_nodes"]
+        # edits on top (the same handles, cleared and refilled): the journal restarts with the batch
+        for b in batches[:5]:
+            b.clear()
+            b.set(None, (1, 1, 1), 9)
+        vx.apply_batches(g, trees[:5], batches[:5])
+        for t, v in zip(trees[:5], vols[:5]):
+            v2 = v.copy()
+            v2[1, 1, 1] = 9
+            assert np.array_equal(t.to_vec(g).astype(np.int64), np.transpose(v2, (1, 2, 0)))
+    assert outs["journal"] == outs["occupancy"]

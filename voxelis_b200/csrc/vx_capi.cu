@@ -147,6 +147,16 @@ struct vx_batch {
     vx_dtype dtype;
     uint64_t touched[8];  // <= 512 units (D = 7), inline
     size_t blocks, slot_bytes;
+    // Journal (D <= 6, batches only ever written through the API): the blocks that hold a non-default voxel, packed —
+    // jblock[k] = block index, jvals[k] = a copy of that block's eight values — in the same pinned slot.  A sparse
+    // batch then crosses the bus as 2 + 8·sizeof(T) contiguous bytes per flagged block instead of scattered 8-byte
+    // reads that the bus moves as 32-byte sectors (vx_stage.cuh: stage_journal_kernel).  jmap (host only) = slot + 1
+    // of a block in the journal.  More than jcap flagged blocks: journal_ok = false and the occupancy path serves.
+    uint16_t* jblock;
+    void* jvals;
+    uint16_t* jmap;
+    uint32_t jcount, jcap;
+    bool journal_ok;
 };
 
 namespace {
@@ -1103,6 +1113,34 @@ inline void batch_touch(vx_batch* b, size_t block) {
     b->touched[u >> 6] |= uint64_t(1) << (u & 63);
     b->occ[block >> 3] |= u8(1u << (block & 7));
 }
+// the journal's copy of block p follows the dense array (called after every write to a block that is, or now has to
+// be, in the journal)
+inline void journal_update(vx_batch* b, size_t p, bool enter) {
+    if (!b->journal_ok) return;
+    uint32_t s = b->jmap[p];
+    if (!s) {
+        if (!enter) return;
+        if (b->jcount == b->jcap) {
+            b->journal_ok = false;  // too dense for a journal: the occupancy bitmap serves this batch
+            return;
+        }
+        s = ++b->jcount;
+        b->jmap[p] = uint16_t(s);
+        b->jblock[s - 1] = uint16_t(p);
+    }
+    const size_t vsz = 8 * dtype_size(b->dtype);
+    memcpy((u8*)b->jvals + size_t(s - 1) * vsz, (const u8*)b->values + p * vsz, vsz);
+}
+inline void journal_reset(vx_batch* b) {
+    if (b->jmap) {
+        if (b->journal_ok)
+            for (uint32_t k = 0; k < b->jcount; ++k) b->jmap[b->jblock[k]] = 0;
+        else
+            memset(b->jmap, 0, b->blocks * 2);
+    }
+    b->jcount = 0;
+    b->journal_ok = b->jmap != nullptr && !b->raw_exposed;
+}
 // Rebuilds the occupancy summary from the arrays (after the caller bulk-wrote them).
 void batch_rescan(vx_batch* b) {
     memset(b->touched, 0, sizeof(b->touched));
@@ -1116,6 +1154,10 @@ void batch_rescan(vx_batch* b) {
         for (size_t p = size_t(u) * b->unit_blocks, e = p + b->unit_blocks; p < e; ++p)
             if (b->masks[2 * p]) b->occ[p >> 3] |= u8(1u << (p & 7));
     }
+    journal_reset(b);
+    if (b->journal_ok)
+        for (size_t p = 0; p < b->blocks && b->journal_ok; ++p)
+            if (b->occ[p >> 3] >> (p & 7) & 1) journal_update(b, p, true);
 }
 
 }  // namespace
@@ -1138,8 +1180,12 @@ vx_batch* vx_batch_create(uint8_t max_depth, vx_dtype dtype) {
     memset(b->touched, 0, sizeof(b->touched));
     // pinned + mapped so apply can read the batch in place over PCIe; no device, no batch
     size_t mb = b->blocks * 2, vb = b->blocks * 8 * dtype_size(dtype);
-    const size_t ob = (b->blocks + 7) / 8;
-    b->slot_bytes = (mb + vb + ob + 3 + 255) & ~size_t(255);  // +3: the staging kernel reads the bitmap as 32-bit words
+    const size_t ob = ((b->blocks + 7) / 8 + 3 + 15) & ~size_t(15);  // +3: the staging kernel reads the bitmap as 32-bit words
+    // journal (see vx_batch): a quarter of the blocks at most, D <= 6 (block indices are 16 bits)
+    b->jcap = max_depth <= 6 && b->blocks >= 64 ? uint32_t(b->blocks / 4) : 0;
+    const size_t jv = size_t(b->jcap) * 8 * dtype_size(dtype), jb = (size_t(b->jcap) * 2 + 15) & ~size_t(15),
+                 jm = b->jcap ? b->blocks * 2 : 0;
+    b->slot_bytes = (mb + vb + ob + jv + jb + jm + 255) & ~size_t(255);
     b->masks = arena().take(b->slot_bytes, &b->alias);
     if (!b->masks) {
         fail(VX_E_CUDA, "vx_batch_create: cudaHostAlloc failed (no CUDA device?)");
@@ -1148,6 +1194,11 @@ vx_batch* vx_batch_create(uint8_t max_depth, vx_dtype dtype) {
     }
     b->values = b->masks + mb;
     b->occ = b->masks + mb + vb;
+    b->jvals = b->jcap ? b->masks + mb + vb + ob : nullptr;
+    b->jblock = b->jcap ? reinterpret_cast<uint16_t*>(b->masks + mb + vb + ob + jv) : nullptr;
+    b->jmap = b->jcap ? reinterpret_cast<uint16_t*>(b->masks + mb + vb + ob + jv + jb) : nullptr;
+    b->jcount = 0;
+    b->journal_ok = b->jcap != 0;
     memset(b->masks, 0, b->slot_bytes);
     return b;
 }
@@ -1192,6 +1243,7 @@ int vx_batch_set(vx_batch* b, int x, int y, int z, int64_t voxel) {
         b->masks[2 * p] &= u8(~bit);
         b->masks[2 * p + 1] |= bit;
     }
+    journal_update(b, p, nonzero);
     b->has_patches = true;
     return 1;
 }
@@ -1210,6 +1262,7 @@ int vx_batch_clear(vx_batch* b) {
     }
     memset(b->touched, 0, sizeof(b->touched));
     memset(b->occ, 0, (b->blocks + 7) / 8);
+    journal_reset(b);
     b->has_fill = false;
     b->fill = 0;
     b->has_patches = false;
@@ -1223,11 +1276,11 @@ int vx_batch_fill(vx_batch* b, int64_t value) {
     return VX_OK;
 }
 uint8_t* vx_batch_masks(vx_batch* b) {
-    if (b) b->raw_exposed = true;
+    if (b) b->raw_exposed = true, b->journal_ok = false;  // the caller may write behind the journal's back
     return b ? b->masks : nullptr;
 }
 void* vx_batch_values(vx_batch* b) {
-    if (b) b->raw_exposed = true;
+    if (b) b->raw_exposed = true, b->journal_ok = false;
     return b ? b->values : nullptr;
 }
 size_t vx_batch_blocks(const vx_batch* b) { return b ? b->blocks : 0; }
@@ -1756,10 +1809,10 @@ int vx_apply_batches(vx_interner* it, vx_tree* const* trees, const vx_batch* con
     const size_t slab_bytes = up(slice * mbytes) + up(slice * vbytes);
     const size_t o_roots = n_slabs * slab_bytes, o_fills = o_roots + up(n * 8), o_old = o_fills + up(n * 8),
                  o_src = o_old + up(n * 8), o_units = o_src + up(n * 8), o_changed = o_units + up(max_units * 4),
-                 o_flags = o_changed + up(n), dev_need = o_flags + up(n);
+                 o_flags = o_changed + up(n), o_jcnt = o_flags + up(n), dev_need = o_jcnt + up(n * 4);
     const size_t h_fills_o = up(n * 8), h_old_o = h_fills_o + up(n * 8), h_src_o = h_old_o + up(n * 8),
                  h_units_o = h_src_o + up(n * 8), h_changed_o = h_units_o + up(max_units * 4),
-                 h_flags_o = h_changed_o + up(n), host_need = h_flags_o + up(n);
+                 h_flags_o = h_changed_o + up(n), h_jcnt_o = h_flags_o + up(n), host_need = h_jcnt_o + up(n * 4);
     int rc = ensure_scratch(it, dev_need, host_need);
     if (rc != VX_OK) return rc;
     u8* dbase = (u8*)it->scratch;
@@ -1770,6 +1823,7 @@ int vx_apply_batches(vx_interner* it, vx_tree* const* trees, const vx_batch* con
     u32* d_units = (u32*)(dbase + o_units);
     u8* d_changed = dbase + o_changed;
     u8* d_flags = dbase + o_flags;
+    u32* d_jcnt = (u32*)(dbase + o_jcnt);
     u8* hbase = (u8*)it->hscratch;
     u64* h_roots = (u64*)hbase;
     int64_t* h_fills = (int64_t*)(hbase + h_fills_o);
@@ -1778,6 +1832,10 @@ int vx_apply_batches(vx_interner* it, vx_tree* const* trees, const vx_batch* con
     u32* h_units = (u32*)(hbase + h_units_o);
     u8* h_changed = hbase + h_changed_o;
     u8* h_flags = hbase + h_flags_o;
+    u32* h_jcnt = (u32*)(hbase + h_jcnt_o);
+    // where a batch's journal sits in its slot (same for every batch of the call: one depth, one dtype)
+    const size_t ob = ((B + 7) / 8 + 3 + 15) & ~size_t(15);
+    const size_t off_jvals = mbytes + vbytes + ob, off_jblock = off_jvals + size_t(batches[0]->jcap) * 8 * dtype_size(it->dtype);
     cudaStream_t s = it->stream, cs = it->copy_stream;
     const bool trace = it->prof;
     if (trace) {
@@ -1791,7 +1849,7 @@ int vx_apply_batches(vx_interner* it, vx_tree* const* trees, const vx_batch* con
     struct Prep {
         int rc = VX_OK;
         const char* err = nullptr;
-        bool fused = true, any_fill = false, old_here = false, raw = false;
+        bool fused = true, any_fill = false, old_here = false, raw = false, journal = true;
         size_t nu = 0;
     };
     std::vector<Prep> prep(n_slices);
@@ -1830,6 +1888,8 @@ int vx_apply_batches(vx_interner* it, vx_tree* const* trees, const vx_batch* con
             P.any_fill = P.any_fill || b->has_fill;
             P.old_here = P.old_here || t->root != VX_BLOCK_EMPTY;
             P.raw = P.raw || b->raw_exposed;
+            P.journal = P.journal && b->journal_ok;
+            h_jcnt[i] = b->has_patches ? b->jcount : 0;
             if (!b->has_patches || !P.fused) continue;
             const u32 first = u32(i - lo) << upc_log2;
             for (uint32_t w = 0; w * 64 < b->units; ++w)
@@ -1894,6 +1954,21 @@ int vx_apply_batches(vx_interner* it, vx_tree* const* trees, const vx_batch* con
             // one CTA per SM keeps enough loads on the bus and leaves the SMs to the build of the previous slice
             static const size_t per_sm = getenv("VX_STAGE_CTAS") ? size_t(atoi(getenv("VX_STAGE_CTAS"))) : 1;
             const unsigned grid = unsigned(std::min<size_t>((nu + STAGE_WARPS - 1) / STAGE_WARPS, size_t(it->sm_count) * per_sm));
+            // every batch of the slice keeps a journal (API-written, sparse): the packed (block, values) arrays travel
+            static const bool no_journal = getenv("VX_STAGE_NO_JOURNAL") != nullptr;
+            if (P.journal && !P.raw && !force_masks && !no_journal) {
+                CU_TRY(cudaMemcpyAsync(d_jcnt + lo, h_jcnt + lo, cnt * 4, cudaMemcpyHostToDevice, cs));
+                if (S.listed)  // (the fused kernel's slab was zeroed whole above)
+                    stage_zero_units_kernel<<<grid, STAGE_THREADS, 0, cs>>>(d_units + k0, u32(nu), upc_log2, ub, S.dm, mbytes);
+                static const size_t jctas = getenv("VX_STAGE_JCTAS") ? size_t(atoi(getenv("VX_STAGE_JCTAS"))) : 1;  // the bus is the bound, not the SMs
+                const unsigned jgrid = unsigned(std::min<size_t>((cnt + STAGE_WARPS - 1) / STAGE_WARPS, size_t(it->sm_count) * jctas));
+                if (it->dtype == VX_U8)
+                    stage_journal_kernel<8><<<jgrid, STAGE_THREADS, 0, cs>>>(d_src + lo, d_jcnt + lo, u32(cnt), off_jvals, off_jblock,
+                                                                            S.dm, S.dv, mbytes, vbytes);
+                else
+                    stage_journal_kernel<32><<<jgrid, STAGE_THREADS, 0, cs>>>(d_src + lo, d_jcnt + lo, u32(cnt), off_jvals, off_jblock,
+                                                                             S.dm, S.dv, mbytes, vbytes);
+            } else
             // a batch that only ever went through set/fill/clear/assign has value != 0 <=> set bit, so its masks
             // stay on the host and the one-bit-per-block map travels instead (vx_stage.cuh)
             if (!P.raw && !force_masks) {

@@ -189,4 +189,91 @@ stage_units_occ_kernel(const u64* __restrict__ src,    // [n] slot address: mask
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Journal path (vx_batch: jblock / jvals).  A batch that was only written through the API keeps the blocks holding a
+// non-default voxel PACKED: 2 bytes of block index + VB bytes of values per flagged block, contiguous in its pinned
+// slot.  stage_journal_kernel streams those arrays over the bus with fully coalesced loads (32 lanes x 8 B = 256 B per
+// request for u8) and scatters them into the slab; the set_mask is rebuilt from the values (value != 0 <=> set bit for
+// such batches, batch.rs:162-168).  Against the occupancy path — 8-byte reads scattered over the unit, which the bus
+// moves as 32-byte sectors — the perlin world sends 13.8 MB instead of ~30.  The masks of the OTHER blocks of a
+// touched unit must read zero: stage_zero_units_kernel clears the listed units' masks in HBM first.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(STAGE_THREADS)
+stage_zero_units_kernel(const u32* __restrict__ units, u32 n_units, u32 upc_log2, u32 unit_blocks, u8* __restrict__ d_masks,
+                        u64 mask_bytes) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const u32 warps = gridDim.x * STAGE_WARPS;
+    const u32 bytes = unit_blocks * 2;  // a multiple of 16 (unit_blocks >= 64 on this path)
+    for (u32 e = blockIdx.x * STAGE_WARPS + w; e < n_units; e += warps) {
+        const u32 u = units[e];
+        const u32 chunk = u >> upc_log2, unit = u & ((1u << upc_log2) - 1u);
+        u8* q = d_masks + u64(chunk) * mask_bytes + u64(unit) * bytes;
+        for (u32 off = u32(lane) * 16; off < bytes; off += 512) *reinterpret_cast<uint4*>(q + off) = make_uint4(0, 0, 0, 0);
+    }
+}
+
+template <int VB>
+__global__ void __launch_bounds__(STAGE_THREADS)
+stage_journal_kernel(const u64* __restrict__ src,   // [n] device-visible address of each batch slot
+                     const u32* __restrict__ jcnt,  // [n] journal entries of each batch
+                     u32 n_chunks, u64 off_jvals, u64 off_jblock, u8* __restrict__ d_masks, u8* __restrict__ d_values,
+                     u64 mask_bytes, u64 value_bytes) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const u32 warps = gridDim.x * STAGE_WARPS;
+    for (u32 chunk = blockIdx.x * STAGE_WARPS + w; chunk < n_chunks; chunk += warps) {
+        const u32 cnt = jcnt[chunk];
+        if (cnt == 0) continue;
+        const u8* base = reinterpret_cast<const u8*>(src[chunk]);
+        const u8* jv = base + off_jvals;
+        const u8* jb = base + off_jblock;
+        u8* vd = d_values + u64(chunk) * value_bytes;
+        u16* md = reinterpret_cast<u16*>(d_masks + u64(chunk) * mask_bytes);
+        constexpr u32 UNR = VB == 8 ? 8 : 4;  // entries per lane in flight: the bus round trip is microseconds
+        for (u32 k0 = 0; k0 < cnt; k0 += 32 * UNR) {
+            u32 blk[UNR];
+            if (VB == 8) {
+                u64 v[UNR];
+#pragma unroll
+                for (u32 j = 0; j < UNR; ++j) {
+                    const u32 k = k0 + j * 32 + lane;
+                    blk[j] = 0xFFFFFFFFu;
+                    v[j] = 0;
+                    if (k < cnt) {
+                        blk[j] = ld_stream_u16(jb + 2 * u64(k));
+                        v[j] = ld_stream_u64(jv + 8 * u64(k));
+                    }
+                }
+#pragma unroll
+                for (u32 j = 0; j < UNR; ++j)
+                    if (blk[j] != 0xFFFFFFFFu) {
+                        *reinterpret_cast<u64*>(vd + u64(blk[j]) * 8) = v[j];
+                        md[blk[j]] = u16(nonzero_bytes(v[j]));
+                    }
+            } else {
+                uint4 a[UNR], c[UNR];
+#pragma unroll
+                for (u32 j = 0; j < UNR; ++j) {
+                    const u32 k = k0 + j * 32 + lane;
+                    blk[j] = 0xFFFFFFFFu;
+                    if (k < cnt) {
+                        blk[j] = ld_stream_u16(jb + 2 * u64(k));
+                        a[j] = ld_stream_v4(jv + 32 * u64(k));
+                        c[j] = ld_stream_v4(jv + 32 * u64(k) + 16);
+                    }
+                }
+#pragma unroll
+                for (u32 j = 0; j < UNR; ++j)
+                    if (blk[j] != 0xFFFFFFFFu) {
+                        uint4* q = reinterpret_cast<uint4*>(vd + u64(blk[j]) * 32);
+                        q[0] = a[j];
+                        q[1] = c[j];
+                        md[blk[j]] = u16((a[j].x != 0) | (a[j].y != 0) << 1 | (a[j].z != 0) << 2 | (a[j].w != 0) << 3 |
+                                         (c[j].x != 0) << 4 | (c[j].y != 0) << 5 | (c[j].z != 0) << 6 | (c[j].w != 0) << 7);
+                    }
+            }
+        }
+    }
+}
+
 }  // namespace vx
