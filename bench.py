@@ -794,17 +794,17 @@ def main():
                                 "device_memory": stats_mem},
             "value_nonempty": total_nonempty / (step_ms_max * 1e-3),
             "e2e": {"value": e2e_value, "unit": "chunks/s", "ms_per_step": e2e_ms_max,
-                    # per step: descriptors (8 B per chunk + 4 B per touched unit) by the copy engine; the touched units'
-                    # occupancy bits and the values of blocks with a set bit by loads the staging kernel issues on
-                    # pinned host memory (batches written through the API never send their masks, vx_stage.cuh)
-                    "h2d_bytes_per_step": int(n * 8 + touched_units * 4 + touched_units * 64 + touched_blocks * 8),
-                    "h2d_bytes_note": "descriptors + 64 B of per-block occupancy per touched unit + 8 B per flagged block; the bus "
-                                      "moves 32-byte sectors, so the traffic ncu sees (pcie__read_bytes) is 2-3x this lower bound",
+                    # per step: descriptors by the copy engine; the batches' packed journals (block index + values of every
+                    # block holding a voxel) by loads the staging kernel issues on pinned host memory (vx_stage.cuh)
+                    "h2d_bytes_per_step": int(n * 12 + touched_units * 4 + touched_blocks * 10),
+                    "h2d_bytes_note": "descriptors (8 + 4 B per chunk, 4 B per touched unit) + the batches' journals: 2 B of block "
+                                      "index + 8 B of values per flagged block, contiguous per batch; ncu pcie__read_bytes for the "
+                                      "staging kernels of one world: 19.8 MB",
                     "host_input_bytes_per_step": int(masks.nbytes + values.nbytes),
                     "d2h_bytes_per_step": int(n * 9),
                     "touched_units": int(touched_units),
                     "path": "vx_apply_batches on n Batch + n VoxTree handles (batches in pinned host memory; "
-                            "stage_units_kernel pulls touched units over PCIe, builders run on the device slab), "
+                            "stage_journal_kernel pulls the batches' journals over PCIe, builders run on the device slab), "
                             "roots + changed flags D2H into the VoxTree handles",
                     "phases_us": e2e_trace, "dense_slab_variant": e2e_slab},
             "gpu_launches": args.steps * launches_per_step,
