@@ -10,6 +10,7 @@
 #include <array>
 #include <atomic>
 #include <chrono>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -144,7 +145,9 @@ struct vx_batch {
     uint8_t depth;
     bool has_fill, has_patches;
     bool raw_exposed;     // the caller holds raw array pointers: clear() wipes everything, apply trusts only the masks
+    bool journal_ok;      // the journal below is complete (first cache line: vx_apply_batches reads it per batch)
     vx_dtype dtype;
+    uint32_t jcount;      // entries in the journal
     uint64_t touched[8];  // <= 512 units (D = 7), inline
     size_t blocks, slot_bytes;
     // Journal (D <= 6, batches only ever written through the API): the blocks that hold a non-default voxel, packed —
@@ -155,9 +158,9 @@ struct vx_batch {
     uint16_t* jblock;
     void* jvals;
     uint16_t* jmap;
-    uint32_t jcount, jcap;
-    bool journal_ok;
+    uint32_t jcap;
 };
+static_assert(offsetof(vx_batch, touched) <= 64, "per-batch fields of vx_apply_batches' host pass fit one cache line");
 
 namespace {
 
