@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB = os.path.join(_HERE, "libvoxelis_b200.so")
 SOURCES = ["vx_capi.cu"]
-HEADERS = ["vx_device.cuh", "vx_build.cuh", "vx_bulk.cuh", "vx_read.cuh", "vx_release.cuh", "vx_dedup.cuh", "vx_stage.cuh", "vx_vtm.cuh", "vx_occupancy.cuh", "vx_terrain.cuh", "vx_voxelize.cuh", "vx_world.cuh",
+HEADERS = ["vx_device.cuh", "vx_build.cuh", "vx_bulk.cuh", "vx_read.cuh", "vx_release.cuh", "vx_dedup.cuh", "vx_stage.cuh", "vx_vtm.cuh", "vx_occupancy.cuh", "vx_terrain.cuh", "vx_voxelize.cuh", "vx_world.cuh", "vx_capi_batch.inl", "vx_capi_voxelize.inl", "vx_capi_vtm.inl",
            os.path.join("..", "..", "include", "voxelis_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC", "-ldl"]
