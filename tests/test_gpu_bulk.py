@@ -247,3 +247,20 @@ def test_unit_memo_is_per_call(gpu_api, oracle_api, monkeypatch):
         assert np.array_equal(dense[i], wl.dense_expected(m, v))
     st = g.stats()
     assert st["branch_nodes"] - 1 == 4200 * 4681 + 5 + 83       # all-miss chunks + checkerboard + sum
+
+
+@pytest.mark.parametrize("name", ["checkerboard", "sum"])
+def test_config2_full_size_counters_and_dag(gpu_api, oracle_api, name):
+    """BASELINE config 2 at its full size (4 096 chunks of 32^3 into one interner, voxtree_bench.rs:699-710,777-786):
+    with 32 767 of the 32 768 units aliased through the unit memo, every InternerStats counter, the DAG and the
+    refcounts still equal the oracle's serial application, and every chunk gets the same root."""
+    vx, o = gpu_api, oracle_api
+    masks, values = wl.named_workload(name, 4096)
+    r = parity.build_both(vx, o, 5, masks, values, wl.U8, budget=256 << 20)
+    g, groots = r[0], r[1]
+    assert len(set(groots.tolist())) == 1
+    parity.assert_parity(vx, o, 5, *r, dense_check=False)
+    st = g.stats()
+    want = {"checkerboard": (5, 1), "sum": (83, 94)}[name]
+    assert st["branch_nodes"] - 1 == want[0] and st["leaf_nodes"] == want[1]          # SURVEY §8c known answers
+    assert np.array_equal(g.roots_to_vec(groots[-1:], 5)[0], wl.dense_expected(masks[-1], values[-1]))
