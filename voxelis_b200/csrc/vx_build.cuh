@@ -38,11 +38,14 @@ namespace vx {
 constexpr int WARPS_PER_CTA = 8;
 constexpr int CTA_THREADS = WARPS_PER_CTA * 32;
 constexpr int UNIT_BLOCKS = 512;  // blocks per warp work unit
+// Per-warp cache sizes.  They set the CTA's shared memory (38 KiB at 128 / 16), and with three CTAs per SM that sets
+// the SM's carve-out and so what is left as L1: 256 / 32 entries (62 KiB per CTA, 60 KiB of L1) built the repetitive
+// worlds 6-14 % slower for the same hit rates; 64 / 16 and below lose hits on terrain (profiles/README.md, round 2).
 #ifndef VX_UC
-#define VX_UC 32
+#define VX_UC 16
 #endif
 #ifndef VX_BC_U8
-#define VX_BC_U8 256
+#define VX_BC_U8 128
 #endif
 constexpr int UC = VX_UC;         // per-warp parent-cache entries (children[8] -> id)
 
