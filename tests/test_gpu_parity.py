@@ -236,3 +236,38 @@ def test_to_vec_at_every_lod(gpu_api, oracle_api, dtype):
             gd = g.roots_to_vec(groots, depth, lod)
             for i in range(len(groots)):
                 assert np.array_equal(gd[i], c.root_to_vec(int(croots[i]), depth, lod)), (depth, lod, i)
+
+
+@pytest.mark.parametrize("dtype", [wl.U8, wl.I32], ids=["u8", "i32"])
+@pytest.mark.parametrize("depth", [5, 6])
+def test_solid_units_take_the_short_way_with_the_same_counters(gpu_api, oracle_api, depth, dtype):
+    """apply_kernel answers a unit whose 512 blocks are all set to one value with that value's leaf (solid_unit,
+    vx_build.cuh) — DAG, refcounts and every counter must be those of the block-by-block build: chunks that are
+    solid throughout, solid but for one voxel / one cleared bit / one unit, two solid halves, and the same under a fill."""
+    B = wl.blocks_per_chunk(depth)
+    n = 7
+    masks = np.zeros((n, B, 2), np.uint8)
+    values = np.zeros((n, B, 8), wl.NP_DTYPE[dtype])
+    masks[:, :, 0] = 0xFF
+    values[:] = 5
+    values[1, 700 % B, 3] = 6                 # one voxel differs inside an otherwise solid unit
+    masks[2, 513 % B, 0] = 0x7F               # one voxel not set
+    values[2, 513 % B, 7] = 0
+    values[3, :512] = 9                       # first unit solid with another value
+    values[4, B // 2:] = 2                    # two solid halves
+    values[5, 1024 % B: 1024 % B + 512] = 0   # one unit entirely unset
+    masks[5, 1024 % B: 1024 % B + 512, 0] = 0
+    values[6, 100 % B] = 7                    # one uniform block of another value inside a solid unit
+    def check(label, *a, **kw):
+        r = parity.build_both(gpu_api, oracle_api, depth, *a, **kw)
+        try:
+            parity.assert_parity(gpu_api, oracle_api, depth, *r, indeg=kw.get("fill") is None)
+        except AssertionError as e:
+            gd, cd = r[0].download(), r[3].download()
+            raise AssertionError(f"{label}: gpu refs {sorted(gd['refs'][:gd['n']].tolist())[-6:]} values {gd['values'][:12].tolist()} "
+                                 f"oracle refs {sorted(cd['refs'][:cd['n']].tolist())[-6:]} values {cd['values'][:12].tolist()}") from e
+    for fill in (None, 3):   # never a fill equal to a set value: the reference's refcounts go wrong there (SURVEY 0)
+        check(f"fill={fill}", masks, values, dtype, fill=fill, budget=256 << 20)
+    # one chunk at a time (n = 1 spreads the units of a chunk over warps that join through global memory)
+    for i in (0, 1, 3):
+        check(f"chunk {i} alone", masks[i:i + 1], values[i:i + 1], dtype)

@@ -1109,6 +1109,32 @@ __device__ __forceinline__ bool build_blocks(Ctx<T>& c, u64 mlo, u64 mhi, const 
     return true;
 }
 
+// True when all 512 blocks of unit `unit` have all eight voxels set (mlo / mhi: load_unit_masks) to ONE non-default
+// value; lane L tests its 16 blocks = 128 * sizeof(T) contiguous bytes, all requested before the first compare.
+template <class T>
+__device__ __forceinline__ bool solid_unit(const void* chunk_values, u32 unit, u64 mlo, u64 mhi, int lane, u32* value) {
+    if (!__all_sync(FULL, (mlo & mhi) == ~0ull)) return false;
+    const uint4* vp = reinterpret_cast<const uint4*>((const u8*)chunk_values + (size_t(unit) * UNIT_BLOCKS + 16 * lane) * 8 * sizeof(T));
+    constexpr int NV = 8 * int(sizeof(T));  // 16-byte vectors holding this lane's 16 blocks
+    uint4 q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) q[j] = ld_stream_v4(vp + j);
+    const u32 v0 = __shfl_sync(FULL, sizeof(T) == 1 ? (q[0].x & 0xFFu) : q[0].x, 0);
+    const u32 splat = sizeof(T) == 1 ? v0 * 0x01010101u : v0;
+    bool uni = v0 != 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) uni = uni && q[j].x == splat && q[j].y == splat && q[j].z == splat && q[j].w == splat;
+#pragma unroll 1
+    for (int j0 = 8; j0 < NV && __all_sync(FULL, uni); j0 += 8) {  // wider T: the rest of the lane's 16 blocks
+#pragma unroll
+        for (int j = 0; j < 8; ++j) q[j] = ld_stream_v4(vp + j0 + j);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) uni = uni && q[j].x == splat && q[j].y == splat && q[j].z == splat && q[j].w == splat;
+    }
+    *value = v0;
+    return __all_sync(FULL, uni);
+}
+
 // Joins ws->l1[0..n) (nodes of depth d; node i sits at position pos0+i of that depth) level by level
 // down to one node, compacting in place.  The ONLY other call site of parent_node (keeps the kernel
 // inside the instruction cache).
@@ -1398,16 +1424,34 @@ __global__ void __launch_bounds__(CTA_THREADS, VX_MIN_CTAS) apply_kernel(ApplyAr
             }
             // ---- stage 0: the unit.  stage 1: its 32^3 cube.  stage 2: the chunk's top levels.
             bool some = false;
+            u64 solid = 0;
             if (use_old)
                 some = build_blocks<T, OLD>(c, mlo, mhi, cv, unit * UNIT_BLOCKS, nblocks, u);
-            else if (R != 8 || ((ne_units >> k) & 1))
-                some = build_blocks<T, false>(c, mlo, mhi, cv, unit * UNIT_BLOCKS, nblocks, u);
+            else if (R != 8 || ((ne_units >> k) & 1)) {
+                // Solid unit (set_uniform, filled volumes): every voxel set to the same non-default value.  Phase 1 makes
+                // 512 identical leaves (:826 does not look at what stood there), phase 2 collapses 64 + 8 + 1 parents
+                // (:1050) — the outcome is that one leaf, and the counters are those of the long way round.
+                u32 v0 = 0;
+                if (nblocks == UNIT_BLOCKS && solid_unit<T>(cv, unit, mlo, mhi, lane, &v0)) {
+                    solid = __shfl_sync(FULL, leaf_get(c, v0, lane == 0), 0);
+                    if (lane == 0) {
+                        c.t.leaf_calls += UNIT_BLOCKS;
+                        c.t.collapsed += UNIT_BLOCKS + UNIT_BLOCKS / 8 + UNIT_BLOCKS / 64 + 1;
+                    }
+                } else {
+                    some = build_blocks<T, false>(c, mlo, mhi, cv, unit * UNIT_BLOCKS, nblocks, u);
+                }
+            }
             u32 rn = u32(nblocks) / 8, rpos = (unit * UNIT_BLOCKS) >> 3;
             int rd = D - 2;
             for (int stage = 0;; ++stage) {
                 u64 node = u.fill_leaf;
                 bool present = false;
-                if (some) node = reduce_levels<T>(c, rn, rd, rpos, u, use_old, &present);
+                if (stage == 0 && solid != 0) {
+                    node = solid;
+                    present = true;
+                } else if (some)
+                    node = reduce_levels<T>(c, rn, rd, rpos, u, use_old, &present);
                 if (stage == 0) {
                     if (upc == 1) {  // D <= 4: the unit is the tree
                         if (lane == 0) write_root<T>(c, a, chunk, node, present);

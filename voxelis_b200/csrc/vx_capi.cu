@@ -96,6 +96,11 @@ struct vx_interner {
     size_t scratch_bytes = 0;
     void* hscratch = nullptr;  // pinned host
     size_t hscratch_bytes = 0;
+    // single-batch applies (vx_tree_apply_batch): per-call options and results in 64 pinned + mapped bytes that the
+    // kernels read / write in place — no small copies either way (layout: struct Mail below)
+    void* mail = nullptr;
+    uint64_t mail_dev = 0;
+    void* mail_stage = nullptr;  // device copy of one small batch (masks + values, <= MAIL_STAGE_BYTES)
     // release (dec_ref_recursive) frontiers, and host mirrors of device state that only changes in
     // synchronous calls
     u64* rel[2]{};
@@ -250,10 +255,14 @@ int launch_apply_t(vx_interner* it, int depth, size_t n, const u8* d_masks, cons
     // join scratch (see apply_kernel): arrival counters + dynamic work counter, ids/present flags per
     // unit and per cube
     const size_t upc = a.blocks > UNIT_BLOCKS ? a.blocks / UNIT_BLOCKS : 1, cpc = upc / 8;
-    int occ = 0;
     const size_t smem = apply_smem_bytes<T>();
-    CU_TRY(cudaFuncSetAttribute(apply_kernel<T, OLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, apply_kernel<T, OLD>, CTA_THREADS, smem));
+    static thread_local int occ_for_device[64] = {};  // function attributes are per device: set them once each
+    int& occ = occ_for_device[it->device & 63];
+    if (occ == 0) {
+        CU_TRY(cudaFuncSetAttribute(apply_kernel<T, OLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, apply_kernel<T, OLD>, CTA_THREADS, smem));
+        occ = std::max(occ, 1);
+    }
     const size_t max_ctas = size_t(std::max(occ, 1)) * it->sm_count, max_warps = max_ctas * WARPS_PER_CTA;
     // a warp takes a whole 32^3 cube when there are plenty of cubes; otherwise single units, so that a
     // one-chunk apply still spreads over 8 (D=5) .. 512 (D=7) warps
@@ -835,6 +844,8 @@ void vx_interner_destroy(vx_interner* it) {
     cudaFree(it->rel[1]);
     cudaFree(it->d_rel_count);
     if (it->hscratch) cudaFreeHost(it->hscratch);
+    if (it->mail) cudaFreeHost(it->mail);
+    cudaFree(it->mail_stage);
     if (it->stream) cudaStreamDestroy(it->stream);
     if (it->copy_stream) cudaStreamDestroy(it->copy_stream);
     cudaGetLastError();
@@ -1286,6 +1297,66 @@ static int apply_slab_impl(vx_interner* it, uint8_t depth, size_t n, const uint8
     return rc;
 }
 
+// One Batch handle on one tree, the latency path (BASELINE config 1: the reference's own apply_batch takes 23 us).
+// The batch sits in the pinned + mapped arena.  A small one (D = 5; u8 at D = 6) crosses the bus as ONE copy of its
+// contiguous masks + values on the interner's stream — a kernel reading them in place waits out a PCIe round trip per
+// 32-block iteration, 44 us for a 32^3 chunk against ~25 with the copy; a big one is read in place (only blocks with a set
+// bit move).  The flag / fill / old root come from the interner's mailbox and the root and the changed flag go back
+// into it (mapped memory, no copies); the host's one wait is for the error word.
+// (apply_slab_impl for the same call: two pageable H2D copies, the masks through the copy stream behind two events, three
+// D2H copies each with its own synchronise, six cudaPointerGetAttributes: 80 us.)
+constexpr size_t MAIL_STAGE_BYTES = 512 << 10;
+struct Mail {
+    uint64_t root, old_root;
+    int64_t fill;
+    uint32_t err;
+    uint8_t changed, flag;
+};
+int apply_one_in_place(vx_interner* it, const vx_batch* b, uint8_t flag, int64_t fill, vx_block_id old_root,
+                       vx_block_id* root_out, uint8_t* changed_out) {
+    if (it->poisoned) return fail(VX_E_POISONED, "interner overflowed earlier; reset it");
+    std::lock_guard<std::mutex> lk(it->mu);
+    DeviceGuard g(it->device);
+    if (!it->mail) {
+        void* dev = nullptr;
+        CU_TRY(cudaHostAlloc(&it->mail, 64, cudaHostAllocMapped));
+        CU_TRY(cudaHostGetDevicePointer(&dev, it->mail, 0));
+        it->mail_dev = reinterpret_cast<uint64_t>(dev);
+    }
+    static_assert(sizeof(Mail) <= 64, "mailbox layout");
+    Mail* m = static_cast<Mail*>(it->mail);
+    *m = Mail{0, old_root, fill, 0, 0, flag};
+    auto dev = [&](size_t off) { return reinterpret_cast<void*>(it->mail_dev + off); };
+    const u8* zm = reinterpret_cast<const u8*>(b->alias);
+    const size_t voff = size_t(static_cast<const u8*>(b->values) - b->masks);
+    const void* zv = zm + voff;
+    cudaStream_t s = it->stream;
+    const size_t span = voff + b->blocks * 8 * dtype_size(b->dtype);  // masks .. end of values, contiguous in the slot
+    if ((flag & VX_FLAG_PATCHES) && span <= MAIL_STAGE_BYTES) {
+        if (!it->mail_stage) CU_TRY(cudaMalloc(&it->mail_stage, MAIL_STAGE_BYTES));
+        CU_TRY(cudaMemcpyAsync(it->mail_stage, b->masks, span, cudaMemcpyHostToDevice, s));
+        zm = static_cast<const u8*>(it->mail_stage);
+        zv = zm + voff;
+    }
+    int rc = launch_apply(it, b->depth, 1, zm, zv, flag == VX_FLAG_PATCHES ? nullptr : static_cast<const u8*>(dev(offsetof(Mail, flag))),
+                          (flag & VX_FLAG_FILL) ? static_cast<const int64_t*>(dev(offsetof(Mail, fill))) : nullptr,
+                          static_cast<u64*>(dev(offsetof(Mail, root))), static_cast<u8*>(dev(offsetof(Mail, changed))), s,
+                          old_root != VX_BLOCK_EMPTY ? static_cast<const u64*>(dev(offsetof(Mail, old_root))) : nullptr);
+    if (rc != VX_OK) return rc;
+    CU_TRY(cudaMemcpyAsync(&m->err, &it->d_scalars->error, sizeof(u32), cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    if (m->err != ERR_NONE) {
+        it->poisoned = true;
+        if (m->err == ERR_OOM) return fail(VX_E_OOM, "Out of memory");  // interner/macros.rs:38
+        if (m->err == ERR_TABLE_FULL) return fail(VX_E_OOM, "interner hash table full");
+        return fail(VX_E_CUDA, "device-side internal error");
+    }
+    *root_out = m->root;
+    *changed_out = m->changed;
+    if (it->free_host > 0) return refresh_free_count(it);
+    return VX_OK;
+}
+
 int vx_apply_batches_slab(vx_interner* it, uint8_t depth, size_t n, const uint8_t* masks, const void* values,
                           const uint8_t* flags, const int64_t* fills, vx_block_id* roots_out, uint8_t* changed_out) {
     return apply_slab_impl(it, depth, n, masks, values, flags, fills, nullptr, roots_out, changed_out);
@@ -1301,7 +1372,12 @@ int vx_tree_apply_batch(vx_interner* it, vx_tree* t, const vx_batch* b) {
     uint8_t changed = 0;
     // a non-empty tree is merged with the batch on the device (old-tree descent, voxtree.rs:785-842,
     // :930-952); with a fill the batch is built against Leaf(fill) and the old tree only released
-    int rc = apply_slab_impl(it, b->depth, 1, b->masks, b->values, &flag, &fill,
+    int rc;
+    static const bool lean = getenv("VX_SINGLE_STAGED") == nullptr;
+    if (lean && b->alias && !getenv("VX_HOST_MODE"))
+        rc = apply_one_in_place(it, b, flag, fill, old_root, &root, &changed);
+    else
+        rc = apply_slab_impl(it, b->depth, 1, b->masks, b->values, &flag, &fill,
                              old_root != VX_BLOCK_EMPTY ? &old_root : nullptr, &root, &changed);
     if (rc != VX_OK) return rc;
     if (!changed) return 0;
