@@ -13,6 +13,12 @@ d = it.roots_to_vec(roots[:4], 5)
 t = vx.VoxTree(5); b = t.create_batch()
 b.masks[:] = masks[20]; b.values[:] = values[20]; b.mark_patched(); t.apply_batch(it, b)
 b.masks[:] = masks[21]; b.values[:] = values[21]; t.apply_batch(it, b); t.clear(it)
+# single batch through the in-place path: a solid chunk (solid_unit), the same with a fill, a nearly solid one
+mu, vu = wl.named_workload("uniform", 1)
+t2 = vx.VoxTree(5); b2 = t2.create_batch(); b2.assign(mu[0], vu[0]); t2.apply_batch(it, b2); assert t2.is_leaf()
+b2.clear(); b2.fill(it, 3); t2.apply_batch(it, b2)
+vu2 = vu.copy(); vu2[0, 700, 3] = 9
+b2.clear(); b2.assign(mu[0], vu2[0]); t2.apply_batch(it, b2); t2.clear(it)
 # i32 + D6
 m2, v2 = wl.batch_from_function(6, wl.p_random(4), wl.I32, 1)
 it2 = vx.VoxInterner.with_memory_budget(64 << 20, vx.I32); it2.apply_batches_slab(6, m2, v2)
