@@ -313,9 +313,13 @@ int launch_apply_t(vx_interner* it, int depth, size_t n, const u8* d_masks, cons
 
 // ---- bulk builder (vx_bulk.cuh): n fresh trees, no flags, depth >= 4 ------------------------------
 // candidate blocks (of 512) from which a unit is built by one warp instead of going through the level lists
+// 512 = only units whose every block is a candidate: those are the ones that can be solid or repeat an earlier unit
+// (the busy-unit loop's two shortcuts).  A partly filled unit is built faster by the level lists — thread per candidate,
+// 32 parents per warp step against 4 in the warp-per-unit loop: the surface-and-below terrain 0.903 ms at 128,
+// 0.852 at 256, 0.794 at 384, 0.698 at 512; the surface-only headline does not move (profiles/README.md).
 u32 bulk_dense_min() {
     if (const char* e = getenv("VX_BULK_DENSE_MIN")) return u32(std::max(1, atoi(e)));
-    return 128;
+    return 512;
 }
 // entries of sparse level l: a unit only enters the lists with fewer than dense_min candidate blocks
 size_t bulk_level_entries(size_t nb, int l) {
