@@ -303,3 +303,30 @@ def test_reset_of_used_state_only_is_a_full_reset(gpu_api, oracle_api, dtype):
     m, v = wl.batch_from_function(5, wl.p_uniform(3), dtype, 1)
     r, ch = small.apply_batches_slab(5, m, v)
     assert ch[0] == 1 and vx.id_is_leaf(r[0]) and small.stats()["alive_nodes"] == 2
+
+
+@pytest.mark.parametrize("depth,dtype", [(6, wl.U8), (6, wl.I32), (7, wl.U8)], ids=["d6-u8", "d6-i32", "d7-u8"])
+def test_single_batch_apply_on_big_trees(gpu_api, depth, dtype):
+    """vx_tree_apply_batch on one handle (apply_one_in_place, vx_capi.cu): a D = 6 u8 batch crosses the bus as one copy,
+    a D = 6 i32 batch and a D = 7 batch are read in place from the pinned arena (D = 7: by the bulk builder's plan
+    kernel, 32-byte vector loads over the bus).  Fresh build, an edit on top of it, a fill, every voxel checked."""
+    vx = gpu_api
+    rng = np.random.default_rng(depth * 10 + dtype)
+    it = vx.VoxInterner.with_memory_budget(1 << 30, dtype)
+    t = vx.VoxTree(depth, dtype)
+    n = 1 << depth
+    dense = np.zeros((n, n, n), wl.NP_DTYPE[dtype])
+    for step, density in enumerate((0.3, 0.02)):
+        masks, values = random_edit(rng, depth, dtype, density, np.array([1, 2, 3, 7]), uniform_blocks=0.3)
+        b = t.create_batch()
+        if step == 0:
+            b.assign(masks, values)            # API-written batch (journal / occupancy kept)
+        else:
+            set_batch_arrays(b, masks, values)  # raw arrays
+        assert t.apply_batch(it, b)
+        dense = overlay(dense, masks, values, depth)
+        assert np.array_equal(t.to_vec(it), dense)
+    b = t.create_batch()
+    b.fill(it, 9)
+    assert t.apply_batch(it, b) and t.is_leaf()
+    assert (t.to_vec(it) == 9).all()
